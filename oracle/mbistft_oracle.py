@@ -1,0 +1,275 @@
+"""CPU oracle for the MB-iSTFT-VITS waveform hot path (flow reverse + iSTFT decoders).
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``mb_istft_vits_b200/`` may import this
+module; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU
+baseline / ``--impl reference`` legs use it, and there only as the checker (or
+as the CPU arm being timed), never as the thing shipped.
+
+It is a functional restatement (plain ``torch`` fp32 on the CPU, no nn.Module,
+no reference code) of the algorithm in the reference files cited per function.
+The arithmetic primitives live in PyTorch (``F.conv1d``, ``F.conv_transpose1d``,
+``torch.istft``), exactly as in the reference: the reference pins
+no torch version; this image ships torch 2.11.0+cu128.
+
+Parity pin: the reference ships no golden vectors or tests for this path
+(SURVEY.md section 4), so the pin is "outputs of the reference itself run here":
+``tools/make_golden.py`` imports the unmodified reference modules from
+/root/reference in the build container, runs them on seeded weights/inputs and
+commits the results under ``tests/golden/``; ``tests/test_oracle_golden.py``
+checks this oracle against every one of those vectors.
+
+Weights are consumed in the reference checkpoint layout (``utils.py:57-60``
+'model' state-dict): ``dec.*`` / ``flow.*`` keys, weight-normed convs stored as
+``weight_g`` / ``weight_v`` (plain ``weight`` is accepted too).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+LRELU_SLOPE = 0.1  # modules.py:17
+
+
+# ----------------------------------------------------------------------------
+# weights
+# ----------------------------------------------------------------------------
+def effective_weight(sd: Dict[str, torch.Tensor], prefix: str) -> torch.Tensor:
+    """torch.nn.utils.weight_norm(dim=0) fold: w = g * v / ||v|| with the norm over
+    every dim but 0 (models.py:257,262,336 / modules.py:128-146,191-206).
+    For ConvTranspose1d dim 0 is the *input* channel."""
+    if prefix + ".weight" in sd:
+        return sd[prefix + ".weight"].float()
+    v = sd[prefix + ".weight_v"].float()
+    g = sd[prefix + ".weight_g"].float()
+    norm = v.reshape(v.shape[0], -1).norm(dim=1).reshape(g.shape)
+    return v * (g / norm)
+
+
+def _bias(sd, prefix):
+    b = sd.get(prefix + ".bias")
+    return None if b is None else b.float()
+
+
+def _conv_same(x, sd, prefix, dilation=1):
+    """Conv1d, stride 1, zero 'same' padding d*(K-1)/2 (commons.py:14-15)."""
+    w = effective_weight(sd, prefix)
+    k = w.shape[-1]
+    return F.conv1d(x, w, _bias(sd, prefix), padding=(k * dilation - dilation) // 2, dilation=dilation)
+
+
+# ----------------------------------------------------------------------------
+# flow reverse: models.py:207-214, modules.py:148-176, 280-287, 334-353
+# ----------------------------------------------------------------------------
+def wn_forward(x, x_mask, sd, prefix, hidden, n_layers=4, kernel_size=5, dilation_rate=1, g=None):
+    """modules.WN.forward (modules.py:148-176) with the gate of commons.py:100-107."""
+    out = torch.zeros_like(x)
+    if g is not None:
+        g = F.conv1d(g, effective_weight(sd, prefix + ".cond_layer"), _bias(sd, prefix + ".cond_layer"))
+    for i in range(n_layers):
+        x_in = _conv_same(x, sd, f"{prefix}.in_layers.{i}", dilation=dilation_rate ** i)
+        if g is not None:
+            x_in = x_in + g[:, 2 * hidden * i: 2 * hidden * (i + 1), :]
+        acts = torch.tanh(x_in[:, :hidden]) * torch.sigmoid(x_in[:, hidden:])
+        rs = _conv_same(acts, sd, f"{prefix}.res_skip_layers.{i}")
+        if i < n_layers - 1:
+            x = (x + rs[:, :hidden]) * x_mask
+            out = out + rs[:, hidden:]
+        else:
+            out = out + rs
+    return out * x_mask
+
+
+def coupling_reverse(x, x_mask, sd, prefix, hidden, g=None):
+    """modules.ResidualCouplingLayer.forward(reverse=True), mean_only (modules.py:334-353)."""
+    half = x.shape[1] // 2
+    x0, x1 = x[:, :half], x[:, half:]
+    h = F.conv1d(x0, sd[prefix + ".pre.weight"].float(), sd[prefix + ".pre.bias"].float()) * x_mask
+    h = wn_forward(h, x_mask, sd, prefix + ".enc", hidden, g=g)
+    m = F.conv1d(h, sd[prefix + ".post.weight"].float(), sd[prefix + ".post.bias"].float()) * x_mask
+    x1 = (x1 - m) * x_mask  # logs == 0 for mean_only
+    return torch.cat([x0, x1], 1)
+
+
+def flow_reverse(sd, cfg, z_p, y_mask, g=None, prefix="flow"):
+    """ResidualCouplingBlock.forward(reverse=True) (models.py:207-214): for flow in
+    reversed(flows): Flip, RCL3, Flip, RCL2, ... (Flip = channel reversal, modules.py:280-287)."""
+    hidden = cfg["hidden_channels"]
+    x = z_p.float()
+    for i in reversed(range(4)):
+        x = torch.flip(x, [1])
+        x = coupling_reverse(x, y_mask, sd, f"{prefix}.flows.{2 * i}", hidden, g=g)
+    return x
+
+
+# ----------------------------------------------------------------------------
+# decoder body: models.py:278-293 / 344-365 / 430-453, modules.py:213-228, 251-262
+# ----------------------------------------------------------------------------
+def resblock(x, sd, prefix, kind, k, dils, g=None):
+    if g is not None and (prefix + ".cond.weight") in sd:
+        x = x + F.conv1d(g, sd[prefix + ".cond.weight"].float(), sd[prefix + ".cond.bias"].float())
+    if kind == "1":  # modules.py:216-225
+        for p, d in enumerate(dils):
+            xt = F.leaky_relu(x, LRELU_SLOPE)
+            xt = _conv_same(xt, sd, f"{prefix}.convs1.{p}", dilation=d)
+            xt = F.leaky_relu(xt, LRELU_SLOPE)
+            xt = _conv_same(xt, sd, f"{prefix}.convs2.{p}")
+            x = xt + x
+    else:  # modules.py:254-259
+        for p, d in enumerate(dils):
+            xt = F.leaky_relu(x, LRELU_SLOPE)
+            xt = _conv_same(xt, sd, f"{prefix}.convs.{p}", dilation=d)
+            x = xt + x
+    return x
+
+
+def decoder_logits(sd, cfg, z, g=None, prefix="dec"):
+    """conv_pre .. conv_post: returns the pre-head logits [B, S*(n_fft+2), F] (F = L+1)."""
+    x = _conv_same(z.float(), sd, prefix + ".conv_pre")
+    nk = len(cfg["resblock_kernel_sizes"])
+    for i, (u, k) in enumerate(zip(cfg["upsample_rates"], cfg["upsample_kernel_sizes"])):
+        x = F.leaky_relu(x, LRELU_SLOPE)
+        x = F.conv_transpose1d(x, effective_weight(sd, f"{prefix}.ups.{i}"), _bias(sd, f"{prefix}.ups.{i}"),
+                               stride=u, padding=(k - u) // 2)
+        xs = None
+        for j in range(nk):
+            y = resblock(x, sd, f"{prefix}.resblocks.{i * nk + j}", cfg["resblock"],
+                         cfg["resblock_kernel_sizes"][j], cfg["resblock_dilation_sizes"][j], g=g)
+            xs = y if xs is None else xs + y
+        x = xs / nk
+    x = F.leaky_relu(x)  # default slope 0.01 (models.py:291/363/451)
+    x = F.pad(x, (1, 0), mode="reflect")  # ReflectionPad1d((1,0))
+    post = ".conv_post" if cfg["variant"] == "istft" else ".subband_conv_post"
+    return _conv_same(x, sd, prefix + post)
+
+
+# ----------------------------------------------------------------------------
+# head + iSTFT + sub-band synthesis: models.py:294-297 / 366-377 / 454-467
+# ----------------------------------------------------------------------------
+def hann_periodic(n):
+    """scipy.signal.get_window('hann', n, fftbins=True) (stft.py:187), float32."""
+    return (0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(n) / n)).astype(np.float32)
+
+
+def istft_torch(mag, phase, n_fft, hop):
+    """TorchSTFT.inverse (stft.py:197-202): torch.istft(mag * exp(j*phase))."""
+    win = torch.from_numpy(hann_periodic(n_fft))
+    return torch.istft(mag * torch.exp(phase * 1j), n_fft, hop, n_fft, window=win)
+
+
+def istft_closed_form(mag, phase, n_fft, hop):
+    """Same transform written out: real inverse DFT per frame (imaginary part of the
+    DC and Nyquist bins ignored), periodic Hann, overlap-add, trim n_fft/2, divide by the
+    window-square envelope.  Used to validate the in-register DFT of the CUDA tail kernel."""
+    nb, nbins, nfr = mag.shape
+    assert nbins == n_fft // 2 + 1
+    n = torch.arange(n_fft, dtype=torch.float64)
+    k = torch.arange(nbins, dtype=torch.float64)
+    ck = torch.full((nbins,), 2.0, dtype=torch.float64)
+    ck[0] = 1.0
+    ck[-1] = 1.0
+    ang = 2.0 * math.pi * k[:, None] * n[None, :] / n_fft
+    cosb = (ck[:, None] * torch.cos(ang) / n_fft)
+    sinb = (ck[:, None] * torch.sin(ang) / n_fft)
+    sinb[0] = 0.0
+    sinb[-1] = 0.0
+    re = (mag * torch.cos(phase)).double()
+    im = (mag * torch.sin(phase)).double()
+    fr = torch.einsum("bkf,kn->bfn", re, cosb) - torch.einsum("bkf,kn->bfn", im, sinb)
+    w = torch.from_numpy(hann_periodic(n_fft)).double()
+    fr = fr * w
+    total = n_fft + hop * (nfr - 1)
+    ola = torch.zeros(nb, total, dtype=torch.float64)
+    env = torch.zeros(total, dtype=torch.float64)
+    for f in range(nfr):
+        ola[:, f * hop: f * hop + n_fft] += fr[:, f]
+        env[f * hop: f * hop + n_fft] += w * w
+    half = n_fft // 2
+    y = ola[:, half: total - half] / env[half: total - half]
+    return y.float()
+
+
+def pqmf_synthesis_filter(subbands=4, taps=62, cutoff_ratio=0.15, beta=9.0):
+    """pqmf.design_prototype_filter + the h_synthesis rows (pqmf.py:15-43, 64-79), float64."""
+    n = np.arange(taps + 1)
+    omega_c = np.pi * cutoff_ratio
+    with np.errstate(invalid="ignore", divide="ignore"):
+        h_i = np.sin(omega_c * (n - 0.5 * taps)) / (np.pi * (n - 0.5 * taps))
+    h_i[taps // 2] = cutoff_ratio
+    from scipy.signal.windows import kaiser
+    h = h_i * kaiser(taps + 1, beta)
+    hs = np.zeros((subbands, taps + 1))
+    for k in range(subbands):
+        hs[k] = 2 * h * np.cos((2 * k + 1) * (np.pi / (2 * subbands)) * (n - (taps - 1) / 2)
+                               - (-1) ** k * np.pi / 4)
+    return hs
+
+
+def zero_stuff(y_mb, subbands):
+    """F.conv_transpose1d(x, updown_filter * subbands, stride=subbands) (pqmf.py:115, models.py:463)."""
+    filt = torch.zeros(subbands, subbands, subbands)
+    for k in range(subbands):
+        filt[k, k, 0] = 1.0
+    return F.conv_transpose1d(y_mb, filt * subbands, stride=subbands)
+
+
+def pqmf_synthesis(y_mb, subbands=4):
+    """PQMF.synthesis (pqmf.py:105-116)."""
+    hs = torch.from_numpy(pqmf_synthesis_filter(subbands)).float().unsqueeze(0)  # [1,S,63]
+    up = zero_stuff(y_mb, subbands)
+    return F.conv1d(F.pad(up, (31, 31)), hs)
+
+
+def decoder_tail(sd, cfg, logits, prefix="dec", closed_form=False):
+    """exp / pi*sin head, iSTFT, sub-band synthesis.  Returns (o, o_mb, spec, phase)."""
+    n_fft, hop = cfg["gen_istft_n_fft"], cfg["gen_istft_hop_size"]
+    nb = n_fft // 2 + 1
+    istft = istft_closed_form if closed_form else istft_torch
+    B, _, Fr = logits.shape
+    if cfg["variant"] == "istft":
+        spec = torch.exp(logits[:, :nb])
+        phase = math.pi * torch.sin(logits[:, nb:])
+        out = istft(spec, phase, n_fft, hop).unsqueeze(-2)
+        return out, None, spec, phase
+    S = cfg["subbands"]
+    x = logits.reshape(B, S, 2 * nb, Fr)
+    spec = torch.exp(x[:, :, :nb])
+    phase = math.pi * torch.sin(x[:, :, nb:])
+    y_mb = istft(spec.reshape(B * S, nb, Fr), phase.reshape(B * S, nb, Fr), n_fft, hop)
+    y_mb = y_mb.reshape(B, S, -1)
+    if cfg["variant"] == "mb":
+        return pqmf_synthesis(y_mb, S), y_mb, spec, phase
+    up = zero_stuff(y_mb, S)  # models.py:463
+    w = effective_weight(sd, prefix + ".multistream_conv_post")  # [1,4,63], no bias (models.py:425)
+    return F.conv1d(up, w, None, padding=31), up, spec, phase
+
+
+def decode(sd, cfg, z, g=None, prefix="dec", closed_form=False):
+    """{iSTFT,Multiband_iSTFT,Multistream_iSTFT}_Generator.forward (models.py:278-297/344-377/430-467)."""
+    with torch.no_grad():
+        return decoder_tail(sd, cfg, decoder_logits(sd, cfg, z, g, prefix), prefix, closed_form)
+
+
+def flow_decode(sd, cfg, z_p, y_mask, g=None):
+    """The tail of SynthesizerTrn.infer (models.py:730-734): z = flow(z_p, y_mask, g, reverse=True);
+    dec(z * y_mask, g)."""
+    with torch.no_grad():
+        z = flow_reverse(sd, cfg, z_p, y_mask, g)
+        return z, decode(sd, cfg, z * y_mask, g)
+
+
+# ----------------------------------------------------------------------------
+# comparators used by the parity tests (tolerances from BASELINE.json north_star)
+# ----------------------------------------------------------------------------
+def max_abs_over_peak(test, ref):
+    ref = ref.double()
+    return float((test.double() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+
+def snr_db(test, ref):
+    ref = ref.double()
+    err = (test.double() - ref).pow(2).sum().clamp_min(1e-300)
+    return float(10.0 * torch.log10(ref.pow(2).sum() / err))

@@ -1,0 +1,139 @@
+#!/usr/bin/env python
+"""Mint golden vectors by running the UNMODIFIED reference modules (build container only).
+
+The reference ships no tests or golden vectors for this path, so the parity pin
+is "outputs of the reference itself run here".  This script imports models.py from /root/reference
+with the three import shims of SURVEY.md section 8c (none of which touches the arithmetic), loads the seeded
+state-dict of ``mb_istft_vits_b200.synth`` into the real ``SynthesizerTrn`` with strict key/shape
+checks on ``dec.*`` / ``flow.*`` / ``emb_g.*``, runs
+
+    z = net_g.flow(z_p, y_mask, g=g, reverse=True)          (models.py:730)
+    o, o_mb, spec, phase = net_g.dec(z * y_mask, g=g)       (models.py:734)
+
+on CPU fp32 and writes ``tests/golden/<case>.npz``.  /root/reference does not exist on the GPU box,
+so nothing at test/bench time imports this file.
+
+    python tools/make_golden.py            # regenerate every case
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+from mb_istft_vits_b200 import configs as cfgs  # noqa: E402
+from mb_istft_vits_b200 import synth  # noqa: E402
+
+CASES = [
+    # name, config, overrides, B, T, lengths, g_scale
+    ("mini_mb", "ljs_mini_mb_istft_vits", {}, 2, 20, [20, 13], 1.0),
+    ("mb", "ljs_mb_istft_vits", {}, 2, 20, [20, 13], 1.0),
+    ("mb_gscale", "ljs_mb_istft_vits", {}, 1, 24, [24], 1.7),
+    ("ms", "ljs_ms_istft_vits", {}, 2, 20, [20, 11], 1.0),
+    ("istft", "ljs_istft_vits", {}, 2, 12, [12, 7], 1.0),
+    ("mini_istft", "ljs_mini_istft_vits", {}, 1, 12, [12], 1.0),
+    ("uudb_spk8", "uudb_spk8_istft_vits", {}, 1, 20, [20], 1.0),
+    ("ms_spk", "uudb_ms_istft_vits_ms", {}, 3, 20, [20, 9, 15], 1.0),
+    ("mb_resblock2", "ljs_mb_istft_vits",
+     {"resblock": "2", "resblock_dilation_sizes": [[1, 3], [1, 3], [1, 3]]}, 1, 20, [20], 1.0),
+    ("mb_long", "ljs_mini_mb_istft_vits", {}, 1, 150, [150], 1.0),
+]
+
+
+def import_reference():
+    """Shims: stub the unbuilt Cython module (models.py:11), stub librosa (stft.py:32-33, unused by
+    TorchSTFT), and let Tensor.cuda(cpu_device) be a no-op (pqmf.py:78,79,86)."""
+    ma = types.ModuleType("monotonic_align")
+    ma.maximum_path = None
+    sys.modules["monotonic_align"] = ma
+    lib, libu = types.ModuleType("librosa"), types.ModuleType("librosa.util")
+    libu.pad_center = lambda d, size, axis=-1, **k: d
+    libu.tiny = lambda x: np.finfo(np.float32).tiny
+    libu.normalize = lambda S, norm=None, **k: S
+    lib.util = libu
+    sys.modules["librosa"] = lib
+    sys.modules["librosa.util"] = libu
+    _cuda = torch.Tensor.cuda
+
+    def cuda(self, device=None, *a, **k):
+        if device is not None and torch.device(device).type == "cpu":
+            return self
+        return _cuda(self, device, *a, **k)
+    torch.Tensor.cuda = cuda
+    sys.path.insert(0, REF)
+    import models  # noqa
+    return models
+
+
+def build_reference(models, cfg, sd):
+    kw = dict(
+        inter_channels=cfg["inter_channels"], hidden_channels=cfg["hidden_channels"],
+        filter_channels=768 if cfg["hidden_channels"] == 192 else 384, n_heads=2, n_layers=3 if cfg["hidden_channels"] == 96 else 6,
+        kernel_size=3, p_dropout=0.1, resblock=cfg["resblock"],
+        resblock_kernel_sizes=cfg["resblock_kernel_sizes"],
+        resblock_dilation_sizes=cfg["resblock_dilation_sizes"],
+        upsample_rates=cfg["upsample_rates"], upsample_initial_channel=cfg["upsample_initial_channel"],
+        upsample_kernel_sizes=cfg["upsample_kernel_sizes"],
+        gen_istft_n_fft=cfg["gen_istft_n_fft"], gen_istft_hop_size=cfg["gen_istft_hop_size"],
+        n_speakers=cfg["n_speakers"], gin_channels=cfg["gin_channels"], use_sdp=False,
+        ms_istft_vits=cfg["variant"] == "ms", mb_istft_vits=cfg["variant"] == "mb",
+        istft_vits=cfg["variant"] == "istft",
+        subbands=cfg["subbands"] if cfg["variant"] != "istft" else False,
+    )
+    net = models.SynthesizerTrn(59, 513, 32, **kw).eval()
+    ref_sd = net.state_dict()
+    want = {k for k in ref_sd if k.startswith(("dec.", "flow.", "emb_g."))}
+    have = set(sd.keys())
+    assert want == have, f"key inventory mismatch: missing {sorted(want - have)[:5]} extra {sorted(have - want)[:5]}"
+    for k in want:
+        assert tuple(ref_sd[k].shape) == tuple(sd[k].shape), (k, ref_sd[k].shape, sd[k].shape)
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected
+    return net
+
+
+def main():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mbistft_oracle as orc
+    models = import_reference()
+    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    for name, cname, over, B, T, lengths, g_scale in CASES:
+        cfg = cfgs.get_config(cname)
+        cfg.update(over)
+        sd = synth.make_state_dict(cfg, seed=1234, g_scale=g_scale)
+        net = build_reference(models, cfg, sd)
+        z_p, mask, lens = synth.make_latents(cfg, B, T, seed=4321, lengths=lengths)
+        g = None
+        sid = None
+        if cfg["gin_channels"]:
+            sid = torch.arange(B) % cfg["n_speakers"]
+            g = net.emb_g(sid).unsqueeze(-1).detach()
+        with torch.no_grad():
+            z = net.flow(z_p, mask, g=g, reverse=True)
+            o, o_mb, spec, phase = net.dec(z * mask, g=g)
+        # cross-check the oracle right here
+        zo, (oo, oo_mb, ospec, ophase) = orc.flow_decode(sd, cfg, z_p, mask, g)
+        print(f"{name:14s} wav peak {o.abs().max():.4f}  oracle-vs-ref: z {(zo - z).abs().max():.2e} "
+              f"wav {orc.max_abs_over_peak(oo, o):.2e} spec {orc.max_abs_over_peak(ospec, spec):.2e} "
+              f"phase {(ophase - phase).abs().max():.2e}")
+        out = dict(z_p=z_p.numpy(), mask=mask.numpy(), z=z.numpy(), o=o.numpy(),
+                   spec=spec.numpy(), phase=phase.numpy(),
+                   meta=np.array([B, T, 1234, 4321], dtype=np.int64), g_scale=np.float32(g_scale),
+                   lengths=np.array(lengths, dtype=np.int64))
+        if o_mb is not None:
+            out["o_mb"] = o_mb.numpy()
+        if g is not None:
+            out["g"] = g.numpy()
+            out["sid"] = sid.numpy()
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
+
+
+if __name__ == "__main__":
+    main()
