@@ -1,0 +1,150 @@
+/*
+ * mbistft.h -- C ABI of libmbistft.so: B200 (sm_100a) flow-reverse + iSTFT waveform decoders.
+ *
+ * This is the drop-in boundary for the reference's waveform hot path.  The reference has no plugin /
+ * operator registry; the seam is two nn.Module attributes of SynthesizerTrn (models.py:634-647):
+ *
+ *     z = self.flow(z_p, y_mask, g=g, reverse=True)                   models.py:730
+ *     o, o_mb, spec, phase = self.dec((z*y_mask)[:,:,:max_len], g=g)  models.py:734
+ *
+ * The Python shims in mb_istft_vits_b200/modules.py (NativeFlow / NativeDecoder) are assigned onto
+ * those attributes and call the entry points below through ctypes.  Conventions:
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - every call returns 0 on success, a negative mbv_status otherwise; mbv_last_error() gives text.
+ *   - the caller owns every activation / output / workspace buffer (device memory); the library owns
+ *     only its packed weight copy.  No allocation and no host synchronisation on the call path; all
+ *     work is enqueued on the caller's stream (CUDA-graph capturable).
+ *   - tensors at the boundary are fp32, contiguous, NCT (time contiguous), like the reference.
+ *   - there is no CPU fallback: every compute entry fails with MBV_ERR_CUDA without a B200.
+ */
+#ifndef MBISTFT_H_
+#define MBISTFT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBV_ABI_VERSION 1
+
+typedef enum {
+  MBV_OK = 0,
+  MBV_ERR_INVALID = -1,      /* bad argument / inconsistent sizes */
+  MBV_ERR_UNSUPPORTED = -2,  /* geometry outside what the kernels implement (never a silent fallback) */
+  MBV_ERR_WEIGHTS = -3,      /* missing / mis-shaped tensor in mbv_load_weights */
+  MBV_ERR_WORKSPACE = -4,    /* workspace too small or misaligned */
+  MBV_ERR_CUDA = -5          /* CUDA runtime / driver error (message has the detail) */
+} mbv_status;
+
+/* decoder family: models.py:248 iSTFT_Generator, :309 Multiband_iSTFT_Generator,
+ * :387 Multistream_iSTFT_Generator (selected by the three booleans at models.py:634-644) */
+typedef enum { MBV_VARIANT_ISTFT = 0, MBV_VARIANT_MB = 1, MBV_VARIANT_MS = 2 } mbv_variant;
+
+/* arithmetic of the dense contractions (residual stream, head, iSTFT, PQMF are always fp32) */
+typedef enum {
+  MBV_PREC_FP32 = 0, /* CUDA-core fp32 FMA: exact-order-independent reference path, slow */
+  MBV_PREC_TF32 = 1, /* tcgen05 kind::tf32, operands rounded to tf32 (RNE), fp32 accumulate */
+  MBV_PREC_BF16 = 2  /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate */
+} mbv_precision;
+
+#define MBV_MAX_UPS 4
+#define MBV_MAX_KERNELS 4
+#define MBV_MAX_DILATIONS 3
+
+/* Mirrors the `model` section of the reference configs (configs/ljs_mb_istft_vits.json:39-62) */
+typedef struct {
+  int32_t variant;                  /* mbv_variant */
+  int32_t precision;                /* mbv_precision */
+  int32_t inter_channels;           /* 192: latent channels (flow channels, decoder input) */
+  int32_t hidden_channels;          /* flow WN width (192; 96 in the mini configs) */
+  int32_t upsample_initial_channel; /* 512 / 256 */
+  int32_t n_ups;
+  int32_t upsample_rates[MBV_MAX_UPS];
+  int32_t upsample_kernel_sizes[MBV_MAX_UPS];
+  int32_t resblock_type;            /* 1 = ResBlock1 (modules.py:187), 2 = ResBlock2 (modules.py:237) */
+  int32_t n_kernels;
+  int32_t resblock_kernel_sizes[MBV_MAX_KERNELS];
+  int32_t n_dilations;              /* 3 for ResBlock1, 2 for ResBlock2 */
+  int32_t resblock_dilations[MBV_MAX_KERNELS][MBV_MAX_DILATIONS];
+  int32_t n_fft;                    /* gen_istft_n_fft = 16 */
+  int32_t hop;                      /* gen_istft_hop_size = 4 */
+  int32_t subbands;                 /* 4 (MB/MS), 1 (iSTFT) */
+  int32_t gin_channels;             /* 0 = no speaker conditioning */
+  int32_t flow_kernel;              /* 5   } hard-coded at models.py:647 */
+  int32_t flow_dilation_rate;       /* 1   } */
+  int32_t flow_layers;              /* 4   } */
+  int32_t flow_n;                   /* 4   } */
+  int32_t device;                   /* CUDA device ordinal */
+  int32_t flags;                    /* MBV_FLAG_* */
+} mbv_config;
+
+/* debug / tuning flags */
+#define MBV_FLAG_TC_PER_TAP_LOADS 1 /* tcgen05 conv: one TMA load per tap instead of a halo slab */
+#define MBV_FLAG_TC_BASE_OFFSET 2   /* tcgen05 conv: set the descriptor base_offset for unaligned tap rows */
+
+/* An EFFECTIVE weight tensor (weight-norm already folded: w = g*v/||v||), fp32, contiguous,
+ * in HOST memory, named as in the reference state-dict minus weight_g/weight_v, e.g.
+ * "dec.conv_pre.weight" [512,192,7], "dec.ups.0.weight" [C_in,C_out,16], "flow.flows.0.pre.bias". */
+typedef struct {
+  const char* name;
+  const float* data;
+  int32_t rank;
+  int64_t shape[4];
+} mbv_tensor;
+
+typedef struct mbv_handle mbv_handle;
+
+int mbv_abi_version(void);
+
+/* Validate the geometry and create a handle bound to cfg->device. */
+int mbv_create(const mbv_config* cfg, mbv_handle** out);
+void mbv_destroy(mbv_handle* h);
+
+/* Pack (transpose to tap-major/K-major, pad, fold the four Flips into pre/post, round to the
+ * operand type) and upload all weights.  Must be called once before any compute call; every tensor
+ * the configuration needs must be present. */
+int mbv_load_weights(mbv_handle* h, const mbv_tensor* tensors, int32_t n);
+
+/* Scratch the caller must provide for a batch of B utterances padded to T latent frames. */
+int mbv_workspace_bytes(mbv_handle* h, int32_t B, int32_t T, size_t* bytes);
+
+/* ResidualCouplingBlock.forward(x, x_mask, g, reverse=True)  (models.py:207-214).
+ * z_p, z_out: [B, inter, T];  y_mask: [B, 1, T];  g: [B, gin, 1] or NULL.  z_out may alias z_p. */
+int mbv_flow_reverse(mbv_handle* h, const float* z_p, const float* y_mask, const float* g,
+                     float* z_out, int32_t B, int32_t T, void* ws, size_t ws_bytes, void* stream);
+
+/* dec.forward(z, g) (models.py:278-297 / 344-377 / 430-467).  z: [B, inter, T]; wav: [B,1,S*T]
+ * with S = samples per latent frame (256).  Optional outputs (NULL to skip):
+ *   o_mb : MB [B,4,64T];  MS [B,4,256T] (the zero-stuffed tensor the reference returns); iSTFT: must be NULL
+ *   spec, phase : [B,4,9,16T+1] (MB/MS) or [B,9,64T+1] (iSTFT)
+ * z_mask (optional, [B,1,T]) is multiplied into z on load, fusing the `z * y_mask` of models.py:734. */
+int mbv_decode(mbv_handle* h, const float* z, const float* z_mask, const float* g, float* wav,
+               float* o_mb, float* spec, float* phase, int32_t B, int32_t T, void* ws,
+               size_t ws_bytes, void* stream);
+
+/* The tail of SynthesizerTrn.infer in one call (models.py:730-734): flow reverse, mask, decode.
+ * z_out (optional) receives the flow output like the reference's returned z. */
+int mbv_flow_decode(mbv_handle* h, const float* z_p, const float* y_mask, const float* g,
+                    float* z_out, float* wav, float* o_mb, float* spec, float* phase, int32_t B,
+                    int32_t T, void* ws, size_t ws_bytes, void* stream);
+
+/* Introspection for benchmarks: number of kernel launches the last compute call enqueued, and the
+ * algorithmic FLOPs (2*MACs of the dense contractions) of a decode / flow call at (B,T). */
+int mbv_last_launch_count(mbv_handle* h);
+double mbv_decode_flops(mbv_handle* h, int32_t B, int32_t T);
+double mbv_flow_flops(mbv_handle* h, int32_t B, int32_t T);
+
+/* Stand-alone entry for the fused tail (head + iSTFT + sub-band synthesis) on caller-provided
+ * logits [B, F, n_logit_channels] (channels-last, F = frames): used by the parity tests and the
+ * HBM-roofline benchmark of that kernel. */
+int mbv_tail(mbv_handle* h, const float* logits, float* wav, float* o_mb, float* spec, float* phase,
+             int32_t B, int32_t T, void* stream);
+
+const char* mbv_last_error(mbv_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBISTFT_H_ */

@@ -1,0 +1,55 @@
+// kernels.h -- host-callable launchers of the CUDA kernels (internal to libmbistft.so).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "common.cuh"
+
+namespace mbv {
+
+// ---- conv_simt.cu
+cudaError_t launch_conv_simt(int prec, const ConvArgs& a, cudaStream_t st);
+
+// ---- conv_tc.cu
+struct TcPlan {
+  CUtensorMap tmA;      // 3-D (Cp_in, L_in, B), box (KB, slab_rows, 1), 128B swizzle
+  CUtensorMap tmB;      // 2-D (Cp_in, phases*taps*N_total), box (KB, box_n), 128B swizzle
+  int slab_rows;        // rows of the A box: 128 + (taps-1)*dil, or 128 with per-tap loads
+  int a_stage_bytes;
+  int b_stage_bytes;    // includes the per-tap A tile when per_tap
+  int n_a_stages;
+  int n_b_stages;
+  int per_tap;
+  int base_offset_mode;
+  int m_tiles, n_tiles, total_tiles;
+  int tmem_cols;
+  int smem_bytes;
+  int grid;
+};
+// Fills plan (tensor maps, staging, grid) for args; returns a message on failure, nullptr on success.
+const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, TcPlan* plan);
+cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& plan, cudaStream_t st);
+cudaError_t tc_set_attributes();
+
+// ---- tail.cu
+struct TailArgs {
+  const float* logits;  // [B][F][n_ch] channels-last, F = L + 1 frames
+  float* wav;           // [B][1][subbands*4*L]  (iSTFT: [B][1][4L])
+  float* o_mb;          // MB: [B][S][4L]; MS: [B][S][16L] zero-stuffed; or null
+  float* spec;          // [B][S][9][F] or null
+  float* phase;
+  int B, L, n_ch, variant;
+  float coef[4][64];    // synthesis FIR h[c][k] (PQMF or the trainable multistream_conv_post), gain folded
+};
+cudaError_t launch_tail(const TailArgs& a, int precise, cudaStream_t st);
+
+// ---- misc.cu
+// fp32 NCT [B][C][T] -> channels-last [B][T][Cp] operand (and optional fp32 copy), optional mask [B][T]
+cudaError_t launch_pack_input(int prec, const float* src, const float* mask, void* dst_op, float* dst_f32,
+                              int B, int C, int T, int Cp, cudaStream_t st);
+// fp32 channels-last [B][T][Cp] -> NCT [B][C][T]
+cudaError_t launch_unpack_output(const float* src, float* dst, int B, int C, int T, int Cp, cudaStream_t st);
+// out[b][n] = bias[n] + sum_c w[n][c] * g[b][c]  (+ base[n] if given); w is [N][G] fp32
+cudaError_t launch_cond_gemv(const float* g, const float* w, const float* bias, const float* base, float* out,
+                             int B, int G, int N, int out_ld, cudaStream_t st);
+
+}  // namespace mbv

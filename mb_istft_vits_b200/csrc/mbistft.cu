@@ -1,0 +1,953 @@
+// mbistft.cu -- the C ABI of include/mbistft.h: handle, weight packer, workspace planner and the launch
+// sequences for flow-reverse (models.py:207-214) and the three iSTFT decoders (models.py:248-474).
+//
+// Nothing here computes on the host: without a CUDA device every compute entry returns MBV_ERR_CUDA.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mbistft.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace mbv;
+
+#define MBV_FLAG_FORCE_SIMT 4  // debug: run the CUDA-core conv on the tensor-core operand layout
+
+namespace {
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---- host float -> operand conversions (RNE)
+inline uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline float f32_to_tf32(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return f;
+  u += 0xfffu + ((u >> 13) & 1u);
+  u &= 0xffffe000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+
+struct ConvLayer {
+  // geometry
+  int Cp_in = 0, N_total = 0, N_tile = 0, taps = 0, dil = 1, n_phases = 1, gate = 0;
+  int shift0[kMaxPhases] = {0};
+  int n_valid = 0;      // real output channels (unpadded)
+  double macs_per_row = 0;  // real MACs per computed row (all phases), for FLOP accounting
+  // device data
+  void* w = nullptr;    // packed operand weights [phase][tap][N_total][Cp_in]
+  float* bias = nullptr;  // [N_total] (gate: [tanh Hp | sigmoid Hp])
+};
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+}  // namespace
+
+struct mbv_handle {
+  mbv_config cfg;
+  int prec = 0;
+  int esize = 4;
+  int num_sms = 148;
+  bool weights_loaded = false;
+  std::string err;
+  int last_launches = 0;
+  std::vector<void*> dev_allocs;
+
+  // derived geometry
+  int Cz = 0;    // inter channels (192), must be a multiple of 64
+  int H = 0, Hp = 0;
+  int n_stage = 0;
+  int stage_C[MBV_MAX_UPS] = {0};
+  int n_logit = 0;  // subbands * 18
+  int spf = 0;      // samples per latent frame
+
+  // decoder layers
+  ConvLayer conv_pre, conv_post;
+  ConvLayer ups[MBV_MAX_UPS];
+  // resblocks[stage][kernel]: convs1[p], convs2[p] (type 1) or convs[p] in c1 (type 2)
+  ConvLayer rb_c1[MBV_MAX_UPS][MBV_MAX_KERNELS][MBV_MAX_DILATIONS];
+  ConvLayer rb_c2[MBV_MAX_UPS][MBV_MAX_KERNELS][MBV_MAX_DILATIONS];
+  float* rb_cond_w[MBV_MAX_UPS][MBV_MAX_KERNELS] = {{nullptr}};  // [C][gin]
+  float* rb_cond_b[MBV_MAX_UPS][MBV_MAX_KERNELS] = {{nullptr}};  // [C]
+  float tail_coef[4][64];
+
+  // flow layers, indexed by coupling layer 0..3 (reference order)
+  ConvLayer fl_pre[4], fl_post[4], fl_in[4][4], fl_rs[4][4];
+  float* fl_cond_w[4] = {nullptr};  // [L*2Hp][gin] packed (tanh | sigmoid per layer)
+  float* fl_cond_b[4] = {nullptr};  // [L*2Hp]
+
+  // tensor-map cache: valid while (B, T, ws) stay the same
+  struct PlanKey { int B, T; void* ws; int kind; bool operator<(const PlanKey& o) const {
+    if (B != o.B) return B < o.B; if (T != o.T) return T < o.T; if (ws != o.ws) return ws < o.ws; return kind < o.kind; } };
+  std::map<PlanKey, std::vector<TcPlan>> plan_cache;
+};
+
+namespace {
+
+int fail(mbv_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                          \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) return fail(h, MBV_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));  \
+  } while (0)
+
+int pick_tile(int n, int maxc) {
+  for (int c = maxc; c >= 16; c -= 16)
+    if (n % c == 0) return c;
+  return 0;
+}
+
+// upload packed weights (host fp32, layout [phase][tap][N_total][Cp_in]) in the operand type
+int upload_weights(mbv_handle* h, ConvLayer& L, const std::vector<float>& packed, const std::vector<float>& bias) {
+  const size_t n = packed.size();
+  void* d = nullptr;
+  if (h->prec == MBV_PREC_BF16) {
+    std::vector<uint16_t> tmp(n);
+    for (size_t i = 0; i < n; ++i) tmp[i] = f32_to_bf16(packed[i]);
+    CUDA_TRY(h, cudaMalloc(&d, n * 2));
+    CUDA_TRY(h, cudaMemcpy(d, tmp.data(), n * 2, cudaMemcpyHostToDevice));
+  } else {
+    std::vector<float> tmp(packed);
+    if (h->prec == MBV_PREC_TF32)
+      for (size_t i = 0; i < n; ++i) tmp[i] = f32_to_tf32(tmp[i]);
+    CUDA_TRY(h, cudaMalloc(&d, n * 4));
+    CUDA_TRY(h, cudaMemcpy(d, tmp.data(), n * 4, cudaMemcpyHostToDevice));
+  }
+  h->dev_allocs.push_back(d);
+  L.w = d;
+  float* db = nullptr;
+  CUDA_TRY(h, cudaMalloc(&db, bias.size() * 4));
+  CUDA_TRY(h, cudaMemcpy(db, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+  h->dev_allocs.push_back(db);
+  L.bias = db;
+  return MBV_OK;
+}
+
+int upload_f32(mbv_handle* h, const std::vector<float>& v, float** out) {
+  float* d = nullptr;
+  CUDA_TRY(h, cudaMalloc(&d, v.size() * 4));
+  CUDA_TRY(h, cudaMemcpy(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+  h->dev_allocs.push_back(d);
+  *out = d;
+  return MBV_OK;
+}
+
+typedef std::map<std::string, HostTensor> TensorMap;
+
+const HostTensor* find_tensor(mbv_handle* h, const TensorMap& m, const std::string& name, int rank, const int64_t* shape) {
+  auto it = m.find(name);
+  if (it == m.end()) {
+    fail(h, MBV_ERR_WEIGHTS, "missing tensor %s", name.c_str());
+    return nullptr;
+  }
+  const HostTensor& t = it->second;
+  bool ok = (int)t.shape.size() == rank;
+  for (int i = 0; ok && i < rank; ++i) ok = t.shape[i] == shape[i];
+  if (!ok) {
+    fail(h, MBV_ERR_WEIGHTS, "tensor %s has the wrong shape", name.c_str());
+    return nullptr;
+  }
+  return &t;
+}
+
+// Conv1d [O][I][K] 'same', dilation d  ->  taps K, shift0 = -d(K-1)/2.  Output rows may be permuted / padded:
+// out_map[n] = source output channel of packed row n (or -1 = zero row); in_map[c] = source input channel of
+// packed column c (or -1).
+int pack_conv1d(mbv_handle* h, const TensorMap& m, const std::string& prefix, int O, int I, int K, int dil,
+                const std::vector<int>& out_map, const std::vector<int>& in_map, bool has_bias, int gate, ConvLayer* L) {
+  const int64_t wshape[3] = {O, I, K};
+  const HostTensor* w = find_tensor(h, m, prefix + ".weight", 3, wshape);
+  if (!w) return MBV_ERR_WEIGHTS;
+  const HostTensor* b = nullptr;
+  if (has_bias) {
+    const int64_t bshape[1] = {O};
+    b = find_tensor(h, m, prefix + ".bias", 1, bshape);
+    if (!b) return MBV_ERR_WEIGHTS;
+  }
+  const int N = (int)out_map.size(), Cp = (int)in_map.size();
+  L->Cp_in = Cp; L->N_total = N; L->taps = K; L->dil = dil; L->n_phases = 1; L->gate = gate;
+  L->shift0[0] = -dil * (K - 1) / 2;
+  L->n_valid = O;
+  L->macs_per_row = (double)O * I * K;
+  if (gate) {
+    const int cl = pick_tile(N / 2, 128);
+    if (!cl) return fail(h, MBV_ERR_UNSUPPORTED, "%s: gate width %d not tileable", prefix.c_str(), N / 2);
+    L->N_tile = 2 * cl;
+  } else {
+    L->N_tile = pick_tile(N, 256);
+    if (!L->N_tile) return fail(h, MBV_ERR_UNSUPPORTED, "%s: output width %d not tileable", prefix.c_str(), N);
+  }
+  std::vector<float> packed((size_t)K * N * Cp, 0.f), bias(N, 0.f);
+  for (int k = 0; k < K; ++k)
+    for (int n = 0; n < N; ++n) {
+      const int o = out_map[n];
+      if (o < 0) continue;
+      float* dst = &packed[((size_t)k * N + n) * Cp];
+      for (int c = 0; c < Cp; ++c) {
+        const int i = in_map[c];
+        if (i >= 0) dst[c] = w->data[((size_t)o * I + i) * K + k];
+      }
+    }
+  if (b)
+    for (int n = 0; n < N; ++n)
+      if (out_map[n] >= 0) bias[n] = b->data[out_map[n]];
+  return upload_weights(h, *L, packed, bias);
+}
+
+std::vector<int> iota_pad(int n, int padded) {
+  std::vector<int> v(padded, -1);
+  for (int i = 0; i < n; ++i) v[i] = i;
+  return v;
+}
+
+// ConvTranspose1d [I][O][K], stride S, padding (K-S)/2 as S polyphase branches of K/S taps
+int pack_convT(mbv_handle* h, const TensorMap& m, const std::string& prefix, int I, int O, int K, int S, ConvLayer* L) {
+  const int64_t wshape[3] = {I, O, K};
+  const int64_t bshape[1] = {O};
+  const HostTensor* w = find_tensor(h, m, prefix + ".weight", 3, wshape);
+  const HostTensor* b = w ? find_tensor(h, m, prefix + ".bias", 1, bshape) : nullptr;
+  if (!w || !b) return MBV_ERR_WEIGHTS;
+  if (K % S != 0 || (K - S) % 2 != 0 || S > kMaxPhases)
+    return fail(h, MBV_ERR_UNSUPPORTED, "%s: upsampler kernel %d / stride %d not supported (need K %% S == 0, K-S even, S <= %d)",
+                prefix.c_str(), K, S, kMaxPhases);
+  const int P = (K - S) / 2, TP = K / S;
+  const int Cp = round_up(I, 64), N = round_up(O, 16);
+  L->Cp_in = Cp; L->N_total = N; L->taps = TP; L->dil = 1; L->n_phases = S; L->gate = 0;
+  L->n_valid = O;
+  L->macs_per_row = (double)I * O * K;  // per input row, all S phases together
+  L->N_tile = pick_tile(N, 256);
+  if (!L->N_tile) return fail(h, MBV_ERR_UNSUPPORTED, "%s: output width %d not tileable", prefix.c_str(), N);
+  std::vector<float> packed((size_t)S * TP * N * Cp, 0.f), bias(N, 0.f);
+  for (int r = 0; r < S; ++r) {
+    const int base = (r + P) / S, k0 = (r + P) % S;
+    L->shift0[r] = base - (TP - 1);
+    for (int j = 0; j < TP; ++j) {
+      const int k = k0 + S * (TP - 1 - j);  // tap j reads input row q + shift0 + j
+      for (int o = 0; o < O; ++o) {
+        float* dst = &packed[(((size_t)r * TP + j) * N + o) * Cp];
+        for (int i = 0; i < I; ++i) dst[i] = w->data[((size_t)i * O + o) * K + k];
+      }
+    }
+  }
+  for (int o = 0; o < O; ++o) bias[o] = b->data[o];
+  return upload_weights(h, *L, packed, bias);
+}
+
+// modified Bessel I0 (power series), for the Kaiser window of pqmf.py:40
+double bessel_i0(double x) {
+  double sum = 1.0, term = 1.0;
+  const double q = x * x / 4.0;
+  for (int k = 1; k < 200; ++k) {
+    term *= q / ((double)k * k);
+    sum += term;
+    if (term < 1e-20 * sum) break;
+  }
+  return sum;
+}
+
+// pqmf.py:15-43 + 64-79: 63-tap Kaiser(beta 9) prototype at cutoff 0.15, cosine-modulated synthesis bank (float64 -> float32)
+void design_pqmf_synthesis(float hs[4][63]) {
+  const int taps = 62;
+  const double cutoff = 0.15, beta = 9.0, pi = 3.14159265358979323846;
+  double proto[63];
+  for (int n = 0; n <= taps; ++n) {
+    const double x = n - 0.5 * taps;
+    const double hi = (n == taps / 2) ? cutoff : sin(pi * cutoff * x) / (pi * x);
+    const double r = 2.0 * n / taps - 1.0;
+    const double wk = bessel_i0(beta * sqrt(1.0 - r * r)) / bessel_i0(beta);
+    proto[n] = hi * wk;
+  }
+  for (int k = 0; k < 4; ++k)
+    for (int n = 0; n <= taps; ++n) {
+      const double v = 2.0 * proto[n] * cos((2 * k + 1) * (pi / 8.0) * (n - (taps - 1) / 2.0) - ((k & 1) ? -1.0 : 1.0) * pi / 4.0);
+      hs[k][n] = (float)v;
+    }
+}
+
+// polyphase table of the synthesis FIR: G[c][r*16 + (d+7)] = 4 * h[c][4d + 31 - r]  (tail.cu phase 3)
+void fill_tail_coef(mbv_handle* h, const float hs[4][63]) {
+  for (int c = 0; c < 4; ++c)
+    for (int r = 0; r < 4; ++r)
+      for (int d = -7; d <= 8; ++d) {
+        const int k = 4 * d + 31 - r;
+        h->tail_coef[c][r * 16 + d + 7] = (k >= 0 && k <= 62) ? 4.f * hs[c][k] : 0.f;
+      }
+}
+
+}  // namespace
+
+// =================================================================================================
+// ABI
+// =================================================================================================
+extern "C" int mbv_abi_version(void) { return MBV_ABI_VERSION; }
+
+extern "C" const char* mbv_last_error(mbv_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+extern "C" int mbv_create(const mbv_config* cfg, mbv_handle** out) {
+  if (!cfg || !out) return MBV_ERR_INVALID;
+  *out = nullptr;
+  mbv_handle* h = new mbv_handle();
+  h->cfg = *cfg;
+  *out = h;  // returned even on failure so the caller can read the message; destroy it either way
+  const mbv_config& c = h->cfg;
+  if (c.variant < 0 || c.variant > 2) return fail(h, MBV_ERR_INVALID, "variant must be 0 (istft), 1 (mb) or 2 (ms)");
+  if (c.precision < 0 || c.precision > 2) return fail(h, MBV_ERR_INVALID, "precision must be 0 (fp32), 1 (tf32) or 2 (bf16)");
+  h->prec = c.precision;
+  h->esize = c.precision == MBV_PREC_BF16 ? 2 : 4;
+  if (c.inter_channels <= 0 || c.inter_channels % 64 != 0 || (c.inter_channels / 2) % 16 != 0)
+    return fail(h, MBV_ERR_UNSUPPORTED, "inter_channels must be a multiple of 64 (got %d)", c.inter_channels);
+  if (c.hidden_channels <= 0 || c.hidden_channels % 16 != 0)
+    return fail(h, MBV_ERR_UNSUPPORTED, "hidden_channels must be a multiple of 16 (got %d)", c.hidden_channels);
+  if (c.n_ups < 1 || c.n_ups > MBV_MAX_UPS) return fail(h, MBV_ERR_UNSUPPORTED, "n_ups must be 1..%d", MBV_MAX_UPS);
+  if (c.n_kernels < 1 || c.n_kernels > 3) return fail(h, MBV_ERR_UNSUPPORTED, "1..3 resblock kernels supported (got %d)", c.n_kernels);
+  if (c.resblock_type != 1 && c.resblock_type != 2) return fail(h, MBV_ERR_INVALID, "resblock_type must be 1 or 2");
+  if (c.n_dilations < 1 || c.n_dilations > MBV_MAX_DILATIONS) return fail(h, MBV_ERR_UNSUPPORTED, "1..3 dilations per resblock supported");
+  if (c.n_fft != 16 || c.hop != 4) return fail(h, MBV_ERR_UNSUPPORTED, "the fused tail implements gen_istft_n_fft=16 / hop=4 only (got %d/%d)", c.n_fft, c.hop);
+  if (c.variant == MBV_VARIANT_ISTFT ? c.subbands != 1 : c.subbands != 4)
+    return fail(h, MBV_ERR_UNSUPPORTED, "subbands must be 4 for mb/ms and 1 for istft (got %d)", c.subbands);
+  if (c.flow_kernel % 2 != 1 || c.flow_layers < 1 || c.flow_layers > 4 || c.flow_n != 4 || c.flow_dilation_rate != 1)
+    return fail(h, MBV_ERR_UNSUPPORTED, "flow geometry: odd kernel, 1..4 layers, dilation_rate 1, n_flows 4");
+  if (c.gin_channels < 0) return fail(h, MBV_ERR_INVALID, "gin_channels < 0");
+  h->Cz = c.inter_channels;
+  h->H = c.hidden_channels;
+  h->Hp = round_up(c.hidden_channels, 64);
+  h->n_stage = c.n_ups;
+  int ch = c.upsample_initial_channel;
+  if (ch % 64 != 0 || ch > 1024) return fail(h, MBV_ERR_UNSUPPORTED, "upsample_initial_channel must be a multiple of 64 and <= 1024");
+  int up = 1;
+  for (int i = 0; i < c.n_ups; ++i) {
+    if (ch % 2) return fail(h, MBV_ERR_UNSUPPORTED, "channel halving hit an odd width");
+    ch /= 2;
+    if (ch % 64 != 0) return fail(h, MBV_ERR_UNSUPPORTED, "stage %d width %d is not a multiple of 64", i, ch);
+    h->stage_C[i] = ch;
+    up *= c.upsample_rates[i];
+    for (int j = 0; j < c.n_kernels; ++j) {
+      const int k = c.resblock_kernel_sizes[j];
+      if (k % 2 != 1) return fail(h, MBV_ERR_UNSUPPORTED, "resblock kernel sizes must be odd");
+      for (int p = 0; p < c.n_dilations; ++p)
+        if ((k - 1) * c.resblock_dilations[j][p] > 128)
+          return fail(h, MBV_ERR_UNSUPPORTED, "resblock receptive field (k-1)*d = %d exceeds the 128-row halo", (k - 1) * c.resblock_dilations[j][p]);
+    }
+  }
+  h->n_logit = c.subbands * (c.n_fft + 2);
+  h->spf = up * c.hop * c.subbands;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    h->err = "no CUDA device: handle created for inspection only, compute entries will fail";
+    return MBV_OK;  // geometry validated; compute entries fail loudly later
+  }
+  if (c.device < 0 || c.device >= ndev) return fail(h, MBV_ERR_INVALID, "device %d out of range", c.device);
+  CUDA_TRY(h, cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  CUDA_TRY(h, cudaGetDeviceProperties(&prop, c.device));
+  h->num_sms = prop.multiProcessorCount;
+  if (prop.major != 10) return fail(h, MBV_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", c.device, prop.major, prop.minor);
+  if (h->prec != MBV_PREC_FP32) CUDA_TRY(h, tc_set_attributes());
+  return MBV_OK;
+}
+
+extern "C" void mbv_destroy(mbv_handle* h) {
+  if (!h) return;
+  for (void* p : h->dev_allocs) cudaFree(p);
+  delete h;
+}
+
+extern "C" int mbv_load_weights(mbv_handle* h, const mbv_tensor* tensors, int32_t n) {
+  if (!h || !tensors || n <= 0) return MBV_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(h, MBV_ERR_CUDA, "mbv_load_weights: no CUDA device (there is no CPU fallback)");
+  }
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const mbv_config& c = h->cfg;
+  TensorMap m;
+  for (int i = 0; i < n; ++i) {
+    const mbv_tensor& t = tensors[i];
+    if (!t.name || !t.data || t.rank < 1 || t.rank > 4) return fail(h, MBV_ERR_WEIGHTS, "tensor %d is malformed", i);
+    HostTensor ht;
+    size_t cnt = 1;
+    for (int r = 0; r < t.rank; ++r) { ht.shape.push_back(t.shape[r]); cnt *= (size_t)t.shape[r]; }
+    ht.data.assign(t.data, t.data + cnt);
+    m[t.name] = std::move(ht);
+  }
+  int rc;
+  const int gin = c.gin_channels;
+  // ---------------- decoder
+  {
+    const int C0 = c.upsample_initial_channel;
+    rc = pack_conv1d(h, m, "dec.conv_pre", C0, h->Cz, 7, 1, iota_pad(C0, C0), iota_pad(h->Cz, h->Cz), true, 0, &h->conv_pre);
+    if (rc) return rc;
+    int cin = C0;
+    for (int i = 0; i < c.n_ups; ++i) {
+      const int C = h->stage_C[i];
+      char name[64];
+      snprintf(name, sizeof(name), "dec.ups.%d", i);
+      rc = pack_convT(h, m, name, cin, C, c.upsample_kernel_sizes[i], c.upsample_rates[i], &h->ups[i]);
+      if (rc) return rc;
+      for (int j = 0; j < c.n_kernels; ++j) {
+        const int k = c.resblock_kernel_sizes[j];
+        char pfx[96];
+        for (int p = 0; p < c.n_dilations; ++p) {
+          const int d = c.resblock_dilations[j][p];
+          if (c.resblock_type == 1) {
+            snprintf(pfx, sizeof(pfx), "dec.resblocks.%d.convs1.%d", i * c.n_kernels + j, p);
+            rc = pack_conv1d(h, m, pfx, C, C, k, d, iota_pad(C, C), iota_pad(C, C), true, 0, &h->rb_c1[i][j][p]);
+            if (rc) return rc;
+            snprintf(pfx, sizeof(pfx), "dec.resblocks.%d.convs2.%d", i * c.n_kernels + j, p);
+            rc = pack_conv1d(h, m, pfx, C, C, k, 1, iota_pad(C, C), iota_pad(C, C), true, 0, &h->rb_c2[i][j][p]);
+            if (rc) return rc;
+          } else {
+            snprintf(pfx, sizeof(pfx), "dec.resblocks.%d.convs.%d", i * c.n_kernels + j, p);
+            rc = pack_conv1d(h, m, pfx, C, C, k, d, iota_pad(C, C), iota_pad(C, C), true, 0, &h->rb_c1[i][j][p]);
+            if (rc) return rc;
+          }
+        }
+        if (gin) {
+          snprintf(pfx, sizeof(pfx), "dec.resblocks.%d.cond", i * c.n_kernels + j);
+          const int64_t ws[3] = {C, gin, 1}, bs[1] = {C};
+          const HostTensor* w = find_tensor(h, m, std::string(pfx) + ".weight", 3, ws);
+          const HostTensor* b = w ? find_tensor(h, m, std::string(pfx) + ".bias", 1, bs) : nullptr;
+          if (!w || !b) return MBV_ERR_WEIGHTS;
+          if ((rc = upload_f32(h, w->data, &h->rb_cond_w[i][j]))) return rc;
+          if ((rc = upload_f32(h, b->data, &h->rb_cond_b[i][j]))) return rc;
+        }
+      }
+      cin = C;
+    }
+    const char* post = c.variant == MBV_VARIANT_ISTFT ? "dec.conv_post" : "dec.subband_conv_post";
+    rc = pack_conv1d(h, m, post, h->n_logit, cin, 7, 1, iota_pad(h->n_logit, round_up(h->n_logit, 16)), iota_pad(cin, cin), true, 0, &h->conv_post);
+    if (rc) return rc;
+    float hs[4][63];
+    memset(hs, 0, sizeof(hs));
+    if (c.variant == MBV_VARIANT_MB) {
+      design_pqmf_synthesis(hs);
+    } else if (c.variant == MBV_VARIANT_MS) {
+      const int64_t ws[3] = {1, 4, 63};
+      const HostTensor* w = find_tensor(h, m, "dec.multistream_conv_post.weight", 3, ws);
+      if (!w) return MBV_ERR_WEIGHTS;
+      for (int ch4 = 0; ch4 < 4; ++ch4)
+        for (int k = 0; k < 63; ++k) hs[ch4][k] = w->data[ch4 * 63 + k];
+    }
+    fill_tail_coef(h, hs);
+  }
+  // ---------------- flow (Flips folded into pre/post)
+  {
+    const int half = h->Cz / 2, H = h->H, Hp = h->Hp, K = c.flow_kernel, NL = c.flow_layers;
+    for (int f = 0; f < 4; ++f) {
+      // coupling layer f runs after (4 - f) flips: odd -> reads rev(z[half:]) and updates rev(z[:half])
+      const bool odd = ((4 - f) & 1) != 0;
+      char pfx[96];
+      std::vector<int> in_map(h->Cz, -1), out_map(Hp, -1);
+      for (int j = 0; j < h->Cz; ++j) {
+        if (!odd && j < half) in_map[j] = j;
+        if (odd && j >= half) in_map[j] = h->Cz - 1 - j;
+      }
+      for (int o = 0; o < H; ++o) out_map[o] = o;
+      snprintf(pfx, sizeof(pfx), "flow.flows.%d.pre", 2 * f);
+      rc = pack_conv1d(h, m, pfx, H, half, 1, 1, out_map, in_map, true, 0, &h->fl_pre[f]);
+      if (rc) return rc;
+      std::vector<int> hin = iota_pad(H, Hp);
+      for (int l = 0; l < NL; ++l) {
+        std::vector<int> gmap(2 * Hp, -1);
+        for (int o = 0; o < H; ++o) { gmap[o] = o; gmap[Hp + o] = H + o; }
+        snprintf(pfx, sizeof(pfx), "flow.flows.%d.enc.in_layers.%d", 2 * f, l);
+        rc = pack_conv1d(h, m, pfx, 2 * H, H, K, 1, gmap, hin, true, 1, &h->fl_in[f][l]);
+        if (rc) return rc;
+        snprintf(pfx, sizeof(pfx), "flow.flows.%d.enc.res_skip_layers.%d", 2 * f, l);
+        if (l < NL - 1) rc = pack_conv1d(h, m, pfx, 2 * H, H, 1, 1, gmap, hin, true, 0, &h->fl_rs[f][l]);
+        else rc = pack_conv1d(h, m, pfx, H, H, 1, 1, iota_pad(H, Hp), hin, true, 0, &h->fl_rs[f][l]);
+        if (rc) return rc;
+      }
+      std::vector<int> pmap(half, -1);
+      for (int j = 0; j < half; ++j) pmap[j] = odd ? half - 1 - j : j;
+      snprintf(pfx, sizeof(pfx), "flow.flows.%d.post", 2 * f);
+      rc = pack_conv1d(h, m, pfx, half, H, 1, 1, pmap, hin, true, 0, &h->fl_post[f]);
+      if (rc) return rc;
+      if (gin) {
+        snprintf(pfx, sizeof(pfx), "flow.flows.%d.enc.cond_layer", 2 * f);
+        const int64_t ws[3] = {2 * H * NL, gin, 1}, bs[1] = {2 * H * NL};
+        const HostTensor* w = find_tensor(h, m, std::string(pfx) + ".weight", 3, ws);
+        const HostTensor* b = w ? find_tensor(h, m, std::string(pfx) + ".bias", 1, bs) : nullptr;
+        if (!w || !b) return MBV_ERR_WEIGHTS;
+        std::vector<float> pw((size_t)NL * 2 * Hp * gin, 0.f), pb((size_t)NL * 2 * Hp, 0.f);
+        for (int l = 0; l < NL; ++l)
+          for (int o = 0; o < 2 * H; ++o) {
+            const int dst = l * 2 * Hp + (o < H ? o : Hp + (o - H));
+            const int src = l * 2 * H + o;
+            memcpy(&pw[(size_t)dst * gin], &w->data[(size_t)src * gin], sizeof(float) * gin);
+            pb[dst] = b->data[src];
+          }
+        if ((rc = upload_f32(h, pw, &h->fl_cond_w[f]))) return rc;
+        if ((rc = upload_f32(h, pb, &h->fl_cond_b[f]))) return rc;
+      }
+    }
+  }
+  h->weights_loaded = true;
+  return MBV_OK;
+}
+
+// =================================================================================================
+// workspace planning
+// =================================================================================================
+namespace {
+
+struct Arena {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Arena(void* p) : base((uint8_t*)p) {}
+  void* take(size_t bytes) {
+    off = (off + 1023) & ~(size_t)1023;
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+struct DecBufs {
+  void* zin_op; void* pre_act;
+  struct Stage { float* x; void* a[3]; float* xr; void* ar; void* hop; float* xs; void* next; } st[MBV_MAX_UPS];
+  float* logits;
+  float* cond;  // [n_stage][n_kernels][2][B][C]: (cond, bias2+cond) per resblock
+};
+struct FlowBufs {
+  float* z; void* zop; float* h; void* hop; void* acts; float* skip; void* hout; float* gcond;  // gcond [4][B][NL*2Hp]
+};
+
+void layout_dec(mbv_handle* h, Arena& A, int B, int T, DecBufs* d) {
+  const int es = h->esize;
+  d->zin_op = A.take((size_t)B * T * h->Cz * es);
+  d->pre_act = A.take((size_t)B * T * h->cfg.upsample_initial_channel * es);
+  int L = T;
+  for (int i = 0; i < h->n_stage; ++i) {
+    L *= h->cfg.upsample_rates[i];
+    const int C = h->stage_C[i];
+    const size_t n = (size_t)B * L * C;
+    auto& s = d->st[i];
+    s.x = (float*)A.take(n * 4);
+    const int na = h->cfg.gin_channels ? h->cfg.n_kernels : 1;
+    for (int j = 0; j < 3; ++j) s.a[j] = j < na ? A.take(n * es) : nullptr;
+    s.xr = (float*)A.take(n * 4);
+    s.ar = A.take(n * es);
+    s.hop = A.take(n * es);
+    s.xs = (float*)A.take(n * 4);
+    const bool last = (i == h->n_stage - 1);
+    s.next = A.take((size_t)B * (L + (last ? 1 : 0)) * C * es);
+  }
+  d->logits = (float*)A.take((size_t)B * (L + 1) * h->n_logit * 4);
+  d->cond = (float*)A.take((size_t)h->n_stage * h->cfg.n_kernels * 2 * B * 512 * 4);
+}
+
+void layout_flow(mbv_handle* h, Arena& A, int B, int T, FlowBufs* f) {
+  const int es = h->esize;
+  const size_t nz = (size_t)B * T * h->Cz, nh = (size_t)B * T * h->Hp;
+  f->z = (float*)A.take(nz * 4);
+  f->zop = A.take(nz * es);
+  f->h = (float*)A.take(nh * 4);
+  f->hop = A.take(nh * es);
+  f->acts = A.take(nh * es);
+  f->skip = (float*)A.take(nh * 4);
+  f->hout = A.take(nh * es);
+  f->gcond = (float*)A.take((size_t)4 * B * h->cfg.flow_layers * 2 * h->Hp * 4);
+}
+
+// Launch context: counts launches, caches tensor maps
+struct Ctx {
+  mbv_handle* h;
+  cudaStream_t st;
+  std::vector<TcPlan>* plans;
+  bool plans_valid;
+  size_t plan_idx = 0;
+  int launches = 0;
+};
+
+int run_conv(Ctx& cx, const ConvLayer& L, const void* x, int B, int L_in, int L_out, const EpiParams& epi) {
+  mbv_handle* h = cx.h;
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x; a.w = L.w; a.B = B; a.L_in = L_in; a.L_out = L_out; a.Cp_in = L.Cp_in; a.N_total = L.N_total;
+  a.N_tile = L.N_tile; a.taps = L.taps; a.dil = L.dil; a.n_phases = L.n_phases; a.gate = L.gate;
+  for (int i = 0; i < kMaxPhases; ++i) a.shift0[i] = L.shift0[i];
+  a.epi = epi;
+  if (a.epi.bias == nullptr) { a.epi.bias = L.bias; a.epi.bias_bs = 0; }
+  if (h->prec == MBV_PREC_FP32 || (h->cfg.flags & MBV_FLAG_FORCE_SIMT)) {
+    CUDA_TRY(h, launch_conv_simt(h->prec, a, cx.st));
+  } else {
+    TcPlan plan;
+    if (cx.plans_valid && cx.plan_idx < cx.plans->size()) {
+      plan = (*cx.plans)[cx.plan_idx];
+    } else {
+      const char* msg = tc_make_plan(h->prec, a, h->cfg.flags, h->num_sms, &plan);
+      if (msg) return fail(h, MBV_ERR_CUDA, "%s", msg);
+      cx.plans->push_back(plan);
+    }
+    cx.plan_idx++;
+    CUDA_TRY(h, launch_conv_tc(h->prec, a, plan, cx.st));
+  }
+  cx.launches++;
+  return MBV_OK;
+}
+
+EpiParams epi_base(int mode, int ld, int rows) {
+  EpiParams e;
+  memset(&e, 0, sizeof(e));
+  e.mode = mode; e.ld = ld; e.rows_out = rows; e.rows_res = rows; e.row_mul = 1; e.row_add = 0;
+  e.dup_src = -1; e.dup_dst = 0; e.slope = 1.f; e.scale = 1.f; e.n_valid = 1 << 30;
+  return e;
+}
+
+int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, const float* g, float* z_out, int B, int T) {
+  mbv_handle* h = cx.h;
+  const mbv_config& c = h->cfg;
+  const int Hp = h->Hp, NL = c.flow_layers;
+  CUDA_TRY(h, launch_pack_input(h->prec, z_p, nullptr, f.zop, f.z, B, h->Cz, T, h->Cz, cx.st));
+  cx.launches++;
+  for (int f_i = 3; f_i >= 0; --f_i) {
+    float* gc = nullptr;
+    if (g) {
+      gc = f.gcond + (size_t)f_i * B * NL * 2 * Hp;
+      CUDA_TRY(h, launch_cond_gemv(g, h->fl_cond_w[f_i], h->fl_cond_b[f_i], nullptr, gc, B, c.gin_channels, NL * 2 * Hp, NL * 2 * Hp, cx.st));
+      cx.launches++;
+    }
+    int rc;
+    {  // h = pre(x0) * mask
+      EpiParams e = epi_base(EPI_ACT, Hp, T);
+      e.mask = mask; e.xout = f.h; e.act[0] = f.hop; e.n_act = 1;
+      if ((rc = run_conv(cx, h->fl_pre[f_i], f.zop, B, T, T, e))) return rc;
+    }
+    for (int l = 0; l < NL; ++l) {
+      {
+        EpiParams e = epi_base(EPI_GATE, Hp, T);
+        e.n_split = Hp; e.act[0] = f.acts; e.n_act = 1;
+        if (gc) { e.add2 = gc + (size_t)l * 2 * Hp; e.add2_bs = NL * 2 * Hp; }
+        if ((rc = run_conv(cx, h->fl_in[f_i][l], f.hop, B, T, T, e))) return rc;
+      }
+      {
+        EpiParams e = epi_base(EPI_RS, Hp, T);
+        e.mask = mask; e.first = (l == 0); e.xs = f.skip;
+        if (l < NL - 1) { e.n_split = Hp; e.xin = f.h; e.xout = f.h; e.act[0] = f.hop; }
+        else { e.n_split = 0; e.act[0] = f.hout; }
+        e.n_act = 1;
+        if ((rc = run_conv(cx, h->fl_rs[f_i][l], f.acts, B, T, T, e))) return rc;
+      }
+    }
+    {  // x1 = (x1 - post(h) * mask) * mask
+      EpiParams e = epi_base(EPI_POST, h->Cz, T);
+      e.mask = mask; e.xin = f.z; e.xout = f.z; e.act[0] = f.zop; e.n_act = 1;
+      e.ch_off = ((4 - f_i) & 1) ? 0 : h->Cz / 2;
+      if ((rc = run_conv(cx, h->fl_post[f_i], f.hout, B, T, T, e))) return rc;
+    }
+  }
+  if (z_out) {
+    CUDA_TRY(h, launch_unpack_output(f.z, z_out, B, h->Cz, T, h->Cz, cx.st));
+    cx.launches++;
+  }
+  return MBV_OK;
+}
+
+int run_tail(Ctx& cx, const float* logits, float* wav, float* o_mb, float* spec, float* phase, int B, int Lfr) {
+  mbv_handle* h = cx.h;
+  TailArgs ta;
+  memset(&ta, 0, sizeof(ta));
+  ta.logits = logits; ta.wav = wav; ta.o_mb = o_mb; ta.spec = spec; ta.phase = phase;
+  ta.B = B; ta.L = Lfr; ta.n_ch = h->n_logit; ta.variant = h->cfg.variant;
+  memcpy(ta.coef, h->tail_coef, sizeof(ta.coef));
+  CUDA_TRY(h, launch_tail(ta, h->prec == MBV_PREC_FP32 ? 1 : 0, cx.st));
+  cx.launches++;
+  return MBV_OK;
+}
+
+// z_op_ready: the operand copy of z already sits in d.zin_op (fused flow+decode path)
+int run_decode(Ctx& cx, const DecBufs& d, const float* z, const float* z_mask, const void* z_op_ready, const float* g,
+               float* wav, float* o_mb, float* spec, float* phase, int B, int T) {
+  mbv_handle* h = cx.h;
+  const mbv_config& c = h->cfg;
+  int rc;
+  const void* zin = z_op_ready;
+  if (!zin) {
+    CUDA_TRY(h, launch_pack_input(h->prec, z, z_mask, d.zin_op, nullptr, B, h->Cz, T, h->Cz, cx.st));
+    cx.launches++;
+    zin = d.zin_op;
+  }
+  const int C0 = c.upsample_initial_channel;
+  {  // x = conv_pre(z); the only consumer is leaky_relu(x, 0.1) -> ups[0]
+    EpiParams e = epi_base(EPI_ACT, C0, T);
+    e.slope = 0.1f; e.act[0] = d.pre_act; e.n_act = 1;
+    if ((rc = run_conv(cx, h->conv_pre, zin, B, T, T, e))) return rc;
+  }
+  const void* cur = d.pre_act;
+  int L = T;
+  for (int i = 0; i < h->n_stage; ++i) {
+    const int S = c.upsample_rates[i], C = h->stage_C[i], Lin = L;
+    L *= S;
+    const auto& s = d.st[i];
+    const bool last = (i == h->n_stage - 1);
+    const int nk = c.n_kernels;
+    // per-resblock conditioning vectors cond_j(g) [B][C] and (bias2_first + cond_j)
+    float* cond[3] = {nullptr, nullptr, nullptr};
+    float* bias2c[3] = {nullptr, nullptr, nullptr};
+    if (g) {
+      for (int j = 0; j < nk; ++j) {
+        cond[j] = d.cond + ((size_t)(i * nk + j) * 2 + 0) * B * 512;
+        bias2c[j] = d.cond + ((size_t)(i * nk + j) * 2 + 1) * B * 512;
+        const ConvLayer& first_res = (c.resblock_type == 1) ? h->rb_c2[i][j][0] : h->rb_c1[i][j][0];
+        CUDA_TRY(h, launch_cond_gemv(g, h->rb_cond_w[i][j], h->rb_cond_b[i][j], nullptr, cond[j], B, c.gin_channels, C, C, cx.st));
+        CUDA_TRY(h, launch_cond_gemv(g, h->rb_cond_w[i][j], h->rb_cond_b[i][j], first_res.bias, bias2c[j], B, c.gin_channels, C, C, cx.st));
+        cx.launches += 2;
+      }
+    }
+    {  // x = ups[i](lrelu(x)): S polyphase branches; emits the fp32 residual stream and lrelu(x [+ cond_j]) operand copies
+      EpiParams e = epi_base(EPI_ACT, C, L);
+      e.rows_res = Lin; e.row_mul = S; e.slope = 0.1f; e.xout = s.x;
+      e.n_act = g ? nk : 1;
+      for (int j = 0; j < e.n_act; ++j) { e.act[j] = s.a[j]; e.act_add[j] = g ? cond[j] : nullptr; }
+      e.act_add_bs = C;
+      if ((rc = run_conv(cx, h->ups[i], cur, B, Lin, Lin, e))) return rc;
+    }
+    for (int j = 0; j < nk; ++j) {
+      const void* a_in = g ? s.a[j] : s.a[0];
+      const float* x_in = s.x;
+      const int np = c.n_dilations;
+      for (int p = 0; p < np; ++p) {
+        const bool final_conv = (p == np - 1);
+        EpiParams e = epi_base(EPI_RES, C, L);
+        e.xin = x_in; e.slope = 0.1f;
+        if (p == 0 && g) { e.bias = bias2c[j]; e.bias_bs = C; }  // x + cond(g) folded into the first residual add
+        if (final_conv) {
+          e.xs = s.xs;
+          e.sum_mode = (nk == 1) ? 4 : (j == 0 ? 1 : (j == nk - 1 ? 3 : 2));
+          if (e.sum_mode >= 3) {
+            e.scale = 1.f / nk; e.act[0] = s.next; e.n_act = 1;
+            e.slope = last ? 0.01f : 0.1f;
+            if (last) { e.rows_out = L + 1; e.row_add = 1; e.dup_src = 2; e.dup_dst = 0; }
+          }
+        } else {
+          e.xout = s.xr;
+        }
+        const void* conv_in;
+        if (c.resblock_type == 1) {
+          EpiParams e1 = epi_base(EPI_ACT, C, L);
+          e1.slope = 0.1f; e1.act[0] = s.hop; e1.n_act = 1;
+          if ((rc = run_conv(cx, h->rb_c1[i][j][p], a_in, B, L, L, e1))) return rc;
+          conv_in = s.hop;
+          if (!final_conv) { e.act[0] = s.ar; e.n_act = 1; }
+          if ((rc = run_conv(cx, h->rb_c2[i][j][p], conv_in, B, L, L, e))) return rc;
+          a_in = s.ar;
+        } else {
+          // ResBlock2: x = x + c_p(lrelu(x)); operand copies ping-pong between ar and hop
+          void* a_out = (p & 1) ? s.hop : s.ar;
+          if (!final_conv) { e.act[0] = a_out; e.n_act = 1; }
+          if ((rc = run_conv(cx, h->rb_c1[i][j][p], a_in, B, L, L, e))) return rc;
+          a_in = a_out;
+        }
+        x_in = s.xr;
+      }
+    }
+    cur = s.next;
+  }
+  {  // conv_post on the reflect-padded L+1 frames -> fp32 logits, pitch n_logit
+    EpiParams e = epi_base(EPI_F32, h->n_logit, L + 1);
+    e.n_valid = h->n_logit; e.xout = d.logits;
+    if ((rc = run_conv(cx, h->conv_post, cur, B, L + 1, L + 1, e))) return rc;
+  }
+  return run_tail(cx, d.logits, wav, o_mb, spec, phase, B, L);
+}
+
+int check_ready(mbv_handle* h, int B, int T) {
+  if (!h) return MBV_ERR_INVALID;
+  if (!h->weights_loaded) return fail(h, MBV_ERR_WEIGHTS, "mbv_load_weights has not completed");
+  if (B < 1 || T < 1) return fail(h, MBV_ERR_INVALID, "B and T must be >= 1");
+  if (B > 65535) return fail(h, MBV_ERR_UNSUPPORTED, "B > 65535");
+  return MBV_OK;
+}
+
+int total_ws(mbv_handle* h, int B, int T, size_t* dec_off, size_t* total) {
+  Arena A(nullptr);
+  FlowBufs f;
+  layout_flow(h, A, B, T, &f);
+  *dec_off = (A.off + 1023) & ~(size_t)1023;
+  DecBufs d;
+  layout_dec(h, A, B, T, &d);
+  *total = A.off + 1024;
+  return 0;
+}
+
+Ctx make_ctx(mbv_handle* h, int B, int T, void* ws, int kind, void* stream) {
+  Ctx cx;
+  cx.h = h;
+  cx.st = (cudaStream_t)stream;
+  mbv_handle::PlanKey key{B, T, ws, kind};
+  auto it = h->plan_cache.find(key);
+  if (it == h->plan_cache.end()) {
+    if (h->plan_cache.size() > 64) h->plan_cache.clear();
+    it = h->plan_cache.emplace(key, std::vector<TcPlan>()).first;
+    cx.plans_valid = false;
+  } else {
+    cx.plans_valid = true;
+  }
+  cx.plans = &it->second;
+  return cx;
+}
+
+int check_ws(mbv_handle* h, int B, int T, void* ws, size_t ws_bytes) {
+  size_t dec_off, total;
+  total_ws(h, B, T, &dec_off, &total);
+  if (!ws || ((uintptr_t)ws & 1023) != 0) return fail(h, MBV_ERR_WORKSPACE, "workspace must be non-null and 1024-byte aligned");
+  if (ws_bytes < total) return fail(h, MBV_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", total, ws_bytes);
+  return MBV_OK;
+}
+
+}  // namespace
+
+extern "C" int mbv_workspace_bytes(mbv_handle* h, int32_t B, int32_t T, size_t* bytes) {
+  if (!h || !bytes) return MBV_ERR_INVALID;
+  if (B < 1 || T < 1) return fail(h, MBV_ERR_INVALID, "B and T must be >= 1");
+  size_t dec_off;
+  return total_ws(h, B, T, &dec_off, bytes);
+}
+
+extern "C" int mbv_flow_reverse(mbv_handle* h, const float* z_p, const float* y_mask, const float* g, float* z_out,
+                                int32_t B, int32_t T, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_ready(h, B, T);
+  if (rc) return rc;
+  if (!z_p || !y_mask || !z_out) return fail(h, MBV_ERR_INVALID, "null tensor");
+  if (g && h->cfg.gin_channels == 0) return fail(h, MBV_ERR_INVALID, "g given but gin_channels == 0");
+  if ((rc = check_ws(h, B, T, ws, ws_bytes))) return rc;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  Arena A(ws);
+  FlowBufs f;
+  layout_flow(h, A, B, T, &f);
+  Ctx cx = make_ctx(h, B, T, ws, g ? 1 : 0, stream);
+  rc = run_flow(cx, f, z_p, y_mask, g, z_out, B, T);
+  if (rc) { cx.plans->clear(); return rc; }
+  h->last_launches = cx.launches;
+  return MBV_OK;
+}
+
+extern "C" int mbv_decode(mbv_handle* h, const float* z, const float* z_mask, const float* g, float* wav, float* o_mb,
+                          float* spec, float* phase, int32_t B, int32_t T, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_ready(h, B, T);
+  if (rc) return rc;
+  if (!z || !wav) return fail(h, MBV_ERR_INVALID, "null tensor");
+  if (g && h->cfg.gin_channels == 0) return fail(h, MBV_ERR_INVALID, "g given but gin_channels == 0");
+  if ((spec == nullptr) != (phase == nullptr)) return fail(h, MBV_ERR_INVALID, "spec and phase must be requested together");
+  if (o_mb && h->cfg.variant == MBV_VARIANT_ISTFT) return fail(h, MBV_ERR_INVALID, "the single-band decoder has no o_mb (models.py:297 returns None)");
+  if ((rc = check_ws(h, B, T, ws, ws_bytes))) return rc;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  size_t dec_off, total;
+  total_ws(h, B, T, &dec_off, &total);
+  Arena A(ws);
+  A.off = dec_off;
+  DecBufs d;
+  layout_dec(h, A, B, T, &d);
+  Ctx cx = make_ctx(h, B, T, ws, g ? 3 : 2, stream);
+  rc = run_decode(cx, d, z, z_mask, nullptr, g, wav, o_mb, spec, phase, B, T);
+  if (rc) { cx.plans->clear(); return rc; }
+  h->last_launches = cx.launches;
+  return MBV_OK;
+}
+
+extern "C" int mbv_flow_decode(mbv_handle* h, const float* z_p, const float* y_mask, const float* g, float* z_out,
+                               float* wav, float* o_mb, float* spec, float* phase, int32_t B, int32_t T, void* ws,
+                               size_t ws_bytes, void* stream) {
+  int rc = check_ready(h, B, T);
+  if (rc) return rc;
+  if (!z_p || !y_mask || !wav) return fail(h, MBV_ERR_INVALID, "null tensor");
+  if (g && h->cfg.gin_channels == 0) return fail(h, MBV_ERR_INVALID, "g given but gin_channels == 0");
+  if ((spec == nullptr) != (phase == nullptr)) return fail(h, MBV_ERR_INVALID, "spec and phase must be requested together");
+  if (o_mb && h->cfg.variant == MBV_VARIANT_ISTFT) return fail(h, MBV_ERR_INVALID, "the single-band decoder has no o_mb");
+  if ((rc = check_ws(h, B, T, ws, ws_bytes))) return rc;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  size_t dec_off, total;
+  total_ws(h, B, T, &dec_off, &total);
+  Arena A(ws);
+  FlowBufs f;
+  layout_flow(h, A, B, T, &f);
+  A.off = dec_off;
+  DecBufs d;
+  layout_dec(h, A, B, T, &d);
+  Ctx cx = make_ctx(h, B, T, ws, g ? 5 : 4, stream);
+  rc = run_flow(cx, f, z_p, y_mask, g, z_out, B, T);
+  // after the four masked couplings z is already zero on padded frames, so z * y_mask is the
+  // identity and the flow's operand copy feeds conv_pre directly
+  if (!rc) rc = run_decode(cx, d, nullptr, nullptr, f.zop, g, wav, o_mb, spec, phase, B, T);
+  if (rc) { cx.plans->clear(); return rc; }
+  h->last_launches = cx.launches;
+  return MBV_OK;
+}
+
+extern "C" int mbv_tail(mbv_handle* h, const float* logits, float* wav, float* o_mb, float* spec, float* phase,
+                        int32_t B, int32_t T, void* stream) {
+  int rc = check_ready(h, B, T);
+  if (rc) return rc;
+  if (!logits || !wav) return fail(h, MBV_ERR_INVALID, "null tensor");
+  if ((spec == nullptr) != (phase == nullptr)) return fail(h, MBV_ERR_INVALID, "spec and phase must be requested together");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  int L = T;
+  for (int i = 0; i < h->n_stage; ++i) L *= h->cfg.upsample_rates[i];
+  Ctx cx;
+  cx.h = h; cx.st = (cudaStream_t)stream; cx.plans = nullptr; cx.plans_valid = false;
+  rc = run_tail(cx, logits, wav, o_mb, spec, phase, B, L);
+  h->last_launches = cx.launches;
+  return rc;
+}
+
+extern "C" int mbv_last_launch_count(mbv_handle* h) { return h ? h->last_launches : 0; }
+
+extern "C" double mbv_decode_flops(mbv_handle* h, int32_t B, int32_t T) {
+  if (!h || !h->weights_loaded) return 0.0;
+  const mbv_config& c = h->cfg;
+  double macs = h->conv_pre.macs_per_row * T;
+  double L = T;
+  for (int i = 0; i < h->n_stage; ++i) {
+    macs += h->ups[i].macs_per_row * L;
+    L *= c.upsample_rates[i];
+    for (int j = 0; j < c.n_kernels; ++j)
+      for (int p = 0; p < c.n_dilations; ++p) {
+        macs += h->rb_c1[i][j][p].macs_per_row * L;
+        if (c.resblock_type == 1) macs += h->rb_c2[i][j][p].macs_per_row * L;
+      }
+  }
+  macs += h->conv_post.macs_per_row * (L + 1);
+  return 2.0 * macs * B;
+}
+
+extern "C" double mbv_flow_flops(mbv_handle* h, int32_t B, int32_t T) {
+  if (!h || !h->weights_loaded) return 0.0;
+  double macs = 0;
+  for (int f = 0; f < 4; ++f) {
+    macs += h->fl_pre[f].macs_per_row + h->fl_post[f].macs_per_row;
+    for (int l = 0; l < h->cfg.flow_layers; ++l) macs += h->fl_in[f][l].macs_per_row + h->fl_rs[f][l].macs_per_row;
+  }
+  return 2.0 * macs * T * B;
+}

@@ -1,0 +1,100 @@
+// misc.cu -- layout conversion at the ABI boundary and the per-utterance conditioning GEMVs.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mbv {
+
+// fp32 NCT [B][C][T] (time contiguous, as the reference passes tensors) -> channels-last [B][T][Cp]:
+// 32x32 smem transpose so both the read (along T) and the write (along C) are coalesced.  Pad channels
+// C..Cp are written as zeros.  Optional mask [B][T] fuses the `z * y_mask` of models.py:734.
+template <typename Op>
+__global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict__ src, const float* __restrict__ mask,
+                                                         typename Op::T* __restrict__ dst_op, float* __restrict__ dst_f32,
+                                                         int C, int T, int Cp) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    float v = 0.f;
+    if (c < C && t < T) {
+      v = src[((size_t)b * C + c) * T + t];
+      if (mask) v *= mask[(size_t)b * T + t];
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    if (t < T && c < Cp) {
+      const float v = tile[tx][i];
+      const size_t o = ((size_t)b * T + t) * Cp + c;
+      if (dst_op) {
+        if constexpr (Op::kPrec == 2) dst_op[o] = __float2bfloat16_rn(v);
+        else dst_op[o] = op_round<Op>(v);
+      }
+      if (dst_f32) dst_f32[o] = v;
+    }
+  }
+}
+
+cudaError_t launch_pack_input(int prec, const float* src, const float* mask, void* dst_op, float* dst_f32, int B, int C,
+                              int T, int Cp, cudaStream_t st) {
+  dim3 grid((T + 31) / 32, (Cp + 31) / 32, B);
+  if (prec == 2)
+    pack_input_kernel<OpBF16><<<grid, 256, 0, st>>>(src, mask, (__nv_bfloat16*)dst_op, dst_f32, C, T, Cp);
+  else if (prec == 1)
+    pack_input_kernel<OpTF32><<<grid, 256, 0, st>>>(src, mask, (float*)dst_op, dst_f32, C, T, Cp);
+  else
+    pack_input_kernel<OpF32><<<grid, 256, 0, st>>>(src, mask, (float*)dst_op, dst_f32, C, T, Cp);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) unpack_output_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                            int C, int T, int Cp) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    tile[i][tx] = (t < T && c < C) ? src[((size_t)b * T + t) * Cp + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    if (c < C && t < T) dst[((size_t)b * C + c) * T + t] = tile[tx][i];
+  }
+}
+
+cudaError_t launch_unpack_output(const float* src, float* dst, int B, int C, int T, int Cp, cudaStream_t st) {
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B);
+  unpack_output_kernel<<<grid, 256, 0, st>>>(src, dst, C, T, Cp);
+  return cudaGetLastError();
+}
+
+// out[b][n] = bias[n] (+ base[n]) + sum_c w[n][c] * g[b][c]: ResBlock.cond (modules.py:209-215) and
+// WN.cond_layer (modules.py:126-128,152-153) act on g [B,gin,1], i.e. one GEMV per utterance.
+__global__ void __launch_bounds__(128) cond_gemv_kernel(const float* __restrict__ g, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, const float* __restrict__ base,
+                                                        float* __restrict__ out, int G, int N, int out_ld) {
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int c = lane; c < G; c += 32) s = fmaf(w[(size_t)n * G + c], g[(size_t)b * G + c], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[(size_t)b * out_ld + n] = s + (bias ? bias[n] : 0.f) + (base ? base[n] : 0.f);
+}
+
+cudaError_t launch_cond_gemv(const float* g, const float* w, const float* bias, const float* base, float* out, int B,
+                             int G, int N, int out_ld, cudaStream_t st) {
+  dim3 grid((N + 3) / 4, B);
+  cond_gemv_kernel<<<grid, 128, 0, st>>>(g, w, bias, base, out, G, N, out_ld);
+  return cudaGetLastError();
+}
+
+}  // namespace mbv

@@ -1,0 +1,187 @@
+"""Host-side owner of one libmbistft handle: weight folding / upload, workspace, and the calls.
+
+PyTorch is used for what it is good at here -- device memory, streams, tensors at the boundary.
+All arithmetic of the hot path happens in libmbistft.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import lib as _lib
+from .configs import samples_per_frame
+
+
+def fold_weight_norm(sd: Dict[str, torch.Tensor], prefixes=("dec.", "flow.")) -> Dict[str, torch.Tensor]:
+    """Reference checkpoint layout -> effective fp32 weights: w = g * v / ||v|| with the norm
+    over all dims but 0 (torch.nn.utils.weight_norm, dim=0; for ConvTranspose1d dim 0 = in-channels).
+    Keys already stored as plain ``weight`` (after remove_weight_norm) pass through."""
+    out: Dict[str, torch.Tensor] = {}
+    for k, v in sd.items():
+        if not k.startswith(prefixes):
+            continue
+        if k.endswith(".weight_v"):
+            base = k[: -len(".weight_v")]
+            g = sd[base + ".weight_g"].detach().float().cpu()
+            vv = v.detach().float().cpu()
+            norm = vv.reshape(vv.shape[0], -1).norm(dim=1).reshape(g.shape)
+            out[base + ".weight"] = (vv * (g / norm)).contiguous()
+        elif k.endswith(".weight_g") or k.endswith("updown_filter"):
+            continue
+        else:
+            out[k] = v.detach().float().cpu().contiguous()
+    return out
+
+
+class Engine:
+    """One handle on one GPU.  Not re-entrant across streams that share its workspace."""
+
+    def __init__(self, cfg, state_dict, precision="bf16", device=0, flags=0):
+        self.cfg = dict(cfg)
+        self.precision = precision
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("mb_istft_vits_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", device)
+        self.spf = samples_per_frame(cfg)
+        self._h = C.c_void_p()
+        ccfg = _lib.make_config(cfg, precision, device, flags)
+        rc = self.lib.mbv_create(C.byref(ccfg), C.byref(self._h))
+        self._check(rc)
+        self._load(state_dict)
+        self._ws = None
+        self._ws_key = None
+
+    # ---- plumbing
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.mbv_last_error(self._h)
+            raise _lib.MbvError(rc, msg.decode() if msg else "")
+
+    def _load(self, sd):
+        eff = fold_weight_norm(sd)
+        arr = (_lib.MbvTensor * len(eff))()
+        keep = []
+        for i, (k, t) in enumerate(eff.items()):
+            t = t.contiguous()
+            keep.append(t)
+            arr[i].name = k.encode()
+            arr[i].data = C.cast(t.data_ptr(), C.POINTER(C.c_float))
+            arr[i].rank = t.dim()
+            for r, s in enumerate(t.shape):
+                arr[i].shape[r] = s
+        self._check(self.lib.mbv_load_weights(self._h, arr, len(eff)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.mbv_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def workspace_bytes(self, B, T):
+        n = C.c_size_t()
+        self._check(self.lib.mbv_workspace_bytes(self._h, B, T, C.byref(n)))
+        return n.value
+
+    def _workspace(self, B, T):
+        need = self.workspace_bytes(B, T)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+        base = self._ws.data_ptr()
+        off = (-base) % 1024
+        return base + off, self._ws.numel() - off
+
+    @staticmethod
+    def _ptr(t: Optional[torch.Tensor]):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def _prep(self, t, shape=None):
+        if t is None:
+            return None
+        t = t.to(device=self.device, dtype=torch.float32).contiguous()
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _alloc_outputs(self, B, T, want_mb, want_spec):
+        v = self.cfg["variant"]
+        S = self.cfg["subbands"] if v != "istft" else 1
+        L = T
+        for u in self.cfg["upsample_rates"]:
+            L *= u
+        wav = torch.empty((B, 1, self.spf * T), dtype=torch.float32, device=self.device)
+        o_mb = None
+        if want_mb and v != "istft":
+            o_mb = torch.empty((B, S, (4 if v == "mb" else 16) * L), dtype=torch.float32, device=self.device)
+        spec = phase = None
+        if want_spec:
+            shape = (B, S, 9, L + 1) if v != "istft" else (B, 9, L + 1)
+            spec = torch.empty(shape, dtype=torch.float32, device=self.device)
+            phase = torch.empty(shape, dtype=torch.float32, device=self.device)
+        return wav, o_mb, spec, phase
+
+    # ---- the three entry points
+    def flow_reverse(self, z_p, y_mask, g=None):
+        B, Cz, T = z_p.shape
+        z_p = self._prep(z_p)
+        y_mask = self._prep(y_mask, (B, 1, T))
+        g = self._prep(g)
+        out = torch.empty_like(z_p)
+        ws, nws = self._workspace(B, T)
+        self._check(self.lib.mbv_flow_reverse(self._h, self._ptr(z_p), self._ptr(y_mask), self._ptr(g), self._ptr(out),
+                                              B, T, C.c_void_p(ws), nws, self._stream()))
+        return out
+
+    def decode(self, z, g=None, z_mask=None, want_mb=True, want_spec=True):
+        B, Cz, T = z.shape
+        z = self._prep(z)
+        g = self._prep(g)
+        z_mask = self._prep(z_mask, (B, 1, T)) if z_mask is not None else None
+        wav, o_mb, spec, phase = self._alloc_outputs(B, T, want_mb, want_spec)
+        ws, nws = self._workspace(B, T)
+        self._check(self.lib.mbv_decode(self._h, self._ptr(z), self._ptr(z_mask), self._ptr(g), self._ptr(wav),
+                                        self._ptr(o_mb), self._ptr(spec), self._ptr(phase), B, T, C.c_void_p(ws), nws,
+                                        self._stream()))
+        return wav, o_mb, spec, phase
+
+    def flow_decode(self, z_p, y_mask, g=None, want_z=True, want_mb=False, want_spec=False):
+        B, Cz, T = z_p.shape
+        z_p = self._prep(z_p)
+        y_mask = self._prep(y_mask, (B, 1, T))
+        g = self._prep(g)
+        z = torch.empty_like(z_p) if want_z else None
+        wav, o_mb, spec, phase = self._alloc_outputs(B, T, want_mb, want_spec)
+        ws, nws = self._workspace(B, T)
+        self._check(self.lib.mbv_flow_decode(self._h, self._ptr(z_p), self._ptr(y_mask), self._ptr(g), self._ptr(z),
+                                             self._ptr(wav), self._ptr(o_mb), self._ptr(spec), self._ptr(phase), B, T,
+                                             C.c_void_p(ws), nws, self._stream()))
+        return z, wav, o_mb, spec, phase
+
+    def tail(self, logits, T, want_mb=True, want_spec=True):
+        """Fused head+iSTFT+synthesis on logits [B, F, n_ch] (channels-last)."""
+        logits = self._prep(logits)
+        B = logits.shape[0]
+        wav, o_mb, spec, phase = self._alloc_outputs(B, T, want_mb, want_spec)
+        self._check(self.lib.mbv_tail(self._h, self._ptr(logits), self._ptr(wav), self._ptr(o_mb), self._ptr(spec),
+                                      self._ptr(phase), B, T, self._stream()))
+        return wav, o_mb, spec, phase
+
+    def last_launch_count(self):
+        return int(self.lib.mbv_last_launch_count(self._h))
+
+    def decode_flops(self, B, T):
+        return float(self.lib.mbv_decode_flops(self._h, B, T))
+
+    def flow_flops(self, B, T):
+        return float(self.lib.mbv_flow_flops(self._h, B, T))

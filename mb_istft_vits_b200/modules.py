@@ -1,0 +1,65 @@
+"""Drop-in replacements for ``SynthesizerTrn.flow`` and ``SynthesizerTrn.dec`` (models.py:634-647).
+
+Usage (the reference's models.py stays untouched)::
+
+    net_g = SynthesizerTrn(...); utils.load_checkpoint(path, net_g, None)      # reference code
+    from mb_istft_vits_b200 import patch_synthesizer
+    patch_synthesizer(net_g, cfg, precision="bf16")                             # swaps flow + dec
+    o, o_mb, spec, phase, attn, y_mask, zs, timings = net_g.infer(x, x_lengths, sid=sid)
+
+Signatures honoured:
+  flow(x, x_mask, g=None, reverse=False) -> x            (reverse=True only; forward is training-only)
+  dec(x, g=None) -> (o, o_mb, spec, phase)               o_mb is None for the single-band decoder
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .engine import Engine
+
+
+class NativeFlow(nn.Module):
+    """ResidualCouplingBlock.forward(reverse=True) (models.py:207-214) on the B200 library."""
+
+    def __init__(self, engine: Engine):
+        super().__init__()
+        self.engine = engine
+
+    @torch.no_grad()
+    def forward(self, x, x_mask, g=None, reverse=False):
+        if not reverse:
+            raise NotImplementedError("NativeFlow implements the inference direction only (reverse=True); "
+                                      "the forward direction is used by training / voice conversion")
+        return self.engine.flow_reverse(x, x_mask, g)
+
+
+class NativeDecoder(nn.Module):
+    """{iSTFT,Multiband_iSTFT,Multistream_iSTFT}_Generator.forward (models.py:278/344/430)."""
+
+    def __init__(self, engine: Engine, want_mb=True, want_spec=True):
+        super().__init__()
+        self.engine = engine
+        cfg = engine.cfg
+        # attributes callers read (inferz_test.ipynb cell 6)
+        self.gen_istft_n_fft = cfg["gen_istft_n_fft"]
+        self.gen_istft_hop_size = cfg["gen_istft_hop_size"]
+        self.subbands = cfg["subbands"]
+        self.want_mb = want_mb
+        self.want_spec = want_spec
+
+    @torch.no_grad()
+    def forward(self, x, g=None):
+        return self.engine.decode(x, g, want_mb=self.want_mb, want_spec=self.want_spec)
+
+    def remove_weight_norm(self):
+        """Weight-norm is folded at load time; nothing to do (reference: models.py:299/379/469)."""
+
+
+def patch_synthesizer(net_g, cfg, precision="bf16", device=0, flags=0):
+    """Replace net_g.flow and net_g.dec by the native path, using net_g's own weights."""
+    sd = {k: v for k, v in net_g.state_dict().items() if k.startswith(("dec.", "flow."))}
+    eng = Engine(cfg, sd, precision=precision, device=device, flags=flags)
+    net_g.flow = NativeFlow(eng)
+    net_g.dec = NativeDecoder(eng)
+    return eng

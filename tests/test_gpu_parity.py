@@ -1,0 +1,198 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference-minted golden vectors.
+
+Tolerances (BASELINE.json north_star): fp32 / TF32 paths within 1e-3 of peak amplitude (the CUDA-core fp32 path is
+held to 1e-4), bf16 path >= 40 dB waveform SNR.
+"""
+import pytest
+import torch
+
+import mbistft_oracle as orc
+from helpers import GOLDEN_CASES, load_case
+from mb_istft_vits_b200 import get_config, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(cfg, sd, prec, flags=0):
+    from mb_istft_vits_b200 import Engine
+    return Engine(cfg, sd, precision=prec, flags=flags)
+
+
+def _run(eng, t):
+    g = t.get("g")
+    g = g.cuda() if g is not None else None
+    z = eng.flow_reverse(t["z_p"].cuda(), t["mask"].cuda(), g)
+    wav, o_mb, spec, phase = eng.decode((t["z"] * t["mask"]).cuda(), g)
+    torch.cuda.synchronize()
+    cpu = lambda x: None if x is None else x.cpu()
+    return cpu(z), cpu(wav), cpu(o_mb), cpu(spec), cpu(phase)
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
+def test_fp32_path_matches_reference_golden(name):
+    cfg, sd, t, meta = load_case(name)
+    eng = _engine(cfg, sd, "fp32")
+    z, wav, o_mb, spec, phase = _run(eng, t)
+    assert (z - t["z"]).abs().max() < 1e-4
+    assert orc.max_abs_over_peak(wav, t["o"]) < 1e-4
+    assert orc.max_abs_over_peak(spec, t["spec"]) < 1e-4
+    assert (phase - t["phase"]).abs().max() < 1e-4
+    if "o_mb" in t:
+        assert orc.max_abs_over_peak(o_mb, t["o_mb"]) < 1e-4
+    else:
+        assert o_mb is None
+    assert float((z * (1 - t["mask"])).abs().max()) == 0.0
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["mini_mb", "mb", "mb_gscale", "ms", "istft", "ms_spk", "mb_resblock2", "mb_long"])
+def test_tf32_path_within_1e3_of_peak(name):
+    cfg, sd, t, meta = load_case(name)
+    eng = _engine(cfg, sd, "tf32")
+    z, wav, o_mb, spec, phase = _run(eng, t)
+    assert (z - t["z"]).abs().max() < 1e-3 * max(1.0, float(t["z"].abs().max()))
+    assert orc.max_abs_over_peak(wav, t["o"]) < 1e-3
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["mini_mb", "mb", "mb_gscale", "ms", "istft", "ms_spk", "mb_resblock2", "mb_long"])
+def test_bf16_path_snr_at_least_40db(name):
+    cfg, sd, t, meta = load_case(name)
+    eng = _engine(cfg, sd, "bf16")
+    z, wav, o_mb, spec, phase = _run(eng, t)
+    assert orc.snr_db(z, t["z"]) > 40.0
+    assert orc.snr_db(wav, t["o"]) > 40.0
+    eng.close()
+
+
+@pytest.mark.parametrize("prec", ["bf16", "tf32"])
+def test_tensor_core_conv_equals_cuda_core_conv_on_identical_operands(prec):
+    """Same packed operands through tcgen05 and through the CUDA-core kernel: only the fp32 accumulation order
+    differs, so the results agree to ~1e-5 of peak.  Also covers the per-tap staging mode."""
+    from mb_istft_vits_b200 import lib as L
+    cfg, sd, t, meta = load_case("mb")
+    ref = _run(_engine(cfg, sd, prec, L.FLAG_FORCE_SIMT), t)
+    for flags in (0, L.FLAG_TC_PER_TAP_LOADS):
+        got = _run(_engine(cfg, sd, prec, flags), t)
+        assert orc.max_abs_over_peak(got[1], ref[1]) < 2e-4, flags
+        assert (got[0] - ref[0]).abs().max() < 2e-4, flags
+
+
+@pytest.mark.parametrize("variant_case", ["mb", "ms", "istft"])
+@pytest.mark.parametrize("T", [1, 3, 17, 40])
+def test_fused_tail_kernel_vs_oracle_on_random_logits(variant_case, T):
+    """Head + inverse DFT + OLA envelope + synthesis FIR on arbitrary logits (edge tiles, T=1 included)."""
+    cfg, sd, _, _ = load_case(variant_case)
+    eng = _engine(cfg, sd, "fp32")
+    L = T
+    for u in cfg["upsample_rates"]:
+        L *= u
+    nch = (cfg["subbands"] if cfg["variant"] != "istft" else 1) * 18
+    gen = torch.Generator().manual_seed(T)
+    logits = torch.randn((2, nch, L + 1), generator=gen) * 1.5  # reference layout [B, C, F]
+    ref = orc.decoder_tail(sd, cfg, logits)
+    wav, o_mb, spec, phase = eng.tail(logits.transpose(1, 2).contiguous().cuda(), T)
+    torch.cuda.synchronize()
+    assert orc.max_abs_over_peak(wav.cpu(), ref[0]) < 2e-5
+    assert orc.max_abs_over_peak(spec.cpu(), ref[2]) < 2e-5
+    assert (phase.cpu() - ref[3]).abs().max() < 2e-5
+    if ref[1] is not None:
+        assert orc.max_abs_over_peak(o_mb.cpu(), ref[1]) < 2e-5
+    # fast-math variant used by the tf32/bf16 paths
+    eng2 = _engine(cfg, sd, "bf16")
+    wav2 = eng2.tail(logits.transpose(1, 2).contiguous().cuda(), T, want_mb=False, want_spec=False)[0]
+    assert orc.max_abs_over_peak(wav2.cpu(), ref[0]) < 5e-5
+
+
+def test_fused_flow_decode_equals_separate_calls_and_masks_padding():
+    cfg, sd, t, meta = load_case("ms_spk")
+    eng = _engine(cfg, sd, "fp32")
+    g = t["g"].cuda()
+    z, wav, o_mb, spec, phase = eng.flow_decode(t["z_p"].cuda(), t["mask"].cuda(), g, want_mb=True, want_spec=True)
+    torch.cuda.synchronize()
+    assert (z.cpu() - t["z"]).abs().max() < 1e-4
+    assert orc.max_abs_over_peak(wav.cpu(), t["o"]) < 1e-4
+    assert orc.max_abs_over_peak(o_mb.cpu(), t["o_mb"]) < 1e-4
+
+
+def test_linearity_free_property_full_size_tail():
+    """Size-independent property at BASELINE config-2 size (B=64, T=862): the tail of a batch equals the tail of
+    each utterance alone (utterance independence), and its output length is 256 samples per latent frame."""
+    cfg = get_config("ljs_mb_istft_vits")
+    sd = synth.make_state_dict(cfg, seed=1234)
+    eng = _engine(cfg, sd, "bf16")
+    B, T = 64, 862
+    L = 16 * T
+    gen = torch.Generator().manual_seed(0)
+    logits = (torch.randn((B, L + 1, 72), generator=gen) * 0.7).cuda()
+    wav = eng.tail(logits, T, want_mb=False, want_spec=False)[0]
+    assert wav.shape == (B, 1, 256 * T)
+    one = eng.tail(logits[5:6].contiguous(), T, want_mb=False, want_spec=False)[0]
+    torch.cuda.synchronize()
+    assert torch.equal(one[0], wav[5])
+    ref = orc.decoder_tail(sd, cfg, logits[5:6].cpu().transpose(1, 2).contiguous())[0]
+    assert orc.max_abs_over_peak(one.cpu(), ref) < 5e-5
+
+
+def test_full_size_decode_batch_independence_and_oracle_spot_check():
+    """BASELINE config 2 (ljs_mb, B=64, T=862) on the bf16 path: finite, right shape, every utterance equals the
+    same utterance decoded alone (no cross-batch leakage through TMA tiles), and one utterance is checked against
+    the CPU oracle at >= 40 dB."""
+    cfg = get_config("ljs_mb_istft_vits")
+    sd = synth.make_state_dict(cfg, seed=1234)
+    eng = _engine(cfg, sd, "bf16")
+    B, T = 64, 862
+    z, mask, _ = synth.make_latents(cfg, B, T, seed=1234)
+    wav = eng.decode(z.cuda(), want_mb=False, want_spec=False)[0]
+    torch.cuda.synchronize()
+    assert wav.shape == (B, 1, 256 * T) and bool(torch.isfinite(wav).all())
+    one = eng.decode(z[63:64].cuda(), want_mb=False, want_spec=False)[0]
+    torch.cuda.synchronize()
+    assert torch.equal(one[0], wav[63])
+    ref = orc.decode(sd, cfg, z[63:64])[0]
+    assert orc.snr_db(one.cpu(), ref) > 40.0
+
+
+def test_variable_length_batch_matches_reference_padding_semantics():
+    """Padded batches: the decoder is never given x_mask (models.py:358), so padded frames produce audio from the
+    conv biases; the CUDA path must reproduce exactly that on the padded tensor (SURVEY 8c trap 4)."""
+    cfg = get_config("ljs_mini_mb_istft_vits")
+    sd = synth.make_state_dict(cfg, seed=5)
+    z_p, mask, lens = synth.make_latents(cfg, 4, 70, seed=11, lengths=[70, 1, 33, 64])
+    z_ref, (o_ref, _, _, _) = orc.flow_decode(sd, cfg, z_p, mask)
+    eng = _engine(cfg, sd, "fp32")
+    z, wav, _, _, _ = eng.flow_decode(z_p.cuda(), mask.cuda())
+    torch.cuda.synchronize()
+    assert (z.cpu() - z_ref).abs().max() < 1e-4
+    assert orc.max_abs_over_peak(wav.cpu(), o_ref) < 1e-4
+
+
+def test_module_shims_have_the_reference_call_signatures():
+    """NativeFlow / NativeDecoder behind a SynthesizerTrn-shaped host: same call forms as models.py:730,734."""
+    from mb_istft_vits_b200 import Engine, NativeDecoder, NativeFlow
+    cfg, sd, t, meta = load_case("mb")
+    eng = Engine(cfg, sd, precision="fp32")
+    flow, dec = NativeFlow(eng), NativeDecoder(eng)
+    z_p, y_mask = t["z_p"].cuda(), t["mask"].cuda()
+    z = flow(z_p, y_mask, g=None, reverse=True)
+    o, o_mb, spec, phase = dec((z * y_mask)[:, :, :None], g=None)
+    assert orc.max_abs_over_peak(o.cpu(), t["o"]) < 1e-4
+    assert o_mb.shape == t["o_mb"].shape and spec.shape == t["spec"].shape and phase.shape == t["phase"].shape
+    with pytest.raises(NotImplementedError):
+        flow(z_p, y_mask, reverse=False)
+    assert dec.gen_istft_n_fft == 16 and dec.gen_istft_hop_size == 4 and dec.subbands == 4
+    dec.remove_weight_norm()
+
+
+def test_errors_are_loud():
+    from mb_istft_vits_b200 import Engine
+    from mb_istft_vits_b200.lib import MbvError
+    cfg, sd, t, meta = load_case("mb")
+    bad = dict(sd)
+    del bad["dec.conv_pre.bias"]
+    with pytest.raises(MbvError):
+        Engine(cfg, bad, precision="fp32")
+    cfg2 = dict(cfg)
+    cfg2["gen_istft_n_fft"] = 32
+    with pytest.raises(MbvError):
+        Engine(cfg2, sd, precision="fp32")
