@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the MB-iSTFT-VITS waveform hot path (flow reverse + iSTFT decoder) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--precision bf16|tf32|fp32]
+
+Workload (BASELINE.json configs[1]): ljs_mb_istft_vits, B = 64 utterances x T = 862 latent frames (10.008 s at
+22 050 Hz) per GPU, synthetic latents, seeded random-init weights.  A "step" is one pass of the hot path over
+that batch: z = flow(z_p, mask, reverse=True); wav = dec(z * mask)  (models.py:730-734) = 14 123 008 samples.
+For N > 1 (launched under torchrun, one rank per GPU) every rank runs its own 64-utterance shard -- utterances are
+independent, so there is no collective on the hot path -- and the whole-job value is N * samples / max-over-ranks time.
+
+One JSON line is printed by rank 0:
+  value       device-resident throughput (inputs already in HBM), CUDA events, max over ranks
+  e2e         the same metric through the public API (NativeFlow / NativeDecoder modules) with pinned HOST inputs
+              and a HOST copy of the waveform inside the timed region
+  roofline    the conv implicit-GEMM kernel (dominant): algorithmic FLOP/s vs the measured bf16 peak;
+              roofline_tail: the fused iSTFT/PQMF tail vs the measured HBM copy bandwidth
+  cpu_baseline the CPU oracle port (same torch ops as the reference) timed on this box's host cores (rank 0, N=1)
+
+--impl reference times that CPU oracle port as the reference arm (the reference is Python/PyTorch; its modules
+cannot travel to the GPU box, the oracle restates them with the same torch primitives -- see DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIG_NAME = "ljs_mb_istft_vits"
+B_PER_GPU = 64
+T_FRAMES = 862
+METRIC = "decoder audio samples/sec (flow-reverse + MB-iSTFT decoder, batch 64 x 10 s per GPU)"
+UNIT = "samples/s"
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tflops_burst=d["bf16_tflops"], tflops_sustained=d["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+def cpu_port_run(cfg, sd, B, T, reps, warmup, threads=None):
+    """The oracle port on the host cores: flow reverse + decode, all threads.  Returns best seconds per pass."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mbistft_oracle as orc
+    from mb_istft_vits_b200 import synth
+    n = threads or len(os.sched_getaffinity(0))
+    torch.set_num_threads(n)
+    z_p, mask, _ = synth.make_latents(cfg, B, T, seed=1234)
+    times = []
+    for i in range(warmup + reps):
+        t0 = time.perf_counter()
+        orc.flow_decode(sd, cfg, z_p, mask)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times, n
+
+
+def run_reference(args):
+    rank, local_rank, world = dist_env()
+    if rank != 0:
+        return
+    from mb_istft_vits_b200 import get_config, synth
+    cfg = get_config(CONFIG_NAME)
+    sd = synth.make_state_dict(cfg, seed=1234)
+    Bs = 4  # bounded sample: CPU throughput is batch-independent
+    times, cores = cpu_port_run(cfg, sd, Bs, T_FRAMES, max(1, args.steps), max(1, min(args.warmup, 2)))
+    mean = sum(times) / len(times)
+    samples = Bs * T_FRAMES * 256
+    v = samples / mean
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": mean * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{CONFIG_NAME} flow-reverse + decoder-from-z, CPU sample B={Bs} x T={T_FRAMES}",
+                   "sampling_rate": cfg["sampling_rate"]},
+        "rtf": mean / (samples / cfg["sampling_rate"]),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"oracle port (torch CPU ops of the reference), B={Bs} x T={T_FRAMES} per step"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_native(args):
+    import torch
+    rank, local_rank, world = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        dist = None
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", local_rank if world > 1 else 0)
+    from mb_istft_vits_b200 import Engine, NativeDecoder, NativeFlow, get_config, synth
+    cfg = get_config(CONFIG_NAME)
+    sd = synth.make_state_dict(cfg, seed=1234)
+    B, T = args.batch, args.frames
+    eng = Engine(cfg, sd, precision=args.precision, device=dev.index)
+    z_p_host, mask_host, _ = synth.make_latents(cfg, B, T, seed=1234 + rank)
+    z_p, mask = z_p_host.to(dev), mask_host.to(dev)
+    samples_per_step = B * T * 256
+    sr = cfg["sampling_rate"]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return eng.flow_decode(z_p, mask, want_z=False, want_mb=False, want_spec=False)
+
+    # ---------------- device-resident timing
+    for _ in range(max(3, args.warmup)):
+        step()
+    launches_per_step = eng.last_launch_count()
+    barrier()
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    eng.set_profiling(True)
+    eng.profile_read()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    prof = eng.profile_read()
+    eng.set_profiling(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t_max = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    ms_step = float(t_max.item()) / args.steps
+    value = world * samples_per_step / (ms_step * 1e-3)
+
+    # decoder-only (no flow) for the record
+    zz = (eng.flow_reverse(z_p, mask) * mask).contiguous()
+    for _ in range(2):
+        eng.decode(zz, want_mb=False, want_spec=False)
+    barrier()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    for _ in range(args.steps):
+        eng.decode(zz, want_mb=False, want_spec=False)
+    d1.record()
+    barrier()
+    dec_ms = d0.elapsed_time(d1) / args.steps
+
+    # ---------------- end-to-end through the module shims, host buffers in and out
+    flow, dec = NativeFlow(eng), NativeDecoder(eng, want_mb=False, want_spec=False)
+    zp_pin, mask_pin = z_p_host.pin_memory(), mask_host.pin_memory()
+    wav_pin = torch.empty((B, 1, 256 * T), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        zp_d = zp_pin.to(dev, non_blocking=True)
+        m_d = mask_pin.to(dev, non_blocking=True)
+        z = flow(zp_d, m_d, g=None, reverse=True)
+        o, _, _, _ = dec(z * m_d, g=None)
+        wav_pin.copy_(o, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    x0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    x1.record()
+    barrier()
+    e2e_t = torch.tensor([x0.elapsed_time(x1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_t.item()) / args.steps
+    e2e_value = world * samples_per_step / (e2e_ms * 1e-3)
+
+    # ---------------- fused tail alone (HBM roofline of that kernel): event-timed stand-alone launches
+    L = 16 * T
+    logits = torch.randn((B, L + 1, 72), device=dev) * 0.5
+    for _ in range(3):
+        eng.tail(logits, T, want_mb=False, want_spec=False)
+    torch.cuda.synchronize()
+    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0e.record()
+    for _ in range(10):
+        eng.tail(logits, T, want_mb=False, want_spec=False)
+    t1e.record()
+    torch.cuda.synchronize()
+    tail_ms = t0e.elapsed_time(t1e) / 10
+    del logits
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    flops_step = eng.decode_flops(B, T) + eng.flow_flops(B, T)
+    conv_ms, conv_n = prof["conv"]
+    tail_prof_ms, tail_n = prof["tail"]
+    conv_tflops = flops_step * args.steps / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None
+    tail_bytes = B * T * 5632.0  # 4608 B logits in + 1024 B waveform out per latent frame
+    prec_peak = peaks["tflops_sustained"] * (0.5 if args.precision == "tf32" else 1.0)
+    roofline = {
+        "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all %d launches per step)" % (conv_n // max(1, args.steps)),
+        "bound": "tensor", "achieved": conv_tflops, "peak": prec_peak, "unit": "TFLOP/s",
+        "frac": (conv_tflops / prec_peak) if conv_tflops else None, "traffic": None,
+        "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)"
+                       + (" x 0.5 for tf32" if args.precision == "tf32" else ""),
+        "flops_per_step": flops_step, "avg_launch_ms": conv_ms / conv_n if conv_n else None,
+        "share_of_step": conv_ms / (ms_total) if ms_total else None,
+    }
+    roofline_tail = {
+        "kernel": "tail_kernel (head + iSTFT + PQMF)", "bound": "hbm",
+        "achieved": tail_bytes / (tail_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+        "peak_source": peaks["source"] + " hbm_gbs (burst; kernel timed alone)", "ms": tail_ms,
+        "ms_inside_step": tail_prof_ms / tail_n if tail_n else None, "bytes_per_launch": tail_bytes,
+    }
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu:
+        Bs = 4
+        times, cores = cpu_port_run(cfg, sd, Bs, T, 3, 1)
+        best = min(times)
+        cpu_baseline = {"value": Bs * T * 256 / best, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"oracle port (torch CPU ops of the reference) on B={Bs} x T={T}, best of 3 after 1 warm-up",
+                        "ms": best * 1e3}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": f"{CONFIG_NAME} flow-reverse + decoder-from-z, B={B} x T={T} per GPU "
+                               f"({samples_per_step} samples = {samples_per_step / sr:.1f} s audio per step per GPU)",
+                   "sampling_rate": sr, "l2": "working set per step (~4 GB of activations) >> 126 MB L2; no explicit flush",
+                   "residual_stream": "fp32", "accumulate": "fp32"},
+        "rtf": ms_step * 1e-3 / (world * samples_per_step / sr),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(zp_pin.numel() * 4 + mask_pin.numel() * 4),
+                "d2h_bytes_per_step": int(wav_pin.numel() * 4)},
+        "gpu_launches": launches_per_step * args.steps,
+        "launches_per_step": launches_per_step,
+        "roofline": roofline, "roofline_tail": roofline_tail, "cpu_baseline": cpu_baseline,
+        "extras": {"decoder_only_ms": dec_ms, "decoder_only_samples_per_s": samples_per_step / (dec_ms * 1e-3),
+                   "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+                   "tflops_whole_step": flops_step / (ms_step * 1e-3) / 1e12},
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--frames", type=int, default=T_FRAMES)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

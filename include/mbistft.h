@@ -82,7 +82,7 @@ typedef struct {
 
 /* debug / tuning flags */
 #define MBV_FLAG_TC_PER_TAP_LOADS 1 /* tcgen05 conv: one TMA load per tap instead of a halo slab */
-#define MBV_FLAG_TC_BASE_OFFSET 2   /* tcgen05 conv: set the descriptor base_offset for unaligned tap rows */
+#define MBV_FLAG_FORCE_SIMT 4       /* run the CUDA-core conv on the tensor-core operand layout (cross-check) */
 
 /* An EFFECTIVE weight tensor (weight-norm already folded: w = g*v/||v||), fp32, contiguous,
  * in HOST memory, named as in the reference state-dict minus weight_g/weight_v, e.g.
@@ -135,6 +135,13 @@ int mbv_flow_decode(mbv_handle* h, const float* z_p, const float* y_mask, const 
 int mbv_last_launch_count(mbv_handle* h);
 double mbv_decode_flops(mbv_handle* h, int32_t B, int32_t T);
 double mbv_flow_flops(mbv_handle* h, int32_t B, int32_t T);
+
+/* Per-kernel device timing.  With profiling on, every launch of a compute call is bracketed by CUDA events on
+ * the caller's stream.  mbv_profile_read synchronises those events, adds the elapsed milliseconds and launch
+ * counts per kernel kind (0 = conv implicit-GEMM, 1 = fused tail, 2 = layout/GEMV helpers) into ms[3] / count[3],
+ * and clears the record. */
+int mbv_set_profiling(mbv_handle* h, int32_t on);
+int mbv_profile_read(mbv_handle* h, double* ms, int32_t* count);
 
 /* Stand-alone entry for the fused tail (head + iSTFT + sub-band synthesis) on caller-provided
  * logits [B, F, n_logit_channels] (channels-last, F = frames): used by the parity tests and the

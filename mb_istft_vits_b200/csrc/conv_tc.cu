@@ -149,7 +149,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t base
 }
 
 struct TcRt {  // runtime scalars the kernel needs beyond ConvArgs
-  int slab_rows, a_stage_bytes, b_stage_bytes, n_a_stages, n_b_stages, per_tap, base_offset_mode;
+  int slab_rows, a_stage_bytes, b_stage_bytes, n_a_stages, n_b_stages, per_tap;
   int m_tiles, n_tiles, total_tiles, tmem_cols;
 };
 
@@ -257,17 +257,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(BAR(iBF + sb), pb);
           tc_fence_after();
           const uint32_t b_addr = smem_u32(smB + (size_t)sb * rt.b_stage_bytes);
-          uint32_t a_addr, bo = 0;
-          if (rt.per_tap) {
-            a_addr = b_addr + (uint32_t)a_pt_off;
-          } else {
-            const int roff = tap * a.dil;  // row offset of this tap inside the slab
-            a_addr = a_base + (uint32_t)roff * TC_ROW_BYTES;
-            if (rt.base_offset_mode) bo = (uint32_t)(roff & 7);
-          }
+          // Tap offset = row offset into the slab.  The 128B swizzle is a function of the absolute shared-memory
+          // address bits (measured on B200: base_offset 0 is exact for any row offset, (row & 7) is wrong), so a
+          // descriptor that merely starts `roff` rows later addresses exactly the rows TMA wrote.
+          const uint32_t a_addr = rt.per_tap ? b_addr + (uint32_t)a_pt_off
+                                             : a_base + (uint32_t)(tap * a.dil) * TC_ROW_BYTES;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = make_smem_desc(a_addr + k * 32, bo);
+            const uint64_t ad = make_smem_desc(a_addr + k * 32, 0);
             const uint64_t bd = make_smem_desc(b_addr + k * 32, 0);
             tc_mma<(Op::kPrec == 2) ? 2 : 1>(tmem_d, ad, bd, idesc, accum);
             accum = 1;
@@ -357,7 +354,6 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
   const int NL = a.gate ? a.N_total / 2 : a.N_total;
   if (NL % cols_logical != 0) return "tcgen05 conv: N tile must divide the padded output channels";
   plan->per_tap = (flags & 1) ? 1 : 0;
-  plan->base_offset_mode = (flags & 2) ? 1 : 0;
   const int halo = (a.taps - 1) * a.dil;
   plan->slab_rows = plan->per_tap ? TC_M : TC_M + halo;
   if (plan->slab_rows > 256) return "tcgen05 conv: activation slab exceeds the 256-row TMA box limit";
@@ -423,7 +419,7 @@ cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStr
   TcRt rt;
   rt.slab_rows = p.slab_rows; rt.a_stage_bytes = p.a_stage_bytes; rt.b_stage_bytes = p.b_stage_bytes;
   rt.n_a_stages = p.n_a_stages; rt.n_b_stages = p.n_b_stages; rt.per_tap = p.per_tap;
-  rt.base_offset_mode = p.base_offset_mode; rt.m_tiles = p.m_tiles; rt.n_tiles = p.n_tiles;
+  rt.m_tiles = p.m_tiles; rt.n_tiles = p.n_tiles;
   rt.total_tiles = p.total_tiles; rt.tmem_cols = p.tmem_cols;
   if (prec == 2)
     conv_tc_kernel<OpBF16><<<p.grid, TC_THREADS, p.smem_bytes, st>>>(p.tmA, p.tmB, a, rt);

@@ -19,7 +19,6 @@ struct TcPlan {
   int n_a_stages;
   int n_b_stages;
   int per_tap;
-  int base_offset_mode;
   int m_tiles, n_tiles, total_tiles;
   int tmem_cols;
   int smem_bytes;

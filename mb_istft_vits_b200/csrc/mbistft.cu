@@ -20,7 +20,6 @@
 
 using namespace mbv;
 
-#define MBV_FLAG_FORCE_SIMT 4  // debug: run the CUDA-core conv on the tensor-core operand layout
 
 namespace {
 
@@ -100,6 +99,18 @@ struct mbv_handle {
   struct PlanKey { int B, T; void* ws; int kind; bool operator<(const PlanKey& o) const {
     if (B != o.B) return B < o.B; if (T != o.T) return T < o.T; if (ws != o.ws) return ws < o.ws; return kind < o.kind; } };
   std::map<PlanKey, std::vector<TcPlan>> plan_cache;
+
+  // per-launch device timing (mbv_set_profiling)
+  bool profiling = false;
+  struct ProfRec { int kind; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  cudaEvent_t get_event() {
+    if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
 };
 
 namespace {
@@ -379,6 +390,8 @@ extern "C" int mbv_create(const mbv_config* cfg, mbv_handle** out) {
 extern "C" void mbv_destroy(mbv_handle* h) {
   if (!h) return;
   for (void* p : h->dev_allocs) cudaFree(p);
+  for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   delete h;
 }
 
@@ -591,6 +604,17 @@ struct Ctx {
   int launches = 0;
 };
 
+// RAII bracket: two events around one launch when profiling is on
+struct ProfScope {
+  mbv_handle* h; cudaStream_t st; int kind; cudaEvent_t e0;
+  ProfScope(Ctx& cx, int kind_) : h(cx.h), st(cx.st), kind(kind_), e0(nullptr) {
+    if (h->profiling) { e0 = h->get_event(); cudaEventRecord(e0, st); }
+  }
+  ~ProfScope() {
+    if (e0) { cudaEvent_t e1 = h->get_event(); cudaEventRecord(e1, st); h->prof.push_back({kind, e0, e1}); }
+  }
+};
+
 int run_conv(Ctx& cx, const ConvLayer& L, const void* x, int B, int L_in, int L_out, const EpiParams& epi) {
   mbv_handle* h = cx.h;
   ConvArgs a;
@@ -600,6 +624,7 @@ int run_conv(Ctx& cx, const ConvLayer& L, const void* x, int B, int L_in, int L_
   for (int i = 0; i < kMaxPhases; ++i) a.shift0[i] = L.shift0[i];
   a.epi = epi;
   if (a.epi.bias == nullptr) { a.epi.bias = L.bias; a.epi.bias_bs = 0; }
+  ProfScope prof(cx, 0);
   if (h->prec == MBV_PREC_FP32 || (h->cfg.flags & MBV_FLAG_FORCE_SIMT)) {
     CUDA_TRY(h, launch_conv_simt(h->prec, a, cx.st));
   } else {
@@ -630,12 +655,16 @@ int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, co
   mbv_handle* h = cx.h;
   const mbv_config& c = h->cfg;
   const int Hp = h->Hp, NL = c.flow_layers;
-  CUDA_TRY(h, launch_pack_input(h->prec, z_p, nullptr, f.zop, f.z, B, h->Cz, T, h->Cz, cx.st));
+  {
+    ProfScope prof(cx, 2);
+    CUDA_TRY(h, launch_pack_input(h->prec, z_p, nullptr, f.zop, f.z, B, h->Cz, T, h->Cz, cx.st));
+  }
   cx.launches++;
   for (int f_i = 3; f_i >= 0; --f_i) {
     float* gc = nullptr;
     if (g) {
       gc = f.gcond + (size_t)f_i * B * NL * 2 * Hp;
+      ProfScope prof(cx, 2);
       CUDA_TRY(h, launch_cond_gemv(g, h->fl_cond_w[f_i], h->fl_cond_b[f_i], nullptr, gc, B, c.gin_channels, NL * 2 * Hp, NL * 2 * Hp, cx.st));
       cx.launches++;
     }
@@ -669,6 +698,7 @@ int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, co
     }
   }
   if (z_out) {
+    ProfScope prof(cx, 2);
     CUDA_TRY(h, launch_unpack_output(f.z, z_out, B, h->Cz, T, h->Cz, cx.st));
     cx.launches++;
   }
@@ -682,6 +712,7 @@ int run_tail(Ctx& cx, const float* logits, float* wav, float* o_mb, float* spec,
   ta.logits = logits; ta.wav = wav; ta.o_mb = o_mb; ta.spec = spec; ta.phase = phase;
   ta.B = B; ta.L = Lfr; ta.n_ch = h->n_logit; ta.variant = h->cfg.variant;
   memcpy(ta.coef, h->tail_coef, sizeof(ta.coef));
+  ProfScope prof(cx, 1);
   CUDA_TRY(h, launch_tail(ta, h->prec == MBV_PREC_FP32 ? 1 : 0, cx.st));
   cx.launches++;
   return MBV_OK;
@@ -695,6 +726,7 @@ int run_decode(Ctx& cx, const DecBufs& d, const float* z, const float* z_mask, c
   int rc;
   const void* zin = z_op_ready;
   if (!zin) {
+    ProfScope prof(cx, 2);
     CUDA_TRY(h, launch_pack_input(h->prec, z, z_mask, d.zin_op, nullptr, B, h->Cz, T, h->Cz, cx.st));
     cx.launches++;
     zin = d.zin_op;
@@ -721,6 +753,7 @@ int run_decode(Ctx& cx, const DecBufs& d, const float* z, const float* z_mask, c
         cond[j] = d.cond + ((size_t)(i * nk + j) * 2 + 0) * B * 512;
         bias2c[j] = d.cond + ((size_t)(i * nk + j) * 2 + 1) * B * 512;
         const ConvLayer& first_res = (c.resblock_type == 1) ? h->rb_c2[i][j][0] : h->rb_c1[i][j][0];
+        ProfScope prof(cx, 2);
         CUDA_TRY(h, launch_cond_gemv(g, h->rb_cond_w[i][j], h->rb_cond_b[i][j], nullptr, cond[j], B, c.gin_channels, C, C, cx.st));
         CUDA_TRY(h, launch_cond_gemv(g, h->rb_cond_w[i][j], h->rb_cond_b[i][j], first_res.bias, bias2c[j], B, c.gin_channels, C, C, cx.st));
         cx.launches += 2;
@@ -923,6 +956,26 @@ extern "C" int mbv_tail(mbv_handle* h, const float* logits, float* wav, float* o
 }
 
 extern "C" int mbv_last_launch_count(mbv_handle* h) { return h ? h->last_launches : 0; }
+
+extern "C" int mbv_set_profiling(mbv_handle* h, int32_t on) {
+  if (!h) return MBV_ERR_INVALID;
+  h->profiling = on != 0;
+  return MBV_OK;
+}
+
+extern "C" int mbv_profile_read(mbv_handle* h, double* ms, int32_t* count) {
+  if (!h || !ms || !count) return MBV_ERR_INVALID;
+  for (auto& r : h->prof) {
+    CUDA_TRY(h, cudaEventSynchronize(r.e1));
+    float t = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&t, r.e0, r.e1));
+    if (r.kind >= 0 && r.kind < 3) { ms[r.kind] += t; count[r.kind] += 1; }
+    h->ev_pool.push_back(r.e0);
+    h->ev_pool.push_back(r.e1);
+  }
+  h->prof.clear();
+  return MBV_OK;
+}
 
 extern "C" double mbv_decode_flops(mbv_handle* h, int32_t B, int32_t T) {
   if (!h || !h->weights_loaded) return 0.0;

@@ -177,6 +177,16 @@ class Engine:
                                       self._ptr(phase), B, T, self._stream()))
         return wav, o_mb, spec, phase
 
+    def set_profiling(self, on: bool):
+        self._check(self.lib.mbv_set_profiling(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        """-> {'conv': (ms, launches), 'tail': (...), 'other': (...)} accumulated since the last read."""
+        ms = (C.c_double * 3)()
+        cnt = (C.c_int32 * 3)()
+        self._check(self.lib.mbv_profile_read(self._h, ms, cnt))
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(("conv", "tail", "other"))}
+
     def last_launch_count(self):
         return int(self.lib.mbv_last_launch_count(self._h))
 

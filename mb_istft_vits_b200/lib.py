@@ -19,7 +19,6 @@ VARIANTS = {"istft": 0, "mb": 1, "ms": 2}
 PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2}
 
 FLAG_TC_PER_TAP_LOADS = 1
-FLAG_TC_BASE_OFFSET = 2
 FLAG_FORCE_SIMT = 4
 
 ERRORS = {0: "MBV_OK", -1: "MBV_ERR_INVALID", -2: "MBV_ERR_UNSUPPORTED", -3: "MBV_ERR_WEIGHTS",
@@ -28,7 +27,7 @@ ERRORS = {0: "MBV_OK", -1: "MBV_ERR_INVALID", -2: "MBV_ERR_UNSUPPORTED", -3: "MB
 # every symbol include/mbistft.h declares (tests check the .so exports all of them)
 SYMBOLS = ["mbv_abi_version", "mbv_create", "mbv_destroy", "mbv_load_weights", "mbv_workspace_bytes",
            "mbv_flow_reverse", "mbv_decode", "mbv_flow_decode", "mbv_last_launch_count", "mbv_decode_flops",
-           "mbv_flow_flops", "mbv_tail", "mbv_last_error"]
+           "mbv_flow_flops", "mbv_tail", "mbv_last_error", "mbv_set_profiling", "mbv_profile_read"]
 
 
 class MbvConfig(C.Structure):
@@ -84,6 +83,8 @@ def load():
     lib.mbv_decode_flops.restype = C.c_double
     lib.mbv_flow_flops.argtypes = [vp, i32, i32]
     lib.mbv_flow_flops.restype = C.c_double
+    lib.mbv_set_profiling.argtypes = [vp, i32]
+    lib.mbv_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     lib.mbv_last_error.argtypes = [vp]
     lib.mbv_last_error.restype = C.c_char_p
     if lib.mbv_abi_version() != MBV_ABI_VERSION:
