@@ -68,14 +68,21 @@ def test_bf16_path_snr_at_least_40db(name):
 @pytest.mark.parametrize("prec", ["bf16", "tf32"])
 def test_tensor_core_conv_equals_cuda_core_conv_on_identical_operands(prec):
     """Same packed operands through tcgen05 and through the CUDA-core kernel: only the fp32 accumulation order
-    differs, so the results agree to ~1e-5 of peak.  Also covers the per-tap staging mode."""
+    differs.  Per layer that is ~1e-6, but every layer re-rounds its output to the operand type, so an occasional
+    1-ulp flip (2^-8 for bf16, 2^-11 for tf32) propagates; end to end the two paths must still agree far better
+    than either agrees with the fp32 reference (bf16 >= 50 dB, tf32 >= 70 dB).  The halo-slab and the per-tap
+    staging modes must be bit-identical to each other (same MMA order)."""
     from mb_istft_vits_b200 import lib as L
     cfg, sd, t, meta = load_case("mb")
     ref = _run(_engine(cfg, sd, prec, L.FLAG_FORCE_SIMT), t)
+    floor = 50.0 if prec == "bf16" else 70.0
+    got = {}
     for flags in (0, L.FLAG_TC_PER_TAP_LOADS):
-        got = _run(_engine(cfg, sd, prec, flags), t)
-        assert orc.max_abs_over_peak(got[1], ref[1]) < 2e-4, flags
-        assert (got[0] - ref[0]).abs().max() < 2e-4, flags
+        got[flags] = _run(_engine(cfg, sd, prec, flags), t)
+        assert orc.snr_db(got[flags][1], ref[1]) > floor, flags
+        assert orc.snr_db(got[flags][0], ref[0]) > floor, flags
+    assert torch.equal(got[0][1], got[L.FLAG_TC_PER_TAP_LOADS][1])
+    assert torch.equal(got[0][0], got[L.FLAG_TC_PER_TAP_LOADS][0])
 
 
 @pytest.mark.parametrize("variant_case", ["mb", "ms", "istft"])
