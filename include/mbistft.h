@@ -81,7 +81,6 @@ typedef struct {
 } mbv_config;
 
 /* debug / tuning flags */
-#define MBV_FLAG_TC_PER_TAP_LOADS 1 /* tcgen05 conv: one TMA load per tap instead of a halo slab */
 #define MBV_FLAG_FORCE_SIMT 4       /* run the CUDA-core conv on the tensor-core operand layout (cross-check) */
 
 /* An EFFECTIVE weight tensor (weight-norm already folded: w = g*v/||v||), fp32, contiguous,

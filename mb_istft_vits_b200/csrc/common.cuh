@@ -88,7 +88,7 @@ enum EpiMode : int {
 
 struct EpiParams {
   int mode;
-  int n_valid;      // columns >= n_valid are never stored
+  int n_valid;      // logical output channels >= n_valid are never stored (packed rows are padded to 128)
   int ld;           // channel pitch (elements) of every output / residual buffer of this conv
   int rows_out;     // rows per utterance of the mapped outputs (act[], xout when mapped)
   int rows_res;     // rows per utterance of xin / xout / xs / mask
@@ -119,6 +119,11 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int b, int ro
                                                float* acc, float* acc2) {
   using T = typename Op::T;
   float tmp[W];
+  {
+    // packed weight rows are padded to a multiple of 128: skip chunks outside the destination's channels
+    const int c0 = (p.mode == EPI_RS && p.n_split > 0 && n0 >= p.n_split) ? n0 - p.n_split : n0;
+    if (c0 >= p.n_valid) return;
+  }
   // bias
   {
     const float* bp = p.bias + (size_t)b * p.bias_bs + n0;
@@ -259,13 +264,12 @@ struct ConvArgs {
   int L_in;           // rows per utterance of x
   int L_out;          // rows computed per utterance and phase
   int Cp_in;          // padded input channels (multiple of 64)
-  int N_total;        // padded output columns (rows of one weight tap)
-  int N_tile;         // accumulator columns per tile (gate: tanh half + sigmoid half)
+  int N_total;        // packed weight rows per tap (multiple of 128; gate: [tanh half | sigmoid half])
   int taps;
   int dil;            // row step between taps
   int n_phases;       // >1 for the polyphase transposed convolutions
   int shift0[kMaxPhases];  // row offset of tap 0 per phase
-  int gate;           // EPI_GATE: tile columns = [N_tile/2 tanh | N_tile/2 sigmoid]
+  int gate;           // EPI_GATE: two accumulators per tile (tanh rows, sigmoid rows N_total/2 further)
   EpiParams epi;
 };
 

@@ -1,19 +1,24 @@
 // conv_tc.cu -- implicit-GEMM Conv1d / polyphase ConvTranspose1d on the 5th-gen tensor cores (sm_100a).
 //
-//   D[time 128, N] (+)= sum_tap sum_kblock  A_tap[time 128, 64ch] * W_tap[N, 64ch]^T
+//   D[C_out 128, time N] (+)= sum_tap sum_kblock  W_tap[C_out 128, 64ch] * X_tap[time N, 64ch]^T        (N <= 256)
 //
-// * activations are channels-last, so BOTH operands are K-major: A = a 128-row time tile of the
-//   activation (rows shifted by the tap offset), B = one tap of the packed weight [N][C_in].
-// * TMA (cp.async.bulk.tensor, 128B swizzle) stages operands; per k-block ONE activation slab with the
-//   halo of all taps (128 + (taps-1)*dil rows) is loaded and every tap's MMA reads it through a
-//   row-offset shared-memory descriptor, so activations cross L2->SMEM once, not `taps` times.
-//   Out-of-range rows (utterance edges = the conv's zero padding) are zero-filled by TMA itself
-//   through a 3-D (C, time, utterance) tensor map.
-// * tcgen05.mma (cta_group::1, M=128, N<=256, kind::f16 bf16 or kind::tf32) accumulates in TMEM;
-//   two accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
-// * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
-//   (tcgen05.ld -> registers -> fused bias / residual / leaky-relu / gate / mask -> global).
-// * persistent: grid = min(#tiles, #SMs), static round-robin tile order.
+// * activations are channels-last, so BOTH operands are K-major: A = one tap of the packed weight (128 output
+//   channels x 64 input channels), B = an N-row time tile of the activation, rows shifted by the tap offset.
+//   Putting the output CHANNEL on the accumulator lane (M) means an epilogue warp's 32 threads own 32 consecutive
+//   channels of one time step: every global load / store of the fused epilogue is a fully coalesced 64-128 B
+//   access on the channels-last tensors, and per-channel constants (bias, conditioning) are registers.
+//   (v1 had time on M: each thread owned a row and every warp access touched 32 different lines -- the ncu
+//   summary in profiles/r01_ncu_full_v1_baseline.txt shows 32 sectors/request and an LSU-bound epilogue.)
+// * TMA (cp.async.bulk.tensor, 128B swizzle) stages operands; per k-block ONE activation slab with the halo of all
+//   taps (N + (taps-1)*dil rows) is loaded and every tap's MMA reads it through a row-offset shared-memory
+//   descriptor, so activations cross L2->SMEM once, not `taps` times.  Rows outside the utterance (= the conv's
+//   zero padding) are zero-filled by TMA through a 3-D (C, time, utterance) tensor map.
+// * tcgen05.mma (cta_group::1, M=128, N<=256, kind::f16 bf16 or kind::tf32) accumulates in TMEM; two accumulator
+//   stages let the epilogue of tile i overlap the MMAs of tile i+1.
+// * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue
+//   (tcgen05.ld -> registers -> fused bias / residual / leaky-relu / gate / mask -> coalesced global access).
+// * persistent: grid = min(#tiles, #SMs), static round-robin tile order (channel tile fastest so neighbouring CTAs
+//   share the activation slab in L2).
 //
 // Reference semantics implemented: F.conv1d 'same' (commons.py:14-15, modules.py:191-206,220-224),
 // F.conv_transpose1d as S polyphase branches (models.py:320-323), WN gate (commons.py:100-107).
@@ -26,9 +31,11 @@
 
 namespace mbv {
 
-constexpr int TC_M = 128;            // time rows per tile (UMMA M)
-constexpr int TC_THREADS = 192;      // 6 warps
+constexpr int TC_M = 128;            // output channels per tile (UMMA M)
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // producer + MMA + epilogue warps
 constexpr int TC_ROW_BYTES = 128;    // one swizzle row = 64 bf16 / 32 tf32 channels
+constexpr int TC_ACC_STRIDE = 256;   // TMEM columns per accumulator stage
 constexpr uint64_t TC_TIMEOUT_CYCLES = 4000000000ull;  // ~2 s: a stuck pipeline traps instead of hanging the box
 
 // ------------------------------------------------------------------------------------------------
@@ -70,9 +77,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -120,54 +124,205 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
         : "memory");
   }
 }
-// 32 lanes x 16 consecutive fp32 columns: thread i of the warp gets lane (base_lane + i)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base_lane + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart.
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
-//  base_offset [49,52), layout SWIZZLE_128B=2 [61,64).)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t base_offset) {
+//  base_offset [49,52) = 0, layout SWIZZLE_128B=2 [61,64).)
+// The swizzle is a function of the absolute shared-memory address bits (measured on B200: base_offset 0 is exact
+// for any 128-byte row offset into a 1024-aligned slab, (row & 7) is wrong), so a descriptor that merely starts
+// `r` rows later addresses exactly the rows TMA wrote there.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;
   d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)(base_offset & 7) << 49;
   d |= (uint64_t)2 << 61;
   return d;
 }
 
+template <typename Op> __device__ __forceinline__ void op_store1(typename Op::T* p, float v) { *p = op_round<Op>(v); }
+template <> __device__ __forceinline__ void op_store1<OpBF16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float fast_tanh(float x) {
+  // tanh(x) = 1 - 2 / (exp(2x) + 1); exact limits at +-inf, abs error ~1e-7 relative to the fp32 reference
+  const float e = __expf(2.f * x);
+  return 1.f - __fdividef(2.f, e + 1.f);
+}
+
 struct TcRt {  // runtime scalars the kernel needs beyond ConvArgs
-  int slab_rows, a_stage_bytes, b_stage_bytes, n_a_stages, n_b_stages, per_tap;
-  int m_tiles, n_tiles, total_tiles, tmem_cols;
+  int n_time;        // time columns per tile (UMMA N), multiple of 16, <= 256 (gate: <= 128)
+  int slab_rows;     // n_time + (taps-1)*dil
+  int box_rows;      // rows per TMA box of the slab
+  int n_boxes;       // 1 or 2
+  int slab_stage_bytes, w_stage_bytes, n_slab_stages, n_w_stages;
+  int t_tiles, c_tiles, total_tiles;
 };
+
+// Fused epilogue for one thread = one output channel `n` (weight row), 32 consecutive time steps.
+template <typename Op>
+__device__ __forceinline__ void tc_epilogue32(const EpiParams& p, int b, int n, int phase, int t_first, int t_end,
+                                              const float* acc, const float* acc2) {
+  using T = typename Op::T;
+  const int nt = t_end - t_first;  // valid columns in this chunk (1..32)
+  switch (p.mode) {
+    case EPI_ACT: {
+      const float bias = p.bias[(size_t)b * p.bias_bs + n];
+      float add[3] = {0.f, 0.f, 0.f};
+      for (int j = 0; j < p.n_act; ++j)
+        if (p.act_add[j]) add[j] = p.act_add[j][(size_t)b * p.act_add_bs + n];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i < nt) {
+          const int t = t_first + i;
+          float y = acc[i] + bias;
+          if (p.mask) y *= p.mask[(size_t)b * p.rows_res + t];
+          const size_t off = ((size_t)b * p.rows_out + (size_t)t * p.row_mul + p.row_add + phase) * p.ld + n;
+          if (p.xout) p.xout[off] = y;
+          for (int j = 0; j < p.n_act; ++j)
+            op_store1<Op>(reinterpret_cast<T*>(p.act[j]) + off, lrelu(y + add[j], p.slope));
+        }
+      }
+    } break;
+    case EPI_RES: {
+      const float bias = p.bias[(size_t)b * p.bias_bs + n];
+      const size_t base = ((size_t)b * p.rows_res + t_first) * p.ld + n;
+      float xv[32], sv[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) xv[i] = (i < nt) ? p.xin[base + (size_t)i * p.ld] : 0.f;
+      if (p.sum_mode == 2 || p.sum_mode == 3) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sv[i] = (i < nt) ? p.xs[base + (size_t)i * p.ld] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i < nt) {
+          const size_t roff = base + (size_t)i * p.ld;
+          float x = xv[i] + acc[i] + bias;
+          if (p.xout) p.xout[roff] = x;
+          if (p.sum_mode == 1) p.xs[roff] = x;
+          else if (p.sum_mode == 2) p.xs[roff] = sv[i] + x;
+          else if (p.sum_mode == 3) x = (sv[i] + x) * p.scale;
+          else if (p.sum_mode == 4) x *= p.scale;
+          if (p.n_act) {
+            const int mrow = (t_first + i) * p.row_mul + p.row_add + phase;
+            const float v = lrelu(x, p.slope);
+            T* dst = reinterpret_cast<T*>(p.act[0]);
+            op_store1<Op>(dst + ((size_t)b * p.rows_out + mrow) * p.ld + n, v);
+            if (mrow == p.dup_src) op_store1<Op>(dst + ((size_t)b * p.rows_out + p.dup_dst) * p.ld + n, v);
+          }
+        }
+      }
+    } break;
+    case EPI_F32: {
+      const float bias = p.bias[(size_t)b * p.bias_bs + n];
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nt) p.xout[((size_t)b * p.rows_out + t_first + i) * p.ld + n] = acc[i] + bias;
+    } break;
+    case EPI_GATE: {
+      float b1 = p.bias[(size_t)b * p.bias_bs + n], b2 = p.bias[(size_t)b * p.bias_bs + p.n_split + n];
+      if (p.add2) {
+        b1 += p.add2[(size_t)b * p.add2_bs + n];
+        b2 += p.add2[(size_t)b * p.add2_bs + p.n_split + n];
+      }
+      T* dst = reinterpret_cast<T*>(p.act[0]) + ((size_t)b * p.rows_out + t_first) * p.ld + n;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i < nt) {
+          const float tv = fast_tanh(acc[i] + b1);
+          const float sg = __fdividef(1.f, 1.f + __expf(-(acc2[i] + b2)));
+          op_store1<Op>(dst + (size_t)i * p.ld, tv * sg);
+        }
+      }
+    } break;
+    case EPI_RS: {
+      const float bias = p.bias[(size_t)b * p.bias_bs + n];
+      const bool res_half = (p.n_split > 0 && n < p.n_split);
+      const int c = res_half ? n : n - p.n_split;
+      const size_t base = ((size_t)b * p.rows_res + t_first) * p.ld + c;
+      const float* mp = p.mask + (size_t)b * p.rows_res + t_first;
+      float xv[32];
+      if (res_half) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xv[i] = (i < nt) ? p.xin[base + (size_t)i * p.ld] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i < nt) {
+            const float x = (xv[i] + acc[i] + bias) * mp[i];
+            p.xout[base + (size_t)i * p.ld] = x;
+            op_store1<Op>(reinterpret_cast<T*>(p.act[0]) + base + (size_t)i * p.ld, x);
+          }
+        }
+      } else {
+        if (!p.first) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) xv[i] = (i < nt) ? p.xs[base + (size_t)i * p.ld] : 0.f;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) xv[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i < nt) {
+            const float s = xv[i] + acc[i] + bias;
+            if (p.n_split > 0) p.xs[base + (size_t)i * p.ld] = s;
+            else op_store1<Op>(reinterpret_cast<T*>(p.act[0]) + base + (size_t)i * p.ld, s * mp[i]);
+          }
+        }
+      }
+    } break;
+    case EPI_POST: {
+      const float bias = p.bias[(size_t)b * p.bias_bs + n];
+      const size_t base = ((size_t)b * p.rows_res + t_first) * p.ld + p.ch_off + n;
+      const float* mp = p.mask + (size_t)b * p.rows_res + t_first;
+      float zv[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) zv[i] = (i < nt) ? p.xin[base + (size_t)i * p.ld] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i < nt) {
+          const float m = mp[i];
+          const float z = (zv[i] - (acc[i] + bias) * m) * m;
+          p.xout[base + (size_t)i * p.ld] = z;
+          op_store1<Op>(reinterpret_cast<T*>(p.act[0]) + base + (size_t)i * p.ld, z);
+        }
+      }
+    } break;
+    default: break;
+  }
+}
 
 template <typename Op>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                const ConvArgs a, const TcRt rt) {
   using T = typename Op::T;
   constexpr int KB = TC_ROW_BYTES / (int)sizeof(T);  // channels per k-block
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [A stages][B stages][barriers][tmem ptr]; dynamic smem base is 1024-aligned by the launch
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smA = smem;
-  uint8_t* smB = smA + (size_t)rt.n_a_stages * rt.a_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + (size_t)rt.n_b_stages * rt.b_stage_bytes);
-  // barrier indices
-  const int iAF = 0, iAE = iAF + rt.n_a_stages, iBF = iAE + rt.n_a_stages, iBE = iBF + rt.n_b_stages;
-  const int iCF = iBE + rt.n_b_stages, iCE = iCF + 2, nBars = iCE + 2;
+  uint8_t* smX = smem;                                                   // activation slabs
+  uint8_t* smW = smX + (size_t)rt.n_slab_stages * rt.slab_stage_bytes;   // weight tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smW + (size_t)rt.n_w_stages * rt.w_stage_bytes);
+  const int iXF = 0, iXE = iXF + rt.n_slab_stages, iWF = iXE + rt.n_slab_stages, iWE = iWF + rt.n_w_stages;
+  const int iCF = iWE + rt.n_w_stages, iCE = iCF + 2, nBars = iCE + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + nBars);
 
   const int warp = threadIdx.x >> 5;
@@ -176,132 +331,126 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int i = 0; i < rt.n_a_stages; ++i) { mbar_init(BAR(iAF + i), 1); mbar_init(BAR(iAE + i), 1); }
-    for (int i = 0; i < rt.n_b_stages; ++i) { mbar_init(BAR(iBF + i), 1); mbar_init(BAR(iBE + i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(iCF + i), 1); mbar_init(BAR(iCE + i), 4); }
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    for (int i = 0; i < rt.n_slab_stages; ++i) { mbar_init(BAR(iXF + i), 1); mbar_init(BAR(iXE + i), 1); }
+    for (int i = 0; i < rt.n_w_stages; ++i) { mbar_init(BAR(iWF + i), 1); mbar_init(BAR(iWE + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(iCF + i), 1); mbar_init(BAR(iCE + i), TC_EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), (uint32_t)rt.tmem_cols);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), 512u);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int kblocks = a.Cp_in / KB;
-  const int box_n = a.gate ? a.N_tile / 2 : a.N_tile;     // weight rows per TMA box
-  const int cols_logical = a.gate ? a.N_tile / 2 : a.N_tile;  // logical output columns per tile
-  const uint32_t a_box_bytes = (uint32_t)rt.slab_rows * TC_ROW_BYTES;
-  const uint32_t b_box_bytes = (uint32_t)a.N_tile * TC_ROW_BYTES;
-  const int a_pt_off = (int)b_box_bytes;  // per-tap mode: the A tile sits after the weights in a B stage
+  const int n_logical = a.gate ? a.N_total / 2 : a.N_total;  // weight rows of one half
+  const uint32_t slab_bytes = (uint32_t)rt.n_boxes * rt.box_rows * TC_ROW_BYTES;
+  const uint32_t w_tile_bytes = TC_M * TC_ROW_BYTES;
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
-    int sa = 0, sb = 0;
-    uint32_t pa = 0, pb = 0;
+    int sx = 0, sw = 0;
+    uint32_t px = 0, pw = 0;
     for (int tile = blockIdx.x; tile < rt.total_tiles; tile += gridDim.x) {
       int rest = tile;
-      const int nt = rest % rt.n_tiles; rest /= rt.n_tiles;
+      const int ct = rest % rt.c_tiles; rest /= rt.c_tiles;
       const int phase = rest % a.n_phases; rest /= a.n_phases;
-      const int mt = rest % rt.m_tiles;
-      const int b = rest / rt.m_tiles;
-      const int t0 = mt * TC_M;
-      const int n0 = nt * cols_logical;
-      const int wrow0 = phase * a.taps * a.N_total;
+      const int tt = rest % rt.t_tiles;
+      const int b = rest / rt.t_tiles;
+      const int t0 = tt * rt.n_time;
+      const int wrow0 = phase * a.taps * a.N_total + ct * TC_M;
       for (int kb = 0; kb < kblocks; ++kb) {
-        if (!rt.per_tap) {
-          mbar_wait(BAR(iAE + sa), pa ^ 1);
-          mbar_expect_tx(BAR(iAF + sa), a_box_bytes);
-          tma_load_3d(smem_u32(smA + (size_t)sa * rt.a_stage_bytes), &tmA, BAR(iAF + sa), kb * KB,
-                      t0 + a.shift0[phase], b);
-          if (++sa == rt.n_a_stages) { sa = 0; pa ^= 1; }
-        }
+        mbar_wait(BAR(iXE + sx), px ^ 1);
+        mbar_expect_tx(BAR(iXF + sx), slab_bytes);
+        const uint32_t dst = smem_u32(smX + (size_t)sx * rt.slab_stage_bytes);
+        for (int i = 0; i < rt.n_boxes; ++i)
+          tma_load_3d(dst + (uint32_t)(i * rt.box_rows) * TC_ROW_BYTES, &tmX, BAR(iXF + sx), kb * KB,
+                      t0 + a.shift0[phase] + i * rt.box_rows, b);
+        if (++sx == rt.n_slab_stages) { sx = 0; px ^= 1; }
         for (int tap = 0; tap < a.taps; ++tap) {
-          mbar_wait(BAR(iBE + sb), pb ^ 1);
-          uint8_t* stage = smB + (size_t)sb * rt.b_stage_bytes;
-          mbar_expect_tx(BAR(iBF + sb), b_box_bytes + (rt.per_tap ? a_box_bytes : 0u));
-          if (rt.per_tap)
-            tma_load_3d(smem_u32(stage + a_pt_off), &tmA, BAR(iBF + sb), kb * KB,
-                        t0 + a.shift0[phase] + tap * a.dil, b);
-          const int wrow = wrow0 + tap * a.N_total + n0;
-          tma_load_2d(smem_u32(stage), &tmB, BAR(iBF + sb), kb * KB, wrow);
-          if (a.gate)
-            tma_load_2d(smem_u32(stage + (size_t)box_n * TC_ROW_BYTES), &tmB, BAR(iBF + sb), kb * KB,
-                        wrow + a.N_total / 2);
-          if (++sb == rt.n_b_stages) { sb = 0; pb ^= 1; }
+          mbar_wait(BAR(iWE + sw), pw ^ 1);
+          const uint32_t wdst = smem_u32(smW + (size_t)sw * rt.w_stage_bytes);
+          mbar_expect_tx(BAR(iWF + sw), a.gate ? 2 * w_tile_bytes : w_tile_bytes);
+          const int wrow = wrow0 + tap * a.N_total;
+          tma_load_2d(wdst, &tmW, BAR(iWF + sw), kb * KB, wrow);
+          if (a.gate) tma_load_2d(wdst + w_tile_bytes, &tmW, BAR(iWF + sw), kb * KB, wrow + n_logical);
+          if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
         }
       }
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
-    // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16 or tf32, K-major both, N, M=128
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16 or tf32, both K-major, N, M=128
     constexpr uint32_t fmt = (Op::kPrec == 2) ? 1u : 2u;
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a.N_tile >> 3) << 17) |
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(rt.n_time >> 3) << 17) |
                            ((uint32_t)(TC_M >> 4) << 24);
-    int sa = 0, sb = 0, sc = 0;
-    uint32_t pa = 0, pb = 0, pc = 0;
+    int sx = 0, sw = 0, sc = 0;
+    uint32_t px = 0, pw = 0, pc = 0;
     for (int tile = blockIdx.x; tile < rt.total_tiles; tile += gridDim.x) {
       mbar_wait(BAR(iCE + sc), pc ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(sc * a.N_tile);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(sc * TC_ACC_STRIDE);
       uint32_t accum = 0;
       for (int kb = 0; kb < kblocks; ++kb) {
-        uint32_t a_base = 0;
-        if (!rt.per_tap) {
-          mbar_wait(BAR(iAF + sa), pa);
-          tc_fence_after();
-          a_base = smem_u32(smA + (size_t)sa * rt.a_stage_bytes);
-        }
+        mbar_wait(BAR(iXF + sx), px);
+        tc_fence_after();
+        const uint32_t x_base = smem_u32(smX + (size_t)sx * rt.slab_stage_bytes);
         for (int tap = 0; tap < a.taps; ++tap) {
-          mbar_wait(BAR(iBF + sb), pb);
+          mbar_wait(BAR(iWF + sw), pw);
           tc_fence_after();
-          const uint32_t b_addr = smem_u32(smB + (size_t)sb * rt.b_stage_bytes);
-          // Tap offset = row offset into the slab.  The 128B swizzle is a function of the absolute shared-memory
-          // address bits (measured on B200: base_offset 0 is exact for any row offset, (row & 7) is wrong), so a
-          // descriptor that merely starts `roff` rows later addresses exactly the rows TMA wrote.
-          const uint32_t a_addr = rt.per_tap ? b_addr + (uint32_t)a_pt_off
-                                             : a_base + (uint32_t)(tap * a.dil) * TC_ROW_BYTES;
+          const uint32_t w_addr = smem_u32(smW + (size_t)sw * rt.w_stage_bytes);
+          const uint32_t x_addr = x_base + (uint32_t)(tap * a.dil) * TC_ROW_BYTES;  // tap = row offset into the slab
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = make_smem_desc(a_addr + k * 32, 0);
-            const uint64_t bd = make_smem_desc(b_addr + k * 32, 0);
-            tc_mma<(Op::kPrec == 2) ? 2 : 1>(tmem_d, ad, bd, idesc, accum);
+            const uint64_t xd = make_smem_desc(x_addr + k * 32);
+            tc_mma<(Op::kPrec == 2) ? 2 : 1>(tmem_d, make_smem_desc(w_addr + k * 32), xd, idesc, accum);
+            if (a.gate)
+              tc_mma<(Op::kPrec == 2) ? 2 : 1>(tmem_d + (uint32_t)rt.n_time, make_smem_desc(w_addr + w_tile_bytes + k * 32),
+                                               xd, idesc, accum);
             accum = 1;
           }
-          tc_commit(BAR(iBE + sb));
-          if (++sb == rt.n_b_stages) { sb = 0; pb ^= 1; }
+          tc_commit(BAR(iWE + sw));
+          if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
         }
-        if (!rt.per_tap) {
-          tc_commit(BAR(iAE + sa));
-          if (++sa == rt.n_a_stages) { sa = 0; pa ^= 1; }
-        }
+        tc_commit(BAR(iXE + sx));
+        if (++sx == rt.n_slab_stages) { sx = 0; px ^= 1; }
       }
       tc_commit(BAR(iCF + sc));
       if (++sc == 2) { sc = 0; pc ^= 1; }
     }
   } else if (warp >= 2) {
     // ===================== epilogue warps =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;       // which alternate 32-column chunks this warp takes
+    const int n_valid = a.epi.n_valid;
     int sc = 0;
     uint32_t pc = 0;
     for (int tile = blockIdx.x; tile < rt.total_tiles; tile += gridDim.x) {
       int rest = tile;
-      const int nt = rest % rt.n_tiles; rest /= rt.n_tiles;
+      const int ct = rest % rt.c_tiles; rest /= rt.c_tiles;
       const int phase = rest % a.n_phases; rest /= a.n_phases;
-      const int mt = rest % rt.m_tiles;
-      const int b = rest / rt.m_tiles;
-      const int row = mt * TC_M + q * 32 + lane;
-      const int n0 = nt * cols_logical;
+      const int tt = rest % rt.t_tiles;
+      const int b = rest / rt.t_tiles;
+      const int t0 = tt * rt.n_time;
+      const int n = ct * TC_M + q * 32 + lane;  // weight row = output channel of this thread
+      // which logical channel does this row write, and is it inside the destination buffer?
+      bool valid;
+      if (a.epi.mode == EPI_RS && a.epi.n_split > 0) valid = (n < a.epi.n_split ? n : n - a.epi.n_split) < n_valid;
+      else valid = n < n_valid;
+      const int t_lim = min(a.L_out, t0 + rt.n_time);
       mbar_wait(BAR(iCF + sc), pc);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc * a.N_tile);
-      for (int c = 0; c < cols_logical; c += 16) {
-        float acc[16], acc2[16];
-        tmem_ld16(taddr + (uint32_t)c, acc);
-        if (a.gate) tmem_ld16(taddr + (uint32_t)(cols_logical + c), acc2);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc * TC_ACC_STRIDE);
+      for (int c = half * 32; c < rt.n_time; c += 64) {
+        float acc[32], acc2[32];
+        tmem_ld32(taddr + (uint32_t)c, acc);
+        if (a.gate) tmem_ld32(taddr + (uint32_t)(rt.n_time + c), acc2);
         tmem_ld_wait();
-        if (row < a.L_out) epilogue_chunk<Op, 16>(a.epi, b, row, phase, n0 + c, acc, acc2);
+        const int t_first = t0 + c;
+        if (valid && t_first < t_lim)
+          tc_epilogue32<Op>(a.epi, b, n, phase, t_first, min(t_lim, t_first + 32), acc, acc2);
       }
       tc_fence_before();
       __syncwarp();
@@ -313,7 +462,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)rt.tmem_cols);
+    tmem_dealloc(tmem_base, 512u);
   }
 }
 
@@ -336,53 +485,40 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int next_pow2_cols(int c) {
-  int p = 32;
-  while (p < c) p <<= 1;
-  return p;
-}
-
 const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, TcPlan* plan) {
+  (void)flags;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return "cuTensorMapEncodeTiled entry point unavailable";
   const int esize = prec == 2 ? 2 : 4;
   const int KB = TC_ROW_BYTES / esize;
   if (a.Cp_in % 64 != 0) return "tcgen05 conv: padded input channels must be a multiple of 64";
-  if (a.N_tile % 16 != 0 || a.N_tile < 16 || a.N_tile > 256) return "tcgen05 conv: N tile must be 16..256, multiple of 16";
-  if (a.gate && (a.N_tile % 32 != 0)) return "tcgen05 conv: gate tile must be a multiple of 32";
-  const int cols_logical = a.gate ? a.N_tile / 2 : a.N_tile;
-  const int NL = a.gate ? a.N_total / 2 : a.N_total;
-  if (NL % cols_logical != 0) return "tcgen05 conv: N tile must divide the padded output channels";
-  plan->per_tap = (flags & 1) ? 1 : 0;
+  const int n_logical = a.gate ? a.N_total / 2 : a.N_total;
+  if (n_logical % TC_M != 0) return "tcgen05 conv: packed output channels must be a multiple of 128";
+  // time tile: as few tiles as a 256-column (gate: 128) accumulator allows, then shrunk to what the length needs
+  const int max_n = a.gate ? 128 : 256;
+  const int tiles = (a.L_out + max_n - 1) / max_n;
+  int n_time = ((a.L_out + tiles - 1) / tiles + 15) / 16 * 16;
+  if (n_time < 16) n_time = 16;
+  plan->n_time = n_time;
+  plan->t_tiles = (a.L_out + n_time - 1) / n_time;
+  plan->c_tiles = n_logical / TC_M;
+  plan->total_tiles = a.B * a.n_phases * plan->t_tiles * plan->c_tiles;
   const int halo = (a.taps - 1) * a.dil;
-  plan->slab_rows = plan->per_tap ? TC_M : TC_M + halo;
-  if (plan->slab_rows > 256) return "tcgen05 conv: activation slab exceeds the 256-row TMA box limit";
-  const int a_bytes = ((plan->slab_rows * TC_ROW_BYTES + 1023) / 1024) * 1024;
-  const int b_bytes = a.N_tile * TC_ROW_BYTES;
-  const int budget = 200 * 1024;
-  if (plan->per_tap) {
-    plan->a_stage_bytes = 0;
-    plan->n_a_stages = 0;
-    plan->b_stage_bytes = b_bytes + a_bytes;
-    plan->n_b_stages = budget / plan->b_stage_bytes;
-  } else {
-    plan->a_stage_bytes = a_bytes;
-    plan->n_a_stages = 3;
-    plan->b_stage_bytes = b_bytes;
-    plan->n_b_stages = (budget - 3 * a_bytes) / b_bytes;
-  }
-  if (plan->n_b_stages > 8) plan->n_b_stages = 8;
-  if (plan->n_b_stages < 2) return "tcgen05 conv: not enough shared memory for two weight stages";
-  plan->m_tiles = (a.L_out + TC_M - 1) / TC_M;
-  plan->n_tiles = NL / cols_logical;
-  plan->total_tiles = a.B * a.n_phases * plan->m_tiles * plan->n_tiles;
-  plan->tmem_cols = next_pow2_cols(2 * a.N_tile);
-  if (plan->tmem_cols > 512) return "tcgen05 conv: accumulators exceed TMEM";
-  const int nbars = 2 * plan->n_a_stages + 2 * plan->n_b_stages + 4;
-  plan->smem_bytes = 1024 + plan->n_a_stages * plan->a_stage_bytes + plan->n_b_stages * plan->b_stage_bytes +
+  plan->slab_rows = n_time + halo;
+  plan->n_boxes = plan->slab_rows > 256 ? 2 : 1;
+  plan->box_rows = ((plan->slab_rows + plan->n_boxes - 1) / plan->n_boxes + 7) / 8 * 8;
+  if (plan->box_rows > 256) return "tcgen05 conv: activation slab exceeds two 256-row TMA boxes";
+  plan->slab_stage_bytes = ((plan->n_boxes * plan->box_rows * TC_ROW_BYTES + 1023) / 1024) * 1024;
+  plan->w_stage_bytes = (a.gate ? 2 : 1) * TC_M * TC_ROW_BYTES;
+  const int budget = 212 * 1024;
+  plan->n_slab_stages = plan->slab_stage_bytes > 36 * 1024 ? 2 : 3;
+  plan->n_w_stages = (budget - plan->n_slab_stages * plan->slab_stage_bytes) / plan->w_stage_bytes;
+  if (plan->n_w_stages > 8) plan->n_w_stages = 8;
+  if (plan->n_w_stages < 2) return "tcgen05 conv: not enough shared memory for two weight stages";
+  const int nbars = 2 * plan->n_slab_stages + 2 * plan->n_w_stages + 4;
+  plan->smem_bytes = 1024 + plan->n_slab_stages * plan->slab_stage_bytes + plan->n_w_stages * plan->w_stage_bytes +
                      nbars * 8 + 16;
-  // keep one CTA per SM (each CTA wants up to all 512 TMEM columns)
-  if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;
+  if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;  // one CTA per SM: each CTA owns all 512 TMEM columns
   plan->grid = plan->total_tiles < num_sms ? plan->total_tiles : num_sms;
   if (plan->grid < 1) plan->grid = 1;
 
@@ -390,17 +526,16 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
   {
     cuuint64_t dims[3] = {(cuuint64_t)a.Cp_in, (cuuint64_t)a.L_in, (cuuint64_t)a.B};
     cuuint64_t strides[2] = {(cuuint64_t)a.Cp_in * esize, (cuuint64_t)a.L_in * a.Cp_in * esize};
-    cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)plan->slab_rows, 1};
+    cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)plan->box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&plan->tmA, dt, 3, const_cast<void*>(a.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed for the activation map";
   }
   {
-    const int box_n = a.gate ? a.N_tile / 2 : a.N_tile;
     cuuint64_t dims[2] = {(cuuint64_t)a.Cp_in, (cuuint64_t)a.n_phases * a.taps * a.N_total};
     cuuint64_t strides[1] = {(cuuint64_t)a.Cp_in * esize};
-    cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)box_n};
+    cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)TC_M};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&plan->tmB, dt, 2, const_cast<void*>(a.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -417,10 +552,10 @@ cudaError_t tc_set_attributes() {
 
 cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStream_t st) {
   TcRt rt;
-  rt.slab_rows = p.slab_rows; rt.a_stage_bytes = p.a_stage_bytes; rt.b_stage_bytes = p.b_stage_bytes;
-  rt.n_a_stages = p.n_a_stages; rt.n_b_stages = p.n_b_stages; rt.per_tap = p.per_tap;
-  rt.m_tiles = p.m_tiles; rt.n_tiles = p.n_tiles;
-  rt.total_tiles = p.total_tiles; rt.tmem_cols = p.tmem_cols;
+  rt.n_time = p.n_time; rt.slab_rows = p.slab_rows; rt.box_rows = p.box_rows; rt.n_boxes = p.n_boxes;
+  rt.slab_stage_bytes = p.slab_stage_bytes; rt.w_stage_bytes = p.w_stage_bytes;
+  rt.n_slab_stages = p.n_slab_stages; rt.n_w_stages = p.n_w_stages;
+  rt.t_tiles = p.t_tiles; rt.c_tiles = p.c_tiles; rt.total_tiles = p.total_tiles;
   if (prec == 2)
     conv_tc_kernel<OpBF16><<<p.grid, TC_THREADS, p.smem_bytes, st>>>(p.tmA, p.tmB, a, rt);
   else

@@ -11,16 +11,12 @@ cudaError_t launch_conv_simt(int prec, const ConvArgs& a, cudaStream_t st);
 
 // ---- conv_tc.cu
 struct TcPlan {
-  CUtensorMap tmA;      // 3-D (Cp_in, L_in, B), box (KB, slab_rows, 1), 128B swizzle
-  CUtensorMap tmB;      // 2-D (Cp_in, phases*taps*N_total), box (KB, box_n), 128B swizzle
-  int slab_rows;        // rows of the A box: 128 + (taps-1)*dil, or 128 with per-tap loads
-  int a_stage_bytes;
-  int b_stage_bytes;    // includes the per-tap A tile when per_tap
-  int n_a_stages;
-  int n_b_stages;
-  int per_tap;
-  int m_tiles, n_tiles, total_tiles;
-  int tmem_cols;
+  CUtensorMap tmA;      // activations: 3-D (Cp_in, L_in, B), box (KB, box_rows, 1), 128B swizzle
+  CUtensorMap tmB;      // weights: 2-D (Cp_in, phases*taps*N_total), box (KB, 128), 128B swizzle
+  int n_time;           // time columns per tile (UMMA N)
+  int slab_rows, box_rows, n_boxes;
+  int slab_stage_bytes, w_stage_bytes, n_slab_stages, n_w_stages;
+  int t_tiles, c_tiles, total_tiles;
   int smem_bytes;
   int grid;
 };

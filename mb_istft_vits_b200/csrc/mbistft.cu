@@ -46,7 +46,7 @@ inline float f32_to_tf32(float f) {
 
 struct ConvLayer {
   // geometry
-  int Cp_in = 0, N_total = 0, N_tile = 0, taps = 0, dil = 1, n_phases = 1, gate = 0;
+  int Cp_in = 0, N_total = 0, taps = 0, dil = 1, n_phases = 1, gate = 0;
   int shift0[kMaxPhases] = {0};
   int n_valid = 0;      // real output channels (unpadded)
   double macs_per_row = 0;  // real MACs per computed row (all phases), for FLOP accounting
@@ -74,7 +74,7 @@ struct mbv_handle {
 
   // derived geometry
   int Cz = 0;    // inter channels (192), must be a multiple of 64
-  int H = 0, Hp = 0;
+  int H = 0, Hp = 0, Hw = 0;  // flow hidden width: real, padded to 64 (activation pitch), padded to 128 (weight rows)
   int n_stage = 0;
   int stage_C[MBV_MAX_UPS] = {0};
   int n_logit = 0;  // subbands * 18
@@ -92,8 +92,8 @@ struct mbv_handle {
 
   // flow layers, indexed by coupling layer 0..3 (reference order)
   ConvLayer fl_pre[4], fl_post[4], fl_in[4][4], fl_rs[4][4];
-  float* fl_cond_w[4] = {nullptr};  // [L*2Hp][gin] packed (tanh | sigmoid per layer)
-  float* fl_cond_b[4] = {nullptr};  // [L*2Hp]
+  float* fl_cond_w[4] = {nullptr};  // [L*2Hw][gin] packed (tanh | sigmoid per layer)
+  float* fl_cond_b[4] = {nullptr};  // [L*2Hw]
 
   // tensor-map cache: valid while (B, T, ws) stay the same
   struct PlanKey { int B, T; void* ws; int kind; bool operator<(const PlanKey& o) const {
@@ -130,12 +130,6 @@ int fail(mbv_handle* h, int code, const char* fmt, ...) {
     cudaError_t _e = (expr);                                                                       \
     if (_e != cudaSuccess) return fail(h, MBV_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));  \
   } while (0)
-
-int pick_tile(int n, int maxc) {
-  for (int c = maxc; c >= 16; c -= 16)
-    if (n % c == 0) return c;
-  return 0;
-}
 
 // upload packed weights (host fp32, layout [phase][tap][N_total][Cp_in]) in the operand type
 int upload_weights(mbv_handle* h, ConvLayer& L, const std::vector<float>& packed, const std::vector<float>& bias) {
@@ -204,22 +198,17 @@ int pack_conv1d(mbv_handle* h, const TensorMap& m, const std::string& prefix, in
     b = find_tensor(h, m, prefix + ".bias", 1, bshape);
     if (!b) return MBV_ERR_WEIGHTS;
   }
-  const int N = (int)out_map.size(), Cp = (int)in_map.size();
+  // packed rows: a multiple of 128 (one UMMA M tile); a gate conv passes [tanh half | sigmoid half], each padded
+  const int n_map = (int)out_map.size(), Cp = (int)in_map.size();
+  const int N = gate ? n_map : round_up(n_map, 128);
+  if (gate && (n_map % 256) != 0) return fail(h, MBV_ERR_INVALID, "%s: gate halves must be padded to 128", prefix.c_str());
   L->Cp_in = Cp; L->N_total = N; L->taps = K; L->dil = dil; L->n_phases = 1; L->gate = gate;
   L->shift0[0] = -dil * (K - 1) / 2;
   L->n_valid = O;
   L->macs_per_row = (double)O * I * K;
-  if (gate) {
-    const int cl = pick_tile(N / 2, 128);
-    if (!cl) return fail(h, MBV_ERR_UNSUPPORTED, "%s: gate width %d not tileable", prefix.c_str(), N / 2);
-    L->N_tile = 2 * cl;
-  } else {
-    L->N_tile = pick_tile(N, 256);
-    if (!L->N_tile) return fail(h, MBV_ERR_UNSUPPORTED, "%s: output width %d not tileable", prefix.c_str(), N);
-  }
   std::vector<float> packed((size_t)K * N * Cp, 0.f), bias(N, 0.f);
   for (int k = 0; k < K; ++k)
-    for (int n = 0; n < N; ++n) {
+    for (int n = 0; n < n_map; ++n) {
       const int o = out_map[n];
       if (o < 0) continue;
       float* dst = &packed[((size_t)k * N + n) * Cp];
@@ -229,7 +218,7 @@ int pack_conv1d(mbv_handle* h, const TensorMap& m, const std::string& prefix, in
       }
     }
   if (b)
-    for (int n = 0; n < N; ++n)
+    for (int n = 0; n < n_map; ++n)
       if (out_map[n] >= 0) bias[n] = b->data[out_map[n]];
   return upload_weights(h, *L, packed, bias);
 }
@@ -251,12 +240,10 @@ int pack_convT(mbv_handle* h, const TensorMap& m, const std::string& prefix, int
     return fail(h, MBV_ERR_UNSUPPORTED, "%s: upsampler kernel %d / stride %d not supported (need K %% S == 0, K-S even, S <= %d)",
                 prefix.c_str(), K, S, kMaxPhases);
   const int P = (K - S) / 2, TP = K / S;
-  const int Cp = round_up(I, 64), N = round_up(O, 16);
+  const int Cp = round_up(I, 64), N = round_up(O, 128);
   L->Cp_in = Cp; L->N_total = N; L->taps = TP; L->dil = 1; L->n_phases = S; L->gate = 0;
   L->n_valid = O;
   L->macs_per_row = (double)I * O * K;  // per input row, all S phases together
-  L->N_tile = pick_tile(N, 256);
-  if (!L->N_tile) return fail(h, MBV_ERR_UNSUPPORTED, "%s: output width %d not tileable", prefix.c_str(), N);
   std::vector<float> packed((size_t)S * TP * N * Cp, 0.f), bias(N, 0.f);
   for (int r = 0; r < S; ++r) {
     const int base = (r + P) / S, k0 = (r + P) % S;
@@ -351,6 +338,7 @@ extern "C" int mbv_create(const mbv_config* cfg, mbv_handle** out) {
   h->Cz = c.inter_channels;
   h->H = c.hidden_channels;
   h->Hp = round_up(c.hidden_channels, 64);
+  h->Hw = round_up(c.hidden_channels, 128);
   h->n_stage = c.n_ups;
   int ch = c.upsample_initial_channel;
   if (ch % 64 != 0 || ch > 1024) return fail(h, MBV_ERR_UNSUPPORTED, "upsample_initial_channel must be a multiple of 64 and <= 1024");
@@ -459,7 +447,7 @@ extern "C" int mbv_load_weights(mbv_handle* h, const mbv_tensor* tensors, int32_
       cin = C;
     }
     const char* post = c.variant == MBV_VARIANT_ISTFT ? "dec.conv_post" : "dec.subband_conv_post";
-    rc = pack_conv1d(h, m, post, h->n_logit, cin, 7, 1, iota_pad(h->n_logit, round_up(h->n_logit, 16)), iota_pad(cin, cin), true, 0, &h->conv_post);
+    rc = pack_conv1d(h, m, post, h->n_logit, cin, 7, 1, iota_pad(h->n_logit, h->n_logit), iota_pad(cin, cin), true, 0, &h->conv_post);
     if (rc) return rc;
     float hs[4][63];
     memset(hs, 0, sizeof(hs));
@@ -477,6 +465,7 @@ extern "C" int mbv_load_weights(mbv_handle* h, const mbv_tensor* tensors, int32_
   // ---------------- flow (Flips folded into pre/post)
   {
     const int half = h->Cz / 2, H = h->H, Hp = h->Hp, K = c.flow_kernel, NL = c.flow_layers;
+    const int Hw = h->Hw;  // weight rows per half, padded to the 128-row MMA tile
     for (int f = 0; f < 4; ++f) {
       // coupling layer f runs after (4 - f) flips: odd -> reads rev(z[half:]) and updates rev(z[:half])
       const bool odd = ((4 - f) & 1) != 0;
@@ -492,8 +481,8 @@ extern "C" int mbv_load_weights(mbv_handle* h, const mbv_tensor* tensors, int32_
       if (rc) return rc;
       std::vector<int> hin = iota_pad(H, Hp);
       for (int l = 0; l < NL; ++l) {
-        std::vector<int> gmap(2 * Hp, -1);
-        for (int o = 0; o < H; ++o) { gmap[o] = o; gmap[Hp + o] = H + o; }
+        std::vector<int> gmap(2 * Hw, -1);
+        for (int o = 0; o < H; ++o) { gmap[o] = o; gmap[Hw + o] = H + o; }
         snprintf(pfx, sizeof(pfx), "flow.flows.%d.enc.in_layers.%d", 2 * f, l);
         rc = pack_conv1d(h, m, pfx, 2 * H, H, K, 1, gmap, hin, true, 1, &h->fl_in[f][l]);
         if (rc) return rc;
@@ -513,10 +502,10 @@ extern "C" int mbv_load_weights(mbv_handle* h, const mbv_tensor* tensors, int32_
         const HostTensor* w = find_tensor(h, m, std::string(pfx) + ".weight", 3, ws);
         const HostTensor* b = w ? find_tensor(h, m, std::string(pfx) + ".bias", 1, bs) : nullptr;
         if (!w || !b) return MBV_ERR_WEIGHTS;
-        std::vector<float> pw((size_t)NL * 2 * Hp * gin, 0.f), pb((size_t)NL * 2 * Hp, 0.f);
+        std::vector<float> pw((size_t)NL * 2 * Hw * gin, 0.f), pb((size_t)NL * 2 * Hw, 0.f);
         for (int l = 0; l < NL; ++l)
           for (int o = 0; o < 2 * H; ++o) {
-            const int dst = l * 2 * Hp + (o < H ? o : Hp + (o - H));
+            const int dst = l * 2 * Hw + (o < H ? o : Hw + (o - H));
             const int src = l * 2 * H + o;
             memcpy(&pw[(size_t)dst * gin], &w->data[(size_t)src * gin], sizeof(float) * gin);
             pb[dst] = b->data[src];
@@ -591,7 +580,7 @@ void layout_flow(mbv_handle* h, Arena& A, int B, int T, FlowBufs* f) {
   f->acts = A.take(nh * es);
   f->skip = (float*)A.take(nh * 4);
   f->hout = A.take(nh * es);
-  f->gcond = (float*)A.take((size_t)4 * B * h->cfg.flow_layers * 2 * h->Hp * 4);
+  f->gcond = (float*)A.take((size_t)4 * B * h->cfg.flow_layers * 2 * h->Hw * 4);
 }
 
 // Launch context: counts launches, caches tensor maps
@@ -620,7 +609,7 @@ int run_conv(Ctx& cx, const ConvLayer& L, const void* x, int B, int L_in, int L_
   ConvArgs a;
   memset(&a, 0, sizeof(a));
   a.x = x; a.w = L.w; a.B = B; a.L_in = L_in; a.L_out = L_out; a.Cp_in = L.Cp_in; a.N_total = L.N_total;
-  a.N_tile = L.N_tile; a.taps = L.taps; a.dil = L.dil; a.n_phases = L.n_phases; a.gate = L.gate;
+  a.taps = L.taps; a.dil = L.dil; a.n_phases = L.n_phases; a.gate = L.gate;
   for (int i = 0; i < kMaxPhases; ++i) a.shift0[i] = L.shift0[i];
   a.epi = epi;
   if (a.epi.bias == nullptr) { a.epi.bias = L.bias; a.epi.bias_bs = 0; }
@@ -643,18 +632,20 @@ int run_conv(Ctx& cx, const ConvLayer& L, const void* x, int B, int L_in, int L_
   return MBV_OK;
 }
 
+// ld = channel pitch of the destination buffers; by default every channel of that pitch is written (pad channels
+// come out as exact zeros because their packed weight rows and biases are zero)
 EpiParams epi_base(int mode, int ld, int rows) {
   EpiParams e;
   memset(&e, 0, sizeof(e));
   e.mode = mode; e.ld = ld; e.rows_out = rows; e.rows_res = rows; e.row_mul = 1; e.row_add = 0;
-  e.dup_src = -1; e.dup_dst = 0; e.slope = 1.f; e.scale = 1.f; e.n_valid = 1 << 30;
+  e.dup_src = -1; e.dup_dst = 0; e.slope = 1.f; e.scale = 1.f; e.n_valid = ld;
   return e;
 }
 
 int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, const float* g, float* z_out, int B, int T) {
   mbv_handle* h = cx.h;
   const mbv_config& c = h->cfg;
-  const int Hp = h->Hp, NL = c.flow_layers;
+  const int Hp = h->Hp, Hw = h->Hw, NL = c.flow_layers;
   {
     ProfScope prof(cx, 2);
     CUDA_TRY(h, launch_pack_input(h->prec, z_p, nullptr, f.zop, f.z, B, h->Cz, T, h->Cz, cx.st));
@@ -663,9 +654,9 @@ int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, co
   for (int f_i = 3; f_i >= 0; --f_i) {
     float* gc = nullptr;
     if (g) {
-      gc = f.gcond + (size_t)f_i * B * NL * 2 * Hp;
+      gc = f.gcond + (size_t)f_i * B * NL * 2 * Hw;
       ProfScope prof(cx, 2);
-      CUDA_TRY(h, launch_cond_gemv(g, h->fl_cond_w[f_i], h->fl_cond_b[f_i], nullptr, gc, B, c.gin_channels, NL * 2 * Hp, NL * 2 * Hp, cx.st));
+      CUDA_TRY(h, launch_cond_gemv(g, h->fl_cond_w[f_i], h->fl_cond_b[f_i], nullptr, gc, B, c.gin_channels, NL * 2 * Hw, NL * 2 * Hw, cx.st));
       cx.launches++;
     }
     int rc;
@@ -677,14 +668,14 @@ int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, co
     for (int l = 0; l < NL; ++l) {
       {
         EpiParams e = epi_base(EPI_GATE, Hp, T);
-        e.n_split = Hp; e.act[0] = f.acts; e.n_act = 1;
-        if (gc) { e.add2 = gc + (size_t)l * 2 * Hp; e.add2_bs = NL * 2 * Hp; }
+        e.n_split = Hw; e.act[0] = f.acts; e.n_act = 1;
+        if (gc) { e.add2 = gc + (size_t)l * 2 * Hw; e.add2_bs = NL * 2 * Hw; }
         if ((rc = run_conv(cx, h->fl_in[f_i][l], f.hop, B, T, T, e))) return rc;
       }
       {
         EpiParams e = epi_base(EPI_RS, Hp, T);
         e.mask = mask; e.first = (l == 0); e.xs = f.skip;
-        if (l < NL - 1) { e.n_split = Hp; e.xin = f.h; e.xout = f.h; e.act[0] = f.hop; }
+        if (l < NL - 1) { e.n_split = Hw; e.xin = f.h; e.xout = f.h; e.act[0] = f.hop; }
         else { e.n_split = 0; e.act[0] = f.hout; }
         e.n_act = 1;
         if ((rc = run_conv(cx, h->fl_rs[f_i][l], f.acts, B, T, T, e))) return rc;
@@ -693,6 +684,7 @@ int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, co
     {  // x1 = (x1 - post(h) * mask) * mask
       EpiParams e = epi_base(EPI_POST, h->Cz, T);
       e.mask = mask; e.xin = f.z; e.xout = f.z; e.act[0] = f.zop; e.n_act = 1;
+      e.n_valid = h->Cz / 2;
       e.ch_off = ((4 - f_i) & 1) ? 0 : h->Cz / 2;
       if ((rc = run_conv(cx, h->fl_post[f_i], f.hout, B, T, T, e))) return rc;
     }

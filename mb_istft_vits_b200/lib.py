@@ -18,7 +18,6 @@ MAX_UPS, MAX_KERNELS, MAX_DILATIONS = 4, 4, 3
 VARIANTS = {"istft": 0, "mb": 1, "ms": 2}
 PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2}
 
-FLAG_TC_PER_TAP_LOADS = 1
 FLAG_FORCE_SIMT = 4
 
 ERRORS = {0: "MBV_OK", -1: "MBV_ERR_INVALID", -2: "MBV_ERR_UNSUPPORTED", -3: "MBV_ERR_WEIGHTS",

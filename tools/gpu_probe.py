@@ -11,8 +11,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 MODES = [
-    ("fp32", 0), ("bf16_simt", 4), ("bf16_pertap", 1), ("bf16_halo", 0),
-    ("tf32_simt", 4), ("tf32_pertap", 1), ("tf32_halo", 0),
+    ("fp32", 0), ("bf16_simt", 4), ("bf16_tc", 0), ("tf32_simt", 4), ("tf32_tc", 0),
 ]
 
 
