@@ -176,141 +176,221 @@ struct TcRt {  // runtime scalars the kernel needs beyond ConvArgs
   int t_tiles, c_tiles, total_tiles;
 };
 
-// Fused epilogue for one thread = one output channel `n` (weight row), 32 consecutive time steps.
-template <typename Op>
-__device__ __forceinline__ void tc_epilogue32(const EpiParams& p, int b, int n, int phase, int t_first, int t_end,
-                                              const float* acc, const float* acc2) {
+// ------------------------------------------------------------------------------------------------
+// Fused epilogues.  One thread = one output channel n (weight row) x 32 consecutive time steps held in registers.
+// MODE and the channel pitch are compile-time so that each kernel carries only its own epilogue and every row
+// offset (i * pitch) folds into the load/store immediate: no per-element address arithmetic, no branches.
+//   STEP > 0: compile-time row pitch in elements;  STEP == 0: runtime pitch `rstep`.
+//   FULL: all 32 time steps are inside the utterance (the common case), else the first `nt` are.
+// ------------------------------------------------------------------------------------------------
+#define MBV_EL(i) if (FULL || (i) < nt)
+
+template <typename Op, int STEP, bool FULL>
+__device__ __forceinline__ void epi_act(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
+                                        size_t rstep, const float* acc) {
   using T = typename Op::T;
-  const int nt = t_end - t_first;  // valid columns in this chunk (1..32)
-  switch (p.mode) {
-    case EPI_ACT: {
-      const float bias = p.bias[(size_t)b * p.bias_bs + n];
-      float add[3] = {0.f, 0.f, 0.f};
-      for (int j = 0; j < p.n_act; ++j)
-        if (p.act_add[j]) add[j] = p.act_add[j][(size_t)b * p.act_add_bs + n];
+  const size_t step = STEP > 0 ? (size_t)STEP : rstep;
+  const float bias = p.bias[(size_t)b * p.bias_bs + n];
+  const size_t off0 = ((size_t)b * p.rows_out + (size_t)t_first * p.row_mul + p.row_add + phase) * p.ld + n;
+  float y[32];
+  if (p.mask) {
+    const float* mp = p.mask + (size_t)b * p.rows_res + t_first;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (i < nt) {
-          const int t = t_first + i;
-          float y = acc[i] + bias;
-          if (p.mask) y *= p.mask[(size_t)b * p.rows_res + t];
-          const size_t off = ((size_t)b * p.rows_out + (size_t)t * p.row_mul + p.row_add + phase) * p.ld + n;
-          if (p.xout) p.xout[off] = y;
-          for (int j = 0; j < p.n_act; ++j)
-            op_store1<Op>(reinterpret_cast<T*>(p.act[j]) + off, lrelu(y + add[j], p.slope));
-        }
-      }
-    } break;
-    case EPI_RES: {
-      const float bias = p.bias[(size_t)b * p.bias_bs + n];
-      const size_t base = ((size_t)b * p.rows_res + t_first) * p.ld + n;
-      float xv[32], sv[32];
+    for (int i = 0; i < 32; ++i) { y[i] = acc[i] + bias; MBV_EL(i) y[i] *= mp[i]; }
+  } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) xv[i] = (i < nt) ? p.xin[base + (size_t)i * p.ld] : 0.f;
-      if (p.sum_mode == 2 || p.sum_mode == 3) {
+    for (int i = 0; i < 32; ++i) y[i] = acc[i] + bias;
+  }
+  if (p.xout) {
+    float* xo = p.xout + off0;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sv[i] = (i < nt) ? p.xs[base + (size_t)i * p.ld] : 0.f;
-      }
+    for (int i = 0; i < 32; ++i) MBV_EL(i) xo[i * step] = y[i];
+  }
+  const float slope = p.slope;
+  for (int j = 0; j < p.n_act; ++j) {
+    const float* addp = j == 0 ? p.act_add[0] : (j == 1 ? p.act_add[1] : p.act_add[2]);
+    void* actp = j == 0 ? p.act[0] : (j == 1 ? p.act[1] : p.act[2]);
+    const float add = addp ? addp[(size_t)b * p.act_add_bs + n] : 0.f;
+    T* dst = reinterpret_cast<T*>(actp) + off0;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (i < nt) {
-          const size_t roff = base + (size_t)i * p.ld;
-          float x = xv[i] + acc[i] + bias;
-          if (p.xout) p.xout[roff] = x;
-          if (p.sum_mode == 1) p.xs[roff] = x;
-          else if (p.sum_mode == 2) p.xs[roff] = sv[i] + x;
-          else if (p.sum_mode == 3) x = (sv[i] + x) * p.scale;
-          else if (p.sum_mode == 4) x *= p.scale;
-          if (p.n_act) {
-            const int mrow = (t_first + i) * p.row_mul + p.row_add + phase;
-            const float v = lrelu(x, p.slope);
-            T* dst = reinterpret_cast<T*>(p.act[0]);
-            op_store1<Op>(dst + ((size_t)b * p.rows_out + mrow) * p.ld + n, v);
-            if (mrow == p.dup_src) op_store1<Op>(dst + ((size_t)b * p.rows_out + p.dup_dst) * p.ld + n, v);
-          }
-        }
-      }
-    } break;
-    case EPI_F32: {
-      const float bias = p.bias[(size_t)b * p.bias_bs + n];
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < nt) p.xout[((size_t)b * p.rows_out + t_first + i) * p.ld + n] = acc[i] + bias;
-    } break;
-    case EPI_GATE: {
-      float b1 = p.bias[(size_t)b * p.bias_bs + n], b2 = p.bias[(size_t)b * p.bias_bs + p.n_split + n];
-      if (p.add2) {
-        b1 += p.add2[(size_t)b * p.add2_bs + n];
-        b2 += p.add2[(size_t)b * p.add2_bs + p.n_split + n];
-      }
-      T* dst = reinterpret_cast<T*>(p.act[0]) + ((size_t)b * p.rows_out + t_first) * p.ld + n;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (i < nt) {
-          const float tv = fast_tanh(acc[i] + b1);
-          const float sg = __fdividef(1.f, 1.f + __expf(-(acc2[i] + b2)));
-          op_store1<Op>(dst + (size_t)i * p.ld, tv * sg);
-        }
-      }
-    } break;
-    case EPI_RS: {
-      const float bias = p.bias[(size_t)b * p.bias_bs + n];
-      const bool res_half = (p.n_split > 0 && n < p.n_split);
-      const int c = res_half ? n : n - p.n_split;
-      const size_t base = ((size_t)b * p.rows_res + t_first) * p.ld + c;
-      const float* mp = p.mask + (size_t)b * p.rows_res + t_first;
-      float xv[32];
-      if (res_half) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) xv[i] = (i < nt) ? p.xin[base + (size_t)i * p.ld] : 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i < nt) {
-            const float x = (xv[i] + acc[i] + bias) * mp[i];
-            p.xout[base + (size_t)i * p.ld] = x;
-            op_store1<Op>(reinterpret_cast<T*>(p.act[0]) + base + (size_t)i * p.ld, x);
-          }
-        }
-      } else {
-        if (!p.first) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) xv[i] = (i < nt) ? p.xs[base + (size_t)i * p.ld] : 0.f;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) xv[i] = 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i < nt) {
-            const float s = xv[i] + acc[i] + bias;
-            if (p.n_split > 0) p.xs[base + (size_t)i * p.ld] = s;
-            else op_store1<Op>(reinterpret_cast<T*>(p.act[0]) + base + (size_t)i * p.ld, s * mp[i]);
-          }
-        }
-      }
-    } break;
-    case EPI_POST: {
-      const float bias = p.bias[(size_t)b * p.bias_bs + n];
-      const size_t base = ((size_t)b * p.rows_res + t_first) * p.ld + p.ch_off + n;
-      const float* mp = p.mask + (size_t)b * p.rows_res + t_first;
-      float zv[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) zv[i] = (i < nt) ? p.xin[base + (size_t)i * p.ld] : 0.f;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (i < nt) {
-          const float m = mp[i];
-          const float z = (zv[i] - (acc[i] + bias) * m) * m;
-          p.xout[base + (size_t)i * p.ld] = z;
-          op_store1<Op>(reinterpret_cast<T*>(p.act[0]) + base + (size_t)i * p.ld, z);
-        }
-      }
-    } break;
-    default: break;
+    for (int i = 0; i < 32; ++i) {
+      const float v = y[i] + add;
+      MBV_EL(i) op_store1<Op>(dst + i * step, fmaxf(v, v * slope));  // leaky-relu, slope in (0,1]
+    }
   }
 }
 
-template <typename Op>
+template <typename Op, int STEP, bool FULL>
+__device__ __forceinline__ void epi_res(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
+                                        size_t rstep, const float* acc) {
+  using T = typename Op::T;
+  const size_t step = STEP > 0 ? (size_t)STEP : rstep;
+  const float bias = p.bias[(size_t)b * p.bias_bs + n];
+  const size_t base = ((size_t)b * p.rows_res + t_first) * p.ld + n;
+  float x[32];
+  {
+    const float* xp = p.xin + base;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { x[i] = 0.f; MBV_EL(i) x[i] = xp[i * step]; }
+  }
+  const int sm = p.sum_mode;
+  if (sm == 2 || sm == 3) {
+    float sv[32];
+    const float* sp = p.xs + base;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { sv[i] = 0.f; MBV_EL(i) sv[i] = sp[i * step]; }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = (x[i] + acc[i] + bias) + sv[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = x[i] + acc[i] + bias;
+  }
+  if (p.xout) {
+    float* xo = p.xout + base;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) MBV_EL(i) xo[i * step] = x[i];
+  }
+  if (sm == 1 || sm == 2) {
+    float* so = p.xs + base;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) MBV_EL(i) so[i * step] = x[i];
+  }
+  if (p.n_act) {
+    const float slope = p.slope, scale = (sm >= 3) ? p.scale : 1.f;
+    T* dst = reinterpret_cast<T*>(p.act[0]) + ((size_t)b * p.rows_out + t_first + p.row_add) * p.ld + n;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float v = x[i] * scale;
+      MBV_EL(i) op_store1<Op>(dst + i * step, fmaxf(v, v * slope));
+    }
+    // ReflectionPad1d((1,0)) of the conv_post input: mapped row dup_src is also stored at row dup_dst
+    const int di = p.dup_src - p.row_add - t_first;
+    if (p.dup_src >= 0 && di >= 0 && di < nt) {
+      float v = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) if (i == di) v = x[i] * scale;
+      op_store1<Op>(reinterpret_cast<T*>(p.act[0]) + ((size_t)b * p.rows_out + p.dup_dst) * p.ld + n, fmaxf(v, v * slope));
+    }
+  }
+}
+
+template <typename Op, int STEP, bool FULL>
+__device__ __forceinline__ void epi_f32(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
+                                        size_t rstep, const float* acc) {
+  const size_t step = STEP > 0 ? (size_t)STEP : rstep;
+  const float bias = p.bias[(size_t)b * p.bias_bs + n];
+  float* o = p.xout + ((size_t)b * p.rows_out + t_first) * p.ld + n;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) MBV_EL(i) o[i * step] = acc[i] + bias;
+}
+
+template <typename Op, int STEP, bool FULL>
+__device__ __forceinline__ void epi_gate(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
+                                         size_t rstep, const float* acc, const float* acc2) {
+  using T = typename Op::T;
+  const size_t step = STEP > 0 ? (size_t)STEP : rstep;
+  float b1 = p.bias[(size_t)b * p.bias_bs + n], b2 = p.bias[(size_t)b * p.bias_bs + p.n_split + n];
+  if (p.add2) {
+    b1 += p.add2[(size_t)b * p.add2_bs + n];
+    b2 += p.add2[(size_t)b * p.add2_bs + p.n_split + n];
+  }
+  T* dst = reinterpret_cast<T*>(p.act[0]) + ((size_t)b * p.rows_out + t_first) * p.ld + n;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float tv = fast_tanh(acc[i] + b1);
+    const float sg = __fdividef(1.f, 1.f + __expf(-(acc2[i] + b2)));
+    MBV_EL(i) op_store1<Op>(dst + i * step, tv * sg);
+  }
+}
+
+template <typename Op, int STEP, bool FULL>
+__device__ __forceinline__ void epi_rs(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
+                                       size_t rstep, const float* acc) {
+  using T = typename Op::T;
+  const size_t step = STEP > 0 ? (size_t)STEP : rstep;
+  const float bias = p.bias[(size_t)b * p.bias_bs + n];
+  const bool res_half = (p.n_split > 0 && n < p.n_split);
+  const int c = res_half ? n : n - p.n_split;
+  const size_t base = ((size_t)b * p.rows_res + t_first) * p.ld + c;
+  const float* mp = p.mask + (size_t)b * p.rows_res + t_first;
+  float x[32];
+  if (res_half) {  // x = (x + rs) * mask -> fp32 stream + operand copy for the next in_layer
+    const float* xp = p.xin + base;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { x[i] = 0.f; MBV_EL(i) x[i] = (xp[i * step] + acc[i] + bias) * mp[i]; }
+    float* xo = p.xout + base;
+    T* dst = reinterpret_cast<T*>(p.act[0]) + base;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) MBV_EL(i) { xo[i * step] = x[i]; op_store1<Op>(dst + i * step, x[i]); }
+  } else {         // skip half: output += rs; the last layer applies the mask and emits the operand copy
+    if (!p.first) {
+      const float* sp = p.xs + base;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { x[i] = acc[i] + bias; MBV_EL(i) x[i] += sp[i * step]; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = acc[i] + bias;
+    }
+    if (p.n_split > 0) {
+      float* so = p.xs + base;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) MBV_EL(i) so[i * step] = x[i];
+    } else {
+      T* dst = reinterpret_cast<T*>(p.act[0]) + base;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) MBV_EL(i) op_store1<Op>(dst + i * step, x[i] * mp[i]);
+    }
+  }
+}
+
+template <typename Op, int STEP, bool FULL>
+__device__ __forceinline__ void epi_post(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
+                                         size_t rstep, const float* acc) {
+  using T = typename Op::T;
+  const size_t step = STEP > 0 ? (size_t)STEP : rstep;
+  const float bias = p.bias[(size_t)b * p.bias_bs + n];
+  const size_t base = ((size_t)b * p.rows_res + t_first) * p.ld + p.ch_off + n;
+  const float* mp = p.mask + (size_t)b * p.rows_res + t_first;
+  const float* zp = p.xin + base;
+  float* zo = p.xout + base;
+  T* dst = reinterpret_cast<T*>(p.act[0]) + base;
+  float z[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    z[i] = 0.f;
+    MBV_EL(i) { const float m = mp[i]; z[i] = (zp[i * step] - (acc[i] + bias) * m) * m; }
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) MBV_EL(i) { zo[i * step] = z[i]; op_store1<Op>(dst + i * step, z[i]); }
+}
+
+template <typename Op, int MODE, int STEP, bool FULL>
+__device__ __forceinline__ void epi_dispatch(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
+                                             size_t rstep, const float* acc, const float* acc2) {
+  if constexpr (MODE == EPI_ACT) epi_act<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc);
+  else if constexpr (MODE == EPI_RES) epi_res<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc);
+  else if constexpr (MODE == EPI_F32) epi_f32<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc);
+  else if constexpr (MODE == EPI_GATE) epi_gate<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc, acc2);
+  else if constexpr (MODE == EPI_RS) epi_rs<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc);
+  else epi_post<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc);
+}
+
+// LD: compile-time channel pitch of the destination buffers (0 = runtime).  The immediate-offset fast path also
+// needs row_mul == 1 (everything but the polyphase upsamplers).
+template <typename Op, int MODE, int LD>
+__device__ __forceinline__ void tc_epilogue32(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
+                                              const float* acc, const float* acc2) {
+  const size_t rstep = (size_t)p.row_mul * p.ld;
+  if (LD > 0 && p.row_mul == 1) {
+    if (nt == 32) epi_dispatch<Op, MODE, LD, true>(p, b, n, phase, t_first, nt, rstep, acc, acc2);
+    else epi_dispatch<Op, MODE, LD, false>(p, b, n, phase, t_first, nt, rstep, acc, acc2);
+  } else {
+    if (nt == 32) epi_dispatch<Op, MODE, 0, true>(p, b, n, phase, t_first, nt, rstep, acc, acc2);
+    else epi_dispatch<Op, MODE, 0, false>(p, b, n, phase, t_first, nt, rstep, acc, acc2);
+  }
+}
+
+template <typename Op, int MODE, int LD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                const ConvArgs a, const TcRt rt) {
@@ -437,7 +517,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const int n = ct * TC_M + q * 32 + lane;  // weight row = output channel of this thread
       // which logical channel does this row write, and is it inside the destination buffer?
       bool valid;
-      if (a.epi.mode == EPI_RS && a.epi.n_split > 0) valid = (n < a.epi.n_split ? n : n - a.epi.n_split) < n_valid;
+      if (MODE == EPI_RS && a.epi.n_split > 0) valid = (n < a.epi.n_split ? n : n - a.epi.n_split) < n_valid;
       else valid = n < n_valid;
       const int t_lim = min(a.L_out, t0 + rt.n_time);
       mbar_wait(BAR(iCF + sc), pc);
@@ -446,11 +526,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       for (int c = half * 32; c < rt.n_time; c += 64) {
         float acc[32], acc2[32];
         tmem_ld32(taddr + (uint32_t)c, acc);
-        if (a.gate) tmem_ld32(taddr + (uint32_t)(rt.n_time + c), acc2);
+        if constexpr (MODE == EPI_GATE) tmem_ld32(taddr + (uint32_t)(rt.n_time + c), acc2);
         tmem_ld_wait();
         const int t_first = t0 + c;
         if (valid && t_first < t_lim)
-          tc_epilogue32<Op>(a.epi, b, n, phase, t_first, min(t_lim, t_first + 32), acc, acc2);
+          tc_epilogue32<Op, MODE, LD>(a.epi, b, n, phase, t_first, min(t_lim - t_first, 32), acc, acc2);
       }
       tc_fence_before();
       __syncwarp();
@@ -544,10 +624,46 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
   return nullptr;
 }
 
+// kernel table: (mode, compile-time pitch) instantiations; pitch 0 = runtime
+template <typename Op, int MODE, int LD>
+static cudaError_t launch_one(const ConvArgs& a, const TcPlan& p, const TcRt& rt, cudaStream_t st, bool set_attr) {
+  auto k = conv_tc_kernel<Op, MODE, LD>;
+  if (set_attr) return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  k<<<p.grid, TC_THREADS, p.smem_bytes, st>>>(p.tmA, p.tmB, a, rt);
+  return cudaGetLastError();
+}
+
+template <typename Op>
+static cudaError_t dispatch(const ConvArgs& a, const TcPlan& p, const TcRt& rt, cudaStream_t st, bool set_attr, int mode,
+                            int ld) {
+#define MBV_CASE(M, L) if (mode == M && ld == L) return launch_one<Op, M, L>(a, p, rt, st, set_attr);
+  MBV_CASE(EPI_ACT, 128) MBV_CASE(EPI_ACT, 256) MBV_CASE(EPI_ACT, 192)
+  MBV_CASE(EPI_RES, 128) MBV_CASE(EPI_RES, 256)
+  MBV_CASE(EPI_GATE, 192) MBV_CASE(EPI_RS, 192) MBV_CASE(EPI_POST, 192)
+#undef MBV_CASE
+  switch (mode) {
+    case EPI_ACT: return launch_one<Op, EPI_ACT, 0>(a, p, rt, st, set_attr);
+    case EPI_RES: return launch_one<Op, EPI_RES, 0>(a, p, rt, st, set_attr);
+    case EPI_F32: return launch_one<Op, EPI_F32, 0>(a, p, rt, st, set_attr);
+    case EPI_GATE: return launch_one<Op, EPI_GATE, 0>(a, p, rt, st, set_attr);
+    case EPI_RS: return launch_one<Op, EPI_RS, 0>(a, p, rt, st, set_attr);
+    default: return launch_one<Op, EPI_POST, 0>(a, p, rt, st, set_attr);
+  }
+}
+
 cudaError_t tc_set_attributes() {
-  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<OpBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(conv_tc_kernel<OpTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  ConvArgs a{};
+  TcPlan p{};
+  TcRt rt{};
+  const int lds[] = {0, 128, 192, 256};
+  for (int mode = EPI_ACT; mode <= EPI_POST; ++mode)
+    for (int ld : lds) {
+      cudaError_t e = dispatch<OpBF16>(a, p, rt, nullptr, true, mode, ld);
+      if (e != cudaSuccess) return e;
+      e = dispatch<OpTF32>(a, p, rt, nullptr, true, mode, ld);
+      if (e != cudaSuccess) return e;
+    }
+  return cudaSuccess;
 }
 
 cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStream_t st) {
@@ -556,11 +672,8 @@ cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStr
   rt.slab_stage_bytes = p.slab_stage_bytes; rt.w_stage_bytes = p.w_stage_bytes;
   rt.n_slab_stages = p.n_slab_stages; rt.n_w_stages = p.n_w_stages;
   rt.t_tiles = p.t_tiles; rt.c_tiles = p.c_tiles; rt.total_tiles = p.total_tiles;
-  if (prec == 2)
-    conv_tc_kernel<OpBF16><<<p.grid, TC_THREADS, p.smem_bytes, st>>>(p.tmA, p.tmB, a, rt);
-  else
-    conv_tc_kernel<OpTF32><<<p.grid, TC_THREADS, p.smem_bytes, st>>>(p.tmA, p.tmB, a, rt);
-  return cudaGetLastError();
+  if (prec == 2) return dispatch<OpBF16>(a, p, rt, st, false, a.epi.mode, a.epi.ld);
+  return dispatch<OpTF32>(a, p, rt, st, false, a.epi.mode, a.epi.ld);
 }
 
 }  // namespace mbv

@@ -70,13 +70,13 @@ def test_tensor_core_conv_equals_cuda_core_conv_on_identical_operands(prec):
     """Same packed operands through tcgen05 and through the CUDA-core kernel: only the fp32 accumulation order
     differs.  Per layer that is ~1e-6, but every layer re-rounds its output to the operand type, so an occasional
     1-ulp flip (2^-8 for bf16, 2^-11 for tf32) propagates; end to end the two paths must still agree far better
-    than either agrees with the fp32 reference (bf16 >= 50 dB, tf32 >= 70 dB)."""
+    than either agrees with the fp32 reference (bf16 >= 50 dB, tf32 >= 65 dB)."""
     from mb_istft_vits_b200 import lib as L
     for case in ("mb", "ms_spk", "mini_mb"):
         cfg, sd, t, meta = load_case(case)
         ref = _run(_engine(cfg, sd, prec, L.FLAG_FORCE_SIMT), t)
         got = _run(_engine(cfg, sd, prec, 0), t)
-        floor = 50.0 if prec == "bf16" else 70.0
+        floor = 50.0 if prec == "bf16" else 65.0
         assert orc.snr_db(got[1], ref[1]) > floor, case
         assert orc.snr_db(got[0], ref[0]) > floor, case
 
