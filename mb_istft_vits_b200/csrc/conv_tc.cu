@@ -162,6 +162,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// descriptor halves: hi is constant (SBO 1024 B, version 1, SWIZZLE_128B); lo = start address >> 4 | LBO field 1
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
+
 template <typename Op> __device__ __forceinline__ void op_store1(typename Op::T* p, float v) { *p = op_round<Op>(v); }
 template <> __device__ __forceinline__ void op_store1<OpBF16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
@@ -433,8 +443,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const uint32_t slab_bytes = (uint32_t)rt.n_boxes * rt.box_rows * TC_ROW_BYTES;
   const uint32_t w_tile_bytes = TC_M * TC_ROW_BYTES;
 
-  if (warp == TC_WARP_TMA && lane == 0) {
+  if (warp == TC_WARP_TMA) {
     // ===================== TMA producer =====================
+    // The whole warp runs the (warp-uniform) loop so addresses and coordinates live in uniform registers; one
+    // elected lane issues the copies.
     int sx = 0, sw = 0;
     uint32_t px = 0, pw = 0;
     for (int tile = blockIdx.x; tile < rt.total_tiles; tile += gridDim.x) {
@@ -445,31 +457,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const int b = rest / rt.t_tiles;
       const int t0 = tt * rt.n_time;
       const int wrow0 = phase * a.taps * a.N_total + ct * TC_M;
+      const int xrow0 = t0 + a.shift0[phase];
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(BAR(iXE + sx), px ^ 1);
-        mbar_expect_tx(BAR(iXF + sx), slab_bytes);
-        const uint32_t dst = smem_u32(smX + (size_t)sx * rt.slab_stage_bytes);
-        for (int i = 0; i < rt.n_boxes; ++i)
-          tma_load_3d(dst + (uint32_t)(i * rt.box_rows) * TC_ROW_BYTES, &tmX, BAR(iXF + sx), kb * KB,
-                      t0 + a.shift0[phase] + i * rt.box_rows, b);
+        if (elect_one()) {
+          mbar_expect_tx(BAR(iXF + sx), slab_bytes);
+          const uint32_t dst = smem_u32(smX + (size_t)sx * rt.slab_stage_bytes);
+          for (int i = 0; i < rt.n_boxes; ++i)
+            tma_load_3d(dst + (uint32_t)(i * rt.box_rows) * TC_ROW_BYTES, &tmX, BAR(iXF + sx), kb * KB,
+                        xrow0 + i * rt.box_rows, b);
+        }
+        __syncwarp();
         if (++sx == rt.n_slab_stages) { sx = 0; px ^= 1; }
         for (int tap = 0; tap < a.taps; ++tap) {
           mbar_wait(BAR(iWE + sw), pw ^ 1);
-          const uint32_t wdst = smem_u32(smW + (size_t)sw * rt.w_stage_bytes);
-          mbar_expect_tx(BAR(iWF + sw), a.gate ? 2 * w_tile_bytes : w_tile_bytes);
-          const int wrow = wrow0 + tap * a.N_total;
-          tma_load_2d(wdst, &tmW, BAR(iWF + sw), kb * KB, wrow);
-          if (a.gate) tma_load_2d(wdst + w_tile_bytes, &tmW, BAR(iWF + sw), kb * KB, wrow + n_logical);
+          if (elect_one()) {
+            const uint32_t wdst = smem_u32(smW + (size_t)sw * rt.w_stage_bytes);
+            mbar_expect_tx(BAR(iWF + sw), MODE == EPI_GATE ? 2 * w_tile_bytes : w_tile_bytes);
+            const int wrow = wrow0 + tap * a.N_total;
+            tma_load_2d(wdst, &tmW, BAR(iWF + sw), kb * KB, wrow);
+            if constexpr (MODE == EPI_GATE) tma_load_2d(wdst + w_tile_bytes, &tmW, BAR(iWF + sw), kb * KB, wrow + n_logical);
+          }
+          __syncwarp();
           if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
         }
       }
     }
-  } else if (warp == TC_WARP_MMA && lane == 0) {
+  } else if (warp == TC_WARP_MMA) {
     // ===================== MMA issuer =====================
+    // Warp-uniform loop, one elected lane issues.  Per (tap, k-block): 4 MMAs whose descriptors differ only by
+    // +32 bytes in the low word -- the issue path must stay far below the 128 tensor-core cycles one MMA takes.
     // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16 or tf32, both K-major, N, M=128
     constexpr uint32_t fmt = (Op::kPrec == 2) ? 1u : 2u;
+    constexpr int KIND = (Op::kPrec == 2) ? 2 : 1;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(rt.n_time >> 3) << 17) |
                            ((uint32_t)(TC_M >> 4) << 24);
+    const uint32_t tap_step = (uint32_t)(a.dil * TC_ROW_BYTES) >> 4;  // descriptor-lo increment per tap
     int sx = 0, sw = 0, sc = 0;
     uint32_t px = 0, pw = 0, pc = 0;
     for (int tile = blockIdx.x; tile < rt.total_tiles; tile += gridDim.x) {
@@ -480,28 +503,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(BAR(iXF + sx), px);
         tc_fence_after();
-        const uint32_t x_base = smem_u32(smX + (size_t)sx * rt.slab_stage_bytes);
+        uint32_t x_lo = desc_lo(smem_u32(smX + (size_t)sx * rt.slab_stage_bytes));
         for (int tap = 0; tap < a.taps; ++tap) {
           mbar_wait(BAR(iWF + sw), pw);
           tc_fence_after();
-          const uint32_t w_addr = smem_u32(smW + (size_t)sw * rt.w_stage_bytes);
-          const uint32_t x_addr = x_base + (uint32_t)(tap * a.dil) * TC_ROW_BYTES;  // tap = row offset into the slab
+          const uint32_t w_lo = desc_lo(smem_u32(smW + (size_t)sw * rt.w_stage_bytes));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t xd = make_smem_desc(x_addr + k * 32);
-            tc_mma<(Op::kPrec == 2) ? 2 : 1>(tmem_d, make_smem_desc(w_addr + k * 32), xd, idesc, accum);
-            if (a.gate)
-              tc_mma<(Op::kPrec == 2) ? 2 : 1>(tmem_d + (uint32_t)rt.n_time, make_smem_desc(w_addr + w_tile_bytes + k * 32),
-                                               xd, idesc, accum);
-            accum = 1;
+            for (int k = 0; k < 4; ++k) {
+              tc_mma<KIND>(tmem_d, desc64(w_lo + 2 * k), desc64(x_lo + 2 * k), idesc, (k == 0) ? accum : 1u);
+              if constexpr (MODE == EPI_GATE)
+                tc_mma<KIND>(tmem_d + (uint32_t)rt.n_time, desc64(w_lo + (w_tile_bytes >> 4) + 2 * k), desc64(x_lo + 2 * k),
+                             idesc, (k == 0) ? accum : 1u);
+            }
+            tc_commit(BAR(iWE + sw));
           }
-          tc_commit(BAR(iWE + sw));
+          __syncwarp();
+          accum = 1;
+          x_lo += tap_step;  // next tap = `dil` rows further into the slab
           if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
         }
-        tc_commit(BAR(iXE + sx));
+        if (elect_one()) tc_commit(BAR(iXE + sx));
+        __syncwarp();
         if (++sx == rt.n_slab_stages) { sx = 0; px ^= 1; }
       }
-      tc_commit(BAR(iCF + sc));
+      if (elect_one()) tc_commit(BAR(iCF + sc));
+      __syncwarp();
       if (++sc == 2) { sc = 0; pc ^= 1; }
     }
   } else if (warp < TC_EPI_WARPS) {
