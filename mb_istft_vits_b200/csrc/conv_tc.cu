@@ -236,17 +236,14 @@ __device__ __forceinline__ void epi_act(const EpiParams& p, int b, int n, int ph
 
 template <typename Op, int STEP, bool FULL>
 __device__ __forceinline__ void epi_res(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
-                                        size_t rstep, const float* acc) {
+                                        size_t rstep, const float* acc, const float* xpre) {
   using T = typename Op::T;
   const size_t step = STEP > 0 ? (size_t)STEP : rstep;
   const float bias = p.bias[(size_t)b * p.bias_bs + n];
   const size_t base = ((size_t)b * p.rows_res + t_first) * p.ld + n;
   float x[32];
-  {
-    const float* xp = p.xin + base;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { x[i] = 0.f; MBV_EL(i) x[i] = xp[i * step]; }
-  }
+  for (int i = 0; i < 32; ++i) x[i] = xpre[i];  // xin, prefetched while the MMAs of this tile were running
   const int sm = p.sum_mode;
   if (sm == 2 || sm == 3) {
     float sv[32];
@@ -319,7 +316,7 @@ __device__ __forceinline__ void epi_gate(const EpiParams& p, int b, int n, int p
 
 template <typename Op, int STEP, bool FULL>
 __device__ __forceinline__ void epi_rs(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
-                                       size_t rstep, const float* acc) {
+                                       size_t rstep, const float* acc, const float* xpre) {
   using T = typename Op::T;
   const size_t step = STEP > 0 ? (size_t)STEP : rstep;
   const float bias = p.bias[(size_t)b * p.bias_bs + n];
@@ -329,22 +326,15 @@ __device__ __forceinline__ void epi_rs(const EpiParams& p, int b, int n, int pha
   const float* mp = p.mask + (size_t)b * p.rows_res + t_first;
   float x[32];
   if (res_half) {  // x = (x + rs) * mask -> fp32 stream + operand copy for the next in_layer
-    const float* xp = p.xin + base;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { x[i] = 0.f; MBV_EL(i) x[i] = (xp[i * step] + acc[i] + bias) * mp[i]; }
+    for (int i = 0; i < 32; ++i) { x[i] = 0.f; MBV_EL(i) x[i] = (xpre[i] + acc[i] + bias) * mp[i]; }
     float* xo = p.xout + base;
     T* dst = reinterpret_cast<T*>(p.act[0]) + base;
 #pragma unroll
     for (int i = 0; i < 32; ++i) MBV_EL(i) { xo[i * step] = x[i]; op_store1<Op>(dst + i * step, x[i]); }
   } else {         // skip half: output += rs; the last layer applies the mask and emits the operand copy
-    if (!p.first) {
-      const float* sp = p.xs + base;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { x[i] = acc[i] + bias; MBV_EL(i) x[i] += sp[i * step]; }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) x[i] = acc[i] + bias;
-    }
+    for (int i = 0; i < 32; ++i) x[i] = acc[i] + bias + xpre[i];  // xpre = running skip sum (zeros for the first layer)
     if (p.n_split > 0) {
       float* so = p.xs + base;
 #pragma unroll
@@ -359,20 +349,19 @@ __device__ __forceinline__ void epi_rs(const EpiParams& p, int b, int n, int pha
 
 template <typename Op, int STEP, bool FULL>
 __device__ __forceinline__ void epi_post(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
-                                         size_t rstep, const float* acc) {
+                                         size_t rstep, const float* acc, const float* xpre) {
   using T = typename Op::T;
   const size_t step = STEP > 0 ? (size_t)STEP : rstep;
   const float bias = p.bias[(size_t)b * p.bias_bs + n];
   const size_t base = ((size_t)b * p.rows_res + t_first) * p.ld + p.ch_off + n;
   const float* mp = p.mask + (size_t)b * p.rows_res + t_first;
-  const float* zp = p.xin + base;
   float* zo = p.xout + base;
   T* dst = reinterpret_cast<T*>(p.act[0]) + base;
   float z[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
     z[i] = 0.f;
-    MBV_EL(i) { const float m = mp[i]; z[i] = (zp[i * step] - (acc[i] + bias) * m) * m; }
+    MBV_EL(i) { const float m = mp[i]; z[i] = (xpre[i] - (acc[i] + bias) * m) * m; }
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) MBV_EL(i) { zo[i * step] = z[i]; op_store1<Op>(dst + i * step, z[i]); }
@@ -380,27 +369,53 @@ __device__ __forceinline__ void epi_post(const EpiParams& p, int b, int n, int p
 
 template <typename Op, int MODE, int STEP, bool FULL>
 __device__ __forceinline__ void epi_dispatch(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
-                                             size_t rstep, const float* acc, const float* acc2) {
+                                             size_t rstep, const float* acc, const float* acc2, const float* xpre) {
   if constexpr (MODE == EPI_ACT) epi_act<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc);
-  else if constexpr (MODE == EPI_RES) epi_res<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc);
+  else if constexpr (MODE == EPI_RES) epi_res<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
   else if constexpr (MODE == EPI_F32) epi_f32<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc);
   else if constexpr (MODE == EPI_GATE) epi_gate<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc, acc2);
-  else if constexpr (MODE == EPI_RS) epi_rs<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc);
-  else epi_post<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc);
+  else if constexpr (MODE == EPI_RS) epi_rs<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
+  else epi_post<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
+}
+
+// Residual-like input of a chunk (xin for EPI_RES / the residual half of EPI_RS, the running skip sum for the skip
+// half, z for EPI_POST).  It does not depend on the accumulator, so the epilogue warps issue these loads one chunk
+// AHEAD -- for the first chunk of a tile that is before the tile's MMAs have finished -- hiding the DRAM latency.
+template <int MODE, int LD>
+__device__ __forceinline__ void epi_prefetch(const EpiParams& p, int b, int n, int t_first, int nt, float* xpre) {
+  const size_t step = LD > 0 ? (size_t)LD : (size_t)p.ld;
+  const float* src = nullptr;
+  if constexpr (MODE == EPI_RES) {
+    src = p.xin + ((size_t)b * p.rows_res + t_first) * p.ld + n;
+  } else if constexpr (MODE == EPI_RS) {
+    const bool res_half = (p.n_split > 0 && n < p.n_split);
+    const int c = res_half ? n : n - p.n_split;
+    if (res_half) src = p.xin + ((size_t)b * p.rows_res + t_first) * p.ld + c;
+    else if (!p.first) src = p.xs + ((size_t)b * p.rows_res + t_first) * p.ld + c;
+  } else if constexpr (MODE == EPI_POST) {
+    src = p.xin + ((size_t)b * p.rows_res + t_first) * p.ld + p.ch_off + n;
+  }
+  if (src != nullptr && nt == 32) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) xpre[i] = src[i * step];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) xpre[i] = (src != nullptr && i < nt) ? src[i * step] : 0.f;
+  }
 }
 
 // LD: compile-time channel pitch of the destination buffers (0 = runtime).  The immediate-offset fast path also
 // needs row_mul == 1 (everything but the polyphase upsamplers).
 template <typename Op, int MODE, int LD>
 __device__ __forceinline__ void tc_epilogue32(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
-                                              const float* acc, const float* acc2) {
+                                              const float* acc, const float* acc2, const float* xpre) {
   const size_t rstep = (size_t)p.row_mul * p.ld;
   if (LD > 0 && p.row_mul == 1) {
-    if (nt == 32) epi_dispatch<Op, MODE, LD, true>(p, b, n, phase, t_first, nt, rstep, acc, acc2);
-    else epi_dispatch<Op, MODE, LD, false>(p, b, n, phase, t_first, nt, rstep, acc, acc2);
+    if (nt == 32) epi_dispatch<Op, MODE, LD, true>(p, b, n, phase, t_first, nt, rstep, acc, acc2, xpre);
+    else epi_dispatch<Op, MODE, LD, false>(p, b, n, phase, t_first, nt, rstep, acc, acc2, xpre);
   } else {
-    if (nt == 32) epi_dispatch<Op, MODE, 0, true>(p, b, n, phase, t_first, nt, rstep, acc, acc2);
-    else epi_dispatch<Op, MODE, 0, false>(p, b, n, phase, t_first, nt, rstep, acc, acc2);
+    if (nt == 32) epi_dispatch<Op, MODE, 0, true>(p, b, n, phase, t_first, nt, rstep, acc, acc2, xpre);
+    else epi_dispatch<Op, MODE, 0, false>(p, b, n, phase, t_first, nt, rstep, acc, acc2, xpre);
   }
 }
 
@@ -533,40 +548,71 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     }
   } else if (warp < TC_EPI_WARPS) {
     // ===================== epilogue warps =====================
+    // Work items of this warp: (tile, 32-column chunk c = half*32 + 64*j).  The residual-like input of item i+1 is
+    // loaded before item i is processed (software pipeline across chunks AND tiles).
+    constexpr bool kPrefetch = (MODE == EPI_RES || MODE == EPI_RS || MODE == EPI_POST);
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = warp >> 2;             // which alternate 32-column chunks this warp takes
     const int n_valid = a.epi.n_valid;
+    const int c_first = half * 32;
     int sc = 0;
     uint32_t pc = 0;
-    for (int tile = blockIdx.x; tile < rt.total_tiles; tile += gridDim.x) {
+
+    struct Item { int b, n, phase, t_first, nt; bool valid; };
+    auto make_item = [&](int tile, int c) {
+      Item it;
       int rest = tile;
       const int ct = rest % rt.c_tiles; rest /= rt.c_tiles;
-      const int phase = rest % a.n_phases; rest /= a.n_phases;
+      it.phase = rest % a.n_phases; rest /= a.n_phases;
       const int tt = rest % rt.t_tiles;
-      const int b = rest / rt.t_tiles;
+      it.b = rest / rt.t_tiles;
       const int t0 = tt * rt.n_time;
-      const int n = ct * TC_M + q * 32 + lane;  // weight row = output channel of this thread
+      it.n = ct * TC_M + q * 32 + lane;  // weight row = output channel of this thread
       // which logical channel does this row write, and is it inside the destination buffer?
-      bool valid;
-      if (MODE == EPI_RS && a.epi.n_split > 0) valid = (n < a.epi.n_split ? n : n - a.epi.n_split) < n_valid;
-      else valid = n < n_valid;
+      bool v;
+      if (MODE == EPI_RS && a.epi.n_split > 0) v = (it.n < a.epi.n_split ? it.n : it.n - a.epi.n_split) < n_valid;
+      else v = it.n < n_valid;
       const int t_lim = min(a.L_out, t0 + rt.n_time);
-      mbar_wait(BAR(iCF + sc), pc);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc * TC_ACC_STRIDE);
-      for (int c = half * 32; c < rt.n_time; c += 64) {
-        float acc[32], acc2[32];
-        tmem_ld32(taddr + (uint32_t)c, acc);
-        if constexpr (MODE == EPI_GATE) tmem_ld32(taddr + (uint32_t)(rt.n_time + c), acc2);
-        tmem_ld_wait();
-        const int t_first = t0 + c;
-        if (valid && t_first < t_lim)
-          tc_epilogue32<Op, MODE, LD>(a.epi, b, n, phase, t_first, min(t_lim - t_first, 32), acc, acc2);
+      it.t_first = t0 + c;
+      it.nt = min(t_lim - it.t_first, 32);
+      it.valid = v && c < rt.n_time && it.nt > 0;
+      return it;
+    };
+
+    int tile = blockIdx.x, c = c_first;
+    float xcur[32], xnext[32];
+    Item cur = make_item(tile, c);
+    if (kPrefetch && tile < rt.total_tiles && cur.valid) epi_prefetch<MODE, LD>(a.epi, cur.b, cur.n, cur.t_first, cur.nt, xcur);
+    while (tile < rt.total_tiles) {
+      if (c == c_first) {
+        mbar_wait(BAR(iCF + sc), pc);
+        tc_fence_after();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(iCE + sc));
-      if (++sc == 2) { sc = 0; pc ^= 1; }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc * TC_ACC_STRIDE);
+      float acc[32], acc2[32];
+      tmem_ld32(taddr + (uint32_t)c, acc);
+      if constexpr (MODE == EPI_GATE) tmem_ld32(taddr + (uint32_t)(rt.n_time + c), acc2);
+      // next work item
+      int ntile = tile, nc = c + 64;
+      if (nc >= rt.n_time) { ntile += gridDim.x; nc = c_first; }
+      Item nxt = cur;
+      if (ntile < rt.total_tiles) {
+        nxt = make_item(ntile, nc);
+        if (kPrefetch && nxt.valid) epi_prefetch<MODE, LD>(a.epi, nxt.b, nxt.n, nxt.t_first, nxt.nt, xnext);
+      }
+      tmem_ld_wait();
+      if (cur.valid) tc_epilogue32<Op, MODE, LD>(a.epi, cur.b, cur.n, cur.phase, cur.t_first, cur.nt, acc, acc2, xcur);
+      if (nc == c_first) {  // last chunk of this tile for this warp: hand the accumulator stage back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(iCE + sc));
+        if (++sc == 2) { sc = 0; pc ^= 1; }
+      }
+      if (kPrefetch) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xcur[i] = xnext[i];
+      }
+      cur = nxt; tile = ntile; c = nc;
     }
   }
   tc_fence_before();
