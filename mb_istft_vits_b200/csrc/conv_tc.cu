@@ -549,7 +549,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   } else if (warp < TC_EPI_WARPS) {
     // ===================== epilogue warps =====================
     // Work items of this warp: (tile, 32-column chunk c = half*32 + 64*j).  The residual-like input of item i+1 is
-    // loaded before item i is processed (software pipeline across chunks AND tiles).
+    // loaded before item i is processed (software pipeline across chunks AND tiles); tiles are decoded once.
     constexpr bool kPrefetch = (MODE == EPI_RES || MODE == EPI_RS || MODE == EPI_POST);
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = warp >> 2;             // which alternate 32-column chunks this warp takes
@@ -558,61 +558,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     int sc = 0;
     uint32_t pc = 0;
 
-    struct Item { int b, n, phase, t_first, nt; bool valid; };
-    auto make_item = [&](int tile, int c) {
-      Item it;
+    struct TileInfo { int b, n, phase, t0, t_lim; bool valid; };
+    auto decode = [&](int tile) {
+      TileInfo ti;
       int rest = tile;
       const int ct = rest % rt.c_tiles; rest /= rt.c_tiles;
-      it.phase = rest % a.n_phases; rest /= a.n_phases;
+      ti.phase = rest % a.n_phases; rest /= a.n_phases;
       const int tt = rest % rt.t_tiles;
-      it.b = rest / rt.t_tiles;
-      const int t0 = tt * rt.n_time;
-      it.n = ct * TC_M + q * 32 + lane;  // weight row = output channel of this thread
+      ti.b = rest / rt.t_tiles;
+      ti.t0 = tt * rt.n_time;
+      ti.n = ct * TC_M + q * 32 + lane;  // weight row = output channel of this thread
       // which logical channel does this row write, and is it inside the destination buffer?
-      bool v;
-      if (MODE == EPI_RS && a.epi.n_split > 0) v = (it.n < a.epi.n_split ? it.n : it.n - a.epi.n_split) < n_valid;
-      else v = it.n < n_valid;
-      const int t_lim = min(a.L_out, t0 + rt.n_time);
-      it.t_first = t0 + c;
-      it.nt = min(t_lim - it.t_first, 32);
-      it.valid = v && c < rt.n_time && it.nt > 0;
-      return it;
+      if (MODE == EPI_RS && a.epi.n_split > 0) ti.valid = (ti.n < a.epi.n_split ? ti.n : ti.n - a.epi.n_split) < n_valid;
+      else ti.valid = ti.n < n_valid;
+      ti.t_lim = min(a.L_out, ti.t0 + rt.n_time);
+      return ti;
+    };
+    auto prefetch = [&](const TileInfo& ti, int c, float* dst) {
+      const int t_first = ti.t0 + c;
+      if (ti.valid && t_first < ti.t_lim)
+        epi_prefetch<MODE, LD>(a.epi, ti.b, ti.n, t_first, min(ti.t_lim - t_first, 32), dst);
     };
 
-    int tile = blockIdx.x, c = c_first;
     float xcur[32], xnext[32];
-    Item cur = make_item(tile, c);
-    if (kPrefetch && tile < rt.total_tiles && cur.valid) epi_prefetch<MODE, LD>(a.epi, cur.b, cur.n, cur.t_first, cur.nt, xcur);
+    int tile = blockIdx.x;
+    TileInfo ti = decode(tile);
+    if (kPrefetch && tile < rt.total_tiles && c_first < rt.n_time) prefetch(ti, c_first, xcur);
     while (tile < rt.total_tiles) {
-      if (c == c_first) {
-        mbar_wait(BAR(iCF + sc), pc);
-        tc_fence_after();
-      }
+      const bool have_next = tile + (int)gridDim.x < rt.total_tiles;
+      TileInfo tn = ti;
+      if (have_next) tn = decode(tile + gridDim.x);
+      mbar_wait(BAR(iCF + sc), pc);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc * TC_ACC_STRIDE);
-      float acc[32], acc2[32];
-      tmem_ld32(taddr + (uint32_t)c, acc);
-      if constexpr (MODE == EPI_GATE) tmem_ld32(taddr + (uint32_t)(rt.n_time + c), acc2);
-      // next work item
-      int ntile = tile, nc = c + 64;
-      if (nc >= rt.n_time) { ntile += gridDim.x; nc = c_first; }
-      Item nxt = cur;
-      if (ntile < rt.total_tiles) {
-        nxt = make_item(ntile, nc);
-        if (kPrefetch && nxt.valid) epi_prefetch<MODE, LD>(a.epi, nxt.b, nxt.n, nxt.t_first, nxt.nt, xnext);
-      }
-      tmem_ld_wait();
-      if (cur.valid) tc_epilogue32<Op, MODE, LD>(a.epi, cur.b, cur.n, cur.phase, cur.t_first, cur.nt, acc, acc2, xcur);
-      if (nc == c_first) {  // last chunk of this tile for this warp: hand the accumulator stage back
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(iCE + sc));
-        if (++sc == 2) { sc = 0; pc ^= 1; }
-      }
-      if (kPrefetch) {
+      for (int c = c_first; c < rt.n_time; c += 64) {
+        float acc[32], acc2[32];
+        tmem_ld32(taddr + (uint32_t)c, acc);
+        if constexpr (MODE == EPI_GATE) tmem_ld32(taddr + (uint32_t)(rt.n_time + c), acc2);
+        if constexpr (kPrefetch) {  // next chunk of this tile, or the first chunk of this CTA's next tile
+          if (c + 64 < rt.n_time) prefetch(ti, c + 64, xnext);
+          else if (have_next) prefetch(tn, c_first, xnext);
+        }
+        tmem_ld_wait();
+        const int t_first = ti.t0 + c;
+        if (ti.valid && t_first < ti.t_lim)
+          tc_epilogue32<Op, MODE, LD>(a.epi, ti.b, ti.n, ti.phase, t_first, min(ti.t_lim - t_first, 32), acc, acc2, xcur);
+        if constexpr (kPrefetch) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) xcur[i] = xnext[i];
+          for (int i = 0; i < 32; ++i) xcur[i] = xnext[i];
+        }
       }
-      cur = nxt; tile = ntile; c = nc;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(iCE + sc));
+      if (++sc == 2) { sc = 0; pc ^= 1; }
+      ti = tn;
+      tile += gridDim.x;
     }
   }
   tc_fence_before();
