@@ -21,6 +21,9 @@ GOLDEN_CASES = {
     "ms_spk": ("uudb_ms_istft_vits_ms", {}),
     "mb_resblock2": ("ljs_mb_istft_vits", {"resblock": "2", "resblock_dilation_sizes": [[1, 3], [1, 3], [1, 3]]}),
     "mb_long": ("ljs_mini_mb_istft_vits", {}),
+    # minted from the reference's full SynthesizerTrn.infer() (tools/make_golden.py infer): BASELINE configs 1 and 4
+    "infer_mini_mb": ("ljs_mini_mb_istft_vits", {}),
+    "infer_istft": ("ljs_istft_vits", {}),
 }
 
 
@@ -32,5 +35,5 @@ def load_case(name):
     t = {k: torch.from_numpy(d[k]) for k in d.files if k not in ("meta", "g_scale", "lengths", "sid")}
     B, T, wseed, zseed = [int(v) for v in d["meta"]]
     sd = synth.make_state_dict(cfg, seed=wseed, g_scale=float(d["g_scale"]))
-    return cfg, sd, t, dict(B=B, T=T, lengths=[int(v) for v in d["lengths"]],
+    return cfg, sd, t, dict(B=B, T=T, zseed=zseed, lengths=[int(v) for v in d["lengths"]],
                             sid=(torch.from_numpy(d["sid"]) if "sid" in d.files else None))

@@ -45,7 +45,8 @@ def test_fp32_path_matches_reference_golden(name):
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["mini_mb", "mb", "mb_gscale", "ms", "istft", "ms_spk", "mb_resblock2", "mb_long"])
+@pytest.mark.parametrize("name", ["mini_mb", "mb", "mb_gscale", "ms", "istft", "ms_spk", "mb_resblock2", "mb_long",
+                                  "infer_mini_mb", "infer_istft"])
 def test_tf32_path_within_1e3_of_peak(name):
     cfg, sd, t, meta = load_case(name)
     eng = _engine(cfg, sd, "tf32")
@@ -55,7 +56,8 @@ def test_tf32_path_within_1e3_of_peak(name):
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["mini_mb", "mb", "mb_gscale", "ms", "istft", "ms_spk", "mb_resblock2", "mb_long"])
+@pytest.mark.parametrize("name", ["mini_mb", "mb", "mb_gscale", "ms", "istft", "ms_spk", "mb_resblock2", "mb_long",
+                                  "infer_mini_mb", "infer_istft"])
 def test_bf16_path_snr_at_least_40db(name):
     cfg, sd, t, meta = load_case(name)
     eng = _engine(cfg, sd, "bf16")
@@ -154,6 +156,48 @@ def test_full_size_decode_batch_independence_and_oracle_spot_check():
     assert torch.equal(one[0], wav[63])
     ref = orc.decode(sd, cfg, z[63:64])[0]
     assert orc.snr_db(one.cpu(), ref) > 40.0
+
+
+def _full_size_check(cfg_name, B, T, lengths=None, spot=0, prec="bf16", use_g=False):
+    """Shared body of the BASELINE-size tests: finite output of the right shape, utterance `spot` decoded inside the
+    batch is bit-identical to the same utterance decoded alone, and it matches the CPU oracle (bf16: >= 40 dB)."""
+    cfg = get_config(cfg_name)
+    sd = synth.make_state_dict(cfg, seed=1234)
+    eng = _engine(cfg, sd, prec)
+    z_p, mask, lens = synth.make_latents(cfg, B, T, seed=99, lengths=lengths)
+    g = None
+    if use_g:
+        g = sd["emb_g.weight"][torch.arange(B) % cfg["n_speakers"]].unsqueeze(-1)
+    gd = g.cuda() if g is not None else None
+    z, wav, _, _, _ = eng.flow_decode(z_p.cuda(), mask.cuda(), gd)
+    torch.cuda.synchronize()
+    assert wav.shape == (B, 1, 256 * T) and bool(torch.isfinite(wav).all())
+    assert float((z.cpu() * (1 - mask)).abs().max()) == 0.0
+    sl = slice(spot, spot + 1)
+    z1, wav1, _, _, _ = eng.flow_decode(z_p[sl].cuda(), mask[sl].cuda(), gd[sl] if gd is not None else None)
+    torch.cuda.synchronize()
+    assert torch.equal(wav1[0], wav[spot]) and torch.equal(z1[0], z[spot])
+    z_ref, (o_ref, _, _, _) = orc.flow_decode(sd, cfg, z_p[sl], mask[sl], g[sl] if g is not None else None)
+    n = int(lens[spot]) * 256
+    assert orc.snr_db(wav1.cpu()[..., :n], o_ref[..., :n]) > 40.0
+    assert orc.snr_db(z1.cpu(), z_ref) > 40.0
+    eng.close()
+
+
+def test_baseline_config3_multistream_shard_at_full_size():
+    """BASELINE config 3: ljs_ms_istft_vits, batch 256 sharded over 8 GPUs = 32 utterances x 862 frames per GPU."""
+    _full_size_check("ljs_ms_istft_vits", 32, 862, spot=31)
+
+
+def test_baseline_config4_single_band_decoder_at_full_size():
+    """BASELINE config 4: ljs_istft_vits (upsample [8,8], 64T-row stage 1, 8-phase transposed convs)."""
+    _full_size_check("ljs_istft_vits", 8, 862, spot=3)
+
+
+def test_baseline_config5_long_variable_length_speaker_conditioned():
+    """BASELINE config 5: 16 kHz multi-speaker MS decoder with g, mixed lengths 1 s .. 60 s (T = 63 .. 3750)."""
+    _full_size_check("uudb_ms_istft_vits_ms", 6, 3750, lengths=[3750, 63, 1875, 625, 2812, 125], spot=2, use_g=True)
+    _full_size_check("uudb_spk8_istft_vits", 3, 1250, lengths=[1250, 312, 1000], spot=0)
 
 
 def test_variable_length_batch_matches_reference_padding_semantics():

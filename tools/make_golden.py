@@ -135,5 +135,38 @@ def main():
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
 
 
+def mint_infer_cases(models, orc):
+    """Golden vectors from the reference's full SynthesizerTrn.infer() (BASELINE configs 1 and 4): synthetic phoneme
+    ids through the reference text encoder / duration predictor / path expansion / prior sampling; the inputs the
+    seam receives (z_p, y_mask, g) are captured with forward hooks and stored next to infer()'s outputs."""
+    for name, cname, B, Tx in (("infer_mini_mb", "ljs_mini_mb_istft_vits", 1, 24), ("infer_istft", "ljs_istft_vits", 2, 12)):
+        cfg = cfgs.get_config(cname)
+        sd = synth.make_state_dict(cfg, seed=1234)
+        torch.manual_seed(77)
+        net = build_reference(models, cfg, sd)  # enc_p / dp keep their own (seeded) random init
+        cap = {}
+        hk = net.flow.register_forward_pre_hook(lambda m, args, kwargs: cap.update(z_p=args[0].detach().clone(), mask=args[1].detach().clone()), with_kwargs=True)
+        x = torch.randint(1, 59, (B, Tx))
+        x_len = torch.tensor([Tx] + [max(3, Tx - 5)] * (B - 1))
+        with torch.no_grad():
+            o, o_mb, spec, phase, attn, y_mask, (z, z_p, m_p, logs_p), timings = net.infer(x, x_len, length_scale=1.0)
+        hk.remove()
+        assert torch.equal(cap["z_p"], z_p) and torch.equal(cap["mask"], y_mask)
+        zo, (oo, _, _, _) = orc.flow_decode(sd, cfg, z_p, y_mask, None)
+        print(f"{name:14s} T={z_p.shape[-1]} oracle-vs-infer: z {(zo - z).abs().max():.2e} wav {orc.max_abs_over_peak(oo, o):.2e}"
+              f"  timings keys {sorted(timings)}")
+        out = dict(z_p=z_p.numpy(), mask=y_mask.numpy(), z=z.numpy(), o=o.numpy(), spec=spec.numpy(), phase=phase.numpy(),
+                   meta=np.array([B, z_p.shape[-1], 1234, -1], dtype=np.int64), g_scale=np.float32(1.0),
+                   lengths=y_mask.sum((1, 2)).long().numpy())
+        if o_mb is not None:
+            out["o_mb"] = o_mb.numpy()
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "infer":
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import mbistft_oracle as _orc
+        mint_infer_cases(import_reference(), _orc)
+    else:
+        main()
