@@ -33,9 +33,12 @@ struct TailArgs {
   float* spec;          // [B][S][9][F] or null
   float* phase;
   int B, L, n_ch, variant;
-  float coef[4][64];    // synthesis FIR h[c][k] (PQMF or the trainable multistream_conv_post), gain folded
+  float coef[4][64];    // generic polyphase synthesis FIR G[c][r*16+(d+7)] = 4*h[c][4d+31-r] (trainable MS filter)
+  float mod[8][4];      // PQMF fast path: cosine modulation 2*cos(theta_c(m)), m = k mod 8
+  float g2[4][16];      // PQMF fast path: 4 * prototype[4d+31-r] * (-1)^floor(k/8), per output residue r
+  int fast_pqmf;        // 1: variant MB (cosine-modulated bank): modulate once per sub-band sample, 16 MACs per output
 };
-cudaError_t launch_tail(const TailArgs& a, int precise, cudaStream_t st);
+cudaError_t launch_tail(const TailArgs& a, int precise, int num_sms, cudaStream_t st);
 
 // ---- misc.cu
 // fp32 NCT [B][C][T] -> channels-last [B][T][Cp] operand (and optional fp32 copy), optional mask [B][T]

@@ -89,6 +89,9 @@ struct mbv_handle {
   float* rb_cond_w[MBV_MAX_UPS][MBV_MAX_KERNELS] = {{nullptr}};  // [C][gin]
   float* rb_cond_b[MBV_MAX_UPS][MBV_MAX_KERNELS] = {{nullptr}};  // [C]
   float tail_coef[4][64];
+  float tail_mod[8][4];
+  float tail_g2[4][16];
+  int tail_fast = 0;
 
   // flow layers, indexed by coupling layer 0..3 (reference order)
   ConvLayer fl_pre[4], fl_post[4], fl_in[4][4], fl_rs[4][4];
@@ -273,10 +276,9 @@ double bessel_i0(double x) {
 }
 
 // pqmf.py:15-43 + 64-79: 63-tap Kaiser(beta 9) prototype at cutoff 0.15, cosine-modulated synthesis bank (float64 -> float32)
-void design_pqmf_synthesis(float hs[4][63]) {
+void design_pqmf_synthesis(float hs[4][63], double proto[63]) {
   const int taps = 62;
   const double cutoff = 0.15, beta = 9.0, pi = 3.14159265358979323846;
-  double proto[63];
   for (int n = 0; n <= taps; ++n) {
     const double x = n - 0.5 * taps;
     const double hi = (n == taps / 2) ? cutoff : sin(pi * cutoff * x) / (pi * x);
@@ -452,7 +454,19 @@ extern "C" int mbv_load_weights(mbv_handle* h, const mbv_tensor* tensors, int32_
     float hs[4][63];
     memset(hs, 0, sizeof(hs));
     if (c.variant == MBV_VARIANT_MB) {
-      design_pqmf_synthesis(hs);
+      // fast path tables: cos(theta_c(k)) = (-1)^floor(k/8) cos(theta_c(k mod 8)) (pqmf.py:72-75)
+      double proto[63];
+      design_pqmf_synthesis(hs, proto);
+      const double pi = 3.14159265358979323846;
+      for (int mI = 0; mI < 8; ++mI)
+        for (int cc = 0; cc < 4; ++cc)
+          h->tail_mod[mI][cc] = (float)(2.0 * cos((2 * cc + 1) * (pi / 8.0) * (mI - 30.5) - ((cc & 1) ? -1.0 : 1.0) * pi / 4.0));
+      for (int r = 0; r < 4; ++r)
+        for (int d = -7; d <= 8; ++d) {
+          const int k = 4 * d + 31 - r;
+          h->tail_g2[r][d + 7] = (k >= 0 && k <= 62) ? (float)(4.0 * proto[k] * (((k / 8) & 1) ? -1.0 : 1.0)) : 0.f;
+        }
+      h->tail_fast = 1;
     } else if (c.variant == MBV_VARIANT_MS) {
       const int64_t ws[3] = {1, 4, 63};
       const HostTensor* w = find_tensor(h, m, "dec.multistream_conv_post.weight", 3, ws);
@@ -704,8 +718,11 @@ int run_tail(Ctx& cx, const float* logits, float* wav, float* o_mb, float* spec,
   ta.logits = logits; ta.wav = wav; ta.o_mb = o_mb; ta.spec = spec; ta.phase = phase;
   ta.B = B; ta.L = Lfr; ta.n_ch = h->n_logit; ta.variant = h->cfg.variant;
   memcpy(ta.coef, h->tail_coef, sizeof(ta.coef));
+  memcpy(ta.mod, h->tail_mod, sizeof(ta.mod));
+  memcpy(ta.g2, h->tail_g2, sizeof(ta.g2));
+  ta.fast_pqmf = h->tail_fast;
   ProfScope prof(cx, 1);
-  CUDA_TRY(h, launch_tail(ta, h->prec == MBV_PREC_FP32 ? 1 : 0, cx.st));
+  CUDA_TRY(h, launch_tail(ta, h->prec == MBV_PREC_FP32 ? 1 : 0, h->num_sms, cx.st));
   cx.launches++;
   return MBV_OK;
 }

@@ -50,15 +50,45 @@ __device__ __forceinline__ void head(float xm, float xp, float& mag, float& ph, 
     sincosf(ph, &s, &c);
   } else {
     mag = __expf(xm);
-    // one Cody-Waite step keeps the fast sine inside its accurate range for any logit
-    const float k = rintf(xp * 0.15915494309189535f);
-    float r = fmaf(-k, 6.2831854820251465f, xp);
-    r = fmaf(-k, -1.7484555e-7f, r);
-    ph = 3.14159265358979323846f * __sinf(r);
+    // MUFU.SIN reduces its argument itself; for |x| < ~100 (logits are O(1)) the absolute error stays ~1e-6
+    ph = 3.14159265358979323846f * __sinf(xp);
     __sincosf(ph, &s, &c);
   }
   re = mag * c;
   im = mag * s;
+}
+
+// 16-point inverse real DFT (imaginary parts of bins 0 and 8 ignored, like torch.istft's irfft) times the periodic
+// Hann window / 16, written as an even/odd-bin split so that it costs ~100 flops instead of 16 x 15 MACs:
+//   x[n] = E[n] + O[n], x[n+8] = E[n] - O[n];  E = bins {0,4,8} (period 4) +- bins {2,6};  O = odd bins with the
+//   n <-> 8-n symmetry of cos / antisymmetry of sin.
+__device__ __forceinline__ void idft16_windowed(const float* re, const float* im, float* fr) {
+  constexpr float c1 = 0.92387953251128674f, c2 = 0.70710678118654752f, c3 = 0.38268343236508977f;
+  const float a0 = re[0] + re[8], a1 = re[0] - re[8];
+  const float A0 = a0 + 2.f * re[4], A1 = a1 - 2.f * im[4], A2 = a0 - 2.f * re[4], A3 = a1 + 2.f * im[4];
+  const float ims = im[2] + im[6];
+  const float B0 = 2.f * (re[2] + re[6]);
+  const float B1 = (2.f * c2) * ((re[2] - re[6]) - ims);
+  const float B2 = 2.f * (im[6] - im[2]);
+  const float B3 = (2.f * c2) * ((re[6] - re[2]) - ims);
+  float E[8] = {A0 + B0, A1 + B1, A2 + B2, A3 + B3, A0 - B0, A1 - B1, A2 - B2, A3 - B3};
+  const float r17 = re[1] - re[7], r35 = re[3] - re[5], i17 = im[1] + im[7], i35 = im[3] + im[5];
+  const float oc0 = (re[1] + re[7]) + (re[3] + re[5]);
+  const float oc1 = c1 * r17 + c3 * r35, os1 = c3 * i17 + c1 * i35;
+  const float oc2 = c2 * ((re[1] + re[7]) - (re[3] + re[5])), os2 = c2 * ((im[1] - im[7]) + (im[3] - im[5]));
+  const float oc3 = c3 * r17 - c1 * r35, os3 = c1 * i17 - c3 * i35;
+  const float os4 = (im[1] - im[3]) + (im[5] - im[7]);
+  float O[8];
+  O[0] = 2.f * oc0;
+  O[1] = 2.f * (oc1 - os1); O[7] = -2.f * (oc1 + os1);
+  O[2] = 2.f * (oc2 - os2); O[6] = -2.f * (oc2 + os2);
+  O[3] = 2.f * (oc3 - os3); O[5] = -2.f * (oc3 + os3);
+  O[4] = -2.f * os4;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    fr[n] = (E[n] + O[n]) * kWin16[n];
+    fr[n + 8] = (E[n] - O[n]) * kWin16[n + 8];
+  }
 }
 
 // VARIANT: 0 = single-band iSTFT (no synthesis filter), 1 = MB / MS (4 bands + 63-tap synthesis FIR)
@@ -135,19 +165,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) tail_kernel(const __grid_cons
         }
       }
       // x[n] = Re0 + (-1)^n Re8 + 2 sum_{k=1..7} (Re_k cos(2 pi k n/16) - Im_k sin(2 pi k n/16)); imag of bins 0, 8 ignored
-      fr[0] = 0.f;  // w[0] == 0
-#pragma unroll
-      for (int n = 1; n <= 8; ++n) {
-        float c = 0.f, sn = 0.f;
-#pragma unroll
-        for (int k = 1; k <= 7; ++k) {
-          c = fmaf(re[k], kCos16[(k * n) & 15], c);
-          sn = fmaf(im[k], kCos16[(k * n + 12) & 15], sn);
-        }
-        const float base = re[0] + ((n & 1) ? -re[8] : re[8]);
-        fr[n] = (base + 2.f * (c - sn)) * kWin16[n];
-        if (n < 8) fr[16 - n] = (base + 2.f * (c + sn)) * kWin16[16 - n];
-      }
+      idft16_windowed(re, im, fr);
     } else {
 #pragma unroll
       for (int n = 0; n < 16; ++n) fr[n] = 0.f;
@@ -231,6 +249,237 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) tail_kernel(const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Multi-band / multi-stream tail, v2: persistent, 1024 threads, thread = (frame, band).
+//   phase 1  item tid = f*4 + s      head + inverse DFT + window            -> FR[f][s][16]
+//   (the logits tile is dead: one thread issues the bulk copy of the NEXT tile's logits, overlapping phases 2-4)
+//   phase 2  item tid = t*4 + s      overlap-add + envelope                 -> Y[s][4t..4t+3]   (+ optional o_mb)
+//   phase 3  item tid = t*2 + mh     PQMF only: cosine modulation           -> U[m][4t..4t+3], m = 4*mh..4*mh+3
+//   phase 4  item tid = t*4 + r      polyphase synthesis FIR, outputs n = 16(Q0+t) + 4e + r, e = 0..3
+// Every shared-memory access pattern above is bank-conflict free (pitches 20 / 1032 floats); 32 resident warps per SM.
+// PQMF fast path (MB): h[c][k] = 2 p[k] cos(theta_c(k)) and cos(theta_c(k)) = (-1)^floor(k/8) cos(theta_c(k mod 8))
+// (pqmf.py:72-75), so U[m][j] = sum_c 2cos(theta_c(m)) y_c[j] is formed once per sub-band sample (8 x 4 MACs) and each
+// output needs only the 16 (15) prototype taps of its residue: ~24 MACs per output sample instead of 63.
+// ------------------------------------------------------------------------------------------------
+constexpr int T2_THREADS = 1024;
+constexpr int T2_YP = 1032;  // floats per band (Y) / per modulation index (U)
+constexpr int T2_NQ = TAIL_NF - 7;
+
+__device__ __forceinline__ void t2_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && (unsigned long long)(clock64() - t0) > 4000000000ull) __trap();
+  }
+}
+
+template <bool PRECISE>
+__global__ void __launch_bounds__(T2_THREADS, 1) tail_mb_kernel(const __grid_constant__ TailArgs a, int tiles_per_utt,
+                                                                int total_tiles) {
+  constexpr int S = 4, NCH = 72, NQ = T2_NQ;
+  extern __shared__ __align__(128) float sm[];
+  float* s_log = sm;                                  // [256][72]
+  float* s_fr = s_log + TAIL_NF * NCH;                // [256*4][20]   (phase 3/4: U[8][T2_YP])
+  float* s_y = s_fr + TAIL_NF * S * FR_PITCH;         // [4][T2_YP]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_y + S * T2_YP);
+  const uint32_t bar_addr = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
+  const int tid = threadIdx.x;
+  const int L = a.L, F = L + 1;
+
+  auto issue_load = [&](int tile) {  // one thread: bulk-copy the logits rows [F0, F0+256) /\ [0, F) of `tile`
+    const int b = tile / tiles_per_utt, tl = tile % tiles_per_utt;
+    const int F0 = tl * NQ - 3;
+    const int f_lo = F0 < 0 ? 0 : F0;
+    const int f_hi = (F0 + TAIL_NF < F) ? F0 + TAIL_NF : F;
+    const uint32_t bytes = (uint32_t)(f_hi - f_lo) * NCH * 4u;
+    const float* src = a.logits + ((size_t)b * F + f_lo) * NCH;
+    const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(s_log + (f_lo - F0) * NCH));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar_addr) : "memory");
+  };
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0 && (int)blockIdx.x < total_tiles) issue_load(blockIdx.x);
+  uint32_t parity = 0;
+
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_utt, tl = tile % tiles_per_utt;
+    const int Q0 = tl * NQ, QY0 = Q0 - 2, F0 = QY0 - 1;
+    const bool last_tile = (tl == tiles_per_utt - 1);
+    t2_mbar_wait(bar_addr, parity);
+    parity ^= 1;
+
+    // ---- phase 1
+    {
+      const int fl = tid >> 2, s = tid & 3;
+      const int f = F0 + fl;
+      float fr[16];
+      if (f >= 0 && f < F) {
+        const float2* lp = reinterpret_cast<const float2*>(s_log + fl * NCH + s * 18);
+        float x[18];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { const float2 v = lp[i]; x[2 * i] = v.x; x[2 * i + 1] = v.y; }
+        const bool emit = (a.spec != nullptr) && (f >= Q0) && (f < Q0 + NQ || (last_tile && f == L));
+        float re[9], im[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          float mag, ph;
+          head<PRECISE>(x[k], x[9 + k], mag, ph, re[k], im[k]);
+          if (emit) {
+            const size_t o = (((size_t)b * S + s) * 9 + k) * F + f;
+            a.spec[o] = mag;
+            a.phase[o] = ph;
+          }
+        }
+        idft16_windowed(re, im, fr);
+      } else {
+#pragma unroll
+        for (int n = 0; n < 16; ++n) fr[n] = 0.f;
+      }
+      float4* dst = reinterpret_cast<float4*>(s_fr + tid * FR_PITCH);
+      dst[0] = make_float4(fr[0], fr[1], fr[2], fr[3]);
+      dst[1] = make_float4(fr[4], fr[5], fr[6], fr[7]);
+      dst[2] = make_float4(fr[8], fr[9], fr[10], fr[11]);
+      dst[3] = make_float4(fr[12], fr[13], fr[14], fr[15]);
+    }
+    __syncthreads();
+    if (tid == 0 && tile + (int)gridDim.x < total_tiles) issue_load(tile + gridDim.x);  // s_log is free again
+
+    // ---- phase 2: y block q = frame q-1 part 3 + q part 2 + q+1 part 1 + q+2 part 0, / window-square envelope
+    {
+      const int t = tid >> 2, s = tid & 3;
+      if (t < TAIL_NF - 3) {
+        const int q = QY0 + t;
+        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q >= 0 && q < L) {
+          const float4 p3 = *reinterpret_cast<const float4*>(s_fr + ((t + 0) * 4 + s) * FR_PITCH + 12);
+          const float4 p2 = *reinterpret_cast<const float4*>(s_fr + ((t + 1) * 4 + s) * FR_PITCH + 8);
+          const float4 p1 = *reinterpret_cast<const float4*>(s_fr + ((t + 2) * 4 + s) * FR_PITCH + 4);
+          const float4 p0 = *reinterpret_cast<const float4*>(s_fr + ((t + 3) * 4 + s) * FR_PITCH + 0);
+          y.x = p3.x + p2.x + p1.x + p0.x;
+          y.y = p3.y + p2.y + p1.y + p0.y;
+          y.z = p3.z + p2.z + p1.z + p0.z;
+          y.w = p3.w + p2.w + p1.w + p0.w;
+          float e0 = 1.5f, e1 = 1.5f, e2 = 1.5f, e3 = 1.5f;
+          if (q == 0) { e0 -= win_sq(12); e1 -= win_sq(13); e2 -= win_sq(14); e3 -= win_sq(15); }
+          if (q == L - 1) { e0 -= win_sq(0); e1 -= win_sq(1); e2 -= win_sq(2); e3 -= win_sq(3); }
+          y.x /= e0; y.y /= e1; y.z /= e2; y.w /= e3;
+          if (a.o_mb != nullptr && t >= 2 && t < 2 + NQ) {
+            if (a.variant == 1) {  // MB: y_mb_hat [B][S][4L]
+              *reinterpret_cast<float4*>(a.o_mb + ((size_t)b * S + s) * 4 * L + 4 * (size_t)q) = y;
+            } else {  // MS: the zero-stuffed tensor [B][S][16L], gain 4 (models.py:463)
+              float4* o = reinterpret_cast<float4*>(a.o_mb + ((size_t)b * S + s) * 16 * L + 16 * (size_t)q);
+              o[0] = make_float4(4.f * y.x, 0.f, 0.f, 0.f);
+              o[1] = make_float4(4.f * y.y, 0.f, 0.f, 0.f);
+              o[2] = make_float4(4.f * y.z, 0.f, 0.f, 0.f);
+              o[3] = make_float4(4.f * y.w, 0.f, 0.f, 0.f);
+            }
+          }
+        }
+        *reinterpret_cast<float4*>(s_y + s * T2_YP + 4 * t) = y;
+      }
+    }
+    __syncthreads();
+
+    float* s_u = s_fr;  // [8][T2_YP], aliases the frame scratch (dead after phase 2)
+    if (a.fast_pqmf) {
+      // ---- phase 3: U[m][j] = sum_c mod[m][c] * y_c[j]
+      const int t = tid >> 1, mh = tid & 1;
+      if (t < TAIL_NF - 3) {
+        float4 yv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) yv[c] = *reinterpret_cast<const float4*>(s_y + c * T2_YP + 4 * t);
+#pragma unroll
+        for (int mm = 0; mm < 4; ++mm) {
+          const int m = mh * 4 + mm;
+          float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float w = mh ? a.mod[4 + mm][c] : a.mod[mm][c];
+            u.x = fmaf(w, yv[c].x, u.x); u.y = fmaf(w, yv[c].y, u.y);
+            u.z = fmaf(w, yv[c].z, u.z); u.w = fmaf(w, yv[c].w, u.w);
+          }
+          *reinterpret_cast<float4*>(s_u + m * T2_YP + 4 * t) = u;
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- phase 4: out[16(Q0+t) + 4e + r], e = 0..3
+    {
+      const int t = tid >> 2, r = tid & 3;
+      if (t < NQ && Q0 + t < L) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a.fast_pqmf) {
+          // taps d = -7..8 -> k = 4d+31-r; even d read U[7-r], odd d read U[3-r]; window index 8+e+d of [4t, 4t+20)
+          float we[20], wo[20];
+          const float4* pe = reinterpret_cast<const float4*>(s_u + (7 - r) * T2_YP + 4 * t);
+          const float4* po = reinterpret_cast<const float4*>(s_u + (3 - r) * T2_YP + 4 * t);
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            const float4 u = pe[i], v = po[i];
+            we[4 * i] = u.x; we[4 * i + 1] = u.y; we[4 * i + 2] = u.z; we[4 * i + 3] = u.w;
+            wo[4 * i] = v.x; wo[4 * i + 1] = v.y; wo[4 * i + 2] = v.z; wo[4 * i + 3] = v.w;
+          }
+          float g[16];
+#pragma unroll
+          for (int d = 0; d < 16; ++d) g[d] = a.g2[r][d];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int d = 0; d < 16; ++d)  // d - 7 in [-7, 8]; (d - 7) even <=> d odd
+              acc[e] = fmaf(g[d], (d & 1) ? we[1 + e + d] : wo[1 + e + d], acc[e]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float v[20];
+            const float4* yp = reinterpret_cast<const float4*>(s_y + c * T2_YP + 4 * t);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+              const float4 u = yp[i];
+              v[4 * i] = u.x; v[4 * i + 1] = u.y; v[4 * i + 2] = u.z; v[4 * i + 3] = u.w;
+            }
+#pragma unroll
+            for (int d = 0; d < 16; ++d) {
+              const float g = a.coef[c][r * 16 + d];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) acc[e] = fmaf(g, v[1 + e + d], acc[e]);
+            }
+          }
+        }
+        float* o = a.wav + (size_t)b * 16 * L + 16 * (size_t)(Q0 + t) + r;
+        o[0] = acc[0]; o[4] = acc[1]; o[8] = acc[2]; o[12] = acc[3];
+      }
+    }
+    __syncthreads();  // FR/U and Y are rewritten by the next tile
+  }
+}
+
+static cudaError_t launch_tail_mb(const TailArgs& a, int precise, int num_sms, cudaStream_t st) {
+  const int tiles = (a.L + T2_NQ - 1) / T2_NQ;
+  const int total = a.B * tiles;
+  const size_t smem = sizeof(float) * ((size_t)TAIL_NF * 72 + (size_t)TAIL_NF * 4 * FR_PITCH + 4 * T2_YP) + 64;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(tail_mb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tail_mb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  const int grid = total < num_sms ? total : num_sms;
+  if (precise) tail_mb_kernel<true><<<grid, T2_THREADS, smem, st>>>(a, tiles, total);
+  else tail_mb_kernel<false><<<grid, T2_THREADS, smem, st>>>(a, tiles, total);
+  return cudaGetLastError();
+}
+
 template <int VARIANT, bool PRECISE>
 static cudaError_t launch_tail_t(const TailArgs& a, cudaStream_t st) {
   constexpr int S = VARIANT == 0 ? 1 : 4;
@@ -248,9 +497,9 @@ static cudaError_t launch_tail_t(const TailArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_tail(const TailArgs& a, int precise, cudaStream_t st) {
+cudaError_t launch_tail(const TailArgs& a, int precise, int num_sms, cudaStream_t st) {
   if (a.variant == 0) return precise ? launch_tail_t<0, true>(a, st) : launch_tail_t<0, false>(a, st);
-  return precise ? launch_tail_t<1, true>(a, st) : launch_tail_t<1, false>(a, st);
+  return launch_tail_mb(a, precise, num_sms, st);
 }
 
 }  // namespace mbv
