@@ -40,6 +40,10 @@ __device__ __forceinline__ float win_sq(int n) {
   return w * w;
 }
 
+__device__ __forceinline__ float ptx_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ptx_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ptx_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 template <bool PRECISE>
 __device__ __forceinline__ void head(float xm, float xp, float& mag, float& ph, float& re, float& im) {
   // spec = exp(x), phase = pi * sin(x)  (models.py:368-369); re/im = spec * (cos, sin)(phase)
@@ -49,10 +53,12 @@ __device__ __forceinline__ void head(float xm, float xp, float& mag, float& ph, 
     ph = 3.14159265358979323846f * sinf(xp);
     sincosf(ph, &s, &c);
   } else {
-    mag = __expf(xm);
-    // MUFU.SIN reduces its argument itself; for |x| < ~100 (logits are O(1)) the absolute error stays ~1e-6
-    ph = 3.14159265358979323846f * __sinf(xp);
-    __sincosf(ph, &s, &c);
+    // MUFU.EX2 / MUFU.SIN / MUFU.COS; the sine's own argument reduction keeps the absolute error ~1e-6 for the
+    // O(1) logits this head sees (|x| < ~100)
+    mag = ptx_ex2(xm * 1.4426950408889634f);
+    ph = 3.14159265358979323846f * ptx_sin(xp);
+    s = ptx_sin(ph);
+    c = ptx_cos(ph);
   }
   re = mag * c;
   im = mag * s;
@@ -283,7 +289,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_mb_kernel(const __grid_con
   float* s_log = sm;                                  // [256][72]
   float* s_fr = s_log + TAIL_NF * NCH;                // [256*4][20]   (phase 3/4: U[8][T2_YP])
   float* s_y = s_fr + TAIL_NF * S * FR_PITCH;         // [4][T2_YP]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(s_y + S * T2_YP);
+  float* s_g2 = s_y + S * T2_YP;                      // [4][16] prototype taps per output residue
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_g2 + 64);
   const uint32_t bar_addr = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
   const int tid = threadIdx.x;
   const int L = a.L, F = L + 1;
@@ -301,6 +308,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_mb_kernel(const __grid_con
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar_addr) : "memory");
   };
 
+  if (tid < 64) s_g2[tid] = a.g2[tid >> 4][tid & 15];
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -367,10 +375,15 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_mb_kernel(const __grid_con
           y.y = p3.y + p2.y + p1.y + p0.y;
           y.z = p3.z + p2.z + p1.z + p0.z;
           y.w = p3.w + p2.w + p1.w + p0.w;
-          float e0 = 1.5f, e1 = 1.5f, e2 = 1.5f, e3 = 1.5f;
-          if (q == 0) { e0 -= win_sq(12); e1 -= win_sq(13); e2 -= win_sq(14); e3 -= win_sq(15); }
-          if (q == L - 1) { e0 -= win_sq(0); e1 -= win_sq(1); e2 -= win_sq(2); e3 -= win_sq(3); }
-          y.x /= e0; y.y /= e1; y.z /= e2; y.w /= e3;
+          if (PRECISE || q == 0 || q == L - 1) {
+            float e0 = 1.5f, e1 = 1.5f, e2 = 1.5f, e3 = 1.5f;
+            if (q == 0) { e0 -= win_sq(12); e1 -= win_sq(13); e2 -= win_sq(14); e3 -= win_sq(15); }
+            if (q == L - 1) { e0 -= win_sq(0); e1 -= win_sq(1); e2 -= win_sq(2); e3 -= win_sq(3); }
+            y.x /= e0; y.y /= e1; y.z /= e2; y.w /= e3;
+          } else {  // steady-state envelope 1.5: multiply by the reciprocal (<= 1 ulp from the division)
+            const float inv = 0.66666666666666667f;
+            y.x *= inv; y.y *= inv; y.z *= inv; y.w *= inv;
+          }
           if (a.o_mb != nullptr && t >= 2 && t < 2 + NQ) {
             if (a.variant == 1) {  // MB: y_mb_hat [B][S][4L]
               *reinterpret_cast<float4*>(a.o_mb + ((size_t)b * S + s) * 4 * L + 4 * (size_t)q) = y;
@@ -430,7 +443,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_mb_kernel(const __grid_con
           }
           float g[16];
 #pragma unroll
-          for (int d = 0; d < 16; ++d) g[d] = a.g2[r][d];
+          for (int i = 0; i < 4; ++i) {
+            const float4 gv = *reinterpret_cast<const float4*>(s_g2 + r * 16 + 4 * i);
+            g[4 * i] = gv.x; g[4 * i + 1] = gv.y; g[4 * i + 2] = gv.z; g[4 * i + 3] = gv.w;
+          }
 #pragma unroll
           for (int e = 0; e < 4; ++e)
 #pragma unroll
@@ -465,7 +481,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_mb_kernel(const __grid_con
 static cudaError_t launch_tail_mb(const TailArgs& a, int precise, int num_sms, cudaStream_t st) {
   const int tiles = (a.L + T2_NQ - 1) / T2_NQ;
   const int total = a.B * tiles;
-  const size_t smem = sizeof(float) * ((size_t)TAIL_NF * 72 + (size_t)TAIL_NF * 4 * FR_PITCH + 4 * T2_YP) + 64;
+  const size_t smem = sizeof(float) * ((size_t)TAIL_NF * 72 + (size_t)TAIL_NF * 4 * FR_PITCH + 4 * T2_YP + 64) + 64;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(tail_mb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

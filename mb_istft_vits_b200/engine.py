@@ -168,6 +168,20 @@ class Engine:
                                              C.c_void_p(ws), nws, self._stream()))
         return z, wav, o_mb, spec, phase
 
+    def capture_flow_decode(self, z_p, y_mask, g=None, want_z=False, want_mb=False, want_spec=False):
+        """Capture one flow_decode() on the given (static) device tensors into a CUDA graph.  Returns
+        (graph, outputs): ``graph.replay()`` re-runs the whole launch sequence with one submission; the outputs
+        tuple (z, wav, o_mb, spec, phase) is overwritten by every replay.  Every library call is allocation-free,
+        host-sync-free and enqueues only on the current stream, so it is capturable as is."""
+        B, _, T = z_p.shape
+        self._workspace(B, T)  # allocate outside the capture
+        self.flow_decode(z_p, y_mask, g, want_z=want_z, want_mb=want_mb, want_spec=want_spec)  # warm-up: tensor maps, attributes
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            outs = self.flow_decode(z_p, y_mask, g, want_z=want_z, want_mb=want_mb, want_spec=want_spec)
+        return graph, outs
+
     def tail(self, logits, T, want_mb=True, want_spec=True):
         """Fused head+iSTFT+synthesis on logits [B, F, n_ch] (channels-last)."""
         logits = self._prep(logits)
