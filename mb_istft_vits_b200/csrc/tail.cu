@@ -267,9 +267,12 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) tail_kernel(const __grid_cons
 // (pqmf.py:72-75), so U[m][j] = sum_c 2cos(theta_c(m)) y_c[j] is formed once per sub-band sample (8 x 4 MACs) and each
 // output needs only the 16 (15) prototype taps of its residue: ~24 MACs per output sample instead of 63.
 // ------------------------------------------------------------------------------------------------
-constexpr int T2_THREADS = 1024;
-constexpr int T2_YP = 1032;  // floats per band (Y) / per modulation index (U)
-constexpr int T2_NQ = TAIL_NF - 7;
+// NF frames per band per tile, NF*4 threads.  NF = 128 -> two 512-thread CTAs per SM whose phases interleave (one
+// CTA's MUFU-bound head overlaps the other's FMA-bound FIR and the bulk copies), 94.5 % useful work per tile.
+constexpr int T2_NF = 128;
+constexpr int T2_THREADS = T2_NF * 4;
+constexpr int T2_YP = (T2_NF == 128) ? 520 : 1032;  // floats per band (Y) / per modulation index (U); YP/4 = 2 mod 8
+constexpr int T2_NQ = T2_NF - 7;
 
 __device__ __forceinline__ void t2_mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
@@ -282,13 +285,13 @@ __device__ __forceinline__ void t2_mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 template <bool PRECISE>
-__global__ void __launch_bounds__(T2_THREADS, 1) tail_mb_kernel(const __grid_constant__ TailArgs a, int tiles_per_utt,
+__global__ void __launch_bounds__(T2_THREADS, 1024 / T2_THREADS) tail_mb_kernel(const __grid_constant__ TailArgs a, int tiles_per_utt,
                                                                 int total_tiles) {
   constexpr int S = 4, NCH = 72, NQ = T2_NQ;
   extern __shared__ __align__(128) float sm[];
   float* s_log = sm;                                  // [256][72]
-  float* s_fr = s_log + TAIL_NF * NCH;                // [256*4][20]   (phase 3/4: U[8][T2_YP])
-  float* s_y = s_fr + TAIL_NF * S * FR_PITCH;         // [4][T2_YP]
+  float* s_fr = s_log + T2_NF * NCH;                // [256*4][20]   (phase 3/4: U[8][T2_YP])
+  float* s_y = s_fr + T2_NF * S * FR_PITCH;         // [4][T2_YP]
   float* s_g2 = s_y + S * T2_YP;                      // [4][16] prototype taps per output residue
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_g2 + 64);
   const uint32_t bar_addr = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_mb_kernel(const __grid_con
     const int b = tile / tiles_per_utt, tl = tile % tiles_per_utt;
     const int F0 = tl * NQ - 3;
     const int f_lo = F0 < 0 ? 0 : F0;
-    const int f_hi = (F0 + TAIL_NF < F) ? F0 + TAIL_NF : F;
+    const int f_hi = (F0 + T2_NF < F) ? F0 + T2_NF : F;
     const uint32_t bytes = (uint32_t)(f_hi - f_lo) * NCH * 4u;
     const float* src = a.logits + ((size_t)b * F + f_lo) * NCH;
     const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(s_log + (f_lo - F0) * NCH));
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_mb_kernel(const __grid_con
     // ---- phase 2: y block q = frame q-1 part 3 + q part 2 + q+1 part 1 + q+2 part 0, / window-square envelope
     {
       const int t = tid >> 2, s = tid & 3;
-      if (t < TAIL_NF - 3) {
+      if (t < T2_NF - 3) {
         const int q = QY0 + t;
         float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q >= 0 && q < L) {
@@ -405,7 +408,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_mb_kernel(const __grid_con
     if (a.fast_pqmf) {
       // ---- phase 3: U[m][j] = sum_c mod[m][c] * y_c[j]
       const int t = tid >> 1, mh = tid & 1;
-      if (t < TAIL_NF - 3) {
+      if (t < T2_NF - 3) {
         float4 yv[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) yv[c] = *reinterpret_cast<const float4*>(s_y + c * T2_YP + 4 * t);
@@ -481,7 +484,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tail_mb_kernel(const __grid_con
 static cudaError_t launch_tail_mb(const TailArgs& a, int precise, int num_sms, cudaStream_t st) {
   const int tiles = (a.L + T2_NQ - 1) / T2_NQ;
   const int total = a.B * tiles;
-  const size_t smem = sizeof(float) * ((size_t)TAIL_NF * 72 + (size_t)TAIL_NF * 4 * FR_PITCH + 4 * T2_YP + 64) + 64;
+  const size_t smem = sizeof(float) * ((size_t)T2_NF * 72 + (size_t)T2_NF * 4 * FR_PITCH + 4 * T2_YP + 64) + 64;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(tail_mb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -490,7 +493,8 @@ static cudaError_t launch_tail_mb(const TailArgs& a, int precise, int num_sms, c
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  const int grid = total < num_sms ? total : num_sms;
+  const int ctas = num_sms * (1024 / T2_THREADS);
+  const int grid = total < ctas ? total : ctas;
   if (precise) tail_mb_kernel<true><<<grid, T2_THREADS, smem, st>>>(a, tiles, total);
   else tail_mb_kernel<false><<<grid, T2_THREADS, smem, st>>>(a, tiles, total);
   return cudaGetLastError();
