@@ -452,6 +452,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the
+  // tail of the previous kernel in the stream; nothing below may touch global memory before that kernel has
+  // completed and flushed.  Our own dependents may be scheduled as soon as SMs free up.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int kblocks = a.Cp_in / KB;
   const int n_logical = a.gate ? a.N_total / 2 : a.N_total;  // weight rows of one half
@@ -707,8 +712,17 @@ template <typename Op, int MODE, int LD>
 static cudaError_t launch_one(const ConvArgs& a, const TcPlan& p, const TcRt& rt, cudaStream_t st, bool set_attr) {
   auto k = conv_tc_kernel<Op, MODE, LD>;
   if (set_attr) return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  k<<<p.grid, TC_THREADS, p.smem_bytes, st>>>(p.tmA, p.tmB, a, rt);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = p.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k, p.tmA, p.tmB, a, rt);
 }
 
 template <typename Op>

@@ -501,7 +501,11 @@ extern "C" int mbv_load_weights(mbv_handle* h, const mbv_tensor* tensors, int32_
         rc = pack_conv1d(h, m, pfx, 2 * H, H, K, 1, gmap, hin, true, 1, &h->fl_in[f][l]);
         if (rc) return rc;
         snprintf(pfx, sizeof(pfx), "flow.flows.%d.enc.res_skip_layers.%d", 2 * f, l);
-        if (l < NL - 1) rc = pack_conv1d(h, m, pfx, 2 * H, H, 1, 1, gmap, hin, true, 0, &h->fl_rs[f][l]);
+        // res/skip rows packed back to back at the activation pitch: [res Hp | skip Hp] (no 128-padding between the
+        // halves -- 2*192 = 384 rows = exactly three MMA tiles; epilogue warps are 32 channels, Hp is a multiple of 64)
+        std::vector<int> rsmap(2 * Hp, -1);
+        for (int o = 0; o < H; ++o) { rsmap[o] = o; rsmap[Hp + o] = H + o; }
+        if (l < NL - 1) rc = pack_conv1d(h, m, pfx, 2 * H, H, 1, 1, rsmap, hin, true, 0, &h->fl_rs[f][l]);
         else rc = pack_conv1d(h, m, pfx, H, H, 1, 1, iota_pad(H, Hp), hin, true, 0, &h->fl_rs[f][l]);
         if (rc) return rc;
       }
@@ -689,7 +693,7 @@ int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, co
       {
         EpiParams e = epi_base(EPI_RS, Hp, T);
         e.mask = mask; e.first = (l == 0); e.xs = f.skip;
-        if (l < NL - 1) { e.n_split = Hw; e.xin = f.h; e.xout = f.h; e.act[0] = f.hop; }
+        if (l < NL - 1) { e.n_split = Hp; e.xin = f.h; e.xout = f.h; e.act[0] = f.hop; }
         else { e.n_split = 0; e.act[0] = f.hout; }
         e.n_act = 1;
         if ((rc = run_conv(cx, h->fl_rs[f_i][l], f.acts, B, T, T, e))) return rc;
