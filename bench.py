@@ -179,7 +179,7 @@ def run_native(args):
     cfg = get_config(CONFIG_NAME)
     sd = synth.make_state_dict(cfg, seed=1234)
     B, T = args.batch, args.frames
-    eng = Engine(cfg, sd, precision=args.precision, device=dev.index)
+    eng = Engine(cfg, sd, precision=args.precision, device=dev.index, residual=args.residual)
     z_p_host, mask_host, _ = synth.make_latents(cfg, B, T, seed=1234 + rank)
     z_p, mask = z_p_host.to(dev), mask_host.to(dev)
     samples_per_step = B * T * 256
@@ -337,7 +337,7 @@ def run_native(args):
         "config": {"workload": f"{CONFIG_NAME} flow-reverse + decoder-from-z, B={B} x T={T} per GPU "
                                f"({samples_per_step} samples = {samples_per_step / sr:.1f} s audio per step per GPU)",
                    "sampling_rate": sr, "l2": "working set per step (~4 GB of activations) >> 126 MB L2; no explicit flush",
-                   "residual_stream": "fp32", "accumulate": "fp32",
+                   "residual_stream": eng.residual, "accumulate": "fp32",
                    "submission": "eager launches" if graph is None else "one CUDA-graph replay per step"},
         "rtf": ms_step * 1e-3 / (world * samples_per_step / sr),
         "clocks": clocks,
@@ -366,6 +366,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--frames", type=int, default=T_FRAMES)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--residual", default=None, choices=["fp16", "fp32"], help="ResBlock residual-stream storage (default: fp16 for bf16)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     args = ap.parse_args()
     if args.impl == "reference":

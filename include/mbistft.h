@@ -82,6 +82,7 @@ typedef struct {
 
 /* debug / tuning flags */
 #define MBV_FLAG_FORCE_SIMT 4       /* run the CUDA-core conv on the tensor-core operand layout (cross-check) */
+#define MBV_FLAG_RESIDUAL_FP16 8    /* bf16 path: keep the decoder's ResBlock residual stream in (saturating) fp16 */
 
 /* An EFFECTIVE weight tensor (weight-norm already folded: w = g*v/||v||), fp32, contiguous,
  * in HOST memory, named as in the reference state-dict minus weight_g/weight_v, e.g.

@@ -6,6 +6,7 @@
 // the tensor cores consume (bf16 / tf32-rounded fp32 / fp32), residual streams are always fp32.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -74,6 +75,38 @@ template <int W> __device__ __forceinline__ void f32_store_vec(float* dst, const
 
 __device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
 
+// fp16 residual stream: saturating round-to-nearest store, widening load
+__device__ __forceinline__ __half to_half_sat(float x) { return __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)); }
+template <int W> __device__ __forceinline__ void res_load_vec(float* v, const void* base, size_t off, int half) {
+  if (half) {
+    const __half* p = reinterpret_cast<const __half*>(base) + off;
+#pragma unroll
+    for (int i = 0; i < W; i += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(p + i);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h2[j]); v[i + 2 * j] = f.x; v[i + 2 * j + 1] = f.y; }
+    }
+  } else {
+    f32_load_vec<W>(v, reinterpret_cast<const float*>(base) + off);
+  }
+}
+template <int W> __device__ __forceinline__ void res_store_vec(void* base, size_t off, const float* v, int half) {
+  if (half) {
+    __half* p = reinterpret_cast<__half*>(base) + off;
+#pragma unroll
+    for (int i = 0; i < W; i += 8) {
+      uint4 u;
+      __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h2[j] = __halves2half2(to_half_sat(v[i + 2 * j]), to_half_sat(v[i + 2 * j + 1]));
+      *reinterpret_cast<uint4*>(p + i) = u;
+    }
+  } else {
+    f32_store_vec<W>(reinterpret_cast<float*>(base) + off, v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // epilogues
 // ------------------------------------------------------------------------------------------------
@@ -99,9 +132,12 @@ struct EpiParams {
   const float* bias; int bias_bs;     // bias[b * bias_bs + n]
   const float* add2; int add2_bs;     // EPI_GATE: per-utterance conditioning (cond_layer(g)) or null
   const float* mask;                  // [B][rows_res] or null
-  const float* xin;
-  float* xout;                        // fp32 residual / plain output
-  float* xs;                          // resblock running sum
+  // residual-stream buffers: fp32, or fp16 when res_half (decoder ResBlock stream with bf16 operands: the stream is
+  // re-rounded once per residual add, 2^-11 relative, invisible next to the 2^-9 operand rounding -- DESIGN.md 3)
+  const void* xin;
+  void* xout;                         // residual / plain output
+  void* xs;                           // resblock running sum
+  int res_half;
   void* act[3];
   const float* act_add[3]; int act_add_bs;  // per-utterance addend before lrelu (ResBlock cond(g))
   int n_act;
@@ -142,7 +178,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int b, int ro
 #pragma unroll
         for (int i = 0; i < W; ++i) acc[i] *= m;
       }
-      if (p.xout) f32_store_vec<W>(p.xout + map_off, acc);
+      if (p.xout) res_store_vec<W>(p.xout, map_off, acc, p.res_half);
       for (int j = 0; j < p.n_act; ++j) {
         if (p.act_add[j]) {
           f32_load_vec<W>(tmp, p.act_add[j] + (size_t)b * p.act_add_bs + n0);
@@ -156,19 +192,19 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int b, int ro
       }
     } break;
     case EPI_RES: {
-      f32_load_vec<W>(tmp, p.xin + res_off);
+      res_load_vec<W>(tmp, p.xin, res_off, p.res_half);
 #pragma unroll
       for (int i = 0; i < W; ++i) acc[i] += tmp[i];
-      if (p.xout) f32_store_vec<W>(p.xout + res_off, acc);
+      if (p.xout) res_store_vec<W>(p.xout, res_off, acc, p.res_half);
       if (p.sum_mode == 1) {
-        f32_store_vec<W>(p.xs + res_off, acc);
+        res_store_vec<W>(p.xs, res_off, acc, p.res_half);
       } else if (p.sum_mode == 2) {
-        f32_load_vec<W>(tmp, p.xs + res_off);
+        res_load_vec<W>(tmp, p.xs, res_off, p.res_half);
 #pragma unroll
         for (int i = 0; i < W; ++i) tmp[i] += acc[i];
-        f32_store_vec<W>(p.xs + res_off, tmp);
+        res_store_vec<W>(p.xs, res_off, tmp, p.res_half);
       } else if (p.sum_mode == 3) {
-        f32_load_vec<W>(tmp, p.xs + res_off);
+        res_load_vec<W>(tmp, p.xs, res_off, p.res_half);
 #pragma unroll
         for (int i = 0; i < W; ++i) acc[i] = (tmp[i] + acc[i]) * p.scale;
       } else if (p.sum_mode == 4) {
@@ -185,7 +221,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int b, int ro
       }
     } break;
     case EPI_F32: {
-      float* dst = p.xout + ((size_t)b * p.rows_out + mrow) * p.ld + n0;
+      float* dst = reinterpret_cast<float*>(p.xout) + ((size_t)b * p.rows_out + mrow) * p.ld + n0;
       if (n0 + W <= p.n_valid && (p.ld & 3) == 0) {
         f32_store_vec<W>(dst, acc);
       } else {
@@ -218,21 +254,21 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int b, int ro
     case EPI_RS: {
       if (p.n_split > 0 && n0 < p.n_split) {
         // residual half: x = (x + rs) * mask -> fp32 stream + operand copy for the next in_layer
-        f32_load_vec<W>(tmp, p.xin + res_off);
+        f32_load_vec<W>(tmp, reinterpret_cast<const float*>(p.xin) + res_off);
 #pragma unroll
         for (int i = 0; i < W; ++i) acc[i] = (acc[i] + tmp[i]) * m;
-        f32_store_vec<W>(p.xout + res_off, acc);
+        f32_store_vec<W>(reinterpret_cast<float*>(p.xout) + res_off, acc);
         op_store_vec<Op, W>(reinterpret_cast<T*>(p.act[0]) + map_off, acc);
       } else {
         // skip half: output += rs; the last layer also applies the mask and emits the operand copy
         const size_t so = ((size_t)b * p.rows_res + row) * p.ld + (n0 - p.n_split);
         if (!p.first) {
-          f32_load_vec<W>(tmp, p.xs + so);
+          f32_load_vec<W>(tmp, reinterpret_cast<const float*>(p.xs) + so);
 #pragma unroll
           for (int i = 0; i < W; ++i) acc[i] += tmp[i];
         }
         if (p.n_split > 0) {
-          f32_store_vec<W>(p.xs + so, acc);
+          f32_store_vec<W>(reinterpret_cast<float*>(p.xs) + so, acc);
         } else {
 #pragma unroll
           for (int i = 0; i < W; ++i) acc[i] *= m;
@@ -242,10 +278,10 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int b, int ro
     } break;
     case EPI_POST: {
       const size_t zo = ((size_t)b * p.rows_res + row) * p.ld + p.ch_off + n0;
-      f32_load_vec<W>(tmp, p.xin + zo);
+      f32_load_vec<W>(tmp, reinterpret_cast<const float*>(p.xin) + zo);
 #pragma unroll
       for (int i = 0; i < W; ++i) acc[i] = (tmp[i] - acc[i] * m) * m;
-      f32_store_vec<W>(p.xout + zo, acc);
+      f32_store_vec<W>(reinterpret_cast<float*>(p.xout) + zo, acc);
       op_store_vec<Op, W>(reinterpret_cast<T*>(p.act[0]) + zo, acc);
     } break;
     default: break;

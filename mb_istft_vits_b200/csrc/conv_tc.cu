@@ -175,6 +175,16 @@ __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)kDes
 template <typename Op> __device__ __forceinline__ void op_store1(typename Op::T* p, float v) { *p = op_round<Op>(v); }
 template <> __device__ __forceinline__ void op_store1<OpBF16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
+// residual-stream element: fp32 or (RH) saturating fp16
+template <bool RH> struct ResT { using T = float; };
+template <> struct ResT<true> { using T = __half; };
+template <bool RH> __device__ __forceinline__ float res_ld(const typename ResT<RH>::T* p) {
+  if constexpr (RH) return __half2float(*p); else return *p;
+}
+template <bool RH> __device__ __forceinline__ void res_st(typename ResT<RH>::T* p, float v) {
+  if constexpr (RH) *p = to_half_sat(v); else *p = v;
+}
+
 __device__ __forceinline__ float fast_tanh(float x) {
   // tanh(x) = 1 - 2 / (exp(2x) + 1); exact limits at +-inf, abs error ~1e-7 relative to the fp32 reference
   const float e = __expf(2.f * x);
@@ -199,7 +209,7 @@ struct TcRt {  // runtime scalars the kernel needs beyond ConvArgs
 // ------------------------------------------------------------------------------------------------
 #define MBV_EL(i) if (FULL || (i) < nt)
 
-template <typename Op, int STEP, bool FULL>
+template <typename Op, int STEP, bool FULL, bool RH>
 __device__ __forceinline__ void epi_act(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
                                         size_t rstep, const float* acc) {
   using T = typename Op::T;
@@ -216,9 +226,9 @@ __device__ __forceinline__ void epi_act(const EpiParams& p, int b, int n, int ph
     for (int i = 0; i < 32; ++i) y[i] = acc[i] + bias;
   }
   if (p.xout) {
-    float* xo = p.xout + off0;
+    typename ResT<RH>::T* xo = reinterpret_cast<typename ResT<RH>::T*>(p.xout) + off0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) MBV_EL(i) xo[i * step] = y[i];
+    for (int i = 0; i < 32; ++i) MBV_EL(i) res_st<RH>(xo + i * step, y[i]);
   }
   const float slope = p.slope;
   for (int j = 0; j < p.n_act; ++j) {
@@ -234,7 +244,7 @@ __device__ __forceinline__ void epi_act(const EpiParams& p, int b, int n, int ph
   }
 }
 
-template <typename Op, int STEP, bool FULL>
+template <typename Op, int STEP, bool FULL, bool RH>
 __device__ __forceinline__ void epi_res(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
                                         size_t rstep, const float* acc, const float* xpre) {
   using T = typename Op::T;
@@ -247,9 +257,9 @@ __device__ __forceinline__ void epi_res(const EpiParams& p, int b, int n, int ph
   const int sm = p.sum_mode;
   if (sm == 2 || sm == 3) {
     float sv[32];
-    const float* sp = p.xs + base;
+    const typename ResT<RH>::T* sp = reinterpret_cast<const typename ResT<RH>::T*>(p.xs) + base;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { sv[i] = 0.f; MBV_EL(i) sv[i] = sp[i * step]; }
+    for (int i = 0; i < 32; ++i) { sv[i] = 0.f; MBV_EL(i) sv[i] = res_ld<RH>(sp + i * step); }
 #pragma unroll
     for (int i = 0; i < 32; ++i) x[i] = (x[i] + acc[i] + bias) + sv[i];
   } else {
@@ -257,14 +267,14 @@ __device__ __forceinline__ void epi_res(const EpiParams& p, int b, int n, int ph
     for (int i = 0; i < 32; ++i) x[i] = x[i] + acc[i] + bias;
   }
   if (p.xout) {
-    float* xo = p.xout + base;
+    typename ResT<RH>::T* xo = reinterpret_cast<typename ResT<RH>::T*>(p.xout) + base;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) MBV_EL(i) xo[i * step] = x[i];
+    for (int i = 0; i < 32; ++i) MBV_EL(i) res_st<RH>(xo + i * step, x[i]);
   }
   if (sm == 1 || sm == 2) {
-    float* so = p.xs + base;
+    typename ResT<RH>::T* so = reinterpret_cast<typename ResT<RH>::T*>(p.xs) + base;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) MBV_EL(i) so[i * step] = x[i];
+    for (int i = 0; i < 32; ++i) MBV_EL(i) res_st<RH>(so + i * step, x[i]);
   }
   if (p.n_act) {
     const float slope = p.slope, scale = (sm >= 3) ? p.scale : 1.f;
@@ -290,7 +300,7 @@ __device__ __forceinline__ void epi_f32(const EpiParams& p, int b, int n, int ph
                                         size_t rstep, const float* acc) {
   const size_t step = STEP > 0 ? (size_t)STEP : rstep;
   const float bias = p.bias[(size_t)b * p.bias_bs + n];
-  float* o = p.xout + ((size_t)b * p.rows_out + t_first) * p.ld + n;
+  float* o = reinterpret_cast<float*>(p.xout) + ((size_t)b * p.rows_out + t_first) * p.ld + n;
 #pragma unroll
   for (int i = 0; i < 32; ++i) MBV_EL(i) o[i * step] = acc[i] + bias;
 }
@@ -328,7 +338,7 @@ __device__ __forceinline__ void epi_rs(const EpiParams& p, int b, int n, int pha
   if (res_half) {  // x = (x + rs) * mask -> fp32 stream + operand copy for the next in_layer
 #pragma unroll
     for (int i = 0; i < 32; ++i) { x[i] = 0.f; MBV_EL(i) x[i] = (xpre[i] + acc[i] + bias) * mp[i]; }
-    float* xo = p.xout + base;
+    float* xo = reinterpret_cast<float*>(p.xout) + base;
     T* dst = reinterpret_cast<T*>(p.act[0]) + base;
 #pragma unroll
     for (int i = 0; i < 32; ++i) MBV_EL(i) { xo[i * step] = x[i]; op_store1<Op>(dst + i * step, x[i]); }
@@ -336,7 +346,7 @@ __device__ __forceinline__ void epi_rs(const EpiParams& p, int b, int n, int pha
 #pragma unroll
     for (int i = 0; i < 32; ++i) x[i] = acc[i] + bias + xpre[i];  // xpre = running skip sum (zeros for the first layer)
     if (p.n_split > 0) {
-      float* so = p.xs + base;
+      float* so = reinterpret_cast<float*>(p.xs) + base;
 #pragma unroll
       for (int i = 0; i < 32; ++i) MBV_EL(i) so[i * step] = x[i];
     } else {
@@ -355,7 +365,7 @@ __device__ __forceinline__ void epi_post(const EpiParams& p, int b, int n, int p
   const float bias = p.bias[(size_t)b * p.bias_bs + n];
   const size_t base = ((size_t)b * p.rows_res + t_first) * p.ld + p.ch_off + n;
   const float* mp = p.mask + (size_t)b * p.rows_res + t_first;
-  float* zo = p.xout + base;
+  float* zo = reinterpret_cast<float*>(p.xout) + base;
   T* dst = reinterpret_cast<T*>(p.act[0]) + base;
   float z[32];
 #pragma unroll
@@ -367,11 +377,11 @@ __device__ __forceinline__ void epi_post(const EpiParams& p, int b, int n, int p
   for (int i = 0; i < 32; ++i) MBV_EL(i) { zo[i * step] = z[i]; op_store1<Op>(dst + i * step, z[i]); }
 }
 
-template <typename Op, int MODE, int STEP, bool FULL>
+template <typename Op, int MODE, int STEP, bool FULL, bool RH>
 __device__ __forceinline__ void epi_dispatch(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
                                              size_t rstep, const float* acc, const float* acc2, const float* xpre) {
-  if constexpr (MODE == EPI_ACT) epi_act<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc);
-  else if constexpr (MODE == EPI_RES) epi_res<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
+  if constexpr (MODE == EPI_ACT) epi_act<Op, STEP, FULL, RH>(p, b, n, phase, t_first, nt, rstep, acc);
+  else if constexpr (MODE == EPI_RES) epi_res<Op, STEP, FULL, RH>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
   else if constexpr (MODE == EPI_F32) epi_f32<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc);
   else if constexpr (MODE == EPI_GATE) epi_gate<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc, acc2);
   else if constexpr (MODE == EPI_RS) epi_rs<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
@@ -381,19 +391,30 @@ __device__ __forceinline__ void epi_dispatch(const EpiParams& p, int b, int n, i
 // Residual-like input of a chunk (xin for EPI_RES / the residual half of EPI_RS, the running skip sum for the skip
 // half, z for EPI_POST).  It does not depend on the accumulator, so the epilogue warps issue these loads one chunk
 // AHEAD -- for the first chunk of a tile that is before the tile's MMAs have finished -- hiding the DRAM latency.
-template <int MODE, int LD>
+template <int MODE, int LD, bool RH>
 __device__ __forceinline__ void epi_prefetch(const EpiParams& p, int b, int n, int t_first, int nt, float* xpre) {
   const size_t step = LD > 0 ? (size_t)LD : (size_t)p.ld;
+  if constexpr (MODE == EPI_RES && RH) {
+    const __half* hs = reinterpret_cast<const __half*>(p.xin) + ((size_t)b * p.rows_res + t_first) * p.ld + n;
+    if (nt == 32) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) xpre[i] = __half2float(hs[i * step]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) xpre[i] = (i < nt) ? __half2float(hs[i * step]) : 0.f;
+    }
+    return;
+  }
   const float* src = nullptr;
   if constexpr (MODE == EPI_RES) {
-    src = p.xin + ((size_t)b * p.rows_res + t_first) * p.ld + n;
+    src = reinterpret_cast<const float*>(p.xin) + ((size_t)b * p.rows_res + t_first) * p.ld + n;
   } else if constexpr (MODE == EPI_RS) {
     const bool res_half = (p.n_split > 0 && n < p.n_split);
     const int c = res_half ? n : n - p.n_split;
-    if (res_half) src = p.xin + ((size_t)b * p.rows_res + t_first) * p.ld + c;
-    else if (!p.first) src = p.xs + ((size_t)b * p.rows_res + t_first) * p.ld + c;
+    if (res_half) src = reinterpret_cast<const float*>(p.xin) + ((size_t)b * p.rows_res + t_first) * p.ld + c;
+    else if (!p.first) src = reinterpret_cast<const float*>(p.xs) + ((size_t)b * p.rows_res + t_first) * p.ld + c;
   } else if constexpr (MODE == EPI_POST) {
-    src = p.xin + ((size_t)b * p.rows_res + t_first) * p.ld + p.ch_off + n;
+    src = reinterpret_cast<const float*>(p.xin) + ((size_t)b * p.rows_res + t_first) * p.ld + p.ch_off + n;
   }
   if (src != nullptr && nt == 32) {
 #pragma unroll
@@ -406,20 +427,20 @@ __device__ __forceinline__ void epi_prefetch(const EpiParams& p, int b, int n, i
 
 // LD: compile-time channel pitch of the destination buffers (0 = runtime).  The immediate-offset fast path also
 // needs row_mul == 1 (everything but the polyphase upsamplers).
-template <typename Op, int MODE, int LD>
+template <typename Op, int MODE, int LD, bool RH>
 __device__ __forceinline__ void tc_epilogue32(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
                                               const float* acc, const float* acc2, const float* xpre) {
   const size_t rstep = (size_t)p.row_mul * p.ld;
   if (LD > 0 && p.row_mul == 1) {
-    if (nt == 32) epi_dispatch<Op, MODE, LD, true>(p, b, n, phase, t_first, nt, rstep, acc, acc2, xpre);
-    else epi_dispatch<Op, MODE, LD, false>(p, b, n, phase, t_first, nt, rstep, acc, acc2, xpre);
+    if (nt == 32) epi_dispatch<Op, MODE, LD, true, RH>(p, b, n, phase, t_first, nt, rstep, acc, acc2, xpre);
+    else epi_dispatch<Op, MODE, LD, false, RH>(p, b, n, phase, t_first, nt, rstep, acc, acc2, xpre);
   } else {
-    if (nt == 32) epi_dispatch<Op, MODE, 0, true>(p, b, n, phase, t_first, nt, rstep, acc, acc2, xpre);
-    else epi_dispatch<Op, MODE, 0, false>(p, b, n, phase, t_first, nt, rstep, acc, acc2, xpre);
+    if (nt == 32) epi_dispatch<Op, MODE, 0, true, RH>(p, b, n, phase, t_first, nt, rstep, acc, acc2, xpre);
+    else epi_dispatch<Op, MODE, 0, false, RH>(p, b, n, phase, t_first, nt, rstep, acc, acc2, xpre);
   }
 }
 
-template <typename Op, int MODE, int LD>
+template <typename Op, int MODE, int LD, bool RH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                const ConvArgs a, const TcRt rt) {
@@ -582,7 +603,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     auto prefetch = [&](const TileInfo& ti, int c, float* dst) {
       const int t_first = ti.t0 + c;
       if (ti.valid && t_first < ti.t_lim)
-        epi_prefetch<MODE, LD>(a.epi, ti.b, ti.n, t_first, min(ti.t_lim - t_first, 32), dst);
+        epi_prefetch<MODE, LD, RH>(a.epi, ti.b, ti.n, t_first, min(ti.t_lim - t_first, 32), dst);
     };
 
     float xcur[32], xnext[32];
@@ -607,7 +628,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         tmem_ld_wait();
         const int t_first = ti.t0 + c;
         if (ti.valid && t_first < ti.t_lim)
-          tc_epilogue32<Op, MODE, LD>(a.epi, ti.b, ti.n, ti.phase, t_first, min(ti.t_lim - t_first, 32), acc, acc2, xcur);
+          tc_epilogue32<Op, MODE, LD, RH>(a.epi, ti.b, ti.n, ti.phase, t_first, min(ti.t_lim - t_first, 32), acc, acc2, xcur);
         if constexpr (kPrefetch) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) xcur[i] = xnext[i];
@@ -708,9 +729,9 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
 }
 
 // kernel table: (mode, compile-time pitch) instantiations; pitch 0 = runtime
-template <typename Op, int MODE, int LD>
+template <typename Op, int MODE, int LD, bool RH = false>
 static cudaError_t launch_one(const ConvArgs& a, const TcPlan& p, const TcRt& rt, cudaStream_t st, bool set_attr) {
-  auto k = conv_tc_kernel<Op, MODE, LD>;
+  auto k = conv_tc_kernel<Op, MODE, LD, RH>;
   if (set_attr) return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p.grid);
@@ -727,7 +748,15 @@ static cudaError_t launch_one(const ConvArgs& a, const TcPlan& p, const TcRt& rt
 
 template <typename Op>
 static cudaError_t dispatch(const ConvArgs& a, const TcPlan& p, const TcRt& rt, cudaStream_t st, bool set_attr, int mode,
-                            int ld) {
+                            int ld, int res_half) {
+  if (res_half) {  // fp16 residual stream: decoder ACT (upsampler) and RES (ResBlock) epilogues only
+#define MBV_CASE_H(M, L) if (mode == M && ld == L) return launch_one<Op, M, L, true>(a, p, rt, st, set_attr);
+    MBV_CASE_H(EPI_ACT, 128) MBV_CASE_H(EPI_ACT, 256) MBV_CASE_H(EPI_RES, 128) MBV_CASE_H(EPI_RES, 256)
+#undef MBV_CASE_H
+    if (mode == EPI_ACT) return launch_one<Op, EPI_ACT, 0, true>(a, p, rt, st, set_attr);
+    if (mode == EPI_RES) return launch_one<Op, EPI_RES, 0, true>(a, p, rt, st, set_attr);
+    return cudaErrorInvalidValue;
+  }
 #define MBV_CASE(M, L) if (mode == M && ld == L) return launch_one<Op, M, L>(a, p, rt, st, set_attr);
   MBV_CASE(EPI_ACT, 128) MBV_CASE(EPI_ACT, 256) MBV_CASE(EPI_ACT, 192)
   MBV_CASE(EPI_RES, 128) MBV_CASE(EPI_RES, 256)
@@ -750,10 +779,14 @@ cudaError_t tc_set_attributes() {
   const int lds[] = {0, 128, 192, 256};
   for (int mode = EPI_ACT; mode <= EPI_POST; ++mode)
     for (int ld : lds) {
-      cudaError_t e = dispatch<OpBF16>(a, p, rt, nullptr, true, mode, ld);
+      cudaError_t e = dispatch<OpBF16>(a, p, rt, nullptr, true, mode, ld, 0);
       if (e != cudaSuccess) return e;
-      e = dispatch<OpTF32>(a, p, rt, nullptr, true, mode, ld);
+      e = dispatch<OpTF32>(a, p, rt, nullptr, true, mode, ld, 0);
       if (e != cudaSuccess) return e;
+      if (mode == EPI_ACT || mode == EPI_RES) {
+        e = dispatch<OpBF16>(a, p, rt, nullptr, true, mode, ld, 1);
+        if (e != cudaSuccess) return e;
+      }
     }
   return cudaSuccess;
 }
@@ -764,8 +797,9 @@ cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStr
   rt.slab_stage_bytes = p.slab_stage_bytes; rt.w_stage_bytes = p.w_stage_bytes;
   rt.n_slab_stages = p.n_slab_stages; rt.n_w_stages = p.n_w_stages;
   rt.t_tiles = p.t_tiles; rt.c_tiles = p.c_tiles; rt.total_tiles = p.total_tiles;
-  if (prec == 2) return dispatch<OpBF16>(a, p, rt, st, false, a.epi.mode, a.epi.ld);
-  return dispatch<OpTF32>(a, p, rt, st, false, a.epi.mode, a.epi.ld);
+  if (prec == 2) return dispatch<OpBF16>(a, p, rt, st, false, a.epi.mode, a.epi.ld, a.epi.res_half);
+  if (a.epi.res_half) return cudaErrorInvalidValue;
+  return dispatch<OpTF32>(a, p, rt, st, false, a.epi.mode, a.epi.ld, 0);
 }
 
 }  // namespace mbv

@@ -66,6 +66,8 @@ struct mbv_handle {
   mbv_config cfg;
   int prec = 0;
   int esize = 4;
+  int res_half = 0;  // decoder residual stream in fp16 (MBV_FLAG_RESIDUAL_FP16, bf16 precision only)
+  int rsize = 4;
   int num_sms = 148;
   bool weights_loaded = false;
   std::string err;
@@ -323,6 +325,11 @@ extern "C" int mbv_create(const mbv_config* cfg, mbv_handle** out) {
   if (c.precision < 0 || c.precision > 2) return fail(h, MBV_ERR_INVALID, "precision must be 0 (fp32), 1 (tf32) or 2 (bf16)");
   h->prec = c.precision;
   h->esize = c.precision == MBV_PREC_BF16 ? 2 : 4;
+  if (c.flags & MBV_FLAG_RESIDUAL_FP16) {
+    if (c.precision != MBV_PREC_BF16) return fail(h, MBV_ERR_INVALID, "MBV_FLAG_RESIDUAL_FP16 requires MBV_PREC_BF16 (the fp32/tf32 paths keep an fp32 residual stream)");
+    h->res_half = 1;
+    h->rsize = 2;
+  }
   if (c.inter_channels <= 0 || c.inter_channels % 64 != 0 || (c.inter_channels / 2) % 16 != 0)
     return fail(h, MBV_ERR_UNSUPPORTED, "inter_channels must be a multiple of 64 (got %d)", c.inter_channels);
   if (c.hidden_channels <= 0 || c.hidden_channels % 16 != 0)
@@ -556,7 +563,7 @@ struct Arena {
 
 struct DecBufs {
   void* zin_op; void* pre_act;
-  struct Stage { float* x; void* a[3]; float* xr; void* ar; void* hop; float* xs; void* next; } st[MBV_MAX_UPS];
+  struct Stage { void* x; void* a[3]; void* xr; void* ar; void* hop; void* xs; void* next; } st[MBV_MAX_UPS];
   float* logits;
   float* cond;  // [n_stage][n_kernels][2][B][C]: (cond, bias2+cond) per resblock
 };
@@ -574,13 +581,13 @@ void layout_dec(mbv_handle* h, Arena& A, int B, int T, DecBufs* d) {
     const int C = h->stage_C[i];
     const size_t n = (size_t)B * L * C;
     auto& s = d->st[i];
-    s.x = (float*)A.take(n * 4);
+    s.x = A.take(n * h->rsize);
     const int na = h->cfg.gin_channels ? h->cfg.n_kernels : 1;
     for (int j = 0; j < 3; ++j) s.a[j] = j < na ? A.take(n * es) : nullptr;
-    s.xr = (float*)A.take(n * 4);
+    s.xr = A.take(n * h->rsize);
     s.ar = A.take(n * es);
     s.hop = A.take(n * es);
-    s.xs = (float*)A.take(n * 4);
+    s.xs = A.take(n * h->rsize);
     const bool last = (i == h->n_stage - 1);
     s.next = A.take((size_t)B * (L + (last ? 1 : 0)) * C * es);
   }
@@ -774,7 +781,7 @@ int run_decode(Ctx& cx, const DecBufs& d, const float* z, const float* z_mask, c
     }
     {  // x = ups[i](lrelu(x)): S polyphase branches; emits the fp32 residual stream and lrelu(x [+ cond_j]) operand copies
       EpiParams e = epi_base(EPI_ACT, C, L);
-      e.rows_res = Lin; e.row_mul = S; e.slope = 0.1f; e.xout = s.x;
+      e.rows_res = Lin; e.row_mul = S; e.slope = 0.1f; e.xout = s.x; e.res_half = h->res_half;
       e.n_act = g ? nk : 1;
       for (int j = 0; j < e.n_act; ++j) { e.act[j] = s.a[j]; e.act_add[j] = g ? cond[j] : nullptr; }
       e.act_add_bs = C;
@@ -782,12 +789,12 @@ int run_decode(Ctx& cx, const DecBufs& d, const float* z, const float* z_mask, c
     }
     for (int j = 0; j < nk; ++j) {
       const void* a_in = g ? s.a[j] : s.a[0];
-      const float* x_in = s.x;
+      const void* x_in = s.x;
       const int np = c.n_dilations;
       for (int p = 0; p < np; ++p) {
         const bool final_conv = (p == np - 1);
         EpiParams e = epi_base(EPI_RES, C, L);
-        e.xin = x_in; e.slope = 0.1f;
+        e.xin = x_in; e.slope = 0.1f; e.res_half = h->res_half;
         if (p == 0 && g) { e.bias = bias2c[j]; e.bias_bs = C; }  // x + cond(g) folded into the first residual add
         if (final_conv) {
           e.xs = s.xs;

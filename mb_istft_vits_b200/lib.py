@@ -19,6 +19,7 @@ VARIANTS = {"istft": 0, "mb": 1, "ms": 2}
 PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2}
 
 FLAG_FORCE_SIMT = 4
+FLAG_RESIDUAL_FP16 = 8
 
 ERRORS = {0: "MBV_OK", -1: "MBV_ERR_INVALID", -2: "MBV_ERR_UNSUPPORTED", -3: "MBV_ERR_WEIGHTS",
           -4: "MBV_ERR_WORKSPACE", -5: "MBV_ERR_CUDA"}

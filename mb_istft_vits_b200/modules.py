@@ -56,10 +56,10 @@ class NativeDecoder(nn.Module):
         """Weight-norm is folded at load time; nothing to do (reference: models.py:299/379/469)."""
 
 
-def patch_synthesizer(net_g, cfg, precision="bf16", device=0, flags=0):
+def patch_synthesizer(net_g, cfg, precision="bf16", device=0, flags=0, residual=None):
     """Replace net_g.flow and net_g.dec by the native path, using net_g's own weights."""
     sd = {k: v for k, v in net_g.state_dict().items() if k.startswith(("dec.", "flow."))}
-    eng = Engine(cfg, sd, precision=precision, device=device, flags=flags)
+    eng = Engine(cfg, sd, precision=precision, device=device, flags=flags, residual=residual)
     net_g.flow = NativeFlow(eng)
     net_g.dec = NativeDecoder(eng)
     return eng

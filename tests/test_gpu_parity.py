@@ -13,9 +13,9 @@ from mb_istft_vits_b200 import get_config, synth
 pytestmark = pytest.mark.gpu
 
 
-def _engine(cfg, sd, prec, flags=0):
+def _engine(cfg, sd, prec, flags=0, residual=None):
     from mb_istft_vits_b200 import Engine
-    return Engine(cfg, sd, precision=prec, flags=flags)
+    return Engine(cfg, sd, precision=prec, flags=flags, residual=residual)
 
 
 def _run(eng, t):
@@ -65,6 +65,18 @@ def test_bf16_path_snr_at_least_40db(name):
     assert orc.snr_db(z, t["z"]) > 40.0
     assert orc.snr_db(wav, t["o"]) > 40.0
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["mb", "mb_gscale", "ms_spk", "istft", "mb_resblock2"])
+def test_bf16_path_with_fp32_residual_stream(name):
+    """The bf16 path defaults to an fp16 (saturating) ResBlock residual stream; the fp32-stream variant must pass the
+    same bar, and the two must agree with each other much better than either agrees with the fp32 reference."""
+    cfg, sd, t, meta = load_case(name)
+    a = _run(_engine(cfg, sd, "bf16", residual="fp32"), t)
+    b = _run(_engine(cfg, sd, "bf16", residual="fp16"), t)
+    assert orc.snr_db(a[1], t["o"]) > 40.0 and orc.snr_db(b[1], t["o"]) > 40.0
+    assert orc.snr_db(b[1], a[1]) > 50.0
+    assert abs(orc.snr_db(a[1], t["o"]) - orc.snr_db(b[1], t["o"])) < 1.5
 
 
 @pytest.mark.parametrize("prec", ["bf16", "tf32"])
