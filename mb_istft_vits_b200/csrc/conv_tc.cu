@@ -95,6 +95,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// L2 prefetch of a tensor box: no shared-memory destination, no barrier
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -198,6 +203,7 @@ struct TcRt {  // runtime scalars the kernel needs beyond ConvArgs
   int n_boxes;       // 1 or 2
   int slab_stage_bytes, w_stage_bytes, n_slab_stages, n_w_stages;
   int t_tiles, c_tiles, total_tiles;
+  int prefetch_res;  // issue an L2 prefetch of the tile's residual input (tmR) when its operand loads start
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -443,7 +449,7 @@ __device__ __forceinline__ void tc_epilogue32(const EpiParams& p, int b, int n, 
 template <typename Op, int MODE, int LD, bool RH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-               const ConvArgs a, const TcRt rt) {
+               const __grid_constant__ CUtensorMap tmR, const ConvArgs a, const TcRt rt) {
   using T = typename Op::T;
   constexpr int KB = TC_ROW_BYTES / (int)sizeof(T);  // channels per k-block
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -499,6 +505,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const int t0 = tt * rt.n_time;
       const int wrow0 = phase * a.taps * a.N_total + ct * TC_M;
       const int xrow0 = t0 + a.shift0[phase];
+      // The epilogue's residual loads are latency-bound (Little's law: 8 warps x 32 x 64 B in flight per SM against
+      // ~1 us of DRAM latency = 1.6 TB/s chip-wide -- measured).  Pull the tile's residual box into L2 now, a whole
+      // tile-time before the epilogue asks for it, so those loads see L2 latency instead.
+      if (MODE == EPI_RES && rt.prefetch_res && elect_one()) tma_prefetch_l2_3d(&tmR, ct * TC_M, t0, b);
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(BAR(iXE + sx), px ^ 1);
         if (elect_one()) {
@@ -725,6 +735,19 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed for the weight map";
   }
+  plan->prefetch_res = 0;
+  if (a.epi.mode == EPI_RES && a.epi.xin != nullptr && a.epi.row_mul == 1) {
+    const int rs = a.epi.res_half ? 2 : 4;
+    cuuint64_t dims[3] = {(cuuint64_t)a.epi.ld, (cuuint64_t)a.epi.rows_res, (cuuint64_t)a.B};
+    cuuint64_t strides[2] = {(cuuint64_t)a.epi.ld * rs, (cuuint64_t)a.epi.rows_res * a.epi.ld * rs};
+    cuuint32_t box[3] = {(cuuint32_t)(a.epi.ld < TC_M ? a.epi.ld : TC_M), (cuuint32_t)n_time, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&plan->tmR, a.epi.res_half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                     const_cast<void*>(a.epi.xin), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) plan->prefetch_res = 1;  // a failed encode only loses the prefetch
+  }
+  if (!plan->prefetch_res) plan->tmR = plan->tmA;  // placeholder, never dereferenced
   return nullptr;
 }
 
@@ -743,7 +766,7 @@ static cudaError_t launch_one(const ConvArgs& a, const TcPlan& p, const TcRt& rt
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k, p.tmA, p.tmB, a, rt);
+  return cudaLaunchKernelEx(&cfg, k, p.tmA, p.tmB, p.tmR, a, rt);
 }
 
 template <typename Op>
@@ -797,6 +820,7 @@ cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStr
   rt.slab_stage_bytes = p.slab_stage_bytes; rt.w_stage_bytes = p.w_stage_bytes;
   rt.n_slab_stages = p.n_slab_stages; rt.n_w_stages = p.n_w_stages;
   rt.t_tiles = p.t_tiles; rt.c_tiles = p.c_tiles; rt.total_tiles = p.total_tiles;
+  rt.prefetch_res = p.prefetch_res;
   if (prec == 2) return dispatch<OpBF16>(a, p, rt, st, false, a.epi.mode, a.epi.ld, a.epi.res_half);
   if (a.epi.res_half) return cudaErrorInvalidValue;
   return dispatch<OpTF32>(a, p, rt, st, false, a.epi.mode, a.epi.ld, 0);

@@ -13,6 +13,8 @@ cudaError_t launch_conv_simt(int prec, const ConvArgs& a, cudaStream_t st);
 struct TcPlan {
   CUtensorMap tmA;      // activations: 3-D (Cp_in, L_in, B), box (KB, box_rows, 1), 128B swizzle
   CUtensorMap tmB;      // weights: 2-D (Cp_in, phases*taps*N_total), box (KB, 128), 128B swizzle
+  CUtensorMap tmR;      // residual input (EPI_RES xin): 3-D (C, rows, B), box (128, n_time, 1), used for L2 prefetch only
+  int prefetch_res;     // 1: tmR is valid
   int n_time;           // time columns per tile (UMMA N)
   int slab_rows, box_rows, n_boxes;
   int slab_stage_bytes, w_stage_bytes, n_slab_stages, n_w_stages;
