@@ -505,10 +505,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const int t0 = tt * rt.n_time;
       const int wrow0 = phase * a.taps * a.N_total + ct * TC_M;
       const int xrow0 = t0 + a.shift0[phase];
-      // The epilogue's residual loads are latency-bound (Little's law: 8 warps x 32 x 64 B in flight per SM against
-      // ~1 us of DRAM latency = 1.6 TB/s chip-wide -- measured).  Pull the tile's residual box into L2 now, a whole
-      // tile-time before the epilogue asks for it, so those loads see L2 latency instead.
-      if (MODE == EPI_RES && rt.prefetch_res && elect_one()) tma_prefetch_l2_3d(&tmR, ct * TC_M, t0, b);
+      // (A whole-tile TMA L2 prefetch of the residual box issued here was measured to be too early: a tile-time later
+      //  a third of it had been evicted again and DRAM reads grew 40 %.  The epilogue warps prefetch two chunks ahead.)
+      if (false && MODE == EPI_RES && rt.prefetch_res && elect_one()) tma_prefetch_l2_3d(&tmR, ct * TC_M, t0, b);
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(BAR(iXE + sx), px ^ 1);
         if (elect_one()) {
@@ -610,6 +609,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       ti.t_lim = min(a.L_out, ti.t0 + rt.n_time);
       return ti;
     };
+    // The residual loads are latency-bound (Little's law: 8 warps x 32 x 64 B in flight per SM against ~1 us of DRAM
+    // latency; ncu: long_scoreboard dominates).  Each lane therefore asks L2 for one row of the chunk two work items
+    // ahead (its warp's 32 channels = 64-128 contiguous bytes), so the register prefetch one item ahead hits L2.
+    auto l2_prefetch = [&](const TileInfo& ti, int c) {
+      if constexpr (MODE == EPI_RES) {
+        const int t = ti.t0 + c + lane;
+        if (ti.valid && c < rt.n_time && t < ti.t_lim) {
+          const size_t off = ((size_t)ti.b * a.epi.rows_res + t) * a.epi.ld + (ti.n - lane);
+          const char* p = reinterpret_cast<const char*>(a.epi.xin) + off * (RH ? 2 : 4);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        }
+      }
+    };
+    const int nch = (rt.n_time - c_first + 63) / 64;  // chunks per tile for this warp
     auto prefetch = [&](const TileInfo& ti, int c, float* dst) {
       const int t_first = ti.t0 + c;
       if (ti.valid && t_first < ti.t_lim)
@@ -632,6 +645,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         tmem_ld32(taddr + (uint32_t)c, acc);
         if constexpr (MODE == EPI_GATE) tmem_ld32(taddr + (uint32_t)(rt.n_time + c), acc2);
         if constexpr (kPrefetch) {  // next chunk of this tile, or the first chunk of this CTA's next tile
+          const int j2 = (c - c_first) / 64 + 2;
+          if (j2 < nch) l2_prefetch(ti, c_first + 64 * j2);
+          else if (have_next) l2_prefetch(tn, c_first + 64 * (j2 - nch));
           if (c + 64 < rt.n_time) prefetch(ti, c + 64, xnext);
           else if (have_next) prefetch(tn, c_first, xnext);
         }
