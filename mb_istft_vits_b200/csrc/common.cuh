@@ -144,7 +144,7 @@ struct EpiParams {
   float slope;      // leaky-relu slope of the operand copies (1 = identity)
   float scale;      // 1 / num_kernels for the final resblock-sum
   int sum_mode;     // EPI_RES: 0 none, 1 xs = x, 2 xs += x, 3 final: v = (xs + x) * scale, 4 final of a single resblock: v = x * scale
-  int n_split;      // EPI_GATE: offset of the sigmoid half in bias/add2; EPI_RS: width of the residual half (0 = last layer)
+  int n_split;      // EPI_RS: width of the residual half (0 = last layer)
   int ch_off;       // EPI_POST: first channel updated
   int first;        // EPI_RS: first WN layer (skip accumulator is set, not added)
 };
@@ -160,9 +160,10 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int b, int ro
     const int c0 = (p.mode == EPI_RS && p.n_split > 0 && n0 >= p.n_split) ? n0 - p.n_split : n0;
     if (c0 >= p.n_valid) return;
   }
-  // bias
+  // bias (indexed by packed weight row; the gate packs 128-row tiles of [64 tanh | 64 sigmoid] rows)
+  const int brow = (p.mode == EPI_GATE) ? 128 * (n0 >> 6) + (n0 & 63) : n0;
   {
-    const float* bp = p.bias + (size_t)b * p.bias_bs + n0;
+    const float* bp = p.bias + (size_t)b * p.bias_bs + brow;
     f32_load_vec<W>(tmp, bp);
 #pragma unroll
     for (int i = 0; i < W; ++i) acc[i] += tmp[i];
@@ -231,15 +232,15 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int b, int ro
       }
     } break;
     case EPI_GATE: {
-      f32_load_vec<W>(tmp, p.bias + (size_t)b * p.bias_bs + p.n_split + n0);
+      f32_load_vec<W>(tmp, p.bias + (size_t)b * p.bias_bs + brow + 64);
 #pragma unroll
       for (int i = 0; i < W; ++i) acc2[i] += tmp[i];
       if (p.add2) {
-        const float* gp = p.add2 + (size_t)b * p.add2_bs + n0;
+        const float* gp = p.add2 + (size_t)b * p.add2_bs + brow;
         f32_load_vec<W>(tmp, gp);
 #pragma unroll
         for (int i = 0; i < W; ++i) acc[i] += tmp[i];
-        f32_load_vec<W>(tmp, gp + p.n_split);
+        f32_load_vec<W>(tmp, gp + 64);
 #pragma unroll
         for (int i = 0; i < W; ++i) acc2[i] += tmp[i];
       }
@@ -300,12 +301,12 @@ struct ConvArgs {
   int L_in;           // rows per utterance of x
   int L_out;          // rows computed per utterance and phase
   int Cp_in;          // padded input channels (multiple of 64)
-  int N_total;        // packed weight rows per tap (multiple of 128; gate: [tanh half | sigmoid half])
+  int N_total;        // packed weight rows per tap (multiple of 128)
   int taps;
   int dil;            // row step between taps
   int n_phases;       // >1 for the polyphase transposed convolutions
   int shift0[kMaxPhases];  // row offset of tap 0 per phase
-  int gate;           // EPI_GATE: two accumulators per tile (tanh rows, sigmoid rows N_total/2 further)
+  int gate;           // EPI_GATE: weight rows packed as 128-row tiles [64 tanh | 64 sigmoid] of 64 consecutive channels
   EpiParams epi;
 };
 

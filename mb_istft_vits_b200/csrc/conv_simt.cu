@@ -25,7 +25,6 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
   const int b = blockIdx.z / a.n_phases;
   const int phase = blockIdx.z % a.n_phases;
   const int NL = a.gate ? a.N_total / 2 : a.N_total;  // logical columns
-  const int half = a.N_total / 2;
 
   float acc[16], acc2[16];
 #pragma unroll
@@ -51,8 +50,10 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
         const int n = nl0 + nn;
         float v = 0.f, v2 = 0.f;
         if (n < NL) {
-          v = op_load<Op>(wt + (size_t)n * a.Cp_in + c0 + cc);
-          if (a.gate) v2 = op_load<Op>(wt + (size_t)(half + n) * a.Cp_in + c0 + cc);
+          // gate packing: 128-row tiles of [64 tanh rows | 64 sigmoid rows] for 64 consecutive channels
+          const int row = a.gate ? 128 * (n >> 6) + (n & 63) : n;
+          v = op_load<Op>(wt + (size_t)row * a.Cp_in + c0 + cc);
+          if (a.gate) v2 = op_load<Op>(wt + (size_t)(row + 64) * a.Cp_in + c0 + cc);
         }
         ws[cc][nn] = v;
         ws2[cc][nn] = v2;

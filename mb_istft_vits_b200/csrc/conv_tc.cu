@@ -203,6 +203,7 @@ struct TcRt {  // runtime scalars the kernel needs beyond ConvArgs
   int n_boxes;       // 1 or 2
   int slab_stage_bytes, w_stage_bytes, n_slab_stages, n_w_stages;
   int t_tiles, c_tiles, total_tiles;
+  int xchg_off;      // byte offset of the gate exchange buffer in dynamic smem
   int prefetch_res;  // issue an L2 prefetch of the tile's residual input (tmR) when its operand loads start
 };
 
@@ -312,25 +313,6 @@ __device__ __forceinline__ void epi_f32(const EpiParams& p, int b, int n, int ph
 }
 
 template <typename Op, int STEP, bool FULL>
-__device__ __forceinline__ void epi_gate(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
-                                         size_t rstep, const float* acc, const float* acc2) {
-  using T = typename Op::T;
-  const size_t step = STEP > 0 ? (size_t)STEP : rstep;
-  float b1 = p.bias[(size_t)b * p.bias_bs + n], b2 = p.bias[(size_t)b * p.bias_bs + p.n_split + n];
-  if (p.add2) {
-    b1 += p.add2[(size_t)b * p.add2_bs + n];
-    b2 += p.add2[(size_t)b * p.add2_bs + p.n_split + n];
-  }
-  T* dst = reinterpret_cast<T*>(p.act[0]) + ((size_t)b * p.rows_out + t_first) * p.ld + n;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const float tv = fast_tanh(acc[i] + b1);
-    const float sg = __fdividef(1.f, 1.f + __expf(-(acc2[i] + b2)));
-    MBV_EL(i) op_store1<Op>(dst + i * step, tv * sg);
-  }
-}
-
-template <typename Op, int STEP, bool FULL>
 __device__ __forceinline__ void epi_rs(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
                                        size_t rstep, const float* acc, const float* xpre) {
   using T = typename Op::T;
@@ -389,7 +371,6 @@ __device__ __forceinline__ void epi_dispatch(const EpiParams& p, int b, int n, i
   if constexpr (MODE == EPI_ACT) epi_act<Op, STEP, FULL, RH>(p, b, n, phase, t_first, nt, rstep, acc);
   else if constexpr (MODE == EPI_RES) epi_res<Op, STEP, FULL, RH>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
   else if constexpr (MODE == EPI_F32) epi_f32<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc);
-  else if constexpr (MODE == EPI_GATE) epi_gate<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc, acc2);
   else if constexpr (MODE == EPI_RS) epi_rs<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
   else epi_post<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
 }
@@ -460,6 +441,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int iXF = 0, iXE = iXF + rt.n_slab_stages, iWF = iXE + rt.n_slab_stages, iWE = iWF + rt.n_w_stages;
   const int iCF = iWE + rt.n_w_stages, iCE = iCF + 2, nBars = iCE + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + nBars);
+  float* xchg = reinterpret_cast<float*>(smem + rt.xchg_off);  // EPI_GATE: sigmoid -> tanh warp exchange, 4 pairs x 2 x 4 KB
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -486,7 +468,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int kblocks = a.Cp_in / KB;
-  const int n_logical = a.gate ? a.N_total / 2 : a.N_total;  // weight rows of one half
   const uint32_t slab_bytes = (uint32_t)rt.n_boxes * rt.box_rows * TC_ROW_BYTES;
   const uint32_t w_tile_bytes = TC_M * TC_ROW_BYTES;
 
@@ -523,10 +504,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           mbar_wait(BAR(iWE + sw), pw ^ 1);
           if (elect_one()) {
             const uint32_t wdst = smem_u32(smW + (size_t)sw * rt.w_stage_bytes);
-            mbar_expect_tx(BAR(iWF + sw), MODE == EPI_GATE ? 2 * w_tile_bytes : w_tile_bytes);
-            const int wrow = wrow0 + tap * a.N_total;
-            tma_load_2d(wdst, &tmW, BAR(iWF + sw), kb * KB, wrow);
-            if constexpr (MODE == EPI_GATE) tma_load_2d(wdst + w_tile_bytes, &tmW, BAR(iWF + sw), kb * KB, wrow + n_logical);
+            mbar_expect_tx(BAR(iWF + sw), w_tile_bytes);
+            tma_load_2d(wdst, &tmW, BAR(iWF + sw), kb * KB, wrow0 + tap * a.N_total);
           }
           __syncwarp();
           if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
@@ -562,9 +541,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               tc_mma<KIND>(tmem_d, desc64(w_lo + 2 * k), desc64(x_lo + 2 * k), idesc, (k == 0) ? accum : 1u);
-              if constexpr (MODE == EPI_GATE)
-                tc_mma<KIND>(tmem_d + (uint32_t)rt.n_time, desc64(w_lo + (w_tile_bytes >> 4) + 2 * k), desc64(x_lo + 2 * k),
-                             idesc, (k == 0) ? accum : 1u);
             }
             tc_commit(BAR(iWE + sw));
           }
@@ -605,6 +581,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       ti.n = ct * TC_M + q * 32 + lane;  // weight row = output channel of this thread
       // which logical channel does this row write, and is it inside the destination buffer?
       if (MODE == EPI_RS && a.epi.n_split > 0) ti.valid = (ti.n < a.epi.n_split ? ti.n : ti.n - a.epi.n_split) < n_valid;
+      else if (MODE == EPI_GATE) ti.valid = (64 * ct + ((q * 32 + lane) & 63)) < n_valid;  // logical channel of this row
       else ti.valid = ti.n < n_valid;
       ti.t_lim = min(a.L_out, ti.t0 + rt.n_time);
       return ti;
@@ -630,6 +607,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     };
 
     float xcur[32], xnext[32];
+    int gate_chunk = 0;
     int tile = blockIdx.x;
     TileInfo ti = decode(tile);
     if (kPrefetch && tile < rt.total_tiles && c_first < rt.n_time) prefetch(ti, c_first, xcur);
@@ -643,7 +621,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       for (int c = c_first; c < rt.n_time; c += 64) {
         float acc[32], acc2[32];
         tmem_ld32(taddr + (uint32_t)c, acc);
-        if constexpr (MODE == EPI_GATE) tmem_ld32(taddr + (uint32_t)(rt.n_time + c), acc2);
         if constexpr (kPrefetch) {  // next chunk of this tile, or the first chunk of this CTA's next tile
           const int j2 = (c - c_first) / 64 + 2;
           if (j2 < nch) l2_prefetch(ti, c_first + 64 * j2);
@@ -653,8 +630,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
         tmem_ld_wait();
         const int t_first = ti.t0 + c;
-        if (ti.valid && t_first < ti.t_lim)
+        if constexpr (MODE == EPI_GATE) {
+          // One accumulator tile = [64 tanh rows | 64 sigmoid rows] of the same 64 channels: lanes i and i+64 belong
+          // together but live in different warps (q and q+2).  The sigmoid warp hands its 32x32 block to its tanh
+          // partner through shared memory (two buffers, one named barrier per chunk), which gates and stores.
+          const EpiParams& p = a.epi;
+          const bool is_sig = q >= 2;
+          const int pair = (q & 1) + 2 * half;
+          float* xb = xchg + (pair * 2 + (gate_chunk & 1)) * 1024;
+          gate_chunk++;
+          float bb = p.bias[(size_t)ti.b * p.bias_bs + ti.n];
+          if (p.add2) bb += p.add2[(size_t)ti.b * p.add2_bs + ti.n];
+          if (is_sig) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xb[i * 32 + lane] = __fdividef(1.f, 1.f + __expf(-(acc[i] + bb)));
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+          if (!is_sig && ti.valid && t_first < ti.t_lim) {
+            using T = typename Op::T;
+            const int nt = min(ti.t_lim - t_first, 32);
+            const int ch = 64 * (ti.n >> 7) + (ti.n & 63);
+            T* dst = reinterpret_cast<T*>(p.act[0]) + ((size_t)ti.b * p.rows_out + t_first) * p.ld + ch;
+            const size_t step = LD > 0 ? (size_t)LD : (size_t)p.ld;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float v = fast_tanh(acc[i] + bb) * xb[i * 32 + lane];
+              if (i < nt) op_store1<Op>(dst + i * step, v);
+            }
+          }
+        } else if (ti.valid && t_first < ti.t_lim) {
           tc_epilogue32<Op, MODE, LD, RH>(a.epi, ti.b, ti.n, ti.phase, t_first, min(ti.t_lim - t_first, 32), acc, acc2, xcur);
+        }
         if constexpr (kPrefetch) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) xcur[i] = xnext[i];
@@ -702,10 +708,10 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
   const int esize = prec == 2 ? 2 : 4;
   const int KB = TC_ROW_BYTES / esize;
   if (a.Cp_in % 64 != 0) return "tcgen05 conv: padded input channels must be a multiple of 64";
-  const int n_logical = a.gate ? a.N_total / 2 : a.N_total;
+  const int n_logical = a.N_total;
   if (n_logical % TC_M != 0) return "tcgen05 conv: packed output channels must be a multiple of 128";
-  // time tile: as few tiles as a 256-column (gate: 128) accumulator allows, then shrunk to what the length needs
-  const int max_n = a.gate ? 128 : 256;
+  // time tile: as few tiles as a 256-column accumulator allows, then shrunk to what the length needs
+  const int max_n = 256;
   const int tiles = (a.L_out + max_n - 1) / max_n;
   int n_time = ((a.L_out + tiles - 1) / tiles + 15) / 16 * 16;
   if (n_time < 16) n_time = 16;
@@ -719,15 +725,17 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
   plan->box_rows = ((plan->slab_rows + plan->n_boxes - 1) / plan->n_boxes + 7) / 8 * 8;
   if (plan->box_rows > 256) return "tcgen05 conv: activation slab exceeds two 256-row TMA boxes";
   plan->slab_stage_bytes = ((plan->n_boxes * plan->box_rows * TC_ROW_BYTES + 1023) / 1024) * 1024;
-  plan->w_stage_bytes = (a.gate ? 2 : 1) * TC_M * TC_ROW_BYTES;
-  const int budget = 212 * 1024;
+  plan->w_stage_bytes = TC_M * TC_ROW_BYTES;
+  const int xchg = a.gate ? 32 * 1024 : 0;
+  const int budget = 212 * 1024 - xchg;
   plan->n_slab_stages = plan->slab_stage_bytes > 36 * 1024 ? 2 : 3;
   plan->n_w_stages = (budget - plan->n_slab_stages * plan->slab_stage_bytes) / plan->w_stage_bytes;
   if (plan->n_w_stages > 8) plan->n_w_stages = 8;
   if (plan->n_w_stages < 2) return "tcgen05 conv: not enough shared memory for two weight stages";
   const int nbars = 2 * plan->n_slab_stages + 2 * plan->n_w_stages + 4;
-  plan->smem_bytes = 1024 + plan->n_slab_stages * plan->slab_stage_bytes + plan->n_w_stages * plan->w_stage_bytes +
-                     nbars * 8 + 16;
+  plan->xchg_off = (plan->n_slab_stages * plan->slab_stage_bytes + plan->n_w_stages * plan->w_stage_bytes + nbars * 8 + 16 +
+                    127) / 128 * 128;
+  plan->smem_bytes = 1024 + plan->xchg_off + xchg;
   if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;  // one CTA per SM: each CTA owns all 512 TMEM columns
   plan->grid = plan->total_tiles < num_sms ? plan->total_tiles : num_sms;
   if (plan->grid < 1) plan->grid = 1;
@@ -837,6 +845,7 @@ cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStr
   rt.n_slab_stages = p.n_slab_stages; rt.n_w_stages = p.n_w_stages;
   rt.t_tiles = p.t_tiles; rt.c_tiles = p.c_tiles; rt.total_tiles = p.total_tiles;
   rt.prefetch_res = p.prefetch_res;
+  rt.xchg_off = p.xchg_off;
   if (prec == 2) return dispatch<OpBF16>(a, p, rt, st, false, a.epi.mode, a.epi.ld, a.epi.res_half);
   if (a.epi.res_half) return cudaErrorInvalidValue;
   return dispatch<OpTF32>(a, p, rt, st, false, a.epi.mode, a.epi.ld, 0);

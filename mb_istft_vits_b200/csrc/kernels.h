@@ -19,6 +19,7 @@ struct TcPlan {
   int slab_rows, box_rows, n_boxes;
   int slab_stage_bytes, w_stage_bytes, n_slab_stages, n_w_stages;
   int t_tiles, c_tiles, total_tiles;
+  int xchg_off;         // byte offset of the gate exchange buffer
   int smem_bytes;
   int grid;
 };

@@ -97,8 +97,8 @@ struct mbv_handle {
 
   // flow layers, indexed by coupling layer 0..3 (reference order)
   ConvLayer fl_pre[4], fl_post[4], fl_in[4][4], fl_rs[4][4];
-  float* fl_cond_w[4] = {nullptr};  // [L*2Hw][gin] packed (tanh | sigmoid per layer)
-  float* fl_cond_b[4] = {nullptr};  // [L*2Hw]
+  float* fl_cond_w[4] = {nullptr};  // [L*2Hp][gin] packed in the gate row order
+  float* fl_cond_b[4] = {nullptr};  // [L*2Hp]
 
   // tensor-map cache: valid while (B, T, ws) stay the same
   struct PlanKey { int B, T; void* ws; int kind; bool operator<(const PlanKey& o) const {
@@ -205,8 +205,8 @@ int pack_conv1d(mbv_handle* h, const TensorMap& m, const std::string& prefix, in
   }
   // packed rows: a multiple of 128 (one UMMA M tile); a gate conv passes [tanh half | sigmoid half], each padded
   const int n_map = (int)out_map.size(), Cp = (int)in_map.size();
-  const int N = gate ? n_map : round_up(n_map, 128);
-  if (gate && (n_map % 256) != 0) return fail(h, MBV_ERR_INVALID, "%s: gate halves must be padded to 128", prefix.c_str());
+  const int N = round_up(n_map, 128);
+  if (gate && (n_map % 128) != 0) return fail(h, MBV_ERR_INVALID, "%s: gate rows must come in 128-row tiles", prefix.c_str());
   L->Cp_in = Cp; L->N_total = N; L->taps = K; L->dil = dil; L->n_phases = 1; L->gate = gate;
   L->shift0[0] = -dil * (K - 1) / 2;
   L->n_valid = O;
@@ -486,7 +486,6 @@ extern "C" int mbv_load_weights(mbv_handle* h, const mbv_tensor* tensors, int32_
   // ---------------- flow (Flips folded into pre/post)
   {
     const int half = h->Cz / 2, H = h->H, Hp = h->Hp, K = c.flow_kernel, NL = c.flow_layers;
-    const int Hw = h->Hw;  // weight rows per half, padded to the 128-row MMA tile
     for (int f = 0; f < 4; ++f) {
       // coupling layer f runs after (4 - f) flips: odd -> reads rev(z[half:]) and updates rev(z[:half])
       const bool odd = ((4 - f) & 1) != 0;
@@ -502,8 +501,10 @@ extern "C" int mbv_load_weights(mbv_handle* h, const mbv_tensor* tensors, int32_
       if (rc) return rc;
       std::vector<int> hin = iota_pad(H, Hp);
       for (int l = 0; l < NL; ++l) {
-        std::vector<int> gmap(2 * Hw, -1);
-        for (int o = 0; o < H; ++o) { gmap[o] = o; gmap[Hw + o] = H + o; }
+        // gate rows: 128-row MMA tiles of [64 tanh rows | 64 sigmoid rows] for 64 consecutive channels, so ONE
+        // accumulator holds both halves of a channel (lanes i and i+64) and H = 192 = 3 x 64 needs no padding
+        std::vector<int> gmap(2 * Hp, -1);
+        for (int o = 0; o < H; ++o) { gmap[128 * (o / 64) + (o % 64)] = o; gmap[128 * (o / 64) + 64 + (o % 64)] = H + o; }
         snprintf(pfx, sizeof(pfx), "flow.flows.%d.enc.in_layers.%d", 2 * f, l);
         rc = pack_conv1d(h, m, pfx, 2 * H, H, K, 1, gmap, hin, true, 1, &h->fl_in[f][l]);
         if (rc) return rc;
@@ -527,10 +528,11 @@ extern "C" int mbv_load_weights(mbv_handle* h, const mbv_tensor* tensors, int32_
         const HostTensor* w = find_tensor(h, m, std::string(pfx) + ".weight", 3, ws);
         const HostTensor* b = w ? find_tensor(h, m, std::string(pfx) + ".bias", 1, bs) : nullptr;
         if (!w || !b) return MBV_ERR_WEIGHTS;
-        std::vector<float> pw((size_t)NL * 2 * Hw * gin, 0.f), pb((size_t)NL * 2 * Hw, 0.f);
+        std::vector<float> pw((size_t)NL * 2 * Hp * gin, 0.f), pb((size_t)NL * 2 * Hp, 0.f);
         for (int l = 0; l < NL; ++l)
           for (int o = 0; o < 2 * H; ++o) {
-            const int dst = l * 2 * Hw + (o < H ? o : Hw + (o - H));
+            const int ch = o < H ? o : o - H;  // same row order as the packed in_layers weights
+            const int dst = l * 2 * Hp + 128 * (ch / 64) + (ch % 64) + (o < H ? 0 : 64);
             const int src = l * 2 * H + o;
             memcpy(&pw[(size_t)dst * gin], &w->data[(size_t)src * gin], sizeof(float) * gin);
             pb[dst] = b->data[src];
@@ -605,7 +607,7 @@ void layout_flow(mbv_handle* h, Arena& A, int B, int T, FlowBufs* f) {
   f->acts = A.take(nh * es);
   f->skip = (float*)A.take(nh * 4);
   f->hout = A.take(nh * es);
-  f->gcond = (float*)A.take((size_t)4 * B * h->cfg.flow_layers * 2 * h->Hw * 4);
+  f->gcond = (float*)A.take((size_t)4 * B * h->cfg.flow_layers * 2 * h->Hp * 4);
 }
 
 // Launch context: counts launches, caches tensor maps
@@ -670,7 +672,7 @@ EpiParams epi_base(int mode, int ld, int rows) {
 int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, const float* g, float* z_out, int B, int T) {
   mbv_handle* h = cx.h;
   const mbv_config& c = h->cfg;
-  const int Hp = h->Hp, Hw = h->Hw, NL = c.flow_layers;
+  const int Hp = h->Hp, NL = c.flow_layers;
   {
     ProfScope prof(cx, 2);
     CUDA_TRY(h, launch_pack_input(h->prec, z_p, nullptr, f.zop, f.z, B, h->Cz, T, h->Cz, cx.st));
@@ -679,9 +681,9 @@ int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, co
   for (int f_i = 3; f_i >= 0; --f_i) {
     float* gc = nullptr;
     if (g) {
-      gc = f.gcond + (size_t)f_i * B * NL * 2 * Hw;
+      gc = f.gcond + (size_t)f_i * B * NL * 2 * Hp;
       ProfScope prof(cx, 2);
-      CUDA_TRY(h, launch_cond_gemv(g, h->fl_cond_w[f_i], h->fl_cond_b[f_i], nullptr, gc, B, c.gin_channels, NL * 2 * Hw, NL * 2 * Hw, cx.st));
+      CUDA_TRY(h, launch_cond_gemv(g, h->fl_cond_w[f_i], h->fl_cond_b[f_i], nullptr, gc, B, c.gin_channels, NL * 2 * Hp, NL * 2 * Hp, cx.st));
       cx.launches++;
     }
     int rc;
@@ -693,8 +695,8 @@ int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, co
     for (int l = 0; l < NL; ++l) {
       {
         EpiParams e = epi_base(EPI_GATE, Hp, T);
-        e.n_split = Hw; e.act[0] = f.acts; e.n_act = 1;
-        if (gc) { e.add2 = gc + (size_t)l * 2 * Hw; e.add2_bs = NL * 2 * Hw; }
+        e.act[0] = f.acts; e.n_act = 1;
+        if (gc) { e.add2 = gc + (size_t)l * 2 * Hp; e.add2_bs = NL * 2 * Hp; }
         if ((rc = run_conv(cx, h->fl_in[f_i][l], f.hop, B, T, T, e))) return rc;
       }
       {
