@@ -27,6 +27,9 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -190,11 +193,21 @@ template <bool RH> __device__ __forceinline__ void res_st(typename ResT<RH>::T* 
   if constexpr (RH) *p = to_half_sat(v); else *p = v;
 }
 
+// MUFU.TANH: one instruction, max abs error 2^-11 -- below the 2^-9 rounding the bf16 operand copy applies anyway.
+__device__ __forceinline__ float mufu_tanh(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+template <typename Op> __device__ __forceinline__ float gate_tanh(float x);
+template <typename Op> __device__ __forceinline__ float gate_sigmoid(float x);
+
 __device__ __forceinline__ float fast_tanh(float x) {
   // tanh(x) = 1 - 2 / (exp(2x) + 1); exact limits at +-inf, abs error ~1e-7 relative to the fp32 reference
   const float e = __expf(2.f * x);
   return 1.f - __fdividef(2.f, e + 1.f);
 }
+
+template <> __device__ __forceinline__ float gate_tanh<OpBF16>(float x) { return mufu_tanh(x); }
+template <> __device__ __forceinline__ float gate_sigmoid<OpBF16>(float x) { return fmaf(mufu_tanh(0.5f * x), 0.5f, 0.5f); }
+template <> __device__ __forceinline__ float gate_tanh<OpTF32>(float x) { return fast_tanh(x); }
+template <> __device__ __forceinline__ float gate_sigmoid<OpTF32>(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 struct TcRt {  // runtime scalars the kernel needs beyond ConvArgs
   int n_time;        // time columns per tile (UMMA N), multiple of 16, <= 256 (gate: <= 128)
@@ -205,6 +218,7 @@ struct TcRt {  // runtime scalars the kernel needs beyond ConvArgs
   int t_tiles, c_tiles, total_tiles;
   int xchg_off;      // byte offset of the gate exchange buffer in dynamic smem
   int prefetch_res;  // issue an L2 prefetch of the tile's residual input (tmR) when its operand loads start
+  long long* dbg;    // MBV_TIMELINE=1: per-CTA clock stamps [cta][role 0..2][tile][2] (debug only)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -486,6 +500,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const int t0 = tt * rt.n_time;
       const int wrow0 = phase * a.taps * a.N_total + ct * TC_M;
       const int xrow0 = t0 + a.shift0[phase];
+      if (rt.dbg && lane == 0) rt.dbg[((size_t)blockIdx.x * 3 + 0) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
       // (A whole-tile TMA L2 prefetch of the residual box issued here was measured to be too early: a tile-time later
       //  a third of it had been evicted again and DRAM reads grew 40 %.  The epilogue warps prefetch two chunks ahead.)
       if (false && MODE == EPI_RES && rt.prefetch_res && elect_one()) tma_prefetch_l2_3d(&tmR, ct * TC_M, t0, b);
@@ -528,6 +543,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       mbar_wait(BAR(iCE + sc), pc ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(sc * TC_ACC_STRIDE);
+      if (rt.dbg && lane == 0) rt.dbg[((size_t)blockIdx.x * 3 + 1) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
       uint32_t accum = 0;
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(BAR(iXF + sx), px);
@@ -555,6 +571,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       if (elect_one()) tc_commit(BAR(iCF + sc));
       __syncwarp();
+      if (rt.dbg && lane == 0) rt.dbg[((size_t)blockIdx.x * 3 + 1) * 64 + 2 * ((tile / gridDim.x) & 31) + 1] = clock64();
       if (++sc == 2) { sc = 0; pc ^= 1; }
     }
   } else if (warp < TC_EPI_WARPS) {
@@ -617,7 +634,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       if (have_next) tn = decode(tile + gridDim.x);
       mbar_wait(BAR(iCF + sc), pc);
       tc_fence_after();
+      if (rt.dbg && warp == 0 && lane == 0) rt.dbg[((size_t)blockIdx.x * 3 + 2) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc * TC_ACC_STRIDE);
+      float gate_bias = 0.f;
+      if constexpr (MODE == EPI_GATE) {  // bias + cond_layer(g) of this thread's weight row, once per tile
+        gate_bias = a.epi.bias[(size_t)ti.b * a.epi.bias_bs + ti.n];
+        if (a.epi.add2) gate_bias += a.epi.add2[(size_t)ti.b * a.epi.add2_bs + ti.n];
+      }
       for (int c = c_first; c < rt.n_time; c += 64) {
         float acc[32], acc2[32];
         tmem_ld32(taddr + (uint32_t)c, acc);
@@ -637,13 +660,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           const EpiParams& p = a.epi;
           const bool is_sig = q >= 2;
           const int pair = (q & 1) + 2 * half;
-          float* xb = xchg + (pair * 2 + (gate_chunk & 1)) * 1024;
+          const uint32_t xb = smem_u32(xchg) + (uint32_t)((pair * 2 + (gate_chunk & 1)) * 4096) + (uint32_t)lane * 4u;
           gate_chunk++;
-          float bb = p.bias[(size_t)ti.b * p.bias_bs + ti.n];
-          if (p.add2) bb += p.add2[(size_t)ti.b * p.add2_bs + ti.n];
           if (is_sig) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) xb[i * 32 + lane] = __fdividef(1.f, 1.f + __expf(-(acc[i] + bb)));
+            for (int i = 0; i < 32; ++i) {
+              const float sg = gate_sigmoid<Op>(acc[i] + gate_bias);
+              asm volatile("st.shared.f32 [%0], %1;" ::"r"(xb + (uint32_t)i * 128u), "f"(sg) : "memory");
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = gate_tanh<Op>(acc[i] + gate_bias);  // overlaps the partner's sigmoids
           }
           asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
           if (!is_sig && ti.valid && t_first < ti.t_lim) {
@@ -654,8 +681,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             const size_t step = LD > 0 ? (size_t)LD : (size_t)p.ld;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const float v = fast_tanh(acc[i] + bb) * xb[i * 32 + lane];
-              if (i < nt) op_store1<Op>(dst + i * step, v);
+              float sg;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sg) : "r"(xb + (uint32_t)i * 128u) : "memory");
+              if (i < nt) op_store1<Op>(dst + i * step, acc[i] * sg);
             }
           }
         } else if (ti.valid && t_first < ti.t_lim) {
@@ -669,6 +697,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(iCE + sc));
+      if (rt.dbg && warp == 0 && lane == 0) rt.dbg[((size_t)blockIdx.x * 3 + 2) * 64 + 2 * ((tile / gridDim.x) & 31) + 1] = clock64();
       if (++sc == 2) { sc = 0; pc ^= 1; }
       ti = tn;
       tile += gridDim.x;
@@ -840,17 +869,42 @@ cudaError_t tc_set_attributes() {
   return cudaSuccess;
 }
 
+// MBV_TIMELINE=<mode>: after every launch whose epilogue mode matches, print CTA 0's per-tile clock stamps (debug)
+static void timeline_dump(const ConvArgs& a, const TcPlan& p, long long* dbg, cudaStream_t st) {
+  cudaStreamSynchronize(st);
+  std::vector<long long> hbuf(3 * 64);
+  cudaMemcpy(hbuf.data(), dbg, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+  const int nt = (p.total_tiles + p.grid - 1) / p.grid;
+  long long t0 = hbuf[0];
+  fprintf(stderr, "[timeline] mode %d taps %d Cp_in %d N_total %d n_time %d tiles/CTA %d slab_st %d w_st %d\n", a.epi.mode, a.taps,
+          a.Cp_in, a.N_total, p.n_time, nt, p.n_slab_stages, p.n_w_stages);
+  for (int i = 0; i < nt && i < 32; ++i)
+    fprintf(stderr, "  tile %2d  prod_start %7lld | mma %7lld .. %7lld | epi %7lld .. %7lld\n", i, hbuf[2 * i] - t0,
+            hbuf[64 + 2 * i] - t0, hbuf[64 + 2 * i + 1] - t0, hbuf[128 + 2 * i] - t0, hbuf[128 + 2 * i + 1] - t0);
+}
+
 cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStream_t st) {
+  static long long* dbg = nullptr;
+  static int dbg_mode = -2;
+  if (dbg_mode == -2) {
+    const char* e = getenv("MBV_TIMELINE");
+    dbg_mode = e ? atoi(e) : -1;
+    if (dbg_mode >= 0) cudaMalloc(&dbg, 148 * 3 * 64 * sizeof(long long));
+  }
   TcRt rt;
+  rt.dbg = (dbg_mode >= 0 && a.epi.mode == dbg_mode) ? dbg : nullptr;
   rt.n_time = p.n_time; rt.slab_rows = p.slab_rows; rt.box_rows = p.box_rows; rt.n_boxes = p.n_boxes;
   rt.slab_stage_bytes = p.slab_stage_bytes; rt.w_stage_bytes = p.w_stage_bytes;
   rt.n_slab_stages = p.n_slab_stages; rt.n_w_stages = p.n_w_stages;
   rt.t_tiles = p.t_tiles; rt.c_tiles = p.c_tiles; rt.total_tiles = p.total_tiles;
   rt.prefetch_res = p.prefetch_res;
   rt.xchg_off = p.xchg_off;
-  if (prec == 2) return dispatch<OpBF16>(a, p, rt, st, false, a.epi.mode, a.epi.ld, a.epi.res_half);
-  if (a.epi.res_half) return cudaErrorInvalidValue;
-  return dispatch<OpTF32>(a, p, rt, st, false, a.epi.mode, a.epi.ld, 0);
+  cudaError_t e;
+  if (prec == 2) e = dispatch<OpBF16>(a, p, rt, st, false, a.epi.mode, a.epi.ld, a.epi.res_half);
+  else if (a.epi.res_half) e = cudaErrorInvalidValue;
+  else e = dispatch<OpTF32>(a, p, rt, st, false, a.epi.mode, a.epi.ld, 0);
+  if (rt.dbg && e == cudaSuccess) timeline_dump(a, p, rt.dbg, st);
+  return e;
 }
 
 }  // namespace mbv
