@@ -603,9 +603,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       ti.t_lim = min(a.L_out, ti.t0 + rt.n_time);
       return ti;
     };
-    // The residual loads are latency-bound (Little's law: 8 warps x 32 x 64 B in flight per SM against ~1 us of DRAM
-    // latency; ncu: long_scoreboard dominates).  Each lane therefore asks L2 for one row of the chunk two work items
-    // ahead (its warp's 32 channels = 64-128 contiguous bytes), so the register prefetch one item ahead hits L2.
+    // The residual loads are latency-bound: the per-tile timeline (MBV_TIMELINE) shows a RES epilogue of ~12k cycles
+    // per tile against ~4.7k for the same tile without the residual read -- the register prefetch one chunk ahead is
+    // shallower than the DRAM latency under load.  L2 prefetches cost no registers, so at the start of a tile every
+    // lane asks L2 for its rows of the WHOLE NEXT tile (its warp's 32 channels = 64-128 contiguous bytes per row);
+    // one tile period later the register prefetch finds them in L2.
     auto l2_prefetch = [&](const TileInfo& ti, int c) {
       if constexpr (MODE == EPI_RES) {
         const int t = ti.t0 + c + lane;
@@ -627,11 +629,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     int gate_chunk = 0;
     int tile = blockIdx.x;
     TileInfo ti = decode(tile);
-    if (kPrefetch && tile < rt.total_tiles && c_first < rt.n_time) prefetch(ti, c_first, xcur);
+    if (kPrefetch && tile < rt.total_tiles && c_first < rt.n_time) {
+      for (int j = 1; j < nch; ++j) l2_prefetch(ti, c_first + 64 * j);
+      prefetch(ti, c_first, xcur);
+    }
     while (tile < rt.total_tiles) {
       const bool have_next = tile + (int)gridDim.x < rt.total_tiles;
       TileInfo tn = ti;
-      if (have_next) tn = decode(tile + gridDim.x);
+      if (have_next) {
+        tn = decode(tile + gridDim.x);
+        for (int j = 0; j < nch; ++j) l2_prefetch(tn, c_first + 64 * j);
+      }
       mbar_wait(BAR(iCF + sc), pc);
       tc_fence_after();
       if (rt.dbg && warp == 0 && lane == 0) rt.dbg[((size_t)blockIdx.x * 3 + 2) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
@@ -645,9 +653,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         float acc[32], acc2[32];
         tmem_ld32(taddr + (uint32_t)c, acc);
         if constexpr (kPrefetch) {  // next chunk of this tile, or the first chunk of this CTA's next tile
-          const int j2 = (c - c_first) / 64 + 2;
-          if (j2 < nch) l2_prefetch(ti, c_first + 64 * j2);
-          else if (have_next) l2_prefetch(tn, c_first + 64 * (j2 - nch));
           if (c + 64 < rt.n_time) prefetch(ti, c + 64, xnext);
           else if (have_next) prefetch(tn, c_first, xnext);
         }
