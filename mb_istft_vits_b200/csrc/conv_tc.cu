@@ -37,10 +37,12 @@
 namespace mbv {
 
 constexpr int TC_M = 128;            // output channels per tile (UMMA M)
-constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // epilogue warps + producer + MMA
-constexpr int TC_WARP_TMA = TC_EPI_WARPS;
-constexpr int TC_WARP_MMA = TC_EPI_WARPS + 1;
+// Epilogue warps per CTA.  The fused epilogues are latency-bound (per-tile timelines: IPC ~0.3 per scheduler with two
+// warps each), so every mode but the gate (whose warp pairs exchange through 32 KB of shared memory) runs FOUR warps
+// per TMEM lane quarter; with 18 warps the register budget is 112 per thread, which is why the residual input is no
+// longer double-buffered in registers (an L2 prefetch one tile ahead plus the extra warps hide its latency instead).
+template <int MODE> struct EpiWarps { static constexpr int value = (MODE == EPI_GATE) ? 8 : 12; };
+template <int MODE> struct TcThreads { static constexpr int value = 64 + 32 * EpiWarps<MODE>::value; };  // epilogue + producer + MMA
 constexpr int TC_ROW_BYTES = 128;    // one swizzle row = 64 bf16 / 32 tf32 channels
 constexpr int TC_ACC_STRIDE = 256;   // TMEM columns per accumulator stage
 constexpr uint64_t TC_TIMEOUT_CYCLES = 4000000000ull;  // ~2 s: a stuck pipeline traps instead of hanging the box
@@ -442,11 +444,14 @@ __device__ __forceinline__ void tc_epilogue32(const EpiParams& p, int b, int n, 
 }
 
 template <typename Op, int MODE, int LD, bool RH>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TcThreads<MODE>::value, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmR, const ConvArgs a, const TcRt rt) {
   using T = typename Op::T;
   constexpr int KB = TC_ROW_BYTES / (int)sizeof(T);  // channels per k-block
+  constexpr int TC_EPI_WARPS = EpiWarps<MODE>::value;
+  constexpr int TC_WARP_TMA = TC_EPI_WARPS, TC_WARP_MMA = TC_EPI_WARPS + 1;
+  constexpr int CSTEP = 32 * (TC_EPI_WARPS / 4);  // column stride between the chunks of one epilogue warp
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smX = smem;                                                   // activation slabs
@@ -576,11 +581,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     }
   } else if (warp < TC_EPI_WARPS) {
     // ===================== epilogue warps =====================
-    // Work items of this warp: (tile, 32-column chunk c = half*32 + 64*j).  The residual-like input of item i+1 is
-    // loaded before item i is processed (software pipeline across chunks AND tiles); tiles are decoded once.
+    // Work items of this warp: (tile, 32-column chunk c = grp*32 + CSTEP*j); tiles are decoded once per tile.
     constexpr bool kPrefetch = (MODE == EPI_RES || MODE == EPI_RS || MODE == EPI_POST);
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = warp >> 2;             // which alternate 32-column chunks this warp takes
+    const int half = warp >> 2;             // column group: which interleaved 32-column chunks this warp takes
     const int n_valid = a.epi.n_valid;
     const int c_first = half * 32;
     int sc = 0;
@@ -603,11 +607,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       ti.t_lim = min(a.L_out, ti.t0 + rt.n_time);
       return ti;
     };
-    // The residual loads are latency-bound: the per-tile timeline (MBV_TIMELINE) shows a RES epilogue of ~12k cycles
-    // per tile against ~4.7k for the same tile without the residual read -- the register prefetch one chunk ahead is
-    // shallower than the DRAM latency under load.  L2 prefetches cost no registers, so at the start of a tile every
-    // lane asks L2 for its rows of the WHOLE NEXT tile (its warp's 32 channels = 64-128 contiguous bytes per row);
-    // one tile period later the register prefetch finds them in L2.
+    // The residual loads are latency-bound (per-tile timelines, MBV_TIMELINE).  L2 prefetches cost no registers, so at
+    // the start of a tile every lane asks L2 for its rows of the WHOLE NEXT tile (its warp's 32 channels = 64-128
+    // contiguous bytes per row); one tile period later the demand loads find them in L2.
     auto l2_prefetch = [&](const TileInfo& ti, int c) {
       if constexpr (MODE == EPI_RES) {
         const int t = ti.t0 + c + lane;
@@ -618,27 +620,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
       }
     };
-    const int nch = (rt.n_time - c_first + 63) / 64;  // chunks per tile for this warp
+    const int nch = (rt.n_time - c_first + CSTEP - 1) / CSTEP;  // chunks per tile for this warp
     auto prefetch = [&](const TileInfo& ti, int c, float* dst) {
       const int t_first = ti.t0 + c;
       if (ti.valid && t_first < ti.t_lim)
         epi_prefetch<MODE, LD, RH>(a.epi, ti.b, ti.n, t_first, min(ti.t_lim - t_first, 32), dst);
     };
 
-    float xcur[32], xnext[32];
+    float xcur[32];
     int gate_chunk = 0;
     int tile = blockIdx.x;
     TileInfo ti = decode(tile);
-    if (kPrefetch && tile < rt.total_tiles && c_first < rt.n_time) {
-      for (int j = 1; j < nch; ++j) l2_prefetch(ti, c_first + 64 * j);
-      prefetch(ti, c_first, xcur);
-    }
+    if (kPrefetch && tile < rt.total_tiles)
+      for (int j = 0; j < nch; ++j) l2_prefetch(ti, c_first + CSTEP * j);
     while (tile < rt.total_tiles) {
       const bool have_next = tile + (int)gridDim.x < rt.total_tiles;
       TileInfo tn = ti;
       if (have_next) {
         tn = decode(tile + gridDim.x);
-        for (int j = 0; j < nch; ++j) l2_prefetch(tn, c_first + 64 * j);
+        for (int j = 0; j < nch; ++j) l2_prefetch(tn, c_first + CSTEP * j);
       }
       mbar_wait(BAR(iCF + sc), pc);
       tc_fence_after();
@@ -649,13 +649,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         gate_bias = a.epi.bias[(size_t)ti.b * a.epi.bias_bs + ti.n];
         if (a.epi.add2) gate_bias += a.epi.add2[(size_t)ti.b * a.epi.add2_bs + ti.n];
       }
-      for (int c = c_first; c < rt.n_time; c += 64) {
-        float acc[32], acc2[32];
+      for (int c = c_first; c < rt.n_time; c += CSTEP) {
+        float acc[32];
         tmem_ld32(taddr + (uint32_t)c, acc);
-        if constexpr (kPrefetch) {  // next chunk of this tile, or the first chunk of this CTA's next tile
-          if (c + 64 < rt.n_time) prefetch(ti, c + 64, xnext);
-          else if (have_next) prefetch(tn, c_first, xnext);
-        }
+        if constexpr (kPrefetch) prefetch(ti, c, xcur);  // residual of THIS chunk, in flight with the TMEM load
         tmem_ld_wait();
         const int t_first = ti.t0 + c;
         if constexpr (MODE == EPI_GATE) {
@@ -692,11 +689,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             }
           }
         } else if (ti.valid && t_first < ti.t_lim) {
-          tc_epilogue32<Op, MODE, LD, RH>(a.epi, ti.b, ti.n, ti.phase, t_first, min(ti.t_lim - t_first, 32), acc, acc2, xcur);
-        }
-        if constexpr (kPrefetch) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) xcur[i] = xnext[i];
+          tc_epilogue32<Op, MODE, LD, RH>(a.epi, ti.b, ti.n, ti.phase, t_first, min(ti.t_lim - t_first, 32), acc, nullptr, xcur);
         }
       }
       tc_fence_before();
@@ -818,7 +811,7 @@ static cudaError_t launch_one(const ConvArgs& a, const TcPlan& p, const TcRt& rt
   if (set_attr) return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p.grid);
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(TcThreads<MODE>::value);
   cfg.dynamicSmemBytes = p.smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
