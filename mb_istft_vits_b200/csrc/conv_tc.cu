@@ -41,7 +41,7 @@ constexpr int TC_M = 128;            // output channels per tile (UMMA M)
 // warps each), so every mode but the gate (whose warp pairs exchange through 32 KB of shared memory) runs FOUR warps
 // per TMEM lane quarter; with 18 warps the register budget is 112 per thread, which is why the residual input is no
 // longer double-buffered in registers (an L2 prefetch one tile ahead plus the extra warps hide its latency instead).
-template <int MODE> struct EpiWarps { static constexpr int value = (MODE == EPI_GATE || MODE == EPI_ACT) ? 8 : (MODE == EPI_RES ? 16 : 12); };
+template <int MODE> struct EpiWarps { static constexpr int value = (MODE == EPI_GATE || MODE == EPI_ACT) ? 8 : 12; };
 template <int MODE> struct TcThreads { static constexpr int value = 64 + 32 * EpiWarps<MODE>::value; };  // epilogue + producer + MMA
 constexpr int TC_ROW_BYTES = 128;    // one swizzle row = 64 bf16 / 32 tf32 channels
 constexpr int TC_ACC_STRIDE = 256;   // TMEM columns per accumulator stage
