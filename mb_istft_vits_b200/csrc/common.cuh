@@ -76,7 +76,11 @@ template <int W> __device__ __forceinline__ void f32_store_vec(float* dst, const
 __device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
 
 // fp16 residual stream: saturating round-to-nearest store, widening load
-__device__ __forceinline__ __half to_half_sat(float x) { return __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)); }
+__device__ __forceinline__ __half to_half_sat(float x) {  // one F2FP.SATFINITE: +-inf / overflow clamp to +-65504
+  unsigned short h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  return __ushort_as_half(h);
+}
 template <int W> __device__ __forceinline__ void res_load_vec(float* v, const void* base, size_t off, int half) {
   if (half) {
     const __half* p = reinterpret_cast<const __half*>(base) + off;

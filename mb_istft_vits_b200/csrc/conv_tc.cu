@@ -219,6 +219,7 @@ struct TcRt {  // runtime scalars the kernel needs beyond ConvArgs
   int slab_stage_bytes, w_stage_bytes, n_slab_stages, n_w_stages;
   int t_tiles, c_tiles, total_tiles;
   int xchg_off;      // byte offset of the gate exchange buffer in dynamic smem
+  int w_resident;    // all weight tiles of the (single) channel tile fit the ring: load them once per CTA
   int prefetch_res;  // issue an L2 prefetch of the tile's residual input (tmR) when its operand loads start
   long long* dbg;    // MBV_TIMELINE=1: per-CTA clock stamps [cta][role 0..2][tile][2] (debug only)
 };
@@ -302,17 +303,18 @@ __device__ __forceinline__ void epi_res(const EpiParams& p, int b, int n, int ph
   if (p.n_act) {
     const float slope = p.slope, scale = (sm >= 3) ? p.scale : 1.f;
     T* dst = reinterpret_cast<T*>(p.act[0]) + ((size_t)b * p.rows_out + t_first + p.row_add) * p.ld + n;
+    if (sm >= 3) {  // mean over the parallel ResBlocks (models.py:361)
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float v = x[i] * scale;
-      MBV_EL(i) op_store1<Op>(dst + i * step, fmaxf(v, v * slope));
+      for (int i = 0; i < 32; ++i) x[i] *= scale;
     }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) MBV_EL(i) op_store1<Op>(dst + i * step, fmaxf(x[i], x[i] * slope));
     // ReflectionPad1d((1,0)) of the conv_post input: mapped row dup_src is also stored at row dup_dst
     const int di = p.dup_src - p.row_add - t_first;
     if (p.dup_src >= 0 && di >= 0 && di < nt) {
       float v = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) if (i == di) v = x[i] * scale;
+      for (int i = 0; i < 32; ++i) if (i == di) v = x[i];
       op_store1<Op>(reinterpret_cast<T*>(p.act[0]) + ((size_t)b * p.rows_out + p.dup_dst) * p.ld + n, fmaxf(v, v * slope));
     }
   }
@@ -521,6 +523,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         __syncwarp();
         if (++sx == rt.n_slab_stages) { sx = 0; px ^= 1; }
         for (int tap = 0; tap < a.taps; ++tap) {
+          if (rt.w_resident && tile != (int)blockIdx.x) continue;  // weights already resident from the first tile
           mbar_wait(BAR(iWE + sw), pw ^ 1);
           if (elect_one()) {
             const uint32_t wdst = smem_u32(smW + (size_t)sw * rt.w_stage_bytes);
@@ -555,6 +558,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         tc_fence_after();
         uint32_t x_lo = desc_lo(smem_u32(smX + (size_t)sx * rt.slab_stage_bytes));
         for (int tap = 0; tap < a.taps; ++tap) {
+          if (rt.w_resident) { sw = kb * a.taps + tap; pw = 0; }  // stage = (k-block, tap); phase 0 stays complete
           mbar_wait(BAR(iWF + sw), pw);
           tc_fence_after();
           const uint32_t w_lo = desc_lo(smem_u32(smW + (size_t)sw * rt.w_stage_bytes));
@@ -563,12 +567,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             for (int k = 0; k < 4; ++k) {
               tc_mma<KIND>(tmem_d, desc64(w_lo + 2 * k), desc64(x_lo + 2 * k), idesc, (k == 0) ? accum : 1u);
             }
-            tc_commit(BAR(iWE + sw));
+            if (!rt.w_resident) tc_commit(BAR(iWE + sw));
           }
           __syncwarp();
           accum = 1;
           x_lo += tap_step;  // next tap = `dil` rows further into the slab
-          if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
+          if (!rt.w_resident && ++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
         }
         if (elect_one()) tc_commit(BAR(iXE + sx));
         __syncwarp();
@@ -788,6 +792,8 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed for the weight map";
   }
+  // small layers (stage-1 k=3 convs, flow post): the whole weight set of the channel tile stays in shared memory
+  plan->w_resident = (plan->c_tiles == 1 && a.n_phases == 1 && a.taps * (a.Cp_in / KB) <= plan->n_w_stages) ? 1 : 0;
   plan->prefetch_res = 0;
   if (a.epi.mode == EPI_RES && a.epi.xin != nullptr && a.epi.row_mul == 1) {
     const int rs = a.epi.res_half ? 2 : 4;
@@ -897,6 +903,7 @@ cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStr
   rt.t_tiles = p.t_tiles; rt.c_tiles = p.c_tiles; rt.total_tiles = p.total_tiles;
   rt.prefetch_res = p.prefetch_res;
   rt.xchg_off = p.xchg_off;
+  rt.w_resident = p.w_resident;
   cudaError_t e;
   if (prec == 2) e = dispatch<OpBF16>(a, p, rt, st, false, a.epi.mode, a.epi.ld, a.epi.res_half);
   else if (a.epi.res_half) e = cudaErrorInvalidValue;

@@ -20,6 +20,7 @@ struct TcPlan {
   int slab_stage_bytes, w_stage_bytes, n_slab_stages, n_w_stages;
   int t_tiles, c_tiles, total_tiles;
   int xchg_off;         // byte offset of the gate exchange buffer
+  int w_resident;       // weights of the single channel tile stay resident in the ring
   int smem_bytes;
   int grid;
 };
