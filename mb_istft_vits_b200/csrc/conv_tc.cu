@@ -761,7 +761,11 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
   // Bytes in flight are what hide the ~1.3 us L2->SMEM TMA round trip (measured: with 5 x 16 KB weight stages the MMA
   // warp found its weights missing on 45 % of its waits): give the weight ring everything two slab stages leave over.
   const int budget = 222 * 1024 - xchg;
-  plan->n_slab_stages = plan->slab_stage_bytes > 20 * 1024 ? 2 : 3;
+  // A slab lasts taps x 512 tensor-core cycles: few taps need more slabs in flight, many taps more weight stages.
+  plan->n_slab_stages = a.taps == 1 ? 4 : (a.taps <= 4 ? 3 : 2);
+  while (plan->n_slab_stages > 2 &&
+         (budget - plan->n_slab_stages * plan->slab_stage_bytes) / plan->w_stage_bytes < (a.taps <= 4 ? 4 : 6))
+    plan->n_slab_stages--;
   plan->n_w_stages = (budget - plan->n_slab_stages * plan->slab_stage_bytes) / plan->w_stage_bytes;
   if (plan->n_w_stages > 10) plan->n_w_stages = 10;
   if (plan->n_w_stages < 2) return "tcgen05 conv: not enough shared memory for two weight stages";
