@@ -297,6 +297,10 @@ def run_native(args):
         return
 
     peaks = measured_peaks()
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp) and args.precision == "bf16" and B == B_PER_GPU and T == T_FRAMES:
+        traffic = json.load(open(tp))  # dram__bytes_read+write per launch from the committed ncu capture of this workload
     flops_step = eng.decode_flops(B, T) + eng.flow_flops(B, T)
     conv_ms, conv_n = prof["conv"]
     tail_prof_ms, tail_n = prof["tail"]
@@ -306,7 +310,9 @@ def run_native(args):
     roofline = {
         "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all %d launches per step)" % (conv_n // max(1, args.steps)),
         "bound": "tensor", "achieved": conv_tflops, "peak": prec_peak, "unit": "TFLOP/s",
-        "frac": (conv_tflops / prec_peak) if conv_tflops else None, "traffic": None,
+        "frac": (conv_tflops / prec_peak) if conv_tflops else None,
+        "traffic": traffic.get("conv_dram_bytes_per_launch"), "traffic_source": traffic.get("source"),
+        "algorithmic_flops_per_launch": flops_step / max(1, conv_n // max(1, args.steps)),
         "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)"
                        + (" x 0.5 for tf32" if args.precision == "tf32" else ""),
         "flops_per_step": flops_step, "avg_launch_ms": conv_ms / conv_n if conv_n else None,
@@ -316,7 +322,7 @@ def run_native(args):
     roofline_tail = {
         "kernel": "tail_kernel (head + iSTFT + PQMF)", "bound": "hbm",
         "achieved": tail_bytes / (tail_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-        "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+        "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic.get("tail_dram_bytes_per_launch"),
         "peak_source": peaks["source"] + " hbm_gbs (burst; kernel timed alone)", "ms": tail_ms,
         "ms_inside_step": tail_prof_ms / tail_n if tail_n else None, "bytes_per_launch": tail_bytes,
     }
