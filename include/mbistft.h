@@ -149,6 +149,14 @@ int mbv_profile_read(mbv_handle* h, double* ms, int32_t* count);
 int mbv_tail(mbv_handle* h, const float* logits, float* wav, float* o_mb, float* spec, float* phase,
              int32_t B, int32_t T, void* stream);
 
+/* NEXT-row widening: the waveform post-processing of the reference's TTS service
+ * (tts_vits.py:204-216): per utterance, peak-normalise to 0.9 if auto_normalize and the peak exceeds 0.01, clip to
+ * [-1, 1], multiply by 32767 and truncate to int16.  wav: [B][stride] fp32 (device), n_samples: [B] valid sample
+ * counts (device int32) or NULL = stride, scratch: >= 4*B bytes (device), pcm: [B][stride] int16 (device; samples
+ * past n_samples[b] are written as 0).  Bit-exact with the reference's numpy arithmetic. */
+int mbv_pcm16(mbv_handle* h, const float* wav, const int32_t* n_samples, int32_t B, int32_t stride, int32_t auto_normalize,
+              void* scratch, int16_t* pcm, void* stream);
+
 const char* mbv_last_error(mbv_handle* h);
 
 #ifdef __cplusplus

@@ -54,4 +54,8 @@ cudaError_t launch_unpack_output(const float* src, float* dst, int B, int C, int
 cudaError_t launch_cond_gemv(const float* g, const float* w, const float* bias, const float* base, float* out,
                              int B, int G, int N, int out_ld, cudaStream_t st);
 
+// per-utterance peak normalise (x0.9 if peak > 0.01), clip, x32767, truncate to int16 (tts_vits.py:204-216)
+cudaError_t launch_pcm16(const float* wav, const int* n_valid, int B, int stride, int auto_normalize, unsigned int* peak_bits,
+                         short* pcm, cudaStream_t st);
+
 }  // namespace mbv

@@ -977,6 +977,17 @@ extern "C" int mbv_tail(mbv_handle* h, const float* logits, float* wav, float* o
   return rc;
 }
 
+extern "C" int mbv_pcm16(mbv_handle* h, const float* wav, const int32_t* n_samples, int32_t B, int32_t stride,
+                         int32_t auto_normalize, void* scratch, int16_t* pcm, void* stream) {
+  if (!h) return MBV_ERR_INVALID;
+  if (!wav || !pcm || !scratch || B < 1 || stride < 1) return fail(h, MBV_ERR_INVALID, "mbv_pcm16: bad argument");
+  if (B > 65535) return fail(h, MBV_ERR_UNSUPPORTED, "B > 65535");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  CUDA_TRY(h, launch_pcm16(wav, n_samples, B, stride, auto_normalize, (unsigned int*)scratch, pcm, (cudaStream_t)stream));
+  h->last_launches = 2;
+  return MBV_OK;
+}
+
 extern "C" int mbv_last_launch_count(mbv_handle* h) { return h ? h->last_launches : 0; }
 
 extern "C" int mbv_set_profiling(mbv_handle* h, int32_t on) {

@@ -97,4 +97,62 @@ cudaError_t launch_cond_gemv(const float* g, const float* w, const float* bias, 
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Waveform post-processing of the reference's TTS service (tts_vits.py:204-216): per-utterance peak normalisation to
+// 0.9 (only if the peak exceeds 0.01), clip to [-1, 1], scale by 32767 and truncate to int16.  Two passes: a per-
+// utterance max |x| (warp shuffle -> one atomicMax on the float bit pattern per CTA), then the conversion.
+// Every float operation is a single correctly-rounded IEEE op in the reference's order, so the PCM is bit-exact.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pcm_peak_kernel(const float* __restrict__ wav, const int* __restrict__ n_valid,
+                                                       int stride, unsigned int* __restrict__ peak_bits) {
+  const int b = blockIdx.y;
+  const int n = n_valid ? n_valid[b] : stride;
+  const float* x = wav + (size_t)b * stride;
+  float m = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float wm[8];
+  if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, wm[i]);
+    atomicMax(peak_bits + b, __float_as_uint(m));  // non-negative floats order like their bit patterns
+  }
+}
+
+__global__ void __launch_bounds__(256) pcm_convert_kernel(const float* __restrict__ wav, const int* __restrict__ n_valid,
+                                                          int stride, const unsigned int* __restrict__ peak_bits,
+                                                          int auto_normalize, short* __restrict__ pcm) {
+  const int b = blockIdx.y;
+  const int n = n_valid ? n_valid[b] : stride;
+  const float peak = __uint_as_float(peak_bits[b]);
+  const bool norm = auto_normalize && peak > 0.01f;
+  const float* x = wav + (size_t)b * stride;
+  short* o = pcm + (size_t)b * stride;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < stride; i += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (i < n) {
+      v = x[i];
+      if (norm) v = __fmul_rn(__fdiv_rn(v, peak), 0.9f);
+      v = fminf(fmaxf(v, -1.f), 1.f);
+      v = __fmul_rn(v, 32767.f);
+    }
+    o[i] = (short)(int)v;  // truncation toward zero, like numpy's astype(int16)
+  }
+}
+
+cudaError_t launch_pcm16(const float* wav, const int* n_valid, int B, int stride, int auto_normalize, unsigned int* peak_bits,
+                         short* pcm, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(peak_bits, 0, sizeof(unsigned int) * B, st);
+  if (e != cudaSuccess) return e;
+  int gx = (stride + 256 * 8 - 1) / (256 * 8);
+  if (gx > 1024) gx = 1024;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, B);
+  pcm_peak_kernel<<<grid, 256, 0, st>>>(wav, n_valid, stride, peak_bits);
+  pcm_convert_kernel<<<grid, 256, 0, st>>>(wav, n_valid, stride, peak_bits, auto_normalize, pcm);
+  return cudaGetLastError();
+}
+
 }  // namespace mbv

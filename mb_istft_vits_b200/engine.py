@@ -202,6 +202,36 @@ class Engine:
                                       self._ptr(phase), B, T, self._stream()))
         return wav, o_mb, spec, phase
 
+    # ---- widening beyond the seam
+    def pcm16(self, wav, n_samples=None, auto_normalize=True):
+        """tts_vits.py:204-216 on the GPU: per-utterance peak normalisation (x0.9 when the peak exceeds 0.01), clip,
+        int16.  wav: [B, 1, S] or [B, S] fp32; n_samples: [B] valid lengths or None.  Returns int16 [B, S]."""
+        w = self._prep(wav)
+        if w.dim() == 3:
+            w = w[:, 0, :]
+        w = w.contiguous()
+        B, S = w.shape
+        ns = None if n_samples is None else torch.as_tensor(n_samples).to(device=self.device, dtype=torch.int32).contiguous()
+        scratch = torch.empty(B, dtype=torch.int32, device=self.device)
+        pcm = torch.empty((B, S), dtype=torch.int16, device=self.device)
+        self._check(self.lib.mbv_pcm16(self._h, self._ptr(w), self._ptr(ns), B, S, 1 if auto_normalize else 0,
+                                       self._ptr(scratch), self._ptr(pcm), self._stream()))
+        return pcm
+
+    def decode_chunked(self, z, g=None, chunk_frames=256, halo_frames=None):
+        """Exact streaming decode: the decoder is convolutional with a receptive field of +-24 latent frames (MB/MS;
+        +-13 single-band), so decoding overlapping windows [a-halo, b+halo) and keeping the samples of
+        [a, b) reproduces the one-shot result bit for bit -- unlike the approximate overlap-add chunking of the
+        reference notebooks (infer.ipynb cells 4-6).  Yields (first_frame, wav_chunk [B,1,256*(b-a)])."""
+        B, _, T = z.shape
+        halo = halo_frames if halo_frames is not None else 32
+        spf = self.spf
+        for a0 in range(0, T, chunk_frames):
+            b0 = min(T, a0 + chunk_frames)
+            lo, hi = max(0, a0 - halo), min(T, b0 + halo)
+            wav = self.decode(z[:, :, lo:hi].contiguous(), g, want_mb=False, want_spec=False)[0]
+            yield a0, wav[:, :, (a0 - lo) * spf: (b0 - lo) * spf]
+
     def set_profiling(self, on: bool):
         self._check(self.lib.mbv_set_profiling(self._h, 1 if on else 0))
 

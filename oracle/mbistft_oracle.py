@@ -262,6 +262,19 @@ def flow_decode(sd, cfg, z_p, y_mask, g=None):
 
 
 # ----------------------------------------------------------------------------
+# next-row widening: waveform post-processing of the TTS service (tts_vits.py:204-216), numpy like the reference
+# ----------------------------------------------------------------------------
+def pcm16(audio, auto_normalize=True):
+    """One utterance, float32 numpy array -> int16.  Steps 3-5 of tts_vits.py:204-216 verbatim in numpy."""
+    audio = np.asarray(audio, dtype=np.float32)
+    max_abs_val = np.abs(audio).max()
+    if auto_normalize and max_abs_val > 0.01:
+        audio = (audio / max_abs_val) * 0.9
+    audio = np.clip(audio, -1.0, 1.0)
+    return (audio * 32767).astype(np.int16)
+
+
+# ----------------------------------------------------------------------------
 # comparators used by the parity tests (tolerances from BASELINE.json north_star)
 # ----------------------------------------------------------------------------
 def max_abs_over_peak(test, ref):

@@ -255,3 +255,43 @@ def test_errors_are_loud():
     cfg2["gen_istft_n_fft"] = 32
     with pytest.raises(MbvError):
         Engine(cfg2, sd, precision="fp32")
+
+
+# ------------------------------------------------------------------------------------------------
+# widening beyond the seam
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("auto_normalize", [True, False])
+def test_pcm16_postprocessing_is_bit_exact(auto_normalize):
+    """tts_vits.py:204-216 (peak-normalise x0.9 if peak > 0.01, clip, x32767, truncate): integer output, so the bar is
+    bit-exact against the numpy restatement -- including a quiet utterance (no normalisation), a clipping one when
+    normalisation is off, ragged lengths and an empty tail."""
+    import numpy as np
+    cfg, sd, t, meta = load_case("mini_mb")
+    eng = _engine(cfg, sd, "fp32")
+    gen = torch.Generator().manual_seed(3)
+    S = 20001
+    wav = torch.randn((5, 1, S), generator=gen) * torch.tensor([0.3, 0.002, 2.5, 1e-4, 0.9]).view(5, 1, 1)
+    wav[4, 0, 17] = 1.0
+    n = torch.tensor([S, 1234, S - 1, 1, 8000], dtype=torch.int32)
+    pcm = eng.pcm16(wav.cuda(), n, auto_normalize=auto_normalize).cpu().numpy()
+    for b in range(5):
+        ref = orc.pcm16(wav[b, 0, : int(n[b])].numpy(), auto_normalize)
+        assert np.array_equal(pcm[b, : int(n[b])], ref), b
+        assert not pcm[b, int(n[b]):].any()
+
+
+@pytest.mark.parametrize("name,chunk", [("mb_long", 37), ("mb_long", 150), ("infer_istft", 8), ("ms_spk", 7)])
+def test_chunked_decode_is_bit_identical_to_one_shot(name, chunk):
+    """Exact streaming decode with the receptive-field halo: every chunk equals the corresponding slice of the
+    one-shot decode bit for bit (the reference notebooks' overlap-add chunking is only approximate)."""
+    cfg, sd, t, meta = load_case(name)
+    eng = _engine(cfg, sd, "bf16")
+    z = (t["z"] * t["mask"]).cuda()
+    g = t.get("g")
+    g = g.cuda() if g is not None else None
+    full = eng.decode(z, g, want_mb=False, want_spec=False)[0]
+    parts = [w for _, w in eng.decode_chunked(z, g, chunk_frames=chunk)]
+    torch.cuda.synchronize()
+    got = torch.cat(parts, dim=-1)
+    assert got.shape == full.shape
+    assert torch.equal(got, full)
