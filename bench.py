@@ -164,7 +164,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _emit(line, fd):
+    os.write(fd, (json.dumps(line) + "\n").encode())
+
+
 def run_native(args):
+    # Libraries (e.g. NCCL's version banner) print to stdout; the contract is ONE JSON line there.  Everything but that
+    # line is routed to stderr at the file-descriptor level.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     rank, local_rank, world = dist_env()
     if world > 1:
@@ -357,9 +366,10 @@ def run_native(args):
                    "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
                    "tflops_whole_step": flops_step / (ms_step * 1e-3) / 1e12},
     }
-    print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    _emit(line, json_fd)
 
 
 def main():
