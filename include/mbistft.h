@@ -142,6 +142,10 @@ double mbv_flow_flops(mbv_handle* h, int32_t B, int32_t T);
  * and clears the record. */
 int mbv_set_profiling(mbv_handle* h, int32_t on);
 int mbv_profile_read(mbv_handle* h, double* ms, int32_t* count);
+/* Same record, launch by launch (in launch order): elapsed ms and a short description ("conv m<epilogue mode>
+ * Ci<in> N<rows> k<taps> d<dil> ph<phases> L<rows out> nt<tile width>", "tail", "") of up to cap launches; *n = how
+ * many were written.  Clears the record. */
+int mbv_profile_read_launches(mbv_handle* h, float* ms, char* desc, int32_t desc_stride, int32_t cap, int32_t* n);
 
 /* Stand-alone entry for the fused tail (head + iSTFT + sub-band synthesis) on caller-provided
  * logits [B, F, n_logit_channels] (channels-last, F = frames): used by the parity tests and the

@@ -720,6 +720,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+static EncodeTiledFn get_encode_fn();
+void* tc_tensormap_encoder() { return reinterpret_cast<void*>(get_encode_fn()); }
+
 static EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
@@ -741,9 +744,12 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
   if (a.Cp_in % 64 != 0) return "tcgen05 conv: padded input channels must be a multiple of 64";
   const int n_logical = a.N_total;
   if (n_logical % TC_M != 0) return "tcgen05 conv: packed output channels must be a multiple of 128";
-  // time tile: as few tiles as a 256-column accumulator allows, then shrunk to what the length needs
-  const int max_n = 256;
-  const int tiles = (a.L_out + max_n - 1) / max_n;
+  // Time tile: as few tiles as a 256-column accumulator allows, then shrunk to what the length needs.
+  // (Measured, profiles/r02_tile_policy_ab.txt: choosing narrower tiles to remove the wave-quantisation tail of the
+  //  persistent grid -- e.g. 192 instead of 256 columns at stage 0, 16 rounds instead of 13 -- is 4-6 % SLOWER per
+  //  step: every tile re-streams its weight taps L2 -> SMEM -> tensor core, so bytes per FLOP grow as the tile narrows
+  //  and the MMA-bound layers lose more than the shorter last round gains.)
+  const int tiles = (a.L_out + 255) / 256;
   int n_time = ((a.L_out + tiles - 1) / tiles + 15) / 16 * 16;
   if (n_time < 16) n_time = 16;
   plan->n_time = n_time;

@@ -28,6 +28,8 @@ struct TcPlan {
 const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, TcPlan* plan);
 cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& plan, cudaStream_t st);
 cudaError_t tc_set_attributes();
+// cuTensorMapEncodeTiled through the runtime's driver entry point (nullptr if unavailable); shared with tail.cu
+void* tc_tensormap_encoder();
 
 // ---- tail.cu
 struct TailArgs {

@@ -107,7 +107,7 @@ struct mbv_handle {
 
   // per-launch device timing (mbv_set_profiling)
   bool profiling = false;
-  struct ProfRec { int kind; cudaEvent_t e0, e1; };
+  struct ProfRec { int kind; cudaEvent_t e0, e1; char desc[56]; };
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_pool;
   cudaEvent_t get_event() {
@@ -622,12 +622,20 @@ struct Ctx {
 
 // RAII bracket: two events around one launch when profiling is on
 struct ProfScope {
-  mbv_handle* h; cudaStream_t st; int kind; cudaEvent_t e0;
-  ProfScope(Ctx& cx, int kind_) : h(cx.h), st(cx.st), kind(kind_), e0(nullptr) {
+  mbv_handle* h; cudaStream_t st; int kind; cudaEvent_t e0; char desc[56];
+  ProfScope(Ctx& cx, int kind_, const char* d = "") : h(cx.h), st(cx.st), kind(kind_), e0(nullptr) {
+    snprintf(desc, sizeof(desc), "%s", d);
     if (h->profiling) { e0 = h->get_event(); cudaEventRecord(e0, st); }
   }
   ~ProfScope() {
-    if (e0) { cudaEvent_t e1 = h->get_event(); cudaEventRecord(e1, st); h->prof.push_back({kind, e0, e1}); }
+    if (e0) {
+      cudaEvent_t e1 = h->get_event();
+      cudaEventRecord(e1, st);
+      mbv_handle::ProfRec r;
+      r.kind = kind; r.e0 = e0; r.e1 = e1;
+      memcpy(r.desc, desc, sizeof(desc));
+      h->prof.push_back(r);
+    }
   }
 };
 
@@ -640,8 +648,8 @@ int run_conv(Ctx& cx, const ConvLayer& L, const void* x, int B, int L_in, int L_
   for (int i = 0; i < kMaxPhases; ++i) a.shift0[i] = L.shift0[i];
   a.epi = epi;
   if (a.epi.bias == nullptr) { a.epi.bias = L.bias; a.epi.bias_bs = 0; }
-  ProfScope prof(cx, 0);
   if (h->prec == MBV_PREC_FP32 || (h->cfg.flags & MBV_FLAG_FORCE_SIMT)) {
+    ProfScope prof(cx, 0, "conv_simt");
     CUDA_TRY(h, launch_conv_simt(h->prec, a, cx.st));
   } else {
     TcPlan plan;
@@ -653,6 +661,10 @@ int run_conv(Ctx& cx, const ConvLayer& L, const void* x, int B, int L_in, int L_
       cx.plans->push_back(plan);
     }
     cx.plan_idx++;
+    char desc[56];
+    snprintf(desc, sizeof(desc), "conv m%d Ci%d N%d k%d d%d ph%d L%d nt%d", epi.mode, L.Cp_in, L.N_total, L.taps, L.dil,
+             L.n_phases, L_out, plan.n_time);
+    ProfScope prof(cx, 0, h->profiling ? desc : "");
     CUDA_TRY(h, launch_conv_tc(h->prec, a, plan, cx.st));
   }
   cx.launches++;
@@ -734,7 +746,7 @@ int run_tail(Ctx& cx, const float* logits, float* wav, float* o_mb, float* spec,
   memcpy(ta.mod, h->tail_mod, sizeof(ta.mod));
   memcpy(ta.g2, h->tail_g2, sizeof(ta.g2));
   ta.fast_pqmf = h->tail_fast;
-  ProfScope prof(cx, 1);
+  ProfScope prof(cx, 1, "tail");
   CUDA_TRY(h, launch_tail(ta, h->prec == MBV_PREC_FP32 ? 1 : 0, h->num_sms, cx.st));
   cx.launches++;
   return MBV_OK;
@@ -1007,6 +1019,26 @@ extern "C" int mbv_profile_read(mbv_handle* h, double* ms, int32_t* count) {
     h->ev_pool.push_back(r.e1);
   }
   h->prof.clear();
+  return MBV_OK;
+}
+
+extern "C" int mbv_profile_read_launches(mbv_handle* h, float* ms, char* desc, int32_t desc_stride, int32_t cap, int32_t* n) {
+  if (!h || !ms || !n || cap < 0) return MBV_ERR_INVALID;
+  int k = 0;
+  for (auto& r : h->prof) {
+    CUDA_TRY(h, cudaEventSynchronize(r.e1));
+    float t = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&t, r.e0, r.e1));
+    if (k < cap) {
+      ms[k] = t;
+      if (desc && desc_stride > 0) snprintf(desc + (size_t)k * desc_stride, desc_stride, "%s", r.desc);
+      ++k;
+    }
+    h->ev_pool.push_back(r.e0);
+    h->ev_pool.push_back(r.e1);
+  }
+  h->prof.clear();
+  *n = k;
   return MBV_OK;
 }
 

@@ -11,6 +11,11 @@
 // blocks of sub-band signal, of which 249 are owned outputs (the FIR needs +-2 hop blocks of halo):
 // 97 % useful work.  Shared memory: logits tile 72 KB + frame scratch 20 KB + sub-band tile 16 KB -> 2 CTAs/SM,
 // so one CTA's loads overlap the other's math.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -481,6 +486,370 @@ __global__ void __launch_bounds__(T2_THREADS, 1024 / T2_THREADS) tail_mb_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Multi-band / multi-stream tail, v3.  v2 was bound by shared-memory wavefronts (17.6 M per launch, 63 % L1 pipe,
+// profiles/r01_ncu_full_final.txt): every intermediate (frames, sub-band signal, modulated signal) made a round
+// trip through shared memory.  v3 keeps them in registers:
+//   * lane = STFT frame, all four bands in the same thread.  The logits tile arrives by TMA with the 128-byte
+//     swizzle, so "one 288-byte row per lane" reads are bank-conflict-free 16-byte loads (18 per frame).
+//   * overlap-add = 12 warp shuffles per band (lane l owns hop block l: frames l, l+1, l+2, l+3); only the 6 vectors
+//     per band that cross a warp boundary go through shared memory.
+//   * the thread then holds its hop block of all four bands: envelope, optional o_mb store and the PQMF cosine
+//     modulation (8 rows) happen in registers; only U[8][512] is written to shared memory.
+//   * synthesis FIR: thread = (pair of hop blocks, residue pair): two 24-float windows serve 8 outputs (v2: 20-float
+//     windows for 4), rows of the two residue classes 516 floats apart so the 16-byte loads of a quarter warp hit
+//     disjoint banks.  Outputs are staged (XOR-swizzled) in the dead logits buffer and leave as coalesced 16-byte stores.
+//   * persistent CTAs of 128 threads, 4 per SM, each owning an EQUAL contiguous range of hop blocks (cut into tiles of
+//     <= 121 blocks that never straddle an utterance): no wave-quantisation tail.
+// Arithmetic (operation order included) is identical to v2, so the parity tests need no new tolerances.
+// ------------------------------------------------------------------------------------------------
+constexpr int T3_NF = 128;                 // frames per tile = threads per CTA
+constexpr int T3_NQ = T3_NF - 7;           // owned hop blocks per tile (max)
+constexpr int T3_UP = 516;                 // floats per U / Y row; = 4 mod 8 (bank spread between adjacent rows)
+constexpr int T3_BOX01 = T3_NF * 128;      // bytes of one 32-float box
+constexpr int T3_BOX2 = T3_NF * 32;        // bytes of the 8-float box
+constexpr int T3_OFF_U = 2 * T3_BOX01 + T3_BOX2;              // 36864
+constexpr int T3_OFF_HALO = T3_OFF_U + 8 * T3_UP * 4;         // + 16512
+constexpr int T3_OFF_TAB = T3_OFF_HALO + 4 * 4 * 6 * 16;      // + 1536
+constexpr int T3_OFF_BAR = T3_OFF_TAB + 1024;
+constexpr int T3_SMEM = T3_OFF_BAR + 16;
+
+__device__ __forceinline__ float4 shfl_down4(const float* v, int delta) {
+  float4 r;
+  r.x = __shfl_down_sync(0xffffffffu, v[0], delta);
+  r.y = __shfl_down_sync(0xffffffffu, v[1], delta);
+  r.z = __shfl_down_sync(0xffffffffu, v[2], delta);
+  r.w = __shfl_down_sync(0xffffffffu, v[3], delta);
+  return r;
+}
+__device__ __forceinline__ void add4(float4& y, const float4& v) { y.x += v.x; y.y += v.y; y.z += v.z; y.w += v.w; }
+
+// 16-byte chunk c (0..17) of frame row r of the swizzled logits tile
+template <int C>
+__device__ __forceinline__ float4 t3_chunk(const uint8_t* sm, int r) {
+  if constexpr (C < 16) {
+    constexpr int box = C >> 3, cc = C & 7;
+    return *reinterpret_cast<const float4*>(sm + box * T3_BOX01 + r * 128 + ((cc ^ (r & 7)) << 4));
+  } else {
+    constexpr int cc = C - 16;
+    return *reinterpret_cast<const float4*>(sm + 2 * T3_BOX01 + r * 32 + ((cc ^ ((r >> 2) & 1)) << 4));
+  }
+}
+template <int C0, int N>
+struct T3Load {
+  static __device__ __forceinline__ void run(const uint8_t* sm, int r, float* buf) {
+    const float4 v = t3_chunk<C0>(sm, r);
+    buf[0] = v.x; buf[1] = v.y; buf[2] = v.z; buf[3] = v.w;
+    T3Load<C0 + 1, N - 1>::run(sm, r, buf + 4);
+  }
+};
+template <int C0> struct T3Load<C0, 0> { static __device__ __forceinline__ void run(const uint8_t*, int, float*) {} };
+
+template <bool PRECISE, bool EMIT>
+__global__ void __launch_bounds__(T3_NF, 4)
+tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__ CUtensorMap tm8,
+                const __grid_constant__ TailArgs a) {
+  constexpr int S = 4;
+  extern __shared__ __align__(1024) uint8_t sm3[];
+  float* s_u = reinterpret_cast<float*>(sm3 + T3_OFF_U);          // [8][T3_UP]  (generic filter: rows 0..3 = Y)
+  float4* s_halo = reinterpret_cast<float4*>(sm3 + T3_OFF_HALO);  // [warp][band][6]
+  float* s_tab = reinterpret_cast<float*>(sm3 + T3_OFF_TAB);      // fast: g2[4][16]; generic: coef[4][64]
+  float* s_out = reinterpret_cast<float*>(sm3);                   // [64 rows of 2 hop blocks][32], chunks XOR-swizzled
+  const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(sm3 + T3_OFF_BAR));
+  const uint32_t sm_base = static_cast<uint32_t>(__cvta_generic_to_shared(sm3));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int L = a.L, F = L + 1;
+
+  // this CTA's equal share of the B*L hop blocks
+  const long long total = (long long)a.B * L;
+  const long long per = (total + gridDim.x - 1) / gridDim.x;
+  long long g = per * blockIdx.x;
+  const long long g_end = (g + per < total) ? g + per : total;
+
+  struct Tile { int b, q0, nq; };
+  auto next_tile = [&](long long pos) {
+    Tile t;
+    t.b = (int)(pos / L);
+    t.q0 = (int)(pos - (long long)t.b * L);
+    const long long rem = g_end - pos;
+    const int left = (int)((rem + T3_NQ - 1) / T3_NQ);
+    int nq = (int)((rem + left - 1) / left);
+    if (nq > L - t.q0) nq = L - t.q0;
+    t.nq = nq;
+    return t;
+  };
+  auto issue_load = [&](const Tile& t) {  // one thread: three boxes of the logits rows [q0-3, q0-3+128) (OOB rows -> 0)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)T3_OFF_U) : "memory");
+    const int f0 = t.q0 - 3;
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(sm_base), "l"(reinterpret_cast<uint64_t>(&tm32)), "r"(bar), "r"(0), "r"(f0), "r"(t.b) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(sm_base + T3_BOX01), "l"(reinterpret_cast<uint64_t>(&tm32)), "r"(bar), "r"(32), "r"(f0), "r"(t.b) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(sm_base + 2 * T3_BOX01), "l"(reinterpret_cast<uint64_t>(&tm8)), "r"(bar), "r"(64), "r"(f0), "r"(t.b) : "memory");
+  };
+
+  if (a.fast_pqmf) { if (tid < 64) s_tab[tid] = a.g2[tid >> 4][tid & 15]; }
+  else { s_tab[tid] = a.coef[tid >> 6][tid & 63]; s_tab[tid + 128] = a.coef[(tid + 128) >> 6][tid & 63]; }
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm32)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm8)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (g >= g_end) return;
+  Tile cur = next_tile(g);
+  if (tid == 0) issue_load(cur);
+  uint32_t parity = 0;
+
+  while (true) {
+    const int b = cur.b, Q0 = cur.q0, nq = cur.nq;
+    const int QY0 = Q0 - 2, F0 = Q0 - 3;
+    const bool last_tile = (Q0 + nq == L);
+    t2_mbar_wait(bar, parity);
+    parity ^= 1;
+
+    // ---- phase A: head + inverse DFT + window (registers), overlap-add by shuffles.  Lane = frame F0 + tid = hop block QY0 + tid.
+    float4 y[S];
+    {
+      const int f = F0 + tid;
+      // Frames outside the utterance read TMA's zero fill (finite head values) and are zeroed after the transform, so the
+      // whole band body is branch-free (v3.0 spent 12 % of its instructions and 40 % of its stall samples on BSSY/BRA/BSYNC).
+      const bool live = (f >= 0) && (f < F);
+      const bool emit = EMIT && live && (f >= Q0) && (f < Q0 + nq || (last_tile && f == L));
+      auto band = [&](auto s_tag) {
+        constexpr int s = decltype(s_tag)::value;
+        float fr[16];
+        {
+          constexpr int f0 = 18 * s, c0 = f0 / 4, c1 = (f0 + 17) / 4;
+          float buf[(c1 - c0 + 1) * 4];
+          T3Load<c0, c1 - c0 + 1>::run(sm3, tid, buf);
+          const float* x = buf + (f0 - 4 * c0);
+          float re[9], im[9], mag[9], ph[9];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) head<PRECISE>(x[k], x[9 + k], mag[k], ph[k], re[k], im[k]);
+          if (EMIT) {
+            if (emit) {
+              float* sp = a.spec + ((size_t)b * S + s) * 9 * F + f;
+              float* pp = a.phase + ((size_t)b * S + s) * 9 * F + f;
+#pragma unroll
+              for (int k = 0; k < 9; ++k) { sp[(size_t)k * F] = mag[k]; pp[(size_t)k * F] = ph[k]; }
+            }
+          }
+          idft16_windowed(re, im, fr);
+          const float keep = live ? 1.f : 0.f;
+#pragma unroll
+          for (int n = 0; n < 16; ++n) fr[n] *= keep;
+        }
+        // hop block of this lane = part 3 of its own frame + part 2 / 1 / 0 of the next three frames (same order as v2)
+        float4 acc = make_float4(fr[12], fr[13], fr[14], fr[15]);
+        const float k1 = lane < 31 ? 1.f : 0.f, k2 = lane < 30 ? 1.f : 0.f, k3 = lane < 29 ? 1.f : 0.f;
+        float4 v = shfl_down4(fr + 8, 1);
+        acc.x = fmaf(k1, v.x, acc.x); acc.y = fmaf(k1, v.y, acc.y); acc.z = fmaf(k1, v.z, acc.z); acc.w = fmaf(k1, v.w, acc.w);
+        v = shfl_down4(fr + 4, 2);
+        acc.x = fmaf(k2, v.x, acc.x); acc.y = fmaf(k2, v.y, acc.y); acc.z = fmaf(k2, v.z, acc.z); acc.w = fmaf(k2, v.w, acc.w);
+        v = shfl_down4(fr, 3);
+        acc.x = fmaf(k3, v.x, acc.x); acc.y = fmaf(k3, v.y, acc.y); acc.z = fmaf(k3, v.z, acc.z); acc.w = fmaf(k3, v.w, acc.w);
+        y[s] = acc;
+        if (warp > 0 && lane < 3) {  // what the previous warp's lanes 29..31 are missing
+          float4* h = s_halo + (warp * S + s) * 6;
+          if (lane == 0) {
+            h[0] = make_float4(fr[0], fr[1], fr[2], fr[3]);
+            h[1] = make_float4(fr[4], fr[5], fr[6], fr[7]);
+            h[2] = make_float4(fr[8], fr[9], fr[10], fr[11]);
+          } else if (lane == 1) {
+            h[3] = make_float4(fr[0], fr[1], fr[2], fr[3]);
+            h[4] = make_float4(fr[4], fr[5], fr[6], fr[7]);
+          } else {
+            h[5] = make_float4(fr[0], fr[1], fr[2], fr[3]);
+          }
+        }
+      };
+      band(std::integral_constant<int, 0>{});
+      band(std::integral_constant<int, 1>{});
+      band(std::integral_constant<int, 2>{});
+      band(std::integral_constant<int, 3>{});
+    }
+    __syncthreads();  // halo visible; the logits tile is dead from here on
+
+    // ---- phase B: finish the blocks that straddle a warp boundary, envelope, optional o_mb, modulation -> U
+    {
+      const int q = QY0 + tid;
+      const bool inside = (q >= 0) && (q < L) && (tid < T3_NF - 3);
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        float4 v = y[s];
+        if (warp < 3 && lane >= 29) {
+          const float4* h = s_halo + ((warp + 1) * S + s) * 6;
+          if (lane == 29) { add4(v, h[0]); }
+          else if (lane == 30) { add4(v, h[1]); add4(v, h[3]); }
+          else { add4(v, h[2]); add4(v, h[4]); add4(v, h[5]); }
+        }
+        if (!inside) {
+          v = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (PRECISE || q == 0 || q == L - 1) {
+          float e0 = 1.5f, e1 = 1.5f, e2 = 1.5f, e3 = 1.5f;
+          if (q == 0) { e0 -= win_sq(12); e1 -= win_sq(13); e2 -= win_sq(14); e3 -= win_sq(15); }
+          if (q == L - 1) { e0 -= win_sq(0); e1 -= win_sq(1); e2 -= win_sq(2); e3 -= win_sq(3); }
+          v.x /= e0; v.y /= e1; v.z /= e2; v.w /= e3;
+        } else {
+          const float inv = 0.66666666666666667f;
+          v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+        }
+        if (a.o_mb != nullptr && inside && tid >= 2 && tid < 2 + nq) {
+          if (a.variant == 1) {
+            *reinterpret_cast<float4*>(a.o_mb + ((size_t)b * S + s) * 4 * L + 4 * (size_t)q) = v;
+          } else {
+            float4* o = reinterpret_cast<float4*>(a.o_mb + ((size_t)b * S + s) * 16 * L + 16 * (size_t)q);
+            o[0] = make_float4(4.f * v.x, 0.f, 0.f, 0.f);
+            o[1] = make_float4(4.f * v.y, 0.f, 0.f, 0.f);
+            o[2] = make_float4(4.f * v.z, 0.f, 0.f, 0.f);
+            o[3] = make_float4(4.f * v.w, 0.f, 0.f, 0.f);
+          }
+        }
+        y[s] = v;
+      }
+      if (a.fast_pqmf) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float w = a.mod[m][c];
+            u.x = fmaf(w, y[c].x, u.x); u.y = fmaf(w, y[c].y, u.y);
+            u.z = fmaf(w, y[c].z, u.z); u.w = fmaf(w, y[c].w, u.w);
+          }
+          *reinterpret_cast<float4*>(s_u + m * T3_UP + 4 * tid) = u;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) *reinterpret_cast<float4*>(s_u + c * T3_UP + 4 * tid) = y[c];
+      }
+    }
+    __syncthreads();
+
+    // ---- phase C: synthesis FIR.  Thread = (hop blocks 2p, 2p+1; residues rh and rh+2); sub-band positions j = 8p + e.
+    {
+      const int p = 16 * warp + (lane >> 1), rh = lane & 1;
+      if (p >= 1 && 2 * p < 2 + nq) {
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int r = rh + 2 * h2;
+          float acc[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+          if (a.fast_pqmf) {
+            // taps d = -7..8 -> prototype tap 4d+31-r; odd index d reads U[7-r], even U[3-r]; window index 1+e+d of [8p-8, 8p+16)
+            float we[24], wo[24], gg[16];
+            const float4* pe = reinterpret_cast<const float4*>(s_u + (7 - r) * T3_UP + 8 * p - 8);
+            const float4* po = reinterpret_cast<const float4*>(s_u + (3 - r) * T3_UP + 8 * p - 8);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+              const float4 u = pe[i], v = po[i];
+              we[4 * i] = u.x; we[4 * i + 1] = u.y; we[4 * i + 2] = u.z; we[4 * i + 3] = u.w;
+              wo[4 * i] = v.x; wo[4 * i + 1] = v.y; wo[4 * i + 2] = v.z; wo[4 * i + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 gv = *reinterpret_cast<const float4*>(s_tab + r * 16 + 4 * i);
+              gg[4 * i] = gv.x; gg[4 * i + 1] = gv.y; gg[4 * i + 2] = gv.z; gg[4 * i + 3] = gv.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+#pragma unroll
+              for (int d = 0; d < 16; ++d)
+                acc[e] = fmaf(gg[d], (d & 1) ? we[1 + e + d] : wo[1 + e + d], acc[e]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float v[24], gg[16];
+              const float4* yp = reinterpret_cast<const float4*>(s_u + c * T3_UP + 8 * p - 8);
+#pragma unroll
+              for (int i = 0; i < 6; ++i) {
+                const float4 u = yp[i];
+                v[4 * i] = u.x; v[4 * i + 1] = u.y; v[4 * i + 2] = u.z; v[4 * i + 3] = u.w;
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 gv = *reinterpret_cast<const float4*>(s_tab + c * 64 + r * 16 + 4 * i);
+                gg[4 * i] = gv.x; gg[4 * i + 1] = gv.y; gg[4 * i + 2] = gv.z; gg[4 * i + 3] = gv.w;
+              }
+#pragma unroll
+              for (int d = 0; d < 16; ++d)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = fmaf(gg[d], v[1 + e + d], acc[e]);
+            }
+          }
+          // staging: row p = 32 floats (blocks 2p, 2p+1), 16-byte chunk e XOR-swizzled with p
+          float* o = s_out + 32 * p + r;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[4 * (e ^ (p & 7))] = acc[e];
+        }
+      }
+    }
+    __syncthreads();
+    // coalesced store of the owned outputs: hop blocks [2, 2+nq) of the staging buffer = 4*nq chunks of 16 bytes
+    {
+      float4* dst = reinterpret_cast<float4*>(a.wav + (size_t)b * 16 * L + 16 * (size_t)Q0);
+      const float4* src = reinterpret_cast<const float4*>(s_out);
+      for (int c = tid; c < 4 * nq; c += T3_NF) {
+        const int lc = c + 8, pr = lc >> 3, e = lc & 7;
+        dst[c] = src[8 * pr + (e ^ (pr & 7))];
+      }
+    }
+    g += nq;
+    if (g >= g_end) break;
+    cur = next_tile(g);
+    __syncthreads();  // staging (aliases the logits tile), U and halo are free again
+    if (tid == 0) issue_load(cur);
+  }
+}
+
+static cudaError_t launch_tail_mb3(const TailArgs& a, int precise, int num_sms, cudaStream_t st) {
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(tc_tensormap_encoder());
+  if (!enc) return cudaErrorNotSupported;
+  const int F = a.L + 1;
+  CUtensorMap tm32, tm8;
+  cuuint64_t dims[3] = {72, (cuuint64_t)F, (cuuint64_t)a.B};
+  cuuint64_t strides[2] = {288, (cuuint64_t)F * 288};
+  cuuint32_t estr[3] = {1, 1, 1};
+  cuuint32_t box32[3] = {32, (cuuint32_t)T3_NF, 1}, box8[3] = {8, (cuuint32_t)T3_NF, 1};
+  if (enc(&tm32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a.logits), dims, strides, box32, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return cudaErrorInvalidValue;
+  if (enc(&tm8, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a.logits), dims, strides, box8, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return cudaErrorInvalidValue;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(tail_mb3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_mb3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_mb3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_mb3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  const long long total = (long long)a.B * a.L;
+  long long ctas = (total + T3_NQ - 1) / T3_NQ;
+  if (ctas > 4LL * num_sms) ctas = 4LL * num_sms;
+  const bool emit = a.spec != nullptr;
+  if (precise) {
+    if (emit) tail_mb3_kernel<true, true><<<(int)ctas, T3_NF, T3_SMEM, st>>>(tm32, tm8, a);
+    else tail_mb3_kernel<true, false><<<(int)ctas, T3_NF, T3_SMEM, st>>>(tm32, tm8, a);
+  } else {
+    if (emit) tail_mb3_kernel<false, true><<<(int)ctas, T3_NF, T3_SMEM, st>>>(tm32, tm8, a);
+    else tail_mb3_kernel<false, false><<<(int)ctas, T3_NF, T3_SMEM, st>>>(tm32, tm8, a);
+  }
+  return cudaGetLastError();
+}
+
 static cudaError_t launch_tail_mb(const TailArgs& a, int precise, int num_sms, cudaStream_t st) {
   const int tiles = (a.L + T2_NQ - 1) / T2_NQ;
   const int total = a.B * tiles;
@@ -519,7 +888,9 @@ static cudaError_t launch_tail_t(const TailArgs& a, cudaStream_t st) {
 
 cudaError_t launch_tail(const TailArgs& a, int precise, int num_sms, cudaStream_t st) {
   if (a.variant == 0) return precise ? launch_tail_t<0, true>(a, st) : launch_tail_t<0, false>(a, st);
-  return launch_tail_mb(a, precise, num_sms, st);
+  static const int use_v2 = getenv("MBV_TAIL_V2") ? atoi(getenv("MBV_TAIL_V2")) : 0;  // A/B measurements only
+  if (use_v2) return launch_tail_mb(a, precise, num_sms, st);
+  return launch_tail_mb3(a, precise, num_sms, st);
 }
 
 }  // namespace mbv

@@ -242,6 +242,16 @@ class Engine:
         self._check(self.lib.mbv_profile_read(self._h, ms, cnt))
         return {k: (ms[i], cnt[i]) for i, k in enumerate(("conv", "tail", "other"))}
 
+    def profile_read_launches(self, cap=4096):
+        """-> [(description, ms)] per launch since the last read, in launch order."""
+        ms = (C.c_float * cap)()
+        stride = 56
+        desc = C.create_string_buffer(cap * stride)
+        n = C.c_int32()
+        self._check(self.lib.mbv_profile_read_launches(self._h, ms, desc, stride, cap, C.byref(n)))
+        raw = desc.raw
+        return [(raw[i * stride:(i + 1) * stride].split(b"\0", 1)[0].decode(), float(ms[i])) for i in range(n.value)]
+
     def last_launch_count(self):
         return int(self.lib.mbv_last_launch_count(self._h))
 
