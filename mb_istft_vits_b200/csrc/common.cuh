@@ -149,7 +149,7 @@ struct EpiParams {
   float scale;      // 1 / num_kernels for the final resblock-sum
   int sum_mode;     // EPI_RES: 0 none, 1 xs = x, 2 xs += x, 3 final: v = (xs + x) * scale, 4 final of a single resblock: v = x * scale
   int n_split;      // EPI_RS: width of the residual half (0 = last layer)
-  int ch_off;       // EPI_POST: first channel updated
+  int ch_off;       // EPI_POST: first channel updated; EPI_GATE: first channel of this layer's slot in the acts buffer
   int first;        // EPI_RS: first WN layer (skip accumulator is set, not added)
 };
 
@@ -254,7 +254,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int b, int ro
         const float s = 1.f / (1.f + __expf(-acc2[i]));
         tmp[i] = t * s;
       }
-      op_store_vec<Op, W>(reinterpret_cast<T*>(p.act[0]) + map_off, tmp);
+      op_store_vec<Op, W>(reinterpret_cast<T*>(p.act[0]) + map_off + p.ch_off, tmp);
     } break;
     case EPI_RS: {
       if (p.n_split > 0 && n0 < p.n_split) {
@@ -299,7 +299,8 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int b, int ro
 constexpr int kMaxPhases = 8;
 
 struct ConvArgs {
-  const void* x;      // operand activations [B][L_in][Cp_in]
+  const void* x;      // operand activations [B][L_in][x_ld]; the conv reads channels [0, Cp_in) of every row
+  int x_ld;           // channel pitch of x in elements (>= Cp_in)
   const void* w;      // packed weights [phase][tap][N_total][Cp_in] (operand type, K-major)
   int B;
   int L_in;           // rows per utterance of x

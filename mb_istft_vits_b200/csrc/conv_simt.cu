@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) { acc[i] = 0.f; acc2[i] = 0.f; }
 
-  const T* x = reinterpret_cast<const T*>(a.x) + (size_t)b * a.L_in * a.Cp_in;
+  const T* x = reinterpret_cast<const T*>(a.x) + (size_t)b * a.L_in * a.x_ld;
   const T* w = reinterpret_cast<const T*>(a.w) + (size_t)phase * a.taps * a.N_total * a.Cp_in;
 
   for (int tap = 0; tap < a.taps; ++tap) {
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
         const int rr = e / SIMT_KC, cc = e % SIMT_KC;
         const int t = t0 + rr + shift;
         float v = 0.f;
-        if (t >= 0 && t < a.L_in) v = op_load<Op>(x + (size_t)t * a.Cp_in + c0 + cc);
+        if (t >= 0 && t < a.L_in) v = op_load<Op>(x + (size_t)t * a.x_ld + c0 + cc);
         xs[cc][rr] = v;
       }
       for (int e = tid; e < SIMT_COLS * SIMT_KC; e += 256) {

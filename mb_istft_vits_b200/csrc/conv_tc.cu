@@ -221,6 +221,9 @@ struct TcRt {  // runtime scalars the kernel needs beyond ConvArgs
   int xchg_off;      // byte offset of the gate exchange buffer in dynamic smem
   int w_resident;    // all weight tiles of the (single) channel tile fit the ring: load them once per CTA
   int prefetch_res;  // issue an L2 prefetch of the tile's residual input (tmR) when its operand loads start
+  int rotate;        // two channel tiles, even grid: swap which one a CTA takes every round.  With a static round-robin
+                     // an even CTA would otherwise ALWAYS get channel tile 0; when the second tile is half padding
+                     // (192 = 128 + 64 rows: flow pre / res convs) its epilogue is half the work and half the CTAs idle.
   long long* dbg;    // MBV_TIMELINE=1: per-CTA clock stamps [cta][role 0..2][tile][2] (debug only)
 };
 
@@ -500,7 +503,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     uint32_t px = 0, pw = 0;
     for (int tile = blockIdx.x; tile < rt.total_tiles; tile += gridDim.x) {
       int rest = tile;
-      const int ct = rest % rt.c_tiles; rest /= rt.c_tiles;
+      int ct = rest % rt.c_tiles; rest /= rt.c_tiles;
+      if (rt.rotate) ct = (ct + tile / (int)gridDim.x) & 1;
       const int phase = rest % a.n_phases; rest /= a.n_phases;
       const int tt = rest % rt.t_tiles;
       const int b = rest / rt.t_tiles;
@@ -598,7 +602,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     auto decode = [&](int tile) {
       TileInfo ti;
       int rest = tile;
-      const int ct = rest % rt.c_tiles; rest /= rt.c_tiles;
+      int ct = rest % rt.c_tiles; rest /= rt.c_tiles;
+      if (rt.rotate) ct = (ct + tile / (int)gridDim.x) & 1;
       ti.phase = rest % a.n_phases; rest /= a.n_phases;
       const int tt = rest % rt.t_tiles;
       ti.b = rest / rt.t_tiles;
@@ -683,7 +688,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             using T = typename Op::T;
             const int nt = min(ti.t_lim - t_first, 32);
             const int ch = 64 * (ti.n >> 7) + (ti.n & 63);
-            T* dst = reinterpret_cast<T*>(p.act[0]) + ((size_t)ti.b * p.rows_out + t_first) * p.ld + ch;
+            T* dst = reinterpret_cast<T*>(p.act[0]) + ((size_t)ti.b * p.rows_out + t_first) * p.ld + p.ch_off + ch;
             const size_t step = LD > 0 ? (size_t)LD : (size_t)p.ld;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -786,7 +791,7 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
   const CUtensorMapDataType dt = prec == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   {
     cuuint64_t dims[3] = {(cuuint64_t)a.Cp_in, (cuuint64_t)a.L_in, (cuuint64_t)a.B};
-    cuuint64_t strides[2] = {(cuuint64_t)a.Cp_in * esize, (cuuint64_t)a.L_in * a.Cp_in * esize};
+    cuuint64_t strides[2] = {(cuuint64_t)a.x_ld * esize, (cuuint64_t)a.L_in * a.x_ld * esize};
     cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)plan->box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&plan->tmA, dt, 3, const_cast<void*>(a.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -852,7 +857,7 @@ static cudaError_t dispatch(const ConvArgs& a, const TcPlan& p, const TcRt& rt, 
 #define MBV_CASE(M, L) if (mode == M && ld == L) return launch_one<Op, M, L>(a, p, rt, st, set_attr);
   MBV_CASE(EPI_ACT, 128) MBV_CASE(EPI_ACT, 256) MBV_CASE(EPI_ACT, 192)
   MBV_CASE(EPI_RES, 128) MBV_CASE(EPI_RES, 256)
-  MBV_CASE(EPI_GATE, 192) MBV_CASE(EPI_RS, 192) MBV_CASE(EPI_POST, 192)
+  MBV_CASE(EPI_GATE, 768) MBV_CASE(EPI_RS, 192) MBV_CASE(EPI_POST, 192)
 #undef MBV_CASE
   switch (mode) {
     case EPI_ACT: return launch_one<Op, EPI_ACT, 0>(a, p, rt, st, set_attr);
@@ -868,7 +873,7 @@ cudaError_t tc_set_attributes() {
   ConvArgs a{};
   TcPlan p{};
   TcRt rt{};
-  const int lds[] = {0, 128, 192, 256};
+  const int lds[] = {0, 128, 192, 256, 768};
   for (int mode = EPI_ACT; mode <= EPI_POST; ++mode)
     for (int ld : lds) {
       cudaError_t e = dispatch<OpBF16>(a, p, rt, nullptr, true, mode, ld, 0);
@@ -914,6 +919,7 @@ cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStr
   rt.prefetch_res = p.prefetch_res;
   rt.xchg_off = p.xchg_off;
   rt.w_resident = p.w_resident;
+  rt.rotate = (p.c_tiles == 2 && (p.grid & 1) == 0 && p.total_tiles > p.grid) ? 1 : 0;
   cudaError_t e;
   if (prec == 2) e = dispatch<OpBF16>(a, p, rt, st, false, a.epi.mode, a.epi.ld, a.epi.res_half);
   else if (a.epi.res_half) e = cudaErrorInvalidValue;

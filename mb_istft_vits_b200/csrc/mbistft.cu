@@ -509,19 +509,65 @@ extern "C" int mbv_load_weights(mbv_handle* h, const mbv_tensor* tensors, int32_
         rc = pack_conv1d(h, m, pfx, 2 * H, H, K, 1, gmap, hin, true, 1, &h->fl_in[f][l]);
         if (rc) return rc;
         snprintf(pfx, sizeof(pfx), "flow.flows.%d.enc.res_skip_layers.%d", 2 * f, l);
-        // res/skip rows packed back to back at the activation pitch: [res Hp | skip Hp] (no 128-padding between the
-        // halves -- 2*192 = 384 rows = exactly three MMA tiles; epilogue warps are 32 channels, Hp is a multiple of 64)
-        std::vector<int> rsmap(2 * Hp, -1);
-        for (int o = 0; o < H; ++o) { rsmap[o] = o; rsmap[Hp + o] = H + o; }
-        if (l < NL - 1) rc = pack_conv1d(h, m, pfx, 2 * H, H, 1, 1, rsmap, hin, true, 0, &h->fl_rs[f][l]);
-        else rc = pack_conv1d(h, m, pfx, H, H, 1, 1, iota_pad(H, Hp), hin, true, 0, &h->fl_rs[f][l]);
-        if (rc) return rc;
+        // Only the RESIDUAL half of res_skip is a per-layer conv (rows [0, H) of the [2H, H, 1] weight).  The skip halves
+        // of all layers and `post` are linear in the gate outputs, so they collapse into ONE conv over the concatenated
+        // gate outputs (built below): the running skip sum never exists in memory and the last layer has no conv at all.
+        if (l < NL - 1) {
+          rc = pack_conv1d(h, m, pfx, 2 * H, H, 1, 1, iota_pad(H, Hp), hin, true, 0, &h->fl_rs[f][l]);
+          if (rc) return rc;
+          h->fl_rs[f][l].n_valid = H;
+        }
+        h->fl_rs[f][l].macs_per_row = (double)(l < NL - 1 ? 2 * H : H) * H;  // algorithmic MACs of the reference layer
       }
-      std::vector<int> pmap(half, -1);
-      for (int j = 0; j < half; ++j) pmap[j] = odd ? half - 1 - j : j;
-      snprintf(pfx, sizeof(pfx), "flow.flows.%d.post", 2 * f);
-      rc = pack_conv1d(h, m, pfx, half, H, 1, 1, pmap, hin, true, 0, &h->fl_post[f]);
-      if (rc) return rc;
+      // m = post(sum_l skip_l) = sum_l (W_post W_skip,l) acts_l + (W_post sum_l b_skip,l + b_post)      (modules.py:169-176,345)
+      {
+        const int64_t pws[3] = {half, H, 1}, pbs[1] = {half};
+        snprintf(pfx, sizeof(pfx), "flow.flows.%d.post", 2 * f);
+        const HostTensor* pw = find_tensor(h, m, std::string(pfx) + ".weight", 3, pws);
+        const HostTensor* pb = pw ? find_tensor(h, m, std::string(pfx) + ".bias", 1, pbs) : nullptr;
+        if (!pw || !pb) return MBV_ERR_WEIGHTS;
+        HostTensor fw, fb;
+        fw.shape = {half, (int64_t)NL * H, 1};
+        fw.data.assign((size_t)half * NL * H, 0.f);
+        fb.shape = {half};
+        fb.data.assign(half, 0.f);
+        std::vector<double> bsum(H, 0.0);
+        for (int l = 0; l < NL; ++l) {
+          const bool lastl = (l == NL - 1);
+          const int64_t ws[3] = {lastl ? H : 2 * H, H, 1}, bs[1] = {lastl ? H : 2 * H};
+          snprintf(pfx, sizeof(pfx), "flow.flows.%d.enc.res_skip_layers.%d", 2 * f, l);
+          const HostTensor* w = find_tensor(h, m, std::string(pfx) + ".weight", 3, ws);
+          const HostTensor* b = w ? find_tensor(h, m, std::string(pfx) + ".bias", 1, bs) : nullptr;
+          if (!w || !b) return MBV_ERR_WEIGHTS;
+          const int r0 = lastl ? 0 : H;  // first skip row
+          for (int j2 = 0; j2 < H; ++j2) bsum[j2] += b->data[r0 + j2];
+          std::vector<double> acc(H);
+          for (int o = 0; o < half; ++o) {
+            for (int cidx = 0; cidx < H; ++cidx) acc[cidx] = 0.0;
+            for (int j2 = 0; j2 < H; ++j2) {
+              const double pv = pw->data[(size_t)o * H + j2];
+              const float* wr = &w->data[(size_t)(r0 + j2) * H];
+              for (int cidx = 0; cidx < H; ++cidx) acc[cidx] += pv * (double)wr[cidx];
+            }
+            for (int cidx = 0; cidx < H; ++cidx) fw.data[(size_t)o * NL * H + (size_t)l * H + cidx] = (float)acc[cidx];
+          }
+        }
+        for (int o = 0; o < half; ++o) {
+          double acc = pb->data[o];
+          for (int j2 = 0; j2 < H; ++j2) acc += (double)pw->data[(size_t)o * H + j2] * bsum[j2];
+          fb.data[o] = (float)acc;
+        }
+        TensorMap fused;
+        fused["post_fused.weight"] = std::move(fw);
+        fused["post_fused.bias"] = std::move(fb);
+        std::vector<int> pmap(half, -1), fin((size_t)NL * Hp, -1);
+        for (int j2 = 0; j2 < half; ++j2) pmap[j2] = odd ? half - 1 - j2 : j2;
+        for (int l = 0; l < NL; ++l)
+          for (int cidx = 0; cidx < H; ++cidx) fin[(size_t)l * Hp + cidx] = l * H + cidx;
+        rc = pack_conv1d(h, fused, "post_fused", half, NL * H, 1, 1, pmap, fin, true, 0, &h->fl_post[f]);
+        if (rc) return rc;
+        h->fl_post[f].macs_per_row = (double)half * H;  // algorithmic MACs of the reference `post`
+      }
       if (gin) {
         snprintf(pfx, sizeof(pfx), "flow.flows.%d.enc.cond_layer", 2 * f);
         const int64_t ws[3] = {2 * H * NL, gin, 1}, bs[1] = {2 * H * NL};
@@ -570,7 +616,7 @@ struct DecBufs {
   float* cond;  // [n_stage][n_kernels][2][B][C]: (cond, bias2+cond) per resblock
 };
 struct FlowBufs {
-  float* z; void* zop; float* h; void* hop; void* acts; float* skip; void* hout; float* gcond;  // gcond [4][B][NL*2Hp]
+  float* z; void* zop; float* h; void* hop; void* acts; float* gcond;  // acts [B][T][NL*Hp]; gcond [4][B][NL*2Hp]
 };
 
 void layout_dec(mbv_handle* h, Arena& A, int B, int T, DecBufs* d) {
@@ -604,9 +650,7 @@ void layout_flow(mbv_handle* h, Arena& A, int B, int T, FlowBufs* f) {
   f->zop = A.take(nz * es);
   f->h = (float*)A.take(nh * 4);
   f->hop = A.take(nh * es);
-  f->acts = A.take(nh * es);
-  f->skip = (float*)A.take(nh * 4);
-  f->hout = A.take(nh * es);
+  f->acts = A.take(nh * h->cfg.flow_layers * es);
   f->gcond = (float*)A.take((size_t)4 * B * h->cfg.flow_layers * 2 * h->Hp * 4);
 }
 
@@ -639,11 +683,11 @@ struct ProfScope {
   }
 };
 
-int run_conv(Ctx& cx, const ConvLayer& L, const void* x, int B, int L_in, int L_out, const EpiParams& epi) {
+int run_conv(Ctx& cx, const ConvLayer& L, const void* x, int B, int L_in, int L_out, const EpiParams& epi, int x_ld = 0) {
   mbv_handle* h = cx.h;
   ConvArgs a;
   memset(&a, 0, sizeof(a));
-  a.x = x; a.w = L.w; a.B = B; a.L_in = L_in; a.L_out = L_out; a.Cp_in = L.Cp_in; a.N_total = L.N_total;
+  a.x = x; a.x_ld = x_ld > 0 ? x_ld : L.Cp_in; a.w = L.w; a.B = B; a.L_in = L_in; a.L_out = L_out; a.Cp_in = L.Cp_in; a.N_total = L.N_total;
   a.taps = L.taps; a.dil = L.dil; a.n_phases = L.n_phases; a.gate = L.gate;
   for (int i = 0; i < kMaxPhases; ++i) a.shift0[i] = L.shift0[i];
   a.epi = epi;
@@ -704,28 +748,28 @@ int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, co
       e.mask = mask; e.xout = f.h; e.act[0] = f.hop; e.n_act = 1;
       if ((rc = run_conv(cx, h->fl_pre[f_i], f.zop, B, T, T, e))) return rc;
     }
+    const int Ha = NL * Hp;  // channel pitch of the gate-output buffer: one Hp-wide slot per WN layer
     for (int l = 0; l < NL; ++l) {
-      {
-        EpiParams e = epi_base(EPI_GATE, Hp, T);
+      {  // acts_l = tanh(.) * sigmoid(.) of in_layer_l(h) [+ cond_l(g)]
+        EpiParams e = epi_base(EPI_GATE, Ha, T);
+        e.n_valid = Hp; e.ch_off = l * Hp;
         e.act[0] = f.acts; e.n_act = 1;
         if (gc) { e.add2 = gc + (size_t)l * 2 * Hp; e.add2_bs = NL * 2 * Hp; }
         if ((rc = run_conv(cx, h->fl_in[f_i][l], f.hop, B, T, T, e))) return rc;
       }
-      {
+      if (l < NL - 1) {  // h = (h + res_l(acts_l)) * mask; the skip halves are applied by the fused post conv below
         EpiParams e = epi_base(EPI_RS, Hp, T);
-        e.mask = mask; e.first = (l == 0); e.xs = f.skip;
-        if (l < NL - 1) { e.n_split = Hp; e.xin = f.h; e.xout = f.h; e.act[0] = f.hop; }
-        else { e.n_split = 0; e.act[0] = f.hout; }
-        e.n_act = 1;
-        if ((rc = run_conv(cx, h->fl_rs[f_i][l], f.acts, B, T, T, e))) return rc;
+        e.mask = mask; e.n_split = h->fl_rs[f_i][l].N_total; e.xin = f.h; e.xout = f.h; e.act[0] = f.hop; e.n_act = 1;
+        const char* ax = (const char*)f.acts + (size_t)l * Hp * h->esize;
+        if ((rc = run_conv(cx, h->fl_rs[f_i][l], ax, B, T, T, e, Ha))) return rc;
       }
     }
-    {  // x1 = (x1 - post(h) * mask) * mask
+    {  // x1 = (x1 - m * mask) * mask,  m = post(sum_l skip_l) as one conv over all gate outputs
       EpiParams e = epi_base(EPI_POST, h->Cz, T);
       e.mask = mask; e.xin = f.z; e.xout = f.z; e.act[0] = f.zop; e.n_act = 1;
       e.n_valid = h->Cz / 2;
       e.ch_off = ((4 - f_i) & 1) ? 0 : h->Cz / 2;
-      if ((rc = run_conv(cx, h->fl_post[f_i], f.hout, B, T, T, e))) return rc;
+      if ((rc = run_conv(cx, h->fl_post[f_i], f.acts, B, T, T, e))) return rc;
     }
   }
   if (z_out) {

@@ -69,27 +69,42 @@ __device__ __forceinline__ void head(float xm, float xp, float& mag, float& ph, 
   im = mag * s;
 }
 
+// Two fp32 values in one 64-bit register pair: sm_100 executes add / mul / fma on both halves with ONE instruction
+// (FADD2 / FMUL2 / FFMA2, IEEE round-to-nearest like the scalar forms).  The multi-band tail puts two sub-bands of the
+// same frame in the two halves, which halves the instruction count of everything between the head and the FIR.
+struct f2 { unsigned long long v; };
+__device__ __forceinline__ f2 mk2(float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ f2 dup2(float a) { return mk2(a, a); }
+__device__ __forceinline__ float lo2(f2 a) { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v)); (void)y; return x; }
+__device__ __forceinline__ float hi2(f2 a) { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v)); (void)x; return y; }
+__device__ __forceinline__ f2 operator+(f2 a, f2 b) { f2 r; asm("add.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f2 operator-(f2 a, f2 b) { f2 r; asm("sub.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f2 operator*(f2 a, f2 b) { f2 r; asm("mul.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f2 operator*(float a, f2 b) { return dup2(a) * b; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+
 // 16-point inverse real DFT (imaginary parts of bins 0 and 8 ignored, like torch.istft's irfft) times the periodic
 // Hann window / 16, written as an even/odd-bin split so that it costs ~100 flops instead of 16 x 15 MACs:
 //   x[n] = E[n] + O[n], x[n+8] = E[n] - O[n];  E = bins {0,4,8} (period 4) +- bins {2,6};  O = odd bins with the
-//   n <-> 8-n symmetry of cos / antisymmetry of sin.
-__device__ __forceinline__ void idft16_windowed(const float* re, const float* im, float* fr) {
+//   n <-> 8-n symmetry of cos / antisymmetry of sin.   T = float, or f2 for two sub-bands at once.
+template <typename T>
+__device__ __forceinline__ void idft16_windowed(const T* re, const T* im, T* fr) {
   constexpr float c1 = 0.92387953251128674f, c2 = 0.70710678118654752f, c3 = 0.38268343236508977f;
-  const float a0 = re[0] + re[8], a1 = re[0] - re[8];
-  const float A0 = a0 + 2.f * re[4], A1 = a1 - 2.f * im[4], A2 = a0 - 2.f * re[4], A3 = a1 + 2.f * im[4];
-  const float ims = im[2] + im[6];
-  const float B0 = 2.f * (re[2] + re[6]);
-  const float B1 = (2.f * c2) * ((re[2] - re[6]) - ims);
-  const float B2 = 2.f * (im[6] - im[2]);
-  const float B3 = (2.f * c2) * ((re[6] - re[2]) - ims);
-  float E[8] = {A0 + B0, A1 + B1, A2 + B2, A3 + B3, A0 - B0, A1 - B1, A2 - B2, A3 - B3};
-  const float r17 = re[1] - re[7], r35 = re[3] - re[5], i17 = im[1] + im[7], i35 = im[3] + im[5];
-  const float oc0 = (re[1] + re[7]) + (re[3] + re[5]);
-  const float oc1 = c1 * r17 + c3 * r35, os1 = c3 * i17 + c1 * i35;
-  const float oc2 = c2 * ((re[1] + re[7]) - (re[3] + re[5])), os2 = c2 * ((im[1] - im[7]) + (im[3] - im[5]));
-  const float oc3 = c3 * r17 - c1 * r35, os3 = c1 * i17 - c3 * i35;
-  const float os4 = (im[1] - im[3]) + (im[5] - im[7]);
-  float O[8];
+  const T a0 = re[0] + re[8], a1 = re[0] - re[8];
+  const T A0 = a0 + 2.f * re[4], A1 = a1 - 2.f * im[4], A2 = a0 - 2.f * re[4], A3 = a1 + 2.f * im[4];
+  const T ims = im[2] + im[6];
+  const T B0 = 2.f * (re[2] + re[6]);
+  const T B1 = (2.f * c2) * ((re[2] - re[6]) - ims);
+  const T B2 = 2.f * (im[6] - im[2]);
+  const T B3 = (2.f * c2) * ((re[6] - re[2]) - ims);
+  T E[8] = {A0 + B0, A1 + B1, A2 + B2, A3 + B3, A0 - B0, A1 - B1, A2 - B2, A3 - B3};
+  const T r17 = re[1] - re[7], r35 = re[3] - re[5], i17 = im[1] + im[7], i35 = im[3] + im[5];
+  const T oc0 = (re[1] + re[7]) + (re[3] + re[5]);
+  const T oc1 = c1 * r17 + c3 * r35, os1 = c3 * i17 + c1 * i35;
+  const T oc2 = c2 * ((re[1] + re[7]) - (re[3] + re[5])), os2 = c2 * ((im[1] - im[7]) + (im[3] - im[5]));
+  const T oc3 = c3 * r17 - c1 * r35, os3 = c1 * i17 - c3 * i35;
+  const T os4 = (im[1] - im[3]) + (im[5] - im[7]);
+  T O[8];
   O[0] = 2.f * oc0;
   O[1] = 2.f * (oc1 - os1); O[7] = -2.f * (oc1 + os1);
   O[2] = 2.f * (oc2 - os2); O[6] = -2.f * (oc2 + os2);
@@ -97,8 +112,8 @@ __device__ __forceinline__ void idft16_windowed(const float* re, const float* im
   O[4] = -2.f * os4;
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
-    fr[n] = (E[n] + O[n]) * kWin16[n];
-    fr[n + 8] = (E[n] - O[n]) * kWin16[n + 8];
+    fr[n] = kWin16[n] * (E[n] + O[n]);
+    fr[n + 8] = kWin16[n + 8] * (E[n] - O[n]);
   }
 }
 
@@ -552,8 +567,8 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
   constexpr int S = 4;
   extern __shared__ __align__(1024) uint8_t sm3[];
   float* s_u = reinterpret_cast<float*>(sm3 + T3_OFF_U);          // [8][T3_UP]  (generic filter: rows 0..3 = Y)
-  float4* s_halo = reinterpret_cast<float4*>(sm3 + T3_OFF_HALO);  // [warp][band][6]
-  float* s_tab = reinterpret_cast<float*>(sm3 + T3_OFF_TAB);      // fast: g2[4][16]; generic: coef[4][64]
+  f2* s_halo = reinterpret_cast<f2*>(sm3 + T3_OFF_HALO);           // [warp][band pair][6 parts][4 samples]
+  float* s_tab = reinterpret_cast<float*>(sm3 + T3_OFF_TAB);      // fast: (g2, g2)[4][16] duplicated pairs; generic: coef[4][64]
   float* s_out = reinterpret_cast<float*>(sm3);                   // [64 rows of 2 hop blocks][32], chunks XOR-swizzled
   const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(sm3 + T3_OFF_BAR));
   const uint32_t sm_base = static_cast<uint32_t>(__cvta_generic_to_shared(sm3));
@@ -590,7 +605,7 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
                  ::"r"(sm_base + 2 * T3_BOX01), "l"(reinterpret_cast<uint64_t>(&tm8)), "r"(bar), "r"(64), "r"(f0), "r"(t.b) : "memory");
   };
 
-  if (a.fast_pqmf) { if (tid < 64) s_tab[tid] = a.g2[tid >> 4][tid & 15]; }
+  if (a.fast_pqmf) { s_tab[tid] = a.g2[tid >> 5][(tid >> 1) & 15]; }
   else { s_tab[tid] = a.coef[tid >> 6][tid & 63]; s_tab[tid + 128] = a.coef[(tid + 128) >> 6][tid & 63]; }
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm32)) : "memory");
@@ -611,66 +626,75 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
     t2_mbar_wait(bar, parity);
     parity ^= 1;
 
-    // ---- phase A: head + inverse DFT + window (registers), overlap-add by shuffles.  Lane = frame F0 + tid = hop block QY0 + tid.
-    float4 y[S];
+    // ---- phase A: head + inverse DFT + window (registers), overlap-add by shuffles.  Lane = frame F0 + tid = hop block
+    // QY0 + tid.  Two sub-bands share every arithmetic instruction (f2): yp[P][i] = sample i of bands (2P, 2P+1).
+    f2 yp[2][4];
     {
       const int f = F0 + tid;
-      // Frames outside the utterance read TMA's zero fill (finite head values) and are zeroed after the transform, so the
-      // whole band body is branch-free (v3.0 spent 12 % of its instructions and 40 % of its stall samples on BSSY/BRA/BSYNC).
+      // Frames outside the utterance read TMA's zero fill (finite head values) and get magnitude 0, so the band body is
+      // branch-free (v3.0 spent 12 % of its instructions and 40 % of its stall samples on BSSY/BRA/BSYNC).
       const bool live = (f >= 0) && (f < F);
       const bool emit = EMIT && live && (f >= Q0) && (f < Q0 + nq || (last_tile && f == L));
-      auto band = [&](auto s_tag) {
-        constexpr int s = decltype(s_tag)::value;
-        float fr[16];
-        {
-          constexpr int f0 = 18 * s, c0 = f0 / 4, c1 = (f0 + 17) / 4;
-          float buf[(c1 - c0 + 1) * 4];
-          T3Load<c0, c1 - c0 + 1>::run(sm3, tid, buf);
-          const float* x = buf + (f0 - 4 * c0);
-          float re[9], im[9], mag[9], ph[9];
+      const f2 keep = dup2(live ? 1.f : 0.f);
+      const f2 k1 = dup2(lane < 31 ? 1.f : 0.f), k2 = dup2(lane < 30 ? 1.f : 0.f), k3 = dup2(lane < 29 ? 1.f : 0.f);
+      auto band_pair = [&](auto p_tag) {
+        constexpr int P = decltype(p_tag)::value, s0 = 2 * P;
+        // floats [36P, 36P + 36) of the frame row = chunks 9P .. 9P+8: band s0 then band s0 + 1
+        float x[36];
+        T3Load<9 * P, 9>::run(sm3, tid, x);
+        f2 re[9], im[9];
 #pragma unroll
-          for (int k = 0; k < 9; ++k) head<PRECISE>(x[k], x[9 + k], mag[k], ph[k], re[k], im[k]);
+        for (int k = 0; k < 9; ++k) {
+          float mag0, mag1, sn0, sn1;
+          if (PRECISE) {
+            mag0 = expf(x[k]); mag1 = expf(x[18 + k]);
+            sn0 = sinf(x[9 + k]); sn1 = sinf(x[27 + k]);
+          } else {
+            mag0 = ptx_ex2(x[k] * 1.4426950408889634f); mag1 = ptx_ex2(x[18 + k] * 1.4426950408889634f);
+            sn0 = ptx_sin(x[9 + k]); sn1 = ptx_sin(x[27 + k]);
+          }
+          const f2 ph = 3.14159265358979323846f * mk2(sn0, sn1);   // phase = pi * sin(x)  (models.py:369)
+          const float ph0 = lo2(ph), ph1 = hi2(ph);
+          float s0v, c0v, s1v, c1v;
+          if (PRECISE) { sincosf(ph0, &s0v, &c0v); sincosf(ph1, &s1v, &c1v); }
+          else { s0v = ptx_sin(ph0); c0v = ptx_cos(ph0); s1v = ptx_sin(ph1); c1v = ptx_cos(ph1); }
           if (EMIT) {
             if (emit) {
-              float* sp = a.spec + ((size_t)b * S + s) * 9 * F + f;
-              float* pp = a.phase + ((size_t)b * S + s) * 9 * F + f;
-#pragma unroll
-              for (int k = 0; k < 9; ++k) { sp[(size_t)k * F] = mag[k]; pp[(size_t)k * F] = ph[k]; }
+              const size_t o = (((size_t)b * S + s0) * 9 + k) * F + f;
+              a.spec[o] = mag0; a.phase[o] = ph0;
+              a.spec[o + (size_t)9 * F] = mag1; a.phase[o + (size_t)9 * F] = ph1;
             }
           }
-          idft16_windowed(re, im, fr);
-          const float keep = live ? 1.f : 0.f;
-#pragma unroll
-          for (int n = 0; n < 16; ++n) fr[n] *= keep;
+          const f2 mag = keep * mk2(mag0, mag1);
+          re[k] = mag * mk2(c0v, c1v);
+          im[k] = mag * mk2(s0v, s1v);
         }
-        // hop block of this lane = part 3 of its own frame + part 2 / 1 / 0 of the next three frames (same order as v2)
-        float4 acc = make_float4(fr[12], fr[13], fr[14], fr[15]);
-        const float k1 = lane < 31 ? 1.f : 0.f, k2 = lane < 30 ? 1.f : 0.f, k3 = lane < 29 ? 1.f : 0.f;
-        float4 v = shfl_down4(fr + 8, 1);
-        acc.x = fmaf(k1, v.x, acc.x); acc.y = fmaf(k1, v.y, acc.y); acc.z = fmaf(k1, v.z, acc.z); acc.w = fmaf(k1, v.w, acc.w);
-        v = shfl_down4(fr + 4, 2);
-        acc.x = fmaf(k2, v.x, acc.x); acc.y = fmaf(k2, v.y, acc.y); acc.z = fmaf(k2, v.z, acc.z); acc.w = fmaf(k2, v.w, acc.w);
-        v = shfl_down4(fr, 3);
-        acc.x = fmaf(k3, v.x, acc.x); acc.y = fmaf(k3, v.y, acc.y); acc.z = fmaf(k3, v.z, acc.z); acc.w = fmaf(k3, v.w, acc.w);
-        y[s] = acc;
-        if (warp > 0 && lane < 3) {  // what the previous warp's lanes 29..31 are missing
-          float4* h = s_halo + (warp * S + s) * 6;
-          if (lane == 0) {
-            h[0] = make_float4(fr[0], fr[1], fr[2], fr[3]);
-            h[1] = make_float4(fr[4], fr[5], fr[6], fr[7]);
-            h[2] = make_float4(fr[8], fr[9], fr[10], fr[11]);
-          } else if (lane == 1) {
-            h[3] = make_float4(fr[0], fr[1], fr[2], fr[3]);
-            h[4] = make_float4(fr[4], fr[5], fr[6], fr[7]);
-          } else {
-            h[5] = make_float4(fr[0], fr[1], fr[2], fr[3]);
-          }
+        f2 fr[16];
+        idft16_windowed<f2>(re, im, fr);
+        // hop block of this lane = part 3 of its own frame + part 2 / 1 / 0 of the next three frames
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          f2 acc = fr[12 + i], v;
+          v.v = __shfl_down_sync(0xffffffffu, fr[8 + i].v, 1); acc = fma2(k1, v, acc);
+          v.v = __shfl_down_sync(0xffffffffu, fr[4 + i].v, 2); acc = fma2(k2, v, acc);
+          v.v = __shfl_down_sync(0xffffffffu, fr[i].v, 3);     acc = fma2(k3, v, acc);
+          yp[P][i] = acc;
+        }
+        if (warp > 0 && lane < 3) {  // what the previous warp's lanes 29..31 are missing: [lane 0: p0 p1 p2 | lane 1: p0 p1 | lane 2: p0]
+          f2* h = s_halo + ((warp * 2 + P) * 6) * 4;
+          const int first = lane == 0 ? 0 : (lane == 1 ? 3 : 5), n = 3 - lane;
+          for (int part = 0; part < n; ++part)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              f2 v = fr[i];
+              if (part == 1) v = fr[4 + i];
+              if (part == 2) v = fr[8 + i];
+              h[(first + part) * 4 + i] = v;
+            }
         }
       };
-      band(std::integral_constant<int, 0>{});
-      band(std::integral_constant<int, 1>{});
-      band(std::integral_constant<int, 2>{});
-      band(std::integral_constant<int, 3>{});
+      band_pair(std::integral_constant<int, 0>{});
+      band_pair(std::integral_constant<int, 1>{});
     }
     __syncthreads();  // halo visible; the logits tile is dead from here on
 
@@ -679,53 +703,72 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
       const int q = QY0 + tid;
       const bool inside = (q >= 0) && (q < L) && (tid < T3_NF - 3);
 #pragma unroll
-      for (int s = 0; s < S; ++s) {
-        float4 v = y[s];
+      for (int P = 0; P < 2; ++P) {
         if (warp < 3 && lane >= 29) {
-          const float4* h = s_halo + ((warp + 1) * S + s) * 6;
-          if (lane == 29) { add4(v, h[0]); }
-          else if (lane == 30) { add4(v, h[1]); add4(v, h[3]); }
-          else { add4(v, h[2]); add4(v, h[4]); add4(v, h[5]); }
+          const f2* h = s_halo + (((warp + 1) * 2 + P) * 6) * 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            f2 v = yp[P][i];
+            if (lane == 29) { v = v + h[0 * 4 + i]; }
+            else if (lane == 30) { v = v + h[1 * 4 + i]; v = v + h[3 * 4 + i]; }
+            else { v = v + h[2 * 4 + i]; v = v + h[4 * 4 + i]; v = v + h[5 * 4 + i]; }
+            yp[P][i] = v;
+          }
         }
         if (!inside) {
-          v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) yp[P][i] = dup2(0.f);
         } else if (PRECISE || q == 0 || q == L - 1) {
-          float e0 = 1.5f, e1 = 1.5f, e2 = 1.5f, e3 = 1.5f;
-          if (q == 0) { e0 -= win_sq(12); e1 -= win_sq(13); e2 -= win_sq(14); e3 -= win_sq(15); }
-          if (q == L - 1) { e0 -= win_sq(0); e1 -= win_sq(1); e2 -= win_sq(2); e3 -= win_sq(3); }
-          v.x /= e0; v.y /= e1; v.z /= e2; v.w /= e3;
-        } else {
-          const float inv = 0.66666666666666667f;
-          v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+          float e[4] = {1.5f, 1.5f, 1.5f, 1.5f};
+          if (q == 0) { e[0] -= win_sq(12); e[1] -= win_sq(13); e[2] -= win_sq(14); e[3] -= win_sq(15); }
+          if (q == L - 1) { e[0] -= win_sq(0); e[1] -= win_sq(1); e[2] -= win_sq(2); e[3] -= win_sq(3); }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) yp[P][i] = mk2(lo2(yp[P][i]) / e[i], hi2(yp[P][i]) / e[i]);
+        } else {  // steady-state envelope 1.5: multiply by the reciprocal (<= 1 ulp from the division)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) yp[P][i] = 0.66666666666666667f * yp[P][i];
         }
         if (a.o_mb != nullptr && inside && tid >= 2 && tid < 2 + nq) {
-          if (a.variant == 1) {
-            *reinterpret_cast<float4*>(a.o_mb + ((size_t)b * S + s) * 4 * L + 4 * (size_t)q) = v;
-          } else {
-            float4* o = reinterpret_cast<float4*>(a.o_mb + ((size_t)b * S + s) * 16 * L + 16 * (size_t)q);
-            o[0] = make_float4(4.f * v.x, 0.f, 0.f, 0.f);
-            o[1] = make_float4(4.f * v.y, 0.f, 0.f, 0.f);
-            o[2] = make_float4(4.f * v.z, 0.f, 0.f, 0.f);
-            o[3] = make_float4(4.f * v.w, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {
+            const int s = 2 * P + hb;
+            const float4 v = hb ? make_float4(hi2(yp[P][0]), hi2(yp[P][1]), hi2(yp[P][2]), hi2(yp[P][3]))
+                                : make_float4(lo2(yp[P][0]), lo2(yp[P][1]), lo2(yp[P][2]), lo2(yp[P][3]));
+            if (a.variant == 1) {
+              *reinterpret_cast<float4*>(a.o_mb + ((size_t)b * S + s) * 4 * L + 4 * (size_t)q) = v;
+            } else {
+              float4* o = reinterpret_cast<float4*>(a.o_mb + ((size_t)b * S + s) * 16 * L + 16 * (size_t)q);
+              o[0] = make_float4(4.f * v.x, 0.f, 0.f, 0.f);
+              o[1] = make_float4(4.f * v.y, 0.f, 0.f, 0.f);
+              o[2] = make_float4(4.f * v.z, 0.f, 0.f, 0.f);
+              o[3] = make_float4(4.f * v.w, 0.f, 0.f, 0.f);
+            }
           }
         }
-        y[s] = v;
       }
       if (a.fast_pqmf) {
+        // U[m][j] = sum_c mod[m][c] y_c[j]: (mod[m][0], mod[m][1]) x (y_0, y_1) + (mod[m][2], mod[m][3]) x (y_2, y_3), halves added
+        const unsigned long long* modp = reinterpret_cast<const unsigned long long*>(&a.mod[0][0]);
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-          float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+          f2 m01, m23;
+          m01.v = modp[2 * m]; m23.v = modp[2 * m + 1];
+          float u[4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float w = a.mod[m][c];
-            u.x = fmaf(w, y[c].x, u.x); u.y = fmaf(w, y[c].y, u.y);
-            u.z = fmaf(w, y[c].z, u.z); u.w = fmaf(w, y[c].w, u.w);
+          for (int i = 0; i < 4; ++i) {
+            const f2 t = fma2(m23, yp[1][i], m01 * yp[0][i]);
+            u[i] = lo2(t) + hi2(t);
           }
-          *reinterpret_cast<float4*>(s_u + m * T3_UP + 4 * tid) = u;
+          *reinterpret_cast<float4*>(s_u + m * T3_UP + 4 * tid) = make_float4(u[0], u[1], u[2], u[3]);
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) *reinterpret_cast<float4*>(s_u + c * T3_UP + 4 * tid) = y[c];
+        for (int c = 0; c < 4; ++c) {
+          const int P = c >> 1;
+          const float4 v = (c & 1) ? make_float4(hi2(yp[P][0]), hi2(yp[P][1]), hi2(yp[P][2]), hi2(yp[P][3]))
+                                   : make_float4(lo2(yp[P][0]), lo2(yp[P][1]), lo2(yp[P][2]), lo2(yp[P][3]));
+          *reinterpret_cast<float4*>(s_u + c * T3_UP + 4 * tid) = v;
+        }
       }
     }
     __syncthreads();
@@ -738,37 +781,51 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
         for (int h2 = 0; h2 < 2; ++h2) {
           const int r = rh + 2 * h2;
           float acc[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = 0.f;
           if (a.fast_pqmf) {
-            // taps d = -7..8 -> prototype tap 4d+31-r; odd index d reads U[7-r], even U[3-r]; window index 1+e+d of [8p-8, 8p+16)
-            float we[24], wo[24], gg[16];
-            const float4* pe = reinterpret_cast<const float4*>(s_u + (7 - r) * T3_UP + 8 * p - 8);
-            const float4* po = reinterpret_cast<const float4*>(s_u + (3 - r) * T3_UP + 8 * p - 8);
+            // taps d = -7..8 -> prototype tap 4d+31-r; odd index d reads U[7-r], even U[3-r]; window index 1+e+d of
+            // [8p-8, 8p+16).  Outputs are paired so that every FFMA2 reads an ALIGNED pair of the window: odd taps
+            // accumulate outputs (0,1)(2,3)(4,5)(6,7), even taps (-1,0)(1,2)(3,4)(5,6)(7,8) (two unused), summed at the end.
+            f2 we[12], wo[12];
+            const ulonglong2* pe = reinterpret_cast<const ulonglong2*>(s_u + (7 - r) * T3_UP + 8 * p - 8);
+            const ulonglong2* po = reinterpret_cast<const ulonglong2*>(s_u + (3 - r) * T3_UP + 8 * p - 8);
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
-              const float4 u = pe[i], v = po[i];
-              we[4 * i] = u.x; we[4 * i + 1] = u.y; we[4 * i + 2] = u.z; we[4 * i + 3] = u.w;
-              wo[4 * i] = v.x; wo[4 * i + 1] = v.y; wo[4 * i + 2] = v.z; wo[4 * i + 3] = v.w;
+              const ulonglong2 u = pe[i], v = po[i];
+              we[2 * i].v = u.x; we[2 * i + 1].v = u.y;
+              wo[2 * i].v = v.x; wo[2 * i + 1].v = v.y;
+            }
+            const ulonglong2* gp = reinterpret_cast<const ulonglong2*>(s_tab) + r * 8;  // (g_d, g_d) pairs, two taps per load
+            f2 accA[4], accB[5];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) accA[i] = dup2(0.f);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) accB[i] = dup2(0.f);
+#pragma unroll
+            for (int dd = 0; dd < 8; ++dd) {
+              const ulonglong2 gv = gp[dd];
+              f2 ge, go;
+              ge.v = gv.x;  // tap index d = 2 dd   (even): window index 2j + d for the output pair (2j-1, 2j)
+              go.v = gv.y;  // tap index d = 2 dd+1 (odd):  window index 2j + d + 1 for the output pair (2j, 2j+1)
+#pragma unroll
+              for (int jj = 0; jj < 5; ++jj) accB[jj] = fma2(ge, wo[jj + dd], accB[jj]);
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) accA[jj] = fma2(go, we[jj + dd + 1], accA[jj]);
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 gv = *reinterpret_cast<const float4*>(s_tab + r * 16 + 4 * i);
-              gg[4 * i] = gv.x; gg[4 * i + 1] = gv.y; gg[4 * i + 2] = gv.z; gg[4 * i + 3] = gv.w;
+            for (int jj = 0; jj < 4; ++jj) {
+              acc[2 * jj] = lo2(accA[jj]) + hi2(accB[jj]);
+              acc[2 * jj + 1] = hi2(accA[jj]) + lo2(accB[jj + 1]);
             }
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-#pragma unroll
-              for (int d = 0; d < 16; ++d)
-                acc[e] = fmaf(gg[d], (d & 1) ? we[1 + e + d] : wo[1 + e + d], acc[e]);
           } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = 0.f;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               float v[24], gg[16];
-              const float4* yp = reinterpret_cast<const float4*>(s_u + c * T3_UP + 8 * p - 8);
+              const float4* yq = reinterpret_cast<const float4*>(s_u + c * T3_UP + 8 * p - 8);
 #pragma unroll
               for (int i = 0; i < 6; ++i) {
-                const float4 u = yp[i];
+                const float4 u = yq[i];
                 v[4 * i] = u.x; v[4 * i + 1] = u.y; v[4 * i + 2] = u.z; v[4 * i + 3] = u.w;
               }
 #pragma unroll
