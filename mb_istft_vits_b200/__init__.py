@@ -16,4 +16,7 @@ def __getattr__(name):
     if name in ("NativeFlow", "NativeDecoder", "patch_synthesizer"):
         from . import modules
         return getattr(modules, name)
+    if name == "HostStream":
+        from . import pipeline
+        return pipeline.HostStream
     raise AttributeError(name)

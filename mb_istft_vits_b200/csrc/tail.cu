@@ -569,7 +569,7 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
   float* s_u = reinterpret_cast<float*>(sm3 + T3_OFF_U);          // [8][T3_UP]  (generic filter: rows 0..3 = Y)
   f2* s_halo = reinterpret_cast<f2*>(sm3 + T3_OFF_HALO);           // [warp][band pair][6 parts][4 samples]
   float* s_tab = reinterpret_cast<float*>(sm3 + T3_OFF_TAB);      // fast: (g2, g2)[4][16] duplicated pairs; generic: coef[4][64]
-  float* s_out = reinterpret_cast<float*>(sm3);                   // [64 rows of 2 hop blocks][32], chunks XOR-swizzled
+  float* s_out = s_u;  // output staging [64 rows of 2 hop blocks][32], chunks XOR-swizzled; reuses U once the FIR has read it
   const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(sm3 + T3_OFF_BAR));
   const uint32_t sm_base = static_cast<uint32_t>(__cvta_generic_to_shared(sm3));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -696,7 +696,14 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
       band_pair(std::integral_constant<int, 0>{});
       band_pair(std::integral_constant<int, 1>{});
     }
-    __syncthreads();  // halo visible; the logits tile is dead from here on
+    __syncthreads();  // halo visible; the logits tile is dead from here on: refill it with the next tile while B/C run
+    const long long g_next = g + nq;
+    const bool has_next = g_next < g_end;
+    Tile nxt = cur;
+    if (has_next) {
+      nxt = next_tile(g_next);
+      if (tid == 0) issue_load(nxt);
+    }
 
     // ---- phase B: finish the blocks that straddle a warp boundary, envelope, optional o_mb, modulation -> U
     {
@@ -776,11 +783,13 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
     // ---- phase C: synthesis FIR.  Thread = (hop blocks 2p, 2p+1; residues rh and rh+2); sub-band positions j = 8p + e.
     {
       const int p = 16 * warp + (lane >> 1), rh = lane & 1;
-      if (p >= 1 && 2 * p < 2 + nq) {
+      const bool fir_on = (p >= 1 && 2 * p < 2 + nq);
+      float accs[2][8];
+      if (fir_on) {
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
           const int r = rh + 2 * h2;
-          float acc[8];
+          float* acc = accs[h2];
           if (a.fast_pqmf) {
             // taps d = -7..8 -> prototype tap 4d+31-r; odd index d reads U[7-r], even U[3-r]; window index 1+e+d of
             // [8p-8, 8p+16).  Outputs are paired so that every FFMA2 reads an ALIGNED pair of the window: odd taps
@@ -839,10 +848,16 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
                 for (int e = 0; e < 8; ++e) acc[e] = fmaf(gg[d], v[1 + e + d], acc[e]);
             }
           }
-          // staging: row p = 32 floats (blocks 2p, 2p+1), 16-byte chunk e XOR-swizzled with p
-          float* o = s_out + 32 * p + r;
+        }
+      }
+      __syncthreads();  // every FIR window has been read: U becomes the output staging buffer
+      if (fir_on) {
+        // row p = 32 floats (blocks 2p, 2p+1), 16-byte chunk e XOR-swizzled with p
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[4 * (e ^ (p & 7))] = acc[e];
+        for (int h2 = 0; h2 < 2; ++h2) {
+          float* o = s_out + 32 * p + rh + 2 * h2;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[4 * (e ^ (p & 7))] = accs[h2][e];
         }
       }
     }
@@ -856,11 +871,9 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
         dst[c] = src[8 * pr + (e ^ (pr & 7))];
       }
     }
-    g += nq;
-    if (g >= g_end) break;
-    cur = next_tile(g);
-    __syncthreads();  // staging (aliases the logits tile), U and halo are free again
-    if (tid == 0) issue_load(cur);
+    if (!has_next) break;
+    g = g_next;
+    cur = nxt;  // (the barrier after the next phase A orders these staging reads before U is rewritten)
   }
 }
 
