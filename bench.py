@@ -426,7 +426,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["fp16", "bf16", "tf32", "fp32"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--frames", type=int, default=T_FRAMES)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")

@@ -46,7 +46,12 @@ typedef enum { MBV_VARIANT_ISTFT = 0, MBV_VARIANT_MB = 1, MBV_VARIANT_MS = 2 } m
 typedef enum {
   MBV_PREC_FP32 = 0, /* CUDA-core fp32 FMA: exact-order-independent reference path, slow */
   MBV_PREC_TF32 = 1, /* tcgen05 kind::tf32, operands rounded to tf32 (RNE), fp32 accumulate */
-  MBV_PREC_BF16 = 2  /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate */
+  MBV_PREC_BF16 = 2, /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate */
+  MBV_PREC_FP16 = 3  /* tcgen05 kind::f16 (fp16 operands, saturating stores), fp32 accumulate.  Same tensor-core rate
+                      * as bf16 with three more mantissa bits, range +-65504.  Because every 16-bit activation is then
+                      * an fp16 tensor, the ResBlock / WaveNet residual streams are not stored separately: the residual
+                      * add reads the fp16 operand tensor lrelu(x) that fed the block and inverts the leaky-relu
+                      * ("single stream"), which removes a quarter of the ResBlock HBM traffic. */
 } mbv_precision;
 
 #define MBV_MAX_UPS 4

@@ -18,6 +18,7 @@ namespace mbv {
 struct OpF32 { using T = float; static constexpr int kPrec = 0; };
 struct OpTF32 { using T = float; static constexpr int kPrec = 1; };
 struct OpBF16 { using T = __nv_bfloat16; static constexpr int kPrec = 2; };
+struct OpF16 { using T = __half; static constexpr int kPrec = 3; };   // kind::f16 with fp16 operands (saturating stores)
 
 __device__ __forceinline__ float round_tf32(float x) {
   uint32_t r;
@@ -29,14 +30,32 @@ template <typename Op> __device__ __forceinline__ float op_round(float x);
 template <> __device__ __forceinline__ float op_round<OpF32>(float x) { return x; }
 template <> __device__ __forceinline__ float op_round<OpTF32>(float x) { return round_tf32(x); }
 template <> __device__ __forceinline__ float op_round<OpBF16>(float x) { return x; }
+template <> __device__ __forceinline__ float op_round<OpF16>(float x) { return x; }
 
 template <typename Op> __device__ __forceinline__ float op_load(const typename Op::T* p) { return *p; }
 template <> __device__ __forceinline__ float op_load<OpBF16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <> __device__ __forceinline__ float op_load<OpF16>(const __half* p) { return __half2float(*p); }
+
+// fp16 stores saturate: one F2FP.SATFINITE, +-inf / overflow clamp to +-65504
+__device__ __forceinline__ __half to_half_sat(float x) {
+  unsigned short h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  return __ushort_as_half(h);
+}
 
 // store W (multiple of 8) consecutive operand elements, 16-byte vectorised
 template <typename Op, int W>
 __device__ __forceinline__ void op_store_vec(typename Op::T* dst, const float* v) {
-  if constexpr (Op::kPrec == 2) {
+  if constexpr (Op::kPrec == 3) {
+#pragma unroll
+    for (int i = 0; i < W; i += 8) {
+      uint4 u;
+      __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h2[j] = __halves2half2(to_half_sat(v[i + 2 * j]), to_half_sat(v[i + 2 * j + 1]));
+      *reinterpret_cast<uint4*>(dst + i) = u;
+    }
+  } else if constexpr (Op::kPrec == 2) {
 #pragma unroll
     for (int i = 0; i < W; i += 8) {
       __nv_bfloat162 a = __floats2bfloat162_rn(v[i + 0], v[i + 1]);
@@ -75,12 +94,7 @@ template <int W> __device__ __forceinline__ void f32_store_vec(float* dst, const
 
 __device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
 
-// fp16 residual stream: saturating round-to-nearest store, widening load
-__device__ __forceinline__ __half to_half_sat(float x) {  // one F2FP.SATFINITE: +-inf / overflow clamp to +-65504
-  unsigned short h;
-  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
-  return __ushort_as_half(h);
-}
+// fp16 residual stream: saturating round-to-nearest store (to_half_sat above), widening load
 template <int W> __device__ __forceinline__ void res_load_vec(float* v, const void* base, size_t off, int half) {
   if (half) {
     const __half* p = reinterpret_cast<const __half*>(base) + off;
@@ -141,7 +155,9 @@ struct EpiParams {
   const void* xin;
   void* xout;                         // residual / plain output
   void* xs;                           // resblock running sum
-  int res_half;
+  int res_half;                       // 0 fp32, 1 plain fp16, 2 single stream: xin is an fp16 operand tensor holding
+                                      // lrelu(x) (inverted with inv_slope on load), no separate residual output
+  float inv_slope;
   void* act[3];
   const float* act_add[3]; int act_add_bs;  // per-utterance addend before lrelu (ResBlock cond(g))
   int n_act;

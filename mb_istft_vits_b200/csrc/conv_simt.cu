@@ -102,6 +102,7 @@ cudaError_t launch_conv_simt(int prec, const ConvArgs& a, cudaStream_t st) {
   switch (prec) {
     case 0: return launch_simt<OpF32>(a, st);
     case 1: return launch_simt<OpTF32>(a, st);
+    case 3: return launch_simt<OpF16>(a, st);
     default: return launch_simt<OpBF16>(a, st);
   }
 }

@@ -184,15 +184,19 @@ __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)kDes
 
 template <typename Op> __device__ __forceinline__ void op_store1(typename Op::T* p, float v) { *p = op_round<Op>(v); }
 template <> __device__ __forceinline__ void op_store1<OpBF16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ void op_store1<OpF16>(__half* p, float v) { *p = to_half_sat(v); }
 
-// residual-stream element: fp32 or (RH) saturating fp16
-template <bool RH> struct ResT { using T = float; };
-template <> struct ResT<true> { using T = __half; };
-template <bool RH> __device__ __forceinline__ float res_ld(const typename ResT<RH>::T* p) {
-  if constexpr (RH) return __half2float(*p); else return *p;
+// residual-stream element.  RH = 0: fp32;  1: saturating fp16;  2: "single stream" (fp16 operands only): the residual
+// input IS the fp16 operand tensor lrelu(x) that fed the block's first conv -- leaky-relu is invertible, x = v >= 0 ? v :
+// v / slope -- and the only output is the next operand tensor, so a ResBlock conv pair moves one 2-byte tensor in and one
+// out instead of two and two.
+template <int RH> struct ResT { using T = __half; };
+template <> struct ResT<0> { using T = float; };
+template <int RH> __device__ __forceinline__ float res_ld(const typename ResT<RH>::T* p) {
+  if constexpr (RH != 0) return __half2float(*p); else return *p;
 }
-template <bool RH> __device__ __forceinline__ void res_st(typename ResT<RH>::T* p, float v) {
-  if constexpr (RH) *p = to_half_sat(v); else *p = v;
+template <int RH> __device__ __forceinline__ void res_st(typename ResT<RH>::T* p, float v) {
+  if constexpr (RH != 0) *p = to_half_sat(v); else *p = v;
 }
 
 // MUFU.TANH: one instruction, max abs error 2^-11 -- below the 2^-9 rounding the bf16 operand copy applies anyway.
@@ -208,6 +212,8 @@ __device__ __forceinline__ float fast_tanh(float x) {
 
 template <> __device__ __forceinline__ float gate_tanh<OpBF16>(float x) { return mufu_tanh(x); }
 template <> __device__ __forceinline__ float gate_sigmoid<OpBF16>(float x) { return fmaf(mufu_tanh(0.5f * x), 0.5f, 0.5f); }
+template <> __device__ __forceinline__ float gate_tanh<OpF16>(float x) { return mufu_tanh(x); }
+template <> __device__ __forceinline__ float gate_sigmoid<OpF16>(float x) { return fmaf(mufu_tanh(0.5f * x), 0.5f, 0.5f); }
 template <> __device__ __forceinline__ float gate_tanh<OpTF32>(float x) { return fast_tanh(x); }
 template <> __device__ __forceinline__ float gate_sigmoid<OpTF32>(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
@@ -236,7 +242,7 @@ struct TcRt {  // runtime scalars the kernel needs beyond ConvArgs
 // ------------------------------------------------------------------------------------------------
 #define MBV_EL(i) if (FULL || (i) < nt)
 
-template <typename Op, int STEP, bool FULL, bool RH>
+template <typename Op, int STEP, bool FULL, int RH>
 __device__ __forceinline__ void epi_act(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
                                         size_t rstep, const float* acc) {
   using T = typename Op::T;
@@ -271,7 +277,7 @@ __device__ __forceinline__ void epi_act(const EpiParams& p, int b, int n, int ph
   }
 }
 
-template <typename Op, int STEP, bool FULL, bool RH>
+template <typename Op, int STEP, bool FULL, int RH>
 __device__ __forceinline__ void epi_res(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
                                         size_t rstep, const float* acc, const float* xpre) {
   using T = typename Op::T;
@@ -281,6 +287,11 @@ __device__ __forceinline__ void epi_res(const EpiParams& p, int b, int n, int ph
   float x[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) x[i] = xpre[i];  // xin, prefetched while the MMAs of this tile were running
+  if constexpr (RH == 2) {
+    const float inv = p.inv_slope;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = fminf(x[i], x[i] * inv);  // inverse leaky-relu (inv_slope >= 1): v < 0 -> v / slope
+  }
   const int sm = p.sum_mode;
   if (sm == 2 || sm == 3) {
     float sv[32];
@@ -333,7 +344,7 @@ __device__ __forceinline__ void epi_f32(const EpiParams& p, int b, int n, int ph
   for (int i = 0; i < 32; ++i) MBV_EL(i) o[i * step] = acc[i] + bias;
 }
 
-template <typename Op, int STEP, bool FULL>
+template <typename Op, int STEP, bool FULL, int RH>
 __device__ __forceinline__ void epi_rs(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
                                        size_t rstep, const float* acc, const float* xpre) {
   using T = typename Op::T;
@@ -347,10 +358,15 @@ __device__ __forceinline__ void epi_rs(const EpiParams& p, int b, int n, int pha
   if (res_half) {  // x = (x + rs) * mask -> fp32 stream + operand copy for the next in_layer
 #pragma unroll
     for (int i = 0; i < 32; ++i) { x[i] = 0.f; MBV_EL(i) x[i] = (xpre[i] + acc[i] + bias) * mp[i]; }
-    float* xo = reinterpret_cast<float*>(p.xout) + base;
     T* dst = reinterpret_cast<T*>(p.act[0]) + base;
+    if constexpr (RH == 2) {  // the operand copy is the stream
 #pragma unroll
-    for (int i = 0; i < 32; ++i) MBV_EL(i) { xo[i * step] = x[i]; op_store1<Op>(dst + i * step, x[i]); }
+      for (int i = 0; i < 32; ++i) MBV_EL(i) op_store1<Op>(dst + i * step, x[i]);
+    } else {
+      float* xo = reinterpret_cast<float*>(p.xout) + base;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) MBV_EL(i) { xo[i * step] = x[i]; op_store1<Op>(dst + i * step, x[i]); }
+    }
   } else {         // skip half: output += rs; the last layer applies the mask and emits the operand copy
 #pragma unroll
     for (int i = 0; i < 32; ++i) x[i] = acc[i] + bias + xpre[i];  // xpre = running skip sum (zeros for the first layer)
@@ -386,23 +402,24 @@ __device__ __forceinline__ void epi_post(const EpiParams& p, int b, int n, int p
   for (int i = 0; i < 32; ++i) MBV_EL(i) { zo[i * step] = z[i]; op_store1<Op>(dst + i * step, z[i]); }
 }
 
-template <typename Op, int MODE, int STEP, bool FULL, bool RH>
+template <typename Op, int MODE, int STEP, bool FULL, int RH>
 __device__ __forceinline__ void epi_dispatch(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
                                              size_t rstep, const float* acc, const float* acc2, const float* xpre) {
   if constexpr (MODE == EPI_ACT) epi_act<Op, STEP, FULL, RH>(p, b, n, phase, t_first, nt, rstep, acc);
   else if constexpr (MODE == EPI_RES) epi_res<Op, STEP, FULL, RH>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
   else if constexpr (MODE == EPI_F32) epi_f32<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc);
-  else if constexpr (MODE == EPI_RS) epi_rs<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
+  else if constexpr (MODE == EPI_RS) epi_rs<Op, STEP, FULL, RH>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
   else epi_post<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
 }
 
 // Residual-like input of a chunk (xin for EPI_RES / the residual half of EPI_RS, the running skip sum for the skip
 // half, z for EPI_POST).  It does not depend on the accumulator, so the epilogue warps issue these loads one chunk
 // AHEAD -- for the first chunk of a tile that is before the tile's MMAs have finished -- hiding the DRAM latency.
-template <int MODE, int LD, bool RH>
+template <int MODE, int LD, int RH>
 __device__ __forceinline__ void epi_prefetch(const EpiParams& p, int b, int n, int t_first, int nt, float* xpre) {
   const size_t step = LD > 0 ? (size_t)LD : (size_t)p.ld;
-  if constexpr (MODE == EPI_RES && RH) {
+  if constexpr ((MODE == EPI_RES && RH != 0) || (MODE == EPI_RS && RH == 2)) {
+    // (EPI_RS single stream: every row of the conv is a residual row, xin = the fp16 operand tensor h)
     const __half* hs = reinterpret_cast<const __half*>(p.xin) + ((size_t)b * p.rows_res + t_first) * p.ld + n;
     if (nt == 32) {
 #pragma unroll
@@ -435,7 +452,7 @@ __device__ __forceinline__ void epi_prefetch(const EpiParams& p, int b, int n, i
 
 // LD: compile-time channel pitch of the destination buffers (0 = runtime).  The immediate-offset fast path also
 // needs row_mul == 1 (everything but the polyphase upsamplers).
-template <typename Op, int MODE, int LD, bool RH>
+template <typename Op, int MODE, int LD, int RH>
 __device__ __forceinline__ void tc_epilogue32(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
                                               const float* acc, const float* acc2, const float* xpre) {
   const size_t rstep = (size_t)p.row_mul * p.ld;
@@ -448,7 +465,7 @@ __device__ __forceinline__ void tc_epilogue32(const EpiParams& p, int b, int n, 
   }
 }
 
-template <typename Op, int MODE, int LD, bool RH>
+template <typename Op, int MODE, int LD, int RH>
 __global__ void __launch_bounds__(TcThreads<MODE>::value, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmR, const ConvArgs a, const TcRt rt) {
@@ -544,8 +561,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     // Warp-uniform loop, one elected lane issues.  Per (tap, k-block): 4 MMAs whose descriptors differ only by
     // +32 bytes in the low word -- the issue path must stay far below the 128 tensor-core cycles one MMA takes.
     // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16 or tf32, both K-major, N, M=128
-    constexpr uint32_t fmt = (Op::kPrec == 2) ? 1u : 2u;
-    constexpr int KIND = (Op::kPrec == 2) ? 2 : 1;
+    constexpr uint32_t fmt = (Op::kPrec == 3) ? 0u : ((Op::kPrec == 2) ? 1u : 2u);  // F16 / BF16 / TF32
+    constexpr int KIND = (Op::kPrec >= 2) ? 2 : 1;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(rt.n_time >> 3) << 17) |
                            ((uint32_t)(TC_M >> 4) << 24);
     const uint32_t tap_step = (uint32_t)(a.dil * TC_ROW_BYTES) >> 4;  // descriptor-lo increment per tap
@@ -624,7 +641,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         const int t = ti.t0 + c + lane;
         if (ti.valid && c < rt.n_time && t < ti.t_lim) {
           const size_t off = ((size_t)ti.b * a.epi.rows_res + t) * a.epi.ld + (ti.n - lane);
-          const char* p = reinterpret_cast<const char*>(a.epi.xin) + off * (RH ? 2 : 4);
+          const char* p = reinterpret_cast<const char*>(a.epi.xin) + off * (RH != 0 ? 2 : 4);
           asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
         }
       }
@@ -636,12 +653,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         epi_prefetch<MODE, LD, RH>(a.epi, ti.b, ti.n, t_first, min(ti.t_lim - t_first, 32), dst);
     };
 
+    // (Measured and dropped: keeping the fp16 residual packed two-per-register and loading it one chunk AHEAD -- same
+    //  register count on paper -- spilled ~100 bytes and made every ResBlock conv 5-10 % slower, 8.9 -> 9.3 ms per step.)
     float xcur[32];
     int gate_chunk = 0;
     int tile = blockIdx.x;
     TileInfo ti = decode(tile);
     if (kPrefetch && tile < rt.total_tiles)
       for (int j = 0; j < nch; ++j) l2_prefetch(ti, c_first + CSTEP * j);
+
     while (tile < rt.total_tiles) {
       const bool have_next = tile + (int)gridDim.x < rt.total_tiles;
       TileInfo tn = ti;
@@ -744,7 +764,7 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
   (void)flags;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return "cuTensorMapEncodeTiled entry point unavailable";
-  const int esize = prec == 2 ? 2 : 4;
+  const int esize = prec >= 2 ? 2 : 4;
   const int KB = TC_ROW_BYTES / esize;
   if (a.Cp_in % 64 != 0) return "tcgen05 conv: padded input channels must be a multiple of 64";
   const int n_logical = a.N_total;
@@ -788,7 +808,8 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
   plan->grid = plan->total_tiles < num_sms ? plan->total_tiles : num_sms;
   if (plan->grid < 1) plan->grid = 1;
 
-  const CUtensorMapDataType dt = prec == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapDataType dt = prec == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                 : (prec == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
   {
     cuuint64_t dims[3] = {(cuuint64_t)a.Cp_in, (cuuint64_t)a.L_in, (cuuint64_t)a.B};
     cuuint64_t strides[2] = {(cuuint64_t)a.x_ld * esize, (cuuint64_t)a.L_in * a.x_ld * esize};
@@ -826,7 +847,7 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
 }
 
 // kernel table: (mode, compile-time pitch) instantiations; pitch 0 = runtime
-template <typename Op, int MODE, int LD, bool RH = false>
+template <typename Op, int MODE, int LD, int RH = 0>
 static cudaError_t launch_one(const ConvArgs& a, const TcPlan& p, const TcRt& rt, cudaStream_t st, bool set_attr) {
   auto k = conv_tc_kernel<Op, MODE, LD, RH>;
   if (set_attr) return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -846,14 +867,27 @@ static cudaError_t launch_one(const ConvArgs& a, const TcPlan& p, const TcRt& rt
 template <typename Op>
 static cudaError_t dispatch(const ConvArgs& a, const TcPlan& p, const TcRt& rt, cudaStream_t st, bool set_attr, int mode,
                             int ld, int res_half) {
-  if (res_half) {  // fp16 residual stream: decoder ACT (upsampler) and RES (ResBlock) epilogues only
-#define MBV_CASE_H(M, L) if (mode == M && ld == L) return launch_one<Op, M, L, true>(a, p, rt, st, set_attr);
-    MBV_CASE_H(EPI_ACT, 128) MBV_CASE_H(EPI_ACT, 256) MBV_CASE_H(EPI_RES, 128) MBV_CASE_H(EPI_RES, 256)
+  if constexpr (Op::kPrec == 3) {
+    if (res_half == 2) {  // single stream: ResBlock residual adds (decoder) and WN residual adds (flow)
+#define MBV_CASE_S(M, L) if (mode == M && ld == L) return launch_one<Op, M, L, 2>(a, p, rt, st, set_attr);
+      MBV_CASE_S(EPI_RES, 128) MBV_CASE_S(EPI_RES, 256) MBV_CASE_S(EPI_RS, 192)
+#undef MBV_CASE_S
+      if (mode == EPI_RES) return launch_one<Op, EPI_RES, 0, 2>(a, p, rt, st, set_attr);
+      if (mode == EPI_RS) return launch_one<Op, EPI_RS, 0, 2>(a, p, rt, st, set_attr);
+      return cudaErrorInvalidValue;
+    }
+  }
+  if (res_half == 1) {  // fp16 residual stream: decoder ACT (upsampler) and RES (ResBlock) epilogues only
+    if constexpr (Op::kPrec == 2) {
+#define MBV_CASE_H(M, L) if (mode == M && ld == L) return launch_one<Op, M, L, 1>(a, p, rt, st, set_attr);
+      MBV_CASE_H(EPI_ACT, 128) MBV_CASE_H(EPI_ACT, 256) MBV_CASE_H(EPI_RES, 128) MBV_CASE_H(EPI_RES, 256)
 #undef MBV_CASE_H
-    if (mode == EPI_ACT) return launch_one<Op, EPI_ACT, 0, true>(a, p, rt, st, set_attr);
-    if (mode == EPI_RES) return launch_one<Op, EPI_RES, 0, true>(a, p, rt, st, set_attr);
+      if (mode == EPI_ACT) return launch_one<Op, EPI_ACT, 0, 1>(a, p, rt, st, set_attr);
+      if (mode == EPI_RES) return launch_one<Op, EPI_RES, 0, 1>(a, p, rt, st, set_attr);
+    }
     return cudaErrorInvalidValue;
   }
+  if (res_half != 0) return cudaErrorInvalidValue;
 #define MBV_CASE(M, L) if (mode == M && ld == L) return launch_one<Op, M, L>(a, p, rt, st, set_attr);
   MBV_CASE(EPI_ACT, 128) MBV_CASE(EPI_ACT, 256) MBV_CASE(EPI_ACT, 192)
   MBV_CASE(EPI_RES, 128) MBV_CASE(EPI_RES, 256)
@@ -880,8 +914,14 @@ cudaError_t tc_set_attributes() {
       if (e != cudaSuccess) return e;
       e = dispatch<OpTF32>(a, p, rt, nullptr, true, mode, ld, 0);
       if (e != cudaSuccess) return e;
+      e = dispatch<OpF16>(a, p, rt, nullptr, true, mode, ld, 0);
+      if (e != cudaSuccess) return e;
       if (mode == EPI_ACT || mode == EPI_RES) {
         e = dispatch<OpBF16>(a, p, rt, nullptr, true, mode, ld, 1);
+        if (e != cudaSuccess) return e;
+      }
+      if (mode == EPI_RES || mode == EPI_RS) {
+        e = dispatch<OpF16>(a, p, rt, nullptr, true, mode, ld, 2);
         if (e != cudaSuccess) return e;
       }
     }
@@ -921,7 +961,8 @@ cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStr
   rt.w_resident = p.w_resident;
   rt.rotate = (p.c_tiles == 2 && (p.grid & 1) == 0 && p.total_tiles > p.grid) ? 1 : 0;
   cudaError_t e;
-  if (prec == 2) e = dispatch<OpBF16>(a, p, rt, st, false, a.epi.mode, a.epi.ld, a.epi.res_half);
+  if (prec == 3) e = dispatch<OpF16>(a, p, rt, st, false, a.epi.mode, a.epi.ld, a.epi.res_half);
+  else if (prec == 2) e = dispatch<OpBF16>(a, p, rt, st, false, a.epi.mode, a.epi.ld, a.epi.res_half);
   else if (a.epi.res_half) e = cudaErrorInvalidValue;
   else e = dispatch<OpTF32>(a, p, rt, st, false, a.epi.mode, a.epi.ld, 0);
   if (rt.dbg && e == cudaSuccess) timeline_dump(a, p, rt.dbg, st);

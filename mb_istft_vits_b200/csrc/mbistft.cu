@@ -33,6 +33,26 @@ inline uint16_t f32_to_bf16(float f) {
   u += 0x7fffu + ((u >> 16) & 1u);
   return (uint16_t)(u >> 16);
 }
+// fp32 -> fp16 bits, round to nearest even, overflow saturates to +-65504 (like the device-side stores)
+inline uint16_t f32_to_f16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  const uint32_t sign = (u >> 16) & 0x8000u;
+  const uint32_t a = u & 0x7fffffffu;
+  if (a > 0x7f800000u) return (uint16_t)(sign | 0x7e00u);          // NaN
+  if (a >= 0x477ff000u) return (uint16_t)(sign | 0x7bffu);         // >= 65520 (or inf) -> max finite
+  if (a < 0x33000001u) return (uint16_t)sign;                      // < 2^-25 -> 0
+  int e = (int)(a >> 23) - 127;
+  uint32_t m = (a & 0x7fffffu) | 0x800000u;
+  int shift = (e < -14) ? (13 + (-14 - e)) : 13;                   // subnormal halves lose extra bits
+  uint32_t half_m = m >> shift;
+  const uint32_t rem = m & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+  if (rem > halfway || (rem == halfway && (half_m & 1u))) half_m++;
+  uint32_t out;
+  if (e < -14) out = half_m;                                       // subnormal (a carry makes it the smallest normal)
+  else out = ((uint32_t)(e + 15) << 10) + (half_m - 0x400u);       // a mantissa carry bumps the exponent
+  return (uint16_t)(sign | out);
+}
 inline float f32_to_tf32(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);
@@ -66,7 +86,8 @@ struct mbv_handle {
   mbv_config cfg;
   int prec = 0;
   int esize = 4;
-  int res_half = 0;  // decoder residual stream in fp16 (MBV_FLAG_RESIDUAL_FP16, bf16 precision only)
+  int res_half = 0;  // decoder residual stream in fp16 (MBV_FLAG_RESIDUAL_FP16 with bf16; always with fp16)
+  int single = 0;    // fp16 precision on the tensor-core path: residual streams live in the operand tensors (EpiParams::res_half 2)
   int rsize = 4;
   int num_sms = 148;
   bool weights_loaded = false;
@@ -140,9 +161,10 @@ int fail(mbv_handle* h, int code, const char* fmt, ...) {
 int upload_weights(mbv_handle* h, ConvLayer& L, const std::vector<float>& packed, const std::vector<float>& bias) {
   const size_t n = packed.size();
   void* d = nullptr;
-  if (h->prec == MBV_PREC_BF16) {
+  if (h->prec == MBV_PREC_BF16 || h->prec == MBV_PREC_FP16) {
     std::vector<uint16_t> tmp(n);
-    for (size_t i = 0; i < n; ++i) tmp[i] = f32_to_bf16(packed[i]);
+    if (h->prec == MBV_PREC_BF16) for (size_t i = 0; i < n; ++i) tmp[i] = f32_to_bf16(packed[i]);
+    else for (size_t i = 0; i < n; ++i) tmp[i] = f32_to_f16(packed[i]);
     CUDA_TRY(h, cudaMalloc(&d, n * 2));
     CUDA_TRY(h, cudaMemcpy(d, tmp.data(), n * 2, cudaMemcpyHostToDevice));
   } else {
@@ -322,13 +344,14 @@ extern "C" int mbv_create(const mbv_config* cfg, mbv_handle** out) {
   *out = h;  // returned even on failure so the caller can read the message; destroy it either way
   const mbv_config& c = h->cfg;
   if (c.variant < 0 || c.variant > 2) return fail(h, MBV_ERR_INVALID, "variant must be 0 (istft), 1 (mb) or 2 (ms)");
-  if (c.precision < 0 || c.precision > 2) return fail(h, MBV_ERR_INVALID, "precision must be 0 (fp32), 1 (tf32) or 2 (bf16)");
+  if (c.precision < 0 || c.precision > 3) return fail(h, MBV_ERR_INVALID, "precision must be 0 (fp32), 1 (tf32), 2 (bf16) or 3 (fp16)");
   h->prec = c.precision;
-  h->esize = c.precision == MBV_PREC_BF16 ? 2 : 4;
-  if (c.flags & MBV_FLAG_RESIDUAL_FP16) {
-    if (c.precision != MBV_PREC_BF16) return fail(h, MBV_ERR_INVALID, "MBV_FLAG_RESIDUAL_FP16 requires MBV_PREC_BF16 (the fp32/tf32 paths keep an fp32 residual stream)");
+  h->esize = c.precision >= MBV_PREC_BF16 ? 2 : 4;
+  if ((c.flags & MBV_FLAG_RESIDUAL_FP16) || c.precision == MBV_PREC_FP16) {
+    if (c.precision < MBV_PREC_BF16) return fail(h, MBV_ERR_INVALID, "MBV_FLAG_RESIDUAL_FP16 requires a 16-bit precision (the fp32/tf32 paths keep an fp32 residual stream)");
     h->res_half = 1;
     h->rsize = 2;
+    h->single = (c.precision == MBV_PREC_FP16 && !(c.flags & MBV_FLAG_FORCE_SIMT)) ? 1 : 0;
   }
   if (c.inter_channels <= 0 || c.inter_channels % 64 != 0 || (c.inter_channels / 2) % 16 != 0)
     return fail(h, MBV_ERR_UNSUPPORTED, "inter_channels must be a multiple of 64 (got %d)", c.inter_channels);
@@ -745,7 +768,7 @@ int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, co
     int rc;
     {  // h = pre(x0) * mask
       EpiParams e = epi_base(EPI_ACT, Hp, T);
-      e.mask = mask; e.xout = f.h; e.act[0] = f.hop; e.n_act = 1;
+      e.mask = mask; e.xout = h->single ? nullptr : f.h; e.act[0] = f.hop; e.n_act = 1;  // single: the fp16 operand copy IS h
       if ((rc = run_conv(cx, h->fl_pre[f_i], f.zop, B, T, T, e))) return rc;
     }
     const int Ha = NL * Hp;  // channel pitch of the gate-output buffer: one Hp-wide slot per WN layer
@@ -760,6 +783,7 @@ int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, co
       if (l < NL - 1) {  // h = (h + res_l(acts_l)) * mask; the skip halves are applied by the fused post conv below
         EpiParams e = epi_base(EPI_RS, Hp, T);
         e.mask = mask; e.n_split = h->fl_rs[f_i][l].N_total; e.xin = f.h; e.xout = f.h; e.act[0] = f.hop; e.n_act = 1;
+        if (h->single) { e.xin = f.hop; e.xout = nullptr; e.res_half = 2; e.inv_slope = 1.f; }
         const char* ax = (const char*)f.acts + (size_t)l * Hp * h->esize;
         if ((rc = run_conv(cx, h->fl_rs[f_i][l], ax, B, T, T, e, Ha))) return rc;
       }
@@ -840,6 +864,7 @@ int run_decode(Ctx& cx, const DecBufs& d, const float* z, const float* z_mask, c
     {  // x = ups[i](lrelu(x)): S polyphase branches; emits the fp32 residual stream and lrelu(x [+ cond_j]) operand copies
       EpiParams e = epi_base(EPI_ACT, C, L);
       e.rows_res = Lin; e.row_mul = S; e.slope = 0.1f; e.xout = s.x; e.res_half = h->res_half;
+      if (h->single) { e.xout = nullptr; e.res_half = 0; }  // x lives in the operand copies lrelu(x [+ cond_j])
       e.n_act = g ? nk : 1;
       for (int j = 0; j < e.n_act; ++j) { e.act[j] = s.a[j]; e.act_add[j] = g ? cond[j] : nullptr; }
       e.act_add_bs = C;
@@ -853,7 +878,8 @@ int run_decode(Ctx& cx, const DecBufs& d, const float* z, const float* z_mask, c
         const bool final_conv = (p == np - 1);
         EpiParams e = epi_base(EPI_RES, C, L);
         e.xin = x_in; e.slope = 0.1f; e.res_half = h->res_half;
-        if (p == 0 && g) { e.bias = bias2c[j]; e.bias_bs = C; }  // x + cond(g) folded into the first residual add
+        if (p == 0 && g && !h->single) { e.bias = bias2c[j]; e.bias_bs = C; }  // x + cond(g) folded into the first residual add
+        if (h->single) { e.xin = a_in; e.res_half = 2; e.inv_slope = 10.f; }    // a_in = lrelu_0.1(x [+ cond_j]) -> x [+ cond_j]
         if (final_conv) {
           e.xs = s.xs;
           e.sum_mode = (nk == 1) ? 4 : (j == 0 ? 1 : (j == nk - 1 ? 3 : 2));
@@ -863,7 +889,7 @@ int run_decode(Ctx& cx, const DecBufs& d, const float* z, const float* z_mask, c
             if (last) { e.rows_out = L + 1; e.row_add = 1; e.dup_src = 2; e.dup_dst = 0; }
           }
         } else {
-          e.xout = s.xr;
+          e.xout = h->single ? nullptr : s.xr;
         }
         const void* conv_in;
         if (c.resblock_type == 1) {

@@ -31,7 +31,8 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict
       const float v = tile[tx][i];
       const size_t o = ((size_t)b * T + t) * Cp + c;
       if (dst_op) {
-        if constexpr (Op::kPrec == 2) dst_op[o] = __float2bfloat16_rn(v);
+        if constexpr (Op::kPrec == 3) dst_op[o] = to_half_sat(v);
+        else if constexpr (Op::kPrec == 2) dst_op[o] = __float2bfloat16_rn(v);
         else dst_op[o] = op_round<Op>(v);
       }
       if (dst_f32) dst_f32[o] = v;
@@ -42,7 +43,9 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict
 cudaError_t launch_pack_input(int prec, const float* src, const float* mask, void* dst_op, float* dst_f32, int B, int C,
                               int T, int Cp, cudaStream_t st) {
   dim3 grid((T + 31) / 32, (Cp + 31) / 32, B);
-  if (prec == 2)
+  if (prec == 3)
+    pack_input_kernel<OpF16><<<grid, 256, 0, st>>>(src, mask, (__half*)dst_op, dst_f32, C, T, Cp);
+  else if (prec == 2)
     pack_input_kernel<OpBF16><<<grid, 256, 0, st>>>(src, mask, (__nv_bfloat16*)dst_op, dst_f32, C, T, Cp);
   else if (prec == 1)
     pack_input_kernel<OpTF32><<<grid, 256, 0, st>>>(src, mask, (float*)dst_op, dst_f32, C, T, Cp);

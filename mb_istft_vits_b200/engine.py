@@ -46,11 +46,13 @@ class Engine:
         self.cfg = dict(cfg)
         self.precision = precision
         if residual is None:
-            residual = "fp16" if precision == "bf16" else "fp32"
+            residual = "fp16" if precision in ("bf16", "fp16") else "fp32"
         if residual not in ("fp16", "fp32"):
             raise ValueError("residual must be 'fp16' or 'fp32'")
         self.residual = residual
-        if residual == "fp16":
+        if precision == "fp16" and residual != "fp16":
+            raise ValueError("precision 'fp16' keeps its residual streams in the fp16 operand tensors")
+        if residual == "fp16" and precision == "bf16":
             flags |= _lib.FLAG_RESIDUAL_FP16
         self.lib = _lib.load()
         if not torch.cuda.is_available():

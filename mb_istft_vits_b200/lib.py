@@ -16,7 +16,7 @@ MBV_ABI_VERSION = 1
 MAX_UPS, MAX_KERNELS, MAX_DILATIONS = 4, 4, 3
 
 VARIANTS = {"istft": 0, "mb": 1, "ms": 2}
-PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2}
+PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2, "fp16": 3}
 
 FLAG_FORCE_SIMT = 4
 FLAG_RESIDUAL_FP16 = 8
