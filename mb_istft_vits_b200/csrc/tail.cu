@@ -680,17 +680,17 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
           v.v = __shfl_down_sync(0xffffffffu, fr[i].v, 3);     acc = fma2(k3, v, acc);
           yp[P][i] = acc;
         }
-        if (warp > 0 && lane < 3) {  // what the previous warp's lanes 29..31 are missing: [lane 0: p0 p1 p2 | lane 1: p0 p1 | lane 2: p0]
-          f2* h = s_halo + ((warp * 2 + P) * 6) * 4;
-          const int first = lane == 0 ? 0 : (lane == 1 ? 3 : 5), n = 3 - lane;
-          for (int part = 0; part < n; ++part)
+        // what the previous warp's lanes 29..31 are missing: slots [lane 0: p0 p1 p2 | lane 1: p0 p1 | lane 2: p0].
+        // Predicated stores, no branch: both band pairs stay in one basic block and the scheduler can interleave them.
+        {
+          f2* h = s_halo + ((warp * 2 + P) * 6) * 4 + (lane == 0 ? 0 : (lane == 1 ? 3 : 5)) * 4;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              f2 v = fr[i];
-              if (part == 1) v = fr[4 + i];
-              if (part == 2) v = fr[8 + i];
-              h[(first + part) * 4 + i] = v;
-            }
+          for (int part = 0; part < 3; ++part) {
+            const bool on = (warp > 0) && (lane + part < 3);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (on) h[part * 4 + i] = fr[4 * part + i];
+          }
         }
       };
       band_pair(std::integral_constant<int, 0>{});
