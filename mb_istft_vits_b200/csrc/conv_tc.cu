@@ -528,7 +528,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const int t0 = tt * rt.n_time;
       const int wrow0 = phase * a.taps * a.N_total + ct * TC_M;
       const int xrow0 = t0 + a.shift0[phase];
-      if (rt.dbg && lane == 0) rt.dbg[((size_t)blockIdx.x * 3 + 0) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
+      if (rt.dbg && lane == 0) rt.dbg[((size_t)blockIdx.x * 5 + 0) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
       // (A whole-tile TMA L2 prefetch of the residual box issued here was measured to be too early: a tile-time later
       //  a third of it had been evicted again and DRAM reads grew 40 %.  The epilogue warps prefetch two chunks ahead.)
       if (false && MODE == EPI_RES && rt.prefetch_res && elect_one()) tma_prefetch_l2_3d(&tmR, ct * TC_M, t0, b);
@@ -572,7 +572,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       mbar_wait(BAR(iCE + sc), pc ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(sc * TC_ACC_STRIDE);
-      if (rt.dbg && lane == 0) rt.dbg[((size_t)blockIdx.x * 3 + 1) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
+      if (rt.dbg && lane == 0) rt.dbg[((size_t)blockIdx.x * 5 + 1) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
       uint32_t accum = 0;
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(BAR(iXF + sx), px);
@@ -601,7 +601,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       if (elect_one()) tc_commit(BAR(iCF + sc));
       __syncwarp();
-      if (rt.dbg && lane == 0) rt.dbg[((size_t)blockIdx.x * 3 + 1) * 64 + 2 * ((tile / gridDim.x) & 31) + 1] = clock64();
+      if (rt.dbg && lane == 0) rt.dbg[((size_t)blockIdx.x * 5 + 1) * 64 + 2 * ((tile / gridDim.x) & 31) + 1] = clock64();
       if (++sc == 2) { sc = 0; pc ^= 1; }
     }
   } else if (warp < TC_EPI_WARPS) {
@@ -671,7 +671,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       mbar_wait(BAR(iCF + sc), pc);
       tc_fence_after();
-      if (rt.dbg && warp == 0 && lane == 0) rt.dbg[((size_t)blockIdx.x * 3 + 2) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
+      if (rt.dbg && warp == 0 && lane == 0) rt.dbg[((size_t)blockIdx.x * 5 + 2) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc * TC_ACC_STRIDE);
       float gate_bias = 0.f;
       if constexpr (MODE == EPI_GATE) {  // bias + cond_layer(g) of this thread's weight row, once per tile
@@ -680,9 +680,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       for (int c = c_first; c < rt.n_time; c += CSTEP) {
         float acc[32];
+        // debug stamps of warp 0's chunks (tiles 0..9): issue | accumulator in registers | residual in registers | done
+        long long* cdbg = nullptr;
+        if (rt.dbg && warp == 0 && lane == 0 && tile / (int)gridDim.x < 10)
+          cdbg = rt.dbg + ((size_t)blockIdx.x * 5 + 3) * 64 + ((tile / gridDim.x) * 3 + (c - c_first) / CSTEP) * 4;
+        if (cdbg) cdbg[0] = clock64();
         tmem_ld32(taddr + (uint32_t)c, acc);
         if constexpr (kPrefetch) prefetch(ti, c, xcur);  // residual of THIS chunk, in flight with the TMEM load
         tmem_ld_wait();
+        if (cdbg) {
+          cdbg[1] = clock64();
+          if constexpr (kPrefetch) {
+            float sdep = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sdep += xcur[i];
+            if (sdep == 1.2345e-30f) cdbg[1] = 0;  // forces the wait for every residual load
+            cdbg[2] = clock64();
+          }
+        }
         const int t_first = ti.t0 + c;
         if constexpr (MODE == EPI_GATE) {
           // One accumulator tile = [64 tanh rows | 64 sigmoid rows] of the same 64 channels: lanes i and i+64 belong
@@ -720,11 +735,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         } else if (ti.valid && t_first < ti.t_lim) {
           tc_epilogue32<Op, MODE, LD, RH>(a.epi, ti.b, ti.n, ti.phase, t_first, min(ti.t_lim - t_first, 32), acc, nullptr, xcur);
         }
+        if (cdbg) cdbg[3] = clock64();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(iCE + sc));
-      if (rt.dbg && warp == 0 && lane == 0) rt.dbg[((size_t)blockIdx.x * 3 + 2) * 64 + 2 * ((tile / gridDim.x) & 31) + 1] = clock64();
+      if (rt.dbg && warp == 0 && lane == 0) rt.dbg[((size_t)blockIdx.x * 5 + 2) * 64 + 2 * ((tile / gridDim.x) & 31) + 1] = clock64();
       if (++sc == 2) { sc = 0; pc ^= 1; }
       ti = tn;
       tile += gridDim.x;
@@ -931,7 +947,7 @@ cudaError_t tc_set_attributes() {
 // MBV_TIMELINE=<mode>: after every launch whose epilogue mode matches, print CTA 0's per-tile clock stamps (debug)
 static void timeline_dump(const ConvArgs& a, const TcPlan& p, long long* dbg, cudaStream_t st) {
   cudaStreamSynchronize(st);
-  std::vector<long long> hbuf(3 * 64);
+  std::vector<long long> hbuf(5 * 64);
   cudaMemcpy(hbuf.data(), dbg, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
   const int nt = (p.total_tiles + p.grid - 1) / p.grid;
   long long t0 = hbuf[0];
@@ -940,6 +956,14 @@ static void timeline_dump(const ConvArgs& a, const TcPlan& p, long long* dbg, cu
   for (int i = 0; i < nt && i < 32; ++i)
     fprintf(stderr, "  tile %2d  prod_start %7lld | mma %7lld .. %7lld | epi %7lld .. %7lld\n", i, hbuf[2 * i] - t0,
             hbuf[64 + 2 * i] - t0, hbuf[64 + 2 * i + 1] - t0, hbuf[128 + 2 * i] - t0, hbuf[128 + 2 * i + 1] - t0);
+  for (int i = 0; i < nt && i < 10; ++i)
+    for (int j = 0; j < 3; ++j) {
+      const long long* c = &hbuf[192 + (i * 3 + j) * 4];
+      if (c[0] == 0) continue;
+      fprintf(stderr, "    tile %2d chunk %d  start %7lld | acc +%5lld | residual +%5lld | done +%5lld\n", i, j, c[0] - t0,
+              c[1] - c[0], c[2] ? c[2] - c[0] : 0, c[3] - c[0]);
+    }
+  cudaMemset(dbg, 0, 148 * 5 * 64 * sizeof(long long));
 }
 
 cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStream_t st) {
@@ -948,7 +972,7 @@ cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStr
   if (dbg_mode == -2) {
     const char* e = getenv("MBV_TIMELINE");
     dbg_mode = e ? atoi(e) : -1;
-    if (dbg_mode >= 0) cudaMalloc(&dbg, 148 * 3 * 64 * sizeof(long long));
+    if (dbg_mode >= 0) { cudaMalloc(&dbg, 148 * 5 * 64 * sizeof(long long)); cudaMemset(dbg, 0, 148 * 5 * 64 * sizeof(long long)); }
   }
   TcRt rt;
   rt.dbg = (dbg_mode >= 0 && a.epi.mode == dbg_mode) ? dbg : nullptr;

@@ -10,7 +10,8 @@ from mb_istft_vits_b200 import Engine, get_config, synth
 
 cfg = get_config("ljs_mb_istft_vits")
 sd = synth.make_state_dict(cfg)
-eng = Engine(cfg, sd, precision="bf16")
+import os
+eng = Engine(cfg, sd, precision=os.environ.get("MBV_PREC", "bf16"))
 z, m, _ = synth.make_latents(cfg, 64, 862)
 z, m = z.cuda(), m.cuda()
 if len(sys.argv) > 1 and sys.argv[1] == "decode":
