@@ -166,6 +166,21 @@ int mbv_tail(mbv_handle* h, const float* logits, float* wav, float* o_mb, float*
 int mbv_pcm16(mbv_handle* h, const float* wav, const int32_t* n_samples, int32_t B, int32_t stride, int32_t auto_normalize,
               void* scratch, int16_t* pcm, void* stream);
 
+/* NEXT-row widening: the alignment expansion and prior sampling of SynthesizerTrn.infer,
+ * models.py:717-729 (commons.generate_path, commons.py:128-143), as one gather kernel instead of a [B,1,Ty,Tx] attention
+ * matrix and two batched matmuls:
+ *   y_lengths = clamp_min(sum(w_ceil), 1);  y_mask[b,0,ty] = ty < y_lengths[b]
+ *   tx(ty) = the token with cumsum(w_ceil)[tx-1] <= ty < cumsum(w_ceil)[tx]  (none for padded frames / masked tokens)
+ *   z_p[b,c,ty] = m_p[b,c,tx] + noise[b,c,ty] * exp(logs_p[b,c,tx]) * noise_scale       (m = logs = 0 when there is no tx)
+ * m_p, logs_p: [B,C,Tx];  w_ceil: [B,1,Tx] = ceil(exp(logw) * x_mask * length_scale);  x_mask: [B,1,Tx] or NULL;
+ * noise: [B,C,Ty] standard normal drawn by the caller (the reference's torch.randn_like(m_p));  Ty = max(y_lengths),
+ * computed by the caller exactly as the reference does (it needs the value on the host to size its tensors).
+ * Outputs: z_p [B,C,Ty], y_mask [B,1,Ty]; optional (NULL to skip) m_exp / logs_exp [B,C,Ty] (the expanded statistics
+ * infer() returns), attn [B,1,Ty,Tx], y_lengths [B] int64.  All device memory, fp32, contiguous. */
+int mbv_expand_prior(mbv_handle* h, const float* m_p, const float* logs_p, const float* w_ceil, const float* x_mask,
+                     const float* noise, float noise_scale, int32_t B, int32_t C, int32_t Tx, int32_t Ty, float* z_p,
+                     float* y_mask, float* m_exp, float* logs_exp, float* attn, int64_t* y_lengths, void* stream);
+
 const char* mbv_last_error(mbv_handle* h);
 
 #ifdef __cplusplus

@@ -13,7 +13,7 @@ def __getattr__(name):
     if name in ("Engine", "fold_weight_norm"):
         from . import engine
         return getattr(engine, name)
-    if name in ("NativeFlow", "NativeDecoder", "patch_synthesizer"):
+    if name in ("NativeFlow", "NativeDecoder", "patch_synthesizer", "infer_native"):
         from . import modules
         return getattr(modules, name)
     if name == "HostStream":

@@ -60,4 +60,10 @@ cudaError_t launch_cond_gemv(const float* g, const float* w, const float* bias, 
 cudaError_t launch_pcm16(const float* wav, const int* n_valid, int B, int stride, int auto_normalize, unsigned int* peak_bits,
                          short* pcm, cudaStream_t st);
 
+// alignment expansion + prior sampling (models.py:717-729): see misc.cu
+cudaError_t launch_expand_prior(const float* m_p, const float* logs_p, const float* w_ceil, const float* x_mask,
+                                const float* noise, float noise_scale, int B, int C, int Tx, int Ty, float* z_p,
+                                float* y_mask, float* m_exp, float* logs_exp, float* attn, long long* y_lengths,
+                                cudaStream_t st);
+
 }  // namespace mbv

@@ -1070,6 +1070,27 @@ extern "C" int mbv_pcm16(mbv_handle* h, const float* wav, const int32_t* n_sampl
   return MBV_OK;
 }
 
+extern "C" int mbv_expand_prior(mbv_handle* h, const float* m_p, const float* logs_p, const float* w_ceil, const float* x_mask,
+                                const float* noise, float noise_scale, int32_t B, int32_t C, int32_t Tx, int32_t Ty,
+                                float* z_p, float* y_mask, float* m_exp, float* logs_exp, float* attn, int64_t* y_lengths,
+                                void* stream) {
+  if (!h) return MBV_ERR_INVALID;
+  if (!m_p || !logs_p || !w_ceil || !noise || !z_p || !y_mask) return fail(h, MBV_ERR_INVALID, "mbv_expand_prior: null tensor");
+  if (B < 1 || C < 1 || Tx < 1 || Ty < 1) return fail(h, MBV_ERR_INVALID, "mbv_expand_prior: sizes must be >= 1");
+  if (B > 65535) return fail(h, MBV_ERR_UNSUPPORTED, "B > 65535");
+  if (Tx > 12000) return fail(h, MBV_ERR_UNSUPPORTED, "mbv_expand_prior: more than 12000 tokens per utterance");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(h, MBV_ERR_CUDA, "mbv_expand_prior: no CUDA device (there is no CPU fallback)");
+  }
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  CUDA_TRY(h, launch_expand_prior(m_p, logs_p, w_ceil, x_mask, noise, noise_scale, B, C, Tx, Ty, z_p, y_mask, m_exp, logs_exp,
+                                  attn, (long long*)y_lengths, (cudaStream_t)stream));
+  h->last_launches = 1;
+  return MBV_OK;
+}
+
 extern "C" int mbv_last_launch_count(mbv_handle* h) { return h ? h->last_launches : 0; }
 
 extern "C" int mbv_set_profiling(mbv_handle* h, int32_t on) {

@@ -158,4 +158,80 @@ cudaError_t launch_pcm16(const float* wav, const int* n_valid, int B, int stride
   return cudaGetLastError();
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// NEXT-row widening: alignment expansion + prior sampling of SynthesizerTrn.infer
+// (models.py:717-729, commons.generate_path commons.py:128-143).  The reference materialises attn [B,1,Ty,Tx] and runs
+// two batched matmuls to gather rows; attn has at most one 1 per output frame, so this is a gather:
+//   tx(ty) = first token whose cumulative duration exceeds ty;   m, logs = m_p[:, tx], logs_p[:, tx]  (0 if none / padded)
+//   z_p = m + noise * exp(logs) * noise_scale;   y_mask = ty < max(sum(w_ceil), 1)
+// One CTA = one utterance x 128 output frames; every CTA redoes the (tiny, exact: integer-valued fp32) prefix sum.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) expand_prior_kernel(const float* __restrict__ m_p, const float* __restrict__ logs_p,
+                                                           const float* __restrict__ w_ceil, const float* __restrict__ x_mask,
+                                                           const float* __restrict__ noise, float noise_scale, int C, int Tx,
+                                                           int Ty, float* __restrict__ z_p, float* __restrict__ y_mask,
+                                                           float* __restrict__ m_exp, float* __restrict__ logs_exp,
+                                                           float* __restrict__ attn, long long* __restrict__ y_lengths) {
+  extern __shared__ float s_cum[];     // [Tx] inclusive prefix sums, then s_tx[128]
+  int* s_tx = reinterpret_cast<int*>(s_cum + Tx);
+  const int b = blockIdx.y, ty0 = blockIdx.x * 128, tid = threadIdx.x;
+  if (tid == 0) {
+    float acc = 0.f;
+    const float* w = w_ceil + (size_t)b * Tx;
+    for (int i = 0; i < Tx; ++i) { acc += w[i]; s_cum[i] = acc; }
+  }
+  __syncthreads();
+  const float total = s_cum[Tx - 1];
+  const int y_len = total < 1.f ? 1 : (int)total;   // clamp_min(sum, 1).long()
+  if (y_lengths && blockIdx.x == 0 && tid == 0) y_lengths[b] = y_len;
+  const int ty = ty0 + tid;
+  int tx = Tx;
+  if (ty < Ty) {
+    // smallest tx with cum[tx] > ty  (path = [ty < cum[tx]] - [ty < cum[tx-1]], commons.py:139-141)
+    int lo = 0, hi = Tx;
+    const float fty = (float)ty;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_cum[mid] > fty) hi = mid; else lo = mid + 1;
+    }
+    tx = lo;
+  }
+  bool ok = (ty < Ty) && (tx < Tx) && (ty < y_len);
+  if (ok && x_mask) ok = x_mask[(size_t)b * Tx + tx] != 0.f;
+  s_tx[tid] = ok ? tx : -1;
+  if (ty < Ty) {
+    y_mask[(size_t)b * Ty + ty] = ty < y_len ? 1.f : 0.f;
+    for (int c = 0; c < C; ++c) {
+      const size_t src = ((size_t)b * C + c) * Tx + tx, dst = ((size_t)b * C + c) * Ty + ty;
+      const float m = ok ? m_p[src] : 0.f, l = ok ? logs_p[src] : 0.f;
+      // m + ((noise * exp(logs)) * noise_scale), every product / sum rounded separately like the reference's tensor ops
+      z_p[dst] = __fadd_rn(m, __fmul_rn(__fmul_rn(noise[dst], expf(l)), noise_scale));
+      if (m_exp) m_exp[dst] = m;
+      if (logs_exp) logs_exp[dst] = l;
+    }
+  }
+  if (attn) {
+    __syncthreads();
+    const int rows = min(128, Ty - ty0);
+    float* a = attn + ((size_t)b * Ty + ty0) * Tx;
+    for (int e = tid; e < rows * Tx; e += 128) {
+      const int rr = e / Tx, cc = e - rr * Tx;
+      a[e] = (s_tx[rr] == cc) ? 1.f : 0.f;
+    }
+  }
+}
+
+cudaError_t launch_expand_prior(const float* m_p, const float* logs_p, const float* w_ceil, const float* x_mask,
+                                const float* noise, float noise_scale, int B, int C, int Tx, int Ty, float* z_p,
+                                float* y_mask, float* m_exp, float* logs_exp, float* attn, long long* y_lengths,
+                                cudaStream_t st) {
+  dim3 grid((Ty + 127) / 128, B);
+  const size_t smem = (size_t)Tx * 4 + 128 * 4;
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  expand_prior_kernel<<<grid, 128, smem, st>>>(m_p, logs_p, w_ceil, x_mask, noise, noise_scale, C, Tx, Ty, z_p, y_mask, m_exp,
+                                               logs_exp, attn, y_lengths);
+  return cudaGetLastError();
+}
+
 }  // namespace mbv

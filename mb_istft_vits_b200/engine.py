@@ -220,6 +220,34 @@ class Engine:
                                        self._ptr(scratch), self._ptr(pcm), self._stream()))
         return pcm
 
+    def expand_prior(self, m_p, logs_p, w_ceil, noise_scale=1.0, x_mask=None, noise=None, want_attn=False,
+                     want_stats=False):
+        """models.py:717-729 on the GPU: durations -> y_mask, gathered prior statistics, z_p = m + noise * exp(logs) *
+        noise_scale.  m_p, logs_p: [B,C,Tx]; w_ceil: [B,1,Tx] (ceil'd, masked durations).  noise: [B,C,Ty] or None = drawn
+        here with torch.randn in the memory order of the reference's randn_like (its expanded m_p has the strides of a
+        [B,Ty,C] tensor), so a seeded run consumes the generator exactly like the reference.
+        Returns (z_p, y_mask, y_lengths, attn | None, (m_exp, logs_exp) | None)."""
+        m_p, logs_p, w_ceil = self._prep(m_p), self._prep(logs_p), self._prep(w_ceil)
+        B, Cc, Tx = m_p.shape
+        if tuple(logs_p.shape) != (B, Cc, Tx) or tuple(w_ceil.shape) != (B, 1, Tx):
+            raise ValueError("expand_prior: m_p / logs_p [B,C,Tx] and w_ceil [B,1,Tx] expected")
+        x_mask = self._prep(x_mask, (B, 1, Tx)) if x_mask is not None else None
+        y_lengths = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()   # models.py:719
+        Ty = int(y_lengths.max())                                          # host sync, as in commons.sequence_mask
+        if noise is None:
+            noise = torch.randn((B, Ty, Cc), dtype=torch.float32, device=self.device).transpose(1, 2)
+        noise = self._prep(noise, (B, Cc, Ty))
+        z_p = torch.empty((B, Cc, Ty), dtype=torch.float32, device=self.device)
+        y_mask = torch.empty((B, 1, Ty), dtype=torch.float32, device=self.device)
+        attn = torch.empty((B, 1, Ty, Tx), dtype=torch.float32, device=self.device) if want_attn else None
+        m_exp = torch.empty_like(z_p) if want_stats else None
+        logs_exp = torch.empty_like(z_p) if want_stats else None
+        self._check(self.lib.mbv_expand_prior(self._h, self._ptr(m_p), self._ptr(logs_p), self._ptr(w_ceil), self._ptr(x_mask),
+                                              self._ptr(noise), float(noise_scale), B, Cc, Tx, Ty, self._ptr(z_p),
+                                              self._ptr(y_mask), self._ptr(m_exp), self._ptr(logs_exp), self._ptr(attn), None,
+                                              self._stream()))
+        return z_p, y_mask, y_lengths, attn, ((m_exp, logs_exp) if want_stats else None)
+
     def decode_chunked(self, z, g=None, chunk_frames=256, halo_frames=None):
         """Exact streaming decode: the decoder is convolutional with a receptive field of +-24 latent frames (MB/MS;
         +-13 single-band), so decoding overlapping windows [a-halo, b+halo) and keeping the samples of

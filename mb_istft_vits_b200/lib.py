@@ -27,7 +27,7 @@ ERRORS = {0: "MBV_OK", -1: "MBV_ERR_INVALID", -2: "MBV_ERR_UNSUPPORTED", -3: "MB
 # every symbol include/mbistft.h declares (tests check the .so exports all of them)
 SYMBOLS = ["mbv_abi_version", "mbv_create", "mbv_destroy", "mbv_load_weights", "mbv_workspace_bytes",
            "mbv_flow_reverse", "mbv_decode", "mbv_flow_decode", "mbv_last_launch_count", "mbv_decode_flops",
-           "mbv_flow_flops", "mbv_tail", "mbv_last_error", "mbv_set_profiling", "mbv_profile_read", "mbv_profile_read_launches", "mbv_pcm16"]
+           "mbv_flow_flops", "mbv_tail", "mbv_last_error", "mbv_set_profiling", "mbv_profile_read", "mbv_profile_read_launches", "mbv_pcm16", "mbv_expand_prior"]
 
 
 class MbvConfig(C.Structure):
@@ -87,6 +87,7 @@ def load():
     lib.mbv_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     lib.mbv_profile_read_launches.argtypes = [vp, C.POINTER(C.c_float), C.c_char_p, i32, i32, C.POINTER(i32)]
     lib.mbv_pcm16.argtypes = [vp, fp, vp, i32, i32, i32, vp, vp, vp]
+    lib.mbv_expand_prior.argtypes = [vp, fp, fp, fp, fp, fp, C.c_float, i32, i32, i32, i32, fp, fp, fp, fp, fp, vp, vp]
     lib.mbv_last_error.argtypes = [vp]
     lib.mbv_last_error.restype = C.c_char_p
     if lib.mbv_abi_version() != MBV_ABI_VERSION:

@@ -56,6 +56,31 @@ class NativeDecoder(nn.Module):
         """Weight-norm is folded at load time; nothing to do (reference: models.py:299/379/469)."""
 
 
+@torch.no_grad()
+def infer_native(net_g, engine, x, x_lengths, sid=None, noise_scale=1, length_scale=1, noise_scale_w=1., max_len=None,
+                 noise=None, want_attn=True):
+    """SynthesizerTrn.infer (models.py:697-737) with everything after the duration predictor on the B200 library: the
+    reference's own text encoder / duration predictor modules run as they are (``net_g.enc_p``, ``net_g.dp``,
+    ``net_g.emb_g``); alignment expansion + prior sampling (models.py:717-729) is ``Engine.expand_prior`` and flow
+    reverse + decoder (models.py:730-734) one ``Engine.flow_decode`` call.  Same return tuple as the reference except that
+    ``timings`` is empty (every call is asynchronous) and ``attn`` is None when ``want_attn`` is False."""
+    x, m_p, logs_p, x_mask = net_g.enc_p(x, x_lengths)
+    g = net_g.emb_g(sid).unsqueeze(-1) if getattr(net_g, "n_speakers", 0) > 0 else None
+    if getattr(net_g, "use_sdp", False):
+        logw = net_g.dp(x, x_mask, g=g, reverse=True, noise_scale=noise_scale_w)
+    else:
+        logw = net_g.dp(x, x_mask, g=g)
+    w_ceil = torch.ceil(torch.exp(logw) * x_mask * length_scale)
+    z_p, y_mask, y_lengths, attn, stats = engine.expand_prior(m_p, logs_p, w_ceil, noise_scale, x_mask=x_mask, noise=noise,
+                                                              want_attn=want_attn, want_stats=True)
+    if max_len is not None:  # the reference decodes (z * y_mask)[:, :, :max_len]; the flow is causal-free, so run it in full
+        z = engine.flow_reverse(z_p, y_mask, g)
+        o, o_mb, spec, phase = engine.decode((z * y_mask)[:, :, :max_len].contiguous(), g)
+    else:
+        z, o, o_mb, spec, phase = engine.flow_decode(z_p, y_mask, g, want_z=True, want_mb=True, want_spec=True)
+    return o, o_mb, spec, phase, attn, y_mask, (z, z_p, stats[0], stats[1]), {}
+
+
 def patch_synthesizer(net_g, cfg, precision="bf16", device=0, flags=0, residual=None):
     """Replace net_g.flow and net_g.dec by the native path, using net_g's own weights."""
     sd = {k: v for k, v in net_g.state_dict().items() if k.startswith(("dec.", "flow."))}

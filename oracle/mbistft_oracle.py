@@ -264,6 +264,43 @@ def flow_decode(sd, cfg, z_p, y_mask, g=None):
 # ----------------------------------------------------------------------------
 # next-row widening: waveform post-processing of the TTS service (tts_vits.py:204-216), numpy like the reference
 # ----------------------------------------------------------------------------
+def expand_prior(m_p, logs_p, w_ceil, noise, noise_scale=1.0, x_mask=None):
+    """NEXT-row widening: the alignment expansion and prior sampling of SynthesizerTrn.infer,
+    models.py:717-729 with commons.generate_path (commons.py:128-143) and commons.sequence_mask (commons.py:120-125):
+
+        y_lengths = clamp_min(sum(w_ceil), 1);  y_mask = (arange(Ty) < y_lengths)
+        attn[b, ty, tx] = 1  iff  cum[tx-1] <= ty < cum[tx]   (cum = cumsum(w_ceil)), times x_mask[tx] * y_mask[ty]
+        m, logs = attn @ m_p, attn @ logs_p                    -- a row gather, since attn has at most one 1 per row
+        z_p = m + noise * exp(logs) * noise_scale              -- noise = the reference's torch.randn_like(m_p)
+
+    m_p, logs_p: [B, C, Tx]; w_ceil: [B, 1, Tx] (ceil'd, already masked durations); noise: [B, C, Ty] with
+    Ty = max(y_lengths).  Written with index arithmetic (no attention matrix product) so that it is an independent
+    restatement.  Returns (z_p, y_mask [B,1,Ty], attn [B,1,Ty,Tx], m [B,C,Ty], logs [B,C,Ty], y_lengths)."""
+    B, C, Tx = m_p.shape
+    cum = torch.cumsum(w_ceil[:, 0, :].to(torch.float32), dim=-1)                 # [B, Tx], integer-valued
+    y_lengths = torch.clamp_min(cum[:, -1], 1).long()
+    Ty = int(y_lengths.max())
+    assert noise.shape == (B, C, Ty), (noise.shape, (B, C, Ty))
+    ty = torch.arange(Ty, dtype=torch.float32)
+    y_mask = (torch.arange(Ty)[None, :] < y_lengths[:, None]).to(m_p.dtype).unsqueeze(1)
+    attn = torch.zeros((B, 1, Ty, Tx), dtype=m_p.dtype)
+    m = torch.zeros((B, C, Ty), dtype=m_p.dtype)
+    logs = torch.zeros((B, C, Ty), dtype=m_p.dtype)
+    for b in range(B):
+        # first token whose cumulative duration exceeds ty
+        tx = torch.searchsorted(cum[b].contiguous(), ty, right=True)              # [Ty], == Tx when none does
+        ok = (tx < Tx) & (torch.arange(Ty) < y_lengths[b])
+        txc = tx.clamp(max=Tx - 1)
+        if x_mask is not None:
+            ok = ok & (x_mask[b, 0, txc] != 0)
+        rows = torch.nonzero(ok)[:, 0]
+        attn[b, 0, rows, txc[rows]] = 1.0
+        m[b][:, rows] = m_p[b][:, txc[rows]]
+        logs[b][:, rows] = logs_p[b][:, txc[rows]]
+    z_p = m + noise * torch.exp(logs) * noise_scale
+    return z_p, y_mask, attn, m, logs, y_lengths
+
+
 def pcm16(audio, auto_normalize=True):
     """One utterance, float32 numpy array -> int16.  Steps 3-5 of tts_vits.py:204-216 verbatim in numpy."""
     audio = np.asarray(audio, dtype=np.float32)

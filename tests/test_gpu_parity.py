@@ -322,3 +322,113 @@ def test_chunked_decode_is_bit_identical_to_one_shot(name, chunk):
     got = torch.cat(parts, dim=-1)
     assert got.shape == full.shape
     assert torch.equal(got, full)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# next-row widening: alignment expansion + prior sampling (models.py:717-729)
+# ---------------------------------------------------------------------------------------------------------------
+def _load_prior(name):
+    import os
+    import numpy as np
+    from helpers import GOLDEN_DIR
+    d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    return {k: (torch.from_numpy(d[k]) if d[k].ndim else float(d[k])) for k in d.files}
+
+
+@pytest.mark.parametrize("name", ["prior_mini", "prior_long"])
+def test_expand_prior_matches_reference_infer(name):
+    """Gathered statistics, masks and the attention matrix are bit-exact; z_p differs only by expf vs torch.exp (<= 2 ulp
+    of the noise term)."""
+    cfg, sd, _, _ = load_case("mini_mb")
+    eng = _engine(cfg, sd, "bf16")
+    t = _load_prior(name)
+    z_p, y_mask, y_len, attn, (m, logs) = eng.expand_prior(t["m_p"].cuda(), t["logs_p"].cuda(), t["w_ceil"].cuda(), t["noise_scale"],
+                                                           x_mask=t["x_mask"].cuda(), noise=t["noise"].cuda(), want_attn=True,
+                                                           want_stats=True)
+    torch.cuda.synchronize()
+    assert torch.equal(y_mask.cpu(), t["y_mask"])
+    assert torch.equal(attn.cpu(), t["attn"])
+    assert torch.equal(m.cpu(), t["m_exp"]) and torch.equal(logs.cpu(), t["logs_exp"])
+    assert y_len.cpu().tolist() == t["y_mask"].sum((1, 2)).long().tolist()
+    scale = float((t["noise"] * torch.exp(t["logs_exp"]) * t["noise_scale"]).abs().max())
+    assert float((z_p.cpu() - t["z_p"]).abs().max()) < 4e-7 * max(1.0, scale)  # 2 ulp of the largest noise term
+    eng.close()
+
+
+def test_expand_prior_edge_cases_vs_oracle():
+    """Zero-duration utterance (y_length clamps to 1, nothing selected), zero-duration tokens inside an utterance, more
+    than one 128-frame CTA per utterance, and no x_mask."""
+    cfg, sd, _, _ = load_case("mini_mb")
+    eng = _engine(cfg, sd, "bf16")
+    g = torch.Generator().manual_seed(3)
+    B, Cc, Tx = 3, 192, 40
+    m_p, logs_p = torch.randn((B, Cc, Tx), generator=g), torch.randn((B, Cc, Tx), generator=g) * 0.3
+    w = torch.randint(0, 9, (B, 1, Tx), generator=g).float()
+    w[1] = 0
+    w[2, 0, 17:] = 0
+    Ty = int(torch.clamp_min(w.sum((1, 2)), 1).max())
+    assert Ty > 128
+    noise = torch.randn((B, Cc, Ty), generator=g)
+    ref = orc.expand_prior(m_p, logs_p, w, noise, 0.8)
+    z_p, y_mask, y_len, attn, (m, logs) = eng.expand_prior(m_p.cuda(), logs_p.cuda(), w.cuda(), 0.8, noise=noise.cuda(),
+                                                           want_attn=True, want_stats=True)
+    torch.cuda.synchronize()
+    assert torch.equal(y_mask.cpu(), ref[1]) and torch.equal(attn.cpu(), ref[2])
+    assert torch.equal(m.cpu(), ref[3]) and torch.equal(logs.cpu(), ref[4])
+    assert y_len.cpu().tolist() == ref[5].tolist()
+    scale = float((noise * torch.exp(ref[4]) * 0.8).abs().max())
+    assert float((z_p.cpu() - ref[0]).abs().max()) < 4e-7 * max(1.0, scale)
+    # drawn noise: same generator consumption as the reference's randn_like on a [B, Ty, C]-strided tensor
+    torch.manual_seed(11)
+    a = eng.expand_prior(m_p.cuda(), logs_p.cuda(), w.cuda(), 0.8)[0]
+    torch.manual_seed(11)
+    n = torch.randn((B, Ty, Cc), device="cuda").transpose(1, 2)
+    b = eng.expand_prior(m_p.cuda(), logs_p.cuda(), w.cuda(), 0.8, noise=n)[0]
+    assert torch.equal(a, b)
+    eng.close()
+
+
+def test_infer_native_wrapper_matches_oracle_pipeline():
+    """infer_native = reference-style enc_p / dp modules (stubs here: the reference cannot travel to the GPU box) +
+    expand_prior + flow_decode; compared with the oracle run on the same intermediate tensors."""
+    from mb_istft_vits_b200 import infer_native
+
+    cfg, sd, _, _ = load_case("mini_mb")
+    eng = _engine(cfg, sd, "fp32")
+    Cc = cfg["inter_channels"]
+
+    class EncStub(torch.nn.Module):
+        def forward(self, x, x_lengths):
+            gen = torch.Generator().manual_seed(int(x.sum()))
+            B, Tx = x.shape
+            m = torch.randn((B, Cc, Tx), generator=gen).cuda()
+            logs = (torch.randn((B, Cc, Tx), generator=gen) * 0.2).cuda()
+            mask = (torch.arange(Tx)[None, :] < x_lengths.cpu()[:, None]).float().unsqueeze(1).cuda()
+            return m, m * mask, logs * mask, mask
+
+    class DpStub(torch.nn.Module):
+        def forward(self, x, x_mask, g=None):
+            return (x[:, :1, :] * 0.5 + 0.3) * x_mask
+
+    class Net:
+        n_speakers, use_sdp = 0, False
+        enc_p, dp = EncStub(), DpStub()
+
+    x = torch.randint(1, 59, (2, 14))
+    x_len = torch.tensor([14, 9])
+    torch.manual_seed(5)
+    o, o_mb, spec, phase, attn, y_mask, (z, z_p, m_exp, logs_exp), _ = infer_native(Net(), eng, x, x_len, noise_scale=0.667,
+                                                                                   length_scale=1.3)
+    torch.cuda.synchronize()
+    _, m_p, logs_p, x_mask = Net.enc_p(x, x_len)
+    w_ceil = torch.ceil(torch.exp(Net.dp(_, x_mask)) * x_mask * 1.3)
+    Ty = z_p.shape[-1]
+    torch.manual_seed(5)
+    noise = torch.randn((2, Ty, Cc), device="cuda").transpose(1, 2).cpu()
+    ref = orc.expand_prior(m_p.cpu(), logs_p.cpu(), w_ceil.cpu(), noise, 0.667, x_mask.cpu())
+    assert torch.equal(attn.cpu(), ref[2]) and torch.equal(y_mask.cpu(), ref[1])
+    assert float((z_p.cpu() - ref[0]).abs().max()) < 1e-5
+    z_ref, (o_ref, _, _, _) = orc.flow_decode(sd, cfg, ref[0], ref[1])
+    assert (z.cpu() - z_ref).abs().max() < 1e-4
+    assert orc.max_abs_over_peak(o.cpu(), o_ref) < 1e-4
+    eng.close()

@@ -163,8 +163,56 @@ def mint_infer_cases(models, orc):
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
 
 
+def mint_prior_cases(models, orc):
+    """Golden vectors for the alignment expansion + prior sampling (models.py:717-729), taken from inside the reference's
+    own infer(): forward hooks capture what enc_p and dp return, and infer()'s own attn,
+    y_mask, z_p, expanded m_p / logs_p are the expected outputs.  The noise is recorded by wrapping torch.randn_like for
+    the duration of the call."""
+    for name, cname, B, Tx, ns, ls in (("prior_mini", "ljs_mini_mb_istft_vits", 3, 20, 0.667, 1.0),
+                                       ("prior_long", "ljs_mini_mb_istft_vits", 2, 31, 1.0, 2.3)):
+        cfg = cfgs.get_config(cname)
+        sd = synth.make_state_dict(cfg, seed=1234)
+        torch.manual_seed(91)
+        net = build_reference(models, cfg, sd)
+        cap = {}
+        h1 = net.enc_p.register_forward_hook(lambda m, a, out: cap.update(m_p=out[1].detach().clone(), logs_p=out[2].detach().clone(),
+                                                                          x_mask=out[3].detach().clone()))
+        h2 = net.dp.register_forward_hook(lambda m, a, out: cap.update(logw=out.detach().clone()))
+        x = torch.randint(1, 59, (B, Tx))
+        x_len = torch.tensor([Tx] + [max(3, Tx - 4 * (i + 1)) for i in range(B - 1)])
+        torch.manual_seed(2024)
+        _randn_like = torch.randn_like
+
+        def recording_randn_like(t, *a, **k):  # records the prior noise infer() draws; the draw itself is untouched
+            r = _randn_like(t, *a, **k)
+            cap.setdefault("noise", []).append(r.detach().clone())
+            return r
+        torch.randn_like = recording_randn_like
+        try:
+            with torch.no_grad():
+                o, o_mb, spec, phase, attn, y_mask, (z, z_p, m_exp, logs_exp), timings = net.infer(x, x_len, noise_scale=ns, length_scale=ls)
+        finally:
+            torch.randn_like = _randn_like
+        h1.remove(); h2.remove()
+        w_ceil = torch.ceil(torch.exp(cap["logw"]) * cap["x_mask"] * ls)          # models.py:717-718
+        noise = [n for n in cap["noise"] if n.shape == m_exp.shape][-1].contiguous()  # the randn_like(m_p) of models.py:729
+        assert torch.equal(m_exp + noise * torch.exp(logs_exp) * ns, z_p), "noise capture failed"
+        got = orc.expand_prior(cap["m_p"], cap["logs_p"], w_ceil, noise, ns, cap["x_mask"])
+        print(f"{name:12s} Tx={Tx} Ty={z_p.shape[-1]} y_len={got[5].tolist()} oracle-vs-infer: z_p {(got[0] - z_p).abs().max():.1e} "
+              f"attn {(got[2] - attn).abs().max():.0f} mask {(got[1] - y_mask).abs().max():.0f}")
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"),
+                            m_p=cap["m_p"].numpy(), logs_p=cap["logs_p"].numpy(), x_mask=cap["x_mask"].numpy(),
+                            w_ceil=w_ceil.numpy(), noise=noise.numpy(), noise_scale=np.float32(ns),
+                            z_p=z_p.numpy(), y_mask=y_mask.numpy(), attn=attn.numpy(), m_exp=m_exp.numpy(),
+                            logs_exp=logs_exp.numpy())
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "infer":
+    if len(sys.argv) > 1 and sys.argv[1] == "prior":
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import mbistft_oracle as _orc
+        mint_prior_cases(import_reference(), _orc)
+    elif len(sys.argv) > 1 and sys.argv[1] == "infer":
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import mbistft_oracle as _orc
         mint_infer_cases(import_reference(), _orc)
