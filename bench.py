@@ -352,7 +352,7 @@ def run_native(args):
 
     peaks = measured_peaks()
     traffic = {}
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(tp) and args.precision == "bf16" and B == B_PER_GPU and T == T_FRAMES:
         traffic = json.load(open(tp))  # dram__bytes_read+write per launch from the committed ncu capture of this workload
     flops_step = eng.decode_flops(B, T) + eng.flow_flops(B, T)
