@@ -328,6 +328,11 @@ struct ConvArgs {
   int n_phases;       // >1 for the polyphase transposed convolutions
   int shift0[kMaxPhases];  // row offset of tap 0 per phase
   int gate;           // EPI_GATE: weight rows packed as 128-row tiles [64 tanh | 64 sigmoid] of 64 consecutive channels
+  // fused ResBlock conv pair (conv_pair_kernel): w / taps / dil / shift0 describe c1, w2 the second conv (same taps,
+  // dilation 1); bias_h / slope_h are c1's bias and the leaky-relu between the convs; epi is c2's RES epilogue
+  const void* w2;
+  const float* bias_h;
+  float slope_h;
   EpiParams epi;
 };
 

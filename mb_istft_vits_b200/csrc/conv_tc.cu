@@ -755,6 +755,297 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused ResBlock1 conv pair (modules.py:217-224):  x' = x + c2(lrelu(c1(a) + b1)) + b2,  a = lrelu(x) the operand tensor.
+// At 128 channels a k=3 conv is HBM-bound (96 FLOP/B) and even the k=7 / k=11 pairs spend a third of their time moving
+// the intermediate h = lrelu(c1(a)) out to HBM and back (profiles/r02_launch_times_bf16.txt: stage-1 pairs take
+// 302 / 379 / 496 us against 106 / 246 / 388 us of tensor work).  This kernel keeps h on the SM:
+//   * one CTA = all 128 channels x 160 output columns.  c1 accumulates D1[128, 176] for the columns [t0-8, t0+168)
+//     (the halo c2 needs, K <= 17); the epilogue warps turn it into bf16 lrelu(.) rows -- zero outside the utterance,
+//     which is c2's own zero padding -- and store them K-major, 128B-swizzled, into a shared-memory tile that is the
+//     B operand of c2 (tap j = rows [8 - (K-1)/2 + j, +160)).  c2 accumulates D2[128, 160] into one of TWO further TMEM
+//     buffers and the normal RES epilogue drains it: conv 1 and conv 2 of the next tile run while the residual add of
+//     this tile is still streaming to HBM (160 columns is what 176 + 2 x 160 <= 512 TMEM columns allow).
+//   * the tensor core never waits for HBM for the second conv, the intermediate never exists in memory, and the pair
+//     reads a and the residual once and writes its two outputs once.
+//   * warp roles: 8 warps residual add (epilogue 2), 4 warps h tile (epilogue 1), 1 TMA producer, 1 MMA issuer.
+// Geometry handled: Cp_in = C_out = 128 (one channel tile, two k-blocks), stride 1, c2 dilation 1; everything else
+// takes the two-launch path.
+// ------------------------------------------------------------------------------------------------
+constexpr int PAIR_N = 160;      // output columns per tile
+constexpr int PAIR_HALO = 8;     // columns of D1 before / after the outputs
+constexpr int PAIR_N1 = PAIR_N + 2 * PAIR_HALO;  // columns of D1 (176)
+constexpr int PAIR_D2_COL0 = 192, PAIR_D2_STRIDE = 160;  // TMEM: D1 [0,176), D2 buffers [192,352) and [352,512)
+constexpr int PAIR_H_BYTES = 2 * PAIR_N1 * TC_ROW_BYTES;
+
+struct PairRt {
+  int box_rows, n_boxes, slab_stage_bytes, n_slab_stages, n_w_stages;
+  int t_tiles, total_tiles;
+  int h_off, w_off, bar_off;  // byte offsets in (aligned) dynamic smem
+  long long* dbg;             // MBV_TIMELINE=9: CTA 0 clock stamps [tile][8] (debug only)
+};
+
+template <typename Op, int LD, int RH>
+__global__ void __launch_bounds__(TcThreads<EPI_RES>::value, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ CUtensorMap tmW2, const ConvArgs a, const PairRt rt) {
+  using T = typename Op::T;
+  constexpr int KB = 64;
+  constexpr int NEPI = EpiWarps<EPI_RES>::value;  // 12 = 8 residual-add warps (epilogue 2) + 4 h-tile warps (epilogue 1)
+  constexpr int NEPI2 = 8, NEPI1 = NEPI - NEPI2;
+  constexpr int WARP_TMA = NEPI, WARP_MMA = NEPI + 1;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smX = smem;
+  uint8_t* smH = smem + rt.h_off;
+  uint8_t* smW = smem + rt.w_off;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + rt.bar_off);
+  const int iXF = 0, iXE = iXF + rt.n_slab_stages, iWF = iXE + rt.n_slab_stages, iWE = iWF + rt.n_w_stages;
+  const int iD1F = iWE + rt.n_w_stages, iHR = iD1F + 1, iD2F = iHR + 1, iD2E = iD2F + 2, nBars = iD2E + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + nBars);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    for (int i = 0; i < rt.n_slab_stages; ++i) { mbar_init(BAR(iXF + i), 1); mbar_init(BAR(iXE + i), 1); }
+    for (int i = 0; i < rt.n_w_stages; ++i) { mbar_init(BAR(iWF + i), 1); mbar_init(BAR(iWE + i), 1); }
+    mbar_init(BAR(iD1F), 1);
+    mbar_init(BAR(iHR), NEPI1);
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(iD2F + i), 1); mbar_init(BAR(iD2E + i), NEPI2); }
+    fence_barrier_init();
+  }
+  if (warp == WARP_MMA) tmem_alloc(smem_u32(tmem_ptr_smem), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  const int taps = a.taps;
+  const uint32_t slab_bytes = (uint32_t)rt.n_boxes * rt.box_rows * TC_ROW_BYTES;
+  const uint32_t w_tile_bytes = TC_M * TC_ROW_BYTES;
+
+  if (warp == WARP_TMA) {
+    // ===================== TMA producer: per tile  [slab kb, W1 taps of kb] x 2, then W2 (kb, tap) =====================
+    int sx = 0, sw = 0;
+    uint32_t px = 0, pw = 0;
+    for (int tile = blockIdx.x; tile < rt.total_tiles; tile += gridDim.x) {
+      const int tt = tile % rt.t_tiles, b = tile / rt.t_tiles;
+      const int xrow0 = tt * PAIR_N - PAIR_HALO + a.shift0[0];
+      for (int kb = 0; kb < 2; ++kb) {
+        mbar_wait(BAR(iXE + sx), px ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(BAR(iXF + sx), slab_bytes);
+          const uint32_t dst = smem_u32(smX + (size_t)sx * rt.slab_stage_bytes);
+          for (int i = 0; i < rt.n_boxes; ++i)
+            tma_load_3d(dst + (uint32_t)(i * rt.box_rows) * TC_ROW_BYTES, &tmX, BAR(iXF + sx), kb * KB,
+                        xrow0 + i * rt.box_rows, b);
+        }
+        __syncwarp();
+        if (++sx == rt.n_slab_stages) { sx = 0; px ^= 1; }
+        for (int tap = 0; tap < taps; ++tap) {
+          mbar_wait(BAR(iWE + sw), pw ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(BAR(iWF + sw), w_tile_bytes);
+            tma_load_2d(smem_u32(smW + (size_t)sw * TC_M * TC_ROW_BYTES), &tmW1, BAR(iWF + sw), kb * KB, tap * TC_M);
+          }
+          __syncwarp();
+          if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
+        }
+      }
+      for (int kb = 0; kb < 2; ++kb)
+        for (int tap = 0; tap < taps; ++tap) {
+          mbar_wait(BAR(iWE + sw), pw ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(BAR(iWF + sw), w_tile_bytes);
+            tma_load_2d(smem_u32(smW + (size_t)sw * TC_M * TC_ROW_BYTES), &tmW2, BAR(iWF + sw), kb * KB, tap * TC_M);
+          }
+          __syncwarp();
+          if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
+        }
+    }
+  } else if (warp == WARP_MMA) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t fmt = (Op::kPrec == 3) ? 0u : 1u;
+    const uint32_t idesc1 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(PAIR_N1 >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(PAIR_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    const uint32_t tap_step1 = (uint32_t)(a.dil * TC_ROW_BYTES) >> 4;
+    const uint32_t h_row0 = (uint32_t)(PAIR_HALO - (taps - 1) / 2);
+    int sx = 0, sw = 0, d2 = 0;
+    uint32_t px = 0, pw = 0, ph = 0, pd2 = 0;
+    for (int tile = blockIdx.x; tile < rt.total_tiles; tile += gridDim.x) {
+      // ---- conv 1 -> D1 (TMEM columns [0, 176)); D1 is free: the previous tile's epilogue 1 signalled HR before conv 2
+      uint32_t accum = 0;
+      long long* dbg = (rt.dbg && blockIdx.x == 0 && lane == 0 && tile / (int)gridDim.x < 16) ? rt.dbg + (tile / gridDim.x) * 8 : nullptr;
+      if (dbg) dbg[0] = clock64();
+      for (int kb = 0; kb < 2; ++kb) {
+        mbar_wait(BAR(iXF + sx), px);
+        tc_fence_after();
+        uint32_t x_lo = desc_lo(smem_u32(smX + (size_t)sx * rt.slab_stage_bytes));
+        for (int tap = 0; tap < taps; ++tap) {
+          mbar_wait(BAR(iWF + sw), pw);
+          tc_fence_after();
+          const uint32_t w_lo = desc_lo(smem_u32(smW + (size_t)sw * TC_M * TC_ROW_BYTES));
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc_mma<2>(tmem_base, desc64(w_lo + 2 * k), desc64(x_lo + 2 * k), idesc1, (k == 0) ? accum : 1u);
+            tc_commit(BAR(iWE + sw));
+          }
+          __syncwarp();
+          accum = 1;
+          x_lo += tap_step1;
+          if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
+        }
+        if (elect_one()) tc_commit(BAR(iXE + sx));
+        __syncwarp();
+        if (++sx == rt.n_slab_stages) { sx = 0; px ^= 1; }
+      }
+      if (elect_one()) tc_commit(BAR(iD1F));
+      __syncwarp();
+      if (dbg) dbg[1] = clock64();
+      // ---- conv 2 -> D2 buffer d2: needs the h tile (epilogue 1 of this tile) and that buffer drained (epilogue 2 of tile i-2)
+      mbar_wait(BAR(iHR), ph);
+      mbar_wait(BAR(iD2E + d2), pd2 ^ 1);
+      tc_fence_after();
+      if (dbg) dbg[2] = clock64();
+      accum = 0;
+      for (int kb = 0; kb < 2; ++kb) {
+        const uint32_t h_lo = desc_lo(smem_u32(smH + (size_t)kb * PAIR_N1 * TC_ROW_BYTES) + h_row0 * TC_ROW_BYTES);
+        for (int tap = 0; tap < taps; ++tap) {
+          mbar_wait(BAR(iWF + sw), pw);
+          tc_fence_after();
+          const uint32_t w_lo = desc_lo(smem_u32(smW + (size_t)sw * TC_M * TC_ROW_BYTES));
+          const uint32_t b_lo = h_lo + (uint32_t)tap * (TC_ROW_BYTES >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma<2>(tmem_base + PAIR_D2_COL0 + d2 * PAIR_D2_STRIDE, desc64(w_lo + 2 * k), desc64(b_lo + 2 * k), idesc2, (k == 0) ? accum : 1u);
+            tc_commit(BAR(iWE + sw));
+          }
+          __syncwarp();
+          accum = 1;
+          if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
+        }
+      }
+      if (elect_one()) tc_commit(BAR(iD2F + d2));
+      __syncwarp();
+      if (dbg) dbg[3] = clock64();
+      ph ^= 1;
+      if (++d2 == 2) { d2 = 0; pd2 ^= 1; }
+    }
+  } else if (warp >= NEPI2 && warp < NEPI) {
+    // ===================== epilogue-1 warps (4): D1 -> h tile =====================
+    // h = lrelu(D1 + b1) in the operand type, zero outside the utterance, into the c2 operand tile.  These warps run
+    // ahead of epilogue 2: tile i+1's h is written while tile i's residual add is still streaming to HBM.  The h tile is
+    // free by then: D1 of tile i+1 being complete implies conv 2 of tile i (issued earlier) has finished reading it.
+    const int q = warp & 3;
+    const int n = q * 32 + lane;
+    const float bias_h = a.bias_h[n], slope_h = a.slope_h;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t chl = (uint32_t)((q & 1) * 32 + lane);   // channel inside k-block q>>1
+    const uint32_t h_thread = smem_u32(smH) + (uint32_t)(q >> 1) * (PAIR_N1 * TC_ROW_BYTES) + (chl & 7u) * 2u;
+    const uint32_t chq = chl >> 3;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < rt.total_tiles; tile += gridDim.x) {
+      const int t0 = (tile % rt.t_tiles) * PAIR_N;
+      long long* dbg = (rt.dbg && blockIdx.x == 0 && q == 0 && lane == 0 && tile / (int)gridDim.x < 16) ? rt.dbg + (tile / gridDim.x) * 8 : nullptr;
+      mbar_wait(BAR(iD1F), ph);
+      tc_fence_after();
+      if (dbg) dbg[4] = clock64();
+      // two TMEM loads in flight: chunk c+32 is fetched while chunk c is converted and stored
+      float accA[32], accB[32];
+      tmem_ld32(taddr, accA);
+      auto emit = [&](const float* acc, int c) {
+        const int t_abs0 = t0 - PAIR_HALO + c;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float v = acc[i] + bias_h;
+          v = fmaxf(v, v * slope_h);
+          const int t_abs = t_abs0 + i;
+          if (t_abs < 0 || t_abs >= a.L_out) v = 0.f;
+          const uint32_t addr = h_thread + (uint32_t)(c + i) * TC_ROW_BYTES + ((chq ^ (uint32_t)(i & 7)) << 4);
+          unsigned short bits;
+          if constexpr (Op::kPrec == 3) bits = __half_as_ushort(to_half_sat(v));
+          else bits = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+          if (c + i < PAIR_N1) asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(bits) : "memory");
+        }
+      };
+#pragma unroll 1
+      for (int c = 0; c < PAIR_N1; c += 64) {
+        tmem_ld_wait();
+        if (c + 32 < PAIR_N1) tmem_ld32(taddr + (uint32_t)(c + 32), accB);
+        emit(accA, c);
+        if (c + 32 < PAIR_N1) {
+          tmem_ld_wait();
+          if (c + 64 < PAIR_N1) tmem_ld32(taddr + (uint32_t)(c + 64), accA);
+          emit(accB, c + 32);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(iHR));
+      if (dbg) dbg[5] = clock64();
+      ph ^= 1;
+    }
+  } else if (warp < NEPI2) {
+    // ===================== epilogue-2 warps (8): the ResBlock residual add on D2 =====================
+    const int q = warp & 3, grp = warp >> 2;
+    const int n = q * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + PAIR_D2_COL0;
+    uint32_t ph = 0;
+    int d2 = 0;
+    float xcur[32];
+    for (int tile = blockIdx.x; tile < rt.total_tiles; tile += gridDim.x) {
+      const int tt = tile % rt.t_tiles, b = tile / rt.t_tiles;
+      const int t0 = tt * PAIR_N;
+      const int t_lim = min(a.L_out, t0 + PAIR_N);
+      long long* dbg = (rt.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && tile / (int)gridDim.x < 16) ? rt.dbg + (tile / gridDim.x) * 8 : nullptr;
+      {  // ask L2 for the residual rows of this warp's chunks of the NEXT tile (demand loads then hit L2)
+        const int tile_n = tile + (int)gridDim.x;
+        if (tile_n < rt.total_tiles && a.epi.xin != nullptr) {
+          const int bn = tile_n / rt.t_tiles, t0n = (tile_n % rt.t_tiles) * PAIR_N;
+          for (int c = grp * 32; c < PAIR_N; c += 64) {
+            const int t = t0n + c + lane;
+            if (t < a.L_out) {
+              const size_t off = ((size_t)bn * a.epi.rows_res + t) * a.epi.ld + (n - lane);
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(a.epi.xin) + off * (RH != 0 ? 2 : 4)));
+            }
+          }
+        }
+      }
+      mbar_wait(BAR(iD2F + d2), ph);
+      tc_fence_after();
+      if (dbg) dbg[6] = clock64();
+      for (int c = grp * 32; c < PAIR_N; c += 64) {
+        float acc[32];
+        tmem_ld32(taddr + (uint32_t)(d2 * PAIR_D2_STRIDE + c), acc);
+        const int t_first = t0 + c;
+        const bool live = t_first < t_lim;
+        if (live) epi_prefetch<EPI_RES, LD, RH>(a.epi, b, n, t_first, min(t_lim - t_first, 32), xcur);
+        tmem_ld_wait();
+        if (live) tc_epilogue32<Op, EPI_RES, LD, RH>(a.epi, b, n, 0, t_first, min(t_lim - t_first, 32), acc, nullptr, xcur);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(iD2E + d2));
+      if (dbg) dbg[7] = clock64();
+      if (++d2 == 2) { d2 = 0; ph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -990,6 +1281,126 @@ cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStr
   else if (a.epi.res_half) e = cudaErrorInvalidValue;
   else e = dispatch<OpTF32>(a, p, rt, st, false, a.epi.mode, a.epi.ld, 0);
   if (rt.dbg && e == cudaSuccess) timeline_dump(a, p, rt.dbg, st);
+  return e;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// fused ResBlock conv pair: plan + launch
+// ------------------------------------------------------------------------------------------------
+const char* tc_make_pair_plan(int prec, const ConvArgs& a, int num_sms, TcPairPlan* plan) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return "cuTensorMapEncodeTiled entry point unavailable";
+  if (prec < 2) return "conv pair: 16-bit operand types only";
+  if (a.Cp_in != 128 || a.N_total != 128 || a.n_phases != 1) return "conv pair: 128 channels, stride 1 only";
+  if ((a.taps - 1) / 2 > PAIR_HALO || (a.taps & 1) == 0) return "conv pair: odd kernel size <= 17";
+  const int slab_rows = PAIR_N1 + (a.taps - 1) * a.dil;
+  plan->n_boxes = slab_rows > 256 ? 2 : 1;
+  plan->box_rows = ((slab_rows + plan->n_boxes - 1) / plan->n_boxes + 7) / 8 * 8;
+  if (plan->box_rows > 256) return "conv pair: activation slab exceeds two 256-row TMA boxes";
+  plan->slab_stage_bytes = ((plan->n_boxes * plan->box_rows * TC_ROW_BYTES + 1023) / 1024) * 1024;
+  plan->n_slab_stages = 2;
+  plan->h_off = plan->n_slab_stages * plan->slab_stage_bytes;
+  plan->w_off = plan->h_off + PAIR_H_BYTES;
+  const int budget = 225 * 1024 - plan->w_off;
+  plan->n_w_stages = budget / (TC_M * TC_ROW_BYTES);
+  if (plan->n_w_stages > 10) plan->n_w_stages = 10;
+  if (plan->n_w_stages < 3) return "conv pair: not enough shared memory for the weight ring";
+  plan->bar_off = plan->w_off + plan->n_w_stages * TC_M * TC_ROW_BYTES;
+  const int nbars = 2 * plan->n_slab_stages + 2 * plan->n_w_stages + 6;
+  plan->smem_bytes = 1024 + plan->bar_off + nbars * 8 + 16;
+  plan->t_tiles = (a.L_out + PAIR_N - 1) / PAIR_N;
+  plan->total_tiles = a.B * plan->t_tiles;
+  plan->grid = plan->total_tiles < num_sms ? plan->total_tiles : num_sms;
+  const CUtensorMapDataType dt = prec == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)a.Cp_in, (cuuint64_t)a.L_in, (cuuint64_t)a.B};
+    cuuint64_t strides[2] = {(cuuint64_t)a.x_ld * 2, (cuuint64_t)a.L_in * a.x_ld * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)plan->box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&plan->tmA, dt, 3, const_cast<void*>(a.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return "cuTensorMapEncodeTiled failed for the activation map";
+  }
+  for (int which = 0; which < 2; ++which) {
+    cuuint64_t dims[2] = {(cuuint64_t)a.Cp_in, (cuuint64_t)a.taps * a.N_total};
+    cuuint64_t strides[1] = {(cuuint64_t)a.Cp_in * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)TC_M};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(which ? &plan->tmB2 : &plan->tmB, dt, 2, const_cast<void*>(which ? a.w2 : a.w), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return "cuTensorMapEncodeTiled failed for a weight map";
+  }
+  return nullptr;
+}
+
+template <typename Op, int LD, int RH>
+static cudaError_t launch_pair_one(const ConvArgs& a, const TcPairPlan& p, const PairRt& rt, cudaStream_t st, bool set_attr) {
+  auto k = conv_pair_kernel<Op, LD, RH>;
+  if (set_attr) return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.grid);
+  cfg.blockDim = dim3(TcThreads<EPI_RES>::value);
+  cfg.dynamicSmemBytes = p.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k, p.tmA, p.tmB, p.tmB2, a, rt);
+}
+
+static cudaError_t pair_dispatch(int prec, const ConvArgs& a, const TcPairPlan& p, const PairRt& rt, cudaStream_t st, bool set_attr) {
+  const int ld = a.epi.ld, rh = a.epi.res_half;
+  if (prec == 2 && rh == 1) return ld == 128 ? launch_pair_one<OpBF16, 128, 1>(a, p, rt, st, set_attr) : launch_pair_one<OpBF16, 0, 1>(a, p, rt, st, set_attr);
+  if (prec == 2 && rh == 0) return launch_pair_one<OpBF16, 0, 0>(a, p, rt, st, set_attr);
+  if (prec == 3 && rh == 2) return ld == 128 ? launch_pair_one<OpF16, 128, 2>(a, p, rt, st, set_attr) : launch_pair_one<OpF16, 0, 2>(a, p, rt, st, set_attr);
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t tc_pair_set_attributes() {
+  ConvArgs a{};
+  TcPairPlan p{};
+  PairRt rt{};
+  const int combos[5][3] = {{2, 128, 1}, {2, 0, 1}, {2, 0, 0}, {3, 128, 2}, {3, 0, 2}};
+  for (auto& c : combos) {
+    a.epi.ld = c[1];
+    a.epi.res_half = c[2];
+    cudaError_t e = pair_dispatch(c[0], a, p, rt, nullptr, true);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+cudaError_t launch_conv_pair(int prec, const ConvArgs& a, const TcPairPlan& p, cudaStream_t st) {
+  PairRt rt;
+  rt.box_rows = p.box_rows; rt.n_boxes = p.n_boxes; rt.slab_stage_bytes = p.slab_stage_bytes;
+  rt.n_slab_stages = p.n_slab_stages; rt.n_w_stages = p.n_w_stages; rt.t_tiles = p.t_tiles; rt.total_tiles = p.total_tiles;
+  rt.h_off = p.h_off; rt.w_off = p.w_off; rt.bar_off = p.bar_off;
+  static long long* dbg = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) {
+    const char* e = getenv("MBV_TIMELINE");
+    dbg_on = (e && atoi(e) == 9) ? 1 : 0;
+    if (dbg_on) { cudaMalloc(&dbg, 16 * 8 * sizeof(long long)); cudaMemset(dbg, 0, 16 * 8 * sizeof(long long)); }
+  }
+  rt.dbg = dbg_on ? dbg : nullptr;
+  cudaError_t e = pair_dispatch(prec, a, p, rt, st, false);
+  if (dbg_on && e == cudaSuccess) {
+    cudaStreamSynchronize(st);
+    long long hb[16 * 8];
+    cudaMemcpy(hb, dbg, sizeof(hb), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[pair timeline] k%d d%d slab_rows/box %d x%d w_stages %d tiles/CTA %d\n", a.taps, a.dil, p.box_rows, p.n_boxes,
+            p.n_w_stages, (p.total_tiles + p.grid - 1) / p.grid);
+    const long long t0 = hb[0];
+    for (int i = 0; i < 8; ++i)
+      fprintf(stderr, "  tile %2d  mma1 %7lld..%7lld | mma2 %7lld..%7lld | epi1 %7lld..%7lld | epi2 %7lld..%7lld\n", i, hb[8 * i] - t0,
+              hb[8 * i + 1] - t0, hb[8 * i + 2] - t0, hb[8 * i + 3] - t0, hb[8 * i + 4] - t0, hb[8 * i + 5] - t0, hb[8 * i + 6] - t0,
+              hb[8 * i + 7] - t0);
+    cudaMemset(dbg, 0, sizeof(hb));
+  }
   return e;
 }
 

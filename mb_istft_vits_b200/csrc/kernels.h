@@ -28,6 +28,15 @@ struct TcPlan {
 const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, TcPlan* plan);
 cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& plan, cudaStream_t st);
 cudaError_t tc_set_attributes();
+// fused ResBlock1 conv pair (c1 -> lrelu -> c2 -> residual add), 128-channel stages: see conv_tc.cu
+struct TcPairPlan {
+  CUtensorMap tmA, tmB, tmB2;   // activations, c1 weights, c2 weights
+  int box_rows, n_boxes, slab_stage_bytes, n_slab_stages, n_w_stages;
+  int t_tiles, total_tiles, h_off, w_off, bar_off, smem_bytes, grid;
+};
+const char* tc_make_pair_plan(int prec, const ConvArgs& a, int num_sms, TcPairPlan* plan);
+cudaError_t launch_conv_pair(int prec, const ConvArgs& a, const TcPairPlan& plan, cudaStream_t st);
+cudaError_t tc_pair_set_attributes();
 // cuTensorMapEncodeTiled through the runtime's driver entry point (nullptr if unavailable); shared with tail.cu
 void* tc_tensormap_encoder();
 

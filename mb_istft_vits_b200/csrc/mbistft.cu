@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -125,6 +126,8 @@ struct mbv_handle {
   struct PlanKey { int B, T; void* ws; int kind; bool operator<(const PlanKey& o) const {
     if (B != o.B) return B < o.B; if (T != o.T) return T < o.T; if (ws != o.ws) return ws < o.ws; return kind < o.kind; } };
   std::map<PlanKey, std::vector<TcPlan>> plan_cache;
+  std::map<PlanKey, std::vector<TcPairPlan>> pair_cache;
+  int use_pair = 0;  // fused ResBlock conv pairs on 128-channel stages (MBV_FLAG_FUSED_PAIR; off by default)
 
   // per-launch device timing (mbv_set_profiling)
   bool profiling = false;
@@ -404,6 +407,8 @@ extern "C" int mbv_create(const mbv_config* cfg, mbv_handle** out) {
   h->num_sms = prop.multiProcessorCount;
   if (prop.major != 10) return fail(h, MBV_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", c.device, prop.major, prop.minor);
   if (h->prec != MBV_PREC_FP32) CUDA_TRY(h, tc_set_attributes());
+  if (h->prec >= MBV_PREC_BF16) CUDA_TRY(h, tc_pair_set_attributes());
+  h->use_pair = (c.flags & MBV_FLAG_FUSED_PAIR) ? 1 : 0;
   return MBV_OK;
 }
 
@@ -682,8 +687,9 @@ struct Ctx {
   mbv_handle* h;
   cudaStream_t st;
   std::vector<TcPlan>* plans;
+  std::vector<TcPairPlan>* pair_plans = nullptr;
   bool plans_valid;
-  size_t plan_idx = 0;
+  size_t plan_idx = 0, pair_idx = 0;
   int launches = 0;
 };
 
@@ -734,6 +740,40 @@ int run_conv(Ctx& cx, const ConvLayer& L, const void* x, int B, int L_in, int L_
     ProfScope prof(cx, 0, h->profiling ? desc : "");
     CUDA_TRY(h, launch_conv_tc(h->prec, a, plan, cx.st));
   }
+  cx.launches++;
+  return MBV_OK;
+}
+
+// fused ResBlock1 conv pair: x' = xin + c2(lrelu(c1(a_in))) (conv_pair_kernel); epi is c2's RES epilogue
+bool pair_ok(const mbv_handle* h, const ConvLayer& c1, const ConvLayer& c2) {
+  return h->use_pair && h->prec >= MBV_PREC_BF16 && !(h->cfg.flags & MBV_FLAG_FORCE_SIMT) && c1.Cp_in == 128 && c1.N_total == 128 &&
+         c2.Cp_in == 128 && c2.N_total == 128 && c1.taps == c2.taps && c2.dil == 1 && (c1.taps & 1) && (c1.taps - 1) / 2 <= 8 &&
+         c1.n_phases == 1 && c2.n_phases == 1;
+}
+
+int run_pair(Ctx& cx, const ConvLayer& c1, const ConvLayer& c2, const void* x, int B, int L, const EpiParams& epi, float slope_h) {
+  mbv_handle* h = cx.h;
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x; a.x_ld = c1.Cp_in; a.w = c1.w; a.w2 = c2.w; a.B = B; a.L_in = L; a.L_out = L; a.Cp_in = c1.Cp_in; a.N_total = c1.N_total;
+  a.taps = c1.taps; a.dil = c1.dil; a.n_phases = 1; a.gate = 0;
+  a.shift0[0] = c1.shift0[0];
+  a.bias_h = c1.bias; a.slope_h = slope_h;
+  a.epi = epi;
+  if (a.epi.bias == nullptr) { a.epi.bias = c2.bias; a.epi.bias_bs = 0; }
+  TcPairPlan plan;
+  if (cx.plans_valid && cx.pair_idx < cx.pair_plans->size()) {
+    plan = (*cx.pair_plans)[cx.pair_idx];
+  } else {
+    const char* msg = tc_make_pair_plan(h->prec, a, h->num_sms, &plan);
+    if (msg) return fail(h, MBV_ERR_CUDA, "%s", msg);
+    cx.pair_plans->push_back(plan);
+  }
+  cx.pair_idx++;
+  char desc[56];
+  snprintf(desc, sizeof(desc), "pair m1 Ci%d N%d k%d d%d ph1 L%d nt240", c1.Cp_in, c1.N_total, c1.taps, c1.dil, L);
+  ProfScope prof(cx, 0, h->profiling ? desc : "");
+  CUDA_TRY(h, launch_conv_pair(h->prec, a, plan, cx.st));
   cx.launches++;
   return MBV_OK;
 }
@@ -892,7 +932,14 @@ int run_decode(Ctx& cx, const DecBufs& d, const float* z, const float* z_mask, c
           e.xout = h->single ? nullptr : s.xr;
         }
         const void* conv_in;
-        if (c.resblock_type == 1) {
+        if (c.resblock_type == 1 && pair_ok(h, h->rb_c1[i][j][p], h->rb_c2[i][j][p])) {
+          // one launch for the conv pair; the operand copies ping-pong (c1 of a neighbouring tile still reads a_in's halo
+          // rows while this tile's epilogue writes its output)
+          void* a_out = (p & 1) ? s.hop : s.ar;
+          if (!final_conv) { e.act[0] = a_out; e.n_act = 1; }
+          if ((rc = run_pair(cx, h->rb_c1[i][j][p], h->rb_c2[i][j][p], a_in, B, L, e, 0.1f))) return rc;
+          a_in = a_out;
+        } else if (c.resblock_type == 1) {
           EpiParams e1 = epi_base(EPI_ACT, C, L);
           e1.slope = 0.1f; e1.act[0] = s.hop; e1.n_act = 1;
           if ((rc = run_conv(cx, h->rb_c1[i][j][p], a_in, B, L, L, e1))) return rc;
@@ -946,13 +993,15 @@ Ctx make_ctx(mbv_handle* h, int B, int T, void* ws, int kind, void* stream) {
   mbv_handle::PlanKey key{B, T, ws, kind};
   auto it = h->plan_cache.find(key);
   if (it == h->plan_cache.end()) {
-    if (h->plan_cache.size() > 64) h->plan_cache.clear();
+    if (h->plan_cache.size() > 64) { h->plan_cache.clear(); h->pair_cache.clear(); }
     it = h->plan_cache.emplace(key, std::vector<TcPlan>()).first;
     cx.plans_valid = false;
   } else {
     cx.plans_valid = true;
   }
   cx.plans = &it->second;
+  cx.pair_plans = &h->pair_cache[key];
+  if (!cx.plans_valid) cx.pair_plans->clear();
   return cx;
 }
 

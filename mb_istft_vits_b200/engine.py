@@ -127,13 +127,17 @@ class Engine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _alloc_outputs(self, B, T, want_mb, want_spec):
+    def _alloc_outputs(self, B, T, want_mb, want_spec, wav=None):
         v = self.cfg["variant"]
         S = self.cfg["subbands"] if v != "istft" else 1
         L = T
         for u in self.cfg["upsample_rates"]:
             L *= u
-        wav = torch.empty((B, 1, self.spf * T), dtype=torch.float32, device=self.device)
+        if wav is None:
+            wav = torch.empty((B, 1, self.spf * T), dtype=torch.float32, device=self.device)
+        elif (tuple(wav.shape) != (B, 1, self.spf * T) or wav.dtype != torch.float32 or not wav.is_contiguous()
+              or wav.device != self.device):
+            raise ValueError("out_wav must be a contiguous fp32 [B, 1, samples] tensor on the engine's device")
         o_mb = None
         if want_mb and v != "istft":
             o_mb = torch.empty((B, S, (4 if v == "mb" else 16) * L), dtype=torch.float32, device=self.device)
@@ -168,13 +172,15 @@ class Engine:
                                         self._stream()))
         return wav, o_mb, spec, phase
 
-    def flow_decode(self, z_p, y_mask, g=None, want_z=True, want_mb=False, want_spec=False):
+    def flow_decode(self, z_p, y_mask, g=None, want_z=True, want_mb=False, want_spec=False, out_wav=None):
+        """out_wav: optional preallocated [B,1,samples] fp32 device tensor to write the waveform into (serving loops that
+        must not allocate per step)."""
         B, Cz, T = z_p.shape
         z_p = self._prep(z_p)
         y_mask = self._prep(y_mask, (B, 1, T))
         g = self._prep(g)
         z = torch.empty_like(z_p) if want_z else None
-        wav, o_mb, spec, phase = self._alloc_outputs(B, T, want_mb, want_spec)
+        wav, o_mb, spec, phase = self._alloc_outputs(B, T, want_mb, want_spec, wav=out_wav)
         ws, nws = self._workspace(B, T)
         self._check(self.lib.mbv_flow_decode(self._h, self._ptr(z_p), self._ptr(y_mask), self._ptr(g), self._ptr(z),
                                              self._ptr(wav), self._ptr(o_mb), self._ptr(spec), self._ptr(phase), B, T,

@@ -16,12 +16,13 @@ from .modules import NativeDecoder, NativeFlow
 
 
 class HostStream:
-    def __init__(self, engine, depth: int = 2, fused: bool = False):
+    def __init__(self, engine, depth: int = 2, fused: bool = False, graphs: bool = True):
         """fused=False: the two drop-in module calls with `z * y_mask` between them, exactly as infer() makes them.
         fused=True: one `Engine.flow_decode` call (mbv_flow_decode: the same arithmetic without the round trip of z
         through its fp32 NCT boundary layout)."""
         self.engine = engine
         self.fused = fused
+        self.graphs = graphs and fused  # fused mode only: every slot replays one captured CUDA graph (static buffers)
         self.dev = engine.device
         self.flow = NativeFlow(engine)
         self.dec = NativeDecoder(engine, want_mb=False, want_spec=False)
@@ -38,8 +39,23 @@ class HostStream:
             s = {"zp": torch.empty(zp_host.shape, dtype=torch.float32, device=self.dev),
                  "m": torch.empty(mask_host.shape, dtype=torch.float32, device=self.dev),
                  "g": None if g_host is None else torch.empty(g_host.shape, dtype=torch.float32, device=self.dev),
-                 "wav": None,
+                 "wav": torch.empty((zp_host.shape[0], 1, self.engine.spf * zp_host.shape[2]), dtype=torch.float32,
+                                    device=self.dev),
                  "ev_in": torch.cuda.Event(), "ev_cmp": torch.cuda.Event(), "ev_out": torch.cuda.Event()}
+            s["graph"] = None
+            if self.graphs:
+                # the slot's buffers are static, so its whole launch sequence is captured once and replayed per batch
+                self.engine._workspace(zp_host.shape[0], zp_host.shape[2])
+                with torch.cuda.stream(self.s_cmp):
+                    s["zp"].zero_(); s["m"].fill_(1.0)
+                    if s["g"] is not None:
+                        s["g"].zero_()
+                    self.engine.flow_decode(s["zp"], s["m"], s["g"], want_z=False, out_wav=s["wav"])  # tensor maps, attributes
+                self.s_cmp.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=self.s_cmp):
+                    self.engine.flow_decode(s["zp"], s["m"], s["g"], want_z=False, out_wav=s["wav"])
+                s["graph"] = gr
             s["ev_cmp"].record(self.s_cmp)
             s["ev_out"].record(self.s_out)
             self.slots[i % self.depth] = s
@@ -60,13 +76,16 @@ class HostStream:
             s["ev_in"].record(self.s_in)
         with torch.cuda.stream(self.s_cmp):
             self.s_cmp.wait_event(s["ev_in"])
-            if self.fused:
-                o = self.engine.flow_decode(s["zp"], s["m"], s["g"], want_z=False)[1]
+            self.s_cmp.wait_event(s["ev_out"])  # this slot's waveform buffer has been downloaded
+            if s["graph"] is not None:
+                s["graph"].replay()
+                o = s["wav"]
+            elif self.fused:  # writes into the slot's preallocated buffer: no allocation per step
+                o = self.engine.flow_decode(s["zp"], s["m"], s["g"], want_z=False, out_wav=s["wav"])[1]
             else:
                 z = self.flow(s["zp"], s["m"], g=s["g"], reverse=True)
                 o = self.dec(z * s["m"], g=s["g"])[0]
-            o.record_stream(self.s_out)
-            s["wav"] = o
+                o.record_stream(self.s_out)
             s["ev_cmp"].record(self.s_cmp)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(s["ev_cmp"])

@@ -82,6 +82,20 @@ def test_fp16_single_stream_path_snr(name):
     eng.close()
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_fused_resblock_pair_kernel_matches_two_launch_path(prec):
+    """MBV_FLAG_FUSED_PAIR: c1 -> lrelu -> c2 -> residual add of a 128-channel ResBlock in one kernel (the intermediate stays
+    in shared memory).  Same operands, same fp32 accumulation per conv; only the accumulation order inside the tensor
+    core tiles differs, so the two paths agree far better than either agrees with the fp32 reference."""
+    from mb_istft_vits_b200 import lib as L
+    for case in ("mb", "ms_spk", "mini_mb", "mb_long"):
+        cfg, sd, t, meta = load_case(case)
+        ref = _run(_engine(cfg, sd, prec, 0), t)
+        got = _run(_engine(cfg, sd, prec, L.FLAG_FUSED_PAIR), t)
+        assert orc.snr_db(got[1], ref[1]) > (50.0 if prec == "bf16" else 58.0), case
+        assert orc.snr_db(got[1], t["o"]) > 40.0, case
+
+
 def test_fp16_tensor_core_path_vs_cuda_core_path():
     """fp16 operands through tcgen05 with single-stream epilogues vs the CUDA-core kernel with a separately stored
     (plain fp16) residual stream: different residual bookkeeping, same arithmetic up to fp16 re-rounding."""
@@ -431,4 +445,30 @@ def test_infer_native_wrapper_matches_oracle_pipeline():
     z_ref, (o_ref, _, _, _) = orc.flow_decode(sd, cfg, ref[0], ref[1])
     assert (z.cpu() - z_ref).abs().max() < 1e-4
     assert orc.max_abs_over_peak(o.cpu(), o_ref) < 1e-4
+    eng.close()
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_host_stream_pipeline_returns_the_same_waveforms(fused):
+    """HostStream (copy-in / compute / copy-out streams, ring of two slots, one CUDA graph per slot when fused): five
+    different batches through two slots must come back exactly as direct calls produce them."""
+    from mb_istft_vits_b200 import HostStream
+    cfg, sd, _, _ = load_case("mini_mb")
+    eng = _engine(cfg, sd, "bf16")
+    hs = HostStream(eng, depth=2, fused=fused)
+    B, T = 2, 30
+    ins, outs, events = [], [], []
+    for i in range(5):
+        z_p, mask, _ = synth.make_latents(cfg, B, T, seed=100 + i, lengths=[T, T - 3 * i])
+        ins.append((z_p.pin_memory(), mask.pin_memory()))
+        outs.append(torch.zeros((B, 1, 256 * T)).pin_memory())
+        events.append(hs.submit(ins[-1][0], ins[-1][1], outs[-1]))
+    hs.drain()
+    for i in range(5):
+        assert events[i].query()
+        z, wav, _, _, _ = eng.flow_decode(ins[i][0].cuda(), ins[i][1].cuda())
+        if fused:
+            assert torch.equal(outs[i], wav.cpu()), i
+        else:  # module calls round-trip z through its fp32 boundary layout: same arithmetic, same result
+            assert orc.snr_db(outs[i], wav.cpu()) > 80.0, i
     eng.close()
