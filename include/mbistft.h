@@ -123,6 +123,13 @@ int mbv_workspace_bytes(mbv_handle* h, int32_t B, int32_t T, size_t* bytes);
 int mbv_flow_reverse(mbv_handle* h, const float* z_p, const float* y_mask, const float* g,
                      float* z_out, int32_t B, int32_t T, void* ws, size_t ws_bytes, void* stream);
 
+/* NEXT-row widening (the flow half of voice conversion, models.py:790-798):
+ * ResidualCouplingBlock.forward(x, x_mask, g, reverse=False) (models.py:207-210) -- RCL0, Flip, RCL1, Flip, ... with
+ * the mean-only coupling x1 <- m + x1 * mask (modules.py:345-347); the log-determinant is discarded as in the reference.
+ * Same tensors and workspace as mbv_flow_reverse; mbv_flow_reverse(mbv_flow_forward(x)) == x * mask up to rounding. */
+int mbv_flow_forward(mbv_handle* h, const float* x, const float* y_mask, const float* g, float* z_out,
+                     int32_t B, int32_t T, void* ws, size_t ws_bytes, void* stream);
+
 /* dec.forward(z, g) (models.py:278-297 / 344-377 / 430-467).  z: [B, inter, T]; wav: [B,1,S*T]
  * with S = samples per latent frame (256).  Optional outputs (NULL to skip):
  *   o_mb : MB [B,4,64T];  MS [B,4,256T] (the zero-stuffed tensor the reference returns); iSTFT: must be NULL

@@ -167,6 +167,7 @@ struct EpiParams {
   int n_split;      // EPI_RS: width of the residual half (0 = last layer)
   int ch_off;       // EPI_POST: first channel updated; EPI_GATE: first channel of this layer's slot in the acts buffer
   int first;        // EPI_RS: first WN layer (skip accumulator is set, not added)
+  float post_sign;  // EPI_POST: +1 reverse (x1 - m), -1 forward direction (x1 + m)
 };
 
 // One row, W consecutive output columns starting at n0.  acc/acc2 are modified in place.
@@ -301,7 +302,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int b, int ro
       const size_t zo = ((size_t)b * p.rows_res + row) * p.ld + p.ch_off + n0;
       f32_load_vec<W>(tmp, reinterpret_cast<const float*>(p.xin) + zo);
 #pragma unroll
-      for (int i = 0; i < W; ++i) acc[i] = (tmp[i] - acc[i] * m) * m;
+      for (int i = 0; i < W; ++i) acc[i] = (tmp[i] - p.post_sign * (acc[i] * m)) * m;
       f32_store_vec<W>(reinterpret_cast<float*>(p.xout) + zo, acc);
       op_store_vec<Op, W>(reinterpret_cast<T*>(p.act[0]) + zo, acc);
     } break;

@@ -396,7 +396,7 @@ __device__ __forceinline__ void epi_post(const EpiParams& p, int b, int n, int p
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
     z[i] = 0.f;
-    MBV_EL(i) { const float m = mp[i]; z[i] = (xpre[i] - (acc[i] + bias) * m) * m; }
+    MBV_EL(i) { const float m = mp[i]; z[i] = (xpre[i] - p.post_sign * ((acc[i] + bias) * m)) * m; }
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) MBV_EL(i) { zo[i * step] = z[i]; op_store1<Op>(dst + i * step, z[i]); }

@@ -784,11 +784,15 @@ EpiParams epi_base(int mode, int ld, int rows) {
   EpiParams e;
   memset(&e, 0, sizeof(e));
   e.mode = mode; e.ld = ld; e.rows_out = rows; e.rows_res = rows; e.row_mul = 1; e.row_add = 0;
-  e.dup_src = -1; e.dup_dst = 0; e.slope = 1.f; e.scale = 1.f; e.n_valid = ld;
+  e.dup_src = -1; e.dup_dst = 0; e.slope = 1.f; e.scale = 1.f; e.n_valid = ld; e.post_sign = 1.f;
   return e;
 }
 
-int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, const float* g, float* z_out, int B, int T) {
+// forward = false: ResidualCouplingBlock.forward(reverse=True) (inference); true: the forward direction (voice conversion).
+// With the Flips folded into the weights a coupling layer sees the same flip parity in both directions (4 - f and f flips
+// before layer f), so the packed weights are shared: forward runs the layers in ascending order and adds m.
+int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, const float* g, float* z_out, int B, int T,
+             bool forward = false) {
   mbv_handle* h = cx.h;
   const mbv_config& c = h->cfg;
   const int Hp = h->Hp, NL = c.flow_layers;
@@ -797,7 +801,8 @@ int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, co
     CUDA_TRY(h, launch_pack_input(h->prec, z_p, nullptr, f.zop, f.z, B, h->Cz, T, h->Cz, cx.st));
   }
   cx.launches++;
-  for (int f_i = 3; f_i >= 0; --f_i) {
+  for (int step = 0; step < 4; ++step) {
+    const int f_i = forward ? step : 3 - step;
     float* gc = nullptr;
     if (g) {
       gc = f.gcond + (size_t)f_i * B * NL * 2 * Hp;
@@ -833,6 +838,7 @@ int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, co
       e.mask = mask; e.xin = f.z; e.xout = f.z; e.act[0] = f.zop; e.n_act = 1;
       e.n_valid = h->Cz / 2;
       e.ch_off = ((4 - f_i) & 1) ? 0 : h->Cz / 2;
+      e.post_sign = forward ? -1.f : 1.f;
       if ((rc = run_conv(cx, h->fl_post[f_i], f.acts, B, T, T, e))) return rc;
     }
   }
@@ -1035,6 +1041,24 @@ extern "C" int mbv_flow_reverse(mbv_handle* h, const float* z_p, const float* y_
   layout_flow(h, A, B, T, &f);
   Ctx cx = make_ctx(h, B, T, ws, g ? 1 : 0, stream);
   rc = run_flow(cx, f, z_p, y_mask, g, z_out, B, T);
+  if (rc) { cx.plans->clear(); return rc; }
+  h->last_launches = cx.launches;
+  return MBV_OK;
+}
+
+extern "C" int mbv_flow_forward(mbv_handle* h, const float* x, const float* y_mask, const float* g, float* z_out, int32_t B,
+                                int32_t T, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_ready(h, B, T);
+  if (rc) return rc;
+  if (!x || !y_mask || !z_out) return fail(h, MBV_ERR_INVALID, "null tensor");
+  if (g && h->cfg.gin_channels == 0) return fail(h, MBV_ERR_INVALID, "g given but gin_channels == 0");
+  if ((rc = check_ws(h, B, T, ws, ws_bytes))) return rc;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  Arena A(ws);
+  FlowBufs f;
+  layout_flow(h, A, B, T, &f);
+  Ctx cx = make_ctx(h, B, T, ws, g ? 7 : 6, stream);
+  rc = run_flow(cx, f, x, y_mask, g, z_out, B, T, true);
   if (rc) { cx.plans->clear(); return rc; }
   h->last_launches = cx.launches;
   return MBV_OK;

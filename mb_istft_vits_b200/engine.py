@@ -160,6 +160,18 @@ class Engine:
                                               B, T, C.c_void_p(ws), nws, self._stream()))
         return out
 
+    def flow_forward(self, x, y_mask, g=None):
+        """ResidualCouplingBlock.forward(reverse=False) (models.py:207-210): the direction voice conversion uses."""
+        B, Cz, T = x.shape
+        x = self._prep(x)
+        y_mask = self._prep(y_mask, (B, 1, T))
+        g = self._prep(g)
+        out = torch.empty_like(x)
+        ws, nws = self._workspace(B, T)
+        self._check(self.lib.mbv_flow_forward(self._h, self._ptr(x), self._ptr(y_mask), self._ptr(g), self._ptr(out),
+                                              B, T, C.c_void_p(ws), nws, self._stream()))
+        return out
+
     def decode(self, z, g=None, z_mask=None, want_mb=True, want_spec=True):
         B, Cz, T = z.shape
         z = self._prep(z)

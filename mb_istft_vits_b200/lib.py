@@ -28,7 +28,7 @@ ERRORS = {0: "MBV_OK", -1: "MBV_ERR_INVALID", -2: "MBV_ERR_UNSUPPORTED", -3: "MB
 # every symbol include/mbistft.h declares (tests check the .so exports all of them)
 SYMBOLS = ["mbv_abi_version", "mbv_create", "mbv_destroy", "mbv_load_weights", "mbv_workspace_bytes",
            "mbv_flow_reverse", "mbv_decode", "mbv_flow_decode", "mbv_last_launch_count", "mbv_decode_flops",
-           "mbv_flow_flops", "mbv_tail", "mbv_last_error", "mbv_set_profiling", "mbv_profile_read", "mbv_profile_read_launches", "mbv_pcm16", "mbv_expand_prior"]
+           "mbv_flow_flops", "mbv_tail", "mbv_last_error", "mbv_set_profiling", "mbv_profile_read", "mbv_profile_read_launches", "mbv_pcm16", "mbv_expand_prior", "mbv_flow_forward"]
 
 
 class MbvConfig(C.Structure):
@@ -76,6 +76,7 @@ def load():
     lib.mbv_load_weights.argtypes = [vp, C.POINTER(MbvTensor), i32]
     lib.mbv_workspace_bytes.argtypes = [vp, i32, i32, C.POINTER(C.c_size_t)]
     lib.mbv_flow_reverse.argtypes = [vp, fp, fp, fp, fp, i32, i32, vp, C.c_size_t, vp]
+    lib.mbv_flow_forward.argtypes = [vp, fp, fp, fp, fp, i32, i32, vp, C.c_size_t, vp]
     lib.mbv_decode.argtypes = [vp, fp, fp, fp, fp, fp, fp, fp, i32, i32, vp, C.c_size_t, vp]
     lib.mbv_flow_decode.argtypes = [vp, fp, fp, fp, fp, fp, fp, fp, fp, i32, i32, vp, C.c_size_t, vp]
     lib.mbv_tail.argtypes = [vp, fp, fp, fp, fp, fp, i32, i32, vp]

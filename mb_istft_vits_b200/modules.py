@@ -8,7 +8,7 @@ Usage (the reference's models.py stays untouched)::
     o, o_mb, spec, phase, attn, y_mask, zs, timings = net_g.infer(x, x_lengths, sid=sid)
 
 Signatures honoured:
-  flow(x, x_mask, g=None, reverse=False) -> x            (reverse=True only; forward is training-only)
+  flow(x, x_mask, g=None, reverse=False) -> x            (both directions; no gradients: inference / voice conversion)
   dec(x, g=None) -> (o, o_mb, spec, phase)               o_mb is None for the single-band decoder
 """
 from __future__ import annotations
@@ -28,9 +28,8 @@ class NativeFlow(nn.Module):
 
     @torch.no_grad()
     def forward(self, x, x_mask, g=None, reverse=False):
-        if not reverse:
-            raise NotImplementedError("NativeFlow implements the inference direction only (reverse=True); "
-                                      "the forward direction is used by training / voice conversion")
+        if not reverse:  # voice conversion (models.py:796); like the reference block it returns x only
+            return self.engine.flow_forward(x, x_mask, g)
         return self.engine.flow_reverse(x, x_mask, g)
 
 

@@ -105,6 +105,24 @@ def flow_reverse(sd, cfg, z_p, y_mask, g=None, prefix="flow"):
     return x
 
 
+def flow_forward(sd, cfg, x, y_mask, g=None, prefix="flow"):
+    """ResidualCouplingBlock.forward(reverse=False) (models.py:207-210), the direction voice conversion uses
+    (models.py:790-798): RCL0, Flip, RCL1, Flip, ...; mean-only coupling x1 <- m + x1 * mask (modules.py:345-347).  The
+    log-determinant the layers return is discarded by the block, as in the reference."""
+    hidden = cfg["hidden_channels"]
+    x = x.float()
+    for i in range(4):
+        pfx = f"{prefix}.flows.{2 * i}"
+        half = x.shape[1] // 2
+        x0, x1 = x[:, :half], x[:, half:]
+        h = F.conv1d(x0, sd[pfx + ".pre.weight"].float(), sd[pfx + ".pre.bias"].float()) * y_mask
+        h = wn_forward(h, y_mask, sd, pfx + ".enc", hidden, g=g)
+        m = F.conv1d(h, sd[pfx + ".post.weight"].float(), sd[pfx + ".post.bias"].float()) * y_mask
+        x = torch.cat([x0, m + x1 * y_mask], 1)
+        x = torch.flip(x, [1])
+    return x
+
+
 # ----------------------------------------------------------------------------
 # decoder body: models.py:278-293 / 344-365 / 430-453, modules.py:213-228, 251-262
 # ----------------------------------------------------------------------------

@@ -31,6 +31,8 @@ def test_oracle_matches_reference_golden(name):
         assert o_mb is None
     # padded frames of z are exactly zero after four masked couplings
     assert float((z * (1 - mask)).abs().max()) == 0.0
+    if "z_fwd" in t:  # the forward direction (voice conversion), minted from the reference's flow(x, mask, g)
+        assert (orc.flow_forward(sd, cfg, z_p, mask, g) - t["z_fwd"]).abs().max() < 1e-5
 
 
 @pytest.mark.parametrize("name", ["mb", "ms", "istft"])

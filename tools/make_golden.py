@@ -118,13 +118,16 @@ def main():
         with torch.no_grad():
             z = net.flow(z_p, mask, g=g, reverse=True)
             o, o_mb, spec, phase = net.dec(z * mask, g=g)
+            z_fwd = net.flow(z_p, mask, g=g)  # the forward direction (voice conversion, models.py:796) on the same input
         # cross-check the oracle right here
         zo, (oo, oo_mb, ospec, ophase) = orc.flow_decode(sd, cfg, z_p, mask, g)
         print(f"{name:14s} wav peak {o.abs().max():.4f}  oracle-vs-ref: z {(zo - z).abs().max():.2e} "
               f"wav {orc.max_abs_over_peak(oo, o):.2e} spec {orc.max_abs_over_peak(ospec, spec):.2e} "
               f"phase {(ophase - phase).abs().max():.2e}")
+        zfo = orc.flow_forward(sd, cfg, z_p, mask, g)
+        print(f"{'':14s} flow forward oracle-vs-ref {(zfo - z_fwd).abs().max():.2e}")
         out = dict(z_p=z_p.numpy(), mask=mask.numpy(), z=z.numpy(), o=o.numpy(),
-                   spec=spec.numpy(), phase=phase.numpy(),
+                   spec=spec.numpy(), phase=phase.numpy(), z_fwd=z_fwd.numpy(),
                    meta=np.array([B, T, 1234, 4321], dtype=np.int64), g_scale=np.float32(g_scale),
                    lengths=np.array(lengths, dtype=np.int64))
         if o_mb is not None:
