@@ -52,6 +52,7 @@ struct TailArgs {
   float mod[8][4];      // PQMF fast path: cosine modulation 2*cos(theta_c(m)), m = k mod 8
   float g2[4][16];      // PQMF fast path: 4 * prototype[4d+31-r] * (-1)^floor(k/8), per output residue r
   int fast_pqmf;        // 1: variant MB (cosine-modulated bank): modulate once per sub-band sample, 16 MACs per output
+  long long* dbg;       // MBV_TAIL_TIMELINE=1: CTA 0 / thread 0 clock stamps [tile < 8][8] (debug only)
 };
 cudaError_t launch_tail(const TailArgs& a, int precise, int num_sms, cudaStream_t st);
 

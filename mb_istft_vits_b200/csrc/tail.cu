@@ -12,6 +12,7 @@
 // 97 % useful work.  Shared memory: logits tile 72 KB + frame scratch 20 KB + sub-band tile 16 KB -> 2 CTAs/SM,
 // so one CTA's loads overlap the other's math.
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <type_traits>
@@ -575,26 +576,30 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = a.L, F = L + 1;
 
-  // this CTA's equal share of the B*L hop blocks
+  // this CTA's equal share of the B*L hop blocks.  The walk keeps (utterance, block, blocks left) as 32-bit state: the
+  // first version recomputed them from a 64-bit global position with two 64-bit divisions per tile in every thread,
+  // ~3 K cycles on the critical path between the phase-A barrier and the next tile's TMA issue (MBV_TAIL_TIMELINE).
   const long long total = (long long)a.B * L;
   const long long per = (total + gridDim.x - 1) / gridDim.x;
-  long long g = per * blockIdx.x;
-  const long long g_end = (g + per < total) ? g + per : total;
+  const long long g0 = per * blockIdx.x;
+  const long long g_end = (g0 + per < total) ? g0 + per : total;
+  long long g = g0;  // only used by the debug stamps
+  int left_blocks = (int)(g_end > g0 ? g_end - g0 : 0);
 
   struct Tile { int b, q0, nq; };
-  auto next_tile = [&](long long pos) {
+  auto make_tile = [&](int b, int q0, int rem) {
     Tile t;
-    t.b = (int)(pos / L);
-    t.q0 = (int)(pos - (long long)t.b * L);
-    const long long rem = g_end - pos;
-    const int left = (int)((rem + T3_NQ - 1) / T3_NQ);
-    int nq = (int)((rem + left - 1) / left);
-    if (nq > L - t.q0) nq = L - t.q0;
+    t.b = b; t.q0 = q0;
+    const int tiles_left = (rem + T3_NQ - 1) / T3_NQ;
+    int nq = (rem + tiles_left - 1) / tiles_left;
+    if (nq > L - q0) nq = L - q0;
     t.nq = nq;
     return t;
   };
-  auto issue_load = [&](const Tile& t) {  // one thread: three boxes of the logits rows [q0-3, q0-3+128) (OOB rows -> 0)
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  // one thread: three boxes of the logits rows [q0-3, q0-3+128) (OOB rows -> 0).  The tile is only ever READ through the
+  // generic proxy, and those reads are ordered before this point by the block barrier, so no proxy fence is needed for
+  // the write-after-read (same discipline as a TMA pipeline's consumer-release / producer-acquire).
+  auto issue_load = [&](const Tile& t) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)T3_OFF_U) : "memory");
     const int f0 = t.q0 - 3;
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -614,8 +619,8 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (g >= g_end) return;
-  Tile cur = next_tile(g);
+  if (left_blocks <= 0) return;
+  Tile cur = make_tile((int)(g0 / L), (int)(g0 % L), left_blocks);
   if (tid == 0) issue_load(cur);
   uint32_t parity = 0;
 
@@ -623,8 +628,15 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
     const int b = cur.b, Q0 = cur.q0, nq = cur.nq;
     const int QY0 = Q0 - 2, F0 = Q0 - 3;
     const bool last_tile = (Q0 + nq == L);
+    long long* dbg = nullptr;
+    if (a.dbg && blockIdx.x == 0 && tid == 0) {
+      const long long k = (g - per * blockIdx.x) / T3_NQ;
+      if (k < 8) dbg = a.dbg + k * 8;
+    }
+    if (dbg) dbg[0] = clock64();
     t2_mbar_wait(bar, parity);
     parity ^= 1;
+    if (dbg) dbg[1] = clock64();
 
     // ---- phase A: head + inverse DFT + window (registers), overlap-add by shuffles.  Lane = frame F0 + tid = hop block
     // QY0 + tid.  Two sub-bands share every arithmetic instruction (f2): yp[P][i] = sample i of bands (2P, 2P+1).
@@ -696,14 +708,18 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
       band_pair(std::integral_constant<int, 0>{});
       band_pair(std::integral_constant<int, 1>{});
     }
+    if (dbg) dbg[2] = clock64();
     __syncthreads();  // halo visible; the logits tile is dead from here on: refill it with the next tile while B/C run
-    const long long g_next = g + nq;
-    const bool has_next = g_next < g_end;
+    if (dbg) dbg[3] = clock64();
+    left_blocks -= nq;
+    const bool has_next = left_blocks > 0;
     Tile nxt = cur;
     if (has_next) {
-      nxt = next_tile(g_next);
+      const bool wrap = (Q0 + nq == L);
+      nxt = make_tile(wrap ? b + 1 : b, wrap ? 0 : Q0 + nq, left_blocks);
       if (tid == 0) issue_load(nxt);
     }
+    if (dbg) dbg[7] = clock64();
 
     // ---- phase B: finish the blocks that straddle a warp boundary, envelope, optional o_mb, modulation -> U
     {
@@ -711,14 +727,24 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
       const bool inside = (q >= 0) && (q < L) && (tid < T3_NF - 3);
 #pragma unroll
       for (int P = 0; P < 2; ++P) {
-        if (warp < 3 && lane >= 29) {
-          const f2* h = s_halo + (((warp + 1) * 2 + P) * 6) * 4;
+        {
+          // lanes 29 / 30 / 31 of warps 0..2 add the 1 / 2 / 3 vectors the next warp left for them.  Unconditional loads
+          // from valid addresses + predicated adds: the first version branched three ways here and the serialised
+          // LDS -> FADD2 chains of three lanes held every warp (and the block barrier) for ~1 K cycles per tile.
+          const bool fix = (warp < 3) && (lane >= 29);
+          const bool on1 = fix && (lane >= 30), on2 = fix && (lane == 31);
+          const int s0 = lane == 30 ? 1 : (lane == 31 ? 2 : 0), s1 = lane == 30 ? 3 : 4;
+          const f2* h = s_halo + ((((fix ? warp + 1 : warp)) * 2 + P) * 6) * 4;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
+            const f2 a0 = h[s0 * 4 + i], a1 = h[s1 * 4 + i], a2 = h[5 * 4 + i];
             f2 v = yp[P][i];
-            if (lane == 29) { v = v + h[0 * 4 + i]; }
-            else if (lane == 30) { v = v + h[1 * 4 + i]; v = v + h[3 * 4 + i]; }
-            else { v = v + h[2 * 4 + i]; v = v + h[4 * 4 + i]; v = v + h[5 * 4 + i]; }
+            const f2 v0 = v + a0;
+            if (fix) v = v0;
+            const f2 v1 = v + a1;
+            if (on1) v = v1;
+            const f2 v2 = v + a2;
+            if (on2) v = v2;
             yp[P][i] = v;
           }
         }
@@ -780,6 +806,7 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
     }
     __syncthreads();
 
+    if (dbg) dbg[4] = clock64();
     // ---- phase C: synthesis FIR.  Thread = (hop blocks 2p, 2p+1; residues rh and rh+2); sub-band positions j = 8p + e.
     {
       const int p = 16 * warp + (lane >> 1), rh = lane & 1;
@@ -850,6 +877,7 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
           }
         }
       }
+      if (dbg) dbg[5] = clock64();
       __syncthreads();  // every FIR window has been read: U becomes the output staging buffer
       if (fir_on) {
         // row p = 32 floats (blocks 2p, 2p+1), 16-byte chunk e XOR-swizzled with p
@@ -871,13 +899,22 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
         dst[c] = src[8 * pr + (e ^ (pr & 7))];
       }
     }
+    if (dbg) dbg[6] = clock64();
     if (!has_next) break;
-    g = g_next;
+    g += nq;
     cur = nxt;  // (the barrier after the next phase A orders these staging reads before U is rewritten)
   }
 }
 
-static cudaError_t launch_tail_mb3(const TailArgs& a, int precise, int num_sms, cudaStream_t st) {
+static cudaError_t launch_tail_mb3(const TailArgs& a_in, int precise, int num_sms, cudaStream_t st) {
+  TailArgs a = a_in;
+  static long long* dbg = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) {
+    dbg_on = (getenv("MBV_TAIL_TIMELINE") && atoi(getenv("MBV_TAIL_TIMELINE"))) ? 1 : 0;
+    if (dbg_on) { cudaMalloc(&dbg, 64 * sizeof(long long)); cudaMemset(dbg, 0, 64 * sizeof(long long)); }
+  }
+  a.dbg = dbg_on ? dbg : nullptr;
   typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -916,6 +953,17 @@ static cudaError_t launch_tail_mb3(const TailArgs& a, int precise, int num_sms, 
   } else {
     if (emit) tail_mb3_kernel<false, true><<<(int)ctas, T3_NF, T3_SMEM, st>>>(tm32, tm8, a);
     else tail_mb3_kernel<false, false><<<(int)ctas, T3_NF, T3_SMEM, st>>>(tm32, tm8, a);
+  }
+  if (dbg_on) {
+    cudaStreamSynchronize(st);
+    long long hb[64];
+    cudaMemcpy(hb, dbg, sizeof(hb), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[tail timeline] CTA 0, thread 0: wait | phase A | barrier | B | C | stage+store  (SM clocks)\n");
+    for (int i = 0; i < 8 && hb[8 * i]; ++i)
+      fprintf(stderr, "  tile %d  start %7lld  wait %5lld  A %5lld  bar %5lld  issue %5lld  B %5lld  C %5lld  store %5lld\n", i, hb[8 * i] - hb[0],
+              hb[8 * i + 1] - hb[8 * i], hb[8 * i + 2] - hb[8 * i + 1], hb[8 * i + 3] - hb[8 * i + 2], hb[8 * i + 7] - hb[8 * i + 3],
+              hb[8 * i + 4] - hb[8 * i + 7], hb[8 * i + 5] - hb[8 * i + 4], hb[8 * i + 6] - hb[8 * i + 5]);
+    cudaMemset(dbg, 0, sizeof(hb));
   }
   return cudaGetLastError();
 }
