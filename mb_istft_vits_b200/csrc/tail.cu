@@ -16,6 +16,7 @@
 #include <stdlib.h>
 
 #include <type_traits>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -515,18 +516,24 @@ __global__ void __launch_bounds__(T2_THREADS, 1024 / T2_THREADS) tail_mb_kernel(
 //   * synthesis FIR: thread = (pair of hop blocks, residue pair): two 24-float windows serve 8 outputs (v2: 20-float
 //     windows for 4), rows of the two residue classes 516 floats apart so the 16-byte loads of a quarter warp hit
 //     disjoint banks.  Outputs are staged (XOR-swizzled) in the dead logits buffer and leave as coalesced 16-byte stores.
-//   * persistent CTAs of 128 threads, 4 per SM, each owning an EQUAL contiguous range of hop blocks (cut into tiles of
-//     <= 121 blocks that never straddle an utterance): no wave-quantisation tail.
+//   * persistent CTAs of 128 threads (tiles of 128 frames, <= 121 owned hop blocks), 4 per SM, each owning an EQUAL
+//     contiguous range of hop blocks (tiles never straddle an utterance): no wave-quantisation tail.  (-DMBV_T3_NF=256,
+//     2 CTAs of 8 warps per SM, measures 8 % slower: 91.6 vs 84.3 us.)
 // Arithmetic (operation order included) is identical to v2, so the parity tests need no new tolerances.
 // ------------------------------------------------------------------------------------------------
-constexpr int T3_NF = 128;                 // frames per tile = threads per CTA
+#ifndef MBV_T3_NF
+#define MBV_T3_NF 128
+#endif
+constexpr int T3_NF = MBV_T3_NF;           // frames per tile = threads per CTA (128 or 256)
+constexpr int T3_CTAS = 512 / T3_NF;       // CTAs per SM: 16 resident warps either way
+constexpr int T3_NW = T3_NF / 32;
 constexpr int T3_NQ = T3_NF - 7;           // owned hop blocks per tile (max)
-constexpr int T3_UP = 516;                 // floats per U / Y row; = 4 mod 8 (bank spread between adjacent rows)
+constexpr int T3_UP = 4 * T3_NF + 4;       // floats per U / Y row; = 4 mod 32 (bank spread between adjacent rows)
 constexpr int T3_BOX01 = T3_NF * 128;      // bytes of one 32-float box
 constexpr int T3_BOX2 = T3_NF * 32;        // bytes of the 8-float box
 constexpr int T3_OFF_U = 2 * T3_BOX01 + T3_BOX2;              // 36864
 constexpr int T3_OFF_HALO = T3_OFF_U + 8 * T3_UP * 4;         // + 16512
-constexpr int T3_OFF_TAB = T3_OFF_HALO + 4 * 4 * 6 * 16;      // + 1536
+constexpr int T3_OFF_TAB = T3_OFF_HALO + T3_NW * 4 * 6 * 16;
 constexpr int T3_OFF_BAR = T3_OFF_TAB + 1024;
 constexpr int T3_SMEM = T3_OFF_BAR + 16;
 
@@ -562,7 +569,7 @@ struct T3Load {
 template <int C0> struct T3Load<C0, 0> { static __device__ __forceinline__ void run(const uint8_t*, int, float*) {} };
 
 template <bool PRECISE, bool EMIT>
-__global__ void __launch_bounds__(T3_NF, 4)
+__global__ void __launch_bounds__(T3_NF, T3_CTAS)
 tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant__ CUtensorMap tm8,
                 const __grid_constant__ TailArgs a) {
   constexpr int S = 4;
@@ -610,8 +617,8 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
                  ::"r"(sm_base + 2 * T3_BOX01), "l"(reinterpret_cast<uint64_t>(&tm8)), "r"(bar), "r"(64), "r"(f0), "r"(t.b) : "memory");
   };
 
-  if (a.fast_pqmf) { s_tab[tid] = a.g2[tid >> 5][(tid >> 1) & 15]; }
-  else { s_tab[tid] = a.coef[tid >> 6][tid & 63]; s_tab[tid + 128] = a.coef[(tid + 128) >> 6][tid & 63]; }
+  if (a.fast_pqmf) { if (tid < 128) s_tab[tid] = a.g2[tid >> 5][(tid >> 1) & 15]; }
+  else { for (int i = tid; i < 256; i += T3_NF) s_tab[i] = a.coef[i >> 6][i & 63]; }
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm32)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm8)) : "memory");
@@ -620,6 +627,14 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
   }
   __syncthreads();
   if (left_blocks <= 0) return;
+  if (a.dbg && tid == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.dbg[64 + 3 * blockIdx.x] = (long long)t;
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    a.dbg[64 + 3 * blockIdx.x + 2] = smid;
+  }
   Tile cur = make_tile((int)(g0 / L), (int)(g0 % L), left_blocks);
   if (tid == 0) issue_load(cur);
   uint32_t parity = 0;
@@ -731,7 +746,7 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
           // lanes 29 / 30 / 31 of warps 0..2 add the 1 / 2 / 3 vectors the next warp left for them.  Unconditional loads
           // from valid addresses + predicated adds: the first version branched three ways here and the serialised
           // LDS -> FADD2 chains of three lanes held every warp (and the block barrier) for ~1 K cycles per tile.
-          const bool fix = (warp < 3) && (lane >= 29);
+          const bool fix = (warp < T3_NW - 1) && (lane >= 29);
           const bool on1 = fix && (lane >= 30), on2 = fix && (lane == 31);
           const int s0 = lane == 30 ? 1 : (lane == 31 ? 2 : 0), s1 = lane == 30 ? 3 : 4;
           const f2* h = s_halo + ((((fix ? warp + 1 : warp)) * 2 + P) * 6) * 4;
@@ -900,7 +915,14 @@ tail_mb3_kernel(const __grid_constant__ CUtensorMap tm32, const __grid_constant_
       }
     }
     if (dbg) dbg[6] = clock64();
-    if (!has_next) break;
+    if (!has_next) {
+      if (a.dbg && tid == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.dbg[64 + 3 * blockIdx.x + 1] = (long long)t;
+      }
+      break;
+    }
     g += nq;
     cur = nxt;  // (the barrier after the next phase A orders these staging reads before U is rewritten)
   }
@@ -912,7 +934,7 @@ static cudaError_t launch_tail_mb3(const TailArgs& a_in, int precise, int num_sm
   static int dbg_on = -1;
   if (dbg_on < 0) {
     dbg_on = (getenv("MBV_TAIL_TIMELINE") && atoi(getenv("MBV_TAIL_TIMELINE"))) ? 1 : 0;
-    if (dbg_on) { cudaMalloc(&dbg, 64 * sizeof(long long)); cudaMemset(dbg, 0, 64 * sizeof(long long)); }
+    if (dbg_on) { cudaMalloc(&dbg, (64 + 3 * 1024) * sizeof(long long)); cudaMemset(dbg, 0, (64 + 3 * 1024) * sizeof(long long)); }
   }
   a.dbg = dbg_on ? dbg : nullptr;
   typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -945,7 +967,7 @@ static cudaError_t launch_tail_mb3(const TailArgs& a_in, int precise, int num_sm
   }
   const long long total = (long long)a.B * a.L;
   long long ctas = (total + T3_NQ - 1) / T3_NQ;
-  if (ctas > 4LL * num_sms) ctas = 4LL * num_sms;
+  if (ctas > (long long)T3_CTAS * num_sms) ctas = (long long)T3_CTAS * num_sms;
   const bool emit = a.spec != nullptr;
   if (precise) {
     if (emit) tail_mb3_kernel<true, true><<<(int)ctas, T3_NF, T3_SMEM, st>>>(tm32, tm8, a);
@@ -963,7 +985,17 @@ static cudaError_t launch_tail_mb3(const TailArgs& a_in, int precise, int num_sm
       fprintf(stderr, "  tile %d  start %7lld  wait %5lld  A %5lld  bar %5lld  issue %5lld  B %5lld  C %5lld  store %5lld\n", i, hb[8 * i] - hb[0],
               hb[8 * i + 1] - hb[8 * i], hb[8 * i + 2] - hb[8 * i + 1], hb[8 * i + 3] - hb[8 * i + 2], hb[8 * i + 7] - hb[8 * i + 3],
               hb[8 * i + 4] - hb[8 * i + 7], hb[8 * i + 5] - hb[8 * i + 4], hb[8 * i + 6] - hb[8 * i + 5]);
-    cudaMemset(dbg, 0, sizeof(hb));
+    {
+      std::vector<long long> cb(3 * 1024);
+      cudaMemcpy(cb.data(), dbg + 64, cb.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      long long t0 = 0, t1 = 0;
+      int n = 0;
+      for (int c = 0; c < 1024; ++c) if (cb[3 * c]) { if (!t0 || cb[3 * c] < t0) t0 = cb[3 * c]; if (cb[3 * c + 1] > t1) t1 = cb[3 * c + 1]; ++n; }
+      fprintf(stderr, "[tail timeline] %d CTAs, first start -> last end %.1f us\n", n, (t1 - t0) * 1e-3);
+      for (int c = 0; c < n; c += 37)
+        fprintf(stderr, "  CTA %3d sm %3lld  start +%6.1f us  end +%6.1f us\n", c, cb[3 * c + 2], (cb[3 * c] - t0) * 1e-3, (cb[3 * c + 1] - t0) * 1e-3);
+    }
+    cudaMemset(dbg, 0, (64 + 3 * 1024) * sizeof(long long));
   }
   return cudaGetLastError();
 }
