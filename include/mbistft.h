@@ -88,6 +88,9 @@ typedef struct {
 /* debug / tuning flags */
 #define MBV_FLAG_FORCE_SIMT 4       /* run the CUDA-core conv on the tensor-core operand layout (cross-check) */
 #define MBV_FLAG_RESIDUAL_FP16 8    /* bf16 path: keep the decoder's ResBlock residual stream in (saturating) fp16 */
+#define MBV_FLAG_CLUSTER_PAIRS 32    /* experimental: run the multi-tap convs as clusters of two CTAs that work on two time tiles of the
+                                     * same weight group; each CTA fetches half of every weight tile and TMA-multicasts it to both.
+                                     * Parity-tested; < 1 % faster per step on B200, hence opt-in. */
 #define MBV_FLAG_FUSED_PAIR 16      /* experimental: run each ResBlock1 conv pair of a 128-channel stage as ONE kernel that keeps
                                      * the intermediate activation in shared memory (conv_pair_kernel).  Parity-tested; currently
                                      * not faster than the two-launch path, hence opt-in. */

@@ -31,6 +31,7 @@
 
 #include <vector>
 
+#include "../../include/mbistft.h"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -117,6 +118,24 @@ __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// ---- thread-block cluster helpers (weight-tile multicast between the two CTAs of a pair)
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+               "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -227,6 +246,9 @@ struct TcRt {  // runtime scalars the kernel needs beyond ConvArgs
   int xchg_off;      // byte offset of the gate exchange buffer in dynamic smem
   int w_resident;    // all weight tiles of the (single) channel tile fit the ring: load them once per CTA
   int prefetch_res;  // issue an L2 prefetch of the tile's residual input (tmR) when its operand loads start
+  int cluster;       // 1: launched as clusters of 2 CTAs that work on two time tiles of the SAME (phase, channel tile) in
+                     // lock step; every weight tile is fetched once per pair (each CTA loads half and multicasts it)
+  int rows, groups;  // cluster mode: B * t_tiles time tiles, n_phases * c_tiles weight groups
   int rotate;        // two channel tiles, even grid: swap which one a CTA takes every round.  With a static round-robin
                      // an even CTA would otherwise ALWAYS get channel tile 0; when the second tile is half padding
                      // (192 = 128 + 64 rows: flow pre / res convs) its epilogue is half the work and half the CTAs idle.
@@ -465,10 +487,11 @@ __device__ __forceinline__ void tc_epilogue32(const EpiParams& p, int b, int n, 
   }
 }
 
-template <typename Op, int MODE, int LD, int RH>
+template <typename Op, int MODE, int LD, int RH, int CL>
 __global__ void __launch_bounds__(TcThreads<MODE>::value, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-               const __grid_constant__ CUtensorMap tmR, const ConvArgs a, const TcRt rt) {
+               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmWh, const ConvArgs a,
+               const TcRt rt) {
   using T = typename Op::T;
   constexpr int KB = TC_ROW_BYTES / (int)sizeof(T);  // channels per k-block
   constexpr int TC_EPI_WARPS = EpiWarps<MODE>::value;
@@ -493,13 +516,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
     for (int i = 0; i < rt.n_slab_stages; ++i) { mbar_init(BAR(iXF + i), 1); mbar_init(BAR(iXE + i), 1); }
-    for (int i = 0; i < rt.n_w_stages; ++i) { mbar_init(BAR(iWF + i), 1); mbar_init(BAR(iWE + i), 1); }
+    // cluster mode: a weight stage may be refilled (by BOTH CTAs' multicasts) only when both CTAs have consumed it
+    for (int i = 0; i < rt.n_w_stages; ++i) { mbar_init(BAR(iWF + i), 1); mbar_init(BAR(iWE + i), (CL != 0) ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(iCF + i), 1); mbar_init(BAR(iCE + i), TC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == TC_WARP_MMA) tmem_alloc(smem_u32(tmem_ptr_smem), 512u);
   tc_fence_before();
   __syncthreads();
+  if ((CL != 0)) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the
@@ -511,6 +536,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int kblocks = a.Cp_in / KB;
   const uint32_t slab_bytes = (uint32_t)rt.n_boxes * rt.box_rows * TC_ROW_BYTES;
   const uint32_t w_tile_bytes = TC_M * TC_ROW_BYTES;
+  const uint32_t crank = blockIdx.x & 1u;  // cluster rank (clusters are pairs of consecutive blocks)
+  // tile index -> (channel tile, phase, time tile, utterance, does this CTA have a time tile).  Cluster mode walks pairs:
+  // tiles 2w and 2w+1 (always on the two CTAs of one cluster, the grid is even) share the weight group w % groups and take
+  // the time tiles 2j and 2j+1, j = w / groups; the odd one out at the end only relays weight tiles.
+  struct Work { int ct, phase, tt, b; bool row_ok; };
+  auto decode_work = [&](int tile) {
+    Work wk;
+    if ((CL != 0)) {
+      const int w = tile >> 1, grp = w % rt.groups, row = 2 * (w / rt.groups) + (tile & 1);
+      wk.ct = grp % rt.c_tiles; wk.phase = grp / rt.c_tiles;
+      wk.row_ok = row < rt.rows;
+      wk.tt = row % rt.t_tiles; wk.b = row / rt.t_tiles;
+    } else {
+      int rest = tile;
+      wk.ct = rest % rt.c_tiles; rest /= rt.c_tiles;
+      if (rt.rotate) wk.ct = (wk.ct + tile / (int)gridDim.x) & 1;
+      wk.phase = rest % a.n_phases; rest /= a.n_phases;
+      wk.tt = rest % rt.t_tiles; wk.b = rest / rt.t_tiles;
+      wk.row_ok = true;
+    }
+    return wk;
+  };
 
   if (warp == TC_WARP_TMA) {
     // ===================== TMA producer =====================
@@ -519,13 +566,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     int sx = 0, sw = 0;
     uint32_t px = 0, pw = 0;
     for (int tile = blockIdx.x; tile < rt.total_tiles; tile += gridDim.x) {
-      int rest = tile;
-      int ct = rest % rt.c_tiles; rest /= rt.c_tiles;
-      if (rt.rotate) ct = (ct + tile / (int)gridDim.x) & 1;
-      const int phase = rest % a.n_phases; rest /= a.n_phases;
-      const int tt = rest % rt.t_tiles;
-      const int b = rest / rt.t_tiles;
-      const int t0 = tt * rt.n_time;
+      const Work wk = decode_work(tile);
+      const int ct = wk.ct, phase = wk.phase, b = wk.b;
+      const int t0 = wk.tt * rt.n_time;
       const int wrow0 = phase * a.taps * a.N_total + ct * TC_M;
       const int xrow0 = t0 + a.shift0[phase];
       if (rt.dbg && lane == 0) rt.dbg[((size_t)blockIdx.x * 5 + 0) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
@@ -533,23 +576,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       //  a third of it had been evicted again and DRAM reads grew 40 %.  The epilogue warps prefetch two chunks ahead.)
       if (false && MODE == EPI_RES && rt.prefetch_res && elect_one()) tma_prefetch_l2_3d(&tmR, ct * TC_M, t0, b);
       for (int kb = 0; kb < kblocks; ++kb) {
-        mbar_wait(BAR(iXE + sx), px ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(BAR(iXF + sx), slab_bytes);
-          const uint32_t dst = smem_u32(smX + (size_t)sx * rt.slab_stage_bytes);
-          for (int i = 0; i < rt.n_boxes; ++i)
-            tma_load_3d(dst + (uint32_t)(i * rt.box_rows) * TC_ROW_BYTES, &tmX, BAR(iXF + sx), kb * KB,
-                        xrow0 + i * rt.box_rows, b);
+        if (wk.row_ok) {
+          mbar_wait(BAR(iXE + sx), px ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(BAR(iXF + sx), slab_bytes);
+            const uint32_t dst = smem_u32(smX + (size_t)sx * rt.slab_stage_bytes);
+            for (int i = 0; i < rt.n_boxes; ++i)
+              tma_load_3d(dst + (uint32_t)(i * rt.box_rows) * TC_ROW_BYTES, &tmX, BAR(iXF + sx), kb * KB,
+                          xrow0 + i * rt.box_rows, b);
+          }
+          __syncwarp();
+          if (++sx == rt.n_slab_stages) { sx = 0; px ^= 1; }
         }
-        __syncwarp();
-        if (++sx == rt.n_slab_stages) { sx = 0; px ^= 1; }
         for (int tap = 0; tap < a.taps; ++tap) {
           if (rt.w_resident && tile != (int)blockIdx.x) continue;  // weights already resident from the first tile
           mbar_wait(BAR(iWE + sw), pw ^ 1);
           if (elect_one()) {
             const uint32_t wdst = smem_u32(smW + (size_t)sw * rt.w_stage_bytes);
             mbar_expect_tx(BAR(iWF + sw), w_tile_bytes);
-            tma_load_2d(wdst, &tmW, BAR(iWF + sw), kb * KB, wrow0 + tap * a.N_total);
+            if ((CL != 0))  // this CTA's 64 rows of the tile, delivered to both CTAs of the pair
+              tma_load_2d_mc(wdst + crank * (w_tile_bytes / 2), &tmWh, BAR(iWF + sw), kb * KB,
+                             wrow0 + tap * a.N_total + (int)crank * (TC_M / 2), (uint16_t)3);
+            else
+              tma_load_2d(wdst, &tmW, BAR(iWF + sw), kb * KB, wrow0 + tap * a.N_total);
           }
           __syncwarp();
           if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
@@ -569,6 +618,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     int sx = 0, sw = 0, sc = 0;
     uint32_t px = 0, pw = 0, pc = 0;
     for (int tile = blockIdx.x; tile < rt.total_tiles; tile += gridDim.x) {
+      if ((CL != 0) && !decode_work(tile).row_ok) {
+        // no time tile for this CTA (odd tile count): keep the pair's weight ring moving -- wait until each stage has
+        // fully landed here, then release it on both CTAs
+        for (int i = 0; i < kblocks * a.taps; ++i) {
+          mbar_wait(BAR(iWF + sw), pw);
+          if (elect_one()) { mbar_arrive(BAR(iWE + sw)); mbar_arrive_remote(BAR(iWE + sw), crank ^ 1u); }
+          __syncwarp();
+          if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
+        }
+        continue;
+      }
       mbar_wait(BAR(iCE + sc), pc ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(sc * TC_ACC_STRIDE);
@@ -588,7 +648,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             for (int k = 0; k < 4; ++k) {
               tc_mma<KIND>(tmem_d, desc64(w_lo + 2 * k), desc64(x_lo + 2 * k), idesc, (k == 0) ? accum : 1u);
             }
-            if (!rt.w_resident) tc_commit(BAR(iWE + sw));
+            if ((CL != 0)) tc_commit_mc(BAR(iWE + sw), (uint16_t)3);
+            else if (!rt.w_resident) tc_commit(BAR(iWE + sw));
           }
           __syncwarp();
           accum = 1;
@@ -615,16 +676,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     int sc = 0;
     uint32_t pc = 0;
 
-    struct TileInfo { int b, n, phase, t0, t_lim; bool valid; };
+    struct TileInfo { int b, n, phase, t0, t_lim; bool valid, row_ok; };
     auto decode = [&](int tile) {
       TileInfo ti;
-      int rest = tile;
-      int ct = rest % rt.c_tiles; rest /= rt.c_tiles;
-      if (rt.rotate) ct = (ct + tile / (int)gridDim.x) & 1;
-      ti.phase = rest % a.n_phases; rest /= a.n_phases;
-      const int tt = rest % rt.t_tiles;
-      ti.b = rest / rt.t_tiles;
-      ti.t0 = tt * rt.n_time;
+      const Work wk = decode_work(tile);
+      const int ct = wk.ct;
+      ti.phase = wk.phase;
+      ti.b = wk.b;
+      ti.row_ok = wk.row_ok;
+      ti.t0 = wk.tt * rt.n_time;
       ti.n = ct * TC_M + q * 32 + lane;  // weight row = output channel of this thread
       // which logical channel does this row write, and is it inside the destination buffer?
       if (MODE == EPI_RS && a.epi.n_split > 0) ti.valid = (ti.n < a.epi.n_split ? ti.n : ti.n - a.epi.n_split) < n_valid;
@@ -667,8 +727,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       TileInfo tn = ti;
       if (have_next) {
         tn = decode(tile + gridDim.x);
-        for (int j = 0; j < nch; ++j) l2_prefetch(tn, c_first + CSTEP * j);
+        if (tn.row_ok) for (int j = 0; j < nch; ++j) l2_prefetch(tn, c_first + CSTEP * j);
       }
+      if (!ti.row_ok) { ti = tn; tile += gridDim.x; continue; }  // cluster mode: this CTA only relayed weights for this tile
       mbar_wait(BAR(iCF + sc), pc);
       tc_fence_after();
       if (rt.dbg && warp == 0 && lane == 0) rt.dbg[((size_t)blockIdx.x * 5 + 2) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
@@ -748,6 +809,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if ((CL != 0)) cluster_sync_all();  // the peer may still be multicasting into this CTA's ring / arriving on its barriers
   if (warp == TC_WARP_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512u);
@@ -1068,7 +1130,6 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, TcPlan* plan) {
-  (void)flags;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return "cuTensorMapEncodeTiled entry point unavailable";
   const int esize = prec >= 2 ? 2 : 4;
@@ -1137,6 +1198,34 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
   }
   // small layers (stage-1 k=3 convs, flow post): the whole weight set of the channel tile stays in shared memory
   plan->w_resident = (plan->c_tiles == 1 && a.n_phases == 1 && a.taps * (a.Cp_in / KB) <= plan->n_w_stages) ? 1 : 0;
+  // Everything else streams its weight taps L2 -> SMEM once per tile and is feed-bound for few taps (k=3 / upsampler /
+  // gate convs issue MMAs at ~70 % inside a tile): run clusters of two CTAs on two time tiles of the same weight group,
+  // each CTA fetching half of every weight tile and multicasting it to both.
+  // Measured (same box, interleaved, profiles/r02_cluster_ab.txt): the MMA-bound layers gain 3-8 %, the step as a whole
+  // < 1 % -- so the feed is not what holds the k=3 / upsampler convs at ~70 % issue efficiency -- hence opt-in.
+  const int use_cluster = (flags & MBV_FLAG_CLUSTER_PAIRS) ? 1 : 0;
+  plan->cluster = 0;
+  plan->rows = a.B * plan->t_tiles;
+  plan->groups = a.n_phases * plan->c_tiles;
+  // (1x1 convs -- flow pre / res / post -- are epilogue- or launch-bound and measured 5-12 % slower in pairs: taps > 1 only)
+  const bool mode_ok = a.epi.mode == EPI_ACT || a.epi.mode == EPI_RES || a.epi.mode == EPI_F32 || a.epi.mode == EPI_GATE;
+  if (use_cluster && prec >= 2 && mode_ok && !plan->w_resident && (num_sms & 1) == 0 && plan->rows >= 2 && a.taps > 1) {
+    const long long pairs = (long long)plan->groups * ((plan->rows + 1) / 2);
+    if (pairs >= num_sms / 2) {
+      plan->cluster = 1;
+      plan->total_tiles = (int)(2 * pairs);
+      plan->grid = num_sms;
+    }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)a.Cp_in, (cuuint64_t)a.n_phases * a.taps * a.N_total};
+    cuuint64_t strides[1] = {(cuuint64_t)a.Cp_in * esize};
+    cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)(TC_M / 2)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&plan->tmBh, dt, 2, const_cast<void*>(a.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed for the half-tile weight map";
+  }
   plan->prefetch_res = 0;
   if (a.epi.mode == EPI_RES && a.epi.xin != nullptr && a.epi.row_mul == 1) {
     const int rs = a.epi.res_half ? 2 : 4;
@@ -1154,21 +1243,49 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
 }
 
 // kernel table: (mode, compile-time pitch) instantiations; pitch 0 = runtime
+// CL = 1: the cluster-pair variant (weight tiles multicast between two CTAs); compiled only where a plan can ask for it
+// (16-bit operands, multi-tap convs: ACT / RES / F32 / GATE epilogues)
 template <typename Op, int MODE, int LD, int RH = 0>
-static cudaError_t launch_one(const ConvArgs& a, const TcPlan& p, const TcRt& rt, cudaStream_t st, bool set_attr) {
-  auto k = conv_tc_kernel<Op, MODE, LD, RH>;
+static cudaError_t launch_one(const ConvArgs& a, const TcPlan& p, const TcRt& rt, cudaStream_t st, bool set_attr);
+
+template <typename Op, int MODE, int LD, int RH, int CL>
+static cudaError_t launch_one_cl(const ConvArgs& a, const TcPlan& p, const TcRt& rt, cudaStream_t st, bool set_attr) {
+  auto k = conv_tc_kernel<Op, MODE, LD, RH, CL>;
   if (set_attr) return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p.grid);
   cfg.blockDim = dim3(TcThreads<MODE>::value);
   cfg.dynamicSmemBytes = p.smem_bytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k, p.tmA, p.tmB, p.tmR, a, rt);
+  if (rt.cluster) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
+  return cudaLaunchKernelEx(&cfg, k, p.tmA, p.tmB, p.tmR, p.tmBh, a, rt);
+}
+
+template <typename Op, int MODE, int LD, int RH>
+static cudaError_t launch_one(const ConvArgs& a, const TcPlan& p, const TcRt& rt, cudaStream_t st, bool set_attr) {
+  constexpr bool kHasCluster = (Op::kPrec >= 2) && (MODE == EPI_ACT || MODE == EPI_RES || MODE == EPI_F32 || MODE == EPI_GATE);
+  if constexpr (kHasCluster) {
+    if (set_attr) {
+      cudaError_t e = launch_one_cl<Op, MODE, LD, RH, 1>(a, p, rt, st, true);
+      if (e != cudaSuccess) return e;
+    } else if (rt.cluster) {
+      return launch_one_cl<Op, MODE, LD, RH, 1>(a, p, rt, st, false);
+    }
+  } else {
+    if (!set_attr && rt.cluster) return cudaErrorInvalidValue;
+  }
+  return launch_one_cl<Op, MODE, LD, RH, 0>(a, p, rt, st, set_attr);
 }
 
 template <typename Op>
@@ -1275,6 +1392,8 @@ cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStr
   rt.xchg_off = p.xchg_off;
   rt.w_resident = p.w_resident;
   rt.rotate = (p.c_tiles == 2 && (p.grid & 1) == 0 && p.total_tiles > p.grid) ? 1 : 0;
+  rt.cluster = p.cluster; rt.rows = p.rows; rt.groups = p.groups;
+  if (p.cluster) rt.rotate = 0;
   cudaError_t e;
   if (prec == 3) e = dispatch<OpF16>(a, p, rt, st, false, a.epi.mode, a.epi.ld, a.epi.res_half);
   else if (prec == 2) e = dispatch<OpBF16>(a, p, rt, st, false, a.epi.mode, a.epi.ld, a.epi.res_half);

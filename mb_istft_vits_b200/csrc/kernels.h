@@ -14,6 +14,8 @@ struct TcPlan {
   CUtensorMap tmA;      // activations: 3-D (Cp_in, L_in, B), box (KB, box_rows, 1), 128B swizzle
   CUtensorMap tmB;      // weights: 2-D (Cp_in, phases*taps*N_total), box (KB, 128), 128B swizzle
   CUtensorMap tmR;      // residual input (EPI_RES xin): 3-D (C, rows, B), box (128, n_time, 1), used for L2 prefetch only
+  CUtensorMap tmBh;     // weights with a 64-row box: the half tile a CTA of a cluster pair fetches and multicasts
+  int cluster, rows, groups;  // cluster mode (pairs of CTAs share every weight tile): see conv_tc.cu
   int prefetch_res;     // 1: tmR is valid
   int n_time;           // time columns per tile (UMMA N)
   int slab_rows, box_rows, n_boxes;

@@ -21,6 +21,7 @@ PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2, "fp16": 3}
 FLAG_FORCE_SIMT = 4
 FLAG_RESIDUAL_FP16 = 8
 FLAG_FUSED_PAIR = 16
+FLAG_CLUSTER_PAIRS = 32
 
 ERRORS = {0: "MBV_OK", -1: "MBV_ERR_INVALID", -2: "MBV_ERR_UNSUPPORTED", -3: "MBV_ERR_WEIGHTS",
           -4: "MBV_ERR_WORKSPACE", -5: "MBV_ERR_CUDA"}

@@ -96,6 +96,26 @@ def test_fused_resblock_pair_kernel_matches_two_launch_path(prec):
         assert orc.snr_db(got[1], t["o"]) > 40.0, case
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_cluster_pair_weight_multicast_is_bit_identical(prec):
+    """MBV_FLAG_CLUSTER_PAIRS: two CTAs per cluster share every weight tile by TMA multicast.  Same operands, same MMA
+    sequence per tile -> bit-identical waveforms, including the odd-tile-count case where one CTA only relays weights."""
+    from mb_istft_vits_b200 import lib as L
+    for case in ("mb", "ms_spk", "istft", "mb_long"):
+        cfg, sd, t, meta = load_case(case)
+        ref = _run(_engine(cfg, sd, prec, 0), t)
+        got = _run(_engine(cfg, sd, prec, L.FLAG_CLUSTER_PAIRS), t)
+        assert torch.equal(got[1], ref[1]) and torch.equal(got[0], ref[0]), case
+    # a size with more pairs than clusters, so the persistent loop and the ring hand-over between tiles are exercised
+    cfg = get_config("ljs_mb_istft_vits")
+    sd = synth.make_state_dict(cfg, seed=1234)
+    z_p, mask, _ = synth.make_latents(cfg, 9, 700, seed=5, lengths=[700, 650, 31, 700, 512, 700, 699, 1, 333])
+    a = _engine(cfg, sd, prec, 0).flow_decode(z_p.cuda(), mask.cuda())
+    b = _engine(cfg, sd, prec, L.FLAG_CLUSTER_PAIRS).flow_decode(z_p.cuda(), mask.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
+
+
 def test_fp16_tensor_core_path_vs_cuda_core_path():
     """fp16 operands through tcgen05 with single-stream epilogues vs the CUDA-core kernel with a separately stored
     (plain fp16) residual stream: different residual bookkeeping, same arithmetic up to fp16 re-rounding."""
