@@ -571,7 +571,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const int t0 = wk.tt * rt.n_time;
       const int wrow0 = phase * a.taps * a.N_total + ct * TC_M;
       const int xrow0 = t0 + a.shift0[phase];
-      if (rt.dbg && lane == 0) rt.dbg[((size_t)blockIdx.x * 5 + 0) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
+      if (rt.dbg && lane == 0) rt.dbg[((size_t)blockIdx.x * 7 + 0) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
       // (A whole-tile TMA L2 prefetch of the residual box issued here was measured to be too early: a tile-time later
       //  a third of it had been evicted again and DRAM reads grew 40 %.  The epilogue warps prefetch two chunks ahead.)
       if (false && MODE == EPI_RES && rt.prefetch_res && elect_one()) tma_prefetch_l2_3d(&tmR, ct * TC_M, t0, b);
@@ -629,18 +629,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
         continue;
       }
+      long long tw0 = rt.dbg ? clock64() : 0, wait_c = 0, wait_x = 0, wait_w = 0;
       mbar_wait(BAR(iCE + sc), pc ^ 1);
+      if (rt.dbg) wait_c = clock64() - tw0;
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(sc * TC_ACC_STRIDE);
-      if (rt.dbg && lane == 0) rt.dbg[((size_t)blockIdx.x * 5 + 1) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
+      if (rt.dbg && lane == 0) rt.dbg[((size_t)blockIdx.x * 7 + 1) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
       uint32_t accum = 0;
       for (int kb = 0; kb < kblocks; ++kb) {
+        if (rt.dbg) tw0 = clock64();
         mbar_wait(BAR(iXF + sx), px);
+        if (rt.dbg) wait_x += clock64() - tw0;
         tc_fence_after();
         uint32_t x_lo = desc_lo(smem_u32(smX + (size_t)sx * rt.slab_stage_bytes));
         for (int tap = 0; tap < a.taps; ++tap) {
           if (rt.w_resident) { sw = kb * a.taps + tap; pw = 0; }  // stage = (k-block, tap); phase 0 stays complete
+          if (rt.dbg) tw0 = clock64();
           mbar_wait(BAR(iWF + sw), pw);
+          if (rt.dbg) wait_w += clock64() - tw0;
           tc_fence_after();
           const uint32_t w_lo = desc_lo(smem_u32(smW + (size_t)sw * rt.w_stage_bytes));
           if (elect_one()) {
@@ -662,7 +668,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       if (elect_one()) tc_commit(BAR(iCF + sc));
       __syncwarp();
-      if (rt.dbg && lane == 0) rt.dbg[((size_t)blockIdx.x * 5 + 1) * 64 + 2 * ((tile / gridDim.x) & 31) + 1] = clock64();
+      if (rt.dbg && lane == 0) {
+        rt.dbg[((size_t)blockIdx.x * 7 + 1) * 64 + 2 * ((tile / gridDim.x) & 31) + 1] = clock64();
+        if (tile / (int)gridDim.x < 16) {  // issuer-side waits of this tile: accumulator free | slabs | weight tiles
+          long long* w = rt.dbg + ((size_t)blockIdx.x * 7 + 6) * 64 + 3 * (tile / gridDim.x);
+          w[0] = wait_c; w[1] = wait_x; w[2] = wait_w;
+        }
+      }
       if (++sc == 2) { sc = 0; pc ^= 1; }
     }
   } else if (warp < TC_EPI_WARPS) {
@@ -732,7 +744,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       if (!ti.row_ok) { ti = tn; tile += gridDim.x; continue; }  // cluster mode: this CTA only relayed weights for this tile
       mbar_wait(BAR(iCF + sc), pc);
       tc_fence_after();
-      if (rt.dbg && warp == 0 && lane == 0) rt.dbg[((size_t)blockIdx.x * 5 + 2) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
+      if (rt.dbg && warp == 0 && lane == 0) rt.dbg[((size_t)blockIdx.x * 7 + 2) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc * TC_ACC_STRIDE);
       float gate_bias = 0.f;
       if constexpr (MODE == EPI_GATE) {  // bias + cond_layer(g) of this thread's weight row, once per tile
@@ -744,7 +756,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         // debug stamps of warp 0's chunks (tiles 0..9): issue | accumulator in registers | residual in registers | done
         long long* cdbg = nullptr;
         if (rt.dbg && warp == 0 && lane == 0 && tile / (int)gridDim.x < 10)
-          cdbg = rt.dbg + ((size_t)blockIdx.x * 5 + 3) * 64 + ((tile / gridDim.x) * 3 + (c - c_first) / CSTEP) * 4;
+          cdbg = rt.dbg + ((size_t)blockIdx.x * 7 + 3) * 64 + ((tile / gridDim.x) * 3 + (c - c_first) / CSTEP) * 4;
         if (cdbg) cdbg[0] = clock64();
         tmem_ld32(taddr + (uint32_t)c, acc);
         if constexpr (kPrefetch) prefetch(ti, c, xcur);  // residual of THIS chunk, in flight with the TMEM load
@@ -801,7 +813,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(iCE + sc));
-      if (rt.dbg && warp == 0 && lane == 0) rt.dbg[((size_t)blockIdx.x * 5 + 2) * 64 + 2 * ((tile / gridDim.x) & 31) + 1] = clock64();
+      if (rt.dbg && warp == 0 && lane == 0) rt.dbg[((size_t)blockIdx.x * 7 + 2) * 64 + 2 * ((tile / gridDim.x) & 31) + 1] = clock64();
       if (++sc == 2) { sc = 0; pc ^= 1; }
       ti = tn;
       tile += gridDim.x;
@@ -1355,15 +1367,16 @@ cudaError_t tc_set_attributes() {
 // MBV_TIMELINE=<mode>: after every launch whose epilogue mode matches, print CTA 0's per-tile clock stamps (debug)
 static void timeline_dump(const ConvArgs& a, const TcPlan& p, long long* dbg, cudaStream_t st) {
   cudaStreamSynchronize(st);
-  std::vector<long long> hbuf(5 * 64);
+  std::vector<long long> hbuf(7 * 64);
   cudaMemcpy(hbuf.data(), dbg, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
   const int nt = (p.total_tiles + p.grid - 1) / p.grid;
   long long t0 = hbuf[0];
   fprintf(stderr, "[timeline] mode %d taps %d Cp_in %d N_total %d n_time %d tiles/CTA %d slab_st %d w_st %d\n", a.epi.mode, a.taps,
           a.Cp_in, a.N_total, p.n_time, nt, p.n_slab_stages, p.n_w_stages);
   for (int i = 0; i < nt && i < 32; ++i)
-    fprintf(stderr, "  tile %2d  prod_start %7lld | mma %7lld .. %7lld | epi %7lld .. %7lld\n", i, hbuf[2 * i] - t0,
-            hbuf[64 + 2 * i] - t0, hbuf[64 + 2 * i + 1] - t0, hbuf[128 + 2 * i] - t0, hbuf[128 + 2 * i + 1] - t0);
+    fprintf(stderr, "  tile %2d  prod_start %7lld | mma %7lld .. %7lld (waits: acc %5lld slab %5lld weights %5lld) | epi %7lld .. %7lld\n", i,
+            hbuf[2 * i] - t0, hbuf[64 + 2 * i] - t0, hbuf[64 + 2 * i + 1] - t0, i < 16 ? hbuf[384 + 3 * i] : 0, i < 16 ? hbuf[384 + 3 * i + 1] : 0,
+            i < 16 ? hbuf[384 + 3 * i + 2] : 0, hbuf[128 + 2 * i] - t0, hbuf[128 + 2 * i + 1] - t0);
   for (int i = 0; i < nt && i < 10; ++i)
     for (int j = 0; j < 3; ++j) {
       const long long* c = &hbuf[192 + (i * 3 + j) * 4];
@@ -1371,7 +1384,7 @@ static void timeline_dump(const ConvArgs& a, const TcPlan& p, long long* dbg, cu
       fprintf(stderr, "    tile %2d chunk %d  start %7lld | acc +%5lld | residual +%5lld | done +%5lld\n", i, j, c[0] - t0,
               c[1] - c[0], c[2] ? c[2] - c[0] : 0, c[3] - c[0]);
     }
-  cudaMemset(dbg, 0, 148 * 5 * 64 * sizeof(long long));
+  cudaMemset(dbg, 0, 148 * 7 * 64 * sizeof(long long));
 }
 
 cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStream_t st) {
@@ -1380,7 +1393,7 @@ cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStr
   if (dbg_mode == -2) {
     const char* e = getenv("MBV_TIMELINE");
     dbg_mode = e ? atoi(e) : -1;
-    if (dbg_mode >= 0) { cudaMalloc(&dbg, 148 * 5 * 64 * sizeof(long long)); cudaMemset(dbg, 0, 148 * 5 * 64 * sizeof(long long)); }
+    if (dbg_mode >= 0) { cudaMalloc(&dbg, 148 * 7 * 64 * sizeof(long long)); cudaMemset(dbg, 0, 148 * 7 * 64 * sizeof(long long)); }
   }
   TcRt rt;
   rt.dbg = (dbg_mode >= 0 && a.epi.mode == dbg_mode) ? dbg : nullptr;
