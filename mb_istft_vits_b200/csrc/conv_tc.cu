@@ -249,6 +249,11 @@ struct TcRt {  // runtime scalars the kernel needs beyond ConvArgs
   int cluster;       // 1: launched as clusters of 2 CTAs that work on two time tiles of the SAME (phase, channel tile) in
                      // lock step; every weight tile is fetched once per pair (each CTA loads half and multicasts it)
   int rows, groups;  // cluster mode: B * t_tiles time tiles, n_phases * c_tiles weight groups
+  // Tail-wave split: the persistent grid's last, partial round (total_tiles % grid tiles) would keep most SMs idle for a
+  // whole tile time; those tiles are cut into split_k column pieces of split_n columns, one per CTA.  Virtual tile
+  // indices >= split_from address the pieces.  (Results are bit-identical: a column's accumulation does not depend on
+  // the tile width.)
+  int split_from, split_k, split_n, virt_tiles;
   int rotate;        // two channel tiles, even grid: swap which one a CTA takes every round.  With a static round-robin
                      // an even CTA would otherwise ALWAYS get channel tile 0; when the second tile is half padding
                      // (192 = 128 + 64 rows: flow pre / res convs) its epilogue is half the work and half the CTAs idle.
@@ -540,9 +545,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   // tile index -> (channel tile, phase, time tile, utterance, does this CTA have a time tile).  Cluster mode walks pairs:
   // tiles 2w and 2w+1 (always on the two CTAs of one cluster, the grid is even) share the weight group w % groups and take
   // the time tiles 2j and 2j+1, j = w / groups; the odd one out at the end only relays weight tiles.
-  struct Work { int ct, phase, tt, b; bool row_ok; };
+  struct Work { int ct, phase, tt, b, t_off, n_cols; bool row_ok; };
   auto decode_work = [&](int tile) {
     Work wk;
+    wk.t_off = 0; wk.n_cols = rt.n_time;
+    if (tile >= rt.split_from && rt.split_k > 1) {  // a piece of a tile of the last round
+      const int s = tile - rt.split_from;
+      tile = rt.split_from + s / rt.split_k;
+      wk.t_off = (s % rt.split_k) * rt.split_n;
+      wk.n_cols = min(rt.split_n, rt.n_time - wk.t_off);
+    }
     if ((CL != 0)) {
       const int w = tile >> 1, grp = w % rt.groups, row = 2 * (w / rt.groups) + (tile & 1);
       wk.ct = grp % rt.c_tiles; wk.phase = grp / rt.c_tiles;
@@ -565,10 +577,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     // elected lane issues the copies.
     int sx = 0, sw = 0;
     uint32_t px = 0, pw = 0;
-    for (int tile = blockIdx.x; tile < rt.total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < rt.virt_tiles; tile += gridDim.x) {
       const Work wk = decode_work(tile);
       const int ct = wk.ct, phase = wk.phase, b = wk.b;
-      const int t0 = wk.tt * rt.n_time;
+      const int t0 = wk.tt * rt.n_time + wk.t_off;
       const int wrow0 = phase * a.taps * a.N_total + ct * TC_M;
       const int xrow0 = t0 + a.shift0[phase];
       if (rt.dbg && lane == 0) rt.dbg[((size_t)blockIdx.x * 7 + 0) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
@@ -612,12 +624,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16 or tf32, both K-major, N, M=128
     constexpr uint32_t fmt = (Op::kPrec == 3) ? 0u : ((Op::kPrec == 2) ? 1u : 2u);  // F16 / BF16 / TF32
     constexpr int KIND = (Op::kPrec >= 2) ? 2 : 1;
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(rt.n_time >> 3) << 17) |
-                           ((uint32_t)(TC_M >> 4) << 24);
+    const uint32_t idesc0 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_M >> 4) << 24);
     const uint32_t tap_step = (uint32_t)(a.dil * TC_ROW_BYTES) >> 4;  // descriptor-lo increment per tap
     int sx = 0, sw = 0, sc = 0;
     uint32_t px = 0, pw = 0, pc = 0;
-    for (int tile = blockIdx.x; tile < rt.total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < rt.virt_tiles; tile += gridDim.x) {
       if ((CL != 0) && !decode_work(tile).row_ok) {
         // no time tile for this CTA (odd tile count): keep the pair's weight ring moving -- wait until each stage has
         // fully landed here, then release it on both CTAs
@@ -629,6 +640,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
         continue;
       }
+      const uint32_t idesc = idesc0 | ((uint32_t)(decode_work(tile).n_cols >> 3) << 17);  // UMMA N = this tile's columns
       long long tw0 = rt.dbg ? clock64() : 0, wait_c = 0, wait_x = 0, wait_w = 0;
       mbar_wait(BAR(iCE + sc), pc ^ 1);
       if (rt.dbg) wait_c = clock64() - tw0;
@@ -688,7 +700,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     int sc = 0;
     uint32_t pc = 0;
 
-    struct TileInfo { int b, n, phase, t0, t_lim; bool valid, row_ok; };
+    struct TileInfo { int b, n, phase, t0, t_lim, n_cols; bool valid, row_ok; };
     auto decode = [&](int tile) {
       TileInfo ti;
       const Work wk = decode_work(tile);
@@ -696,13 +708,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       ti.phase = wk.phase;
       ti.b = wk.b;
       ti.row_ok = wk.row_ok;
-      ti.t0 = wk.tt * rt.n_time;
+      ti.t0 = wk.tt * rt.n_time + wk.t_off;
+      ti.n_cols = wk.n_cols;
       ti.n = ct * TC_M + q * 32 + lane;  // weight row = output channel of this thread
       // which logical channel does this row write, and is it inside the destination buffer?
       if (MODE == EPI_RS && a.epi.n_split > 0) ti.valid = (ti.n < a.epi.n_split ? ti.n : ti.n - a.epi.n_split) < n_valid;
       else if (MODE == EPI_GATE) ti.valid = (64 * ct + ((q * 32 + lane) & 63)) < n_valid;  // logical channel of this row
       else ti.valid = ti.n < n_valid;
-      ti.t_lim = min(a.L_out, ti.t0 + rt.n_time);
+      ti.t_lim = min(a.L_out, ti.t0 + wk.n_cols);
       return ti;
     };
     // The residual loads are latency-bound (per-tile timelines, MBV_TIMELINE).  L2 prefetches cost no registers, so at
@@ -711,7 +724,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     auto l2_prefetch = [&](const TileInfo& ti, int c) {
       if constexpr (MODE == EPI_RES) {
         const int t = ti.t0 + c + lane;
-        if (ti.valid && c < rt.n_time && t < ti.t_lim) {
+        if (ti.valid && c < ti.n_cols && t < ti.t_lim) {
           const size_t off = ((size_t)ti.b * a.epi.rows_res + t) * a.epi.ld + (ti.n - lane);
           const char* p = reinterpret_cast<const char*>(a.epi.xin) + off * (RH != 0 ? 2 : 4);
           asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -731,11 +744,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     int gate_chunk = 0;
     int tile = blockIdx.x;
     TileInfo ti = decode(tile);
-    if (kPrefetch && tile < rt.total_tiles)
+    if (kPrefetch && tile < rt.virt_tiles)
       for (int j = 0; j < nch; ++j) l2_prefetch(ti, c_first + CSTEP * j);
 
-    while (tile < rt.total_tiles) {
-      const bool have_next = tile + (int)gridDim.x < rt.total_tiles;
+    while (tile < rt.virt_tiles) {
+      const bool have_next = tile + (int)gridDim.x < rt.virt_tiles;
       TileInfo tn = ti;
       if (have_next) {
         tn = decode(tile + gridDim.x);
@@ -751,7 +764,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         gate_bias = a.epi.bias[(size_t)ti.b * a.epi.bias_bs + ti.n];
         if (a.epi.add2) gate_bias += a.epi.add2[(size_t)ti.b * a.epi.add2_bs + ti.n];
       }
-      for (int c = c_first; c < rt.n_time; c += CSTEP) {
+      for (int c = c_first; c < ti.n_cols; c += CSTEP) {
         float acc[32];
         // debug stamps of warp 0's chunks (tiles 0..9): issue | accumulator in registers | residual in registers | done
         long long* cdbg = nullptr;
@@ -1407,6 +1420,22 @@ cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStr
   rt.rotate = (p.c_tiles == 2 && (p.grid & 1) == 0 && p.total_tiles > p.grid) ? 1 : 0;
   rt.cluster = p.cluster; rt.rows = p.rows; rt.groups = p.groups;
   if (p.cluster) rt.rotate = 0;
+  rt.split_from = p.total_tiles; rt.split_k = 1; rt.split_n = p.n_time; rt.virt_tiles = p.total_tiles;
+  static const int no_split = getenv("MBV_NO_SPLIT") ? atoi(getenv("MBV_NO_SPLIT")) : 0;  // A/B measurements only
+  const int rem = p.total_tiles % p.grid;
+  if (!no_split && !p.cluster && p.total_tiles > p.grid && rem > 0 && 2 * rem <= p.grid) {
+    int k = p.grid / rem;                          // pieces per tile so that the last round still fits the grid
+    const int kmax = p.n_time / 64;                // pieces of >= 64 columns
+    if (k > kmax) k = kmax;
+    if (k >= 2) {
+      const int n_sub = ((p.n_time + k - 1) / k + 15) / 16 * 16;
+      const int ksub = (p.n_time + n_sub - 1) / n_sub;
+      if (ksub >= 2 && rem * ksub <= p.grid) {
+        rt.split_from = p.total_tiles - rem; rt.split_k = ksub; rt.split_n = n_sub;
+        rt.virt_tiles = rt.split_from + rem * ksub;
+      }
+    }
+  }
   cudaError_t e;
   if (prec == 3) e = dispatch<OpF16>(a, p, rt, st, false, a.epi.mode, a.epi.ld, a.epi.res_half);
   else if (prec == 2) e = dispatch<OpBF16>(a, p, rt, st, false, a.epi.mode, a.epi.ld, a.epi.res_half);
