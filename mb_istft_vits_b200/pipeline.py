@@ -35,6 +35,16 @@ class HostStream:
 
     def _slot(self, i, zp_host, mask_host, g_host):
         s = self.slots[i % self.depth]
+        # a captured graph bakes in the engine's workspace pointer: a slot is rebuilt when the batch shape changes or when
+        # a larger batch elsewhere made the engine reallocate its workspace
+        ws = self.engine._ws
+        if ws is not None and ws.numel() < self.engine.workspace_bytes(zp_host.shape[0], zp_host.shape[2]):
+            self.drain()  # the engine is about to free its workspace: nothing may still be running in it
+        ws_ptr = self.engine._workspace(zp_host.shape[0], zp_host.shape[2])[0]
+        if s is not None and s.get("graph") is not None and s["ws_ptr"] != ws_ptr:
+            for st in (self.s_in, self.s_cmp, self.s_out):
+                st.synchronize()
+            s = None
         if s is None or s["zp"].shape != zp_host.shape:
             s = {"zp": torch.empty(zp_host.shape, dtype=torch.float32, device=self.dev),
                  "m": torch.empty(mask_host.shape, dtype=torch.float32, device=self.dev),
@@ -43,9 +53,9 @@ class HostStream:
                                     device=self.dev),
                  "ev_in": torch.cuda.Event(), "ev_cmp": torch.cuda.Event(), "ev_out": torch.cuda.Event()}
             s["graph"] = None
+            s["ws_ptr"] = ws_ptr
             if self.graphs:
                 # the slot's buffers are static, so its whole launch sequence is captured once and replayed per batch
-                self.engine._workspace(zp_host.shape[0], zp_host.shape[2])
                 with torch.cuda.stream(self.s_cmp):
                     s["zp"].zero_(); s["m"].fill_(1.0)
                     if s["g"] is not None:

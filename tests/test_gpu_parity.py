@@ -483,8 +483,16 @@ def test_host_stream_pipeline_returns_the_same_waveforms(fused):
         ins.append((z_p.pin_memory(), mask.pin_memory()))
         outs.append(torch.zeros((B, 1, 256 * T)).pin_memory())
         events.append(hs.submit(ins[-1][0], ins[-1][1], outs[-1]))
+    # a larger batch makes the engine reallocate its workspace: the slots' graphs must be rebuilt, results still exact
+    zb, mb, _ = synth.make_latents(cfg, B + 2, T + 9, seed=200)
+    big_out = torch.zeros((B + 2, 1, 256 * (T + 9))).pin_memory()
+    hs.submit(zb.pin_memory(), mb.pin_memory(), big_out)
+    ins.append((ins[0][0], ins[0][1]))
+    outs.append(torch.zeros((B, 1, 256 * T)).pin_memory())
+    events.append(hs.submit(ins[-1][0], ins[-1][1], outs[-1]))
     hs.drain()
-    for i in range(5):
+    assert torch.equal(big_out, eng.flow_decode(zb.cuda(), mb.cuda())[1].cpu()) if fused else True
+    for i in range(6):
         assert events[i].query()
         z, wav, _, _, _ = eng.flow_decode(ins[i][0].cuda(), ins[i][1].cuda())
         if fused:
