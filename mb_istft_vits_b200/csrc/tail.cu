@@ -1019,6 +1019,100 @@ static cudaError_t launch_tail_mb(const TailArgs& a, int precise, int num_sms, c
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Single-band tail, v3: lane = STFT frame, overlap-add by warp shuffles, hop blocks stored straight from registers.
+// Each WARP covers 32 consecutive frames = 29 complete hop blocks and the warps of a CTA overlap by 3 frames, so there
+// is no cross-warp exchange and only ONE block barrier (after the coalesced copy of the logits rows); the 10 % of
+// repeated head work buys the removal of the frame scratch round trip and the second barrier of the v1 kernel
+// (tail_kernel<0>, 96 us on the BASELINE-size problem).  Arithmetic identical to v1.
+// ------------------------------------------------------------------------------------------------
+constexpr int SB_THREADS = 256;
+constexpr int SB_NQ = 29 * (SB_THREADS / 32);   // 232 owned hop blocks per CTA
+constexpr int SB_ROWS = SB_NQ + 3;              // 235 frames held in shared memory
+
+template <bool PRECISE>
+__global__ void __launch_bounds__(SB_THREADS) tail_sb3_kernel(const __grid_constant__ TailArgs a, int tiles_per_utt) {
+  __shared__ __align__(16) float s_log[SB_ROWS * 18 + 4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / tiles_per_utt, tile = blockIdx.x % tiles_per_utt;
+  const int L = a.L, F = L + 1;
+  const int Q0 = tile * SB_NQ, F0 = Q0 - 1;
+  const int nq = min(SB_NQ, L - Q0);
+  const bool last_tile = (Q0 + nq == L);
+  // ---- coalesced copy of the logits rows [F0, F0 + 235) /\ [0, F); rows outside the utterance are zero-filled
+  {
+    const int f_lo = max(F0, 0), f_hi = min(F0 + SB_ROWS, F);
+    const float* src = a.logits + ((size_t)b * F + f_lo) * 18;
+    float* dst = s_log + (f_lo - F0) * 18;
+    const int n = (f_hi - f_lo) * 18;
+    for (int i = tid; i < (f_lo - F0) * 18; i += SB_THREADS) s_log[i] = 0.f;
+    for (int i = (f_hi - F0) * 18 + tid; i < SB_ROWS * 18; i += SB_THREADS) s_log[i] = 0.f;
+    if ((((size_t)b * F + f_lo) * 18 & 3) == 0 && (((f_lo - F0) * 18) & 3) == 0) {
+      const int n4 = n >> 2;
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* d4 = reinterpret_cast<float4*>(dst);
+      for (int i = tid; i < n4; i += SB_THREADS) d4[i] = __ldg(s4 + i);
+      for (int i = (n4 << 2) + tid; i < n; i += SB_THREADS) dst[i] = __ldg(src + i);
+    } else {
+      for (int i = tid; i < n; i += SB_THREADS) dst[i] = __ldg(src + i);
+    }
+  }
+  __syncthreads();
+  // ---- head + inverse DFT + window for frame F0 + r, r = 29 * warp + lane
+  const int r = 29 * warp + lane;
+  const int f = F0 + r;
+  const bool live = (f >= 0) && (f < F);
+  float fr[16];
+  {
+    const float2* lp = reinterpret_cast<const float2*>(s_log + r * 18);  // stride 18 words: conflict-free 8-byte loads
+    float x[18];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { const float2 v = lp[i]; x[2 * i] = v.x; x[2 * i + 1] = v.y; }
+    // this lane emits spec / phase of its frame if it is the frame's owner (rows 29w..29w+28; the last warp also its tail rows)
+    const bool owner = (lane < 29) || (warp == SB_THREADS / 32 - 1);
+    const bool emit = (a.spec != nullptr) && live && owner && (f >= Q0) && (f < Q0 + nq || (last_tile && f == L));
+    float re[9], im[9];
+    const float keep = live ? 1.f : 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      float mag, ph;
+      head<PRECISE>(x[k], x[9 + k], mag, ph, re[k], im[k]);
+      if (emit) {
+        const size_t o = ((size_t)b * 9 + k) * F + f;
+        a.spec[o] = mag;
+        a.phase[o] = ph;
+      }
+      re[k] *= keep; im[k] *= keep;
+    }
+    idft16_windowed<float>(re, im, fr);
+  }
+  // ---- overlap-add: hop block q = f + 1 = part 3 of this frame + part 2 / 1 / 0 of the next three frames
+  float4 y = make_float4(fr[12], fr[13], fr[14], fr[15]);
+  add4(y, shfl_down4(fr + 8, 1));
+  add4(y, shfl_down4(fr + 4, 2));
+  add4(y, shfl_down4(fr, 3));
+  const int q = Q0 + r;
+  if (lane < 29 && r < nq) {
+    if (PRECISE || q == 0 || q == L - 1) {
+      float e0 = 1.5f, e1 = 1.5f, e2 = 1.5f, e3 = 1.5f;
+      if (q == 0) { e0 -= win_sq(12); e1 -= win_sq(13); e2 -= win_sq(14); e3 -= win_sq(15); }
+      if (q == L - 1) { e0 -= win_sq(0); e1 -= win_sq(1); e2 -= win_sq(2); e3 -= win_sq(3); }
+      y.x /= e0; y.y /= e1; y.z /= e2; y.w /= e3;
+    } else {
+      const float inv = 0.66666666666666667f;
+      y.x *= inv; y.y *= inv; y.z *= inv; y.w *= inv;
+    }
+    *reinterpret_cast<float4*>(a.wav + (size_t)b * 4 * L + 4 * (size_t)q) = y;
+  }
+}
+
+static cudaError_t launch_tail_sb3(const TailArgs& a, int precise, cudaStream_t st) {
+  const int tiles = (a.L + SB_NQ - 1) / SB_NQ;
+  if (precise) tail_sb3_kernel<true><<<a.B * tiles, SB_THREADS, 0, st>>>(a, tiles);
+  else tail_sb3_kernel<false><<<a.B * tiles, SB_THREADS, 0, st>>>(a, tiles);
+  return cudaGetLastError();
+}
+
 template <int VARIANT, bool PRECISE>
 static cudaError_t launch_tail_t(const TailArgs& a, cudaStream_t st) {
   constexpr int S = VARIANT == 0 ? 1 : 4;
@@ -1037,8 +1131,11 @@ static cudaError_t launch_tail_t(const TailArgs& a, cudaStream_t st) {
 }
 
 cudaError_t launch_tail(const TailArgs& a, int precise, int num_sms, cudaStream_t st) {
-  if (a.variant == 0) return precise ? launch_tail_t<0, true>(a, st) : launch_tail_t<0, false>(a, st);
   static const int use_v2 = getenv("MBV_TAIL_V2") ? atoi(getenv("MBV_TAIL_V2")) : 0;  // A/B measurements only
+  if (a.variant == 0) {
+    if (use_v2) return precise ? launch_tail_t<0, true>(a, st) : launch_tail_t<0, false>(a, st);
+    return launch_tail_sb3(a, precise, st);
+  }
   if (use_v2) return launch_tail_mb(a, precise, num_sms, st);
   return launch_tail_mb3(a, precise, num_sms, st);
 }
