@@ -389,6 +389,10 @@ __device__ __forceinline__ void epi_rs(const EpiParams& p, int b, int n, int pha
     if constexpr (RH == 2) {  // the operand copy is the stream
 #pragma unroll
       for (int i = 0; i < 32; ++i) MBV_EL(i) op_store1<Op>(dst + i * step, x[i]);
+    } else if constexpr (RH == 1) {  // fp16 stream next to the bf16 operand copy
+      __half* xo = reinterpret_cast<__half*>(p.xout) + base;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) MBV_EL(i) { xo[i * step] = to_half_sat(x[i]); op_store1<Op>(dst + i * step, x[i]); }
     } else {
       float* xo = reinterpret_cast<float*>(p.xout) + base;
 #pragma unroll
@@ -445,7 +449,7 @@ __device__ __forceinline__ void epi_dispatch(const EpiParams& p, int b, int n, i
 template <int MODE, int LD, int RH>
 __device__ __forceinline__ void epi_prefetch(const EpiParams& p, int b, int n, int t_first, int nt, float* xpre) {
   const size_t step = LD > 0 ? (size_t)LD : (size_t)p.ld;
-  if constexpr ((MODE == EPI_RES && RH != 0) || (MODE == EPI_RS && RH == 2)) {
+  if constexpr ((MODE == EPI_RES && RH != 0) || (MODE == EPI_RS && RH != 0)) {
     // (EPI_RS single stream: every row of the conv is a residual row, xin = the fp16 operand tensor h)
     const __half* hs = reinterpret_cast<const __half*>(p.xin) + ((size_t)b * p.rows_res + t_first) * p.ld + n;
     if (nt == 32) {
@@ -1330,9 +1334,11 @@ static cudaError_t dispatch(const ConvArgs& a, const TcPlan& p, const TcRt& rt, 
     if constexpr (Op::kPrec == 2) {
 #define MBV_CASE_H(M, L) if (mode == M && ld == L) return launch_one<Op, M, L, 1>(a, p, rt, st, set_attr);
       MBV_CASE_H(EPI_ACT, 128) MBV_CASE_H(EPI_ACT, 256) MBV_CASE_H(EPI_RES, 128) MBV_CASE_H(EPI_RES, 256)
+      MBV_CASE_H(EPI_ACT, 192) MBV_CASE_H(EPI_RS, 192)
 #undef MBV_CASE_H
       if (mode == EPI_ACT) return launch_one<Op, EPI_ACT, 0, 1>(a, p, rt, st, set_attr);
       if (mode == EPI_RES) return launch_one<Op, EPI_RES, 0, 1>(a, p, rt, st, set_attr);
+      if (mode == EPI_RS) return launch_one<Op, EPI_RS, 0, 1>(a, p, rt, st, set_attr);
     }
     return cudaErrorInvalidValue;
   }
@@ -1365,7 +1371,7 @@ cudaError_t tc_set_attributes() {
       if (e != cudaSuccess) return e;
       e = dispatch<OpF16>(a, p, rt, nullptr, true, mode, ld, 0);
       if (e != cudaSuccess) return e;
-      if (mode == EPI_ACT || mode == EPI_RES) {
+      if (mode == EPI_ACT || mode == EPI_RES || mode == EPI_RS) {
         e = dispatch<OpBF16>(a, p, rt, nullptr, true, mode, ld, 1);
         if (e != cudaSuccess) return e;
       }

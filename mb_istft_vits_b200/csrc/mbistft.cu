@@ -796,6 +796,7 @@ int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, co
   mbv_handle* h = cx.h;
   const mbv_config& c = h->cfg;
   const int Hp = h->Hp, NL = c.flow_layers;
+  const bool tc_path = h->prec >= MBV_PREC_BF16 && !(c.flags & MBV_FLAG_FORCE_SIMT);  // (the CUDA-core epilogues keep h in fp32)
   {
     ProfScope prof(cx, 2);
     CUDA_TRY(h, launch_pack_input(h->prec, z_p, nullptr, f.zop, f.z, B, h->Cz, T, h->Cz, cx.st));
@@ -814,6 +815,7 @@ int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, co
     {  // h = pre(x0) * mask
       EpiParams e = epi_base(EPI_ACT, Hp, T);
       e.mask = mask; e.xout = h->single ? nullptr : f.h; e.act[0] = f.hop; e.n_act = 1;  // single: the fp16 operand copy IS h
+      if (!h->single && h->res_half && tc_path) e.res_half = 1;  // bf16 + fp16 streams: h is carried in fp16 next to its bf16 operand copy
       if ((rc = run_conv(cx, h->fl_pre[f_i], f.zop, B, T, T, e))) return rc;
     }
     const int Ha = NL * Hp;  // channel pitch of the gate-output buffer: one Hp-wide slot per WN layer
@@ -829,6 +831,7 @@ int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, co
         EpiParams e = epi_base(EPI_RS, Hp, T);
         e.mask = mask; e.n_split = h->fl_rs[f_i][l].N_total; e.xin = f.h; e.xout = f.h; e.act[0] = f.hop; e.n_act = 1;
         if (h->single) { e.xin = f.hop; e.xout = nullptr; e.res_half = 2; e.inv_slope = 1.f; }
+        else if (h->res_half && tc_path) e.res_half = 1;
         const char* ax = (const char*)f.acts + (size_t)l * Hp * h->esize;
         if ((rc = run_conv(cx, h->fl_rs[f_i][l], ax, B, T, T, e, Ha))) return rc;
       }
