@@ -590,7 +590,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       if (rt.dbg && lane == 0) rt.dbg[((size_t)blockIdx.x * 7 + 0) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
       // (A whole-tile TMA L2 prefetch of the residual box issued here was measured to be too early: a tile-time later
       //  a third of it had been evicted again and DRAM reads grew 40 %.  The epilogue warps prefetch two chunks ahead.)
-      if (false && MODE == EPI_RES && rt.prefetch_res && elect_one()) tma_prefetch_l2_3d(&tmR, ct * TC_M, t0, b);
       for (int kb = 0; kb < kblocks; ++kb) {
         if (wk.row_ok) {
           mbar_wait(BAR(iXE + sx), px ^ 1);

@@ -28,13 +28,6 @@ constexpr int TAIL_NF = 256;        // frames per band per tile
 constexpr int FR_PITCH = 20;        // floats per frame row in smem (16 + pad: conflict-free float4)
 constexpr int YMB_PITCH = 1024;     // floats per band in the sub-band tile (253 * 4 = 1012 used)
 
-// cos(2*pi*m/16)
-__device__ constexpr float kCos16[16] = {
-    1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
-    0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f,
-    -1.0f, -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f,
-    0.0f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f};
-
 // periodic Hann / 16 (the irfft normalisation folded in): w[n] = 0.5 - 0.5 cos(2 pi n / 16)
 __device__ constexpr float kWin16[16] = {
     0.0f / 16, 0.03806023374435663f / 16, 0.14644660940672624f / 16, 0.30865828381745514f / 16,
