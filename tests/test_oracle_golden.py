@@ -52,3 +52,13 @@ def test_flow_is_not_vacuous():
     (SURVEY 8c trap 1); the synthetic weights must exercise the WN stack."""
     cfg, sd, t, meta = load_case("mb")
     assert (t["z"] - t["z_p"]).abs().max() > 1e-2
+
+
+@pytest.mark.parametrize("name", ["mini_mb", "ms_spk"])
+def test_oracle_flow_forward_inverts_flow_reverse(name):
+    """The two directions of the coupling block are exact inverses on the unmasked frames (mean-only couplings):
+    forward(reverse(z_p)) == z_p * mask up to fp32 rounding."""
+    cfg, sd, t, meta = load_case(name)
+    g = t.get("g")
+    back = orc.flow_forward(sd, cfg, orc.flow_reverse(sd, cfg, t["z_p"], t["mask"], g), t["mask"], g)
+    assert (back - t["z_p"] * t["mask"]).abs().max() < 2e-5
