@@ -345,6 +345,38 @@ def run_native(args):
     tail_ms = t0e.elapsed_time(t1e) / 10
     del logits
 
+    # ---------------- the reference's own arithmetic as PyTorch eager ops ON THIS GPU ("the real bar to beat"):
+    # the oracle port issues the same F.conv1d / conv_transpose1d / torch.istft calls as the reference modules; fp32 with
+    # TF32 off (the gold setting) and with PyTorch's default TF32 convs.  Bounded sample, rank 0 at N = 1 only.
+    torch_eager = None
+    if world == 1 and not args.no_cpu:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import mbistft_oracle as orc
+            Bs = min(B, 16)
+            sd_dev = {k: v.to(dev) for k, v in sd.items()}
+            zs, ms = z_p[:Bs].contiguous(), mask[:Bs].contiguous()
+            torch_eager = {"sample": f"oracle port (the reference's torch ops) on cuda, B={Bs} x T={T}, best of 3", "unit": UNIT}
+            for label, tf32 in (("fp32", False), ("tf32", True)):
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                best = None
+                with torch.no_grad():
+                    for i in range(4):
+                        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        g0.record()
+                        orc.flow_decode(sd_dev, cfg, zs, ms)
+                        g1.record()
+                        torch.cuda.synchronize()
+                        if i > 0:
+                            t = g0.elapsed_time(g1)
+                            best = t if best is None else min(best, t)
+                torch_eager[label] = Bs * T * 256 / (best * 1e-3)
+                torch_eager[label + "_ms"] = best
+            del sd_dev
+        except Exception as e:  # the leg is informational: never fail the bench on it
+            torch_eager = {"error": repr(e)}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -412,7 +444,8 @@ def run_native(args):
         "roofline": roofline, "roofline_tail": roofline_tail, "cpu_baseline": cpu_baseline,
         "extras": {"decoder_only_ms": dec_ms, "decoder_only_samples_per_s": samples_per_step / (dec_ms * 1e-3),
                    "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
-                   "tflops_whole_step": flops_step / (ms_step * 1e-3) / 1e12},
+                   "tflops_whole_step": flops_step / (ms_step * 1e-3) / 1e12,
+                   "torch_eager_gpu": torch_eager},
     }
     if dist is not None:
         dist.destroy_process_group()

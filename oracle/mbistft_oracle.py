@@ -174,7 +174,7 @@ def hann_periodic(n):
 
 def istft_torch(mag, phase, n_fft, hop):
     """TorchSTFT.inverse (stft.py:197-202): torch.istft(mag * exp(j*phase))."""
-    win = torch.from_numpy(hann_periodic(n_fft))
+    win = torch.from_numpy(hann_periodic(n_fft)).to(mag.device)
     return torch.istft(mag * torch.exp(phase * 1j), n_fft, hop, n_fft, window=win)
 
 
@@ -228,7 +228,7 @@ def pqmf_synthesis_filter(subbands=4, taps=62, cutoff_ratio=0.15, beta=9.0):
 
 def zero_stuff(y_mb, subbands):
     """F.conv_transpose1d(x, updown_filter * subbands, stride=subbands) (pqmf.py:115, models.py:463)."""
-    filt = torch.zeros(subbands, subbands, subbands)
+    filt = torch.zeros(subbands, subbands, subbands, device=y_mb.device)
     for k in range(subbands):
         filt[k, k, 0] = 1.0
     return F.conv_transpose1d(y_mb, filt * subbands, stride=subbands)
@@ -236,7 +236,7 @@ def zero_stuff(y_mb, subbands):
 
 def pqmf_synthesis(y_mb, subbands=4):
     """PQMF.synthesis (pqmf.py:105-116)."""
-    hs = torch.from_numpy(pqmf_synthesis_filter(subbands)).float().unsqueeze(0)  # [1,S,63]
+    hs = torch.from_numpy(pqmf_synthesis_filter(subbands)).float().unsqueeze(0).to(y_mb.device)  # [1,S,63]
     up = zero_stuff(y_mb, subbands)
     return F.conv1d(F.pad(up, (31, 31)), hs)
 
