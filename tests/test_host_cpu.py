@@ -105,3 +105,25 @@ def test_from_reference_json_maps_the_three_decoder_booleans():
     d["model"]["mb_istft_vits"] = False
     with pytest.raises(ValueError):
         from_reference_json(d)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16", "fp16"])
+def test_every_precision_and_flag_combination_validates_without_gpu(lib, prec):
+    """mbv_create accepts the four precisions (and the experimental flags on the 16-bit ones), rejects the fp16 residual
+    flag on the fp32 / tf32 paths, and every new compute entry fails loudly without a device."""
+    cfg = get_config("ljs_mb_istft_vits")
+    for flags in (0, L.FLAG_FUSED_PAIR | L.FLAG_CLUSTER_PAIRS):
+        h = C.c_void_p()
+        c = L.make_config(cfg, prec, flags=flags)
+        assert lib.mbv_create(C.byref(c), C.byref(h)) == 0
+        lib.mbv_destroy(h)
+    h = C.c_void_p()
+    c = L.make_config(cfg, prec, flags=L.FLAG_RESIDUAL_FP16)
+    rc = lib.mbv_create(C.byref(c), C.byref(h))
+    assert (rc == 0) == (prec in ("bf16", "fp16"))
+    if not torch.cuda.is_available():
+        one = (C.c_float * 4)()
+        p = C.cast(one, C.c_void_p)
+        assert lib.mbv_expand_prior(h, p, p, p, None, p, 1.0, 1, 1, 1, 1, p, p, None, None, None, None, None) != 0
+        assert lib.mbv_flow_forward(h, p, p, None, p, 1, 1, p, 1 << 20, None) != 0
+    lib.mbv_destroy(h)
