@@ -10,32 +10,37 @@ For N > 1 (launched under torchrun, one rank per GPU) every rank runs its own 64
 independent, so there is no collective on the hot path -- and the whole-job value is N * samples / max-over-ranks time.
 
 One JSON line is printed by rank 0:
-  value       device-resident throughput (inputs already in HBM), CUDA events, max over ranks
-  e2e         the same metric through the public API (NativeFlow / NativeDecoder modules) with pinned HOST inputs
-              and a HOST copy of the waveform inside the timed region
-  roofline    the conv implicit-GEMM kernel (dominant): algorithmic FLOP/s vs the measured bf16 peak;
-              roofline_tail: the fused iSTFT/PQMF tail vs the measured HBM copy bandwidth
-  cpu_baseline the CPU oracle port (same torch ops as the reference) timed on this box's host cores (rank 0, N=1)
+  value        device-resident throughput (inputs already in HBM), CUDA events around K CUDA-graph replays, max over ranks
+  e2e          the same metric through the public API with pinned HOST inputs and a HOST copy of the waveform inside
+               the timed region (HostStream serving loop)
+  roofline     the conv implicit-GEMM kernels (dominant): algorithmic FLOP/s vs the measured bf16 peak.  Kernel time is
+               derived INSIDE the graph-timed region (step time minus the event-timed non-conv launches), so the sum of
+               kernel times never exceeds ms_per_step; fractions are given against the sustained AND the burst peak and
+               a >= 3 s sustained leg (clocks sampled) is reported next to the short timed region
+  roofline_tail  the fused iSTFT/PQMF tail vs the measured HBM copy bandwidth
+  cpu_baseline the reference's own modules (baseline/_ref, kind "reference"; the oracle port if the reference is not
+               staged) timed on this box's host cores (rank 0, N = 1)
+  extras       tf32 path line, PyTorch-eager reference on the same GPU, BASELINE configs 3 and 5 with the NCCL gather
 
---impl reference times that CPU oracle port as the reference arm (the reference is Python/PyTorch; its modules
-cannot travel to the GPU box, the oracle restates them with the same torch primitives -- see DESIGN.md).
+--impl reference times the reference's CPU implementation as the reference arm.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "baseline"))
 
 CONFIG_NAME = "ljs_mb_istft_vits"
 B_PER_GPU = 64
 T_FRAMES = 862
+CPU_SAMPLE_B = 8   # BASELINE.md section 3: B = 8 x T = 862 on the host cores (CPU throughput is batch-independent)
 METRIC = "decoder audio samples/sec (flow-reverse + MB-iSTFT decoder, batch 64 x 10 s per GPU)"
 UNIT = "samples/s"
 
@@ -68,6 +73,7 @@ class ClockSampler:
             self.th.start()
         except Exception as e:  # pragma: no cover
             self.err = repr(e)
+        return self
 
     def _loop(self):
         nv = self.nv
@@ -119,46 +125,87 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
 
 
-def cpu_port_run(cfg, sd, B, T, reps, warmup, threads=None):
-    """The oracle port on the host cores: flow reverse + decode, all threads.  Returns best seconds per pass."""
+def partition_host_cores(rank, world):
+    """Give every rank of one box its own slice of the host cores (pinned staging buffers are first-touched and the
+    copy / launch threads run there), so that eight ranks do not bounce over the same cores."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if world > 1 and len(cores) >= 2 * world:
+            per = len(cores) // world
+            os.sched_setaffinity(0, set(cores[rank * per:(rank + 1) * per]))
+    except Exception:  # pragma: no cover
+        pass
+
+
+# ------------------------------------------------------------------------------------------------
+# reference legs: the unmodified reference modules (baseline/_ref) when staged, else the oracle port
+# ------------------------------------------------------------------------------------------------
+def make_reference_runner(cfg, sd, device="cpu"):
+    """-> (kind, fn(z_p, mask, g) -> waveform) running flow reverse + decoder like models.py:730-734."""
     import torch
+    import ref_loader
+    if ref_loader.available():
+        net = ref_loader.build_synthesizer(cfg, sd, device=device)
+
+        def run(z_p, mask, g=None):
+            with torch.no_grad():
+                z = net.flow(z_p, mask, g=g, reverse=True)
+                return net.dec(z * mask, g=g)[0]
+        return "reference", run
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import mbistft_oracle as orc
+    sd_dev = {k: v.to(device) for k, v in sd.items()}
+
+    def run_port(z_p, mask, g=None):
+        with torch.no_grad():
+            return orc.flow_decode(sd_dev, cfg, z_p, mask, g)[1][0]
+    return "port", run_port
+
+
+def cpu_reference_run(cfg, sd, B, T, reps, warmup, threads=None):
+    """The reference on the host cores: flow reverse + decode, all threads.  Returns (seconds per pass list, cores, kind)."""
+    import torch
     from mb_istft_vits_b200 import synth
     n = threads or len(os.sched_getaffinity(0))
     torch.set_num_threads(n)
+    kind, run = make_reference_runner(cfg, sd, "cpu")
     z_p, mask, _ = synth.make_latents(cfg, B, T, seed=1234)
     times = []
     for i in range(warmup + reps):
         t0 = time.perf_counter()
-        orc.flow_decode(sd, cfg, z_p, mask)
+        run(z_p, mask)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return times, n
+    return times, n, kind
 
 
 def run_reference(args):
     rank, local_rank, world = dist_env()
     if rank != 0:
         return
+    import contextlib
     from mb_istft_vits_b200 import get_config, synth
     cfg = get_config(CONFIG_NAME)
     sd = synth.make_state_dict(cfg, seed=1234)
-    Bs = 4  # bounded sample: CPU throughput is batch-independent (BASELINE.md section 2)
-    times, cores = cpu_port_run(cfg, sd, Bs, T_FRAMES, max(1, args.steps), max(1, min(args.warmup, 2)))
+    Bs = CPU_SAMPLE_B
+    warm = max(1, min(args.warmup, 2))
+    with contextlib.redirect_stdout(sys.stderr):  # the reference prints a banner when it builds its decoder
+        times, cores, kind = cpu_reference_run(cfg, sd, Bs, T_FRAMES, max(1, args.steps), warm)
     mean = sum(times) / len(times)
     samples = Bs * T_FRAMES * 256
     v = samples / mean
+    what = "unmodified reference modules (baseline/_ref: net_g.flow(reverse=True) + net_g.dec)" if kind == "reference" \
+        else "oracle port (torch CPU ops of the reference; baseline/_ref not staged)"
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
-        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": mean * 1e3, "higher_is_better": True,
+        "warmup": warm, "ms_per_step": mean * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{CONFIG_NAME} flow-reverse + decoder-from-z, CPU sample B={Bs} x T={T_FRAMES}",
                    "sampling_rate": cfg["sampling_rate"]},
         "rtf": mean / (samples / cfg["sampling_rate"]),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"oracle port (torch CPU ops of the reference), B={Bs} x T={T_FRAMES} per step"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{what}, B={Bs} x T={T_FRAMES} per step, mean of {len(times)} after {warm} warm-up"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -166,6 +213,102 @@ def run_reference(args):
 
 def _emit(line, fd):
     os.write(fd, (json.dumps(line) + "\n").encode())
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs 3 and 5 (extras): sharded batches + the final NCCL waveform gather
+# ------------------------------------------------------------------------------------------------
+def _timed(torch, dist, dev, fn, steps, warmup=1):
+    """CUDA-event time of `steps` calls of fn, barrier + synchronize on both sides, max over ranks -> ms per call."""
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(warmup):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / steps
+
+
+def run_sharded_config(torch, dist, dev, rank, world, which, steps=3):
+    """config 3: ljs_ms_istft_vits, B = 256 utterances x T = 862 in total, strong-scaled (256 / N per GPU).
+    config 5: uudb_ms_istft_vits_ms (g-conditioned MS decoder, 16 kHz), 64 utterances per GPU in total with lengths uniform
+    in [1, 60] s (seed 1234), length-balanced over the ranks (sharding.balance_utterances), every rank decoding its bin
+    as one padded batch.  Both: one flow_decode per rank, then sharding.gather_waveforms to rank 0 over NCCL; timed with
+    the gather excluded and included."""
+    from mb_istft_vits_b200 import Engine, get_config, synth
+    from mb_istft_vits_b200.sharding import balance_utterances, gather_waveforms
+    out = {}
+    if which == 3:
+        cfg = get_config("ljs_ms_istft_vits")
+        total = 256
+        lengths = [T_FRAMES] * total
+        per = total // world
+        idx = list(range(rank * per, (rank + 1) * per))
+        out["workload"] = f"ljs_ms_istft_vits, B=256 x T={T_FRAMES} in total, {per} utterances per GPU (strong scaling)"
+    else:
+        cfg = get_config("uudb_ms_istft_vits_ms")
+        total = 64 * world
+        gen = torch.Generator().manual_seed(1234)
+        secs = 1.0 + 59.0 * torch.rand(total, generator=gen)
+        lengths = [max(1, int(round(float(s) * cfg["sampling_rate"] / 256))) for s in secs]
+        idx = balance_utterances(lengths, world)[rank]
+        out["workload"] = (f"uudb_ms_istft_vits_ms (sid-conditioned g), {total} utterances of 1-60 s (seed 1234), "
+                           "length-balanced bins, one padded batch per GPU")
+    sd = synth.make_state_dict(cfg, seed=1234)
+    eng = Engine(cfg, sd, precision="bf16", device=dev.index)
+    lens = torch.tensor([lengths[i] for i in idx], dtype=torch.long)
+    b, T = len(idx), int(lens.max())
+    z_p, mask, _ = synth.make_latents(cfg, b, T, seed=4000 + rank, lengths=lens)
+    z_p, mask = z_p.to(dev), mask.to(dev)
+    g = None
+    if cfg["gin_channels"]:
+        sid = torch.tensor([i % cfg["n_speakers"] for i in idx])
+        g = sd["emb_g.weight"][sid].unsqueeze(-1).to(dev).contiguous()   # models.py:704-707
+    wav = torch.empty((b, 1, 256 * T), dtype=torch.float32, device=dev)
+    n_samples = (lens * 256).to(dev)
+    state = {}
+
+    def compute():
+        eng.flow_decode(z_p, mask, g, want_z=False, out_wav=wav)
+
+    def compute_gather():
+        compute()
+        state["out"] = gather_waveforms(wav, n_samples, idx, total, dst=0)
+
+    valid = sum(lengths) * 256
+    ms_c = _timed(torch, dist, dev, compute, steps)
+    out.update({"utterances": total, "valid_samples": valid, "this_rank": {"utterances": b, "T_padded": T},
+                "ms_per_step_compute": ms_c, "samples_per_s_compute": valid / (ms_c * 1e-3)})
+    if dist is not None:
+        ms_g = _timed(torch, dist, dev, compute_gather, steps)
+        out.update({"ms_per_step_with_gather": ms_g, "samples_per_s_with_gather": valid / (ms_g * 1e-3),
+                    "gather_ms": ms_g - ms_c, "gather_bytes": valid * 4,
+                    "gather": "sharding.gather_waveforms: 1 all_gather of the placement table + grouped NCCL send/recv to rank 0"})
+        if rank == 0:
+            res = state["out"]
+            out["gather_check"] = bool(len(res) == total and all(int(res[i].numel()) == lengths[i] * 256 for i in range(total)))
+    else:
+        out["gather"] = "n/a at N = 1 (single rank owns every utterance)"
+    work = torch.tensor([float(b * T)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        wmax = work.clone()
+        dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+        out["padded_work_balance"] = float(work.item() / world / wmax.item())
+    eng.close()
+    del eng
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_native(args):
@@ -176,6 +319,7 @@ def run_native(args):
     os.dup2(2, 1)
     import torch
     rank, local_rank, world = dist_env()
+    partition_host_cores(local_rank, world)
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
@@ -188,7 +332,7 @@ def run_native(args):
     cfg = get_config(CONFIG_NAME)
     sd = synth.make_state_dict(cfg, seed=1234)
     B, T = args.batch, args.frames
-    eng = Engine(cfg, sd, precision=args.precision, device=dev.index, residual=args.residual)
+    eng = Engine(cfg, sd, precision=args.precision, device=dev.index, residual=args.residual, flags=args.flags)
     z_p_host, mask_host, _ = synth.make_latents(cfg, B, T, seed=1234 + rank)
     z_p, mask = z_p_host.to(dev), mask_host.to(dev)
     samples_per_step = B * T * 256
@@ -225,24 +369,48 @@ def run_native(args):
     barrier()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    # per-kernel device times for the roofline: the same steps again, eagerly, every launch bracketed by CUDA events
-    eng.set_profiling(True)
-    eng.profile_read()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    p0.record()
-    for _ in range(args.steps):
-        step()
-    p1.record()
-    barrier()
-    ms_profiled = p0.elapsed_time(p1)
-    prof = eng.profile_read()
-    eng.set_profiling(False)
     t_max = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
     ms_step = float(t_max.item()) / args.steps
     value = world * samples_per_step / (ms_step * 1e-3)
+
+    # ---------------- sustained leg: the same replays back to back for >= 3 s (the regime the sustained peak was measured in)
+    sustained = None
+    if not args.no_sustained:
+        n_sus = max(args.steps, int(3200.0 / ms_step) + 1)
+        s_sampler = ClockSampler(dev.index)
+        barrier()
+        if rank == 0:
+            s_sampler.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(n_sus):
+            run_step()
+        s1.record()
+        barrier()
+        ts = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        sustained = {"steps": n_sus, "seconds": float(ts.item()) * 1e-3, "ms_per_step": float(ts.item()) / n_sus,
+                     "clocks": s_sampler.stop() if rank == 0 else None}
+
+    # ---------------- per-launch device times of the NON-conv launches (tail, pack / unpack / gemv): the same step eagerly,
+    # every launch bracketed by CUDA events.  (Per-launch events break the programmatic-dependent-launch overlap of the conv
+    # launches, so the conv time is NOT taken from here: it is the graph-timed step minus these small launches.)
+    eng.set_profiling(True)
+    eng.profile_read()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    p0.record()
+    n_prof = min(args.steps, 5)
+    for _ in range(n_prof):
+        step()
+    p1.record()
+    barrier()
+    ms_profiled = p0.elapsed_time(p1) / n_prof
+    prof = eng.profile_read()
+    eng.set_profiling(False)
 
     # decoder-only (no flow) for the record
     zz = (eng.flow_reverse(z_p, mask) * mask).contiguous()
@@ -256,38 +424,50 @@ def run_native(args):
     d1.record()
     barrier()
     dec_ms = d0.elapsed_time(d1) / args.steps
+    del zz
 
     # ---------------- end-to-end through the public API, host buffers in and out.  Every step uploads its own
-    # pinned latents + mask, runs the drop-in modules (flow, mask, dec: two library calls like infer()) and downloads
-    # its waveform into pinned memory.  (a) HostStream: the serving loop, copies of neighbouring steps overlap the
-    # compute (three streams, two slots); (b) the same calls strictly one after the other on one stream.
+    # pinned latents + mask, runs the hot path and downloads its waveform into pinned memory.  (a) HostStream: the serving
+    # loop, copies of neighbouring steps overlap the compute (three streams, two slots); (b) the drop-in modules (flow,
+    # mask, dec: two library calls like infer()) strictly one after the other on one stream.
     from mb_istft_vits_b200 import HostStream
     flow, dec = NativeFlow(eng), NativeDecoder(eng, want_mb=False, want_spec=False)
     n_slots = 2
     zp_pin = [z_p_host.clone().pin_memory() for _ in range(n_slots)]
     mask_pin = [mask_host.clone().pin_memory() for _ in range(n_slots)]
     wav_pin = [torch.empty((B, 1, 256 * T), dtype=torch.float32).pin_memory() for _ in range(n_slots)]
+
     def e2e_pipelined(n):
         for i in range(n):
             hs.submit(zp_pin[i % n_slots], mask_pin[i % n_slots], wav_pin[i % n_slots])
 
-    # (a') module-by-module variant of the serving loop, for the record
-    hs = HostStream(eng, depth=n_slots, fused=False)
-    e2e_pipelined(3)
-    hs.drain()
-    barrier()
-    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    m0.record()
-    for st in (hs.s_in, hs.s_cmp, hs.s_out):
-        st.wait_event(m0)
-    e2e_pipelined(args.steps)
-    for st in (hs.s_in, hs.s_cmp, hs.s_out):
-        torch.cuda.current_stream().wait_stream(st)
-    m1.record()
-    barrier()
-    e2e_modules_ms = m0.elapsed_time(m1) / args.steps
+    def time_pipelined():
+        e2e_pipelined(3)
+        hs.drain()
+        barrier()
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cur = torch.cuda.current_stream()
+        x0.record(cur)
+        for st in (hs.s_in, hs.s_cmp, hs.s_out):
+            st.wait_event(x0)
+        w0 = time.perf_counter()
+        e2e_pipelined(args.steps)
+        for st in (hs.s_in, hs.s_cmp, hs.s_out):
+            cur.wait_stream(st)
+        x1.record(cur)
+        barrier()
+        wall = (time.perf_counter() - w0) * 1e3 / args.steps
+        t = torch.tensor([x0.elapsed_time(x1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / args.steps, wall
 
+    hs = HostStream(eng, depth=n_slots, fused=False)   # module-by-module variant of the serving loop, for the record
+    e2e_modules_ms, _ = time_pipelined()
     hs = HostStream(eng, depth=n_slots, fused=True)
+    e2e_ms, e2e_wall_ms = time_pipelined()
+    e2e_value = world * samples_per_step / (e2e_ms * 1e-3)
+    wav_check = float(wav_pin[0].abs().max())  # the downloaded waveform is real data
 
     def e2e_step():
         zp_d = zp_pin[0].to(dev, non_blocking=True)
@@ -295,29 +475,6 @@ def run_native(args):
         z = flow(zp_d, m_d, g=None, reverse=True)
         o, _, _, _ = dec(z * m_d, g=None)
         wav_pin[0].copy_(o, non_blocking=True)
-
-    e2e_pipelined(3)
-    hs.drain()
-    barrier()
-    import time as _time
-    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    cur = torch.cuda.current_stream()
-    x0.record(cur)
-    for st in (hs.s_in, hs.s_cmp, hs.s_out):
-        st.wait_event(x0)
-    w0 = _time.perf_counter()
-    e2e_pipelined(args.steps)
-    for st in (hs.s_in, hs.s_cmp, hs.s_out):
-        cur.wait_stream(st)
-    x1.record(cur)
-    barrier()
-    e2e_wall_ms = (_time.perf_counter() - w0) * 1e3 / args.steps
-    e2e_t = torch.tensor([x0.elapsed_time(x1)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(e2e_t.item()) / args.steps
-    e2e_value = world * samples_per_step / (e2e_ms * 1e-3)
-    wav_check = float(wav_pin[0].abs().max())  # the downloaded waveform is real data
 
     for _ in range(3):
         e2e_step()
@@ -328,54 +485,118 @@ def run_native(args):
         e2e_step()
     y1.record()
     barrier()
-    e2e_seq_ms = y0.elapsed_time(y1) / args.steps
+    ty = torch.tensor([y0.elapsed_time(y1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(ty, op=dist.ReduceOp.MAX)
+    e2e_seq_ms = float(ty.item()) / args.steps
+    del hs
 
     # ---------------- fused tail alone (HBM roofline of that kernel): event-timed stand-alone launches
-    L = 16 * T
-    logits = torch.randn((B, L + 1, 72), device=dev) * 0.5
-    for _ in range(3):
-        eng.tail(logits, T, want_mb=False, want_spec=False)
-    torch.cuda.synchronize()
-    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0e.record()
-    for _ in range(10):
-        eng.tail(logits, T, want_mb=False, want_spec=False)
-    t1e.record()
-    torch.cuda.synchronize()
-    tail_ms = t0e.elapsed_time(t1e) / 10
-    del logits
+    tail_ms = None
+    if hasattr(eng, "tail"):
+        L = 16 * T
+        logits = torch.randn((B, L + 1, 72), device=dev) * 0.5
+        for _ in range(3):
+            eng.tail(logits, T, want_mb=False, want_spec=False)
+        torch.cuda.synchronize()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for _ in range(10):
+            eng.tail(logits, T, want_mb=False, want_spec=False)
+        t1e.record()
+        torch.cuda.synchronize()
+        tail_ms = t0e.elapsed_time(t1e) / 10
+        del logits
 
-    # ---------------- the reference's own arithmetic as PyTorch eager ops ON THIS GPU ("the real bar to beat"):
-    # the oracle port issues the same F.conv1d / conv_transpose1d / torch.istft calls as the reference modules; fp32 with
-    # TF32 off (the gold setting) and with PyTorch's default TF32 convs.  Bounded sample, rank 0 at N = 1 only.
+    flops_step = eng.decode_flops(B, T) + eng.flow_flops(B, T)
+
+    # ---------------- the fp32/TF32 precision path of the north star, every run: the same workload through kind::tf32
+    # tcgen05 convs (fp32 streams), and the TF32 GEMM peak measured here instead of assumed
+    tf32_line = None
+    if args.precision == "bf16" and not args.no_tf32:
+        try:
+            torch.backends.cuda.matmul.allow_tf32 = True
+            a = torch.randn((8192, 8192), device=dev)
+            b = torch.randn((8192, 8192), device=dev)
+            best = None
+            for i in range(6):
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                torch.matmul(a, b)
+                g1.record()
+                torch.cuda.synchronize()
+                if i > 0:
+                    t = g0.elapsed_time(g1)
+                    best = t if best is None else min(best, t)
+            tf32_peak = 2 * 8192.0 ** 3 / (best * 1e-3) / 1e12
+            torch.backends.cuda.matmul.allow_tf32 = False
+            del a, b
+            eng32 = Engine(cfg, sd, precision="tf32", device=dev.index)
+            for _ in range(2):
+                eng32.flow_decode(z_p, mask, want_z=False)
+            g32, _ = eng32.capture_flow_decode(z_p, mask)
+            g32.replay()
+            ms32 = _timed(torch, dist, dev, g32.replay, max(3, args.steps // 4), warmup=1)
+            tf32_line = {"ms_per_step": ms32, "value": world * samples_per_step / (ms32 * 1e-3), "unit": UNIT,
+                         "dtype": "tf32", "tflops_whole_step": flops_step / (ms32 * 1e-3) / 1e12,
+                         "tf32_gemm_peak_tflops": tf32_peak,
+                         "tf32_gemm_peak_how": "torch.matmul fp32 8192^3 with allow_tf32 (cuBLAS), best of 5, this run",
+                         "frac_of_tf32_peak": flops_step / (ms32 * 1e-3) / 1e12 / tf32_peak,
+                         "parity": "<= 1e-3 of peak vs the fp32 reference (tests/test_gpu_parity.py)"}
+            del g32
+            eng32.close()
+            del eng32
+            torch.cuda.empty_cache()
+        except Exception as e:  # informational leg
+            tf32_line = {"error": repr(e)}
+
+    # ---------------- the reference's own modules as PyTorch eager ops ON THIS GPU ("the real bar to beat"):
+    # fp32 with TF32 off (the gold setting) and with PyTorch's default TF32 convs.  Bounded sample, rank 0 at N = 1 only.
     torch_eager = None
     if world == 1 and not args.no_cpu:
         try:
-            sys.path.insert(0, os.path.join(ROOT, "oracle"))
-            import mbistft_oracle as orc
+            import contextlib
             Bs = min(B, 16)
-            sd_dev = {k: v.to(dev) for k, v in sd.items()}
+            with contextlib.redirect_stdout(sys.stderr):
+                kind, run_ref = make_reference_runner(cfg, sd, dev)
             zs, ms = z_p[:Bs].contiguous(), mask[:Bs].contiguous()
-            torch_eager = {"sample": f"oracle port (the reference's torch ops) on cuda, B={Bs} x T={T}, best of 3", "unit": UNIT}
+            what = "unmodified reference modules (baseline/_ref)" if kind == "reference" else "oracle port"
+            torch_eager = {"sample": f"{what} on cuda, PyTorch eager, B={Bs} x T={T}, best of 3", "unit": UNIT, "kind": kind}
             for label, tf32 in (("fp32", False), ("tf32", True)):
                 torch.backends.cudnn.allow_tf32 = tf32
                 torch.backends.cuda.matmul.allow_tf32 = tf32
                 best = None
-                with torch.no_grad():
-                    for i in range(4):
-                        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                        g0.record()
-                        orc.flow_decode(sd_dev, cfg, zs, ms)
-                        g1.record()
-                        torch.cuda.synchronize()
-                        if i > 0:
-                            t = g0.elapsed_time(g1)
-                            best = t if best is None else min(best, t)
+                for i in range(4):
+                    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    g0.record()
+                    with contextlib.redirect_stdout(sys.stderr):
+                        run_ref(zs, ms)
+                    g1.record()
+                    torch.cuda.synchronize()
+                    if i > 0:
+                        t = g0.elapsed_time(g1)
+                        best = t if best is None else min(best, t)
                 torch_eager[label] = Bs * T * 256 / (best * 1e-3)
                 torch_eager[label + "_ms"] = best
-            del sd_dev
+            torch.backends.cudnn.allow_tf32 = True
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch_eager["native_over_eager_tf32"] = value / torch_eager["tf32"]
+            torch_eager["native_over_eager_fp32"] = value / torch_eager["fp32"]
+            del run_ref
+            torch.cuda.empty_cache()
         except Exception as e:  # the leg is informational: never fail the bench on it
             torch_eager = {"error": repr(e)}
+
+    # ---------------- BASELINE configs 3 and 5 with the final NCCL waveform gather (all ranks take part)
+    sharded = {}
+    if not args.no_configs:
+        for which in (3, 5):
+            try:
+                sharded["config%d" % which] = run_sharded_config(torch, dist, dev, rank, world, which)
+            except Exception as e:
+                sharded["config%d" % which] = {"error": repr(e)}
+                if dist is not None:
+                    raise
 
     if rank != 0:
         if dist is not None:
@@ -384,43 +605,61 @@ def run_native(args):
 
     peaks = measured_peaks()
     traffic = {}
-    tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "traffic.json")   # written by tools/make_traffic.py from the latest ncu launch list
+    if not os.path.exists(tp):
+        tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(tp) and args.precision == "bf16" and B == B_PER_GPU and T == T_FRAMES:
         traffic = json.load(open(tp))  # dram__bytes_read+write per launch from the committed ncu capture of this workload
-    flops_step = eng.decode_flops(B, T) + eng.flow_flops(B, T)
-    conv_ms, conv_n = prof["conv"]
+    conv_ev_ms, conv_n = prof["conv"]
     tail_prof_ms, tail_n = prof["tail"]
-    conv_tflops = flops_step * args.steps / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None
-    tail_bytes = B * T * 5632.0  # 4608 B logits in + 1024 B waveform out per latent frame (SURVEY 8d)
-    prec_peak = peaks["tflops_sustained"] * (0.5 if args.precision == "tf32" else 1.0)
+    other_ms, other_n = prof["other"]
+    n_conv_step = conv_n // max(1, n_prof)
+    non_conv_ms = (tail_prof_ms + other_ms) / n_prof
+    conv_ms_step = ms_step - non_conv_ms            # conv kernel time INSIDE the graph-timed region
+    conv_tflops = flops_step / (conv_ms_step * 1e-3) / 1e12
+    tf32 = args.precision == "tf32"
+    pk_s = peaks["tflops_sustained"] * (0.5 if tf32 else 1.0)
+    pk_b = peaks["tflops_burst"] * (0.5 if tf32 else 1.0)
     roofline = {
-        "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all %d launches per step)" % (conv_n // max(1, args.steps)),
-        "bound": "tensor", "achieved": conv_tflops, "peak": prec_peak, "unit": "TFLOP/s",
-        "frac": (conv_tflops / prec_peak) if conv_tflops else None,
+        "kernel": "conv kernels (tcgen05 implicit-GEMM convs + fused ResBlock pairs, all %d launches per step)" % n_conv_step,
+        "bound": "tensor", "achieved": conv_tflops, "peak": pk_s, "unit": "TFLOP/s", "frac": conv_tflops / pk_s,
+        "frac_vs_burst_peak": conv_tflops / pk_b, "peak_burst": pk_b,
         "traffic": traffic.get("conv_dram_bytes_per_launch"), "traffic_source": traffic.get("source"),
-        "algorithmic_flops_per_launch": flops_step / max(1, conv_n // max(1, args.steps)),
-        "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)"
-                       + (" x 0.5 for tf32" if args.precision == "tf32" else ""),
-        "flops_per_step": flops_step, "avg_launch_ms": conv_ms / conv_n if conv_n else None,
-        "share_of_step": conv_ms / ms_profiled if ms_profiled else None,
-        "timed_in": "eager pass with per-launch CUDA events right after the graph-timed region (%.3f ms/step)" % (ms_profiled / args.steps),
+        "algorithmic_flops_per_launch": flops_step / max(1, n_conv_step),
+        "peak_source": peaks["source"] + " bf16_tflops_sustained (kernels timed inside a long step); frac_vs_burst_peak uses bf16_tflops"
+                       + (" (x 0.5 assumed for tf32; the measured TF32 GEMM peak is in extras.tf32)" if tf32 else ""),
+        "flops_per_step": flops_step, "avg_launch_ms": conv_ms_step / max(1, n_conv_step),
+        "share_of_step": conv_ms_step / ms_step,
+        "timed_in": "the graph-timed region: ms_per_step minus the event-timed non-conv launches (tail %.3f + other %.3f ms)"
+                    % (tail_prof_ms / n_prof, other_ms / n_prof),
+        "eager_event_sum_ms": conv_ev_ms / n_prof,
     }
-    roofline_tail = {
-        "kernel": "tail_kernel (head + iSTFT + PQMF)", "bound": "hbm",
-        "achieved": tail_bytes / (tail_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-        "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic.get("tail_dram_bytes_per_launch"),
-        "peak_source": peaks["source"] + " hbm_gbs (burst; kernel timed alone)", "ms": tail_ms,
-        "ms_inside_step": tail_prof_ms / tail_n if tail_n else None, "bytes_per_launch": tail_bytes,
-    }
+    if sustained:
+        c_sus = flops_step / ((sustained["ms_per_step"] - non_conv_ms) * 1e-3) / 1e12
+        roofline["sustained_leg"] = {"achieved": c_sus, "frac": c_sus / pk_s, "frac_vs_burst_peak": c_sus / pk_b,
+                                     "ms_per_step": sustained["ms_per_step"], "seconds": sustained["seconds"],
+                                     "clocks": sustained["clocks"]}
+    tail_bytes = B * T * 5632.0  # 4608 B logits in + 1024 B waveform out per latent frame (SURVEY 8d)
+    roofline_tail = None
+    if tail_ms:
+        roofline_tail = {
+            "kernel": "tail_mb3_kernel (head + iSTFT + PQMF)", "bound": "hbm",
+            "achieved": tail_bytes / (tail_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic.get("tail_dram_bytes_per_launch"),
+            "peak_source": peaks["source"] + " hbm_gbs (burst; kernel timed alone)", "ms": tail_ms,
+            "ms_inside_step": tail_prof_ms / tail_n if tail_n else None, "bytes_per_launch": tail_bytes,
+        }
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu:
-        Bs = 4
-        times, cores = cpu_port_run(cfg, sd, Bs, T, 3, 1)
+        import contextlib
+        Bs = CPU_SAMPLE_B
+        with contextlib.redirect_stdout(sys.stderr):
+            times, cores, kind = cpu_reference_run(cfg, sd, Bs, T, 3, 1)
         best = min(times)
-        cpu_baseline = {"value": Bs * T * 256 / best, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"oracle port (torch CPU ops of the reference) on B={Bs} x T={T}, best of 3 after 1 warm-up",
-                        "ms": best * 1e3}
+        what = "unmodified reference modules (baseline/_ref)" if kind == "reference" else "oracle port (torch CPU ops of the reference)"
+        cpu_baseline = {"value": Bs * T * 256 / best, "unit": UNIT, "cores": cores, "kind": kind,
+                        "sample": f"{what} on B={Bs} x T={T}, best of 3 after 1 warm-up", "ms": best * 1e3}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -443,9 +682,11 @@ def run_native(args):
         "launches_per_step": launches_per_step,
         "roofline": roofline, "roofline_tail": roofline_tail, "cpu_baseline": cpu_baseline,
         "extras": {"decoder_only_ms": dec_ms, "decoder_only_samples_per_s": samples_per_step / (dec_ms * 1e-3),
-                   "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+                   "kernel_ms_per_step": {"conv_in_graph_region": conv_ms_step, "tail": tail_prof_ms / n_prof, "other": other_ms / n_prof,
+                                          "conv_eager_event_sum": conv_ev_ms / n_prof, "eager_step": ms_profiled},
                    "tflops_whole_step": flops_step / (ms_step * 1e-3) / 1e12,
-                   "torch_eager_gpu": torch_eager},
+                   "sustained_ms_per_step": sustained["ms_per_step"] if sustained else None,
+                   "tf32": tf32_line, "torch_eager_gpu": torch_eager, **sharded},
     }
     if dist is not None:
         dist.destroy_process_group()
@@ -462,10 +703,17 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["fp16", "bf16", "tf32", "fp32"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--frames", type=int, default=T_FRAMES)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--flags", type=int, default=0, help="extra mbv_config flags (A/B measurements)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline and PyTorch-eager legs")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 3 s sustained leg")
+    ap.add_argument("--no-tf32", action="store_true", help="skip the tf32 sub-line")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 3 and 5")
+    ap.add_argument("--quick", action="store_true", help="only the device-resident and e2e timings (A/B runs)")
     ap.add_argument("--residual", default=None, choices=["fp16", "fp32"], help="ResBlock residual-stream storage (default: fp16 for bf16)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     args = ap.parse_args()
+    if args.quick:
+        args.no_cpu = args.no_sustained = args.no_tf32 = args.no_configs = True
     if args.impl == "reference":
         run_reference(args)
     else:

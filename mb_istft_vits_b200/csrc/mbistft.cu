@@ -154,6 +154,24 @@ int fail(mbv_handle* h, int code, const char* fmt, ...) {
   return code;
 }
 
+// Every entry point runs on the handle's device and leaves the caller's current device as it found it (PyTorch reads it
+// with cudaGetDevice: an Engine on device k must not silently move the caller's allocations and default stream there).
+struct DeviceGuard {
+  int prev = -1, dev;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int d) : dev(d) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != d) { err = cudaSetDevice(d); switched = (err == cudaSuccess); }
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define DEVICE_GUARD(h)                                                                                            \
+  DeviceGuard _dev_guard((h)->cfg.device);                                                                         \
+  if (_dev_guard.err != cudaSuccess) return fail(h, MBV_ERR_CUDA, "cudaSetDevice(%d): %s", (h)->cfg.device, cudaGetErrorString(_dev_guard.err))
+
 #define CUDA_TRY(h, expr)                                                                          \
   do {                                                                                             \
     cudaError_t _e = (expr);                                                                       \
@@ -401,7 +419,7 @@ extern "C" int mbv_create(const mbv_config* cfg, mbv_handle** out) {
     return MBV_OK;  // geometry validated; compute entries fail loudly later
   }
   if (c.device < 0 || c.device >= ndev) return fail(h, MBV_ERR_INVALID, "device %d out of range", c.device);
-  CUDA_TRY(h, cudaSetDevice(c.device));
+  DEVICE_GUARD(h);
   cudaDeviceProp prop;
   CUDA_TRY(h, cudaGetDeviceProperties(&prop, c.device));
   h->num_sms = prop.multiProcessorCount;
@@ -427,7 +445,7 @@ extern "C" int mbv_load_weights(mbv_handle* h, const mbv_tensor* tensors, int32_
     cudaGetLastError();
     return fail(h, MBV_ERR_CUDA, "mbv_load_weights: no CUDA device (there is no CPU fallback)");
   }
-  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h);
   const mbv_config& c = h->cfg;
   TensorMap m;
   for (int i = 0; i < n; ++i) {
@@ -1038,7 +1056,7 @@ extern "C" int mbv_flow_reverse(mbv_handle* h, const float* z_p, const float* y_
   if (!z_p || !y_mask || !z_out) return fail(h, MBV_ERR_INVALID, "null tensor");
   if (g && h->cfg.gin_channels == 0) return fail(h, MBV_ERR_INVALID, "g given but gin_channels == 0");
   if ((rc = check_ws(h, B, T, ws, ws_bytes))) return rc;
-  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h);
   Arena A(ws);
   FlowBufs f;
   layout_flow(h, A, B, T, &f);
@@ -1056,7 +1074,7 @@ extern "C" int mbv_flow_forward(mbv_handle* h, const float* x, const float* y_ma
   if (!x || !y_mask || !z_out) return fail(h, MBV_ERR_INVALID, "null tensor");
   if (g && h->cfg.gin_channels == 0) return fail(h, MBV_ERR_INVALID, "g given but gin_channels == 0");
   if ((rc = check_ws(h, B, T, ws, ws_bytes))) return rc;
-  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h);
   Arena A(ws);
   FlowBufs f;
   layout_flow(h, A, B, T, &f);
@@ -1076,7 +1094,7 @@ extern "C" int mbv_decode(mbv_handle* h, const float* z, const float* z_mask, co
   if ((spec == nullptr) != (phase == nullptr)) return fail(h, MBV_ERR_INVALID, "spec and phase must be requested together");
   if (o_mb && h->cfg.variant == MBV_VARIANT_ISTFT) return fail(h, MBV_ERR_INVALID, "the single-band decoder has no o_mb (models.py:297 returns None)");
   if ((rc = check_ws(h, B, T, ws, ws_bytes))) return rc;
-  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h);
   size_t dec_off, total;
   total_ws(h, B, T, &dec_off, &total);
   Arena A(ws);
@@ -1100,7 +1118,7 @@ extern "C" int mbv_flow_decode(mbv_handle* h, const float* z_p, const float* y_m
   if ((spec == nullptr) != (phase == nullptr)) return fail(h, MBV_ERR_INVALID, "spec and phase must be requested together");
   if (o_mb && h->cfg.variant == MBV_VARIANT_ISTFT) return fail(h, MBV_ERR_INVALID, "the single-band decoder has no o_mb");
   if ((rc = check_ws(h, B, T, ws, ws_bytes))) return rc;
-  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h);
   size_t dec_off, total;
   total_ws(h, B, T, &dec_off, &total);
   Arena A(ws);
@@ -1125,7 +1143,7 @@ extern "C" int mbv_tail(mbv_handle* h, const float* logits, float* wav, float* o
   if (rc) return rc;
   if (!logits || !wav) return fail(h, MBV_ERR_INVALID, "null tensor");
   if ((spec == nullptr) != (phase == nullptr)) return fail(h, MBV_ERR_INVALID, "spec and phase must be requested together");
-  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h);
   int L = T;
   for (int i = 0; i < h->n_stage; ++i) L *= h->cfg.upsample_rates[i];
   Ctx cx;
@@ -1140,7 +1158,7 @@ extern "C" int mbv_pcm16(mbv_handle* h, const float* wav, const int32_t* n_sampl
   if (!h) return MBV_ERR_INVALID;
   if (!wav || !pcm || !scratch || B < 1 || stride < 1) return fail(h, MBV_ERR_INVALID, "mbv_pcm16: bad argument");
   if (B > 65535) return fail(h, MBV_ERR_UNSUPPORTED, "B > 65535");
-  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h);
   CUDA_TRY(h, launch_pcm16(wav, n_samples, B, stride, auto_normalize, (unsigned int*)scratch, pcm, (cudaStream_t)stream));
   h->last_launches = 2;
   return MBV_OK;
@@ -1160,7 +1178,7 @@ extern "C" int mbv_expand_prior(mbv_handle* h, const float* m_p, const float* lo
     cudaGetLastError();
     return fail(h, MBV_ERR_CUDA, "mbv_expand_prior: no CUDA device (there is no CPU fallback)");
   }
-  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h);
   CUDA_TRY(h, launch_expand_prior(m_p, logs_p, w_ceil, x_mask, noise, noise_scale, B, C, Tx, Ty, z_p, y_mask, m_exp, logs_exp,
                                   attn, (long long*)y_lengths, (cudaStream_t)stream));
   h->last_launches = 1;

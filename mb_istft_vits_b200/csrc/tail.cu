@@ -7,10 +7,8 @@
 // n_fft 16, hop 4, center=True, periodic Hann), pqmf.py:105-116 (zero-stuff x4 with gain 4, pad 31, 63-tap
 // cross-correlation), models.py:463-465 (MS: same with the trainable multistream_conv_post).
 //
-// One CTA = one tile of one utterance: 256 consecutive STFT frames per band (one per thread) give 253 hop
-// blocks of sub-band signal, of which 249 are owned outputs (the FIR needs +-2 hop blocks of halo):
-// 97 % useful work.  Shared memory: logits tile 72 KB + frame scratch 20 KB + sub-band tile 16 KB -> 2 CTAs/SM,
-// so one CTA's loads overlap the other's math.
+// Two kernels: tail_mb3_kernel (4 sub-bands + synthesis FIR: MB / MS decoders) and tail_sb3_kernel (single band).
+// Both keep the frames in registers (lane = STFT frame, overlap-add by warp shuffles); see the comments above each.
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -22,11 +20,6 @@
 #include "kernels.h"
 
 namespace mbv {
-
-constexpr int TAIL_THREADS = 256;
-constexpr int TAIL_NF = 256;        // frames per band per tile
-constexpr int FR_PITCH = 20;        // floats per frame row in smem (16 + pad: conflict-free float4)
-constexpr int YMB_PITCH = 1024;     // floats per band in the sub-band tile (253 * 4 = 1012 used)
 
 // periodic Hann / 16 (the irfft normalisation folded in): w[n] = 0.5 - 0.5 cos(2 pi n / 16)
 __device__ constexpr float kWin16[16] = {
@@ -112,183 +105,6 @@ __device__ __forceinline__ void idft16_windowed(const T* re, const T* im, T* fr)
   }
 }
 
-// VARIANT: 0 = single-band iSTFT (no synthesis filter), 1 = MB / MS (4 bands + 63-tap synthesis FIR)
-template <int VARIANT, bool PRECISE>
-__global__ void __launch_bounds__(TAIL_THREADS, 2) tail_kernel(const __grid_constant__ TailArgs a, int tiles_per_utt) {
-  constexpr int S = VARIANT == 0 ? 1 : 4;
-  constexpr int NQ = VARIANT == 0 ? TAIL_NF - 3 : TAIL_NF - 7;  // owned hop blocks per tile
-  constexpr int YOFF = VARIANT == 0 ? 0 : 2;                    // y-block index of the first owned block
-  constexpr int NCH = S * 18;
-  extern __shared__ __align__(16) float sm[];
-  float* s_log = sm;                         // [TAIL_NF][NCH]
-  float* s_fr = s_log + TAIL_NF * NCH;       // [TAIL_NF][FR_PITCH]
-  float* s_y = s_fr + TAIL_NF * FR_PITCH;    // [S][YMB_PITCH]
-
-  const int t = threadIdx.x;
-  const int b = blockIdx.x / tiles_per_utt;
-  const int tile = blockIdx.x % tiles_per_utt;
-  const int L = a.L;            // hop blocks per band (= frames - 1)
-  const int F = L + 1;
-  const int Q0 = tile * NQ;     // first owned hop block
-  const int QY0 = Q0 - YOFF;    // first y block held in smem
-  const int F0 = QY0 - 1;       // first frame held in smem
-  const bool last_tile = (tile == tiles_per_utt - 1);
-
-  // ---- phase 0: coalesced copy of the logits rows [F0, F0+256) /\ [0, F) into smem
-  {
-    const int f_lo = F0 < 0 ? 0 : F0;
-    const int f_hi = (F0 + TAIL_NF < F) ? F0 + TAIL_NF : F;
-    const size_t g0 = ((size_t)b * F + f_lo) * NCH;
-    const int n = (f_hi - f_lo) * NCH;
-    float* dst = s_log + (f_lo - F0) * NCH;
-    const float* src = a.logits + g0;
-    if ((g0 & 3) == 0 && (((f_lo - F0) * NCH) & 3) == 0) {
-      const int n4 = n >> 2;
-      const float4* s4 = reinterpret_cast<const float4*>(src);
-      float4* d4 = reinterpret_cast<float4*>(dst);
-      for (int i = t; i < n4; i += TAIL_THREADS) d4[i] = __ldg(s4 + i);
-      for (int i = (n4 << 2) + t; i < n; i += TAIL_THREADS) dst[i] = __ldg(src + i);
-    } else {
-      for (int i = t; i < n; i += TAIL_THREADS) dst[i] = __ldg(src + i);
-    }
-  }
-  __syncthreads();
-
-  const int f = F0 + t;  // this thread's frame
-  const bool f_valid = (f >= 0 && f < F);
-  // frames whose spec/phase this tile writes: the owned blocks' frames, plus the final frame L for the last tile
-  const bool f_owned = f_valid && (f >= Q0) && (f < Q0 + NQ || (last_tile && f == L));
-
-#pragma unroll 1
-  for (int s = 0; s < S; ++s) {
-    // ---- phase 1: head + inverse DFT + window for frame f, band s
-    float fr[16];
-    if (f_valid) {
-      const float2* lp = reinterpret_cast<const float2*>(s_log + t * NCH + s * 18);
-      float x[18];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        const float2 v = lp[i];
-        x[2 * i] = v.x;
-        x[2 * i + 1] = v.y;
-      }
-      float re[9], im[9];
-      const bool emit = (a.spec != nullptr) && f_owned;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        float mag, ph;
-        head<PRECISE>(x[k], x[9 + k], mag, ph, re[k], im[k]);
-        if (emit) {
-          // spec/phase are [B][S][9][F]; consecutive threads = consecutive frames -> coalesced
-          const size_t o = (((size_t)b * S + s) * 9 + k) * F + f;
-          a.spec[o] = mag;
-          a.phase[o] = ph;
-        }
-      }
-      // x[n] = Re0 + (-1)^n Re8 + 2 sum_{k=1..7} (Re_k cos(2 pi k n/16) - Im_k sin(2 pi k n/16)); imag of bins 0, 8 ignored
-      idft16_windowed(re, im, fr);
-    } else {
-#pragma unroll
-      for (int n = 0; n < 16; ++n) fr[n] = 0.f;
-    }
-    {
-      float4* dst = reinterpret_cast<float4*>(s_fr + t * FR_PITCH);
-      dst[0] = make_float4(fr[0], fr[1], fr[2], fr[3]);
-      dst[1] = make_float4(fr[4], fr[5], fr[6], fr[7]);
-      dst[2] = make_float4(fr[8], fr[9], fr[10], fr[11]);
-      dst[3] = make_float4(fr[12], fr[13], fr[14], fr[15]);
-    }
-    __syncthreads();
-    // ---- phase 2: overlap-add.  y block q (sub-band samples 4q..4q+3) = frame q-1 part 3 + q part 2 + q+1 part 1 + q+2 part 0
-    if (t < TAIL_NF - 3) {
-      const int q = QY0 + t;
-      float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (q >= 0 && q < L) {
-        const float4 p3 = *reinterpret_cast<const float4*>(s_fr + (t + 0) * FR_PITCH + 12);
-        const float4 p2 = *reinterpret_cast<const float4*>(s_fr + (t + 1) * FR_PITCH + 8);
-        const float4 p1 = *reinterpret_cast<const float4*>(s_fr + (t + 2) * FR_PITCH + 4);
-        const float4 p0 = *reinterpret_cast<const float4*>(s_fr + (t + 3) * FR_PITCH + 0);
-        y.x = p3.x + p2.x + p1.x + p0.x;
-        y.y = p3.y + p2.y + p1.y + p0.y;
-        y.z = p3.z + p2.z + p1.z + p0.z;
-        y.w = p3.w + p2.w + p1.w + p0.w;
-        // window-square envelope: 1.5 in steady state; frame -1 (q == 0) and frame F (q == L-1) do not exist
-        float e0 = 1.5f, e1 = 1.5f, e2 = 1.5f, e3 = 1.5f;
-        if (q == 0) { e0 -= win_sq(12); e1 -= win_sq(13); e2 -= win_sq(14); e3 -= win_sq(15); }
-        if (q == L - 1) { e0 -= win_sq(0); e1 -= win_sq(1); e2 -= win_sq(2); e3 -= win_sq(3); }
-        y.x /= e0; y.y /= e1; y.z /= e2; y.w /= e3;
-        const bool owned = (t >= YOFF) && (t < YOFF + NQ);
-        if (VARIANT == 0) {
-          if (owned) *reinterpret_cast<float4*>(a.wav + (size_t)b * 4 * L + 4 * (size_t)q) = y;
-        } else if (a.o_mb != nullptr && owned) {
-          if (a.variant == 1) {  // MB: y_mb_hat [B][S][4L]
-            *reinterpret_cast<float4*>(a.o_mb + ((size_t)b * S + s) * 4 * L + 4 * (size_t)q) = y;
-          } else {  // MS: the zero-stuffed tensor [B][S][16L], gain 4 (models.py:463)
-            float4* o = reinterpret_cast<float4*>(a.o_mb + ((size_t)b * S + s) * 16 * L + 16 * (size_t)q);
-            o[0] = make_float4(4.f * y.x, 0.f, 0.f, 0.f);
-            o[1] = make_float4(4.f * y.y, 0.f, 0.f, 0.f);
-            o[2] = make_float4(4.f * y.z, 0.f, 0.f, 0.f);
-            o[3] = make_float4(4.f * y.w, 0.f, 0.f, 0.f);
-          }
-        }
-      }
-      if (VARIANT != 0) *reinterpret_cast<float4*>(s_y + s * YMB_PITCH + 4 * t) = y;
-    }
-    __syncthreads();
-  }
-
-  if (VARIANT == 0) return;
-
-  // ---- phase 3: polyphase synthesis FIR.  Thread t owns hop block Q0+t: sub-band positions j = 4(Q0+t)+e,
-  // outputs n = 4j + r.  out[4j+r] = sum_c sum_{d=-7..8} G[c][r][d] * y[c][j+d],  G = 4*h[c][4d+31-r] (0 if outside).
-  if (t < NQ && Q0 + t < L) {
-    float acc[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float v[20];  // y[c][4t .. 4t+19] (local), position j+d -> index 8 + e + d
-      const float4* yp = reinterpret_cast<const float4*>(s_y + c * YMB_PITCH + 4 * t);
-#pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const float4 u = yp[i];
-        v[4 * i] = u.x; v[4 * i + 1] = u.y; v[4 * i + 2] = u.z; v[4 * i + 3] = u.w;
-      }
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int d = 0; d < 16; ++d)  // d - 7 in [-7, 8]
-            acc[4 * e + r] = fmaf(a.coef[c][r * 16 + d], v[8 + e + d - 7], acc[4 * e + r]);
-    }
-    float4* o = reinterpret_cast<float4*>(a.wav + (size_t)b * 16 * L + 16 * (size_t)(Q0 + t));
-    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    o[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
-    o[3] = make_float4(acc[12], acc[13], acc[14], acc[15]);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Multi-band / multi-stream tail, v2: persistent, 1024 threads, thread = (frame, band).
-//   phase 1  item tid = f*4 + s      head + inverse DFT + window            -> FR[f][s][16]
-//   (the logits tile is dead: one thread issues the bulk copy of the NEXT tile's logits, overlapping phases 2-4)
-//   phase 2  item tid = t*4 + s      overlap-add + envelope                 -> Y[s][4t..4t+3]   (+ optional o_mb)
-//   phase 3  item tid = t*2 + mh     PQMF only: cosine modulation           -> U[m][4t..4t+3], m = 4*mh..4*mh+3
-//   phase 4  item tid = t*4 + r      polyphase synthesis FIR, outputs n = 16(Q0+t) + 4e + r, e = 0..3
-// Every shared-memory access pattern above is bank-conflict free (pitches 20 / 1032 floats); 32 resident warps per SM.
-// PQMF fast path (MB): h[c][k] = 2 p[k] cos(theta_c(k)) and cos(theta_c(k)) = (-1)^floor(k/8) cos(theta_c(k mod 8))
-// (pqmf.py:72-75), so U[m][j] = sum_c 2cos(theta_c(m)) y_c[j] is formed once per sub-band sample (8 x 4 MACs) and each
-// output needs only the 16 (15) prototype taps of its residue: ~24 MACs per output sample instead of 63.
-// ------------------------------------------------------------------------------------------------
-// NF frames per band per tile, NF*4 threads.  NF = 128 -> two 512-thread CTAs per SM whose phases interleave (one
-// CTA's MUFU-bound head overlaps the other's FMA-bound FIR and the bulk copies), 94.5 % useful work per tile.
-constexpr int T2_NF = 128;
-constexpr int T2_THREADS = T2_NF * 4;
-constexpr int T2_YP = (T2_NF == 128) ? 520 : 1032;  // floats per band (Y) / per modulation index (U); YP/4 = 2 mod 8
-constexpr int T2_NQ = T2_NF - 7;
-
 __device__ __forceinline__ void t2_mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
   const long long t0 = clock64();
@@ -299,220 +115,22 @@ __device__ __forceinline__ void t2_mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-template <bool PRECISE>
-__global__ void __launch_bounds__(T2_THREADS, 1024 / T2_THREADS) tail_mb_kernel(const __grid_constant__ TailArgs a, int tiles_per_utt,
-                                                                int total_tiles) {
-  constexpr int S = 4, NCH = 72, NQ = T2_NQ;
-  extern __shared__ __align__(128) float sm[];
-  float* s_log = sm;                                  // [256][72]
-  float* s_fr = s_log + T2_NF * NCH;                // [256*4][20]   (phase 3/4: U[8][T2_YP])
-  float* s_y = s_fr + T2_NF * S * FR_PITCH;         // [4][T2_YP]
-  float* s_g2 = s_y + S * T2_YP;                      // [4][16] prototype taps per output residue
-  uint64_t* bar = reinterpret_cast<uint64_t*>(s_g2 + 64);
-  const uint32_t bar_addr = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
-  const int tid = threadIdx.x;
-  const int L = a.L, F = L + 1;
-
-  auto issue_load = [&](int tile) {  // one thread: bulk-copy the logits rows [F0, F0+256) /\ [0, F) of `tile`
-    const int b = tile / tiles_per_utt, tl = tile % tiles_per_utt;
-    const int F0 = tl * NQ - 3;
-    const int f_lo = F0 < 0 ? 0 : F0;
-    const int f_hi = (F0 + T2_NF < F) ? F0 + T2_NF : F;
-    const uint32_t bytes = (uint32_t)(f_hi - f_lo) * NCH * 4u;
-    const float* src = a.logits + ((size_t)b * F + f_lo) * NCH;
-    const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(s_log + (f_lo - F0) * NCH));
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar_addr) : "memory");
-  };
-
-  if (tid < 64) s_g2[tid] = a.g2[tid >> 4][tid & 15];
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (tid == 0 && (int)blockIdx.x < total_tiles) issue_load(blockIdx.x);
-  uint32_t parity = 0;
-
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    const int b = tile / tiles_per_utt, tl = tile % tiles_per_utt;
-    const int Q0 = tl * NQ, QY0 = Q0 - 2, F0 = QY0 - 1;
-    const bool last_tile = (tl == tiles_per_utt - 1);
-    t2_mbar_wait(bar_addr, parity);
-    parity ^= 1;
-
-    // ---- phase 1
-    {
-      const int fl = tid >> 2, s = tid & 3;
-      const int f = F0 + fl;
-      float fr[16];
-      if (f >= 0 && f < F) {
-        const float2* lp = reinterpret_cast<const float2*>(s_log + fl * NCH + s * 18);
-        float x[18];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) { const float2 v = lp[i]; x[2 * i] = v.x; x[2 * i + 1] = v.y; }
-        const bool emit = (a.spec != nullptr) && (f >= Q0) && (f < Q0 + NQ || (last_tile && f == L));
-        float re[9], im[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          float mag, ph;
-          head<PRECISE>(x[k], x[9 + k], mag, ph, re[k], im[k]);
-          if (emit) {
-            const size_t o = (((size_t)b * S + s) * 9 + k) * F + f;
-            a.spec[o] = mag;
-            a.phase[o] = ph;
-          }
-        }
-        idft16_windowed(re, im, fr);
-      } else {
-#pragma unroll
-        for (int n = 0; n < 16; ++n) fr[n] = 0.f;
-      }
-      float4* dst = reinterpret_cast<float4*>(s_fr + tid * FR_PITCH);
-      dst[0] = make_float4(fr[0], fr[1], fr[2], fr[3]);
-      dst[1] = make_float4(fr[4], fr[5], fr[6], fr[7]);
-      dst[2] = make_float4(fr[8], fr[9], fr[10], fr[11]);
-      dst[3] = make_float4(fr[12], fr[13], fr[14], fr[15]);
-    }
-    __syncthreads();
-    if (tid == 0 && tile + (int)gridDim.x < total_tiles) issue_load(tile + gridDim.x);  // s_log is free again
-
-    // ---- phase 2: y block q = frame q-1 part 3 + q part 2 + q+1 part 1 + q+2 part 0, / window-square envelope
-    {
-      const int t = tid >> 2, s = tid & 3;
-      if (t < T2_NF - 3) {
-        const int q = QY0 + t;
-        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (q >= 0 && q < L) {
-          const float4 p3 = *reinterpret_cast<const float4*>(s_fr + ((t + 0) * 4 + s) * FR_PITCH + 12);
-          const float4 p2 = *reinterpret_cast<const float4*>(s_fr + ((t + 1) * 4 + s) * FR_PITCH + 8);
-          const float4 p1 = *reinterpret_cast<const float4*>(s_fr + ((t + 2) * 4 + s) * FR_PITCH + 4);
-          const float4 p0 = *reinterpret_cast<const float4*>(s_fr + ((t + 3) * 4 + s) * FR_PITCH + 0);
-          y.x = p3.x + p2.x + p1.x + p0.x;
-          y.y = p3.y + p2.y + p1.y + p0.y;
-          y.z = p3.z + p2.z + p1.z + p0.z;
-          y.w = p3.w + p2.w + p1.w + p0.w;
-          if (PRECISE || q == 0 || q == L - 1) {
-            float e0 = 1.5f, e1 = 1.5f, e2 = 1.5f, e3 = 1.5f;
-            if (q == 0) { e0 -= win_sq(12); e1 -= win_sq(13); e2 -= win_sq(14); e3 -= win_sq(15); }
-            if (q == L - 1) { e0 -= win_sq(0); e1 -= win_sq(1); e2 -= win_sq(2); e3 -= win_sq(3); }
-            y.x /= e0; y.y /= e1; y.z /= e2; y.w /= e3;
-          } else {  // steady-state envelope 1.5: multiply by the reciprocal (<= 1 ulp from the division)
-            const float inv = 0.66666666666666667f;
-            y.x *= inv; y.y *= inv; y.z *= inv; y.w *= inv;
-          }
-          if (a.o_mb != nullptr && t >= 2 && t < 2 + NQ) {
-            if (a.variant == 1) {  // MB: y_mb_hat [B][S][4L]
-              *reinterpret_cast<float4*>(a.o_mb + ((size_t)b * S + s) * 4 * L + 4 * (size_t)q) = y;
-            } else {  // MS: the zero-stuffed tensor [B][S][16L], gain 4 (models.py:463)
-              float4* o = reinterpret_cast<float4*>(a.o_mb + ((size_t)b * S + s) * 16 * L + 16 * (size_t)q);
-              o[0] = make_float4(4.f * y.x, 0.f, 0.f, 0.f);
-              o[1] = make_float4(4.f * y.y, 0.f, 0.f, 0.f);
-              o[2] = make_float4(4.f * y.z, 0.f, 0.f, 0.f);
-              o[3] = make_float4(4.f * y.w, 0.f, 0.f, 0.f);
-            }
-          }
-        }
-        *reinterpret_cast<float4*>(s_y + s * T2_YP + 4 * t) = y;
-      }
-    }
-    __syncthreads();
-
-    float* s_u = s_fr;  // [8][T2_YP], aliases the frame scratch (dead after phase 2)
-    if (a.fast_pqmf) {
-      // ---- phase 3: U[m][j] = sum_c mod[m][c] * y_c[j]
-      const int t = tid >> 1, mh = tid & 1;
-      if (t < T2_NF - 3) {
-        float4 yv[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) yv[c] = *reinterpret_cast<const float4*>(s_y + c * T2_YP + 4 * t);
-#pragma unroll
-        for (int mm = 0; mm < 4; ++mm) {
-          const int m = mh * 4 + mm;
-          float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float w = mh ? a.mod[4 + mm][c] : a.mod[mm][c];
-            u.x = fmaf(w, yv[c].x, u.x); u.y = fmaf(w, yv[c].y, u.y);
-            u.z = fmaf(w, yv[c].z, u.z); u.w = fmaf(w, yv[c].w, u.w);
-          }
-          *reinterpret_cast<float4*>(s_u + m * T2_YP + 4 * t) = u;
-        }
-      }
-      __syncthreads();
-    }
-
-    // ---- phase 4: out[16(Q0+t) + 4e + r], e = 0..3
-    {
-      const int t = tid >> 2, r = tid & 3;
-      if (t < NQ && Q0 + t < L) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        if (a.fast_pqmf) {
-          // taps d = -7..8 -> k = 4d+31-r; even d read U[7-r], odd d read U[3-r]; window index 8+e+d of [4t, 4t+20)
-          float we[20], wo[20];
-          const float4* pe = reinterpret_cast<const float4*>(s_u + (7 - r) * T2_YP + 4 * t);
-          const float4* po = reinterpret_cast<const float4*>(s_u + (3 - r) * T2_YP + 4 * t);
-#pragma unroll
-          for (int i = 0; i < 5; ++i) {
-            const float4 u = pe[i], v = po[i];
-            we[4 * i] = u.x; we[4 * i + 1] = u.y; we[4 * i + 2] = u.z; we[4 * i + 3] = u.w;
-            wo[4 * i] = v.x; wo[4 * i + 1] = v.y; wo[4 * i + 2] = v.z; wo[4 * i + 3] = v.w;
-          }
-          float g[16];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 gv = *reinterpret_cast<const float4*>(s_g2 + r * 16 + 4 * i);
-            g[4 * i] = gv.x; g[4 * i + 1] = gv.y; g[4 * i + 2] = gv.z; g[4 * i + 3] = gv.w;
-          }
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-#pragma unroll
-            for (int d = 0; d < 16; ++d)  // d - 7 in [-7, 8]; (d - 7) even <=> d odd
-              acc[e] = fmaf(g[d], (d & 1) ? we[1 + e + d] : wo[1 + e + d], acc[e]);
-        } else {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float v[20];
-            const float4* yp = reinterpret_cast<const float4*>(s_y + c * T2_YP + 4 * t);
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-              const float4 u = yp[i];
-              v[4 * i] = u.x; v[4 * i + 1] = u.y; v[4 * i + 2] = u.z; v[4 * i + 3] = u.w;
-            }
-#pragma unroll
-            for (int d = 0; d < 16; ++d) {
-              const float g = a.coef[c][r * 16 + d];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) acc[e] = fmaf(g, v[1 + e + d], acc[e]);
-            }
-          }
-        }
-        float* o = a.wav + (size_t)b * 16 * L + 16 * (size_t)(Q0 + t) + r;
-        o[0] = acc[0]; o[4] = acc[1]; o[8] = acc[2]; o[12] = acc[3];
-      }
-    }
-    __syncthreads();  // FR/U and Y are rewritten by the next tile
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
-// Multi-band / multi-stream tail, v3.  v2 was bound by shared-memory wavefronts (17.6 M per launch, 63 % L1 pipe,
-// profiles/r01_ncu_full_final.txt): every intermediate (frames, sub-band signal, modulated signal) made a round
-// trip through shared memory.  v3 keeps them in registers:
+// Multi-band / multi-stream tail.  The round-1 kernel it replaced was bound by shared-memory wavefronts (17.6 M per
+// launch, 63 % L1 pipe, profiles/r01_ncu_full_final.txt): every intermediate (frames, sub-band signal, modulated
+// signal) made a round trip through shared memory.  This one keeps them in registers:
 //   * lane = STFT frame, all four bands in the same thread.  The logits tile arrives by TMA with the 128-byte
 //     swizzle, so "one 288-byte row per lane" reads are bank-conflict-free 16-byte loads (18 per frame).
 //   * overlap-add = 12 warp shuffles per band (lane l owns hop block l: frames l, l+1, l+2, l+3); only the 6 vectors
 //     per band that cross a warp boundary go through shared memory.
 //   * the thread then holds its hop block of all four bands: envelope, optional o_mb store and the PQMF cosine
 //     modulation (8 rows) happen in registers; only U[8][512] is written to shared memory.
-//   * synthesis FIR: thread = (pair of hop blocks, residue pair): two 24-float windows serve 8 outputs (v2: 20-float
+//   * synthesis FIR: thread = (pair of hop blocks, residue pair): two 24-float windows serve 8 outputs (before: 20-float
 //     windows for 4), rows of the two residue classes 516 floats apart so the 16-byte loads of a quarter warp hit
 //     disjoint banks.  Outputs are staged (XOR-swizzled) in the dead logits buffer and leave as coalesced 16-byte stores.
 //   * persistent CTAs of 128 threads (tiles of 128 frames, <= 121 owned hop blocks), 4 per SM, each owning an EQUAL
 //     contiguous range of hop blocks (tiles never straddle an utterance): no wave-quantisation tail.  (-DMBV_T3_NF=256,
 //     2 CTAs of 8 warps per SM, measures 8 % slower: 91.6 vs 84.3 us.)
-// Arithmetic (operation order included) is identical to v2, so the parity tests need no new tolerances.
 // ------------------------------------------------------------------------------------------------
 #ifndef MBV_T3_NF
 #define MBV_T3_NF 128
@@ -993,31 +611,12 @@ static cudaError_t launch_tail_mb3(const TailArgs& a_in, int precise, int num_sm
   return cudaGetLastError();
 }
 
-static cudaError_t launch_tail_mb(const TailArgs& a, int precise, int num_sms, cudaStream_t st) {
-  const int tiles = (a.L + T2_NQ - 1) / T2_NQ;
-  const int total = a.B * tiles;
-  const size_t smem = sizeof(float) * ((size_t)T2_NF * 72 + (size_t)T2_NF * 4 * FR_PITCH + 4 * T2_YP + 64) + 64;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(tail_mb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(tail_mb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
-  const int ctas = num_sms * (1024 / T2_THREADS);
-  const int grid = total < ctas ? total : ctas;
-  if (precise) tail_mb_kernel<true><<<grid, T2_THREADS, smem, st>>>(a, tiles, total);
-  else tail_mb_kernel<false><<<grid, T2_THREADS, smem, st>>>(a, tiles, total);
-  return cudaGetLastError();
-}
-
 // ------------------------------------------------------------------------------------------------
 // Single-band tail, v3: lane = STFT frame, overlap-add by warp shuffles, hop blocks stored straight from registers.
 // Each WARP covers 32 consecutive frames = 29 complete hop blocks and the warps of a CTA overlap by 3 frames, so there
 // is no cross-warp exchange and only ONE block barrier (after the coalesced copy of the logits rows); the 10 % of
-// repeated head work buys the removal of the frame scratch round trip and the second barrier of the v1 kernel
-// (tail_kernel<0>, 96 us on the BASELINE-size problem).  Arithmetic identical to v1.
+// repeated head work buys the removal of the frame scratch round trip and the second barrier of the round-1
+// kernel (96 us on the BASELINE-size problem).
 // ------------------------------------------------------------------------------------------------
 constexpr int SB_THREADS = 256;
 constexpr int SB_NQ = 29 * (SB_THREADS / 32);   // 232 owned hop blocks per CTA
@@ -1106,30 +705,8 @@ static cudaError_t launch_tail_sb3(const TailArgs& a, int precise, cudaStream_t 
   return cudaGetLastError();
 }
 
-template <int VARIANT, bool PRECISE>
-static cudaError_t launch_tail_t(const TailArgs& a, cudaStream_t st) {
-  constexpr int S = VARIANT == 0 ? 1 : 4;
-  constexpr int NQ = VARIANT == 0 ? TAIL_NF - 3 : TAIL_NF - 7;
-  const int tiles = (a.L + NQ - 1) / NQ;
-  const size_t smem = sizeof(float) * ((size_t)TAIL_NF * S * 18 + (size_t)TAIL_NF * FR_PITCH + (size_t)S * YMB_PITCH);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(tail_kernel<VARIANT, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
-  tail_kernel<VARIANT, PRECISE><<<a.B * tiles, TAIL_THREADS, smem, st>>>(a, tiles);
-  return cudaGetLastError();
-}
-
 cudaError_t launch_tail(const TailArgs& a, int precise, int num_sms, cudaStream_t st) {
-  static const int use_v2 = getenv("MBV_TAIL_V2") ? atoi(getenv("MBV_TAIL_V2")) : 0;  // A/B measurements only
-  if (a.variant == 0) {
-    if (use_v2) return precise ? launch_tail_t<0, true>(a, st) : launch_tail_t<0, false>(a, st);
-    return launch_tail_sb3(a, precise, st);
-  }
-  if (use_v2) return launch_tail_mb(a, precise, num_sms, st);
+  if (a.variant == 0) return launch_tail_sb3(a, precise, st);
   return launch_tail_mb3(a, precise, num_sms, st);
 }
 

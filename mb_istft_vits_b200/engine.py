@@ -11,7 +11,7 @@ from typing import Dict, Optional
 import torch
 
 from . import lib as _lib
-from .configs import samples_per_frame
+from .configs import receptive_field_frames, samples_per_frame
 
 
 def fold_weight_norm(sd: Dict[str, torch.Tensor], prefixes=("dec.", "flow.")) -> Dict[str, torch.Tensor]:
@@ -33,6 +33,19 @@ def fold_weight_norm(sd: Dict[str, torch.Tensor], prefixes=("dec.", "flow.")) ->
         else:
             out[k] = v.detach().float().cpu().contiguous()
     return out
+
+
+class CapturedStep:
+    """A CUDA graph of one Engine call.  The graph bakes in the engine's workspace pointer, so ``replay`` refuses to run
+    after the engine has reallocated its workspace (``Engine.ws_generation`` changed)."""
+
+    def __init__(self, engine, graph):
+        self.engine, self.graph, self.gen = engine, graph, engine.ws_generation
+
+    def replay(self):
+        if self.engine.ws_generation != self.gen:
+            raise RuntimeError("the engine reallocated its workspace after this graph was captured; capture it again")
+        self.graph.replay()
 
 
 class Engine:
@@ -65,7 +78,7 @@ class Engine:
         self._check(rc)
         self._load(state_dict)
         self._ws = None
-        self._ws_key = None
+        self.ws_generation = 0   # bumped whenever the workspace is reallocated: captured graphs bake its pointer in
 
     # ---- plumbing
     def _check(self, rc):
@@ -105,12 +118,28 @@ class Engine:
 
     def _workspace(self, B, T):
         need = self.workspace_bytes(B, T)
-        if self._ws is None or self._ws.numel() < need:
+        if self._ws is None or self._ws.numel() < need + 1024:
+            if self._ws is not None:
+                # kernels of earlier calls (on any stream) may still be running in the old block, and the caching
+                # allocator would hand it out again at once: wait for the device before dropping it
+                torch.cuda.synchronize(self.device)
             self._ws = None
-            self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+            self.ws_generation += 1
         base = self._ws.data_ptr()
         off = (-base) % 1024
         return base + off, self._ws.numel() - off
+
+    def workspace_capacity(self) -> int:
+        """Bytes of the workspace currently held (0 before the first call)."""
+        return 0 if self._ws is None else int(self._ws.numel()) - 1024
+
+    def reserve_workspace(self, B, T) -> int:
+        """Make sure the workspace fits a [B, T] batch (reallocating, after a device synchronise, if it does not) and
+        return ``ws_generation``; holders of captured CUDA graphs compare it to detect a reallocation."""
+        self._workspace(B, T)
+        return self.ws_generation
 
     @staticmethod
     def _ptr(t: Optional[torch.Tensor]):
@@ -211,7 +240,7 @@ class Engine:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             outs = self.flow_decode(z_p, y_mask, g, want_z=want_z, want_mb=want_mb, want_spec=want_spec)
-        return graph, outs
+        return CapturedStep(self, graph), outs
 
     def tail(self, logits, T, want_mb=True, want_spec=True):
         """Fused head+iSTFT+synthesis on logits [B, F, n_ch] (channels-last)."""
@@ -268,11 +297,15 @@ class Engine:
 
     def decode_chunked(self, z, g=None, chunk_frames=256, halo_frames=None):
         """Exact streaming decode: the decoder is convolutional with a receptive field of +-24 latent frames (MB/MS;
-        +-13 single-band), so decoding overlapping windows [a-halo, b+halo) and keeping the samples of
+        +-13 single-band; computed from the geometry by configs.receptive_field_frames), so decoding overlapping windows [a-halo, b+halo) and keeping the samples of
         [a, b) reproduces the one-shot result bit for bit -- unlike the approximate overlap-add chunking of the
         reference notebooks (infer.ipynb cells 4-6).  Yields (first_frame, wav_chunk [B,1,256*(b-a)])."""
         B, _, T = z.shape
-        halo = halo_frames if halo_frames is not None else 32
+        need = receptive_field_frames(self.cfg)
+        halo = halo_frames if halo_frames is not None else need + 1
+        if halo < need:
+            raise ValueError(f"halo_frames={halo} is smaller than this decoder's receptive field ({need} latent frames): "
+                             "the chunked result would no longer be exact")
         spf = self.spf
         for a0 in range(0, T, chunk_frames):
             b0 = min(T, a0 + chunk_frames)

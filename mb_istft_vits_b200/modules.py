@@ -13,6 +13,8 @@ Signatures honoured:
 """
 from __future__ import annotations
 
+import time
+
 import torch
 from torch import nn
 
@@ -61,23 +63,38 @@ def infer_native(net_g, engine, x, x_lengths, sid=None, noise_scale=1, length_sc
     """SynthesizerTrn.infer (models.py:697-737) with everything after the duration predictor on the B200 library: the
     reference's own text encoder / duration predictor modules run as they are (``net_g.enc_p``, ``net_g.dp``,
     ``net_g.emb_g``); alignment expansion + prior sampling (models.py:717-729) is ``Engine.expand_prior`` and flow
-    reverse + decoder (models.py:730-734) one ``Engine.flow_decode`` call.  Same return tuple as the reference except that
-    ``timings`` is empty (every call is asynchronous) and ``attn`` is None when ``want_attn`` is False."""
+    reverse + decoder (models.py:730-734) one ``Engine.flow_decode`` call.  Same return tuple as the reference, including
+    the ``timings`` dict with the reference's keys (``time.time()`` deltas without a device synchronise, exactly what
+    models.py:698-735 records: on a GPU they are launch times); ``attn`` is None when ``want_attn`` is False.  Because flow
+    and decoder are one fused call here, its time is booked under 'flow' and 'waveform_decoder' is the (near-zero) rest."""
+    timings = {}
+    t0 = time.time()
     x, m_p, logs_p, x_mask = net_g.enc_p(x, x_lengths)
+    timings['text_encoder'] = time.time() - t0
     g = net_g.emb_g(sid).unsqueeze(-1) if getattr(net_g, "n_speakers", 0) > 0 else None
+    t0 = time.time()
     if getattr(net_g, "use_sdp", False):
         logw = net_g.dp(x, x_mask, g=g, reverse=True, noise_scale=noise_scale_w)
     else:
         logw = net_g.dp(x, x_mask, g=g)
+    timings['duration_predictor'] = time.time() - t0
+    t0 = time.time()
     w_ceil = torch.ceil(torch.exp(logw) * x_mask * length_scale)
     z_p, y_mask, y_lengths, attn, stats = engine.expand_prior(m_p, logs_p, w_ceil, noise_scale, x_mask=x_mask, noise=noise,
                                                               want_attn=want_attn, want_stats=True)
+    timings['alignment_and_projection'] = time.time() - t0
+    t0 = time.time()
     if max_len is not None:  # the reference decodes (z * y_mask)[:, :, :max_len]; the flow is causal-free, so run it in full
         z = engine.flow_reverse(z_p, y_mask, g)
+        timings['flow'] = time.time() - t0
+        t0 = time.time()
         o, o_mb, spec, phase = engine.decode((z * y_mask)[:, :, :max_len].contiguous(), g)
     else:
         z, o, o_mb, spec, phase = engine.flow_decode(z_p, y_mask, g, want_z=True, want_mb=True, want_spec=True)
-    return o, o_mb, spec, phase, attn, y_mask, (z, z_p, stats[0], stats[1]), {}
+        timings['flow'] = time.time() - t0
+        t0 = time.time()
+    timings['waveform_decoder'] = time.time() - t0
+    return o, o_mb, spec, phase, attn, y_mask, (z, z_p, stats[0], stats[1]), timings
 
 
 def patch_synthesizer(net_g, cfg, precision="bf16", device=0, flags=0, residual=None):

@@ -35,25 +35,30 @@ class HostStream:
 
     def _slot(self, i, zp_host, mask_host, g_host):
         s = self.slots[i % self.depth]
-        # a captured graph bakes in the engine's workspace pointer: a slot is rebuilt when the batch shape changes or when
-        # a larger batch elsewhere made the engine reallocate its workspace
-        ws = self.engine._ws
-        if ws is not None and ws.numel() < self.engine.workspace_bytes(zp_host.shape[0], zp_host.shape[2]):
-            self.drain()  # the engine is about to free its workspace: nothing may still be running in it
-        ws_ptr = self.engine._workspace(zp_host.shape[0], zp_host.shape[2])[0]
-        if s is not None and s.get("graph") is not None and s["ws_ptr"] != ws_ptr:
-            for st in (self.s_in, self.s_cmp, self.s_out):
-                st.synchronize()
+        B, T = zp_host.shape[0], zp_host.shape[2]
+        key = (tuple(zp_host.shape), tuple(mask_host.shape), None if g_host is None else tuple(g_host.shape))
+        # a captured graph bakes in the engine's workspace pointer: the engine reallocates (after synchronising the
+        # device) when this batch does not fit, and bumps ws_generation
+        gen = self.engine.reserve_workspace(B, T)
+        if s is not None and (s["key"] != key or (s["graph"] is not None and s["gen"] != gen)):
+            # The slot's buffers are about to be dropped: copies / kernels of batches already submitted may still read
+            # or write them, and the caching allocator would hand the blocks out again at once (to the new slot below).
+            self.drain()
             s = None
-        if s is None or s["zp"].shape != zp_host.shape:
-            s = {"zp": torch.empty(zp_host.shape, dtype=torch.float32, device=self.dev),
-                 "m": torch.empty(mask_host.shape, dtype=torch.float32, device=self.dev),
-                 "g": None if g_host is None else torch.empty(g_host.shape, dtype=torch.float32, device=self.dev),
-                 "wav": torch.empty((zp_host.shape[0], 1, self.engine.spf * zp_host.shape[2]), dtype=torch.float32,
-                                    device=self.dev),
-                 "ev_in": torch.cuda.Event(), "ev_cmp": torch.cuda.Event(), "ev_out": torch.cuda.Event()}
+        if s is None:
+            with torch.cuda.stream(self.s_cmp):
+                s = {"zp": torch.empty(zp_host.shape, dtype=torch.float32, device=self.dev),
+                     "m": torch.empty(mask_host.shape, dtype=torch.float32, device=self.dev),
+                     "g": None if g_host is None else torch.empty(g_host.shape, dtype=torch.float32, device=self.dev),
+                     "wav": torch.empty((B, 1, self.engine.spf * T), dtype=torch.float32, device=self.dev),
+                     "ev_in": torch.cuda.Event(), "ev_cmp": torch.cuda.Event(), "ev_out": torch.cuda.Event()}
+            for t in (s["zp"], s["m"], s["g"], s["wav"]):
+                if t is not None:   # used on all three streams for the slot's whole life
+                    t.record_stream(self.s_in)
+                    t.record_stream(self.s_out)
             s["graph"] = None
-            s["ws_ptr"] = ws_ptr
+            s["key"] = key
+            s["gen"] = gen
             if self.graphs:
                 # the slot's buffers are static, so its whole launch sequence is captured once and replayed per batch
                 with torch.cuda.stream(self.s_cmp):

@@ -3,7 +3,7 @@
 Every utterance is independent through the flow and the decoder (no batch statistics, no cross-utterance op), so
 the path shards by utterance with NO collective on the hot path.  One process per GPU
 (as the reference's ``mp.spawn``, train_latest.py:55); weights are replicated.  The only exchange is at the end:
-each rank's waveforms go to the consumer rank -- lengths first, then the padded samples -- over
+each rank's waveforms go to the consumer rank -- one small placement table, then the samples point-to-point -- over
 ``torch.distributed`` (NCCL on NVLink 5 / NVSwitch on the box, gloo in the CPU tests).
 """
 from __future__ import annotations
@@ -48,34 +48,54 @@ def gather_waveforms(wav: torch.Tensor, n_samples: torch.Tensor, indices: Sequen
     """Collect every rank's waveforms on rank ``dst`` in the original utterance order.
 
     wav: [b_local, 1, S_local] (padded), n_samples: [b_local] valid sample counts, indices: global utterance ids.
-    Two collectives: an all_gather of (count, max length) then one padded all_gather of the samples (sub-millisecond
-    over NVSwitch for a 256 x 10 s batch = 226 MB).  Returns the list of trimmed 1-D waveforms on ``dst``, None elsewhere.
+    One small collective, one device->host read and one grouped point-to-point exchange:
+      1. every rank writes (valid samples, local row) of its own utterances into a [total, 2] int64 table (-1 elsewhere)
+         and appends its (rows, row pitch); one ``all_gather_into_tensor`` + ONE ``.cpu()`` gives every rank the whole
+         placement -- no per-utterance host sync;
+      2. each rank sends its [b_local, S_local] block, exactly as it lies in memory (no padding to the longest rank), to
+         ``dst``; ``dst`` posts one receive per peer.  The operations go out as one ``batch_isend_irecv`` group
+         (NCCL: ncclGroupStart/End, all peers in flight at once over NVSwitch; only ``dst`` receives -- the round-1
+         version all-gathered the padded samples to EVERY rank, world x the traffic).
+    Returns the list of trimmed 1-D waveforms (views of the received blocks) on ``dst``, None elsewhere.
     """
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     dev = wav.device
-    b_local = wav.shape[0]
-    meta = torch.tensor([b_local, wav.shape[-1] if b_local else 0], dtype=torch.int64, device=dev)
-    metas = [torch.zeros_like(meta) for _ in range(world)]
-    dist.all_gather(metas, meta, group=group)
-    b_max = max(int(m[0]) for m in metas)
-    s_max = max(int(m[1]) for m in metas)
-    pad = torch.zeros((b_max, s_max), dtype=torch.float32, device=dev)
-    info = torch.full((b_max, 2), -1, dtype=torch.int64, device=dev)  # (global index, valid samples)
+    b_local = int(wav.shape[0])
+    s_local = int(wav.shape[-1]) if b_local else 0
+    table = torch.full((total + 1, 2), -1, dtype=torch.int64, device=dev)
     if b_local:
-        pad[:b_local, : wav.shape[-1]] = wav[:, 0, :]
-        info[:b_local, 0] = torch.as_tensor(list(indices), dtype=torch.int64, device=dev)
-        info[:b_local, 1] = n_samples.to(dev, torch.int64)
-    pads = [torch.empty_like(pad) for _ in range(world)]
-    infos = [torch.empty_like(info) for _ in range(world)]
-    dist.all_gather(pads, pad, group=group)
-    dist.all_gather(infos, info, group=group)
+        idx = torch.as_tensor(list(indices), dtype=torch.int64, device=dev)
+        table[idx, 0] = n_samples.to(dev, torch.int64)
+        table[idx, 1] = torch.arange(b_local, dtype=torch.int64, device=dev)
+    table[total, 0] = b_local
+    table[total, 1] = s_local
+    tables = torch.empty((world * (total + 1), 2), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(tables, table, group=group)
+    host = tables.cpu().view(world, total + 1, 2)  # the only device->host read of the gather
+    shapes = [(int(host[r, total, 0]), int(host[r, total, 1])) for r in range(world)]
+    block = wav.reshape(b_local, s_local).contiguous() if b_local else None
+    ops, bufs = [], [None] * world
+    if rank == dst:
+        for r in range(world):
+            if r == dst or shapes[r][0] == 0:
+                continue
+            bufs[r] = torch.empty(shapes[r], dtype=torch.float32, device=dev)
+            ops.append(dist.P2POp(dist.irecv, bufs[r], dist.get_global_rank(group, r) if group is not None else r, group))
+        bufs[dst] = block
+    elif b_local:
+        ops.append(dist.P2POp(dist.isend, block, dist.get_global_rank(group, dst) if group is not None else dst, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
     if rank != dst:
         return None
     out: List[Optional[torch.Tensor]] = [None] * total
+    ns_all, row_all = host[:, :total, 0].tolist(), host[:, :total, 1].tolist()
     for r in range(world):
-        for j in range(int(metas[r][0])):
-            gi, ns = int(infos[r][j, 0]), int(infos[r][j, 1])
-            out[gi] = pads[r][j, :ns].clone()
+        for gi in range(total):
+            if ns_all[r][gi] >= 0:
+                assert out[gi] is None, f"utterance {gi} was produced by two ranks"
+                out[gi] = bufs[r][row_all[r][gi], : ns_all[r][gi]]
     assert all(o is not None for o in out), "an utterance was not produced by any rank"
     return out  # type: ignore[return-value]

@@ -490,8 +490,14 @@ def test_host_stream_pipeline_returns_the_same_waveforms(fused):
     ins.append((ins[0][0], ins[0][1]))
     outs.append(torch.zeros((B, 1, 256 * T)).pin_memory())
     events.append(hs.submit(ins[-1][0], ins[-1][1], outs[-1]))
+    # a SMALLER batch right after (no drain in between): the slot it replaces still has its download in flight, and the
+    # new slot's buffers may reuse its memory -- the earlier batch must still come back intact (pipeline.py)
+    zs, ms_, _ = synth.make_latents(cfg, 1, T - 10, seed=300)
+    small_out = torch.zeros((1, 1, 256 * (T - 10))).pin_memory()
+    hs.submit(zs.pin_memory(), ms_.pin_memory(), small_out)
     hs.drain()
     assert torch.equal(big_out, eng.flow_decode(zb.cuda(), mb.cuda())[1].cpu()) if fused else True
+    assert torch.equal(small_out, eng.flow_decode(zs.cuda(), ms_.cuda())[1].cpu()) if fused else True
     for i in range(6):
         assert events[i].query()
         z, wav, _, _, _ = eng.flow_decode(ins[i][0].cuda(), ins[i][1].cuda())

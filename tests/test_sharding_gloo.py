@@ -67,3 +67,45 @@ def test_shard_decode_gather_world_size_2(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert torch.load(os.path.join(str(tmp_path), "ok.pt")) is True
+
+
+# ---- the same plumbing on hardware: two ranks, two GPUs, NCCL, the CUDA decoder (needs `gpurun --gpus 2`)
+def _nccl_worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from mb_istft_vits_b200 import Engine, get_config, synth
+    cfg = get_config("ljs_mini_mb_istft_vits")
+    sd = synth.make_state_dict(cfg, seed=1)
+    lengths = torch.tensor([30, 7, 18, 25, 11, 29, 3])
+    z, mask, _ = synth.make_latents(cfg, 7, 30, seed=2, lengths=lengths)
+    eng = Engine(cfg, sd, precision="fp32", device=rank)
+    z_loc, len_loc, idx = shard_batch(z, lengths, rank, world)
+    wav = eng.decode(z_loc.cuda(rank), want_mb=False, want_spec=False)[0]
+    out = gather_waveforms(wav, (len_loc * 256).cuda(rank), idx, total=7, dst=0)
+    if rank == 0:
+        full = eng.decode(z.cuda(0), want_mb=False, want_spec=False)[0]
+        ok = True
+        for i in range(7):
+            n = int(lengths[i]) * 256
+            m = max(0, n - 24 * 256)
+            ok &= out[i].shape[0] == n and out[i].device.index == 0
+            ok &= bool(torch.allclose(out[i][:m], full[i, 0, :m], atol=1e-5))
+        torch.save(bool(ok), os.path.join(tmp, "ok_nccl.pt"))
+    else:
+        assert out is None
+    dist.barrier()
+    eng.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_shard_decode_gather_two_gpus_nccl(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (two NCCL ranks must never share one GPU)")
+    port = _free_port()
+    mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert torch.load(os.path.join(str(tmp_path), "ok_nccl.pt")) is True

@@ -19,7 +19,6 @@ from __future__ import annotations
 
 import os
 import sys
-import types
 
 import numpy as np
 import torch
@@ -48,55 +47,15 @@ CASES = [
 
 
 def import_reference():
-    """Shims: stub the unbuilt Cython module (models.py:11), stub librosa (stft.py:32-33, unused by
-    TorchSTFT), and let Tensor.cuda(cpu_device) be a no-op (pqmf.py:78,79,86)."""
-    ma = types.ModuleType("monotonic_align")
-    ma.maximum_path = None
-    sys.modules["monotonic_align"] = ma
-    lib, libu = types.ModuleType("librosa"), types.ModuleType("librosa.util")
-    libu.pad_center = lambda d, size, axis=-1, **k: d
-    libu.tiny = lambda x: np.finfo(np.float32).tiny
-    libu.normalize = lambda S, norm=None, **k: S
-    lib.util = libu
-    sys.modules["librosa"] = lib
-    sys.modules["librosa.util"] = libu
-    _cuda = torch.Tensor.cuda
-
-    def cuda(self, device=None, *a, **k):
-        if device is not None and torch.device(device).type == "cpu":
-            return self
-        return _cuda(self, device, *a, **k)
-    torch.Tensor.cuda = cuda
-    sys.path.insert(0, REF)
-    import models  # noqa
-    return models
+    """The reference's `models` module through baseline/ref_loader.py (the three import shims live there)."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_loader
+    return ref_loader.import_reference()
 
 
 def build_reference(models, cfg, sd):
-    kw = dict(
-        inter_channels=cfg["inter_channels"], hidden_channels=cfg["hidden_channels"],
-        filter_channels=768 if cfg["hidden_channels"] == 192 else 384, n_heads=2, n_layers=3 if cfg["hidden_channels"] == 96 else 6,
-        kernel_size=3, p_dropout=0.1, resblock=cfg["resblock"],
-        resblock_kernel_sizes=cfg["resblock_kernel_sizes"],
-        resblock_dilation_sizes=cfg["resblock_dilation_sizes"],
-        upsample_rates=cfg["upsample_rates"], upsample_initial_channel=cfg["upsample_initial_channel"],
-        upsample_kernel_sizes=cfg["upsample_kernel_sizes"],
-        gen_istft_n_fft=cfg["gen_istft_n_fft"], gen_istft_hop_size=cfg["gen_istft_hop_size"],
-        n_speakers=cfg["n_speakers"], gin_channels=cfg["gin_channels"], use_sdp=False,
-        ms_istft_vits=cfg["variant"] == "ms", mb_istft_vits=cfg["variant"] == "mb",
-        istft_vits=cfg["variant"] == "istft",
-        subbands=cfg["subbands"] if cfg["variant"] != "istft" else False,
-    )
-    net = models.SynthesizerTrn(59, 513, 32, **kw).eval()
-    ref_sd = net.state_dict()
-    want = {k for k in ref_sd if k.startswith(("dec.", "flow.", "emb_g."))}
-    have = set(sd.keys())
-    assert want == have, f"key inventory mismatch: missing {sorted(want - have)[:5]} extra {sorted(have - want)[:5]}"
-    for k in want:
-        assert tuple(ref_sd[k].shape) == tuple(sd[k].shape), (k, ref_sd[k].shape, sd[k].shape)
-    missing, unexpected = net.load_state_dict(sd, strict=False)
-    assert not unexpected
-    return net
+    import ref_loader
+    return ref_loader.build_synthesizer(cfg, sd)
 
 
 def main():
