@@ -85,6 +85,8 @@ typedef struct {
   int32_t flags;                    /* MBV_FLAG_* */
 } mbv_config;
 
+#define MBV_MAX_ENCQ_LAYERS 16     /* PosteriorEncoder WN depth (models.py:646) */
+
 /* debug / tuning flags */
 #define MBV_FLAG_FORCE_SIMT 4       /* run the CUDA-core conv on the tensor-core operand layout (cross-check) */
 #define MBV_FLAG_RESIDUAL_FP16 8    /* bf16 path: keep the decoder's ResBlock residual stream in (saturating) fp16 */

@@ -33,8 +33,8 @@ cudaError_t tc_set_attributes();
 // fused ResBlock1 conv pair (c1 -> lrelu -> c2 -> residual add), 128-channel stages: see conv_tc.cu
 struct TcPairPlan {
   CUtensorMap tmA, tmB, tmB2;   // activations, c1 weights, c2 weights
-  int box_rows, n_boxes, slab_stage_bytes, n_slab_stages, n_w_stages;
-  int t_tiles, total_tiles, h_off, w_off, bar_off, smem_bytes, grid;
+  int box_rows, slab_stage_bytes, n_slab_stages, n_w_stages;
+  int n_out, t_tiles, total_tiles, h_off, w_off, bar_off, smem_bytes, grid;
 };
 const char* tc_make_pair_plan(int prec, const ConvArgs& a, int num_sms, TcPairPlan* plan);
 cudaError_t launch_conv_pair(int prec, const ConvArgs& a, const TcPairPlan& plan, cudaStream_t st);

@@ -122,12 +122,22 @@ struct mbv_handle {
   float* fl_cond_w[4] = {nullptr};  // [L*2Hp][gin] packed in the gate row order
   float* fl_cond_b[4] = {nullptr};  // [L*2Hp]
 
+  // posterior encoder (models.py:217-246; optional: loaded when the state-dict carries enc_q.*): pre 1x1 -> 16-layer WN ->
+  // proj 1x1, the WN skip path collapsed into proj like the flow's into post
+  bool has_enc_q = false;
+  int eq_layers = 16;        // hard-coded at models.py:646 (kernel 5, dilation_rate 1, 16 layers)
+  int eq_spec = 0, eq_spec_p = 0;   // spectrogram channels (513) and their 64-padded pitch
+  ConvLayer eq_pre, eq_proj, eq_in[MBV_MAX_ENCQ_LAYERS], eq_rs[MBV_MAX_ENCQ_LAYERS];
+  float* eq_cond_w = nullptr;
+  float* eq_cond_b = nullptr;
+
   // tensor-map cache: valid while (B, T, ws) stay the same
   struct PlanKey { int B, T; void* ws; int kind; bool operator<(const PlanKey& o) const {
     if (B != o.B) return B < o.B; if (T != o.T) return T < o.T; if (ws != o.ws) return ws < o.ws; return kind < o.kind; } };
   std::map<PlanKey, std::vector<TcPlan>> plan_cache;
   std::map<PlanKey, std::vector<TcPairPlan>> pair_cache;
-  int use_pair = 0;  // fused ResBlock conv pairs on 128-channel stages (MBV_FLAG_FUSED_PAIR; off by default)
+  int use_pair = 0;  // fused ResBlock conv pairs on 128-channel stages (conv_pair_kernel)
+  int pair_max_taps = 17;
 
   // per-launch device timing (mbv_set_profiling)
   bool profiling = false;
@@ -348,6 +358,104 @@ void fill_tail_coef(mbv_handle* h, const float hs[4][63]) {
       }
 }
 
+
+// One WaveNet stack (modules.WN, modules.py:111-176) feeding a 1x1 projection `post` (ResidualCouplingLayer.post /
+// PosteriorEncoder.proj).  Packs, for l < NL: the gate conv in_layers[l] as 128-row tiles of [64 tanh | 64 sigmoid] rows and,
+// for l < NL-1, the RESIDUAL half of res_skip_layers[l].  The skip halves of all layers and `post` are linear in the gate
+// outputs, so they collapse into ONE conv over the concatenated gate outputs:
+//   post(sum_l skip_l) = sum_l (W_post W_skip,l) acts_l + (W_post sum_l b_skip,l + b_post)      (modules.py:169-176)
+// post_map[n] = source row of `post` for packed output row n.  The running skip sum never exists in memory and the last
+// layer has no res/skip conv at all.
+int pack_wn(mbv_handle* h, const TensorMap& m, const std::string& enc, int NL, int K, const std::string& post_name, int post_out,
+            const std::vector<int>& post_map, ConvLayer* in_layers, ConvLayer* rs_layers, ConvLayer* post, float** cond_w,
+            float** cond_b) {
+  const int H = h->H, Hp = h->Hp, gin = h->cfg.gin_channels;
+  int rc;
+  char pfx[128];
+  std::vector<int> hin = iota_pad(H, Hp);
+  for (int l = 0; l < NL; ++l) {
+    // gate rows: 128-row MMA tiles of [64 tanh rows | 64 sigmoid rows] for 64 consecutive channels, so ONE
+    // accumulator holds both halves of a channel (lanes i and i+64) and H = 192 = 3 x 64 needs no padding
+    std::vector<int> gmap(2 * Hp, -1);
+    for (int o = 0; o < H; ++o) { gmap[128 * (o / 64) + (o % 64)] = o; gmap[128 * (o / 64) + 64 + (o % 64)] = H + o; }
+    snprintf(pfx, sizeof(pfx), "%s.in_layers.%d", enc.c_str(), l);
+    rc = pack_conv1d(h, m, pfx, 2 * H, H, K, 1, gmap, hin, true, 1, &in_layers[l]);
+    if (rc) return rc;
+    snprintf(pfx, sizeof(pfx), "%s.res_skip_layers.%d", enc.c_str(), l);
+    if (l < NL - 1) {
+      rc = pack_conv1d(h, m, pfx, 2 * H, H, 1, 1, iota_pad(H, Hp), hin, true, 0, &rs_layers[l]);
+      if (rc) return rc;
+      rs_layers[l].n_valid = H;
+    }
+    rs_layers[l].macs_per_row = (double)(l < NL - 1 ? 2 * H : H) * H;  // algorithmic MACs of the reference layer
+  }
+  {
+    const int64_t pws[3] = {post_out, H, 1}, pbs[1] = {post_out};
+    const HostTensor* pw = find_tensor(h, m, post_name + ".weight", 3, pws);
+    const HostTensor* pb = pw ? find_tensor(h, m, post_name + ".bias", 1, pbs) : nullptr;
+    if (!pw || !pb) return MBV_ERR_WEIGHTS;
+    HostTensor fw, fb;
+    fw.shape = {post_out, (int64_t)NL * H, 1};
+    fw.data.assign((size_t)post_out * NL * H, 0.f);
+    fb.shape = {post_out};
+    fb.data.assign(post_out, 0.f);
+    std::vector<double> bsum(H, 0.0);
+    for (int l = 0; l < NL; ++l) {
+      const bool lastl = (l == NL - 1);
+      const int64_t ws[3] = {lastl ? H : 2 * H, H, 1}, bs[1] = {lastl ? H : 2 * H};
+      snprintf(pfx, sizeof(pfx), "%s.res_skip_layers.%d", enc.c_str(), l);
+      const HostTensor* w = find_tensor(h, m, std::string(pfx) + ".weight", 3, ws);
+      const HostTensor* b = w ? find_tensor(h, m, std::string(pfx) + ".bias", 1, bs) : nullptr;
+      if (!w || !b) return MBV_ERR_WEIGHTS;
+      const int r0 = lastl ? 0 : H;  // first skip row
+      for (int j2 = 0; j2 < H; ++j2) bsum[j2] += b->data[r0 + j2];
+      std::vector<double> acc(H);
+      for (int o = 0; o < post_out; ++o) {
+        for (int cidx = 0; cidx < H; ++cidx) acc[cidx] = 0.0;
+        for (int j2 = 0; j2 < H; ++j2) {
+          const double pv = pw->data[(size_t)o * H + j2];
+          const float* wr = &w->data[(size_t)(r0 + j2) * H];
+          for (int cidx = 0; cidx < H; ++cidx) acc[cidx] += pv * (double)wr[cidx];
+        }
+        for (int cidx = 0; cidx < H; ++cidx) fw.data[(size_t)o * NL * H + (size_t)l * H + cidx] = (float)acc[cidx];
+      }
+    }
+    for (int o = 0; o < post_out; ++o) {
+      double acc = pb->data[o];
+      for (int j2 = 0; j2 < H; ++j2) acc += (double)pw->data[(size_t)o * H + j2] * bsum[j2];
+      fb.data[o] = (float)acc;
+    }
+    TensorMap fused;
+    fused["post_fused.weight"] = std::move(fw);
+    fused["post_fused.bias"] = std::move(fb);
+    std::vector<int> fin((size_t)NL * Hp, -1);
+    for (int l = 0; l < NL; ++l)
+      for (int cidx = 0; cidx < H; ++cidx) fin[(size_t)l * Hp + cidx] = l * H + cidx;
+    rc = pack_conv1d(h, fused, "post_fused", post_out, NL * H, 1, 1, post_map, fin, true, 0, post);
+    if (rc) return rc;
+    post->macs_per_row = (double)post_out * H;  // algorithmic MACs of the reference projection
+  }
+  if (gin) {
+    snprintf(pfx, sizeof(pfx), "%s.cond_layer", enc.c_str());
+    const int64_t ws[3] = {2 * H * NL, gin, 1}, bs[1] = {2 * H * NL};
+    const HostTensor* w = find_tensor(h, m, std::string(pfx) + ".weight", 3, ws);
+    const HostTensor* b = w ? find_tensor(h, m, std::string(pfx) + ".bias", 1, bs) : nullptr;
+    if (!w || !b) return MBV_ERR_WEIGHTS;
+    std::vector<float> pw((size_t)NL * 2 * Hp * gin, 0.f), pb((size_t)NL * 2 * Hp, 0.f);
+    for (int l = 0; l < NL; ++l)
+      for (int o = 0; o < 2 * H; ++o) {
+        const int ch = o < H ? o : o - H;  // same row order as the packed in_layers weights
+        const int dst = l * 2 * Hp + 128 * (ch / 64) + (ch % 64) + (o < H ? 0 : 64);
+        const int src = l * 2 * H + o;
+        memcpy(&pw[(size_t)dst * gin], &w->data[(size_t)src * gin], sizeof(float) * gin);
+        pb[dst] = b->data[src];
+      }
+    if ((rc = upload_f32(h, pw, cond_w))) return rc;
+    if ((rc = upload_f32(h, pb, cond_b))) return rc;
+  }
+  return MBV_OK;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -427,6 +535,7 @@ extern "C" int mbv_create(const mbv_config* cfg, mbv_handle** out) {
   if (h->prec != MBV_PREC_FP32) CUDA_TRY(h, tc_set_attributes());
   if (h->prec >= MBV_PREC_BF16) CUDA_TRY(h, tc_pair_set_attributes());
   h->use_pair = (c.flags & MBV_FLAG_FUSED_PAIR) ? 1 : 0;
+  if (const char* e = getenv("MBV_PAIR_MAX_TAPS")) h->pair_max_taps = atoi(e);  // A/B measurements only
   return MBV_OK;
 }
 
@@ -545,94 +654,33 @@ extern "C" int mbv_load_weights(mbv_handle* h, const mbv_tensor* tensors, int32_
       snprintf(pfx, sizeof(pfx), "flow.flows.%d.pre", 2 * f);
       rc = pack_conv1d(h, m, pfx, H, half, 1, 1, out_map, in_map, true, 0, &h->fl_pre[f]);
       if (rc) return rc;
-      std::vector<int> hin = iota_pad(H, Hp);
-      for (int l = 0; l < NL; ++l) {
-        // gate rows: 128-row MMA tiles of [64 tanh rows | 64 sigmoid rows] for 64 consecutive channels, so ONE
-        // accumulator holds both halves of a channel (lanes i and i+64) and H = 192 = 3 x 64 needs no padding
-        std::vector<int> gmap(2 * Hp, -1);
-        for (int o = 0; o < H; ++o) { gmap[128 * (o / 64) + (o % 64)] = o; gmap[128 * (o / 64) + 64 + (o % 64)] = H + o; }
-        snprintf(pfx, sizeof(pfx), "flow.flows.%d.enc.in_layers.%d", 2 * f, l);
-        rc = pack_conv1d(h, m, pfx, 2 * H, H, K, 1, gmap, hin, true, 1, &h->fl_in[f][l]);
-        if (rc) return rc;
-        snprintf(pfx, sizeof(pfx), "flow.flows.%d.enc.res_skip_layers.%d", 2 * f, l);
-        // Only the RESIDUAL half of res_skip is a per-layer conv (rows [0, H) of the [2H, H, 1] weight).  The skip halves
-        // of all layers and `post` are linear in the gate outputs, so they collapse into ONE conv over the concatenated
-        // gate outputs (built below): the running skip sum never exists in memory and the last layer has no conv at all.
-        if (l < NL - 1) {
-          rc = pack_conv1d(h, m, pfx, 2 * H, H, 1, 1, iota_pad(H, Hp), hin, true, 0, &h->fl_rs[f][l]);
-          if (rc) return rc;
-          h->fl_rs[f][l].n_valid = H;
-        }
-        h->fl_rs[f][l].macs_per_row = (double)(l < NL - 1 ? 2 * H : H) * H;  // algorithmic MACs of the reference layer
-      }
-      // m = post(sum_l skip_l) = sum_l (W_post W_skip,l) acts_l + (W_post sum_l b_skip,l + b_post)      (modules.py:169-176,345)
-      {
-        const int64_t pws[3] = {half, H, 1}, pbs[1] = {half};
-        snprintf(pfx, sizeof(pfx), "flow.flows.%d.post", 2 * f);
-        const HostTensor* pw = find_tensor(h, m, std::string(pfx) + ".weight", 3, pws);
-        const HostTensor* pb = pw ? find_tensor(h, m, std::string(pfx) + ".bias", 1, pbs) : nullptr;
-        if (!pw || !pb) return MBV_ERR_WEIGHTS;
-        HostTensor fw, fb;
-        fw.shape = {half, (int64_t)NL * H, 1};
-        fw.data.assign((size_t)half * NL * H, 0.f);
-        fb.shape = {half};
-        fb.data.assign(half, 0.f);
-        std::vector<double> bsum(H, 0.0);
-        for (int l = 0; l < NL; ++l) {
-          const bool lastl = (l == NL - 1);
-          const int64_t ws[3] = {lastl ? H : 2 * H, H, 1}, bs[1] = {lastl ? H : 2 * H};
-          snprintf(pfx, sizeof(pfx), "flow.flows.%d.enc.res_skip_layers.%d", 2 * f, l);
-          const HostTensor* w = find_tensor(h, m, std::string(pfx) + ".weight", 3, ws);
-          const HostTensor* b = w ? find_tensor(h, m, std::string(pfx) + ".bias", 1, bs) : nullptr;
-          if (!w || !b) return MBV_ERR_WEIGHTS;
-          const int r0 = lastl ? 0 : H;  // first skip row
-          for (int j2 = 0; j2 < H; ++j2) bsum[j2] += b->data[r0 + j2];
-          std::vector<double> acc(H);
-          for (int o = 0; o < half; ++o) {
-            for (int cidx = 0; cidx < H; ++cidx) acc[cidx] = 0.0;
-            for (int j2 = 0; j2 < H; ++j2) {
-              const double pv = pw->data[(size_t)o * H + j2];
-              const float* wr = &w->data[(size_t)(r0 + j2) * H];
-              for (int cidx = 0; cidx < H; ++cidx) acc[cidx] += pv * (double)wr[cidx];
-            }
-            for (int cidx = 0; cidx < H; ++cidx) fw.data[(size_t)o * NL * H + (size_t)l * H + cidx] = (float)acc[cidx];
-          }
-        }
-        for (int o = 0; o < half; ++o) {
-          double acc = pb->data[o];
-          for (int j2 = 0; j2 < H; ++j2) acc += (double)pw->data[(size_t)o * H + j2] * bsum[j2];
-          fb.data[o] = (float)acc;
-        }
-        TensorMap fused;
-        fused["post_fused.weight"] = std::move(fw);
-        fused["post_fused.bias"] = std::move(fb);
-        std::vector<int> pmap(half, -1), fin((size_t)NL * Hp, -1);
-        for (int j2 = 0; j2 < half; ++j2) pmap[j2] = odd ? half - 1 - j2 : j2;
-        for (int l = 0; l < NL; ++l)
-          for (int cidx = 0; cidx < H; ++cidx) fin[(size_t)l * Hp + cidx] = l * H + cidx;
-        rc = pack_conv1d(h, fused, "post_fused", half, NL * H, 1, 1, pmap, fin, true, 0, &h->fl_post[f]);
-        if (rc) return rc;
-        h->fl_post[f].macs_per_row = (double)half * H;  // algorithmic MACs of the reference `post`
-      }
-      if (gin) {
-        snprintf(pfx, sizeof(pfx), "flow.flows.%d.enc.cond_layer", 2 * f);
-        const int64_t ws[3] = {2 * H * NL, gin, 1}, bs[1] = {2 * H * NL};
-        const HostTensor* w = find_tensor(h, m, std::string(pfx) + ".weight", 3, ws);
-        const HostTensor* b = w ? find_tensor(h, m, std::string(pfx) + ".bias", 1, bs) : nullptr;
-        if (!w || !b) return MBV_ERR_WEIGHTS;
-        std::vector<float> pw((size_t)NL * 2 * Hp * gin, 0.f), pb((size_t)NL * 2 * Hp, 0.f);
-        for (int l = 0; l < NL; ++l)
-          for (int o = 0; o < 2 * H; ++o) {
-            const int ch = o < H ? o : o - H;  // same row order as the packed in_layers weights
-            const int dst = l * 2 * Hp + 128 * (ch / 64) + (ch % 64) + (o < H ? 0 : 64);
-            const int src = l * 2 * H + o;
-            memcpy(&pw[(size_t)dst * gin], &w->data[(size_t)src * gin], sizeof(float) * gin);
-            pb[dst] = b->data[src];
-          }
-        if ((rc = upload_f32(h, pw, &h->fl_cond_w[f]))) return rc;
-        if ((rc = upload_f32(h, pb, &h->fl_cond_b[f]))) return rc;
-      }
+      std::vector<int> pmap(half, -1);
+      for (int j2 = 0; j2 < half; ++j2) pmap[j2] = odd ? half - 1 - j2 : j2;
+      snprintf(pfx, sizeof(pfx), "flow.flows.%d.enc", 2 * f);
+      char post_name[96];
+      snprintf(post_name, sizeof(post_name), "flow.flows.%d.post", 2 * f);
+      rc = pack_wn(h, m, pfx, NL, K, post_name, half, pmap, h->fl_in[f], h->fl_rs[f], &h->fl_post[f], &h->fl_cond_w[f], &h->fl_cond_b[f]);
+      if (rc) return rc;
     }
+  }
+  // ---------------- posterior encoder (optional)
+  if (m.count("enc_q.pre.weight")) {
+    const HostTensor& pw = m["enc_q.pre.weight"];
+    if (pw.shape.size() != 3 || pw.shape[0] != h->H || pw.shape[2] != 1) return fail(h, MBV_ERR_WEIGHTS, "enc_q.pre.weight has the wrong shape");
+    int NL = 0;
+    char pfx[96];
+    for (;; ++NL) { snprintf(pfx, sizeof(pfx), "enc_q.enc.in_layers.%d.weight", NL); if (!m.count(pfx)) break; }
+    if (NL < 1 || NL > MBV_MAX_ENCQ_LAYERS) return fail(h, MBV_ERR_UNSUPPORTED, "enc_q: %d WN layers (1..%d supported)", NL, MBV_MAX_ENCQ_LAYERS);
+    h->eq_layers = NL;
+    h->eq_spec = (int)pw.shape[1];
+    h->eq_spec_p = round_up(h->eq_spec, 64);
+    rc = pack_conv1d(h, m, "enc_q.pre", h->H, h->eq_spec, 1, 1, iota_pad(h->H, h->Hp), iota_pad(h->eq_spec, h->eq_spec_p), true, 0, &h->eq_pre);
+    if (rc) return rc;
+    // proj rows [m (inter) | logs (inter)] in their own order (models.py:243-244)
+    rc = pack_wn(h, m, "enc_q.enc", NL, c.flow_kernel, "enc_q.proj", 2 * h->Cz, iota_pad(2 * h->Cz, 2 * h->Cz), h->eq_in, h->eq_rs, &h->eq_proj,
+                 &h->eq_cond_w, &h->eq_cond_b);
+    if (rc) return rc;
+    h->has_enc_q = true;
   }
   h->weights_loaded = true;
   return MBV_OK;
@@ -764,9 +812,9 @@ int run_conv(Ctx& cx, const ConvLayer& L, const void* x, int B, int L_in, int L_
 
 // fused ResBlock1 conv pair: x' = xin + c2(lrelu(c1(a_in))) (conv_pair_kernel); epi is c2's RES epilogue
 bool pair_ok(const mbv_handle* h, const ConvLayer& c1, const ConvLayer& c2) {
-  return h->use_pair && h->prec >= MBV_PREC_BF16 && !(h->cfg.flags & MBV_FLAG_FORCE_SIMT) && c1.Cp_in == 128 && c1.N_total == 128 &&
-         c2.Cp_in == 128 && c2.N_total == 128 && c1.taps == c2.taps && c2.dil == 1 && (c1.taps & 1) && (c1.taps - 1) / 2 <= 8 &&
-         c1.n_phases == 1 && c2.n_phases == 1;
+  return h->use_pair && h->prec >= MBV_PREC_BF16 && h->res_half && !(h->cfg.flags & MBV_FLAG_FORCE_SIMT) && c1.Cp_in == 128 &&
+         c1.N_total == 128 && c2.Cp_in == 128 && c2.N_total == 128 && c1.taps == c2.taps && c2.dil == 1 && (c1.taps & 1) &&
+         c1.taps <= h->pair_max_taps && c1.n_phases == 1 && c2.n_phases == 1;
 }
 
 int run_pair(Ctx& cx, const ConvLayer& c1, const ConvLayer& c2, const void* x, int B, int L, const EpiParams& epi, float slope_h) {
@@ -789,7 +837,7 @@ int run_pair(Ctx& cx, const ConvLayer& c1, const ConvLayer& c2, const void* x, i
   }
   cx.pair_idx++;
   char desc[56];
-  snprintf(desc, sizeof(desc), "pair m1 Ci%d N%d k%d d%d ph1 L%d nt240", c1.Cp_in, c1.N_total, c1.taps, c1.dil, L);
+  snprintf(desc, sizeof(desc), "pair m1 Ci%d N%d k%d d%d ph1 L%d nt%d", c1.Cp_in, c1.N_total, c1.taps, c1.dil, L, plan.n_out);
   ProfScope prof(cx, 0, h->profiling ? desc : "");
   CUDA_TRY(h, launch_conv_pair(h->prec, a, plan, cx.st));
   cx.launches++;

@@ -26,10 +26,11 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--flags", type=int, default=0, help="extra mbv_config flags (16 = fused pairs, 32 = cluster pairs)")
     a = ap.parse_args()
     cfg = get_config(a.config)
     sd = synth.make_state_dict(cfg, seed=1234)
-    eng = Engine(cfg, sd, precision=a.precision)
+    eng = Engine(cfg, sd, precision=a.precision, flags=a.flags)
     z_p, mask, _ = synth.make_latents(cfg, a.batch, a.frames, seed=1234)
     z_p, mask = z_p.cuda(), mask.cuda()
     g = None

@@ -11,7 +11,7 @@ from mb_istft_vits_b200 import Engine, get_config, synth
 cfg = get_config("ljs_mb_istft_vits")
 sd = synth.make_state_dict(cfg)
 import os
-eng = Engine(cfg, sd, precision=os.environ.get("MBV_PREC", "bf16"))
+eng = Engine(cfg, sd, precision=os.environ.get("MBV_PREC", "bf16"), flags=int(os.environ.get("MBV_FLAGS", "0")))
 z, m, _ = synth.make_latents(cfg, 64, 862)
 z, m = z.cuda(), m.cuda()
 if len(sys.argv) > 1 and sys.argv[1] == "decode":
