@@ -97,8 +97,9 @@ def build_synthesizer(cfg, sd, device="cpu"):
     models = import_reference()
     net = models.SynthesizerTrn(59, 513, 32, **model_kwargs(cfg)).eval()
     ref_sd = net.state_dict()
-    want = {k for k in ref_sd if k.startswith(("dec.", "flow.", "emb_g."))}
-    have = {k for k in sd if k.startswith(("dec.", "flow.", "emb_g."))}
+    pre = ("dec.", "flow.", "emb_g.") + (("enc_q.",) if any(k.startswith("enc_q.") for k in sd) else ())
+    want = {k for k in ref_sd if k.startswith(pre)}
+    have = {k for k in sd if k.startswith(pre)}
     assert want == have, f"key inventory mismatch: missing {sorted(want - have)[:5]} extra {sorted(have - want)[:5]}"
     for k in want:
         assert tuple(ref_sd[k].shape) == tuple(sd[k].shape), (k, ref_sd[k].shape, sd[k].shape)

@@ -93,6 +93,10 @@ typedef struct {
 #define MBV_FLAG_CLUSTER_PAIRS 32    /* experimental: run the multi-tap convs as clusters of two CTAs that work on two time tiles of the
                                      * same weight group; each CTA fetches half of every weight tile and TMA-multicasts it to both.
                                      * Parity-tested; < 1 % faster per step on B200, hence opt-in. */
+#define MBV_FLAG_BRANCHES 64         /* experimental: run the parallel ResBlocks of a stage on the library's two extra streams (own
+                                     * residual / operand buffers per branch) so that one branch's launches fill the drain and
+                                     * partial last round of another's.  Results identical; measured neutral (9.32-9.35 vs
+                                     * 9.33-9.56 ms per step, profiles/round2_branches_ab.txt), hence opt-in. */
 #define MBV_FLAG_FUSED_PAIR 16      /* experimental: run each ResBlock1 conv pair of a 128-channel stage as ONE kernel that keeps
                                      * the intermediate activation in shared memory (conv_pair_kernel).  Parity-tested; currently
                                      * not faster than the two-launch path, hence opt-in. */
@@ -135,6 +139,17 @@ int mbv_flow_reverse(mbv_handle* h, const float* z_p, const float* y_mask, const
 int mbv_flow_forward(mbv_handle* h, const float* x, const float* y_mask, const float* g, float* z_out,
                      int32_t B, int32_t T, void* ws, size_t ws_bytes, void* stream);
 
+/* NEXT-row widening (completes voice conversion, models.py:790-798): PosteriorEncoder.forward
+ * (models.py:236-246): x = pre(spec) * mask; x = WN(x, mask, g) (16 layers, models.py:646); stats = proj(x) * mask;
+ * m, logs = split(stats); z = (m + noise * exp(logs)) * mask.  Available when mbv_load_weights received the enc_q.* tensors
+ * (enc_q.pre / enc_q.enc.in_layers.N / enc_q.enc.res_skip_layers.N / enc_q.enc.cond_layer / enc_q.proj), else
+ * MBV_ERR_WEIGHTS.  spec: [B, spec_channels (513), T]; y_mask: [B,1,T] (the caller builds it from the lengths, as
+ * commons.sequence_mask does); g: [B,gin,1] or NULL; noise: [B,inter,T] (the reference draws torch.randn_like(m));
+ * z: [B,inter,T]; stats: [B, 2*inter, T] = m | logs.  Its own workspace size: mbv_posterior_workspace_bytes. */
+int mbv_posterior_workspace_bytes(mbv_handle* h, int32_t B, int32_t T, size_t* bytes);
+int mbv_posterior_encode(mbv_handle* h, const float* spec, const float* y_mask, const float* g, const float* noise,
+                         float* z, float* stats, int32_t B, int32_t T, void* ws, size_t ws_bytes, void* stream);
+
 /* dec.forward(z, g) (models.py:278-297 / 344-377 / 430-467).  z: [B, inter, T]; wav: [B,1,S*T]
  * with S = samples per latent frame (256).  Optional outputs (NULL to skip):
  *   o_mb : MB [B,4,64T];  MS [B,4,256T] (the zero-stuffed tensor the reference returns); iSTFT: must be NULL
@@ -149,6 +164,28 @@ int mbv_decode(mbv_handle* h, const float* z, const float* z_mask, const float* 
 int mbv_flow_decode(mbv_handle* h, const float* z_p, const float* y_mask, const float* g,
                     float* z_out, float* wav, float* o_mb, float* spec, float* phase, int32_t B,
                     int32_t T, void* ws, size_t ws_bytes, void* stream);
+
+/* NEXT-row widening: exact streaming decode.  The decoders are convolutional with a finite receptive
+ * field (mbv_receptive_field latent frames per side: 25 for the MB / MS geometry, 13 single-band), so a stream of latent
+ * chunks can be decoded with bounded latency and a result that equals the one-shot mbv_decode bit for bit -- unlike the
+ * overlap-add chunking of the reference notebooks (infer.ipynb cells 4-6), which ignores the receptive field.
+ *   mbv_stream_open   device state for B parallel utterances and chunks of <= max_chunk_frames latent frames: the latent
+ *                     history (left halo + frames whose right halo has not arrived yet) and the decoded window
+ *   mbv_stream_push   appends z_chunk [B, inter, n_frames] (device, already multiplied by the mask like dec's input) and
+ *                     writes the samples of every frame whose right context is now complete -- all remaining frames when
+ *                     `last` -- to wav_out [B, 1, 256 * n_frames_out] (device; capacity in frames given).  *first_frame /
+ *                     *n_frames_out say which frames were emitted (n_frames_out may be 0).  Latency = halo frames.
+ *                     ws: mbv_stream_workspace_bytes.  Asynchronous on `stream`; the state is not re-entrant.
+ * PCM chunking (tts_vits.py:204-226) sits on top: mbv_pcm16 on the emitted samples, 20 ms slices on the host. */
+typedef struct mbv_stream mbv_stream;
+int mbv_receptive_field(mbv_handle* h);
+int mbv_stream_open(mbv_handle* h, int32_t B, int32_t max_chunk_frames, mbv_stream** out);
+int mbv_stream_workspace_bytes(mbv_stream* s, size_t* bytes);
+int mbv_stream_halo(mbv_stream* s);
+int mbv_stream_push(mbv_stream* s, const float* z_chunk, int32_t n_frames, int32_t last, const float* g, float* wav_out,
+                    int32_t wav_capacity_frames, int64_t* first_frame, int32_t* n_frames_out, void* ws, size_t ws_bytes,
+                    void* stream);
+void mbv_stream_close(mbv_stream* s);
 
 /* Introspection for benchmarks: number of kernel launches the last compute call enqueued, and the
  * algorithmic FLOPs (2*MACs of the dense contractions) of a decode / flow call at (B,T). */

@@ -100,7 +100,7 @@ def receptive_field_frames(cfg) -> int:
     (K / (2 S) input rows), each stage's widest ResBlock (sum over its convs of (k-1)/2 * d, plus (k-1)/2 per second conv
     of a ResBlock1), conv_post (k 7) with its 1-frame reflection pad, the 16/4 iSTFT overlap (4 frames) and the 63-tap
     synthesis FIR (8 sub-band samples = 2 hop blocks), each divided by the cumulative upsampling rate it runs at.
-    ljs_mb: 24.95 -> 25 (SURVEY 3.3 measured +-24); single band [8,8]: 13.9 -> 14 (measured +-13)."""
+    ljs_mb: 24.95 -> 25 (SURVEY 3.3 measured +-24); single band [8,8]: 12.7 -> 13 (measured +-13)."""
     import math
     rf = 3.0
     rate = 1.0

@@ -254,6 +254,7 @@ struct TcRt {  // runtime scalars the kernel needs beyond ConvArgs
   // indices >= split_from address the pieces.  (Results are bit-identical: a column's accumulation does not depend on
   // the tile width.)
   int split_from, split_k, split_n, virt_tiles;
+  int pdl;           // launch with programmatic stream serialization
   int rotate;        // two channel tiles, even grid: swap which one a CTA takes every round.  With a static round-robin
                      // an even CTA would otherwise ALWAYS get channel tile 0; when the second tile is half padding
                      // (192 = 128 + 64 rows: flow pre / res convs) its epilogue is half the work and half the CTAs idle.
@@ -846,158 +847,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
 // ------------------------------------------------------------------------------------------------
 // Fused ResBlock1 conv pair (modules.py:217-224):  x' = x + c2(lrelu(c1(a) + b1)) + b2,  a = lrelu(x) the operand tensor.
-// At 128 channels a k=3 conv is HBM-bound (96 FLOP/B): the two-launch path moves 1356 MB per pair where 904 MB are
-// needed, because the intermediate h = lrelu(c1(a)) goes to HBM and back.  This kernel keeps h on the SM.
-//
-//   * one CTA = all 128 channels x N_out = 128 - (K-1) output columns.  c1 accumulates D1[128 ch, 128 cols] for the
-//     columns [t0 - (K-1)/2, +128) -- the outputs plus the halo c2 needs; epilogue-1 warps turn it into 16-bit
-//     lrelu(. + b1) rows (zero outside the utterance = c2's own zero padding) stored K-major, 128B-swizzled, in a
-//     shared-memory tile that is the B operand of c2 (tap j = rows [j, j+128)); c2 accumulates D2[128, 128] (columns
-//     >= N_out are computed from rows past the tile and never stored) and the RES epilogue drains it.
-//   * TMEM = four 128-column accumulators: D1 and D2 are BOTH double-buffered, and the MMA warp issues
-//         conv1(i+1), conv2(i), conv1(i+2), conv2(i+1), ...
-//     so the tensor pipe runs conv 1 of the next tile while epilogue 1 of this tile builds h, and both convs of later
-//     tiles while the residual add of this tile streams to HBM.  (The first version had one D1: conv 1 -> h epilogue ->
-//     conv 2 were serial, 17 % of a k=11 tile and 45 % of a k=3 tile with the tensor pipe idle -- profiles/r02_pair_timeline.txt.)
-//   * both epilogues move TWO adjacent channels per lane (lane pairs exchange halves with one shuffle per column pair):
-//     32-bit shared / global accesses instead of 16-bit ones, half the LSU instructions of the plain RES epilogue.
+// At 128 channels a k=3 conv is HBM-bound (96 FLOP/B) and even the k=7 / k=11 pairs spend a third of their time moving
+// the intermediate h = lrelu(c1(a)) out to HBM and back (profiles/r02_launch_times_bf16.txt: stage-1 pairs take
+// 302 / 379 / 496 us against 106 / 246 / 388 us of tensor work).  This kernel keeps h on the SM:
+//   * one CTA = all 128 channels x 160 output columns.  c1 accumulates D1[128, 176] for the columns [t0-8, t0+168)
+//     (the halo c2 needs, K <= 17); the epilogue warps turn it into bf16 lrelu(.) rows -- zero outside the utterance,
+//     which is c2's own zero padding -- and store them K-major, 128B-swizzled, into a shared-memory tile that is the
+//     B operand of c2 (tap j = rows [8 - (K-1)/2 + j, +160)).  c2 accumulates D2[128, 160] into one of TWO further TMEM
+//     buffers and the normal RES epilogue drains it: conv 1 and conv 2 of the next tile run while the residual add of
+//     this tile is still streaming to HBM (160 columns is what 176 + 2 x 160 <= 512 TMEM columns allow).
+//   * the tensor core never waits for HBM for the second conv, the intermediate never exists in memory, and the pair
+//     reads a and the residual once and writes its two outputs once.
 //   * warp roles: 8 warps residual add (epilogue 2), 4 warps h tile (epilogue 1), 1 TMA producer, 1 MMA issuer.
-// Geometry handled: Cp_in = C_out = 128 (one channel tile, two k-blocks), stride 1, c2 dilation 1, odd K <= 17, 16-bit
-// operands with a 16-bit residual stream (bf16 + fp16 stream, or fp16 single stream); everything else takes the
-// two-launch path.
+// Geometry handled: Cp_in = C_out = 128 (one channel tile, two k-blocks), stride 1, c2 dilation 1; everything else
+// takes the two-launch path.
 // ------------------------------------------------------------------------------------------------
-constexpr int PAIR_COLS = 128;                       // columns of D1 / D2 = rows of h that conv 1 produces
-constexpr int PAIR_H_ROWS = 144;                     // h rows per k-block (conv 2 reads rows [tap, tap + 128), tap <= 16)
-constexpr int PAIR_H_BYTES = 2 * PAIR_H_ROWS * TC_ROW_BYTES;
-constexpr int PAIR_NEPI2 = 8, PAIR_NEPI1 = 4;
-constexpr int PAIR_THREADS = 32 * (PAIR_NEPI2 + PAIR_NEPI1 + 2);
+constexpr int PAIR_N = 160;      // output columns per tile
+constexpr int PAIR_HALO = 8;     // columns of D1 before / after the outputs
+constexpr int PAIR_N1 = PAIR_N + 2 * PAIR_HALO;  // columns of D1 (176)
+constexpr int PAIR_D2_COL0 = 192, PAIR_D2_STRIDE = 160;  // TMEM: D1 [0,176), D2 buffers [192,352) and [352,512)
+constexpr int PAIR_H_BYTES = 2 * PAIR_N1 * TC_ROW_BYTES;
 
 struct PairRt {
-  int box_rows, slab_stage_bytes, n_slab_stages, n_w_stages;
-  int n_out, t_tiles, total_tiles;
+  int pdl;
+  int box_rows, n_boxes, slab_stage_bytes, n_slab_stages, n_w_stages;
+  int t_tiles, total_tiles;
   int h_off, w_off, bar_off;  // byte offsets in (aligned) dynamic smem
   long long* dbg;             // MBV_TIMELINE=9: CTA 0 clock stamps [tile][8] (debug only)
 };
 
-// ---- two channels per lane.  Lane 2m holds channel c, lane 2m+1 channel c+1, each 32 consecutive time steps in
-// registers.  In memory (channels-last, 16-bit) the pair is one aligned 32-bit word per time step: the even lane moves the
-// words of the even steps, the odd lane those of the odd steps, and one shuffle per step pair swaps the halves.
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-  return r;
-}
-template <typename T> __device__ __forceinline__ uint32_t pack16(float lo, float hi);
-template <> __device__ __forceinline__ uint32_t pack16<__half>(float lo, float hi) {
-  return (uint32_t)__half_as_ushort(to_half_sat(lo)) | ((uint32_t)__half_as_ushort(to_half_sat(hi)) << 16);
-}
-template <> __device__ __forceinline__ uint32_t pack16<__nv_bfloat16>(float lo, float hi) {
-  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<const uint32_t*>(&v);
-}
-template <typename T> __device__ __forceinline__ float unpack_lo(uint32_t w);
-template <typename T> __device__ __forceinline__ float unpack_hi(uint32_t w);
-template <> __device__ __forceinline__ float unpack_lo<__half>(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); }
-template <> __device__ __forceinline__ float unpack_hi<__half>(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
-
-// own-channel values v[0..31] -> the words this lane stores: word i = {even channel, odd channel} at step 2i + (lane & 1)
-template <typename T>
-__device__ __forceinline__ void pair_words(const float* v, int odd, uint32_t* w) {
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const uint32_t own = pack16<T>(v[2 * i], v[2 * i + 1]);          // this channel at steps 2i, 2i+1
-    const uint32_t oth = __shfl_xor_sync(0xffffffffu, own, 1);       // the partner channel at the same steps
-    // even lane: {own step 2i, partner step 2i}; odd lane: {partner step 2i+1, own step 2i+1}
-    w[i] = odd ? prmt(oth, own, 0x7632u) : prmt(own, oth, 0x5410u);
-  }
-}
-// the words this lane loaded (fp16 pairs) -> own-channel values
-__device__ __forceinline__ void pair_unwords_half(const uint32_t* w, int odd, float* v) {
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const uint32_t oth = __shfl_xor_sync(0xffffffffu, w[i], 1);
-    // even lane loaded step 2i: {own, partner}; the odd lane's word (step 2i+1) has this lane's value in its low half
-    // odd lane loaded step 2i+1: {partner, own}; the even lane's word (step 2i) has this lane's value in its high half
-    v[2 * i] = odd ? unpack_hi<__half>(oth) : unpack_lo<__half>(w[i]);
-    v[2 * i + 1] = odd ? unpack_hi<__half>(w[i]) : unpack_lo<__half>(oth);
-  }
-}
-// global pointer of this lane's first word: rows step 2 apart (row 2i + odd), channel pair (n & ~1)
-template <bool FULL>
-__device__ __forceinline__ void pair_load_rows(const void* base, size_t elem_off, int odd, int nt, uint32_t* w) {
-  const char* p = reinterpret_cast<const char*>(base) + elem_off * 2 + (size_t)odd * (TC_M * 2);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    w[i] = 0u;
-    if (FULL || 2 * i + odd < nt) w[i] = *reinterpret_cast<const uint32_t*>(p + (size_t)i * (2 * TC_M * 2));
-  }
-}
-template <bool FULL>
-__device__ __forceinline__ void pair_store_rows(void* base, size_t elem_off, int odd, int nt, const uint32_t* w) {
-  char* p = reinterpret_cast<char*>(base) + elem_off * 2 + (size_t)odd * (TC_M * 2);
-#pragma unroll
-  for (int i = 0; i < 16; ++i)
-    if (FULL || 2 * i + odd < nt) *reinterpret_cast<uint32_t*>(p + (size_t)i * (2 * TC_M * 2)) = w[i];
-}
-
-// The ResBlock residual add on one 32-step chunk (semantics of epi_res above), channel pitch 128, 16-bit streams.
-//   RH = 1: xin / xout / xs are fp16 streams next to the bf16 operand copies;  RH = 2: xin is the fp16 operand tensor
-//   lrelu(x) (inverted on load), no xout.  xw = this lane's words of xin, loaded while the accumulator was in flight.
-template <typename Op, int RH, bool FULL>
-__device__ __forceinline__ void pair_epi_res(const EpiParams& p, int b, int n, int t_first, int nt, const float* acc,
-                                             const uint32_t* xw) {
-  using T = typename Op::T;
-  const int odd = n & 1;
-  const float bias = p.bias[(size_t)b * p.bias_bs + n];
-  const size_t base = ((size_t)b * p.rows_res + t_first) * TC_M + (n & ~1);   // channel pitch = 128 elements
-  float x[32];
-  pair_unwords_half(xw, odd, x);
-  if constexpr (RH == 2) {
-    const float inv = p.inv_slope;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) x[i] = fminf(x[i], x[i] * inv);
-  }
-  const int sm = p.sum_mode;
-  uint32_t w[16];
-  if (sm == 2 || sm == 3) {
-    float sv[32];
-    pair_load_rows<FULL>(p.xs, base, odd, nt, w);
-    pair_unwords_half(w, odd, sv);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) x[i] = (x[i] + acc[i] + bias) + sv[i];
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) x[i] = x[i] + acc[i] + bias;
-  }
-  if (p.xout || sm == 1 || sm == 2) {
-    pair_words<__half>(x, odd, w);
-    if (p.xout) pair_store_rows<FULL>(p.xout, base, odd, nt, w);
-    if (sm == 1 || sm == 2) pair_store_rows<FULL>(p.xs, base, odd, nt, w);
-  }
-  if (p.n_act) {
-    const float slope = p.slope, scale = (sm >= 3) ? p.scale : 1.f;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) { x[i] *= scale; x[i] = fmaxf(x[i], x[i] * slope); }
-    pair_words<T>(x, odd, w);
-    pair_store_rows<FULL>(p.act[0], ((size_t)b * p.rows_out + t_first + p.row_add) * TC_M + (n & ~1), odd, nt, w);
-    // ReflectionPad1d((1,0)) of the conv_post input: mapped row dup_src is also stored at row dup_dst
-    const int di = p.dup_src - p.row_add - t_first;
-    if (p.dup_src >= 0 && di >= 0 && di < nt) {
-      float v = 0.f;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) if (i == di) v = x[i];
-      op_store1<Op>(reinterpret_cast<T*>(p.act[0]) + ((size_t)b * p.rows_out + p.dup_dst) * TC_M + n, v);
-    }
-  }
-}
-
-template <typename Op, int RH>
-__global__ void __launch_bounds__(PAIR_THREADS, 1)
+template <typename Op, int LD, int RH>
+__global__ void __launch_bounds__(TcThreads<EPI_RES>::value, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const ConvArgs a, const PairRt rt) {
   using T = typename Op::T;
   constexpr int KB = 64;
-  constexpr int NEPI2 = PAIR_NEPI2, NEPI1 = PAIR_NEPI1, NEPI = NEPI1 + NEPI2;
+  constexpr int NEPI = EpiWarps<EPI_RES>::value;  // 12 = 8 residual-add warps (epilogue 2) + 4 h-tile warps (epilogue 1)
+  constexpr int NEPI2 = 8, NEPI1 = NEPI - NEPI2;
   constexpr int WARP_TMA = NEPI, WARP_MMA = NEPI + 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1006,8 +892,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint8_t* smW = smem + rt.w_off;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + rt.bar_off);
   const int iXF = 0, iXE = iXF + rt.n_slab_stages, iWF = iXE + rt.n_slab_stages, iWE = iWF + rt.n_w_stages;
-  const int iD1F = iWE + rt.n_w_stages, iD1E = iD1F + 2, iHF = iD1E + 2, iHE = iHF + 1, iD2F = iHE + 1, iD2E = iD2F + 2,
-            nBars = iD2E + 2;
+  const int iD1F = iWE + rt.n_w_stages, iHR = iD1F + 1, iD2F = iHR + 1, iD2E = iD2F + 2, nBars = iD2E + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + nBars);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -1019,20 +904,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     tma_prefetch_desc(&tmW2);
     for (int i = 0; i < rt.n_slab_stages; ++i) { mbar_init(BAR(iXF + i), 1); mbar_init(BAR(iXE + i), 1); }
     for (int i = 0; i < rt.n_w_stages; ++i) { mbar_init(BAR(iWF + i), 1); mbar_init(BAR(iWE + i), 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(BAR(iD1F + i), 1); mbar_init(BAR(iD1E + i), NEPI1);
-      mbar_init(BAR(iD2F + i), 1); mbar_init(BAR(iD2E + i), NEPI2);
-    }
-    mbar_init(BAR(iHF), NEPI1);
-    mbar_init(BAR(iHE), 1);
+    mbar_init(BAR(iD1F), 1);
+    mbar_init(BAR(iHR), NEPI1);
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(iD2F + i), 1); mbar_init(BAR(iD2E + i), NEPI2); }
     fence_barrier_init();
   }
-  // rows [128, 144) of the h tile are read by conv 2 for its (never stored) columns >= N_out: keep them finite
-  for (int i = threadIdx.x; i < 2 * (PAIR_H_ROWS - PAIR_COLS) * TC_ROW_BYTES / 16; i += blockDim.x) {
-    const int kb = i / ((PAIR_H_ROWS - PAIR_COLS) * TC_ROW_BYTES / 16), r = i % ((PAIR_H_ROWS - PAIR_COLS) * TC_ROW_BYTES / 16);
-    *reinterpret_cast<uint4*>(smH + (size_t)kb * PAIR_H_ROWS * TC_ROW_BYTES + PAIR_COLS * TC_ROW_BYTES + r * 16) = make_uint4(0, 0, 0, 0);
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (warp == WARP_MMA) tmem_alloc(smem_u32(tmem_ptr_smem), 512u);
   tc_fence_before();
   __syncthreads();
@@ -1042,225 +918,215 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int taps = a.taps;
-  const int h2 = (taps - 1) / 2;
-  const int n_out = rt.n_out;
-  const uint32_t slab_bytes = (uint32_t)rt.box_rows * TC_ROW_BYTES;
+  const uint32_t slab_bytes = (uint32_t)rt.n_boxes * rt.box_rows * TC_ROW_BYTES;
   const uint32_t w_tile_bytes = TC_M * TC_ROW_BYTES;
-  const int n_my = (rt.total_tiles > (int)blockIdx.x) ? (rt.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp == WARP_TMA) {
-    // ===================== TMA producer, in the MMA warp's consumption order =====================
-    //   conv1(0) | conv1(1) conv2(0) | conv1(2) conv2(1) | ... | conv2(n-1)
+    // ===================== TMA producer: per tile  [slab kb, W1 taps of kb] x 2, then W2 (kb, tap) =====================
     int sx = 0, sw = 0;
     uint32_t px = 0, pw = 0;
-    auto load_w = [&](const CUtensorMap* map, int kb, int tap) {
-      mbar_wait(BAR(iWE + sw), pw ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(BAR(iWF + sw), w_tile_bytes);
-        tma_load_2d(smem_u32(smW + (size_t)sw * TC_M * TC_ROW_BYTES), map, BAR(iWF + sw), kb * KB, tap * TC_M);
-      }
-      __syncwarp();
-      if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
-    };
-    for (int it = 0; it <= n_my; ++it) {
-      if (it < n_my) {
-        const int tile = blockIdx.x + it * gridDim.x;
-        const int tt = tile % rt.t_tiles, b = tile / rt.t_tiles;
-        const int xrow0 = tt * n_out - h2 + a.shift0[0];
-        for (int kb = 0; kb < 2; ++kb) {
-          mbar_wait(BAR(iXE + sx), px ^ 1);
+    for (int tile = blockIdx.x; tile < rt.total_tiles; tile += gridDim.x) {
+      const int tt = tile % rt.t_tiles, b = tile / rt.t_tiles;
+      const int xrow0 = tt * PAIR_N - PAIR_HALO + a.shift0[0];
+      for (int kb = 0; kb < 2; ++kb) {
+        mbar_wait(BAR(iXE + sx), px ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(BAR(iXF + sx), slab_bytes);
+          const uint32_t dst = smem_u32(smX + (size_t)sx * rt.slab_stage_bytes);
+          for (int i = 0; i < rt.n_boxes; ++i)
+            tma_load_3d(dst + (uint32_t)(i * rt.box_rows) * TC_ROW_BYTES, &tmX, BAR(iXF + sx), kb * KB,
+                        xrow0 + i * rt.box_rows, b);
+        }
+        __syncwarp();
+        if (++sx == rt.n_slab_stages) { sx = 0; px ^= 1; }
+        for (int tap = 0; tap < taps; ++tap) {
+          mbar_wait(BAR(iWE + sw), pw ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(BAR(iXF + sx), slab_bytes);
-            tma_load_3d(smem_u32(smX + (size_t)sx * rt.slab_stage_bytes), &tmX, BAR(iXF + sx), kb * KB, xrow0, b);
+            mbar_expect_tx(BAR(iWF + sw), w_tile_bytes);
+            tma_load_2d(smem_u32(smW + (size_t)sw * TC_M * TC_ROW_BYTES), &tmW1, BAR(iWF + sw), kb * KB, tap * TC_M);
           }
           __syncwarp();
-          if (++sx == rt.n_slab_stages) { sx = 0; px ^= 1; }
-          for (int tap = 0; tap < taps; ++tap) load_w(&tmW1, kb, tap);
+          if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
         }
       }
-      if (it > 0)
-        for (int kb = 0; kb < 2; ++kb)
-          for (int tap = 0; tap < taps; ++tap) load_w(&tmW2, kb, tap);
+      for (int kb = 0; kb < 2; ++kb)
+        for (int tap = 0; tap < taps; ++tap) {
+          mbar_wait(BAR(iWE + sw), pw ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(BAR(iWF + sw), w_tile_bytes);
+            tma_load_2d(smem_u32(smW + (size_t)sw * TC_M * TC_ROW_BYTES), &tmW2, BAR(iWF + sw), kb * KB, tap * TC_M);
+          }
+          __syncwarp();
+          if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
+        }
     }
   } else if (warp == WARP_MMA) {
     // ===================== MMA issuer =====================
     constexpr uint32_t fmt = (Op::kPrec == 3) ? 0u : 1u;
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(PAIR_COLS >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    const uint32_t idesc1 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(PAIR_N1 >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(PAIR_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
     const uint32_t tap_step1 = (uint32_t)(a.dil * TC_ROW_BYTES) >> 4;
-    int sx = 0, sw = 0;
-    uint32_t px = 0, pw = 0;
-    for (int it = 0; it <= n_my; ++it) {
-      long long* dbg = (rt.dbg && blockIdx.x == 0 && lane == 0 && it < 16) ? rt.dbg + it * 8 : nullptr;
-      if (it < n_my) {
-        // ---- conv 1 of tile `it` -> D1[it & 1]; the buffer was drained by epilogue 1 of tile it - 2
-        const int d1 = it & 1;
-        mbar_wait(BAR(iD1E + d1), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+    const uint32_t h_row0 = (uint32_t)(PAIR_HALO - (taps - 1) / 2);
+    int sx = 0, sw = 0, d2 = 0;
+    uint32_t px = 0, pw = 0, ph = 0, pd2 = 0;
+    for (int tile = blockIdx.x; tile < rt.total_tiles; tile += gridDim.x) {
+      // ---- conv 1 -> D1 (TMEM columns [0, 176)); D1 is free: the previous tile's epilogue 1 signalled HR before conv 2
+      uint32_t accum = 0;
+      long long* dbg = (rt.dbg && blockIdx.x == 0 && lane == 0 && tile / (int)gridDim.x < 16) ? rt.dbg + (tile / gridDim.x) * 8 : nullptr;
+      if (dbg) dbg[0] = clock64();
+      for (int kb = 0; kb < 2; ++kb) {
+        mbar_wait(BAR(iXF + sx), px);
         tc_fence_after();
-        if (dbg) dbg[0] = clock64();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(d1 * PAIR_COLS);
-        uint32_t accum = 0;
-        for (int kb = 0; kb < 2; ++kb) {
-          mbar_wait(BAR(iXF + sx), px);
+        uint32_t x_lo = desc_lo(smem_u32(smX + (size_t)sx * rt.slab_stage_bytes));
+        for (int tap = 0; tap < taps; ++tap) {
+          mbar_wait(BAR(iWF + sw), pw);
           tc_fence_after();
-          uint32_t x_lo = desc_lo(smem_u32(smX + (size_t)sx * rt.slab_stage_bytes));
-          for (int tap = 0; tap < taps; ++tap) {
-            mbar_wait(BAR(iWF + sw), pw);
-            tc_fence_after();
-            const uint32_t w_lo = desc_lo(smem_u32(smW + (size_t)sw * TC_M * TC_ROW_BYTES));
-            if (elect_one()) {
+          const uint32_t w_lo = desc_lo(smem_u32(smW + (size_t)sw * TC_M * TC_ROW_BYTES));
+          if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) tc_mma<2>(tmem_d, desc64(w_lo + 2 * k), desc64(x_lo + 2 * k), idesc, (k == 0) ? accum : 1u);
-              tc_commit(BAR(iWE + sw));
-            }
-            __syncwarp();
-            accum = 1;
-            x_lo += tap_step1;
-            if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
+            for (int k = 0; k < 4; ++k) tc_mma<2>(tmem_base, desc64(w_lo + 2 * k), desc64(x_lo + 2 * k), idesc1, (k == 0) ? accum : 1u);
+            tc_commit(BAR(iWE + sw));
           }
-          if (elect_one()) tc_commit(BAR(iXE + sx));
           __syncwarp();
-          if (++sx == rt.n_slab_stages) { sx = 0; px ^= 1; }
+          accum = 1;
+          x_lo += tap_step1;
+          if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
         }
-        if (elect_one()) tc_commit(BAR(iD1F + d1));
+        if (elect_one()) tc_commit(BAR(iXE + sx));
         __syncwarp();
-        if (dbg) dbg[1] = clock64();
+        if (++sx == rt.n_slab_stages) { sx = 0; px ^= 1; }
       }
-      if (it > 0) {
-        // ---- conv 2 of tile it - 1 -> D2[(it - 1) & 1]: needs its h tile and that buffer drained (epilogue 2 of tile it - 3)
-        const int j = it - 1, d2 = j & 1;
-        long long* dbg2 = (rt.dbg && blockIdx.x == 0 && lane == 0 && j < 16) ? rt.dbg + j * 8 : nullptr;
-        mbar_wait(BAR(iHF), (uint32_t)j & 1u);
-        mbar_wait(BAR(iD2E + d2), ((uint32_t)(j >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        if (dbg2) dbg2[2] = clock64();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(2 * PAIR_COLS + d2 * PAIR_COLS);
-        uint32_t accum = 0;
-        for (int kb = 0; kb < 2; ++kb) {
-          const uint32_t h_lo = desc_lo(smem_u32(smH + (size_t)kb * PAIR_H_ROWS * TC_ROW_BYTES));
-          for (int tap = 0; tap < taps; ++tap) {
-            mbar_wait(BAR(iWF + sw), pw);
-            tc_fence_after();
-            const uint32_t w_lo = desc_lo(smem_u32(smW + (size_t)sw * TC_M * TC_ROW_BYTES));
-            const uint32_t b_lo = h_lo + (uint32_t)tap * (TC_ROW_BYTES >> 4);
-            if (elect_one()) {
+      if (elect_one()) tc_commit(BAR(iD1F));
+      __syncwarp();
+      if (dbg) dbg[1] = clock64();
+      // ---- conv 2 -> D2 buffer d2: needs the h tile (epilogue 1 of this tile) and that buffer drained (epilogue 2 of tile i-2)
+      mbar_wait(BAR(iHR), ph);
+      mbar_wait(BAR(iD2E + d2), pd2 ^ 1);
+      tc_fence_after();
+      if (dbg) dbg[2] = clock64();
+      accum = 0;
+      for (int kb = 0; kb < 2; ++kb) {
+        const uint32_t h_lo = desc_lo(smem_u32(smH + (size_t)kb * PAIR_N1 * TC_ROW_BYTES) + h_row0 * TC_ROW_BYTES);
+        for (int tap = 0; tap < taps; ++tap) {
+          mbar_wait(BAR(iWF + sw), pw);
+          tc_fence_after();
+          const uint32_t w_lo = desc_lo(smem_u32(smW + (size_t)sw * TC_M * TC_ROW_BYTES));
+          const uint32_t b_lo = h_lo + (uint32_t)tap * (TC_ROW_BYTES >> 4);
+          if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) tc_mma<2>(tmem_d, desc64(w_lo + 2 * k), desc64(b_lo + 2 * k), idesc, (k == 0) ? accum : 1u);
-              tc_commit(BAR(iWE + sw));
-            }
-            __syncwarp();
-            accum = 1;
-            if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
+            for (int k = 0; k < 4; ++k)
+              tc_mma<2>(tmem_base + PAIR_D2_COL0 + d2 * PAIR_D2_STRIDE, desc64(w_lo + 2 * k), desc64(b_lo + 2 * k), idesc2, (k == 0) ? accum : 1u);
+            tc_commit(BAR(iWE + sw));
           }
+          __syncwarp();
+          accum = 1;
+          if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
         }
-        if (elect_one()) { tc_commit(BAR(iHE)); tc_commit(BAR(iD2F + d2)); }
-        __syncwarp();
-        if (dbg2) dbg2[3] = clock64();
       }
+      if (elect_one()) tc_commit(BAR(iD2F + d2));
+      __syncwarp();
+      if (dbg) dbg[3] = clock64();
+      ph ^= 1;
+      if (++d2 == 2) { d2 = 0; pd2 ^= 1; }
     }
   } else if (warp >= NEPI2 && warp < NEPI) {
     // ===================== epilogue-1 warps (4): D1 -> h tile =====================
-    // h = lrelu(D1 + b1) in the operand type, zero outside the utterance, into the c2 operand tile.  The single h tile is
-    // free again when conv 2 of the previous tile has finished reading it (HE, a tcgen05.commit).
+    // h = lrelu(D1 + b1) in the operand type, zero outside the utterance, into the c2 operand tile.  These warps run
+    // ahead of epilogue 2: tile i+1's h is written while tile i's residual add is still streaming to HBM.  The h tile is
+    // free by then: D1 of tile i+1 being complete implies conv 2 of tile i (issued earlier) has finished reading it.
     const int q = warp & 3;
     const int n = q * 32 + lane;
-    const int odd = lane & 1;
     const float bias_h = a.bias_h[n], slope_h = a.slope_h;
-    // word address of this lane pair inside a row: k-block q>>1, channel pair ((q & 1) * 32 + lane) & ~1
-    const uint32_t chp = (uint32_t)(((q & 1) * 32 + lane) & ~1);
-    const uint32_t h_lane = smem_u32(smH) + (uint32_t)(q >> 1) * (PAIR_H_ROWS * TC_ROW_BYTES) + (chp & 7u) * 2u;
-    const uint32_t chq = chp >> 3;  // 16-byte chunk of the row before swizzling
-    for (int it = 0; it < n_my; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const int t_d1 = (tile % rt.t_tiles) * n_out - h2;   // time step of D1 column 0
-      const int d1 = it & 1;
-      long long* dbg = (rt.dbg && blockIdx.x == 0 && q == 0 && lane == 0 && it < 16) ? rt.dbg + it * 8 : nullptr;
-      mbar_wait(BAR(iD1F + d1), (uint32_t)(it >> 1) & 1u);
-      if (it > 0) mbar_wait(BAR(iHE), (uint32_t)(it - 1) & 1u);
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t chl = (uint32_t)((q & 1) * 32 + lane);   // channel inside k-block q>>1
+    const uint32_t h_thread = smem_u32(smH) + (uint32_t)(q >> 1) * (PAIR_N1 * TC_ROW_BYTES) + (chl & 7u) * 2u;
+    const uint32_t chq = chl >> 3;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < rt.total_tiles; tile += gridDim.x) {
+      const int t0 = (tile % rt.t_tiles) * PAIR_N;
+      long long* dbg = (rt.dbg && blockIdx.x == 0 && q == 0 && lane == 0 && tile / (int)gridDim.x < 16) ? rt.dbg + (tile / gridDim.x) * 8 : nullptr;
+      mbar_wait(BAR(iD1F), ph);
       tc_fence_after();
       if (dbg) dbg[4] = clock64();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(d1 * PAIR_COLS);
+      // two TMEM loads in flight: chunk c+32 is fetched while chunk c is converted and stored
       float accA[32], accB[32];
       tmem_ld32(taddr, accA);
-      auto emit = [&](float* acc, int c) {
+      auto emit = [&](const float* acc, int c) {
+        const int t_abs0 = t0 - PAIR_HALO + c;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           float v = acc[i] + bias_h;
           v = fmaxf(v, v * slope_h);
-          const int t_abs = t_d1 + c + i;
-          acc[i] = (t_abs < 0 || t_abs >= a.L_out) ? 0.f : v;
-        }
-        uint32_t w[16];
-        pair_words<T>(acc, odd, w);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          // row c + 2i + odd; c is a multiple of 32, so (row & 7) = (2i + odd) & 7
-          const uint32_t row = (uint32_t)(c + 2 * i) + (uint32_t)odd;
-          const uint32_t addr = h_lane + row * TC_ROW_BYTES + ((chq ^ (row & 7u)) << 4);
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(w[i]) : "memory");
+          const int t_abs = t_abs0 + i;
+          if (t_abs < 0 || t_abs >= a.L_out) v = 0.f;
+          const uint32_t addr = h_thread + (uint32_t)(c + i) * TC_ROW_BYTES + ((chq ^ (uint32_t)(i & 7)) << 4);
+          unsigned short bits;
+          if constexpr (Op::kPrec == 3) bits = __half_as_ushort(to_half_sat(v));
+          else bits = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+          if (c + i < PAIR_N1) asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(bits) : "memory");
         }
       };
 #pragma unroll 1
-      for (int c = 0; c < PAIR_COLS; c += 64) {
+      for (int c = 0; c < PAIR_N1; c += 64) {
         tmem_ld_wait();
-        tmem_ld32(taddr + (uint32_t)(c + 32), accB);
+        if (c + 32 < PAIR_N1) tmem_ld32(taddr + (uint32_t)(c + 32), accB);
         emit(accA, c);
-        tmem_ld_wait();
-        if (c + 64 < PAIR_COLS) tmem_ld32(taddr + (uint32_t)(c + 64), accA);
-        emit(accB, c + 32);
+        if (c + 32 < PAIR_N1) {
+          tmem_ld_wait();
+          if (c + 64 < PAIR_N1) tmem_ld32(taddr + (uint32_t)(c + 64), accA);
+          emit(accB, c + 32);
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core's async-proxy reads
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(BAR(iD1E + d1)); mbar_arrive(BAR(iHF)); }
+      if (lane == 0) mbar_arrive(BAR(iHR));
       if (dbg) dbg[5] = clock64();
+      ph ^= 1;
     }
   } else if (warp < NEPI2) {
     // ===================== epilogue-2 warps (8): the ResBlock residual add on D2 =====================
     const int q = warp & 3, grp = warp >> 2;
     const int n = q * 32 + lane;
-    const int odd = lane & 1;
-    for (int it = 0; it < n_my; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + PAIR_D2_COL0;
+    uint32_t ph = 0;
+    int d2 = 0;
+    float xcur[32];
+    for (int tile = blockIdx.x; tile < rt.total_tiles; tile += gridDim.x) {
       const int tt = tile % rt.t_tiles, b = tile / rt.t_tiles;
-      const int t0 = tt * n_out;
-      const int t_lim = min(a.L_out, t0 + n_out);
-      const int d2 = it & 1;
-      long long* dbg = (rt.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && it < 16) ? rt.dbg + it * 8 : nullptr;
+      const int t0 = tt * PAIR_N;
+      const int t_lim = min(a.L_out, t0 + PAIR_N);
+      long long* dbg = (rt.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && tile / (int)gridDim.x < 16) ? rt.dbg + (tile / gridDim.x) * 8 : nullptr;
       {  // ask L2 for the residual rows of this warp's chunks of the NEXT tile (demand loads then hit L2)
         const int tile_n = tile + (int)gridDim.x;
-        if (tile_n < rt.total_tiles) {
-          const int bn = tile_n / rt.t_tiles, t0n = (tile_n % rt.t_tiles) * n_out;
-          for (int c = grp * 32; c < n_out; c += 64) {
+        if (tile_n < rt.total_tiles && a.epi.xin != nullptr) {
+          const int bn = tile_n / rt.t_tiles, t0n = (tile_n % rt.t_tiles) * PAIR_N;
+          for (int c = grp * 32; c < PAIR_N; c += 64) {
             const int t = t0n + c + lane;
-            if (c + lane < n_out && t < a.L_out) {
-              const size_t off = ((size_t)bn * a.epi.rows_res + t) * TC_M + (n - lane);
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(a.epi.xin) + off * 2));
+            if (t < a.L_out) {
+              const size_t off = ((size_t)bn * a.epi.rows_res + t) * a.epi.ld + (n - lane);
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(a.epi.xin) + off * (RH != 0 ? 2 : 4)));
             }
           }
         }
       }
-      mbar_wait(BAR(iD2F + d2), (uint32_t)(it >> 1) & 1u);
+      mbar_wait(BAR(iD2F + d2), ph);
       tc_fence_after();
       if (dbg) dbg[6] = clock64();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * PAIR_COLS + d2 * PAIR_COLS);
-      for (int c = grp * 32; c < n_out; c += 64) {
+      for (int c = grp * 32; c < PAIR_N; c += 64) {
         float acc[32];
-        uint32_t xw[16];
-        tmem_ld32(taddr + (uint32_t)c, acc);
+        tmem_ld32(taddr + (uint32_t)(d2 * PAIR_D2_STRIDE + c), acc);
         const int t_first = t0 + c;
-        const int nt = min(min(t_lim - t_first, n_out - c), 32);
-        const size_t xoff = ((size_t)b * a.epi.rows_res + t_first) * TC_M + (n & ~1);
-        if (nt == 32) pair_load_rows<true>(a.epi.xin, xoff, odd, nt, xw);
-        else pair_load_rows<false>(a.epi.xin, xoff, odd, nt > 0 ? nt : 0, xw);
+        const bool live = t_first < t_lim;
+        if (live) epi_prefetch<EPI_RES, LD, RH>(a.epi, b, n, t_first, min(t_lim - t_first, 32), xcur);
         tmem_ld_wait();
-        // (all 32 lanes take part in the shuffles even when the chunk is partly or wholly outside the utterance)
-        if (nt == 32) pair_epi_res<Op, RH, true>(a.epi, b, n, t_first, nt, acc, xw);
-        else pair_epi_res<Op, RH, false>(a.epi, b, n, t_first, nt > 0 ? nt : 0, acc, xw);
+        if (live) tc_epilogue32<Op, EPI_RES, LD, RH>(a.epi, b, n, 0, t_first, min(t_lim - t_first, 32), acc, nullptr, xcur);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(iD2E + d2));
       if (dbg) dbg[7] = clock64();
+      if (++d2 == 2) { d2 = 0; ph ^= 1; }
     }
   }
   tc_fence_before();
@@ -1424,6 +1290,7 @@ static cudaError_t launch_one_cl(const ConvArgs& a, const TcPlan& p, const TcRt&
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = rt.pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (rt.cluster) {
@@ -1541,7 +1408,7 @@ static void timeline_dump(const ConvArgs& a, const TcPlan& p, long long* dbg, cu
   cudaMemset(dbg, 0, 148 * 7 * 64 * sizeof(long long));
 }
 
-cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStream_t st) {
+cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStream_t st, int pdl) {
   static long long* dbg = nullptr;
   static int dbg_mode = -2;
   if (dbg_mode == -2) {
@@ -1550,6 +1417,7 @@ cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStr
     if (dbg_mode >= 0) { cudaMalloc(&dbg, 148 * 7 * 64 * sizeof(long long)); cudaMemset(dbg, 0, 148 * 7 * 64 * sizeof(long long)); }
   }
   TcRt rt;
+  rt.pdl = pdl;
   rt.dbg = (dbg_mode >= 0 && a.epi.mode == dbg_mode) ? dbg : nullptr;
   rt.n_time = p.n_time; rt.slab_rows = p.slab_rows; rt.box_rows = p.box_rows; rt.n_boxes = p.n_boxes;
   rt.slab_stage_bytes = p.slab_stage_bytes; rt.w_stage_bytes = p.w_stage_bytes;
@@ -1594,15 +1462,14 @@ const char* tc_make_pair_plan(int prec, const ConvArgs& a, int num_sms, TcPairPl
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return "cuTensorMapEncodeTiled entry point unavailable";
   if (prec < 2) return "conv pair: 16-bit operand types only";
-  if (a.Cp_in != 128 || a.N_total != 128 || a.n_phases != 1 || a.epi.ld != 128) return "conv pair: 128 channels, stride 1 only";
-  if ((a.taps & 1) == 0 || a.taps > 17) return "conv pair: odd kernel size <= 17";
-  if (!((prec == 2 && a.epi.res_half == 1) || (prec == 3 && a.epi.res_half == 2))) return "conv pair: 16-bit residual streams only";
-  plan->n_out = PAIR_COLS - (a.taps - 1);
-  const int slab_rows = PAIR_COLS + (a.taps - 1) * a.dil;
-  plan->box_rows = (slab_rows + 7) / 8 * 8;
-  if (plan->box_rows > 256) return "conv pair: activation slab exceeds one 256-row TMA box";
-  plan->slab_stage_bytes = ((plan->box_rows * TC_ROW_BYTES + 1023) / 1024) * 1024;
-  plan->n_slab_stages = 3;
+  if (a.Cp_in != 128 || a.N_total != 128 || a.n_phases != 1) return "conv pair: 128 channels, stride 1 only";
+  if ((a.taps - 1) / 2 > PAIR_HALO || (a.taps & 1) == 0) return "conv pair: odd kernel size <= 17";
+  const int slab_rows = PAIR_N1 + (a.taps - 1) * a.dil;
+  plan->n_boxes = slab_rows > 256 ? 2 : 1;
+  plan->box_rows = ((slab_rows + plan->n_boxes - 1) / plan->n_boxes + 7) / 8 * 8;
+  if (plan->box_rows > 256) return "conv pair: activation slab exceeds two 256-row TMA boxes";
+  plan->slab_stage_bytes = ((plan->n_boxes * plan->box_rows * TC_ROW_BYTES + 1023) / 1024) * 1024;
+  plan->n_slab_stages = 2;
   plan->h_off = plan->n_slab_stages * plan->slab_stage_bytes;
   plan->w_off = plan->h_off + PAIR_H_BYTES;
   const int budget = 225 * 1024 - plan->w_off;
@@ -1610,9 +1477,9 @@ const char* tc_make_pair_plan(int prec, const ConvArgs& a, int num_sms, TcPairPl
   if (plan->n_w_stages > 10) plan->n_w_stages = 10;
   if (plan->n_w_stages < 3) return "conv pair: not enough shared memory for the weight ring";
   plan->bar_off = plan->w_off + plan->n_w_stages * TC_M * TC_ROW_BYTES;
-  const int nbars = 2 * plan->n_slab_stages + 2 * plan->n_w_stages + 10;
+  const int nbars = 2 * plan->n_slab_stages + 2 * plan->n_w_stages + 6;
   plan->smem_bytes = 1024 + plan->bar_off + nbars * 8 + 16;
-  plan->t_tiles = (a.L_out + plan->n_out - 1) / plan->n_out;
+  plan->t_tiles = (a.L_out + PAIR_N - 1) / PAIR_N;
   plan->total_tiles = a.B * plan->t_tiles;
   plan->grid = plan->total_tiles < num_sms ? plan->total_tiles : num_sms;
   const CUtensorMapDataType dt = prec == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -1638,27 +1505,28 @@ const char* tc_make_pair_plan(int prec, const ConvArgs& a, int num_sms, TcPairPl
   return nullptr;
 }
 
-template <typename Op, int RH>
+template <typename Op, int LD, int RH>
 static cudaError_t launch_pair_one(const ConvArgs& a, const TcPairPlan& p, const PairRt& rt, cudaStream_t st, bool set_attr) {
-  auto k = conv_pair_kernel<Op, RH>;
+  auto k = conv_pair_kernel<Op, LD, RH>;
   if (set_attr) return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p.grid);
-  cfg.blockDim = dim3(PAIR_THREADS);
+  cfg.blockDim = dim3(TcThreads<EPI_RES>::value);
   cfg.dynamicSmemBytes = p.smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = rt.pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, k, p.tmA, p.tmB, p.tmB2, a, rt);
 }
 
 static cudaError_t pair_dispatch(int prec, const ConvArgs& a, const TcPairPlan& p, const PairRt& rt, cudaStream_t st, bool set_attr) {
-  const int rh = a.epi.res_half;
-  if (prec == 2 && rh == 1) return launch_pair_one<OpBF16, 1>(a, p, rt, st, set_attr);
-  if (prec == 3 && rh == 2) return launch_pair_one<OpF16, 2>(a, p, rt, st, set_attr);
+  const int ld = a.epi.ld, rh = a.epi.res_half;
+  if (prec == 2 && rh == 1) return ld == 128 ? launch_pair_one<OpBF16, 128, 1>(a, p, rt, st, set_attr) : launch_pair_one<OpBF16, 0, 1>(a, p, rt, st, set_attr);
+  if (prec == 2 && rh == 0) return launch_pair_one<OpBF16, 0, 0>(a, p, rt, st, set_attr);
+  if (prec == 3 && rh == 2) return ld == 128 ? launch_pair_one<OpF16, 128, 2>(a, p, rt, st, set_attr) : launch_pair_one<OpF16, 0, 2>(a, p, rt, st, set_attr);
   return cudaErrorInvalidValue;
 }
 
@@ -1666,20 +1534,21 @@ cudaError_t tc_pair_set_attributes() {
   ConvArgs a{};
   TcPairPlan p{};
   PairRt rt{};
-  const int combos[2][2] = {{2, 1}, {3, 2}};
+  const int combos[5][3] = {{2, 128, 1}, {2, 0, 1}, {2, 0, 0}, {3, 128, 2}, {3, 0, 2}};
   for (auto& c : combos) {
-    a.epi.res_half = c[1];
+    a.epi.ld = c[1];
+    a.epi.res_half = c[2];
     cudaError_t e = pair_dispatch(c[0], a, p, rt, nullptr, true);
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
 }
 
-cudaError_t launch_conv_pair(int prec, const ConvArgs& a, const TcPairPlan& p, cudaStream_t st) {
+cudaError_t launch_conv_pair(int prec, const ConvArgs& a, const TcPairPlan& p, cudaStream_t st, int pdl) {
   PairRt rt;
-  rt.box_rows = p.box_rows; rt.slab_stage_bytes = p.slab_stage_bytes;
-  rt.n_slab_stages = p.n_slab_stages; rt.n_w_stages = p.n_w_stages; rt.n_out = p.n_out; rt.t_tiles = p.t_tiles;
-  rt.total_tiles = p.total_tiles;
+  rt.pdl = pdl;
+  rt.box_rows = p.box_rows; rt.n_boxes = p.n_boxes; rt.slab_stage_bytes = p.slab_stage_bytes;
+  rt.n_slab_stages = p.n_slab_stages; rt.n_w_stages = p.n_w_stages; rt.t_tiles = p.t_tiles; rt.total_tiles = p.total_tiles;
   rt.h_off = p.h_off; rt.w_off = p.w_off; rt.bar_off = p.bar_off;
   static long long* dbg = nullptr;
   static int dbg_on = -1;
@@ -1694,10 +1563,10 @@ cudaError_t launch_conv_pair(int prec, const ConvArgs& a, const TcPairPlan& p, c
     cudaStreamSynchronize(st);
     long long hb[16 * 8];
     cudaMemcpy(hb, dbg, sizeof(hb), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[pair timeline] k%d d%d slab rows %d (x%d stages) w_stages %d n_out %d tiles/CTA %d\n", a.taps, a.dil, p.box_rows,
-            p.n_slab_stages, p.n_w_stages, p.n_out, (p.total_tiles + p.grid - 1) / p.grid);
+    fprintf(stderr, "[pair timeline] k%d d%d slab_rows/box %d x%d w_stages %d tiles/CTA %d\n", a.taps, a.dil, p.box_rows, p.n_boxes,
+            p.n_w_stages, (p.total_tiles + p.grid - 1) / p.grid);
     const long long t0 = hb[0];
-    for (int i = 0; i < 10; ++i)
+    for (int i = 0; i < 8; ++i)
       fprintf(stderr, "  tile %2d  mma1 %7lld..%7lld | mma2 %7lld..%7lld | epi1 %7lld..%7lld | epi2 %7lld..%7lld\n", i, hb[8 * i] - t0,
               hb[8 * i + 1] - t0, hb[8 * i + 2] - t0, hb[8 * i + 3] - t0, hb[8 * i + 4] - t0, hb[8 * i + 5] - t0, hb[8 * i + 6] - t0,
               hb[8 * i + 7] - t0);

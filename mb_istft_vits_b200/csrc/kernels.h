@@ -28,16 +28,16 @@ struct TcPlan {
 };
 // Fills plan (tensor maps, staging, grid) for args; returns a message on failure, nullptr on success.
 const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, TcPlan* plan);
-cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& plan, cudaStream_t st);
+cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& plan, cudaStream_t st, int pdl = 1);
 cudaError_t tc_set_attributes();
 // fused ResBlock1 conv pair (c1 -> lrelu -> c2 -> residual add), 128-channel stages: see conv_tc.cu
 struct TcPairPlan {
   CUtensorMap tmA, tmB, tmB2;   // activations, c1 weights, c2 weights
-  int box_rows, slab_stage_bytes, n_slab_stages, n_w_stages;
-  int n_out, t_tiles, total_tiles, h_off, w_off, bar_off, smem_bytes, grid;
+  int box_rows, n_boxes, slab_stage_bytes, n_slab_stages, n_w_stages;
+  int t_tiles, total_tiles, h_off, w_off, bar_off, smem_bytes, grid;
 };
 const char* tc_make_pair_plan(int prec, const ConvArgs& a, int num_sms, TcPairPlan* plan);
-cudaError_t launch_conv_pair(int prec, const ConvArgs& a, const TcPairPlan& plan, cudaStream_t st);
+cudaError_t launch_conv_pair(int prec, const ConvArgs& a, const TcPairPlan& plan, cudaStream_t st, int pdl = 1);
 cudaError_t tc_pair_set_attributes();
 // cuTensorMapEncodeTiled through the runtime's driver entry point (nullptr if unavailable); shared with tail.cu
 void* tc_tensormap_encoder();
@@ -67,6 +67,10 @@ cudaError_t launch_unpack_output(const float* src, float* dst, int B, int C, int
 // out[b][n] = bias[n] + sum_c w[n][c] * g[b][c]  (+ base[n] if given); w is [N][G] fp32
 cudaError_t launch_cond_gemv(const float* g, const float* w, const float* bias, const float* base, float* out,
                              int B, int G, int N, int out_ld, cudaStream_t st);
+
+// z = (m + noise * exp(logs)) * mask with stats = [m | logs] [B][2C][T], everything NCT (models.py:243-245)
+cudaError_t launch_posterior_sample(const float* stats, const float* noise, const float* mask, float* z, int B, int C, int T,
+                                    cudaStream_t st);
 
 // per-utterance peak normalise (x0.9 if peak > 0.01), clip, x32767, truncate to int16 (tts_vits.py:204-216)
 cudaError_t launch_pcm16(const float* wav, const int* n_valid, int B, int stride, int auto_normalize, unsigned int* peak_bits,

@@ -136,6 +136,9 @@ struct mbv_handle {
     if (B != o.B) return B < o.B; if (T != o.T) return T < o.T; if (ws != o.ws) return ws < o.ws; return kind < o.kind; } };
   std::map<PlanKey, std::vector<TcPlan>> plan_cache;
   std::map<PlanKey, std::vector<TcPairPlan>> pair_cache;
+  int use_branches = 0;  // the parallel ResBlocks of a stage run on separate streams (run_decode)
+  cudaStream_t br_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   int use_pair = 0;  // fused ResBlock conv pairs on 128-channel stages (conv_pair_kernel)
   int pair_max_taps = 17;
 
@@ -534,6 +537,16 @@ extern "C" int mbv_create(const mbv_config* cfg, mbv_handle** out) {
   if (prop.major != 10) return fail(h, MBV_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", c.device, prop.major, prop.minor);
   if (h->prec != MBV_PREC_FP32) CUDA_TRY(h, tc_set_attributes());
   if (h->prec >= MBV_PREC_BF16) CUDA_TRY(h, tc_pair_set_attributes());
+  h->use_branches = (c.flags & MBV_FLAG_BRANCHES) ? 1 : 0;
+  if (h->use_branches && h->prec != MBV_PREC_FP32) {
+    for (int i = 0; i < 2; ++i) {
+      CUDA_TRY(h, cudaStreamCreateWithFlags(&h->br_stream[i], cudaStreamNonBlocking));
+      CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  } else {
+    h->use_branches = 0;
+  }
   h->use_pair = (c.flags & MBV_FLAG_FUSED_PAIR) ? 1 : 0;
   if (const char* e = getenv("MBV_PAIR_MAX_TAPS")) h->pair_max_taps = atoi(e);  // A/B measurements only
   return MBV_OK;
@@ -544,6 +557,11 @@ extern "C" void mbv_destroy(mbv_handle* h) {
   for (void* p : h->dev_allocs) cudaFree(p);
   for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) {
+    if (h->br_stream[i]) cudaStreamDestroy(h->br_stream[i]);
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   delete h;
 }
 
@@ -705,7 +723,7 @@ struct Arena {
 
 struct DecBufs {
   void* zin_op; void* pre_act;
-  struct Stage { void* x; void* a[3]; void* xr; void* ar; void* hop; void* xs; void* next; } st[MBV_MAX_UPS];
+  struct Stage { void* x; void* a[3]; void* xr[3]; void* ar[3]; void* hop[3]; void* xs; void* next; } st[MBV_MAX_UPS];
   float* logits;
   float* cond;  // [n_stage][n_kernels][2][B][C]: (cond, bias2+cond) per resblock
 };
@@ -726,9 +744,12 @@ void layout_dec(mbv_handle* h, Arena& A, int B, int T, DecBufs* d) {
     s.x = A.take(n * h->rsize);
     const int na = h->cfg.gin_channels ? h->cfg.n_kernels : 1;
     for (int j = 0; j < 3; ++j) s.a[j] = j < na ? A.take(n * es) : nullptr;
-    s.xr = A.take(n * h->rsize);
-    s.ar = A.take(n * es);
-    s.hop = A.take(n * es);
+    const int nb = (h->use_branches && h->cfg.n_kernels > 1) ? h->cfg.n_kernels : 1;  // one buffer set per ResBlock branch
+    for (int j = 0; j < 3; ++j) {
+      s.xr[j] = j < nb ? A.take(n * h->rsize) : nullptr;
+      s.ar[j] = j < nb ? A.take(n * es) : nullptr;
+      s.hop[j] = j < nb ? A.take(n * es) : nullptr;
+    }
     s.xs = A.take(n * h->rsize);
     const bool last = (i == h->n_stage - 1);
     s.next = A.take((size_t)B * (L + (last ? 1 : 0)) * C * es);
@@ -757,6 +778,7 @@ struct Ctx {
   bool plans_valid;
   size_t plan_idx = 0, pair_idx = 0;
   int launches = 0;
+  bool pdl = true;   // launch convs with programmatic stream serialization (off inside ResBlock branches)
 };
 
 // RAII bracket: two events around one launch when profiling is on
@@ -804,7 +826,7 @@ int run_conv(Ctx& cx, const ConvLayer& L, const void* x, int B, int L_in, int L_
     snprintf(desc, sizeof(desc), "conv m%d Ci%d N%d k%d d%d ph%d L%d nt%d", epi.mode, L.Cp_in, L.N_total, L.taps, L.dil,
              L.n_phases, L_out, plan.n_time);
     ProfScope prof(cx, 0, h->profiling ? desc : "");
-    CUDA_TRY(h, launch_conv_tc(h->prec, a, plan, cx.st));
+    CUDA_TRY(h, launch_conv_tc(h->prec, a, plan, cx.st, cx.pdl ? 1 : 0));
   }
   cx.launches++;
   return MBV_OK;
@@ -812,8 +834,8 @@ int run_conv(Ctx& cx, const ConvLayer& L, const void* x, int B, int L_in, int L_
 
 // fused ResBlock1 conv pair: x' = xin + c2(lrelu(c1(a_in))) (conv_pair_kernel); epi is c2's RES epilogue
 bool pair_ok(const mbv_handle* h, const ConvLayer& c1, const ConvLayer& c2) {
-  return h->use_pair && h->prec >= MBV_PREC_BF16 && h->res_half && !(h->cfg.flags & MBV_FLAG_FORCE_SIMT) && c1.Cp_in == 128 &&
-         c1.N_total == 128 && c2.Cp_in == 128 && c2.N_total == 128 && c1.taps == c2.taps && c2.dil == 1 && (c1.taps & 1) &&
+  return h->use_pair && h->prec >= MBV_PREC_BF16 && !(h->cfg.flags & MBV_FLAG_FORCE_SIMT) && c1.Cp_in == 128 && c1.N_total == 128 &&
+         c2.Cp_in == 128 && c2.N_total == 128 && c1.taps == c2.taps && c2.dil == 1 && (c1.taps & 1) && (c1.taps - 1) / 2 <= 8 &&
          c1.taps <= h->pair_max_taps && c1.n_phases == 1 && c2.n_phases == 1;
 }
 
@@ -837,9 +859,9 @@ int run_pair(Ctx& cx, const ConvLayer& c1, const ConvLayer& c2, const void* x, i
   }
   cx.pair_idx++;
   char desc[56];
-  snprintf(desc, sizeof(desc), "pair m1 Ci%d N%d k%d d%d ph1 L%d nt%d", c1.Cp_in, c1.N_total, c1.taps, c1.dil, L, plan.n_out);
+  snprintf(desc, sizeof(desc), "pair m1 Ci%d N%d k%d d%d ph1 L%d nt160", c1.Cp_in, c1.N_total, c1.taps, c1.dil, L);
   ProfScope prof(cx, 0, h->profiling ? desc : "");
-  CUDA_TRY(h, launch_conv_pair(h->prec, a, plan, cx.st));
+  CUDA_TRY(h, launch_conv_pair(h->prec, a, plan, cx.st, cx.pdl ? 1 : 0));
   cx.launches++;
   return MBV_OK;
 }
@@ -852,6 +874,37 @@ EpiParams epi_base(int mode, int ld, int rows) {
   e.mode = mode; e.ld = ld; e.rows_out = rows; e.rows_res = rows; e.row_mul = 1; e.row_add = 0;
   e.dup_src = -1; e.dup_dst = 0; e.slope = 1.f; e.scale = 1.f; e.n_valid = ld; e.post_sign = 1.f;
   return e;
+}
+
+// modules.WN.forward (modules.py:148-176) on h (fp32 / fp16 stream `hres` + operand copy `hop`): per layer the gate conv
+// writes acts_l = tanh(.) * sigmoid(.) into slot l of the gate-output buffer `acts` [B][T][NL*Hp] and, for l < NL-1, the
+// residual 1x1 conv updates h = (h + res_l(acts_l)) * mask.  The skip path is applied by the caller's fused projection
+// over `acts` (pack_wn).  gc: per-utterance cond_layer(g) rows [B][NL*2Hp] in the packed gate row order, or null.
+int run_wn(Ctx& cx, const ConvLayer* in_layers, const ConvLayer* rs_layers, int NL, float* hres, void* hop, void* acts,
+           const float* mask, const float* gc, int B, int T) {
+  mbv_handle* h = cx.h;
+  const int Hp = h->Hp;
+  const bool tc_path = h->prec >= MBV_PREC_BF16 && !(h->cfg.flags & MBV_FLAG_FORCE_SIMT);  // (the CUDA-core epilogues keep h in fp32)
+  const int Ha = NL * Hp;  // channel pitch of the gate-output buffer: one Hp-wide slot per WN layer
+  int rc;
+  for (int l = 0; l < NL; ++l) {
+    {  // acts_l = tanh(.) * sigmoid(.) of in_layer_l(h) [+ cond_l(g)]
+      EpiParams e = epi_base(EPI_GATE, Ha, T);
+      e.n_valid = Hp; e.ch_off = l * Hp;
+      e.act[0] = acts; e.n_act = 1;
+      if (gc) { e.add2 = gc + (size_t)l * 2 * Hp; e.add2_bs = NL * 2 * Hp; }
+      if ((rc = run_conv(cx, in_layers[l], hop, B, T, T, e))) return rc;
+    }
+    if (l < NL - 1) {  // h = (h + res_l(acts_l)) * mask; the skip halves are applied by the fused projection
+      EpiParams e = epi_base(EPI_RS, Hp, T);
+      e.mask = mask; e.n_split = rs_layers[l].N_total; e.xin = hres; e.xout = hres; e.act[0] = hop; e.n_act = 1;
+      if (h->single) { e.xin = hop; e.xout = nullptr; e.res_half = 2; e.inv_slope = 1.f; }
+      else if (h->res_half && tc_path) e.res_half = 1;
+      const char* ax = (const char*)acts + (size_t)l * Hp * h->esize;
+      if ((rc = run_conv(cx, rs_layers[l], ax, B, T, T, e, Ha))) return rc;
+    }
+  }
+  return MBV_OK;
 }
 
 // forward = false: ResidualCouplingBlock.forward(reverse=True) (inference); true: the forward direction (voice conversion).
@@ -884,24 +937,7 @@ int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, co
       if (!h->single && h->res_half && tc_path) e.res_half = 1;  // bf16 + fp16 streams: h is carried in fp16 next to its bf16 operand copy
       if ((rc = run_conv(cx, h->fl_pre[f_i], f.zop, B, T, T, e))) return rc;
     }
-    const int Ha = NL * Hp;  // channel pitch of the gate-output buffer: one Hp-wide slot per WN layer
-    for (int l = 0; l < NL; ++l) {
-      {  // acts_l = tanh(.) * sigmoid(.) of in_layer_l(h) [+ cond_l(g)]
-        EpiParams e = epi_base(EPI_GATE, Ha, T);
-        e.n_valid = Hp; e.ch_off = l * Hp;
-        e.act[0] = f.acts; e.n_act = 1;
-        if (gc) { e.add2 = gc + (size_t)l * 2 * Hp; e.add2_bs = NL * 2 * Hp; }
-        if ((rc = run_conv(cx, h->fl_in[f_i][l], f.hop, B, T, T, e))) return rc;
-      }
-      if (l < NL - 1) {  // h = (h + res_l(acts_l)) * mask; the skip halves are applied by the fused post conv below
-        EpiParams e = epi_base(EPI_RS, Hp, T);
-        e.mask = mask; e.n_split = h->fl_rs[f_i][l].N_total; e.xin = f.h; e.xout = f.h; e.act[0] = f.hop; e.n_act = 1;
-        if (h->single) { e.xin = f.hop; e.xout = nullptr; e.res_half = 2; e.inv_slope = 1.f; }
-        else if (h->res_half && tc_path) e.res_half = 1;
-        const char* ax = (const char*)f.acts + (size_t)l * Hp * h->esize;
-        if ((rc = run_conv(cx, h->fl_rs[f_i][l], ax, B, T, T, e, Ha))) return rc;
-      }
-    }
+    if ((rc = run_wn(cx, h->fl_in[f_i], h->fl_rs[f_i], NL, f.h, f.hop, f.acts, mask, gc, B, T))) return rc;
     {  // x1 = (x1 - m * mask) * mask,  m = post(sum_l skip_l) as one conv over all gate outputs
       EpiParams e = epi_base(EPI_POST, h->Cz, T);
       e.mask = mask; e.xin = f.z; e.xout = f.z; e.act[0] = f.zop; e.n_act = 1;
@@ -915,6 +951,60 @@ int run_flow(Ctx& cx, const FlowBufs& f, const float* z_p, const float* mask, co
     ProfScope prof(cx, 2);
     CUDA_TRY(h, launch_unpack_output(f.z, z_out, B, h->Cz, T, h->Cz, cx.st));
     cx.launches++;
+  }
+  return MBV_OK;
+}
+
+struct PostBufs { void* spec_op; float* h; void* hop; void* acts; float* gcond; float* stats; };
+
+void layout_posterior(mbv_handle* h, Arena& A, int B, int T, PostBufs* p) {
+  const int es = h->esize, NL = h->eq_layers;
+  const size_t nh = (size_t)B * T * h->Hp;
+  p->spec_op = A.take((size_t)B * T * h->eq_spec_p * es);
+  p->h = (float*)A.take(nh * 4);
+  p->hop = A.take(nh * es);
+  p->acts = A.take(nh * NL * es);
+  p->gcond = (float*)A.take((size_t)B * NL * 2 * h->Hp * 4);
+  p->stats = (float*)A.take((size_t)B * T * 2 * h->Cz * 4);
+}
+
+// PosteriorEncoder.forward (models.py:236-246): x = pre(spec) * mask; x = WN(x, mask, g); stats = proj(x) * mask;
+// m, logs = split(stats); z = (m + noise * exp(logs)) * mask.  stats_out is [B, 2*inter, T] (m | logs), NCT like z.
+int run_posterior(Ctx& cx, const PostBufs& p, const float* spec, const float* mask, const float* g, const float* noise,
+                  float* z_out, float* stats_out, int B, int T) {
+  mbv_handle* h = cx.h;
+  const int Hp = h->Hp, NL = h->eq_layers;
+  const bool tc_path = h->prec >= MBV_PREC_BF16 && !(h->cfg.flags & MBV_FLAG_FORCE_SIMT);
+  int rc;
+  {
+    ProfScope prof(cx, 2);
+    CUDA_TRY(h, launch_pack_input(h->prec, spec, nullptr, p.spec_op, nullptr, B, h->eq_spec, T, h->eq_spec_p, cx.st));
+    cx.launches++;
+  }
+  float* gc = nullptr;
+  if (g) {
+    gc = p.gcond;
+    ProfScope prof(cx, 2);
+    CUDA_TRY(h, launch_cond_gemv(g, h->eq_cond_w, h->eq_cond_b, nullptr, gc, B, h->cfg.gin_channels, NL * 2 * Hp, NL * 2 * Hp, cx.st));
+    cx.launches++;
+  }
+  {  // x = pre(spec) * mask
+    EpiParams e = epi_base(EPI_ACT, Hp, T);
+    e.mask = mask; e.xout = h->single ? nullptr : p.h; e.act[0] = p.hop; e.n_act = 1;
+    if (!h->single && h->res_half && tc_path) e.res_half = 1;
+    if ((rc = run_conv(cx, h->eq_pre, p.spec_op, B, T, T, e))) return rc;
+  }
+  if ((rc = run_wn(cx, h->eq_in, h->eq_rs, NL, p.h, p.hop, p.acts, mask, gc, B, T))) return rc;
+  {  // stats = proj(sum_l skip_l) * mask as one conv over all gate outputs, fp32 channels-last
+    EpiParams e = epi_base(EPI_ACT, 2 * h->Cz, T);
+    e.mask = mask; e.xout = p.stats; e.n_act = 0;
+    if ((rc = run_conv(cx, h->eq_proj, p.acts, B, T, T, e))) return rc;
+  }
+  {
+    ProfScope prof(cx, 2);
+    CUDA_TRY(h, launch_unpack_output(p.stats, stats_out, B, 2 * h->Cz, T, 2 * h->Cz, cx.st));
+    CUDA_TRY(h, launch_posterior_sample(stats_out, noise, mask, z_out, B, h->Cz, T, cx.st));
+    cx.launches += 2;
   }
   return MBV_OK;
 }
@@ -985,11 +1075,27 @@ int run_decode(Ctx& cx, const DecBufs& d, const float* z, const float* z_mask, c
       e.act_add_bs = C;
       if ((rc = run_conv(cx, h->ups[i], cur, B, Lin, Lin, e))) return rc;
     }
-    for (int j = 0; j < nk; ++j) {
-      const void* a_in = g ? s.a[j] : s.a[0];
-      const void* x_in = s.x;
-      const int np = c.n_dilations;
-      for (int p = 0; p < np; ++p) {
+    // The nk parallel ResBlocks of a stage are independent until their outputs are summed (models.py:355-361).  With
+    // `branches` each runs on its own stream (its own residual / operand buffers): the persistent conv kernels own a whole
+    // SM per CTA, so kernels of different branches do not share SMs -- but the CTAs of the next kernel move onto SMs as
+    // soon as the CTAs of the running one retire, which hides every launch's fill / drain and partial last round behind
+    // another branch's work.  Only the LAST launch of each ResBlock (the one that folds x into the running sum xs) stays
+    // on the caller's stream, in ResBlock order.
+    const bool branches = h->use_branches && nk > 1 && nk <= 3 && !h->profiling && h->prec != MBV_PREC_FP32 &&
+                          !(c.flags & MBV_FLAG_FORCE_SIMT);
+    cudaStream_t main_st = cx.st;
+    const void* a_cur[3];
+    const void* x_cur[3];
+    const int np = c.n_dilations;
+    // phase 0: everything but the last launch of ResBlock j;  phase 1: that last launch
+    auto run_block = [&](int j, int phase) -> int {
+      const int bj = branches ? j : 0;  // buffer set
+      void* xr = s.xr[bj]; void* ar = s.ar[bj]; void* hop = s.hop[bj];
+      if (phase == 0) { a_cur[j] = g ? s.a[j] : s.a[0]; x_cur[j] = s.x; }
+      const void*& a_in = a_cur[j];
+      const void*& x_in = x_cur[j];
+      int rc2;
+      for (int p = (phase == 0 ? 0 : np - 1); p < np; ++p) {
         const bool final_conv = (p == np - 1);
         EpiParams e = epi_base(EPI_RES, C, L);
         e.xin = x_in; e.slope = 0.1f; e.res_half = h->res_half;
@@ -1004,34 +1110,61 @@ int run_decode(Ctx& cx, const DecBufs& d, const float* z, const float* z_mask, c
             if (last) { e.rows_out = L + 1; e.row_add = 1; e.dup_src = 2; e.dup_dst = 0; }
           }
         } else {
-          e.xout = h->single ? nullptr : s.xr;
+          e.xout = h->single ? nullptr : xr;
         }
-        const void* conv_in;
         if (c.resblock_type == 1 && pair_ok(h, h->rb_c1[i][j][p], h->rb_c2[i][j][p])) {
           // one launch for the conv pair; the operand copies ping-pong (c1 of a neighbouring tile still reads a_in's halo
           // rows while this tile's epilogue writes its output)
-          void* a_out = (p & 1) ? s.hop : s.ar;
+          if (final_conv && phase == 0) break;
+          void* a_out = (p & 1) ? hop : ar;
           if (!final_conv) { e.act[0] = a_out; e.n_act = 1; }
-          if ((rc = run_pair(cx, h->rb_c1[i][j][p], h->rb_c2[i][j][p], a_in, B, L, e, 0.1f))) return rc;
+          if ((rc2 = run_pair(cx, h->rb_c1[i][j][p], h->rb_c2[i][j][p], a_in, B, L, e, 0.1f))) return rc2;
           a_in = a_out;
         } else if (c.resblock_type == 1) {
-          EpiParams e1 = epi_base(EPI_ACT, C, L);
-          e1.slope = 0.1f; e1.act[0] = s.hop; e1.n_act = 1;
-          if ((rc = run_conv(cx, h->rb_c1[i][j][p], a_in, B, L, L, e1))) return rc;
-          conv_in = s.hop;
-          if (!final_conv) { e.act[0] = s.ar; e.n_act = 1; }
-          if ((rc = run_conv(cx, h->rb_c2[i][j][p], conv_in, B, L, L, e))) return rc;
-          a_in = s.ar;
+          if (!(final_conv && phase == 1)) {  // c1 of the last pair still belongs to the branch
+            EpiParams e1 = epi_base(EPI_ACT, C, L);
+            e1.slope = 0.1f; e1.act[0] = hop; e1.n_act = 1;
+            if ((rc2 = run_conv(cx, h->rb_c1[i][j][p], a_in, B, L, L, e1))) return rc2;
+          }
+          if (final_conv && phase == 0) break;
+          if (!final_conv) { e.act[0] = ar; e.n_act = 1; }
+          if ((rc2 = run_conv(cx, h->rb_c2[i][j][p], hop, B, L, L, e))) return rc2;
+          a_in = ar;
         } else {
           // ResBlock2: x = x + c_p(lrelu(x)); operand copies ping-pong between ar and hop
-          void* a_out = (p & 1) ? s.hop : s.ar;
+          if (final_conv && phase == 0) break;
+          void* a_out = (p & 1) ? hop : ar;
           if (!final_conv) { e.act[0] = a_out; e.n_act = 1; }
-          if ((rc = run_conv(cx, h->rb_c1[i][j][p], a_in, B, L, L, e))) return rc;
+          if ((rc2 = run_conv(cx, h->rb_c1[i][j][p], a_in, B, L, L, e))) return rc2;
           a_in = a_out;
         }
-        x_in = s.xr;
+        x_in = xr;
+      }
+      return MBV_OK;
+    };
+    if (branches) CUDA_TRY(h, cudaEventRecord(h->ev_fork, main_st));
+    static const int branch_pdl = getenv("MBV_BRANCH_PDL") ? atoi(getenv("MBV_BRANCH_PDL")) : 0;  // A/B measurements only
+    cx.pdl = !branches || branch_pdl;
+    if (!branches) {  // one buffer set: each ResBlock runs to completion before the next starts
+      for (int j = 0; j < nk; ++j)
+        for (int phase = 0; phase < 2; ++phase)
+          if ((rc = run_block(j, phase))) return rc;
+    } else {
+      for (int j = 0; j < nk; ++j) {
+        if (j > 0) {
+          cx.st = h->br_stream[j - 1];
+          CUDA_TRY(h, cudaStreamWaitEvent(cx.st, h->ev_fork, 0));
+        }
+        if ((rc = run_block(j, 0))) { cx.st = main_st; cx.pdl = true; return rc; }
+        if (j > 0) CUDA_TRY(h, cudaEventRecord(h->ev_join[j - 1], cx.st));
+        cx.st = main_st;
+      }
+      for (int j = 0; j < nk; ++j) {
+        if (j > 0) CUDA_TRY(h, cudaStreamWaitEvent(main_st, h->ev_join[j - 1], 0));
+        if ((rc = run_block(j, 1))) { cx.pdl = true; return rc; }
       }
     }
+    cx.pdl = true;
     cur = s.next;
   }
   {  // conv_post on the reflect-padded L+1 frames -> fp32 logits, pitch n_logit
@@ -1065,7 +1198,8 @@ Ctx make_ctx(mbv_handle* h, int B, int T, void* ws, int kind, void* stream) {
   Ctx cx;
   cx.h = h;
   cx.st = (cudaStream_t)stream;
-  mbv_handle::PlanKey key{B, T, ws, kind};
+  // (cached tensor maps bake in buffer addresses: the branch layout uses other ResBlock buffers than the sequential one)
+  mbv_handle::PlanKey key{B, T, ws, kind + ((h->use_branches && !h->profiling) ? 16 : 0)};
   auto it = h->plan_cache.find(key);
   if (it == h->plan_cache.end()) {
     if (h->plan_cache.size() > 64) { h->plan_cache.clear(); h->pair_cache.clear(); }
@@ -1185,6 +1319,39 @@ extern "C" int mbv_flow_decode(mbv_handle* h, const float* z_p, const float* y_m
   return MBV_OK;
 }
 
+extern "C" int mbv_posterior_workspace_bytes(mbv_handle* h, int32_t B, int32_t T, size_t* bytes) {
+  if (!h || !bytes) return MBV_ERR_INVALID;
+  if (!h->has_enc_q) return fail(h, MBV_ERR_WEIGHTS, "no enc_q.* weights were loaded");
+  if (B < 1 || T < 1) return fail(h, MBV_ERR_INVALID, "B and T must be >= 1");
+  Arena A(nullptr);
+  PostBufs p;
+  layout_posterior(h, A, B, T, &p);
+  *bytes = A.off + 1024;
+  return MBV_OK;
+}
+
+extern "C" int mbv_posterior_encode(mbv_handle* h, const float* spec, const float* y_mask, const float* g, const float* noise,
+                                    float* z, float* stats, int32_t B, int32_t T, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_ready(h, B, T);
+  if (rc) return rc;
+  if (!h->has_enc_q) return fail(h, MBV_ERR_WEIGHTS, "no enc_q.* weights were loaded");
+  if (!spec || !y_mask || !noise || !z || !stats) return fail(h, MBV_ERR_INVALID, "null tensor");
+  if (g && h->cfg.gin_channels == 0) return fail(h, MBV_ERR_INVALID, "g given but gin_channels == 0");
+  size_t need = 0;
+  mbv_posterior_workspace_bytes(h, B, T, &need);
+  if (!ws || ((uintptr_t)ws & 1023) != 0) return fail(h, MBV_ERR_WORKSPACE, "workspace must be non-null and 1024-byte aligned");
+  if (ws_bytes < need) return fail(h, MBV_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+  DEVICE_GUARD(h);
+  Arena A(ws);
+  PostBufs p;
+  layout_posterior(h, A, B, T, &p);
+  Ctx cx = make_ctx(h, B, T, ws, g ? 9 : 8, stream);
+  rc = run_posterior(cx, p, spec, y_mask, g, noise, z, stats, B, T);
+  if (rc) { cx.plans->clear(); return rc; }
+  h->last_launches = cx.launches;
+  return MBV_OK;
+}
+
 extern "C" int mbv_tail(mbv_handle* h, const float* logits, float* wav, float* o_mb, float* spec, float* phase,
                         int32_t B, int32_t T, void* stream) {
   int rc = check_ready(h, B, T);
@@ -1230,6 +1397,149 @@ extern "C" int mbv_expand_prior(mbv_handle* h, const float* m_p, const float* lo
   CUDA_TRY(h, launch_expand_prior(m_p, logs_p, w_ceil, x_mask, noise, noise_scale, B, C, Tx, Ty, z_p, y_mask, m_exp, logs_exp,
                                   attn, (long long*)y_lengths, (cudaStream_t)stream));
   h->last_launches = 1;
+  return MBV_OK;
+}
+
+// =================================================================================================
+// streaming decode: exact chunked decoding with receptive-field halos carried in device state
+// =================================================================================================
+struct mbv_stream {
+  mbv_handle* h = nullptr;
+  int B = 0, max_chunk = 0, halo = 0, cap = 0;
+  float* hist[2] = {nullptr, nullptr};  // [B][inter][cap] latent history (ping-pong for the shift), column 0 = frame hist_start
+  float* win = nullptr;                 // [B][inter][W] contiguous decode window
+  float* wav = nullptr;                 // [B][1][spf * cap] decoded window
+  int cur = 0;
+  long long received = 0, emitted = 0, hist_start = 0;
+  bool finished = false;
+};
+
+namespace {
+// Upper bound (latent frames, one side) of the decoder's receptive field; mirrors configs.receptive_field_frames
+int receptive_field(const mbv_handle* h) {
+  const mbv_config& c = h->cfg;
+  double rf = 3.0, rate = 1.0;
+  for (int i = 0; i < c.n_ups; ++i) {
+    const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
+    rf += (double)((k + 2 * u - 1) / (2 * u)) / rate;
+    rate *= u;
+    int widest = 0;
+    for (int j = 0; j < c.n_kernels; ++j) {
+      const int rk = c.resblock_kernel_sizes[j];
+      int r = 0;
+      for (int p = 0; p < c.n_dilations; ++p) r += (rk - 1) / 2 * c.resblock_dilations[j][p];
+      if (c.resblock_type == 1) r += (rk - 1) / 2 * c.n_dilations;
+      if (r > widest) widest = r;
+    }
+    rf += widest / rate;
+  }
+  rf += (3 + 1 + 4 + (c.variant != MBV_VARIANT_ISTFT ? 3 : 0)) / rate;
+  return (int)ceil(rf);
+}
+}  // namespace
+
+extern "C" int mbv_receptive_field(mbv_handle* h) { return h ? receptive_field(h) : 0; }
+
+extern "C" int mbv_stream_open(mbv_handle* h, int32_t B, int32_t max_chunk_frames, mbv_stream** out) {
+  if (!h || !out) return MBV_ERR_INVALID;
+  *out = nullptr;
+  int rc = check_ready(h, B, max_chunk_frames);
+  if (rc) return rc;
+  DEVICE_GUARD(h);
+  mbv_stream* s = new mbv_stream();
+  s->h = h; s->B = B; s->max_chunk = max_chunk_frames;
+  s->halo = receptive_field(h) + 1;
+  s->cap = max_chunk_frames + 3 * s->halo;
+  const size_t nz = (size_t)B * h->Cz * s->cap * sizeof(float);
+  cudaError_t e = cudaMalloc(&s->hist[0], nz);
+  if (e == cudaSuccess) e = cudaMalloc(&s->hist[1], nz);
+  if (e == cudaSuccess) e = cudaMalloc(&s->win, nz);
+  if (e == cudaSuccess) e = cudaMalloc(&s->wav, (size_t)B * h->spf * s->cap * sizeof(float));
+  if (e != cudaSuccess) {
+    for (float* p : {s->hist[0], s->hist[1], s->win, s->wav}) if (p) cudaFree(p);
+    delete s;
+    return fail(h, MBV_ERR_CUDA, "mbv_stream_open: %s", cudaGetErrorString(e));
+  }
+  *out = s;
+  return MBV_OK;
+}
+
+extern "C" void mbv_stream_close(mbv_stream* s) {
+  if (!s) return;
+  for (float* p : {s->hist[0], s->hist[1], s->win, s->wav}) if (p) cudaFree(p);
+  delete s;
+}
+
+extern "C" int mbv_stream_workspace_bytes(mbv_stream* s, size_t* bytes) {
+  if (!s || !bytes) return MBV_ERR_INVALID;
+  return mbv_workspace_bytes(s->h, s->B, s->cap, bytes);
+}
+
+extern "C" int mbv_stream_halo(mbv_stream* s) { return s ? s->halo : 0; }
+
+extern "C" int mbv_stream_push(mbv_stream* s, const float* z_chunk, int32_t n_frames, int32_t last, const float* g,
+                               float* wav_out, int32_t wav_capacity_frames, int64_t* first_frame, int32_t* n_frames_out,
+                               void* ws, size_t ws_bytes, void* stream) {
+  if (!s || !first_frame || !n_frames_out) return MBV_ERR_INVALID;
+  mbv_handle* h = s->h;
+  *n_frames_out = 0;
+  *first_frame = s->emitted;
+  if (s->finished) return fail(h, MBV_ERR_INVALID, "mbv_stream_push after the last chunk");
+  if (n_frames < 0 || n_frames > s->max_chunk) return fail(h, MBV_ERR_INVALID, "chunk of %d frames (stream opened for <= %d)", n_frames, s->max_chunk);
+  if (n_frames > 0 && !z_chunk) return fail(h, MBV_ERR_INVALID, "null chunk");
+  if (g && h->cfg.gin_channels == 0) return fail(h, MBV_ERR_INVALID, "g given but gin_channels == 0");
+  DEVICE_GUARD(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Cz = h->Cz, rows = s->B * Cz;
+  const size_t cap_pitch = (size_t)s->cap * sizeof(float);
+  if (n_frames > 0) {  // append the chunk to the history
+    const long long col = s->received - s->hist_start;
+    CUDA_TRY(h, cudaMemcpy2DAsync(s->hist[s->cur] + col, cap_pitch, z_chunk, (size_t)n_frames * sizeof(float),
+                                  (size_t)n_frames * sizeof(float), rows, cudaMemcpyDeviceToDevice, st));
+    s->received += n_frames;
+  }
+  // frames [emitted, emit_end) have their whole right context (or the stream ends here)
+  long long emit_end = last ? s->received : s->received - s->halo;
+  if (emit_end < s->emitted) emit_end = s->emitted;
+  const int n_emit = (int)(emit_end - s->emitted);
+  if (last) s->finished = true;
+  if (n_emit == 0) return MBV_OK;
+  if (!wav_out || wav_capacity_frames < n_emit) return fail(h, MBV_ERR_INVALID, "wav_out holds %d frames, %d are due", wav_capacity_frames, n_emit);
+  const long long w0 = s->emitted - s->halo > 0 ? s->emitted - s->halo : 0;
+  const long long w1 = emit_end + s->halo < s->received ? emit_end + s->halo : s->received;
+  const int W = (int)(w1 - w0);
+  int rc = check_ws(h, s->B, W, ws, ws_bytes);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaMemcpy2DAsync(s->win, (size_t)W * sizeof(float), s->hist[s->cur] + (w0 - s->hist_start), cap_pitch,
+                                (size_t)W * sizeof(float), rows, cudaMemcpyDeviceToDevice, st));
+  {
+    size_t dec_off, total;
+    total_ws(h, s->B, W, &dec_off, &total);
+    Arena A(ws);
+    A.off = dec_off;
+    DecBufs d;
+    layout_dec(h, A, s->B, W, &d);
+    Ctx cx = make_ctx(h, s->B, W, ws, g ? 11 : 10, stream);
+    rc = run_decode(cx, d, s->win, nullptr, nullptr, g, s->wav, nullptr, nullptr, nullptr, s->B, W);
+    if (rc) { cx.plans->clear(); return rc; }
+    h->last_launches = cx.launches + 3;
+  }
+  const int spf = h->spf;
+  CUDA_TRY(h, cudaMemcpy2DAsync(wav_out, (size_t)n_emit * spf * sizeof(float), s->wav + (size_t)(s->emitted - w0) * spf,
+                                (size_t)W * spf * sizeof(float), (size_t)n_emit * spf * sizeof(float), s->B,
+                                cudaMemcpyDeviceToDevice, st));
+  *n_frames_out = n_emit;
+  s->emitted = emit_end;
+  // keep [emitted - halo, received) for the next push
+  const long long keep0 = s->emitted - s->halo > 0 ? s->emitted - s->halo : 0;
+  if (!last && keep0 > s->hist_start) {
+    const long long n_keep = s->received - keep0;
+    if (n_keep > 0)
+      CUDA_TRY(h, cudaMemcpy2DAsync(s->hist[s->cur ^ 1], cap_pitch, s->hist[s->cur] + (keep0 - s->hist_start), cap_pitch,
+                                    (size_t)n_keep * sizeof(float), rows, cudaMemcpyDeviceToDevice, st));
+    s->cur ^= 1;
+    s->hist_start = keep0;
+  }
   return MBV_OK;
 }
 

@@ -100,6 +100,24 @@ cudaError_t launch_cond_gemv(const float* g, const float* w, const float* bias, 
   return cudaGetLastError();
 }
 
+// PosteriorEncoder sampling (models.py:243-245): m, logs = split(stats); z = (m + noise * exp(logs)) * mask, all NCT.
+__global__ void __launch_bounds__(256) posterior_sample_kernel(const float* __restrict__ stats, const float* __restrict__ noise,
+                                                               const float* __restrict__ mask, float* __restrict__ z, int C, int T) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= T) return;
+  const float m = stats[((size_t)b * 2 * C + c) * T + t];
+  const float logs = stats[((size_t)b * 2 * C + C + c) * T + t];
+  z[((size_t)b * C + c) * T + t] = (m + noise[((size_t)b * C + c) * T + t] * expf(logs)) * mask[(size_t)b * T + t];
+}
+
+cudaError_t launch_posterior_sample(const float* stats, const float* noise, const float* mask, float* z, int B, int C, int T,
+                                    cudaStream_t st) {
+  dim3 grid((T + 255) / 256, C, B);
+  posterior_sample_kernel<<<grid, 256, 0, st>>>(stats, noise, mask, z, C, T);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Waveform post-processing of the reference's TTS service (tts_vits.py:204-216): per-utterance peak normalisation to
 // 0.9 (only if the peak exceeds 0.01), clip to [-1, 1], scale by 32767 and truncate to int16.  Two passes: a per-

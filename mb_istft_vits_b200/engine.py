@@ -14,7 +14,7 @@ from . import lib as _lib
 from .configs import receptive_field_frames, samples_per_frame
 
 
-def fold_weight_norm(sd: Dict[str, torch.Tensor], prefixes=("dec.", "flow.")) -> Dict[str, torch.Tensor]:
+def fold_weight_norm(sd: Dict[str, torch.Tensor], prefixes=("dec.", "flow.", "enc_q.")) -> Dict[str, torch.Tensor]:
     """Reference checkpoint layout -> effective fp32 weights: w = g * v / ||v|| with the norm
     over all dims but 0 (torch.nn.utils.weight_norm, dim=0; for ConvTranspose1d dim 0 = in-channels).
     Keys already stored as plain ``weight`` (after remove_weight_norm) pass through."""
@@ -116,8 +116,8 @@ class Engine:
         self._check(self.lib.mbv_workspace_bytes(self._h, B, T, C.byref(n)))
         return n.value
 
-    def _workspace(self, B, T):
-        need = self.workspace_bytes(B, T)
+    def _workspace(self, B, T, need=None):
+        need = self.workspace_bytes(B, T) if need is None else need
         if self._ws is None or self._ws.numel() < need + 1024:
             if self._ws is not None:
                 # kernels of earlier calls (on any stream) may still be running in the old block, and the caching
@@ -200,6 +200,30 @@ class Engine:
         self._check(self.lib.mbv_flow_forward(self._h, self._ptr(x), self._ptr(y_mask), self._ptr(g), self._ptr(out),
                                               B, T, C.c_void_p(ws), nws, self._stream()))
         return out
+
+    def posterior_encode(self, spec, y_lengths=None, g=None, noise=None, y_mask=None):
+        """PosteriorEncoder.forward (models.py:236-246) on the library: spec [B, spec_channels, T], lengths [B] (or a ready
+        y_mask [B,1,T]) -> (z, m, logs, y_mask).  noise [B,inter,T] or None = drawn here with torch.randn, which is what
+        the reference's ``torch.randn_like(m)`` yields for its (contiguous) result.  Needs the enc_q.* weights."""
+        spec = self._prep(spec)
+        B, _, T = spec.shape
+        if y_mask is None:
+            lens = torch.as_tensor(y_lengths).to(self.device)
+            y_mask = (torch.arange(T, device=self.device)[None, :] < lens[:, None]).to(torch.float32).unsqueeze(1)  # commons.sequence_mask
+        y_mask = self._prep(y_mask, (B, 1, T))
+        g = self._prep(g)
+        inter = self.cfg["inter_channels"]
+        if noise is None:
+            noise = torch.randn((B, inter, T), dtype=torch.float32, device=self.device)
+        noise = self._prep(noise, (B, inter, T))
+        z = torch.empty((B, inter, T), dtype=torch.float32, device=self.device)
+        stats = torch.empty((B, 2 * inter, T), dtype=torch.float32, device=self.device)
+        n = C.c_size_t()
+        self._check(self.lib.mbv_posterior_workspace_bytes(self._h, B, T, C.byref(n)))
+        ws, nws = self._workspace(B, T, need=max(n.value, self.workspace_capacity()))
+        self._check(self.lib.mbv_posterior_encode(self._h, self._ptr(spec), self._ptr(y_mask), self._ptr(g), self._ptr(noise),
+                                                  self._ptr(z), self._ptr(stats), B, T, C.c_void_p(ws), nws, self._stream()))
+        return z, stats[:, :inter], stats[:, inter:], y_mask
 
     def decode(self, z, g=None, z_mask=None, want_mb=True, want_spec=True):
         B, Cz, T = z.shape

@@ -22,6 +22,7 @@ FLAG_FORCE_SIMT = 4
 FLAG_RESIDUAL_FP16 = 8
 FLAG_FUSED_PAIR = 16
 FLAG_CLUSTER_PAIRS = 32
+FLAG_BRANCHES = 64
 
 ERRORS = {0: "MBV_OK", -1: "MBV_ERR_INVALID", -2: "MBV_ERR_UNSUPPORTED", -3: "MBV_ERR_WEIGHTS",
           -4: "MBV_ERR_WORKSPACE", -5: "MBV_ERR_CUDA"}
@@ -29,7 +30,9 @@ ERRORS = {0: "MBV_OK", -1: "MBV_ERR_INVALID", -2: "MBV_ERR_UNSUPPORTED", -3: "MB
 # every symbol include/mbistft.h declares (tests check the .so exports all of them)
 SYMBOLS = ["mbv_abi_version", "mbv_create", "mbv_destroy", "mbv_load_weights", "mbv_workspace_bytes",
            "mbv_flow_reverse", "mbv_decode", "mbv_flow_decode", "mbv_last_launch_count", "mbv_decode_flops",
-           "mbv_flow_flops", "mbv_tail", "mbv_last_error", "mbv_set_profiling", "mbv_profile_read", "mbv_profile_read_launches", "mbv_pcm16", "mbv_expand_prior", "mbv_flow_forward"]
+           "mbv_flow_flops", "mbv_tail", "mbv_last_error", "mbv_set_profiling", "mbv_profile_read", "mbv_profile_read_launches", "mbv_pcm16", "mbv_expand_prior", "mbv_flow_forward",
+           "mbv_posterior_workspace_bytes", "mbv_posterior_encode", "mbv_receptive_field", "mbv_stream_open",
+           "mbv_stream_workspace_bytes", "mbv_stream_halo", "mbv_stream_push", "mbv_stream_close"]
 
 
 class MbvConfig(C.Structure):
@@ -91,6 +94,15 @@ def load():
     lib.mbv_profile_read_launches.argtypes = [vp, C.POINTER(C.c_float), C.c_char_p, i32, i32, C.POINTER(i32)]
     lib.mbv_pcm16.argtypes = [vp, fp, vp, i32, i32, i32, vp, vp, vp]
     lib.mbv_expand_prior.argtypes = [vp, fp, fp, fp, fp, fp, C.c_float, i32, i32, i32, i32, fp, fp, fp, fp, fp, vp, vp]
+    lib.mbv_posterior_workspace_bytes.argtypes = [vp, i32, i32, C.POINTER(C.c_size_t)]
+    lib.mbv_posterior_encode.argtypes = [vp, fp, fp, fp, fp, fp, fp, i32, i32, vp, C.c_size_t, vp]
+    lib.mbv_receptive_field.argtypes = [vp]
+    lib.mbv_stream_open.argtypes = [vp, i32, i32, C.POINTER(vp)]
+    lib.mbv_stream_workspace_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]
+    lib.mbv_stream_halo.argtypes = [vp]
+    lib.mbv_stream_push.argtypes = [vp, fp, i32, i32, fp, fp, i32, C.POINTER(C.c_int64), C.POINTER(i32), vp, C.c_size_t, vp]
+    lib.mbv_stream_close.argtypes = [vp]
+    lib.mbv_stream_close.restype = None
     lib.mbv_last_error.argtypes = [vp]
     lib.mbv_last_error.restype = C.c_char_p
     if lib.mbv_abi_version() != MBV_ABI_VERSION:

@@ -40,7 +40,8 @@ def _plain_conv(sd, gen, name, shape, fan_in):
     sd[name + ".bias"] = _uniform(gen, (shape[0],), 1.0 / math.sqrt(fan_in))
 
 
-def make_state_dict(cfg, seed: int = 1234, g_scale: float = 1.0) -> Dict[str, torch.Tensor]:
+def make_state_dict(cfg, seed: int = 1234, g_scale: float = 1.0, enc_q: bool = False, spec_channels: int = 513,
+                    enc_q_layers: int = 16) -> Dict[str, torch.Tensor]:
     gen = torch.Generator().manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
     inter, hid, gin = cfg["inter_channels"], cfg["hidden_channels"], cfg["gin_channels"]
@@ -96,6 +97,18 @@ def make_state_dict(cfg, seed: int = 1234, g_scale: float = 1.0) -> Dict[str, to
 
     if cfg.get("n_speakers", 0) > 1 and gin:
         sd["emb_g.weight"] = torch.randn((cfg["n_speakers"], gin), generator=gen)
+
+    # ---- posterior encoder (models.py:217-246, built at models.py:646 with kernel 5 / dilation_rate 1 / 16 layers); drawn
+    # after everything else so that the dec.* / flow.* / emb_g tensors of a seed do not depend on this switch
+    if enc_q:
+        _plain_conv(sd, gen, "enc_q.pre", (hid, spec_channels, 1), spec_channels)
+        if gin:
+            _wn_conv(sd, gen, "enc_q.enc.cond_layer", (2 * hid * enc_q_layers, gin, 1), gin, g_scale)
+        for l in range(enc_q_layers):
+            _wn_conv(sd, gen, f"enc_q.enc.in_layers.{l}", (2 * hid, hid, FLOW_KERNEL), hid * FLOW_KERNEL, g_scale)
+            rs = 2 * hid if l < enc_q_layers - 1 else hid
+            _wn_conv(sd, gen, f"enc_q.enc.res_skip_layers.{l}", (rs, hid, 1), hid, g_scale)
+        _plain_conv(sd, gen, "enc_q.proj", (2 * inter, hid, 1), hid)
     return sd
 
 

@@ -123,6 +123,32 @@ def flow_forward(sd, cfg, x, y_mask, g=None, prefix="flow"):
     return x
 
 
+def posterior_encoder(sd, cfg, y, y_lengths, g=None, noise=None, prefix="enc_q", n_layers=16):
+    """PosteriorEncoder.forward (models.py:236-246; built with kernel 5, dilation_rate 1, 16 layers at models.py:646):
+    x = pre(y) * mask; x = WN(x, mask, g); stats = proj(x) * mask; m, logs = split(stats);
+    z = (m + noise * exp(logs)) * mask.  Returns (z, m, logs, mask)."""
+    hidden, inter = cfg["hidden_channels"], cfg["inter_channels"]
+    T = y.shape[2]
+    mask = (torch.arange(T)[None, :] < torch.as_tensor(y_lengths)[:, None]).to(y.dtype).unsqueeze(1)  # commons.py:121-125
+    x = F.conv1d(y.float(), sd[prefix + ".pre.weight"].float(), sd[prefix + ".pre.bias"].float()) * mask
+    x = wn_forward(x, mask, sd, prefix + ".enc", hidden, n_layers=n_layers, g=g)
+    stats = F.conv1d(x, sd[prefix + ".proj.weight"].float(), sd[prefix + ".proj.bias"].float()) * mask
+    m, logs = stats[:, :inter], stats[:, inter:]
+    if noise is None:
+        noise = torch.randn_like(m)
+    z = (m + noise * torch.exp(logs)) * mask
+    return z, m, logs, mask
+
+
+def voice_conversion(sd, cfg, y, y_lengths, g_src, g_tgt, noise):
+    """SynthesizerTrn.voice_conversion (models.py:790-798) with the embeddings already looked up."""
+    z, m_q, logs_q, y_mask = posterior_encoder(sd, cfg, y, y_lengths, g_src, noise)
+    z_p = flow_forward(sd, cfg, z, y_mask, g_src)
+    z_hat = flow_reverse(sd, cfg, z_p, y_mask, g_tgt)
+    o_hat, o_hat_mb, _, _ = decode(sd, cfg, z_hat * y_mask, g_tgt)
+    return o_hat, o_hat_mb, y_mask, (z, z_p, z_hat)
+
+
 # ----------------------------------------------------------------------------
 # decoder body: models.py:278-293 / 344-365 / 430-453, modules.py:213-228, 251-262
 # ----------------------------------------------------------------------------

@@ -37,3 +37,15 @@ def load_case(name):
     sd = synth.make_state_dict(cfg, seed=wseed, g_scale=float(d["g_scale"]))
     return cfg, sd, t, dict(B=B, T=T, zseed=zseed, lengths=[int(v) for v in d["lengths"]],
                             sid=(torch.from_numpy(d["sid"]) if "sid" in d.files else None))
+
+
+# voice-conversion / posterior-encoder cases (tools/make_golden.py vc): name -> config name
+VC_CASES = {"vc_ms_spk": "uudb_ms_istft_vits_ms", "posterior_mini": "ljs_mini_mb_istft_vits"}
+
+
+def load_vc_case(name):
+    cfg = cfgs.get_config(VC_CASES[name])
+    d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    t = {k: torch.from_numpy(d[k]) for k in d.files}
+    sd = synth.make_state_dict(cfg, seed=1234, enc_q=True)
+    return cfg, sd, t

@@ -101,3 +101,39 @@ def test_infer_native_on_the_real_reference_modules():
     assert (zp - zp_r).abs().max() < 1e-5            # same generator consumption, expf vs torch.exp
     assert orc.max_abs_over_peak(o.cpu(), o_r.cpu()) < 1e-3
     eng.close()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_patched_voice_conversion_matches_reference_voice_conversion(prec):
+    """SynthesizerTrn.voice_conversion (models.py:790-798) with enc_q, flow and dec all swapped for the native modules
+    (patch_synthesizer(posterior=True)) against the unmodified model's own voice_conversion on the same GPU."""
+    import ref_loader
+    from mb_istft_vits_b200 import patch_synthesizer
+    if not ref_loader.available():
+        pytest.skip("reference not staged (python baseline/stage_ref.py)")
+    _gold_mode()
+    cfg = get_config("uudb_ms_istft_vits_ms")
+    sd = synth.make_state_dict(cfg, seed=1234, enc_q=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = ref_loader.build_synthesizer(cfg, sd, device="cuda")
+    B, T = 2, 40
+    y = torch.randn((B, 513, T), device="cuda").abs()
+    y_len = torch.tensor([T, T - 9], device="cuda")
+    sid_s, sid_t = torch.tensor([1, 4], device="cuda"), torch.tensor([7, 0], device="cuda")
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        torch.manual_seed(21)
+        o_r, omb_r, ymask_r, (z_r, zp_r, zhat_r) = net.voice_conversion(y, y_len, sid_s, sid_t)
+        eng = patch_synthesizer(net, cfg, precision=prec, posterior=True)
+        assert type(net.enc_q).__name__ == "NativePosteriorEncoder"
+        torch.manual_seed(21)
+        o, omb, ymask, (z, zp, zhat) = net.voice_conversion(y, y_len, sid_s, sid_t)
+        torch.cuda.synchronize()
+    assert torch.equal(ymask, ymask_r)
+    if prec == "fp32":
+        assert (z - z_r).abs().max() < 1e-4 * max(1.0, float(z_r.abs().max()))
+        assert (zhat - zhat_r).abs().max() < 1e-4 * max(1.0, float(zhat_r.abs().max()))
+        assert orc.max_abs_over_peak(o.cpu(), o_r.cpu()) < 1e-4
+    else:
+        assert orc.snr_db(z.cpu(), z_r.cpu()) > 40.0
+        assert orc.snr_db(o.cpu(), o_r.cpu()) > 40.0
+    eng.close()

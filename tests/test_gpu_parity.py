@@ -526,3 +526,142 @@ def test_flow_forward_matches_reference_and_inverts_reverse(name):
     zf = eng.flow_forward(t["z_p"].cuda(), t["mask"].cuda(), g)
     assert orc.snr_db(zf.cpu(), t["z_fwd"]) > 40.0
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# next-row widening: posterior encoder + the whole voice-conversion path (models.py:217-246, 790-798)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["vc_ms_spk", "posterior_mini"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16", "fp16"])
+def test_posterior_encoder_matches_reference(name, prec):
+    """mbv_posterior_encode against the reference's own enc_q output: fp32 path within 1e-4, tf32 within 1e-3 of the
+    largest statistic, bf16 / fp16 >= 40 dB on m, logs and z (16 gated layers deep)."""
+    from helpers import load_vc_case
+    cfg, sd, t = load_vc_case(name)
+    eng = _engine(cfg, sd, prec)
+    g = t.get("g_src")
+    z, m, logs, mask = eng.posterior_encode(t["y"].cuda(), t["y_lengths"].cuda(), None if g is None else g.cuda(), t["noise"].cuda())
+    torch.cuda.synchronize()
+    z, m, logs = z.cpu(), m.cpu(), logs.cpu()
+    assert torch.equal(mask.cpu(), t["y_mask"])
+    assert float((z * (1 - t["y_mask"])).abs().max()) == 0.0
+    if prec in ("fp32", "tf32"):
+        tol = (1e-4 if prec == "fp32" else 1e-3) * max(1.0, float(t["m"].abs().max()), float(t["logs"].abs().max()))
+        assert (m - t["m"]).abs().max() < tol and (logs - t["logs"]).abs().max() < tol
+        assert (z - t["z"]).abs().max() < 2 * tol
+    else:
+        assert orc.snr_db(m, t["m"]) > 40.0 and orc.snr_db(logs, t["logs"]) > 40.0
+        assert orc.snr_db(z, t["z"]) > 40.0
+    eng.close()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_voice_conversion_path_matches_reference(prec):
+    """enc_q -> flow forward (g_src) -> flow reverse (g_tgt) -> dec (g_tgt), every step on the library, against the
+    reference's voice_conversion() outputs (golden vc_ms_spk)."""
+    from helpers import load_vc_case
+    cfg, sd, t = load_vc_case("vc_ms_spk")
+    eng = _engine(cfg, sd, prec)
+    g_s, g_t = t["g_src"].cuda(), t["g_tgt"].cuda()
+    z, m, logs, mask = eng.posterior_encode(t["y"].cuda(), t["y_lengths"].cuda(), g_s, t["noise"].cuda())
+    z_p = eng.flow_forward(z, mask, g_s)
+    z_hat = eng.flow_reverse(z_p, mask, g_t)
+    o = eng.decode(z_hat * mask, g_t, want_mb=False, want_spec=False)[0]
+    torch.cuda.synchronize()
+    if prec == "fp32":
+        assert (z_p.cpu() - t["z_p"]).abs().max() < 1e-4 and (z_hat.cpu() - t["z_hat"]).abs().max() < 1e-4
+        assert orc.max_abs_over_peak(o.cpu(), t["o"]) < 1e-4
+    else:
+        assert orc.snr_db(z_hat.cpu(), t["z_hat"]) > 40.0
+        assert orc.snr_db(o.cpu(), t["o"]) > 40.0
+    eng.close()
+
+
+def test_posterior_encoder_needs_its_weights():
+    """A handle loaded without enc_q.* tensors refuses the posterior entry (no silent fallback)."""
+    from mb_istft_vits_b200 import lib as L
+    cfg, sd, t, meta = load_case("mini_mb")
+    eng = _engine(cfg, sd, "bf16")
+    with pytest.raises(L.MbvError):
+        eng.posterior_encode(torch.zeros((1, 513, 8)).cuda(), torch.tensor([8]).cuda())
+    eng.close()
+
+
+def test_resblock_branches_are_bit_identical():
+    """MBV_FLAG_BRANCHES: the parallel ResBlocks of a stage on separate streams (own buffers per branch).  Same kernels, same
+    operands -> bit-identical waveforms, eagerly and from a captured CUDA graph."""
+    from mb_istft_vits_b200 import lib as L
+    for case in ("mb", "ms_spk", "mb_resblock2", "istft"):
+        cfg, sd, t, meta = load_case(case)
+        ref = _run(_engine(cfg, sd, "bf16", 0), t)
+        got = _run(_engine(cfg, sd, "bf16", L.FLAG_BRANCHES), t)
+        assert torch.equal(got[1], ref[1]) and torch.equal(got[0], ref[0]), case
+    cfg, sd, t, meta = load_case("mb_long")
+    eng = _engine(cfg, sd, "bf16", L.FLAG_BRANCHES)
+    z_p, mask = t["z_p"].cuda(), t["mask"].cuda()
+    eager = eng.flow_decode(z_p, mask)[1].clone()
+    graph, outs = eng.capture_flow_decode(z_p, mask)
+    outs[1].zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(outs[1], eager)
+    eng.close()
+
+
+@pytest.mark.parametrize("name,chunks", [("mb_long", [37, 13, 50, 50]), ("mb_long", [150]), ("mb_long", [1] * 30 + [60, 60]),
+                                         ("infer_istft", [5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5]), ("ms_spk", [7, 7, 6])])
+def test_streaming_decode_is_bit_identical_to_one_shot(name, chunks):
+    """mbv_stream_push: latent chunks in, final samples out with a latency of `halo` frames; the concatenation equals the
+    one-shot decode bit for bit, whatever the chunking (including 1-frame chunks and a single chunk)."""
+    from mb_istft_vits_b200 import StreamingDecoder
+    cfg, sd, t, meta = load_case(name)
+    eng = _engine(cfg, sd, "bf16")
+    z = (t["z"] * t["mask"]).cuda()
+    g = t.get("g")
+    g = g.cuda() if g is not None else None
+    B, _, T = z.shape
+    chunks = list(chunks)
+    while sum(chunks) < T:
+        chunks.append(chunks[-1])
+    full = eng.decode(z, g, want_mb=False, want_spec=False)[0]
+    sdec = StreamingDecoder(eng, B, max(chunks))
+    assert sdec.halo == eng.lib.mbv_receptive_field(eng._h) + 1
+    parts, pos, a = [], 0, 0
+    for i, n in enumerate(chunks):
+        n = min(n, T - a)
+        if n <= 0:
+            break
+        last = a + n >= T
+        first, wav = sdec.push(z[:, :, a:a + n].contiguous(), g, last=last)
+        assert first == pos
+        pos += wav.shape[-1] // 256
+        parts.append(wav)
+        a += n
+    torch.cuda.synchronize()
+    got = torch.cat(parts, dim=-1)
+    assert got.shape == full.shape
+    assert torch.equal(got, full)
+    sdec.close()
+    eng.close()
+
+
+def test_streaming_pcm_chunks_match_reference_arithmetic():
+    """20 ms int16 slices (tts_vits.py:204-226 with auto_normalize off): concatenated they equal the reference arithmetic
+    on the one-shot waveform; every slice but the last has chunk_size samples."""
+    import numpy as np
+    from mb_istft_vits_b200 import StreamingDecoder
+    cfg, sd, t, meta = load_case("mb_long")
+    eng = _engine(cfg, sd, "bf16")
+    z = (t["z"] * t["mask"]).cuda()
+    full = eng.decode(z, None, want_mb=False, want_spec=False)[0].cpu() * 3.0
+    sdec = StreamingDecoder(eng, 1, 40)
+    assert sdec.chunk_size == round(0.02 * cfg["sampling_rate"])
+    slices = []
+    T = z.shape[2]
+    for a in range(0, T, 40):
+        slices += sdec.push_pcm(z[:, :, a:a + 40].contiguous(), last=a + 40 >= T, gain=3.0)[0]
+    assert all(s.numel() == sdec.chunk_size for s in slices[:-1]) and 0 < slices[-1].numel() <= sdec.chunk_size
+    ref = orc.pcm16(full[0, 0].numpy(), False)
+    assert np.array_equal(torch.cat(slices).numpy(), ref)
+    sdec.close()
+    eng.close()

@@ -127,3 +127,22 @@ def test_every_precision_and_flag_combination_validates_without_gpu(lib, prec):
         assert lib.mbv_expand_prior(h, p, p, p, None, p, 1.0, 1, 1, 1, 1, p, p, None, None, None, None, None) != 0
         assert lib.mbv_flow_forward(h, p, p, None, p, 1, 1, p, 1 << 20, None) != 0
     lib.mbv_destroy(h)
+
+
+def test_receptive_field_library_and_host_formula_agree():
+    """mbv_receptive_field (C, used by the streaming state) == configs.receptive_field_frames (host, decode_chunked) for every
+    shipped geometry; 25 latent frames for the MB / MS decoders (SURVEY 3.3 measured +-24), 13 single-band (+-13)."""
+    import ctypes as C
+    from mb_istft_vits_b200 import configs, lib as L
+    lib = L.load()
+    want = {"ljs_mb_istft_vits": 25, "ljs_istft_vits": 13}
+    for name in configs.CONFIGS:
+        cfg = configs.get_config(name)
+        h = C.c_void_p()
+        ccfg = L.make_config(cfg, "bf16", 0, 0)
+        assert lib.mbv_create(C.byref(ccfg), C.byref(h)) == 0
+        rf = lib.mbv_receptive_field(h)
+        lib.mbv_destroy(h)
+        assert rf == configs.receptive_field_frames(cfg), name
+        if name in want:
+            assert rf == want[name]

@@ -62,3 +62,20 @@ def test_oracle_flow_forward_inverts_flow_reverse(name):
     g = t.get("g")
     back = orc.flow_forward(sd, cfg, orc.flow_reverse(sd, cfg, t["z_p"], t["mask"], g), t["mask"], g)
     assert (back - t["z_p"] * t["mask"]).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("name", ["vc_ms_spk", "posterior_mini"])
+def test_oracle_posterior_encoder_and_voice_conversion_match_reference(name):
+    """PosteriorEncoder.forward (models.py:236-246) and, for the multi-speaker case, the whole voice_conversion path
+    (models.py:790-798) against vectors minted from the reference's own enc_q / flow / dec (tools/make_golden.py vc)."""
+    from helpers import load_vc_case
+    cfg, sd, t = load_vc_case(name)
+    g = t.get("g_src")
+    z, m, logs, mask = orc.posterior_encoder(sd, cfg, t["y"], t["y_lengths"], g, t["noise"])
+    assert torch.equal(mask, t["y_mask"])
+    assert (m - t["m"]).abs().max() < 1e-5 and (logs - t["logs"]).abs().max() < 1e-5
+    assert (z - t["z"]).abs().max() < 2e-5
+    if "o" in t:
+        o, _, _, (z2, z_p, z_hat) = orc.voice_conversion(sd, cfg, t["y"], t["y_lengths"], g, t["g_tgt"], t["noise"])
+        assert (z_p - t["z_p"]).abs().max() < 2e-5 and (z_hat - t["z_hat"]).abs().max() < 2e-5
+        assert orc.max_abs_over_peak(o, t["o"]) < 2e-5

@@ -169,11 +169,66 @@ def mint_prior_cases(models, orc):
                             logs_exp=logs_exp.numpy())
 
 
+def mint_vc_cases(models, orc):
+    """Golden vectors for the posterior encoder and the voice-conversion path (models.py:217-246, 790-798): the reference's
+    own enc_q / flow / dec on seeded enc_q.* weights (synth.make_state_dict(enc_q=True)); the noise enc_q draws is
+    recorded by wrapping torch.randn_like for the duration of the call."""
+    for name, cname, B, T, lens in (("vc_ms_spk", "uudb_ms_istft_vits_ms", 2, 24, [24, 17]),
+                                    ("posterior_mini", "ljs_mini_mb_istft_vits", 2, 30, [30, 21])):
+        cfg = cfgs.get_config(cname)
+        sd = synth.make_state_dict(cfg, seed=1234, enc_q=True)
+        net = build_reference(models, cfg, sd)
+        y = torch.randn((B, 513, T), generator=torch.Generator().manual_seed(8)).abs()   # a magnitude spectrogram
+        y_len = torch.tensor(lens)
+        cap = {}
+        _randn_like = torch.randn_like
+
+        def recording_randn_like(t, *a, **k):
+            r = _randn_like(t, *a, **k)
+            cap.setdefault("noise", []).append(r.detach().clone())
+            return r
+        torch.manual_seed(99)
+        torch.randn_like = recording_randn_like
+        out = {}
+        try:
+            with torch.no_grad():
+                if cfg["n_speakers"]:
+                    sid_s, sid_t = torch.arange(B) % cfg["n_speakers"], (torch.arange(B) + 5) % cfg["n_speakers"]
+                    g_s, g_t = net.emb_g(sid_s).unsqueeze(-1), net.emb_g(sid_t).unsqueeze(-1)
+                    o_hat, o_hat_mb, y_mask, (z, z_p, z_hat) = net.voice_conversion(y, y_len, sid_s, sid_t)
+                    out.update(g_src=g_s.numpy(), g_tgt=g_t.numpy(), sid_src=sid_s.numpy(), sid_tgt=sid_t.numpy(),
+                               z_p=z_p.numpy(), z_hat=z_hat.numpy(), o=o_hat.numpy())
+                    noise = cap["noise"][0]
+                    _, m_q, logs_q, _ = None, None, None, None
+                    torch.manual_seed(99)
+                    z2, m_q, logs_q, _ = net.enc_q(y, y_len, g=g_s)
+                    assert torch.equal(z2, z)
+                else:
+                    z, m_q, logs_q, y_mask = net.enc_q(y, y_len, g=None)
+                    noise = cap["noise"][0]
+        finally:
+            torch.randn_like = _randn_like
+        assert torch.equal((m_q + noise * torch.exp(logs_q)) * y_mask, z), "noise capture failed"
+        g_s_t = torch.from_numpy(out["g_src"]) if "g_src" in out else None
+        zo, mo, lo, _ = orc.posterior_encoder(sd, cfg, y, y_len, g_s_t, noise)
+        print(f"{name:16s} oracle-vs-ref: z {(zo - z).abs().max():.2e} m {(mo - m_q).abs().max():.2e} logs {(lo - logs_q).abs().max():.2e}")
+        if "o" in out:
+            oo = orc.voice_conversion(sd, cfg, y, y_len, g_s_t, torch.from_numpy(out["g_tgt"]), noise)[0]
+            print(f"{'':16s} voice conversion wav oracle-vs-ref {orc.max_abs_over_peak(oo, torch.from_numpy(out['o'])):.2e}")
+        out.update(y=y.numpy(), y_lengths=y_len.numpy(), noise=noise.numpy(), z=z.numpy(), m=m_q.numpy(), logs=logs_q.numpy(),
+                   y_mask=y_mask.numpy())
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "prior":
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import mbistft_oracle as _orc
         mint_prior_cases(import_reference(), _orc)
+    elif len(sys.argv) > 1 and sys.argv[1] == "vc":
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import mbistft_oracle as _orc
+        mint_vc_cases(import_reference(), _orc)
     elif len(sys.argv) > 1 and sys.argv[1] == "infer":
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import mbistft_oracle as _orc
