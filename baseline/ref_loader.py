@@ -97,7 +97,7 @@ def build_synthesizer(cfg, sd, device="cpu"):
     models = import_reference()
     net = models.SynthesizerTrn(59, 513, 32, **model_kwargs(cfg)).eval()
     ref_sd = net.state_dict()
-    pre = ("dec.", "flow.", "emb_g.") + (("enc_q.",) if any(k.startswith("enc_q.") for k in sd) else ())
+    pre = ("dec.", "flow.", "emb_g.") + tuple(p for p in ("enc_q.", "enc_p.") if any(k.startswith(p) for k in sd))
     want = {k for k in ref_sd if k.startswith(pre)}
     have = {k for k in sd if k.startswith(pre)}
     assert want == have, f"key inventory mismatch: missing {sorted(want - have)[:5]} extra {sorted(have - want)[:5]}"

@@ -85,6 +85,7 @@ typedef struct {
   int32_t flags;                    /* MBV_FLAG_* */
 } mbv_config;
 
+#define MBV_MAX_TEXT_LAYERS 12     /* text encoder depth (configs: n_layers 6; 3 in the mini configs) */
 #define MBV_MAX_ENCQ_LAYERS 16     /* PosteriorEncoder WN depth (models.py:646) */
 
 /* debug / tuning flags */
@@ -149,6 +150,16 @@ int mbv_flow_forward(mbv_handle* h, const float* x, const float* y_mask, const f
 int mbv_posterior_workspace_bytes(mbv_handle* h, int32_t B, int32_t T, size_t* bytes);
 int mbv_posterior_encode(mbv_handle* h, const float* spec, const float* y_mask, const float* g, const float* noise,
                          float* z, float* stats, int32_t B, int32_t T, void* ws, size_t ws_bytes, void* stream);
+
+/* NEXT-row widening: TextEncoder.forward (models.py:172-181) -- embedding * sqrt(H), n_layers x
+ * [relative-position windowed self-attention (attentions.py:101-254, window 4, shared embeddings), LayerNorm, k=3 conv
+ * FFN with ReLU (attentions.py:257-303), LayerNorm], proj.  Available when mbv_load_weights received the enc_p.* tensors
+ * (geometry is read off their shapes), else MBV_ERR_WEIGHTS.  tokens: [B, Tx] int64 (device); x_mask: [B,1,Tx] (the
+ * caller builds it from the lengths like commons.sequence_mask); x_out: [B, hidden, Tx]; stats: [B, 2*inter, Tx] = m | logs.
+ * The projections and FFN convs run on the conv kernels at the handle's precision; attention and LayerNorm in fp32. */
+int mbv_text_workspace_bytes(mbv_handle* h, int32_t B, int32_t Tx, size_t* bytes);
+int mbv_text_encode(mbv_handle* h, const int64_t* tokens, const float* x_mask, float* x_out, float* stats, int32_t B,
+                    int32_t Tx, void* ws, size_t ws_bytes, void* stream);
 
 /* dec.forward(z, g) (models.py:278-297 / 344-377 / 430-467).  z: [B, inter, T]; wav: [B,1,S*T]
  * with S = samples per latent frame (256).  Optional outputs (NULL to skip):

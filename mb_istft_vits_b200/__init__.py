@@ -13,7 +13,7 @@ def __getattr__(name):
     if name in ("Engine", "fold_weight_norm"):
         from . import engine
         return getattr(engine, name)
-    if name in ("NativeFlow", "NativeDecoder", "NativePosteriorEncoder", "patch_synthesizer", "infer_native"):
+    if name in ("NativeFlow", "NativeDecoder", "NativePosteriorEncoder", "NativeTextEncoder", "patch_synthesizer", "infer_native"):
         from . import modules
         return getattr(modules, name)
     if name == "StreamingDecoder":

@@ -82,4 +82,12 @@ cudaError_t launch_expand_prior(const float* m_p, const float* logs_p, const flo
                                 float* y_mask, float* m_exp, float* logs_exp, float* attn, long long* y_lengths,
                                 cudaStream_t st);
 
+// ---- text.cu (text encoder helpers; ld = channel pitch of the operand copies)
+cudaError_t launch_text_embed(const long long* tokens, const float* emb, const float* mask, float* x, void* xop, int n_rows, int C,
+                              int ld_op, int n_vocab, int prec, cudaStream_t st);
+cudaError_t launch_text_ln(const float* x, const float* y, int y_ld, const float* gamma, const float* beta, const float* mask,
+                           float* x_out, void* xop, int n_rows, int C, int ld_op, int mask_out, int prec, cudaStream_t st);
+cudaError_t launch_text_attention(const float* qkv, const float* mask, const float* rel_k, const float* rel_v, void* out, int B,
+                                  int T, int C, int ld_op, int n_heads, int W, int prec, cudaStream_t st);
+
 }  // namespace mbv

@@ -131,6 +131,16 @@ struct mbv_handle {
   float* eq_cond_w = nullptr;
   float* eq_cond_b = nullptr;
 
+  // text encoder (models.py:140-181; optional: loaded when the state-dict carries enc_p.*).  Geometry is read off the
+  // tensors: layers = number of attn_layers, heads = hidden / emb_rel_k.shape[2], window = (emb_rel_k.shape[1] - 1) / 2
+  bool has_enc_p = false;
+  int tp_layers = 0, tp_heads = 0, tp_window = 0, tp_filter = 0, tp_vocab = 0;
+  float* tp_emb = nullptr;
+  ConvLayer tp_qkv[MBV_MAX_TEXT_LAYERS], tp_o[MBV_MAX_TEXT_LAYERS], tp_f1[MBV_MAX_TEXT_LAYERS], tp_f2[MBV_MAX_TEXT_LAYERS], tp_proj;
+  float* tp_relk[MBV_MAX_TEXT_LAYERS] = {nullptr};
+  float* tp_relv[MBV_MAX_TEXT_LAYERS] = {nullptr};
+  float* tp_ln[MBV_MAX_TEXT_LAYERS][4] = {{nullptr}};  // gamma1, beta1, gamma2, beta2
+
   // tensor-map cache: valid while (B, T, ws) stay the same
   struct PlanKey { int B, T; void* ws; int kind; bool operator<(const PlanKey& o) const {
     if (B != o.B) return B < o.B; if (T != o.T) return T < o.T; if (ws != o.ws) return ws < o.ws; return kind < o.kind; } };
@@ -700,6 +710,75 @@ extern "C" int mbv_load_weights(mbv_handle* h, const mbv_tensor* tensors, int32_
     if (rc) return rc;
     h->has_enc_q = true;
   }
+  // ---------------- text encoder (optional)
+  if (m.count("enc_p.emb.weight")) {
+    const HostTensor& ew = m["enc_p.emb.weight"];
+    if (ew.shape.size() != 2 || ew.shape[1] != h->H) return fail(h, MBV_ERR_WEIGHTS, "enc_p.emb.weight has the wrong shape");
+    const int H = h->H, Hp = h->Hp;
+    h->tp_vocab = (int)ew.shape[0];
+    if ((rc = upload_f32(h, ew.data, &h->tp_emb))) return rc;
+    int NL = 0;
+    char pfx[128];
+    for (;; ++NL) { snprintf(pfx, sizeof(pfx), "enc_p.encoder.attn_layers.%d.conv_q.weight", NL); if (!m.count(pfx)) break; }
+    if (NL < 1 || NL > MBV_MAX_TEXT_LAYERS) return fail(h, MBV_ERR_UNSUPPORTED, "enc_p: %d encoder layers (1..%d supported)", NL, MBV_MAX_TEXT_LAYERS);
+    h->tp_layers = NL;
+    for (int l = 0; l < NL; ++l) {
+      snprintf(pfx, sizeof(pfx), "enc_p.encoder.attn_layers.%d", l);
+      const std::string a(pfx);
+      auto rk = m.find(a + ".emb_rel_k"), rv = m.find(a + ".emb_rel_v");
+      if (rk == m.end() || rv == m.end() || rk->second.shape.size() != 3 || rk->second.shape[0] != 1 || rk->second.shape != rv->second.shape)
+        return fail(h, MBV_ERR_UNSUPPORTED, "%s: shared relative embeddings [1, 2w+1, dk] expected", pfx);
+      const int dk = (int)rk->second.shape[2], win = ((int)rk->second.shape[1] - 1) / 2;
+      if (dk < 4 || dk > 128 || (dk & 3) || H % dk != 0) return fail(h, MBV_ERR_UNSUPPORTED, "%s: head width %d not supported", pfx, dk);
+      if (l == 0) { h->tp_heads = H / dk; h->tp_window = win; }
+      else if (h->tp_heads != H / dk || h->tp_window != win) return fail(h, MBV_ERR_WEIGHTS, "%s: inconsistent attention geometry", pfx);
+      if ((rc = upload_f32(h, rk->second.data, &h->tp_relk[l]))) return rc;
+      if ((rc = upload_f32(h, rv->second.data, &h->tp_relv[l]))) return rc;
+      // q | k | v as ONE 1x1 conv with 3H output rows
+      HostTensor qw, qb;
+      qw.shape = {3 * H, H, 1};
+      qb.shape = {3 * H};
+      const char* names[3] = {".conv_q", ".conv_k", ".conv_v"};
+      for (int j = 0; j < 3; ++j) {
+        const int64_t ws[3] = {H, H, 1}, bs[1] = {H};
+        const HostTensor* w = find_tensor(h, m, a + names[j] + ".weight", 3, ws);
+        const HostTensor* b = w ? find_tensor(h, m, a + names[j] + ".bias", 1, bs) : nullptr;
+        if (!w || !b) return MBV_ERR_WEIGHTS;
+        qw.data.insert(qw.data.end(), w->data.begin(), w->data.end());
+        qb.data.insert(qb.data.end(), b->data.begin(), b->data.end());
+      }
+      TensorMap fused;
+      fused["qkv.weight"] = std::move(qw);
+      fused["qkv.bias"] = std::move(qb);
+      rc = pack_conv1d(h, fused, "qkv", 3 * H, H, 1, 1, iota_pad(3 * H, round_up(3 * H, 128)), iota_pad(H, Hp), true, 0, &h->tp_qkv[l]);
+      if (rc) return rc;
+      rc = pack_conv1d(h, m, a + ".conv_o", H, H, 1, 1, iota_pad(H, round_up(H, 128)), iota_pad(H, Hp), true, 0, &h->tp_o[l]);
+      if (rc) return rc;
+      snprintf(pfx, sizeof(pfx), "enc_p.encoder.ffn_layers.%d.conv_1.weight", l);
+      auto f1 = m.find(pfx);
+      if (f1 == m.end() || f1->second.shape.size() != 3) return fail(h, MBV_ERR_WEIGHTS, "missing tensor %s", pfx);
+      const int F = (int)f1->second.shape[0], ks = (int)f1->second.shape[2];
+      if (F % 64 != 0 || (ks & 1) == 0) return fail(h, MBV_ERR_UNSUPPORTED, "enc_p FFN: filter_channels %d must be a multiple of 64, kernel %d odd", F, ks);
+      h->tp_filter = F;
+      snprintf(pfx, sizeof(pfx), "enc_p.encoder.ffn_layers.%d", l);
+      rc = pack_conv1d(h, m, std::string(pfx) + ".conv_1", F, H, ks, 1, iota_pad(F, round_up(F, 128)), iota_pad(H, Hp), true, 0, &h->tp_f1[l]);
+      if (rc) return rc;
+      rc = pack_conv1d(h, m, std::string(pfx) + ".conv_2", H, F, ks, 1, iota_pad(H, round_up(H, 128)), iota_pad(F, F), true, 0, &h->tp_f2[l]);
+      if (rc) return rc;
+      const char* ln[4] = {"norm_layers_1.%d.gamma", "norm_layers_1.%d.beta", "norm_layers_2.%d.gamma", "norm_layers_2.%d.beta"};
+      for (int j = 0; j < 4; ++j) {
+        char nm[128];
+        snprintf(nm, sizeof(nm), ln[j], l);
+        const int64_t vs[1] = {H};
+        const HostTensor* v = find_tensor(h, m, std::string("enc_p.encoder.") + nm, 1, vs);
+        if (!v) return MBV_ERR_WEIGHTS;
+        if ((rc = upload_f32(h, v->data, &h->tp_ln[l][j]))) return rc;
+      }
+    }
+    rc = pack_conv1d(h, m, "enc_p.proj", 2 * h->Cz, H, 1, 1, iota_pad(2 * h->Cz, round_up(2 * h->Cz, 128)), iota_pad(H, Hp), true, 0, &h->tp_proj);
+    if (rc) return rc;
+    h->has_enc_p = true;
+  }
   h->weights_loaded = true;
   return MBV_OK;
 }
@@ -1004,6 +1083,88 @@ int run_posterior(Ctx& cx, const PostBufs& p, const float* spec, const float* ma
     ProfScope prof(cx, 2);
     CUDA_TRY(h, launch_unpack_output(p.stats, stats_out, B, 2 * h->Cz, T, 2 * h->Cz, cx.st));
     CUDA_TRY(h, launch_posterior_sample(stats_out, noise, mask, z_out, B, h->Cz, T, cx.st));
+    cx.launches += 2;
+  }
+  return MBV_OK;
+}
+
+struct TextBufs { float* x; void* xop; float* qkv; void* att; float* y; void* hid; float* stats; };
+
+void layout_text(mbv_handle* h, Arena& A, int B, int T, TextBufs* t) {
+  const int es = h->esize;
+  const size_t n = (size_t)B * T;
+  t->x = (float*)A.take(n * h->H * 4);
+  t->xop = A.take(n * h->Hp * es);
+  t->qkv = (float*)A.take(n * 3 * h->H * 4);
+  t->att = A.take(n * h->Hp * es);
+  t->y = (float*)A.take(n * h->H * 4);
+  t->hid = A.take(n * h->tp_filter * es);
+  t->stats = (float*)A.take(n * 2 * h->Cz * 4);
+}
+
+// TextEncoder.forward (models.py:172-181) + attentions.Encoder.forward (attentions.py:35-47)
+int run_text(Ctx& cx, const TextBufs& t, const long long* tokens, const float* mask, float* x_out, float* stats_out, int B, int T) {
+  mbv_handle* h = cx.h;
+  const int H = h->H, Hp = h->Hp, F = h->tp_filter, rows = B * T;
+  int rc;
+  {
+    ProfScope prof(cx, 2);
+    // pad channels [H, Hp) of the operand copies are never written below: keep them zero (their weight columns are zero,
+    // but 0 x NaN is not)
+    if (Hp != H) {
+      CUDA_TRY(h, cudaMemsetAsync(t.xop, 0, (size_t)rows * Hp * h->esize, cx.st));
+      CUDA_TRY(h, cudaMemsetAsync(t.att, 0, (size_t)rows * Hp * h->esize, cx.st));
+    }
+    CUDA_TRY(h, launch_text_embed(tokens, h->tp_emb, mask, t.x, t.xop, rows, H, Hp, h->tp_vocab, h->prec, cx.st));
+    cx.launches++;
+  }
+  for (int l = 0; l < h->tp_layers; ++l) {
+    {  // q | k | v = 1x1 convs of x -> fp32 [B][T][3H]
+      EpiParams e = epi_base(EPI_ACT, 3 * H, T);
+      e.xout = t.qkv; e.n_act = 0;
+      if ((rc = run_conv(cx, h->tp_qkv[l], t.xop, B, T, T, e))) return rc;
+    }
+    {
+      ProfScope prof(cx, 2);
+      CUDA_TRY(h, launch_text_attention(t.qkv, mask, h->tp_relk[l], h->tp_relv[l], t.att, B, T, H, Hp, h->tp_heads, h->tp_window, h->prec, cx.st));
+      cx.launches++;
+    }
+    {  // y = conv_o(attention)
+      EpiParams e = epi_base(EPI_ACT, H, T);
+      e.xout = t.y; e.n_act = 0;
+      if ((rc = run_conv(cx, h->tp_o[l], t.att, B, T, T, e))) return rc;
+    }
+    {
+      ProfScope prof(cx, 2);
+      CUDA_TRY(h, launch_text_ln(t.x, t.y, H, h->tp_ln[l][0], h->tp_ln[l][1], mask, t.x, t.xop, rows, H, Hp, 0, h->prec, cx.st));
+      cx.launches++;
+    }
+    {  // FFN: relu(conv_1(x * mask)) * mask -> operand
+      EpiParams e = epi_base(EPI_ACT, F, T);
+      e.mask = mask; e.slope = 0.f; e.act[0] = t.hid; e.n_act = 1;
+      if ((rc = run_conv(cx, h->tp_f1[l], t.xop, B, T, T, e))) return rc;
+    }
+    {  // y = conv_2(.) * mask
+      EpiParams e = epi_base(EPI_ACT, H, T);
+      e.mask = mask; e.xout = t.y; e.n_act = 0;
+      if ((rc = run_conv(cx, h->tp_f2[l], t.hid, B, T, T, e))) return rc;
+    }
+    {
+      ProfScope prof(cx, 2);
+      const int last = (l == h->tp_layers - 1) ? 1 : 0;  // x = x * x_mask after the last layer (attentions.py:46)
+      CUDA_TRY(h, launch_text_ln(t.x, t.y, H, h->tp_ln[l][2], h->tp_ln[l][3], mask, t.x, t.xop, rows, H, Hp, last, h->prec, cx.st));
+      cx.launches++;
+    }
+  }
+  {  // stats = proj(x) * mask
+    EpiParams e = epi_base(EPI_ACT, 2 * h->Cz, T);
+    e.mask = mask; e.xout = t.stats; e.n_act = 0;
+    if ((rc = run_conv(cx, h->tp_proj, t.xop, B, T, T, e))) return rc;
+  }
+  {
+    ProfScope prof(cx, 2);
+    CUDA_TRY(h, launch_unpack_output(t.x, x_out, B, H, T, H, cx.st));
+    CUDA_TRY(h, launch_unpack_output(t.stats, stats_out, B, 2 * h->Cz, T, 2 * h->Cz, cx.st));
     cx.launches += 2;
   }
   return MBV_OK;
@@ -1347,6 +1508,39 @@ extern "C" int mbv_posterior_encode(mbv_handle* h, const float* spec, const floa
   layout_posterior(h, A, B, T, &p);
   Ctx cx = make_ctx(h, B, T, ws, g ? 9 : 8, stream);
   rc = run_posterior(cx, p, spec, y_mask, g, noise, z, stats, B, T);
+  if (rc) { cx.plans->clear(); return rc; }
+  h->last_launches = cx.launches;
+  return MBV_OK;
+}
+
+extern "C" int mbv_text_workspace_bytes(mbv_handle* h, int32_t B, int32_t T, size_t* bytes) {
+  if (!h || !bytes) return MBV_ERR_INVALID;
+  if (!h->has_enc_p) return fail(h, MBV_ERR_WEIGHTS, "no enc_p.* weights were loaded");
+  if (B < 1 || T < 1) return fail(h, MBV_ERR_INVALID, "B and T must be >= 1");
+  Arena A(nullptr);
+  TextBufs t;
+  layout_text(h, A, B, T, &t);
+  *bytes = A.off + 1024;
+  return MBV_OK;
+}
+
+extern "C" int mbv_text_encode(mbv_handle* h, const int64_t* tokens, const float* x_mask, float* x_out, float* stats, int32_t B,
+                               int32_t T, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_ready(h, B, T);
+  if (rc) return rc;
+  if (!h->has_enc_p) return fail(h, MBV_ERR_WEIGHTS, "no enc_p.* weights were loaded");
+  if (!tokens || !x_mask || !x_out || !stats) return fail(h, MBV_ERR_INVALID, "null tensor");
+  if (T > 2048) return fail(h, MBV_ERR_UNSUPPORTED, "mbv_text_encode: more than 2048 tokens per utterance");
+  size_t need = 0;
+  mbv_text_workspace_bytes(h, B, T, &need);
+  if (!ws || ((uintptr_t)ws & 1023) != 0) return fail(h, MBV_ERR_WORKSPACE, "workspace must be non-null and 1024-byte aligned");
+  if (ws_bytes < need) return fail(h, MBV_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+  DEVICE_GUARD(h);
+  Arena A(ws);
+  TextBufs t;
+  layout_text(h, A, B, T, &t);
+  Ctx cx = make_ctx(h, B, T, ws, 12, stream);
+  rc = run_text(cx, t, (const long long*)tokens, x_mask, x_out, stats, B, T);
   if (rc) { cx.plans->clear(); return rc; }
   h->last_launches = cx.launches;
   return MBV_OK;

@@ -14,7 +14,7 @@ from . import lib as _lib
 from .configs import receptive_field_frames, samples_per_frame
 
 
-def fold_weight_norm(sd: Dict[str, torch.Tensor], prefixes=("dec.", "flow.", "enc_q.")) -> Dict[str, torch.Tensor]:
+def fold_weight_norm(sd: Dict[str, torch.Tensor], prefixes=("dec.", "flow.", "enc_q.", "enc_p.")) -> Dict[str, torch.Tensor]:
     """Reference checkpoint layout -> effective fp32 weights: w = g * v / ||v|| with the norm
     over all dims but 0 (torch.nn.utils.weight_norm, dim=0; for ConvTranspose1d dim 0 = in-channels).
     Keys already stored as plain ``weight`` (after remove_weight_norm) pass through."""
@@ -200,6 +200,23 @@ class Engine:
         self._check(self.lib.mbv_flow_forward(self._h, self._ptr(x), self._ptr(y_mask), self._ptr(g), self._ptr(out),
                                               B, T, C.c_void_p(ws), nws, self._stream()))
         return out
+
+    def text_encode(self, tokens, x_lengths):
+        """TextEncoder.forward (models.py:172-181) on the library: tokens [B, Tx] int64, lengths [B] ->
+        (x [B,H,Tx], m_p [B,inter,Tx], logs_p [B,inter,Tx], x_mask [B,1,Tx]).  Needs the enc_p.* weights."""
+        tokens = torch.as_tensor(tokens).to(device=self.device, dtype=torch.int64).contiguous()
+        B, Tx = tokens.shape
+        lens = torch.as_tensor(x_lengths).to(self.device)
+        x_mask = (torch.arange(Tx, device=self.device)[None, :] < lens[:, None]).to(torch.float32).unsqueeze(1)  # commons.sequence_mask
+        inter, hid = self.cfg["inter_channels"], self.cfg["hidden_channels"]
+        x = torch.empty((B, hid, Tx), dtype=torch.float32, device=self.device)
+        stats = torch.empty((B, 2 * inter, Tx), dtype=torch.float32, device=self.device)
+        n = C.c_size_t()
+        self._check(self.lib.mbv_text_workspace_bytes(self._h, B, Tx, C.byref(n)))
+        ws, nws = self._workspace(B, Tx, need=max(n.value, self.workspace_capacity()))
+        self._check(self.lib.mbv_text_encode(self._h, C.c_void_p(tokens.data_ptr()), self._ptr(x_mask), self._ptr(x), self._ptr(stats),
+                                             B, Tx, C.c_void_p(ws), nws, self._stream()))
+        return x, stats[:, :inter], stats[:, inter:], x_mask
 
     def posterior_encode(self, spec, y_lengths=None, g=None, noise=None, y_mask=None):
         """PosteriorEncoder.forward (models.py:236-246) on the library: spec [B, spec_channels, T], lengths [B] (or a ready

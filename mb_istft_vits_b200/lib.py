@@ -32,7 +32,8 @@ SYMBOLS = ["mbv_abi_version", "mbv_create", "mbv_destroy", "mbv_load_weights", "
            "mbv_flow_reverse", "mbv_decode", "mbv_flow_decode", "mbv_last_launch_count", "mbv_decode_flops",
            "mbv_flow_flops", "mbv_tail", "mbv_last_error", "mbv_set_profiling", "mbv_profile_read", "mbv_profile_read_launches", "mbv_pcm16", "mbv_expand_prior", "mbv_flow_forward",
            "mbv_posterior_workspace_bytes", "mbv_posterior_encode", "mbv_receptive_field", "mbv_stream_open",
-           "mbv_stream_workspace_bytes", "mbv_stream_halo", "mbv_stream_push", "mbv_stream_close"]
+           "mbv_stream_workspace_bytes", "mbv_stream_halo", "mbv_stream_push", "mbv_stream_close",
+           "mbv_text_workspace_bytes", "mbv_text_encode"]
 
 
 class MbvConfig(C.Structure):
@@ -96,6 +97,8 @@ def load():
     lib.mbv_expand_prior.argtypes = [vp, fp, fp, fp, fp, fp, C.c_float, i32, i32, i32, i32, fp, fp, fp, fp, fp, vp, vp]
     lib.mbv_posterior_workspace_bytes.argtypes = [vp, i32, i32, C.POINTER(C.c_size_t)]
     lib.mbv_posterior_encode.argtypes = [vp, fp, fp, fp, fp, fp, fp, i32, i32, vp, C.c_size_t, vp]
+    lib.mbv_text_workspace_bytes.argtypes = [vp, i32, i32, C.POINTER(C.c_size_t)]
+    lib.mbv_text_encode.argtypes = [vp, vp, fp, fp, fp, i32, i32, vp, C.c_size_t, vp]
     lib.mbv_receptive_field.argtypes = [vp]
     lib.mbv_stream_open.argtypes = [vp, i32, i32, C.POINTER(vp)]
     lib.mbv_stream_workspace_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]

@@ -57,6 +57,18 @@ class NativeDecoder(nn.Module):
         """Weight-norm is folded at load time; nothing to do (reference: models.py:299/379/469)."""
 
 
+class NativeTextEncoder(nn.Module):
+    """TextEncoder.forward (models.py:172-181): (x, x_lengths) -> (x, m, logs, x_mask)."""
+
+    def __init__(self, engine: Engine):
+        super().__init__()
+        self.engine = engine
+
+    @torch.no_grad()
+    def forward(self, x, x_lengths):
+        return self.engine.text_encode(x, x_lengths)
+
+
 class NativePosteriorEncoder(nn.Module):
     """PosteriorEncoder.forward (models.py:236-246): (x, x_lengths, g=None) -> (z, m, logs, x_mask).  Used by
     ``SynthesizerTrn.voice_conversion`` (models.py:794); with it the whole conversion path runs on the library."""
@@ -110,14 +122,19 @@ def infer_native(net_g, engine, x, x_lengths, sid=None, noise_scale=1, length_sc
     return o, o_mb, spec, phase, attn, y_mask, (z, z_p, stats[0], stats[1]), timings
 
 
-def patch_synthesizer(net_g, cfg, precision="bf16", device=0, flags=0, residual=None, posterior=False):
+def patch_synthesizer(net_g, cfg, precision="bf16", device=0, flags=0, residual=None, posterior=False, text=False):
     """Replace net_g.flow and net_g.dec by the native path, using net_g's own weights.  posterior=True also replaces
-    net_g.enc_q (PosteriorEncoder), so that ``net_g.voice_conversion`` (models.py:790-798) runs entirely on the library."""
-    keep = ("dec.", "flow.", "enc_q.") if posterior else ("dec.", "flow.")
+    net_g.enc_q (PosteriorEncoder), so that ``net_g.voice_conversion`` (models.py:790-798) runs entirely on the library;
+    text=True also replaces net_g.enc_p (TextEncoder).  Mind that a 16-bit text encoder can move a predicted duration
+    across a ceil() boundary (models.py:717-718) and so change the utterance length; use 'tf32' / 'fp32' when the
+    durations must match the reference exactly."""
+    keep = ("dec.", "flow.") + (("enc_q.",) if posterior else ()) + (("enc_p.",) if text else ())
     sd = {k: v for k, v in net_g.state_dict().items() if k.startswith(keep)}
     eng = Engine(cfg, sd, precision=precision, device=device, flags=flags, residual=residual)
     net_g.flow = NativeFlow(eng)
     net_g.dec = NativeDecoder(eng)
     if posterior:
         net_g.enc_q = NativePosteriorEncoder(eng)
+    if text:
+        net_g.enc_p = NativeTextEncoder(eng)
     return eng

@@ -41,7 +41,7 @@ def _plain_conv(sd, gen, name, shape, fan_in):
 
 
 def make_state_dict(cfg, seed: int = 1234, g_scale: float = 1.0, enc_q: bool = False, spec_channels: int = 513,
-                    enc_q_layers: int = 16) -> Dict[str, torch.Tensor]:
+                    enc_q_layers: int = 16, enc_p: bool = False, n_vocab: int = 59) -> Dict[str, torch.Tensor]:
     gen = torch.Generator().manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
     inter, hid, gin = cfg["inter_channels"], cfg["hidden_channels"], cfg["gin_channels"]
@@ -109,6 +109,28 @@ def make_state_dict(cfg, seed: int = 1234, g_scale: float = 1.0, enc_q: bool = F
             rs = 2 * hid if l < enc_q_layers - 1 else hid
             _wn_conv(sd, gen, f"enc_q.enc.res_skip_layers.{l}", (rs, hid, 1), hid, g_scale)
         _plain_conv(sd, gen, "enc_q.proj", (2 * inter, hid, 1), hid)
+
+    # ---- text encoder (models.py:140-181; attentions.py:13-47): the reference builds it with n_heads 2, kernel 3,
+    # window 4 and filter_channels / n_layers from the config (768 / 6; 384 / 3 for the mini configs).  Initial
+    # distributions as in the reference constructors; LayerNorm gains / offsets are perturbed so that they matter.
+    if enc_p:
+        filt, n_layers, n_heads, ks, win = (768, 6, 2, 3, 4) if hid == 192 else (384, 3, 2, 3, 4)
+        dk = hid // n_heads
+        sd["enc_p.emb.weight"] = torch.randn((n_vocab, hid), generator=gen) * hid ** -0.5
+        for i in range(n_layers):
+            a = f"enc_p.encoder.attn_layers.{i}"
+            sd[a + ".emb_rel_k"] = torch.randn((1, 2 * win + 1, dk), generator=gen) * dk ** -0.5
+            sd[a + ".emb_rel_v"] = torch.randn((1, 2 * win + 1, dk), generator=gen) * dk ** -0.5
+            for n in ("conv_q", "conv_k", "conv_v", "conv_o"):
+                bound = math.sqrt(6.0 / (2 * hid)) if n != "conv_o" else 1.0 / math.sqrt(hid)   # xavier_uniform / default
+                sd[f"{a}.{n}.weight"] = _uniform(gen, (hid, hid, 1), bound)
+                sd[f"{a}.{n}.bias"] = _uniform(gen, (hid,), 1.0 / math.sqrt(hid))
+            for j in (1, 2):
+                sd[f"enc_p.encoder.norm_layers_{j}.{i}.gamma"] = 1.0 + 0.1 * torch.randn((hid,), generator=gen)
+                sd[f"enc_p.encoder.norm_layers_{j}.{i}.beta"] = 0.1 * torch.randn((hid,), generator=gen)
+            _plain_conv(sd, gen, f"enc_p.encoder.ffn_layers.{i}.conv_1", (filt, hid, ks), hid * ks)
+            _plain_conv(sd, gen, f"enc_p.encoder.ffn_layers.{i}.conv_2", (hid, filt, ks), filt * ks)
+        _plain_conv(sd, gen, "enc_p.proj", (2 * inter, hid, 1), hid)
     return sd
 
 

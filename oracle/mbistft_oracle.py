@@ -150,6 +150,81 @@ def voice_conversion(sd, cfg, y, y_lengths, g_src, g_tgt, noise):
 
 
 # ----------------------------------------------------------------------------
+# text encoder: models.py:140-181, attentions.py:13-47 (Encoder), 101-254 (MultiHeadAttention), 257-303 (FFN),
+# modules.py:20-33 (LayerNorm)
+# ----------------------------------------------------------------------------
+def _layer_norm_channels(x, gamma, beta, eps=1e-5):
+    """modules.LayerNorm: normalise over the channel axis of [B, C, T]."""
+    mean = x.mean(1, keepdim=True)
+    var = ((x - mean) ** 2).mean(1, keepdim=True)
+    return (x - mean) * torch.rsqrt(var + eps) * gamma.view(1, -1, 1) + beta.view(1, -1, 1)
+
+
+def relative_attention(q, k, v, mask, emb_rel_k, emb_rel_v, n_heads, window=4):
+    """MultiHeadAttention.attention with window_size=4, heads_share=True (attentions.py:142-178): scores = q k^T / sqrt(dk)
+    plus the relative-key logits q . E_k[j - i] for |j - i| <= window, masked_fill(mask == 0, -1e4), softmax, p v plus the
+    relative-value term sum_r p[i, i + r] E_v[r].  q, k, v: [B, C, T]; mask: [B, 1, T] (1 = valid)."""
+    B, C, T = q.shape
+    dk = C // n_heads
+    qh = q.view(B, n_heads, dk, T).transpose(2, 3) / math.sqrt(dk)
+    kh = k.view(B, n_heads, dk, T).transpose(2, 3)
+    vh = v.view(B, n_heads, dk, T).transpose(2, 3)
+    scores = qh @ kh.transpose(-2, -1)                                   # [B, H, T, T]
+    idx = torch.arange(T)
+    rel = idx[None, :] - idx[:, None]                                    # rel[i, j] = j - i
+    inside = rel.abs() <= window
+    e_k = emb_rel_k[0]                                                   # [2w+1, dk]
+    rel_logits = qh @ e_k.t()                                            # [B, H, T, 2w+1]
+    gathered = torch.gather(rel_logits, 3, (rel.clamp(-window, window) + window).expand(B, n_heads, T, T))
+    scores = scores + gathered * inside
+    amask = mask.unsqueeze(2) * mask.unsqueeze(-1)                       # [B, 1, T, T]
+    scores = scores.masked_fill(amask == 0, -1e4)
+    p = F.softmax(scores, dim=-1)
+    out = p @ vh
+    e_v = emb_rel_v[0]
+    for r in range(-window, window + 1):                                  # sum_r p[i, i + r] E_v[r]
+        i0, i1 = max(0, -r), min(T, T - r)
+        if i1 > i0:
+            pr = p[:, :, torch.arange(i0, i1), torch.arange(i0 + r, i1 + r)]   # [B, H, n]
+            out[:, :, i0:i1] = out[:, :, i0:i1] + pr.unsqueeze(-1) * e_v[r + window]
+    return out.transpose(2, 3).contiguous().view(B, C, T)
+
+
+def text_encoder(sd, x_tokens, x_lengths, prefix="enc_p", n_heads=2, window=4):
+    """TextEncoder.forward (models.py:172-181): embedding * sqrt(H), mask, n_layers x [x = LN(x + attn(x));
+    x = LN(x + FFN(x))] (attentions.py:35-47), x * mask, stats = proj(x) * mask.  Returns (x, m, logs, x_mask)."""
+    emb = sd[prefix + ".emb.weight"].float()
+    H = emb.shape[1]
+    T = x_tokens.shape[1]
+    mask = (torch.arange(T)[None, :] < torch.as_tensor(x_lengths)[:, None]).float().unsqueeze(1)
+    x = (emb[x_tokens] * math.sqrt(H)).transpose(1, 2) * mask
+    e = prefix + ".encoder"
+    n_layers = 0
+    while f"{e}.attn_layers.{n_layers}.conv_q.weight" in sd:
+        n_layers += 1
+    w = lambda name: sd[name].float()
+    for i in range(n_layers):
+        a = f"{e}.attn_layers.{i}"
+        q = F.conv1d(x, w(a + ".conv_q.weight"), w(a + ".conv_q.bias"))
+        k = F.conv1d(x, w(a + ".conv_k.weight"), w(a + ".conv_k.bias"))
+        v = F.conv1d(x, w(a + ".conv_v.weight"), w(a + ".conv_v.bias"))
+        y = relative_attention(q, k, v, mask, w(a + ".emb_rel_k"), w(a + ".emb_rel_v"), n_heads, window)
+        y = F.conv1d(y, w(a + ".conv_o.weight"), w(a + ".conv_o.bias"))
+        x = _layer_norm_channels(x + y, w(f"{e}.norm_layers_1.{i}.gamma"), w(f"{e}.norm_layers_1.{i}.beta"))
+        f = f"{e}.ffn_layers.{i}"
+        ks = sd[f + ".conv_1.weight"].shape[2]
+        pad = ((ks - 1) // 2, ks // 2)
+        y = F.conv1d(F.pad(x * mask, pad), w(f + ".conv_1.weight"), w(f + ".conv_1.bias"))
+        y = torch.relu(y)
+        y = F.conv1d(F.pad(y * mask, pad), w(f + ".conv_2.weight"), w(f + ".conv_2.bias")) * mask
+        x = _layer_norm_channels(x + y, w(f"{e}.norm_layers_2.{i}.gamma"), w(f"{e}.norm_layers_2.{i}.beta"))
+    x = x * mask
+    stats = F.conv1d(x, w(prefix + ".proj.weight"), w(prefix + ".proj.bias")) * mask
+    C = stats.shape[1] // 2
+    return x, stats[:, :C], stats[:, C:], mask
+
+
+# ----------------------------------------------------------------------------
 # decoder body: models.py:278-293 / 344-365 / 430-453, modules.py:213-228, 251-262
 # ----------------------------------------------------------------------------
 def resblock(x, sd, prefix, kind, k, dils, g=None):

@@ -49,3 +49,15 @@ def load_vc_case(name):
     t = {k: torch.from_numpy(d[k]) for k in d.files}
     sd = synth.make_state_dict(cfg, seed=1234, enc_q=True)
     return cfg, sd, t
+
+
+# text-encoder cases (tools/make_golden.py text): name -> config name
+TEXT_CASES = {"text_mb": "ljs_mb_istft_vits", "text_mini": "ljs_mini_mb_istft_vits", "text_short": "ljs_mb_istft_vits"}
+
+
+def load_text_case(name):
+    cfg = cfgs.get_config(TEXT_CASES[name])
+    d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    t = {k: torch.from_numpy(d[k]) for k in d.files}
+    sd = synth.make_state_dict(cfg, seed=1234, enc_p=True)
+    return cfg, sd, t

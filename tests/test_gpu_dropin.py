@@ -137,3 +137,33 @@ def test_patched_voice_conversion_matches_reference_voice_conversion(prec):
         assert orc.snr_db(z.cpu(), z_r.cpu()) > 40.0
         assert orc.snr_db(o.cpu(), o_r.cpu()) > 40.0
     eng.close()
+
+
+def test_fully_native_infer_matches_reference_infer():
+    """patch_synthesizer(text=True): text encoder, flow and decoder on the library (the duration predictor stays the
+    reference module) against the unmodified model's infer() on the same GPU, fp32 path.  Durations come out of a ceil()
+    (models.py:717-718), so the lengths are compared first."""
+    import ref_loader
+    from mb_istft_vits_b200 import patch_synthesizer
+    if not ref_loader.available():
+        pytest.skip("reference not staged (python baseline/stage_ref.py)")
+    _gold_mode()
+    cfg = get_config("ljs_mini_mb_istft_vits")
+    sd = synth.make_state_dict(cfg, seed=1234, enc_p=True)
+    torch.manual_seed(31)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = ref_loader.build_synthesizer(cfg, sd, device="cuda")
+    x = torch.randint(1, 59, (2, 19), device="cuda")
+    x_len = torch.tensor([19, 12], device="cuda")
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        torch.manual_seed(6)
+        o_r, _, _, _, attn_r, ymask_r, (z_r, zp_r, mp_r, _), _ = net.infer(x, x_len, noise_scale=0.5)
+        eng = patch_synthesizer(net, cfg, precision="fp32", text=True)
+        assert type(net.enc_p).__name__ == "NativeTextEncoder"
+        torch.manual_seed(6)
+        o, _, _, _, attn, ymask, (z, zp, mp, _), _ = net.infer(x, x_len, noise_scale=0.5)
+        torch.cuda.synchronize()
+    assert torch.equal(ymask, ymask_r) and torch.equal(attn, attn_r), "a duration moved across a ceil() boundary"
+    assert (mp - mp_r).abs().max() < 1e-4 * max(1.0, float(mp_r.abs().max()))
+    assert orc.max_abs_over_peak(o.cpu(), o_r.cpu()) < 1e-3
+    eng.close()

@@ -665,3 +665,27 @@ def test_streaming_pcm_chunks_match_reference_arithmetic():
     assert np.array_equal(torch.cat(slices).numpy(), ref)
     sdec.close()
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# next-row widening: text encoder (models.py:140-181, attentions.py)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["text_mb", "text_mini", "text_short"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16"])
+def test_text_encoder_matches_reference(name, prec):
+    """mbv_text_encode against the reference's own enc_p output: fp32 path within 1e-4 of the largest activation, tf32
+    within 1e-3, bf16 >= 40 dB on x, m and logs; padded tokens exactly zero."""
+    from helpers import load_text_case
+    cfg, sd, t = load_text_case(name)
+    eng = _engine(cfg, sd, prec)
+    x, m, logs, mask = eng.text_encode(t["tokens"].cuda(), t["x_lengths"].cuda())
+    torch.cuda.synchronize()
+    x, m, logs = x.cpu(), m.cpu(), logs.cpu()
+    assert torch.equal(mask.cpu(), t["x_mask"])
+    assert float((x * (1 - t["x_mask"])).abs().max()) == 0.0 and float((m * (1 - t["x_mask"])).abs().max()) == 0.0
+    for got, ref in ((x, t["x"]), (m, t["m"]), (logs, t["logs"])):
+        if prec == "bf16":
+            assert orc.snr_db(got, ref) > 40.0
+        else:
+            assert (got - ref).abs().max() < (1e-4 if prec == "fp32" else 1e-3) * max(1.0, float(ref.abs().max()))
+    eng.close()

@@ -79,3 +79,13 @@ def test_oracle_posterior_encoder_and_voice_conversion_match_reference(name):
         o, _, _, (z2, z_p, z_hat) = orc.voice_conversion(sd, cfg, t["y"], t["y_lengths"], g, t["g_tgt"], t["noise"])
         assert (z_p - t["z_p"]).abs().max() < 2e-5 and (z_hat - t["z_hat"]).abs().max() < 2e-5
         assert orc.max_abs_over_peak(o, t["o"]) < 2e-5
+
+
+@pytest.mark.parametrize("name", ["text_mb", "text_mini", "text_short"])
+def test_oracle_text_encoder_matches_reference(name):
+    """TextEncoder.forward (models.py:172-181) against vectors minted from the reference's own enc_p."""
+    from helpers import load_text_case
+    cfg, sd, t = load_text_case(name)
+    x, m, logs, mask = orc.text_encoder(sd, t["tokens"], t["x_lengths"])
+    assert torch.equal(mask, t["x_mask"])
+    assert (x - t["x"]).abs().max() < 2e-5 and (m - t["m"]).abs().max() < 2e-5 and (logs - t["logs"]).abs().max() < 2e-5

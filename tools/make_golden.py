@@ -220,11 +220,34 @@ def mint_vc_cases(models, orc):
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
 
 
+def mint_text_cases(models, orc):
+    """Golden vectors for the text encoder (models.py:140-181): the reference's own enc_p on seeded enc_p.* weights
+    (synth.make_state_dict(enc_p=True)) and synthetic phoneme ids."""
+    for name, cname, B, Tx, lens in (("text_mb", "ljs_mb_istft_vits", 3, 37, [37, 20, 5]),
+                                     ("text_mini", "ljs_mini_mb_istft_vits", 2, 150, [150, 97]),
+                                     ("text_short", "ljs_mb_istft_vits", 2, 3, [3, 1])):
+        cfg = cfgs.get_config(cname)
+        sd = synth.make_state_dict(cfg, seed=1234, enc_p=True)
+        net = build_reference(models, cfg, sd)
+        tokens = torch.randint(0, 59, (B, Tx), generator=torch.Generator().manual_seed(12))
+        x_len = torch.tensor(lens)
+        with torch.no_grad():
+            x, m, logs, x_mask = net.enc_p(tokens, x_len)
+        xo, mo, lo, mk = orc.text_encoder(sd, tokens, x_len)
+        print(f"{name:12s} oracle-vs-ref: x {(xo - x).abs().max():.2e} m {(mo - m).abs().max():.2e} logs {(lo - logs).abs().max():.2e}")
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), tokens=tokens.numpy(), x_lengths=x_len.numpy(),
+                            x=x.numpy(), m=m.numpy(), logs=logs.numpy(), x_mask=x_mask.numpy())
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "prior":
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import mbistft_oracle as _orc
         mint_prior_cases(import_reference(), _orc)
+    elif len(sys.argv) > 1 and sys.argv[1] == "text":
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import mbistft_oracle as _orc
+        mint_text_cases(import_reference(), _orc)
     elif len(sys.argv) > 1 and sys.argv[1] == "vc":
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import mbistft_oracle as _orc
