@@ -94,6 +94,8 @@ typedef struct {
 #define MBV_FLAG_CLUSTER_PAIRS 32    /* experimental: run the multi-tap convs as clusters of two CTAs that work on two time tiles of the
                                      * same weight group; each CTA fetches half of every weight tile and TMA-multicasts it to both.
                                      * Parity-tested; < 1 % faster per step on B200, hence opt-in. */
+#define MBV_FLAG_SPLIT_TAIL 128     /* keep conv_post as its own conv launch writing fp32 logits for the stand-alone tail kernel instead
+                                     * of the fused conv_post + tail kernel (the default on the 16-bit paths; A/B and cross-check tests) */
 #define MBV_FLAG_BRANCHES 64         /* experimental: run the parallel ResBlocks of a stage on the library's two extra streams (own
                                      * residual / operand buffers per branch) so that one branch's launches fill the drain and
                                      * partial last round of another's.  Results identical; measured neutral (9.32-9.35 vs
@@ -220,6 +222,12 @@ int mbv_profile_read_launches(mbv_handle* h, float* ms, char* desc, int32_t desc
  * HBM-roofline benchmark of that kernel. */
 int mbv_tail(mbv_handle* h, const float* logits, float* wav, float* o_mb, float* spec, float* phase,
              int32_t B, int32_t T, void* stream);
+
+/* The fused conv_post + tail kernel alone (benchmarks / tests): act = the 16-bit operand tensor [B, 16T+1, C] that
+ * conv_post consumes (device; bf16 or fp16 per the handle's precision) -> same outputs as mbv_tail.  16-bit precisions and
+ * 4-band decoders only (else MBV_ERR_UNSUPPORTED). */
+int mbv_tail_fused(mbv_handle* h, const void* act, float* wav, float* o_mb, float* spec, float* phase, int32_t B, int32_t T,
+                   void* stream);
 
 /* NEXT-row widening: the waveform post-processing of the reference's TTS service
  * (tts_vits.py:204-216): per utterance, peak-normalise to 0.9 if auto_normalize and the peak exceeds 0.01, clip to

@@ -57,6 +57,10 @@ struct TailArgs {
   long long* dbg;       // MBV_TAIL_TIMELINE=1: CTA 0 / thread 0 clock stamps [tile < 8][8] (debug only)
 };
 cudaError_t launch_tail(const TailArgs& a, int precise, int num_sms, cudaStream_t st);
+// conv_post + tail in one kernel (tail.cu): act = the 16-bit operand tensor [B][L+1][C] the last ResBlock wrote (reflect-padded,
+// lrelu'd), w = conv_post's packed weights [7][128][C], bias [>= 72]; C = 64 or 128; MB / MS variants only
+cudaError_t launch_tail_fused(const TailArgs& t, const void* act, const void* w, const float* bias, int C, int f16, int num_sms,
+                              cudaStream_t st);
 
 // ---- misc.cu
 // fp32 NCT [B][C][T] -> channels-last [B][T][Cp] operand (and optional fp32 copy), optional mask [B][T]

@@ -1170,6 +1170,36 @@ int run_text(Ctx& cx, const TextBufs& t, const long long* tokens, const float* m
   return MBV_OK;
 }
 
+// conv_post inside the tail kernel (tail_fused_kernel): 16-bit tensor-core paths, the 4-band decoders (72 logit channels),
+// conv_post k = 7 on 64 or 128 channels.  Everything else (fp32 / tf32 paths, single-band decoder) keeps conv_post as a
+// conv launch that writes fp32 logits for the stand-alone tail kernel.
+bool fused_tail_ok(const mbv_handle* h) {
+  return h->prec >= MBV_PREC_BF16 && !(h->cfg.flags & (MBV_FLAG_FORCE_SIMT | MBV_FLAG_SPLIT_TAIL)) && h->cfg.variant != MBV_VARIANT_ISTFT &&
+         h->n_logit == 72 && h->conv_post.taps == 7 && h->conv_post.dil == 1 && (h->conv_post.Cp_in == 64 || h->conv_post.Cp_in == 128);
+}
+
+void fill_tail_args(mbv_handle* h, TailArgs* ta, float* wav, float* o_mb, float* spec, float* phase, int B, int Lfr) {
+  memset(ta, 0, sizeof(*ta));
+  ta->wav = wav; ta->o_mb = o_mb; ta->spec = spec; ta->phase = phase;
+  ta->B = B; ta->L = Lfr; ta->n_ch = h->n_logit; ta->variant = h->cfg.variant;
+  memcpy(ta->coef, h->tail_coef, sizeof(ta->coef));
+  memcpy(ta->mod, h->tail_mod, sizeof(ta->mod));
+  memcpy(ta->g2, h->tail_g2, sizeof(ta->g2));
+  ta->fast_pqmf = h->tail_fast;
+}
+
+// act: the operand tensor [B][Lfr + 1][C] conv_post consumes (reflect-padded lrelu_0.01 of the last stage)
+int run_tail_fused(Ctx& cx, const void* act, float* wav, float* o_mb, float* spec, float* phase, int B, int Lfr) {
+  mbv_handle* h = cx.h;
+  TailArgs ta;
+  fill_tail_args(h, &ta, wav, o_mb, spec, phase, B, Lfr);
+  ProfScope prof(cx, 1, "tail (conv_post fused)");
+  CUDA_TRY(h, launch_tail_fused(ta, act, h->conv_post.w, h->conv_post.bias, h->conv_post.Cp_in, h->prec == MBV_PREC_FP16 ? 1 : 0,
+                                h->num_sms, cx.st));
+  cx.launches++;
+  return MBV_OK;
+}
+
 int run_tail(Ctx& cx, const float* logits, float* wav, float* o_mb, float* spec, float* phase, int B, int Lfr) {
   mbv_handle* h = cx.h;
   TailArgs ta;
@@ -1328,6 +1358,7 @@ int run_decode(Ctx& cx, const DecBufs& d, const float* z, const float* z_mask, c
     cx.pdl = true;
     cur = s.next;
   }
+  if (fused_tail_ok(h)) return run_tail_fused(cx, cur, wav, o_mb, spec, phase, B, L);
   {  // conv_post on the reflect-padded L+1 frames -> fp32 logits, pitch n_logit
     EpiParams e = epi_base(EPI_F32, h->n_logit, L + 1);
     e.n_valid = h->n_logit; e.xout = d.logits;
@@ -1558,6 +1589,23 @@ extern "C" int mbv_tail(mbv_handle* h, const float* logits, float* wav, float* o
   Ctx cx;
   cx.h = h; cx.st = (cudaStream_t)stream; cx.plans = nullptr; cx.plans_valid = false;
   rc = run_tail(cx, logits, wav, o_mb, spec, phase, B, L);
+  h->last_launches = cx.launches;
+  return rc;
+}
+
+extern "C" int mbv_tail_fused(mbv_handle* h, const void* act, float* wav, float* o_mb, float* spec, float* phase, int32_t B,
+                              int32_t T, void* stream) {
+  int rc = check_ready(h, B, T);
+  if (rc) return rc;
+  if (!act || !wav) return fail(h, MBV_ERR_INVALID, "null tensor");
+  if ((spec == nullptr) != (phase == nullptr)) return fail(h, MBV_ERR_INVALID, "spec and phase must be requested together");
+  if (!fused_tail_ok(h)) return fail(h, MBV_ERR_UNSUPPORTED, "the fused conv_post + tail kernel needs a 16-bit precision and a 4-band decoder");
+  DEVICE_GUARD(h);
+  int L = T;
+  for (int i = 0; i < h->n_stage; ++i) L *= h->cfg.upsample_rates[i];
+  Ctx cx;
+  cx.h = h; cx.st = (cudaStream_t)stream; cx.plans = nullptr; cx.plans_valid = false;
+  rc = run_tail_fused(cx, act, wav, o_mb, spec, phase, B, L);
   h->last_launches = cx.launches;
   return rc;
 }

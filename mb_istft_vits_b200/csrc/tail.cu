@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "tc_ptx.cuh"
 
 namespace mbv {
 
@@ -609,6 +610,541 @@ static cudaError_t launch_tail_mb3(const TailArgs& a_in, int precise, int num_sm
     cudaMemset(dbg, 0, (64 + 3 * 1024) * sizeof(long long));
   }
   return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_post INSIDE the tail (16-bit operand paths, MB / MS decoders):  models.py:363-375 as ONE kernel.
+//
+// The two-kernel path writes the fp32 logits [B][16T+1][72] (254 MB at BASELINE size) and reads them back.  Here the
+// logits never leave the SM:
+//   * conv_post (Conv1d C -> 72, k 7, on the reflect-padded lrelu_0.01 operand tensor the last ResBlock wrote) runs on
+//     the tensor cores with the FRAME on the accumulator lane:  D[128 frames, 80] = sum_tap sum_kb X[frames + tap, 64] .
+//     W[tap][kb][80, 64]^T  (tcgen05.mma M 128, N 80 = 72 channels + padding, K 16; the activation slab is the A
+//     operand, tap = row offset of its descriptor).  A consumer thread then owns one frame and reads its 72 logits with
+//     tcgen05.ld -- exactly the "lane = frame" layout the tail arithmetic wants, no transpose, no shared-memory tile.
+//   * all conv_post weights (7 taps x C/64 k-blocks x 72 rows x 128 B = 126 KB for C = 128) stay resident in shared
+//     memory for the life of the (persistent) CTA; the 8 padding rows of a tile are simply the first rows of the next one
+//     (they only feed the 8 unused accumulator columns).
+//   * warp roles: 1 TMA producer (activation slabs, one k-block per stage), 1 MMA issuer, TF_G consumer groups of 4
+//     warps.  Each group walks its own equal share of the hop blocks (like one CTA of tail_mb3_kernel) with its own
+//     double-buffered 80-column accumulator pair in TMEM, so head / iDFT / FIR of one group overlap the MMAs and the
+//     tile of the others.  The tail arithmetic is the one of tail_mb3_kernel (same operation order).
+// Algorithmic HBM bytes per latent frame: 16 frames x C x 2 B in (4096 for C = 128) + 1024 B of samples out.
+// ------------------------------------------------------------------------------------------------
+constexpr int TF_G = 3;                        // consumer groups per CTA
+constexpr int TF_THREADS = 128 * TF_G + 64;
+constexpr int TF_NCOL = 80;                    // UMMA N
+constexpr int TF_WROWS = 72;                   // weight rows kept per (tap, k-block) tile
+constexpr int TF_WTILE = TF_WROWS * 128;       // 9216 B (a multiple of the 1024-byte swizzle atom)
+constexpr int TF_TAPS = 7;
+constexpr int TF_SLAB_ROWS = 136;              // 128 frames + 6 rows of tap halo, rounded up to 8
+constexpr int TF_SLAB = TF_SLAB_ROWS * 128;
+constexpr int TF_NSLAB = 2;
+constexpr int TF_OFF_X = TF_TAPS * 2 * TF_WTILE;                        // weights first (129024 B)
+constexpr int TF_OFF_G = TF_OFF_X + TF_NSLAB * TF_SLAB;
+constexpr int TF_GROUP_BYTES = 8 * T3_UP * 4 + T3_NW * 4 * 6 * 16;      // U + halo of one group
+constexpr int TF_OFF_TAB = TF_OFF_G + TF_G * TF_GROUP_BYTES;
+constexpr int TF_OFF_BIAS = TF_OFF_TAB + 1024;
+constexpr int TF_OFF_BAR = TF_OFF_BIAS + 512;
+constexpr int TF_NBAR = 1 + 2 * TF_NSLAB + 4 * TF_G;
+constexpr int TF_SMEM = TF_OFF_BAR + TF_NBAR * 8 + 16 + 1024;          // + slack for the 1024-byte alignment
+static_assert(TF_SMEM <= 227 * 1024, "fused tail: shared memory budget");
+static_assert(T3_NF == 128, "fused tail: one consumer group = 128 frames = 128 TMEM lanes");
+
+struct FusedTailArgs {
+  TailArgs t;          // outputs, filter tables, B, L (t.logits unused)
+  const float* bias;   // conv_post bias [>= 72] (device)
+  int kblocks;         // input channels / 64 (1 or 2)
+  int f16;             // operand element type: 0 bf16, 1 fp16
+};
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// the hop-block walk of one consumer group (identical in the producer, the MMA issuer and the group itself)
+struct TfWalk {
+  int b, q0, left, L;
+  __device__ __forceinline__ void init(long long total, int n_v, int v, int L_) {
+    L = L_;
+    const long long per = (total + n_v - 1) / n_v;
+    const long long g0 = per * v;
+    const long long g_end = (g0 + per < total) ? g0 + per : total;
+    left = (int)(g_end > g0 ? g_end - g0 : 0);
+    b = (int)(g0 / L); q0 = (int)(g0 % L);
+  }
+  __device__ __forceinline__ int nq() const {
+    const int tiles_left = (left + T3_NQ - 1) / T3_NQ;
+    int n = (left + tiles_left - 1) / tiles_left;
+    if (n > L - q0) n = L - q0;
+    return n;
+  }
+  __device__ __forceinline__ void advance(int n) {
+    left -= n;
+    if (q0 + n == L) { b += 1; q0 = 0; } else { q0 += n; }
+  }
+};
+
+template <bool EMIT>
+__global__ void __launch_bounds__(TF_THREADS, 1)
+tail_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ FusedTailArgs fa) {
+  constexpr int S = 4;
+  constexpr bool PRECISE = false;
+  const TailArgs& a = fa.t;
+  extern __shared__ __align__(1024) uint8_t tf_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tf_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smW = sm;
+  uint8_t* smX = sm + TF_OFF_X;
+  float* s_tab = reinterpret_cast<float*>(sm + TF_OFF_TAB);
+  float* s_bias = reinterpret_cast<float*>(sm + TF_OFF_BIAS);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + TF_OFF_BAR);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + TF_NBAR);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  constexpr int iWF = 0, iXF = 1, iXE = iXF + TF_NSLAB, iDF = iXE + TF_NSLAB, iDE = iDF + 2 * TF_G;
+  const int tid_cta = threadIdx.x, warp_cta = tid_cta >> 5, lane = tid_cta & 31;
+  const int L = a.L, F = L + 1;
+  const int kblocks = fa.kblocks;
+  const long long total = (long long)a.B * L;
+  const int n_v = (int)gridDim.x * TF_G;
+
+  if (a.fast_pqmf) { if (tid_cta < 128) s_tab[tid_cta] = a.g2[tid_cta >> 5][(tid_cta >> 1) & 15]; }
+  else { for (int i = tid_cta; i < 256; i += TF_THREADS) s_tab[i] = a.coef[i >> 6][i & 63]; }
+  if (tid_cta == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    mbar_init(BAR(iWF), 1);
+    for (int i = 0; i < TF_NSLAB; ++i) { mbar_init(BAR(iXF + i), 1); mbar_init(BAR(iXE + i), 1); }
+    for (int i = 0; i < 2 * TF_G; ++i) { mbar_init(BAR(iDF + i), 1); mbar_init(BAR(iDE + i), 4); }
+    fence_barrier_init();
+  }
+  if (warp_cta == 4 * TF_G + 1) tmem_alloc(smem_u32(tmem_ptr_smem), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (tid_cta < 72) s_bias[tid_cta] = fa.bias[tid_cta];   // (first read is after a group barrier)
+
+  if (warp_cta == 4 * TF_G) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_expect_tx(BAR(iWF), (uint32_t)(TF_TAPS * kblocks * TF_WTILE));
+      for (int tap = 0; tap < TF_TAPS; ++tap)
+        for (int kb = 0; kb < kblocks; ++kb)
+          tma_load_2d(smem_u32(smW + (size_t)(tap * kblocks + kb) * TF_WTILE), &tmW, BAR(iWF), kb * 64, tap * 128);
+    }
+    __syncwarp();
+    TfWalk w[TF_G];
+#pragma unroll
+    for (int g = 0; g < TF_G; ++g) w[g].init(total, n_v, (int)blockIdx.x * TF_G + g, L);
+    int sx = 0;
+    uint32_t px = 0;
+    bool any = true;
+    while (any) {
+      any = false;
+#pragma unroll
+      for (int g = 0; g < TF_G; ++g) {
+        if (w[g].left <= 0) continue;
+        any = true;
+        const int nq = w[g].nq();
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(BAR(iXE + sx), px ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(BAR(iXF + sx), (uint32_t)TF_SLAB);
+            // frames [q0 - 3, +128) need the operand rows [q0 - 6, +134): rows outside [0, F) are conv_post's zero padding
+            tma_load_3d(smem_u32(smX + (size_t)sx * TF_SLAB), &tmX, BAR(iXF + sx), kb * 64, w[g].q0 - 6, w[g].b);
+          }
+          __syncwarp();
+          if (++sx == TF_NSLAB) { sx = 0; px ^= 1; }
+        }
+        w[g].advance(nq);
+      }
+    }
+  } else if (warp_cta == 4 * TF_G + 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t fmt = fa.f16 ? 0u : 1u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TF_NCOL >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    TfWalk w[TF_G];
+    int n_done[TF_G];
+#pragma unroll
+    for (int g = 0; g < TF_G; ++g) { w[g].init(total, n_v, (int)blockIdx.x * TF_G + g, L); n_done[g] = 0; }
+    mbar_wait(BAR(iWF), 0);
+    tc_fence_after();
+    int sx = 0;
+    uint32_t px = 0;
+    bool any = true;
+    while (any) {
+      any = false;
+#pragma unroll
+      for (int g = 0; g < TF_G; ++g) {
+        if (w[g].left <= 0) continue;
+        any = true;
+        const int nq = w[g].nq();
+        const int buf = n_done[g] & 1;
+        mbar_wait(BAR(iDE + 2 * g + buf), (((uint32_t)n_done[g] >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)((2 * g + buf) * TF_NCOL);
+        uint32_t accum = 0;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(BAR(iXF + sx), px);
+          tc_fence_after();
+          const uint32_t x_lo = desc_lo(smem_u32(smX + (size_t)sx * TF_SLAB));
+          if (elect_one()) {
+            for (int tap = 0; tap < TF_TAPS; ++tap) {
+              const uint32_t w_lo = desc_lo(smem_u32(smW + (size_t)(tap * kblocks + kb) * TF_WTILE));
+              const uint32_t a_lo = x_lo + (uint32_t)tap * (TC_ROW_BYTES >> 4);   // tap = `tap` rows further into the slab
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                tc_mma<2>(tmem_d, desc64(a_lo + 2 * k), desc64(w_lo + 2 * k), idesc, accum);
+                accum = 1;
+              }
+            }
+            tc_commit(BAR(iXE + sx));
+          }
+          __syncwarp();
+          accum = 1;
+          if (++sx == TF_NSLAB) { sx = 0; px ^= 1; }
+        }
+        if (elect_one()) tc_commit(BAR(iDF + 2 * g + buf));
+        __syncwarp();
+        n_done[g]++;
+        w[g].advance(nq);
+      }
+    }
+  } else {
+    // ===================== consumer groups: head + iDFT + overlap-add + synthesis FIR on TMEM-resident logits =====================
+    const int grp = warp_cta >> 2;
+    const int tid = tid_cta & 127, warp = warp_cta & 3;
+    uint8_t* gsm = sm + TF_OFF_G + (size_t)grp * TF_GROUP_BYTES;
+    float* s_u = reinterpret_cast<float*>(gsm);                      // [8][T3_UP]
+    f2* s_halo = reinterpret_cast<f2*>(gsm + 8 * T3_UP * 4);          // [warp][band pair][6 parts][4 samples]
+    float* s_out = s_u;
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); };
+    TfWalk wk;
+    wk.init(total, n_v, (int)blockIdx.x * TF_G + grp, L);
+    int n_done = 0;
+    group_sync();   // s_tab / s_bias written
+    while (wk.left > 0) {
+      const int b = wk.b, Q0 = wk.q0, nq = wk.nq();
+      const int QY0 = Q0 - 2, F0 = Q0 - 3;
+      const bool last_tile = (Q0 + nq == L);
+      const int buf = n_done & 1;
+      mbar_wait(BAR(iDF + 2 * grp + buf), ((uint32_t)n_done >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((2 * grp + buf) * TF_NCOL);
+
+      // ---- phase A (see tail_mb3_kernel): lane = frame F0 + tid = hop block QY0 + tid
+      f2 yp[2][4];
+      {
+        const int f = F0 + tid;
+        const bool live = (f >= 0) && (f < F);
+        const bool emit = EMIT && live && (f >= Q0) && (f < Q0 + nq || (last_tile && f == L));
+        const f2 keep = dup2(live ? 1.f : 0.f);
+        const f2 k1 = dup2(lane < 31 ? 1.f : 0.f), k2 = dup2(lane < 30 ? 1.f : 0.f), k3 = dup2(lane < 29 ? 1.f : 0.f);
+        auto band_pair = [&](auto p_tag) {
+          constexpr int P = decltype(p_tag)::value, s0 = 2 * P;
+          // logits [36P, 36P + 36) of this frame: band s0 then band s0 + 1 (9 magnitudes, 9 phases each)
+          float x[36];
+          tmem_ld32(taddr + 36 * P, x);
+          tmem_ld4(taddr + 36 * P + 32, x + 32);
+          tmem_ld_wait();
+          if (P == 1) {  // the accumulator is in registers: hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(iDE + 2 * grp + buf));
+          }
+#pragma unroll
+          for (int i = 0; i < 36; ++i) x[i] += s_bias[36 * P + i];
+          f2 re[9], im[9];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) {
+            const float mag0 = ptx_ex2(x[k] * 1.4426950408889634f), mag1 = ptx_ex2(x[18 + k] * 1.4426950408889634f);
+            const float sn0 = ptx_sin(x[9 + k]), sn1 = ptx_sin(x[27 + k]);
+            const f2 ph = 3.14159265358979323846f * mk2(sn0, sn1);   // phase = pi * sin(x)  (models.py:369)
+            const float ph0 = lo2(ph), ph1 = hi2(ph);
+            const float s0v = ptx_sin(ph0), c0v = ptx_cos(ph0), s1v = ptx_sin(ph1), c1v = ptx_cos(ph1);
+            if (EMIT) {
+              if (emit) {
+                const size_t o = (((size_t)b * S + s0) * 9 + k) * F + f;
+                a.spec[o] = mag0; a.phase[o] = ph0;
+                a.spec[o + (size_t)9 * F] = mag1; a.phase[o + (size_t)9 * F] = ph1;
+              }
+            }
+            const f2 mag = keep * mk2(mag0, mag1);
+            re[k] = mag * mk2(c0v, c1v);
+            im[k] = mag * mk2(s0v, s1v);
+          }
+          f2 fr[16];
+          idft16_windowed<f2>(re, im, fr);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            f2 acc = fr[12 + i], v;
+            v.v = __shfl_down_sync(0xffffffffu, fr[8 + i].v, 1); acc = fma2(k1, v, acc);
+            v.v = __shfl_down_sync(0xffffffffu, fr[4 + i].v, 2); acc = fma2(k2, v, acc);
+            v.v = __shfl_down_sync(0xffffffffu, fr[i].v, 3);     acc = fma2(k3, v, acc);
+            yp[P][i] = acc;
+          }
+          {
+            f2* h = s_halo + ((warp * 2 + P) * 6) * 4 + (lane == 0 ? 0 : (lane == 1 ? 3 : 5)) * 4;
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+              const bool on = (warp > 0) && (lane + part < 3);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (on) h[part * 4 + i] = fr[4 * part + i];
+            }
+          }
+        };
+        band_pair(std::integral_constant<int, 0>{});
+        band_pair(std::integral_constant<int, 1>{});
+      }
+      group_sync();  // halo visible; the previous tile's staged outputs have been stored (U is free)
+
+      // ---- phase B: blocks that straddle a warp boundary, envelope, optional o_mb, modulation -> U
+      {
+        const int q = QY0 + tid;
+        const bool inside = (q >= 0) && (q < L) && (tid < T3_NF - 3);
+#pragma unroll
+        for (int P = 0; P < 2; ++P) {
+          {
+            const bool fix = (warp < T3_NW - 1) && (lane >= 29);
+            const bool on1 = fix && (lane >= 30), on2 = fix && (lane == 31);
+            const int s0 = lane == 30 ? 1 : (lane == 31 ? 2 : 0), s1 = lane == 30 ? 3 : 4;
+            const f2* h = s_halo + ((((fix ? warp + 1 : warp)) * 2 + P) * 6) * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const f2 a0 = h[s0 * 4 + i], a1 = h[s1 * 4 + i], a2 = h[5 * 4 + i];
+              f2 v = yp[P][i];
+              const f2 v0 = v + a0;
+              if (fix) v = v0;
+              const f2 v1 = v + a1;
+              if (on1) v = v1;
+              const f2 v2 = v + a2;
+              if (on2) v = v2;
+              yp[P][i] = v;
+            }
+          }
+          if (!inside) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) yp[P][i] = dup2(0.f);
+          } else if (PRECISE || q == 0 || q == L - 1) {
+            float e[4] = {1.5f, 1.5f, 1.5f, 1.5f};
+            if (q == 0) { e[0] -= win_sq(12); e[1] -= win_sq(13); e[2] -= win_sq(14); e[3] -= win_sq(15); }
+            if (q == L - 1) { e[0] -= win_sq(0); e[1] -= win_sq(1); e[2] -= win_sq(2); e[3] -= win_sq(3); }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) yp[P][i] = mk2(lo2(yp[P][i]) / e[i], hi2(yp[P][i]) / e[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) yp[P][i] = 0.66666666666666667f * yp[P][i];
+          }
+          if (a.o_mb != nullptr && inside && tid >= 2 && tid < 2 + nq) {
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {
+              const int s = 2 * P + hb;
+              const float4 v = hb ? make_float4(hi2(yp[P][0]), hi2(yp[P][1]), hi2(yp[P][2]), hi2(yp[P][3]))
+                                  : make_float4(lo2(yp[P][0]), lo2(yp[P][1]), lo2(yp[P][2]), lo2(yp[P][3]));
+              if (a.variant == 1) {
+                *reinterpret_cast<float4*>(a.o_mb + ((size_t)b * S + s) * 4 * L + 4 * (size_t)q) = v;
+              } else {
+                float4* o = reinterpret_cast<float4*>(a.o_mb + ((size_t)b * S + s) * 16 * L + 16 * (size_t)q);
+                o[0] = make_float4(4.f * v.x, 0.f, 0.f, 0.f);
+                o[1] = make_float4(4.f * v.y, 0.f, 0.f, 0.f);
+                o[2] = make_float4(4.f * v.z, 0.f, 0.f, 0.f);
+                o[3] = make_float4(4.f * v.w, 0.f, 0.f, 0.f);
+              }
+            }
+          }
+        }
+        if (a.fast_pqmf) {
+          const unsigned long long* modp = reinterpret_cast<const unsigned long long*>(&a.mod[0][0]);
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            f2 m01, m23;
+            m01.v = modp[2 * m]; m23.v = modp[2 * m + 1];
+            float u[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const f2 t = fma2(m23, yp[1][i], m01 * yp[0][i]);
+              u[i] = lo2(t) + hi2(t);
+            }
+            *reinterpret_cast<float4*>(s_u + m * T3_UP + 4 * tid) = make_float4(u[0], u[1], u[2], u[3]);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int P = c >> 1;
+            const float4 v = (c & 1) ? make_float4(hi2(yp[P][0]), hi2(yp[P][1]), hi2(yp[P][2]), hi2(yp[P][3]))
+                                     : make_float4(lo2(yp[P][0]), lo2(yp[P][1]), lo2(yp[P][2]), lo2(yp[P][3]));
+            *reinterpret_cast<float4*>(s_u + c * T3_UP + 4 * tid) = v;
+          }
+        }
+      }
+      group_sync();
+
+      // ---- phase C: synthesis FIR (thread = hop blocks 2p, 2p+1; residues rh and rh + 2)
+      {
+        const int p = 16 * warp + (lane >> 1), rh = lane & 1;
+        const bool fir_on = (p >= 1 && 2 * p < 2 + nq);
+        float accs[2][8];
+        if (fir_on) {
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int r = rh + 2 * h2;
+            float* acc = accs[h2];
+            if (a.fast_pqmf) {
+              f2 we[12], wo[12];
+              const ulonglong2* pe = reinterpret_cast<const ulonglong2*>(s_u + (7 - r) * T3_UP + 8 * p - 8);
+              const ulonglong2* po = reinterpret_cast<const ulonglong2*>(s_u + (3 - r) * T3_UP + 8 * p - 8);
+#pragma unroll
+              for (int i = 0; i < 6; ++i) {
+                const ulonglong2 u = pe[i], v = po[i];
+                we[2 * i].v = u.x; we[2 * i + 1].v = u.y;
+                wo[2 * i].v = v.x; wo[2 * i + 1].v = v.y;
+              }
+              const ulonglong2* gp = reinterpret_cast<const ulonglong2*>(s_tab) + r * 8;
+              f2 accA[4], accB[5];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) accA[i] = dup2(0.f);
+#pragma unroll
+              for (int i = 0; i < 5; ++i) accB[i] = dup2(0.f);
+#pragma unroll
+              for (int dd = 0; dd < 8; ++dd) {
+                const ulonglong2 gv = gp[dd];
+                f2 ge, go;
+                ge.v = gv.x;
+                go.v = gv.y;
+#pragma unroll
+                for (int jj = 0; jj < 5; ++jj) accB[jj] = fma2(ge, wo[jj + dd], accB[jj]);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) accA[jj] = fma2(go, we[jj + dd + 1], accA[jj]);
+              }
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                acc[2 * jj] = lo2(accA[jj]) + hi2(accB[jj]);
+                acc[2 * jj + 1] = hi2(accA[jj]) + lo2(accB[jj + 1]);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                float v[24], gg[16];
+                const float4* yq = reinterpret_cast<const float4*>(s_u + c * T3_UP + 8 * p - 8);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                  const float4 u = yq[i];
+                  v[4 * i] = u.x; v[4 * i + 1] = u.y; v[4 * i + 2] = u.z; v[4 * i + 3] = u.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float4 gv = *reinterpret_cast<const float4*>(s_tab + c * 64 + r * 16 + 4 * i);
+                  gg[4 * i] = gv.x; gg[4 * i + 1] = gv.y; gg[4 * i + 2] = gv.z; gg[4 * i + 3] = gv.w;
+                }
+#pragma unroll
+                for (int d = 0; d < 16; ++d)
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) acc[e] = fmaf(gg[d], v[1 + e + d], acc[e]);
+              }
+            }
+          }
+        }
+        group_sync();  // every FIR window has been read: U becomes the output staging buffer
+        if (fir_on) {
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            float* o = s_out + 32 * p + rh + 2 * h2;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[4 * (e ^ (p & 7))] = accs[h2][e];
+          }
+        }
+      }
+      group_sync();
+      {
+        float4* dst = reinterpret_cast<float4*>(a.wav + (size_t)b * 16 * L + 16 * (size_t)Q0);
+        const float4* src = reinterpret_cast<const float4*>(s_out);
+        for (int c = tid; c < 4 * nq; c += T3_NF) {
+          const int lc = c + 8, pr = lc >> 3, e = lc & 7;
+          dst[c] = src[8 * pr + (e ^ (pr & 7))];
+        }
+      }
+      n_done++;
+      wk.advance(nq);
+      // (the group barrier after the next phase A orders these staging reads before U is rewritten)
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp_cta == 4 * TF_G + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+cudaError_t launch_tail_fused(const TailArgs& t, const void* act, const void* w, const float* bias, int C, int f16, int num_sms,
+                              cudaStream_t st) {
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(tc_tensormap_encoder());
+  if (!enc) return cudaErrorNotSupported;
+  if (C != 64 && C != 128) return cudaErrorInvalidValue;
+  FusedTailArgs fa;
+  fa.t = t;
+  fa.t.dbg = nullptr;
+  fa.bias = bias;
+  fa.kblocks = C / 64;
+  fa.f16 = f16;
+  const int F = t.L + 1;
+  const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap tmX, tmW;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)F, (cuuint64_t)t.B};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)F * C * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)TF_SLAB_ROWS, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&tmX, dt, 3, const_cast<void*>(act), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)TF_TAPS * 128};
+    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)TF_WROWS};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&tmW, dt, 2, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(tail_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  const long long total = (long long)t.B * t.L;
+  long long ctas = (total + (long long)TF_G * T3_NQ - 1) / ((long long)TF_G * T3_NQ);
+  if (ctas > num_sms) ctas = num_sms;
+  if (ctas < 1) ctas = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.blockDim = dim3(TF_THREADS);
+  cfg.dynamicSmemBytes = TF_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (t.spec != nullptr) return cudaLaunchKernelEx(&cfg, tail_fused_kernel<true>, tmX, tmW, fa);
+  return cudaLaunchKernelEx(&cfg, tail_fused_kernel<false>, tmX, tmW, fa);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -292,6 +292,18 @@ class Engine:
                                       self._ptr(phase), B, T, self._stream()))
         return wav, o_mb, spec, phase
 
+    def tail_fused(self, act, T, want_mb=False, want_spec=False):
+        """The fused conv_post + head + iSTFT + synthesis kernel alone, on the operand tensor conv_post consumes:
+        act [B, 16T+1, C] in the engine's 16-bit operand type (bf16 / fp16), channels-last."""
+        want = torch.bfloat16 if self.precision == "bf16" else torch.float16
+        if act.dtype != want or not act.is_contiguous() or act.device != self.device:
+            raise ValueError(f"act must be a contiguous {want} tensor on the engine's device")
+        B = act.shape[0]
+        wav, o_mb, spec, phase = self._alloc_outputs(B, T, want_mb, want_spec)
+        self._check(self.lib.mbv_tail_fused(self._h, C.c_void_p(act.data_ptr()), self._ptr(wav), self._ptr(o_mb), self._ptr(spec),
+                                            self._ptr(phase), B, T, self._stream()))
+        return wav, o_mb, spec, phase
+
     # ---- widening beyond the seam (SURVEY 8f rank 2)
     def pcm16(self, wav, n_samples=None, auto_normalize=True):
         """tts_vits.py:204-216 on the GPU: per-utterance peak normalisation (x0.9 when the peak exceeds 0.01), clip,

@@ -23,6 +23,7 @@ FLAG_RESIDUAL_FP16 = 8
 FLAG_FUSED_PAIR = 16
 FLAG_CLUSTER_PAIRS = 32
 FLAG_BRANCHES = 64
+FLAG_SPLIT_TAIL = 128
 
 ERRORS = {0: "MBV_OK", -1: "MBV_ERR_INVALID", -2: "MBV_ERR_UNSUPPORTED", -3: "MBV_ERR_WEIGHTS",
           -4: "MBV_ERR_WORKSPACE", -5: "MBV_ERR_CUDA"}
@@ -33,7 +34,7 @@ SYMBOLS = ["mbv_abi_version", "mbv_create", "mbv_destroy", "mbv_load_weights", "
            "mbv_flow_flops", "mbv_tail", "mbv_last_error", "mbv_set_profiling", "mbv_profile_read", "mbv_profile_read_launches", "mbv_pcm16", "mbv_expand_prior", "mbv_flow_forward",
            "mbv_posterior_workspace_bytes", "mbv_posterior_encode", "mbv_receptive_field", "mbv_stream_open",
            "mbv_stream_workspace_bytes", "mbv_stream_halo", "mbv_stream_push", "mbv_stream_close",
-           "mbv_text_workspace_bytes", "mbv_text_encode"]
+           "mbv_text_workspace_bytes", "mbv_text_encode", "mbv_tail_fused"]
 
 
 class MbvConfig(C.Structure):
@@ -85,6 +86,7 @@ def load():
     lib.mbv_decode.argtypes = [vp, fp, fp, fp, fp, fp, fp, fp, i32, i32, vp, C.c_size_t, vp]
     lib.mbv_flow_decode.argtypes = [vp, fp, fp, fp, fp, fp, fp, fp, fp, i32, i32, vp, C.c_size_t, vp]
     lib.mbv_tail.argtypes = [vp, fp, fp, fp, fp, fp, i32, i32, vp]
+    lib.mbv_tail_fused.argtypes = [vp, vp, fp, fp, fp, fp, i32, i32, vp]
     lib.mbv_last_launch_count.argtypes = [vp]
     lib.mbv_decode_flops.argtypes = [vp, i32, i32]
     lib.mbv_decode_flops.restype = C.c_double
