@@ -491,22 +491,30 @@ def run_native(args):
     e2e_seq_ms = float(ty.item()) / args.steps
     del hs
 
-    # ---------------- fused tail alone (HBM roofline of that kernel): event-timed stand-alone launches
-    tail_ms = None
-    if hasattr(eng, "tail"):
-        L = 16 * T
-        logits = torch.randn((B, L + 1, 72), device=dev) * 0.5
+    # ---------------- the tail kernels alone, event-timed stand-alone launches: (a) the fused conv_post + head + iSTFT + PQMF
+    # kernel the step runs (16-bit paths) on a random operand tensor, (b) the stand-alone tail kernel on fp32 logits
+    # (the two-kernel path: conv_post writes 254 MB of logits, this kernel reads them)
+    def time_alone(fn, n=10):
         for _ in range(3):
-            eng.tail(logits, T, want_mb=False, want_spec=False)
+            fn()
         torch.cuda.synchronize()
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0e.record()
-        for _ in range(10):
-            eng.tail(logits, T, want_mb=False, want_spec=False)
+        for _ in range(n):
+            fn()
         t1e.record()
         torch.cuda.synchronize()
-        tail_ms = t0e.elapsed_time(t1e) / 10
-        del logits
+        return t0e.elapsed_time(t1e) / n
+
+    L = 16 * T
+    logits = torch.randn((B, L + 1, 72), device=dev) * 0.5
+    tail_ms = time_alone(lambda: eng.tail(logits, T, want_mb=False, want_spec=False))
+    del logits
+    fused_tail_ms = None
+    if args.precision in ("bf16", "fp16") and not (args.flags & 128):
+        act = (torch.randn((B, L + 1, 128), device=dev) * 0.5).to(torch.bfloat16 if args.precision == "bf16" else torch.float16)
+        fused_tail_ms = time_alone(lambda: eng.tail_fused(act, T))
+        del act
 
     flops_step = eng.decode_flops(B, T) + eng.flow_flops(B, T)
 
@@ -616,7 +624,9 @@ def run_native(args):
     n_conv_step = conv_n // max(1, n_prof)
     non_conv_ms = (tail_prof_ms + other_ms) / n_prof
     conv_ms_step = ms_step - non_conv_ms            # conv kernel time INSIDE the graph-timed region
-    conv_tflops = flops_step / (conv_ms_step * 1e-3) / 1e12
+    # conv_post runs inside the tail kernel on the 16-bit paths: its FLOPs and its time belong to roofline_tail
+    flops_conv = flops_step - (2.0 * 72 * 896 * B * (16 * T + 1) if fused_tail_ms else 0.0)
+    conv_tflops = flops_conv / (conv_ms_step * 1e-3) / 1e12
     tf32 = args.precision == "tf32"
     pk_s = peaks["tflops_sustained"] * (0.5 if tf32 else 1.0)
     pk_b = peaks["tflops_burst"] * (0.5 if tf32 else 1.0)
@@ -625,25 +635,48 @@ def run_native(args):
         "bound": "tensor", "achieved": conv_tflops, "peak": pk_s, "unit": "TFLOP/s", "frac": conv_tflops / pk_s,
         "frac_vs_burst_peak": conv_tflops / pk_b, "peak_burst": pk_b,
         "traffic": traffic.get("conv_dram_bytes_per_launch"), "traffic_source": traffic.get("source"),
-        "algorithmic_flops_per_launch": flops_step / max(1, n_conv_step),
+        "algorithmic_flops_per_launch": flops_conv / max(1, n_conv_step),
         "peak_source": peaks["source"] + " bf16_tflops_sustained (kernels timed inside a long step); frac_vs_burst_peak uses bf16_tflops"
                        + (" (x 0.5 assumed for tf32; the measured TF32 GEMM peak is in extras.tf32)" if tf32 else ""),
-        "flops_per_step": flops_step, "avg_launch_ms": conv_ms_step / max(1, n_conv_step),
+        "flops_per_step": flops_step, "flops_in_conv_launches": flops_conv, "avg_launch_ms": conv_ms_step / max(1, n_conv_step),
         "share_of_step": conv_ms_step / ms_step,
         "timed_in": "the graph-timed region: ms_per_step minus the event-timed non-conv launches (tail %.3f + other %.3f ms)"
                     % (tail_prof_ms / n_prof, other_ms / n_prof),
         "eager_event_sum_ms": conv_ev_ms / n_prof,
     }
     if sustained:
-        c_sus = flops_step / ((sustained["ms_per_step"] - non_conv_ms) * 1e-3) / 1e12
+        c_sus = flops_conv / ((sustained["ms_per_step"] - non_conv_ms) * 1e-3) / 1e12
         roofline["sustained_leg"] = {"achieved": c_sus, "frac": c_sus / pk_s, "frac_vs_burst_peak": c_sus / pk_b,
                                      "ms_per_step": sustained["ms_per_step"], "seconds": sustained["seconds"],
                                      "clocks": sustained["clocks"]}
-    tail_bytes = B * T * 5632.0  # 4608 B logits in + 1024 B waveform out per latent frame
+    # fused conv_post + tail kernel (what the step runs): per latent frame it reads 16 frames x 128 ch x 2 B = 4096 B of
+    # operands and writes 1024 B of samples ("conv_post fused" variant), and does 2 x 72 x 896 MACs per frame
+    # on the tensor cores.  Both ceilings are reported; the binding one is the tensor time.
     roofline_tail = None
-    if tail_ms:
+    if fused_tail_ms:
+        fbytes = B * T * 5120.0 + B * 128 * 2.0        # + the extra reflect-pad frame per utterance
+        fflops = 2.0 * 72 * 896 * B * (16 * T + 1)
+        t_hbm, t_tc = fbytes / (peaks["hbm_gbs"] * 1e9), fflops / (peaks["tflops_burst"] * 1e12)
         roofline_tail = {
-            "kernel": "tail_mb3_kernel (head + iSTFT + PQMF)", "bound": "hbm",
+            "kernel": "tail_fused_kernel (conv_post on tcgen05 + head + iSTFT + PQMF, logits stay in TMEM)",
+            "variant": "conv_post fused: reads the bf16 stage-1 operand tensor (4096 B per latent frame), writes 1024 B",
+            "bound": "tensor" if t_tc > t_hbm else "hbm",
+            "achieved": fflops / (fused_tail_ms * 1e-3) / 1e12, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
+            "frac": max(t_tc, t_hbm) / (fused_tail_ms * 1e-3),
+            "hbm": {"achieved": fbytes / (fused_tail_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": fbytes / (fused_tail_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+            "traffic": traffic.get("tail_dram_bytes_per_launch"),
+            "peak_source": peaks["source"] + " bf16_tflops (burst) and hbm_gbs; kernel timed alone",
+            "ms": fused_tail_ms, "ms_inside_step": tail_prof_ms / tail_n if tail_n else None,
+            "bytes_per_launch": fbytes, "flops_per_launch": fflops,
+            "two_kernel_path": {"conv_post_ms": "see profiles/round2_launch_times_bf16_split_tail.txt", "tail_ms": tail_ms,
+                                "tail_hbm_frac": B * T * 5632.0 / (tail_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                "tail_bytes_per_launch": B * T * 5632.0},
+        }
+    elif tail_ms:
+        tail_bytes = B * T * 5632.0  # 4608 B logits in + 1024 B waveform out per latent frame
+        roofline_tail = {
+            "kernel": "tail_mb3_kernel (head + iSTFT + PQMF on fp32 logits)", "bound": "hbm",
             "achieved": tail_bytes / (tail_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic.get("tail_dram_bytes_per_launch"),
             "peak_source": peaks["source"] + " hbm_gbs (burst; kernel timed alone)", "ms": tail_ms,
@@ -703,7 +736,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["fp16", "bf16", "tf32", "fp32"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--frames", type=int, default=T_FRAMES)
-    ap.add_argument("--flags", type=int, default=0, help="extra mbv_config flags (A/B measurements)")
+    ap.add_argument("--flags", type=int, default=0, help="extra mbv_config flags (A/B measurements: 16 fused pairs, 32 cluster pairs, 64 branches, 128 split tail)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline and PyTorch-eager legs")
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 3 s sustained leg")
     ap.add_argument("--no-tf32", action="store_true", help="skip the tf32 sub-line")

@@ -94,6 +94,10 @@ typedef struct {
 #define MBV_FLAG_CLUSTER_PAIRS 32    /* experimental: run the multi-tap convs as clusters of two CTAs that work on two time tiles of the
                                      * same weight group; each CTA fetches half of every weight tile and TMA-multicasts it to both.
                                      * Parity-tested; < 1 % faster per step on B200, hence opt-in. */
+#define MBV_FLAG_NO_CTA_PAIRS 256   /* A/B and cross-check tests: do NOT run the multi-tap convs with an even number of channel tiles
+                                     * (conv_pre, first upsampler, 256-channel ResBlocks) as cta_group::2 MMAs over CTA pairs
+                                     * (one MMA spans two channel tiles, M = 256; each CTA stages half of the activation rows --
+                                     * DESIGN.md section 4.1c).  Results are bit-identical either way. */
 #define MBV_FLAG_SPLIT_TAIL 128     /* keep conv_post as its own conv launch writing fp32 logits for the stand-alone tail kernel instead
                                      * of the fused conv_post + tail kernel (the default on the 16-bit paths; A/B and cross-check tests) */
 #define MBV_FLAG_BRANCHES 64         /* experimental: run the parallel ResBlocks of a stage on the library's two extra streams (own

@@ -372,11 +372,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     tma_prefetch_desc(&tmW);
     for (int i = 0; i < rt.n_slab_stages; ++i) { mbar_init(BAR(iXF + i), 1); mbar_init(BAR(iXE + i), 1); }
     // cluster mode: a weight stage may be refilled (by BOTH CTAs' multicasts) only when both CTAs have consumed it
-    for (int i = 0; i < rt.n_w_stages; ++i) { mbar_init(BAR(iWF + i), 1); mbar_init(BAR(iWE + i), (CL != 0) ? 2 : 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(iCF + i), 1); mbar_init(BAR(iCE + i), TC_EPI_WARPS); }
+    for (int i = 0; i < rt.n_w_stages; ++i) { mbar_init(BAR(iWF + i), 1); mbar_init(BAR(iWE + i), (CL == 1) ? 2 : 1); }
+    // CTA pairs (CL == 2): the even CTA issues the MMAs of both, so ITS accumulator-free barrier collects the epilogue warps of both
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(iCF + i), 1); mbar_init(BAR(iCE + i), (CL == 2) ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == TC_WARP_MMA) tmem_alloc(smem_u32(tmem_ptr_smem), 512u);
+  if (warp == TC_WARP_MMA) {
+    if constexpr (CL == 2) tmem_alloc2(smem_u32(tmem_ptr_smem), 512u);  // the same 512 columns in both CTAs of the pair
+    else tmem_alloc(smem_u32(tmem_ptr_smem), 512u);
+  }
   tc_fence_before();
   __syncthreads();
   if ((CL != 0)) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
@@ -405,7 +409,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       wk.t_off = (s % rt.split_k) * rt.split_n;
       wk.n_cols = min(rt.split_n, rt.n_time - wk.t_off);
     }
-    if ((CL != 0)) {
+    if constexpr (CL == 2) {
+      // CTA pairs: tiles 2w and 2w+1 (the two CTAs of a cluster) are the two channel tiles 2p and 2p+1 of ONE time tile
+      int rest = tile >> 1;
+      const int cpairs = rt.c_tiles >> 1;
+      wk.ct = 2 * (rest % cpairs) + (tile & 1); rest /= cpairs;
+      wk.phase = rest % a.n_phases; rest /= a.n_phases;
+      wk.tt = rest % rt.t_tiles; wk.b = rest / rt.t_tiles;
+      wk.row_ok = true;
+    } else if constexpr (CL == 1) {
       const int w = tile >> 1, grp = w % rt.groups, row = 2 * (w / rt.groups) + (tile & 1);
       wk.ct = grp % rt.c_tiles; wk.phase = grp / rt.c_tiles;
       wk.row_ok = row < rt.rows;
@@ -432,7 +444,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const int ct = wk.ct, phase = wk.phase, b = wk.b;
       const int t0 = wk.tt * rt.n_time + wk.t_off;
       const int wrow0 = phase * a.taps * a.N_total + ct * TC_M;
-      const int xrow0 = t0 + a.shift0[phase];
+      // CTA pairs: this CTA stages its HALF of the tile's time rows (the B operand of a cta_group::2 MMA is split by rows)
+      const int xrow0 = t0 + a.shift0[phase] + ((CL == 2) ? (int)crank * (rt.n_time >> 1) : 0);
       if (rt.dbg && lane == 0) rt.dbg[((size_t)blockIdx.x * 7 + 0) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
       // (A whole-tile TMA L2 prefetch of the residual box issued here was measured to be too early: a tile-time later
       //  a third of it had been evicted again and DRAM reads grew 40 %.  The epilogue warps prefetch two chunks ahead.)
@@ -440,11 +453,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         if (wk.row_ok) {
           mbar_wait(BAR(iXE + sx), px ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(BAR(iXF + sx), slab_bytes);
             const uint32_t dst = smem_u32(smX + (size_t)sx * rt.slab_stage_bytes);
-            for (int i = 0; i < rt.n_boxes; ++i)
-              tma_load_3d(dst + (uint32_t)(i * rt.box_rows) * TC_ROW_BYTES, &tmX, BAR(iXF + sx), kb * KB,
-                          xrow0 + i * rt.box_rows, b);
+            if constexpr (CL == 2) {
+              // both CTAs' copies complete on the EVEN CTA's barrier, which expects the bytes of both
+              if (crank == 0) mbar_expect_tx(BAR(iXF + sx), 2 * slab_bytes);
+              const uint32_t xf = mapa_shared(BAR(iXF + sx), 0);
+              for (int i = 0; i < rt.n_boxes; ++i)
+                tma_load_3d_2sm(dst + (uint32_t)(i * rt.box_rows) * TC_ROW_BYTES, &tmX, xf, kb * KB, xrow0 + i * rt.box_rows, b);
+            } else {
+              mbar_expect_tx(BAR(iXF + sx), slab_bytes);
+              for (int i = 0; i < rt.n_boxes; ++i)
+                tma_load_3d(dst + (uint32_t)(i * rt.box_rows) * TC_ROW_BYTES, &tmX, BAR(iXF + sx), kb * KB,
+                            xrow0 + i * rt.box_rows, b);
+            }
           }
           __syncwarp();
           if (++sx == rt.n_slab_stages) { sx = 0; px ^= 1; }
@@ -454,12 +475,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           mbar_wait(BAR(iWE + sw), pw ^ 1);
           if (elect_one()) {
             const uint32_t wdst = smem_u32(smW + (size_t)sw * rt.w_stage_bytes);
-            mbar_expect_tx(BAR(iWF + sw), w_tile_bytes);
-            if ((CL != 0))  // this CTA's 64 rows of the tile, delivered to both CTAs of the pair
+            if constexpr (CL == 2) {  // this CTA's own 128 weight rows (its channel tile = its half of the M = 256 A operand)
+              if (crank == 0) mbar_expect_tx(BAR(iWF + sw), 2 * w_tile_bytes);
+              tma_load_2d_2sm(wdst, &tmW, mapa_shared(BAR(iWF + sw), 0), kb * KB, wrow0 + tap * a.N_total);
+            } else if constexpr (CL == 1) {  // this CTA's 64 rows of the tile, delivered to both CTAs of the pair
+              mbar_expect_tx(BAR(iWF + sw), w_tile_bytes);
               tma_load_2d_mc(wdst + crank * (w_tile_bytes / 2), &tmWh, BAR(iWF + sw), kb * KB,
                              wrow0 + tap * a.N_total + (int)crank * (TC_M / 2), (uint16_t)3);
-            else
+            } else {
+              mbar_expect_tx(BAR(iWF + sw), w_tile_bytes);
               tma_load_2d(wdst, &tmW, BAR(iWF + sw), kb * KB, wrow0 + tap * a.N_total);
+            }
           }
           __syncwarp();
           if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
@@ -473,12 +499,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16 or tf32, both K-major, N, M=128
     constexpr uint32_t fmt = (Op::kPrec == 3) ? 0u : ((Op::kPrec == 2) ? 1u : 2u);  // F16 / BF16 / TF32
     constexpr int KIND = (Op::kPrec >= 2) ? 2 : 1;
-    const uint32_t idesc0 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_M >> 4) << 24);
+    const uint32_t idesc0 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(((CL == 2) ? 2 * TC_M : TC_M) >> 4) << 24);
     const uint32_t tap_step = (uint32_t)(a.dil * TC_ROW_BYTES) >> 4;  // descriptor-lo increment per tap
     int sx = 0, sw = 0, sc = 0;
     uint32_t px = 0, pw = 0, pc = 0;
     for (int tile = blockIdx.x; tile < rt.virt_tiles; tile += gridDim.x) {
-      if ((CL != 0) && !decode_work(tile).row_ok) {
+      if ((CL == 2) && crank != 0) break;  // CTA pairs: the even CTA issues the MMAs of both
+      if ((CL == 1) && !decode_work(tile).row_ok) {
         // no time tile for this CTA (odd tile count): keep the pair's weight ring moving -- wait until each stage has
         // fully landed here, then release it on both CTAs
         for (int i = 0; i < kblocks * a.taps; ++i) {
@@ -513,9 +540,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              tc_mma<KIND>(tmem_d, desc64(w_lo + 2 * k), desc64(x_lo + 2 * k), idesc, (k == 0) ? accum : 1u);
+              if constexpr (CL == 2) tc_mma2<KIND>(tmem_d, desc64(w_lo + 2 * k), desc64(x_lo + 2 * k), idesc, (k == 0) ? accum : 1u);
+              else tc_mma<KIND>(tmem_d, desc64(w_lo + 2 * k), desc64(x_lo + 2 * k), idesc, (k == 0) ? accum : 1u);
             }
-            if ((CL != 0)) tc_commit_mc(BAR(iWE + sw), (uint16_t)3);
+            if constexpr (CL == 2) tc_commit2_mc(BAR(iWE + sw), (uint16_t)3);
+            else if constexpr (CL == 1) tc_commit_mc(BAR(iWE + sw), (uint16_t)3);
             else if (!rt.w_resident) tc_commit(BAR(iWE + sw));
           }
           __syncwarp();
@@ -523,11 +552,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           x_lo += tap_step;  // next tap = `dil` rows further into the slab
           if (!rt.w_resident && ++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
         }
-        if (elect_one()) tc_commit(BAR(iXE + sx));
+        if (elect_one()) { if constexpr (CL == 2) tc_commit2_mc(BAR(iXE + sx), (uint16_t)3); else tc_commit(BAR(iXE + sx)); }
         __syncwarp();
         if (++sx == rt.n_slab_stages) { sx = 0; px ^= 1; }
       }
-      if (elect_one()) tc_commit(BAR(iCF + sc));
+      if (elect_one()) { if constexpr (CL == 2) tc_commit2_mc(BAR(iCF + sc), (uint16_t)3); else tc_commit(BAR(iCF + sc)); }
       __syncwarp();
       if (rt.dbg && lane == 0) {
         rt.dbg[((size_t)blockIdx.x * 7 + 1) * 64 + 2 * ((tile / gridDim.x) & 31) + 1] = clock64();
@@ -674,7 +703,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(iCE + sc));
+      if (lane == 0) {
+        if ((CL == 2) && crank != 0) mbar_arrive_remote(BAR(iCE + sc), 0u);  // the accumulator-free barrier lives in the even CTA
+        else mbar_arrive(BAR(iCE + sc));
+      }
       if (rt.dbg && warp == 0 && lane == 0) rt.dbg[((size_t)blockIdx.x * 7 + 2) * 64 + 2 * ((tile / gridDim.x) & 31) + 1] = clock64();
       if (++sc == 2) { sc = 0; pc ^= 1; }
       ti = tn;
@@ -686,7 +718,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   if ((CL != 0)) cluster_sync_all();  // the peer may still be multicasting into this CTA's ring / arriving on its barriers
   if (warp == TC_WARP_MMA) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512u);
+    if constexpr (CL == 2) tmem_dealloc2(tmem_base, 512u);
+    else tmem_dealloc(tmem_base, 512u);
   }
 }
 
@@ -1051,6 +1084,33 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
   plan->grid = plan->total_tiles < num_sms ? plan->total_tiles : num_sms;
   if (plan->grid < 1) plan->grid = 1;
 
+  plan->cluster = 0;
+  // CTA pairs (cta_group::2): the two CTAs of a cluster take the two channel tiles of ONE time tile.  One MMA spans both
+  // (M = 256); each CTA feeds its own 128 weight rows and only HALF of the activation rows from its shared memory, so the
+  // operand bytes read per MMA and CTA fall from 12 KB to 8 KB -- the single-CTA MMAs are bound by the shared-memory port
+  // (operand reads + TMA writes ~ 107 B/clk of 128), see DESIGN.md.  Needs an even number of channel tiles.
+  // Measured (profiles/round2_cta_pairs_ab.txt): stage-0 k=11 convs 245 -> 210 us (1295 -> 1520 TFLOP/s), k=7 156 -> 145,
+  // first upsampler 207 -> 180, conv_pre 74 -> 66; the HBM-bound k=3 residual convs get slightly slower (113 -> 125 us:
+  // two CTAs in lock step share one tile's epilogue traffic pattern), so RES epilogues pair up from 5 taps on.
+  const bool pair_mode = (a.epi.mode == EPI_ACT && a.taps > 1) || (a.epi.mode == EPI_RES && a.taps >= 5);
+  if (!(flags & MBV_FLAG_NO_CTA_PAIRS) && prec >= 2 && pair_mode && plan->c_tiles % 2 == 0 && num_sms >= 2 && n_time % 16 == 0) {
+    plan->cluster = 2;
+    plan->slab_rows = n_time / 2 + halo;
+    plan->n_boxes = 1;
+    plan->box_rows = (plan->slab_rows + 7) / 8 * 8;
+    plan->slab_stage_bytes = ((plan->box_rows * TC_ROW_BYTES + 1023) / 1024) * 1024;
+    plan->n_slab_stages = a.taps <= 4 ? 4 : 3;
+    plan->n_w_stages = (budget - plan->n_slab_stages * plan->slab_stage_bytes) / plan->w_stage_bytes;
+    if (plan->n_w_stages > 10) plan->n_w_stages = 10;
+    const int nb2 = 2 * plan->n_slab_stages + 2 * plan->n_w_stages + 4;
+    plan->xchg_off = (plan->n_slab_stages * plan->slab_stage_bytes + plan->n_w_stages * plan->w_stage_bytes + nb2 * 8 + 16 + 127) / 128 * 128;
+    plan->smem_bytes = 1024 + plan->xchg_off + xchg;
+    if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;
+    plan->grid = (plan->total_tiles < num_sms ? plan->total_tiles : num_sms) & ~1;  // whole pairs (total_tiles is even)
+  }
+  plan->rows = a.B * plan->t_tiles;
+  plan->groups = a.n_phases * plan->c_tiles;
+
   const CUtensorMapDataType dt = prec == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                                  : (prec == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
   {
@@ -1072,19 +1132,16 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
     if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed for the weight map";
   }
   // small layers (stage-1 k=3 convs, flow post): the whole weight set of the channel tile stays in shared memory
-  plan->w_resident = (plan->c_tiles == 1 && a.n_phases == 1 && a.taps * (a.Cp_in / KB) <= plan->n_w_stages) ? 1 : 0;
+  plan->w_resident = (plan->cluster == 0 && plan->c_tiles == 1 && a.n_phases == 1 && a.taps * (a.Cp_in / KB) <= plan->n_w_stages) ? 1 : 0;
   // Everything else streams its weight taps L2 -> SMEM once per tile and is feed-bound for few taps (k=3 / upsampler /
   // gate convs issue MMAs at ~70 % inside a tile): run clusters of two CTAs on two time tiles of the same weight group,
   // each CTA fetching half of every weight tile and multicasting it to both.
   // Measured (same box, interleaved, profiles/r02_cluster_ab.txt): the MMA-bound layers gain 3-8 %, the step as a whole
   // < 1 % -- so the feed is not what holds the k=3 / upsampler convs at ~70 % issue efficiency -- hence opt-in.
   const int use_cluster = (flags & MBV_FLAG_CLUSTER_PAIRS) ? 1 : 0;
-  plan->cluster = 0;
-  plan->rows = a.B * plan->t_tiles;
-  plan->groups = a.n_phases * plan->c_tiles;
   // (1x1 convs -- flow pre / res / post -- are epilogue- or launch-bound and measured 5-12 % slower in pairs: taps > 1 only)
   const bool mode_ok = a.epi.mode == EPI_ACT || a.epi.mode == EPI_RES || a.epi.mode == EPI_F32 || a.epi.mode == EPI_GATE;
-  if (use_cluster && prec >= 2 && mode_ok && !plan->w_resident && (num_sms & 1) == 0 && plan->rows >= 2 && a.taps > 1) {
+  if (plan->cluster == 0 && use_cluster && prec >= 2 && mode_ok && !plan->w_resident && (num_sms & 1) == 0 && plan->rows >= 2 && a.taps > 1) {
     const long long pairs = (long long)plan->groups * ((plan->rows + 1) / 2);
     if (pairs >= num_sms / 2) {
       plan->cluster = 1;
@@ -1151,6 +1208,17 @@ static cudaError_t launch_one_cl(const ConvArgs& a, const TcPlan& p, const TcRt&
 template <typename Op, int MODE, int LD, int RH>
 static cudaError_t launch_one(const ConvArgs& a, const TcPlan& p, const TcRt& rt, cudaStream_t st, bool set_attr) {
   constexpr bool kHasCluster = (Op::kPrec >= 2) && (MODE == EPI_ACT || MODE == EPI_RES || MODE == EPI_F32 || MODE == EPI_GATE);
+  constexpr bool kHasPairs = (Op::kPrec >= 2) && (MODE == EPI_ACT || MODE == EPI_RES);   // cta_group::2 variant
+  if constexpr (kHasPairs) {
+    if (set_attr) {
+      cudaError_t e = launch_one_cl<Op, MODE, LD, RH, 2>(a, p, rt, st, true);
+      if (e != cudaSuccess) return e;
+    } else if (rt.cluster == 2) {
+      return launch_one_cl<Op, MODE, LD, RH, 2>(a, p, rt, st, false);
+    }
+  } else {
+    if (!set_attr && rt.cluster == 2) return cudaErrorInvalidValue;
+  }
   if constexpr (kHasCluster) {
     if (set_attr) {
       cudaError_t e = launch_one_cl<Op, MODE, LD, RH, 1>(a, p, rt, st, true);

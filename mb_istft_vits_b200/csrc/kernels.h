@@ -58,7 +58,7 @@ struct TailArgs {
 };
 cudaError_t launch_tail(const TailArgs& a, int precise, int num_sms, cudaStream_t st);
 // conv_post + tail in one kernel (tail.cu): act = the 16-bit operand tensor [B][L+1][C] the last ResBlock wrote (reflect-padded,
-// lrelu'd), w = conv_post's packed weights [7][128][C], bias [>= 72]; C = 64 or 128; MB / MS variants only
+// lrelu'd), w = conv_post's packed weights [7][128][C], bias = 72 HOST floats; C = 64 or 128; MB / MS variants only
 cudaError_t launch_tail_fused(const TailArgs& t, const void* act, const void* w, const float* bias, int C, int f16, int num_sms,
                               cudaStream_t st);
 

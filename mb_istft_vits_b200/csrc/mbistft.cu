@@ -112,6 +112,7 @@ struct mbv_handle {
   ConvLayer rb_c2[MBV_MAX_UPS][MBV_MAX_KERNELS][MBV_MAX_DILATIONS];
   float* rb_cond_w[MBV_MAX_UPS][MBV_MAX_KERNELS] = {{nullptr}};  // [C][gin]
   float* rb_cond_b[MBV_MAX_UPS][MBV_MAX_KERNELS] = {{nullptr}};  // [C]
+  float post_bias[72];
   float tail_coef[4][64];
   float tail_mod[8][4];
   float tail_g2[4][16];
@@ -641,6 +642,11 @@ extern "C" int mbv_load_weights(mbv_handle* h, const mbv_tensor* tensors, int32_
     const char* post = c.variant == MBV_VARIANT_ISTFT ? "dec.conv_post" : "dec.subband_conv_post";
     rc = pack_conv1d(h, m, post, h->n_logit, cin, 7, 1, iota_pad(h->n_logit, h->n_logit), iota_pad(cin, cin), true, 0, &h->conv_post);
     if (rc) return rc;
+    {  // host copy of the bias: the fused conv_post + tail kernel takes it by value (constant-bank operands)
+      const HostTensor& pb = m[std::string(post) + ".bias"];
+      memset(h->post_bias, 0, sizeof(h->post_bias));
+      for (int i = 0; i < h->n_logit && i < 72; ++i) h->post_bias[i] = pb.data[i];
+    }
     float hs[4][63];
     memset(hs, 0, sizeof(hs));
     if (c.variant == MBV_VARIANT_MB) {
@@ -1194,7 +1200,7 @@ int run_tail_fused(Ctx& cx, const void* act, float* wav, float* o_mb, float* spe
   TailArgs ta;
   fill_tail_args(h, &ta, wav, o_mb, spec, phase, B, Lfr);
   ProfScope prof(cx, 1, "tail (conv_post fused)");
-  CUDA_TRY(h, launch_tail_fused(ta, act, h->conv_post.w, h->conv_post.bias, h->conv_post.Cp_in, h->prec == MBV_PREC_FP16 ? 1 : 0,
+  CUDA_TRY(h, launch_tail_fused(ta, act, h->conv_post.w, h->post_bias, h->conv_post.Cp_in, h->prec == MBV_PREC_FP16 ? 1 : 0,
                                 h->num_sms, cx.st));
   cx.launches++;
   return MBV_OK;

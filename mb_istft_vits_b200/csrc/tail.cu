@@ -631,7 +631,10 @@ static cudaError_t launch_tail_mb3(const TailArgs& a_in, int precise, int num_sm
 //     tile of the others.  The tail arithmetic is the one of tail_mb3_kernel (same operation order).
 // Algorithmic HBM bytes per latent frame: 16 frames x C x 2 B in (4096 for C = 128) + 1024 B of samples out.
 // ------------------------------------------------------------------------------------------------
-constexpr int TF_G = 3;                        // consumer groups per CTA
+#ifndef MBV_TF_G
+#define MBV_TF_G 3
+#endif
+constexpr int TF_G = MBV_TF_G;                 // consumer groups per CTA
 constexpr int TF_THREADS = 128 * TF_G + 64;
 constexpr int TF_NCOL = 80;                    // UMMA N
 constexpr int TF_WROWS = 72;                   // weight rows kept per (tap, k-block) tile
@@ -639,13 +642,15 @@ constexpr int TF_WTILE = TF_WROWS * 128;       // 9216 B (a multiple of the 1024
 constexpr int TF_TAPS = 7;
 constexpr int TF_SLAB_ROWS = 136;              // 128 frames + 6 rows of tap halo, rounded up to 8
 constexpr int TF_SLAB = TF_SLAB_ROWS * 128;
-constexpr int TF_NSLAB = 2;
+#ifndef MBV_TF_NSLAB
+#define MBV_TF_NSLAB 2
+#endif
+constexpr int TF_NSLAB = MBV_TF_NSLAB;
 constexpr int TF_OFF_X = TF_TAPS * 2 * TF_WTILE;                        // weights first (129024 B)
 constexpr int TF_OFF_G = TF_OFF_X + TF_NSLAB * TF_SLAB;
 constexpr int TF_GROUP_BYTES = 8 * T3_UP * 4 + T3_NW * 4 * 6 * 16;      // U + halo of one group
 constexpr int TF_OFF_TAB = TF_OFF_G + TF_G * TF_GROUP_BYTES;
-constexpr int TF_OFF_BIAS = TF_OFF_TAB + 1024;
-constexpr int TF_OFF_BAR = TF_OFF_BIAS + 512;
+constexpr int TF_OFF_BAR = TF_OFF_TAB + 1024;
 constexpr int TF_NBAR = 1 + 2 * TF_NSLAB + 4 * TF_G;
 constexpr int TF_SMEM = TF_OFF_BAR + TF_NBAR * 8 + 16 + 1024;          // + slack for the 1024-byte alignment
 static_assert(TF_SMEM <= 227 * 1024, "fused tail: shared memory budget");
@@ -653,7 +658,7 @@ static_assert(T3_NF == 128, "fused tail: one consumer group = 128 frames = 128 T
 
 struct FusedTailArgs {
   TailArgs t;          // outputs, filter tables, B, L (t.logits unused)
-  const float* bias;   // conv_post bias [>= 72] (device)
+  float bias[72];      // conv_post bias (by value: read as constant-bank operands)
   int kblocks;         // input channels / 64 (1 or 2)
   int f16;             // operand element type: 0 bf16, 1 fp16
 };
@@ -701,7 +706,6 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint8_t* smW = sm;
   uint8_t* smX = sm + TF_OFF_X;
   float* s_tab = reinterpret_cast<float*>(sm + TF_OFF_TAB);
-  float* s_bias = reinterpret_cast<float*>(sm + TF_OFF_BIAS);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + TF_OFF_BAR);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + TF_NBAR);
   const uint32_t bar0 = smem_u32(bars);
@@ -730,7 +734,6 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr_smem;
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (tid_cta < 72) s_bias[tid_cta] = fa.bias[tid_cta];   // (first read is after a group barrier)
 
   if (warp_cta == 4 * TF_G) {
     // ===================== TMA producer =====================
@@ -830,7 +833,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     TfWalk wk;
     wk.init(total, n_v, (int)blockIdx.x * TF_G + grp, L);
     int n_done = 0;
-    group_sync();   // s_tab / s_bias written
+    group_sync();   // s_tab written
     while (wk.left > 0) {
       const int b = wk.b, Q0 = wk.q0, nq = wk.nq();
       const int QY0 = Q0 - 2, F0 = Q0 - 3;
@@ -861,7 +864,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             if (lane == 0) mbar_arrive(BAR(iDE + 2 * grp + buf));
           }
 #pragma unroll
-          for (int i = 0; i < 36; ++i) x[i] += s_bias[36 * P + i];
+          for (int i = 0; i < 36; ++i) x[i] += fa.bias[36 * P + i];
           f2 re[9], im[9];
 #pragma unroll
           for (int k = 0; k < 9; ++k) {
@@ -1098,7 +1101,7 @@ cudaError_t launch_tail_fused(const TailArgs& t, const void* act, const void* w,
   FusedTailArgs fa;
   fa.t = t;
   fa.t.dbg = nullptr;
-  fa.bias = bias;
+  memcpy(fa.bias, bias, sizeof(fa.bias));
   fa.kblocks = C / 64;
   fa.f16 = f16;
   const int F = t.L + 1;

@@ -744,3 +744,23 @@ def test_fused_conv_post_tail_matches_split_path(prec):
     assert orc.snr_db(b.cpu(), a.cpu()) > 80.0
     for i in range(9):  # per utterance (a quiet utterance must not hide behind a loud one)
         assert orc.snr_db(b[i].cpu(), a[i].cpu()) > 75.0, i
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_cta_pair_mma_is_bit_identical(prec):
+    """cta_group::2 MMAs over CTA pairs (the default for the 256-channel multi-tap convs: one MMA spans two channel tiles,
+    each CTA stages half of the activation rows) against single-CTA MMAs (MBV_FLAG_NO_CTA_PAIRS).  Every accumulator row
+    sees the same operands in the same order -> bit-identical results."""
+    from mb_istft_vits_b200 import lib as L
+    for case in ("mb", "ms_spk", "istft", "mb_long", "mb_resblock2"):
+        cfg, sd, t, meta = load_case(case)
+        ref = _run(_engine(cfg, sd, prec, L.FLAG_NO_CTA_PAIRS), t)
+        got = _run(_engine(cfg, sd, prec, 0), t)
+        assert torch.equal(got[1], ref[1]) and torch.equal(got[0], ref[0]), case
+    cfg = get_config("ljs_mb_istft_vits")
+    sd = synth.make_state_dict(cfg, seed=1234)
+    z_p, mask, _ = synth.make_latents(cfg, 9, 700, seed=5, lengths=[700, 650, 31, 700, 512, 700, 699, 1, 333])
+    a = _engine(cfg, sd, prec, L.FLAG_NO_CTA_PAIRS).flow_decode(z_p.cuda(), mask.cuda())
+    b = _engine(cfg, sd, prec, 0).flow_decode(z_p.cuda(), mask.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
