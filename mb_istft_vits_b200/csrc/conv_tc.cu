@@ -99,6 +99,7 @@ struct TcRt {  // runtime scalars the kernel needs beyond ConvArgs
   // indices >= split_from address the pieces.  (Results are bit-identical: a column's accumulation does not depend on
   // the tile width.)
   int split_from, split_k, split_n, virt_tiles;
+  int pair_phase;    // CTA pairs (CL == 2): the pair is two polyphase branches with equal input shift instead of two channel tiles
   int pdl;           // launch with programmatic stream serialization
   int rotate;        // two channel tiles, even grid: swap which one a CTA takes every round.  With a static round-robin
                      // an even CTA would otherwise ALWAYS get channel tile 0; when the second tile is half padding
@@ -411,10 +412,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     }
     if constexpr (CL == 2) {
       // CTA pairs: tiles 2w and 2w+1 (the two CTAs of a cluster) are the two channel tiles 2p and 2p+1 of ONE time tile
+      // (or, for an upsampler with one channel tile, two polyphase branches that read the same input rows)
       int rest = tile >> 1;
-      const int cpairs = rt.c_tiles >> 1;
-      wk.ct = 2 * (rest % cpairs) + (tile & 1); rest /= cpairs;
-      wk.phase = rest % a.n_phases; rest /= a.n_phases;
+      if (rt.pair_phase) {
+        const int ppairs = a.n_phases >> 1;
+        wk.ct = rest % rt.c_tiles; rest /= rt.c_tiles;
+        wk.phase = 2 * (rest % ppairs) + (tile & 1); rest /= ppairs;
+      } else {
+        const int cpairs = rt.c_tiles >> 1;
+        wk.ct = 2 * (rest % cpairs) + (tile & 1); rest /= cpairs;
+        wk.phase = rest % a.n_phases; rest /= a.n_phases;
+      }
       wk.tt = rest % rt.t_tiles; wk.b = rest / rt.t_tiles;
       wk.row_ok = true;
     } else if constexpr (CL == 1) {
@@ -1093,8 +1101,15 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
   // first upsampler 207 -> 180, conv_pre 74 -> 66; the HBM-bound k=3 residual convs get slightly slower (113 -> 125 us:
   // two CTAs in lock step share one tile's epilogue traffic pattern), so RES epilogues pair up from 5 taps on.
   const bool pair_mode = (a.epi.mode == EPI_ACT && a.taps > 1) || (a.epi.mode == EPI_RES && a.taps >= 5);
-  if (!(flags & MBV_FLAG_NO_CTA_PAIRS) && prec >= 2 && pair_mode && plan->c_tiles % 2 == 0 && num_sms >= 2 && n_time % 16 == 0) {
+  // A pair is two channel tiles of one time tile or -- polyphase upsamplers with an odd number of channel tiles -- two
+  // branches that read the same input rows (k16 / stride 4: branches (0,1) and (2,3) have the same first input row).
+  bool phase_pairs = (plan->c_tiles % 2 != 0) && (a.n_phases % 2 == 0);
+  for (int r = 0; phase_pairs && r + 1 < a.n_phases; r += 2) phase_pairs = a.shift0[r] == a.shift0[r + 1];
+  plan->pair_phase = 0;
+  if (!(flags & MBV_FLAG_NO_CTA_PAIRS) && prec >= 2 && pair_mode && (plan->c_tiles % 2 == 0 || phase_pairs) && num_sms >= 2 &&
+      n_time % 16 == 0) {
     plan->cluster = 2;
+    plan->pair_phase = (plan->c_tiles % 2 == 0) ? 0 : 1;
     plan->slab_rows = n_time / 2 + halo;
     plan->n_boxes = 1;
     plan->box_rows = (plan->slab_rows + 7) / 8 * 8;
@@ -1341,6 +1356,7 @@ cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStr
   rt.w_resident = p.w_resident;
   rt.rotate = (p.c_tiles == 2 && (p.grid & 1) == 0 && p.total_tiles > p.grid) ? 1 : 0;
   rt.cluster = p.cluster; rt.rows = p.rows; rt.groups = p.groups;
+  rt.pair_phase = p.pair_phase;
   if (p.cluster) rt.rotate = 0;
   rt.split_from = p.total_tiles; rt.split_k = 1; rt.split_n = p.n_time; rt.virt_tiles = p.total_tiles;
   static const int no_split = getenv("MBV_NO_SPLIT") ? atoi(getenv("MBV_NO_SPLIT")) : 0;  // A/B measurements only

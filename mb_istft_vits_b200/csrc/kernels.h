@@ -15,6 +15,7 @@ struct TcPlan {
   CUtensorMap tmB;      // weights: 2-D (Cp_in, phases*taps*N_total), box (KB, 128), 128B swizzle
   CUtensorMap tmR;      // residual input (EPI_RES xin): 3-D (C, rows, B), box (128, n_time, 1), used for L2 prefetch only
   CUtensorMap tmBh;     // weights with a 64-row box: the half tile a CTA of a cluster pair fetches and multicasts
+  int pair_phase;       // cluster == 2: pairs are polyphase branches instead of channel tiles
   int cluster, rows, groups;  // cluster mode (pairs of CTAs share every weight tile): see conv_tc.cu
   int prefetch_res;     // 1: tmR is valid
   int n_time;           // time columns per tile (UMMA N)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise an ncu launch list (CSV of `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
---clock-control none --csv ... python bench.py --steps 1 --warmup 1 --no-cpu --no-graph`) into the per-launch DRAM
+--clock-control none --csv ... python tools/profile_step.py`) into the per-launch DRAM
 traffic figures bench.py reports as `roofline.traffic`.
 
     python tools/make_traffic.py profiles/r02_launches.csv profiles/r02_traffic.json
@@ -21,7 +21,7 @@ def main(src, dst):
         d.setdefault(int(r[0]), {"name": r[4]})[r[12]] = float(r[14].replace(",", ""))
     # one step = from a pack_input launch to the tail launch that follows it; take the LAST complete step
     ids = sorted(d)
-    tails = [i for i in ids if "tail_mb" in d[i]["name"] or "tail_kernel" in d[i]["name"]]
+    tails = [i for i in ids if "tail_mb" in d[i]["name"] or "tail_kernel" in d[i]["name"] or "tail_fused" in d[i]["name"]]
     packs = [i for i in ids if "pack_input" in d[i]["name"]]
     # candidate steps: a pack_input launch up to the first tail launch after it; the full hot-path step (flow + decoder)
     # is the longest such run (decoder-only and stand-alone tail launches of the bench are shorter)
