@@ -100,6 +100,8 @@ struct TcRt {  // runtime scalars the kernel needs beyond ConvArgs
   // the tile width.)
   int split_from, split_k, split_n, virt_tiles;
   int pair_phase;    // CTA pairs (CL == 2): the pair is two polyphase branches with equal input shift instead of two channel tiles
+  int res_off;       // > 0: byte offset of the per-warp residual staging rings (two 2 KB stages per epilogue warp): the 2-byte
+                     // residual input of chunk i+1 is fetched by TMA while chunk i is processed (EPI_RES / EPI_RS, RH != 0)
   int pdl;           // launch with programmatic stream serialization
   int rotate;        // two channel tiles, even grid: swap which one a CTA takes every round.  With a static round-robin
                      // an even CTA would otherwise ALWAYS get channel tile 0; when the second tile is half padding
@@ -151,7 +153,9 @@ __device__ __forceinline__ void epi_act(const EpiParams& p, int b, int n, int ph
   }
 }
 
-template <typename Op, int STEP, bool FULL, int RH>
+// FOLDED: the caller (staged residual path of conv_tc_kernel) has already inverted the leaky-relu of a single-stream
+// residual and added the running ResBlock sum xs into xpre.
+template <typename Op, int STEP, bool FULL, int RH, bool FOLDED>
 __device__ __forceinline__ void epi_res(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
                                         size_t rstep, const float* acc, const float* xpre) {
   using T = typename Op::T;
@@ -161,19 +165,19 @@ __device__ __forceinline__ void epi_res(const EpiParams& p, int b, int n, int ph
   float x[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) x[i] = xpre[i];  // xin, prefetched while the MMAs of this tile were running
-  if constexpr (RH == 2) {
+  if constexpr (RH == 2 && !FOLDED) {
     const float inv = p.inv_slope;
 #pragma unroll
     for (int i = 0; i < 32; ++i) x[i] = fminf(x[i], x[i] * inv);  // inverse leaky-relu (inv_slope >= 1): v < 0 -> v / slope
   }
   const int sm = p.sum_mode;
-  if (sm == 2 || sm == 3) {
+  if (!FOLDED && (sm == 2 || sm == 3)) {
     float sv[32];
     const typename ResT<RH>::T* sp = reinterpret_cast<const typename ResT<RH>::T*>(p.xs) + base;
 #pragma unroll
     for (int i = 0; i < 32; ++i) { sv[i] = 0.f; MBV_EL(i) sv[i] = res_ld<RH>(sp + i * step); }
 #pragma unroll
-    for (int i = 0; i < 32; ++i) x[i] = (x[i] + acc[i] + bias) + sv[i];
+    for (int i = 0; i < 32; ++i) x[i] = (x[i] + sv[i]) + acc[i] + bias;  // same order as the staged path: bit-identical
   } else {
 #pragma unroll
     for (int i = 0; i < 32; ++i) x[i] = x[i] + acc[i] + bias;
@@ -280,11 +284,11 @@ __device__ __forceinline__ void epi_post(const EpiParams& p, int b, int n, int p
   for (int i = 0; i < 32; ++i) MBV_EL(i) { zo[i * step] = z[i]; op_store1<Op>(dst + i * step, z[i]); }
 }
 
-template <typename Op, int MODE, int STEP, bool FULL, int RH>
+template <typename Op, int MODE, int STEP, bool FULL, int RH, bool FOLDED>
 __device__ __forceinline__ void epi_dispatch(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
-                                             size_t rstep, const float* acc, const float* acc2, const float* xpre) {
+                                             size_t rstep, const float* acc, const float* xpre) {
   if constexpr (MODE == EPI_ACT) epi_act<Op, STEP, FULL, RH>(p, b, n, phase, t_first, nt, rstep, acc);
-  else if constexpr (MODE == EPI_RES) epi_res<Op, STEP, FULL, RH>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
+  else if constexpr (MODE == EPI_RES) epi_res<Op, STEP, FULL, RH, FOLDED>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
   else if constexpr (MODE == EPI_F32) epi_f32<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc);
   else if constexpr (MODE == EPI_RS) epi_rs<Op, STEP, FULL, RH>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
   else epi_post<Op, STEP, FULL>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
@@ -330,24 +334,24 @@ __device__ __forceinline__ void epi_prefetch(const EpiParams& p, int b, int n, i
 
 // LD: compile-time channel pitch of the destination buffers (0 = runtime).  The immediate-offset fast path also
 // needs row_mul == 1 (everything but the polyphase upsamplers).
-template <typename Op, int MODE, int LD, int RH>
+template <typename Op, int MODE, int LD, int RH, bool FOLDED = false>
 __device__ __forceinline__ void tc_epilogue32(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
-                                              const float* acc, const float* acc2, const float* xpre) {
+                                              const float* acc, const float* xpre) {
   const size_t rstep = (size_t)p.row_mul * p.ld;
   if (LD > 0 && p.row_mul == 1) {
-    if (nt == 32) epi_dispatch<Op, MODE, LD, true, RH>(p, b, n, phase, t_first, nt, rstep, acc, acc2, xpre);
-    else epi_dispatch<Op, MODE, LD, false, RH>(p, b, n, phase, t_first, nt, rstep, acc, acc2, xpre);
+    if (nt == 32) epi_dispatch<Op, MODE, LD, true, RH, FOLDED>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
+    else epi_dispatch<Op, MODE, LD, false, RH, FOLDED>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
   } else {
-    if (nt == 32) epi_dispatch<Op, MODE, 0, true, RH>(p, b, n, phase, t_first, nt, rstep, acc, acc2, xpre);
-    else epi_dispatch<Op, MODE, 0, false, RH>(p, b, n, phase, t_first, nt, rstep, acc, acc2, xpre);
+    if (nt == 32) epi_dispatch<Op, MODE, 0, true, RH, FOLDED>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
+    else epi_dispatch<Op, MODE, 0, false, RH, FOLDED>(p, b, n, phase, t_first, nt, rstep, acc, xpre);
   }
 }
 
 template <typename Op, int MODE, int LD, int RH, int CL>
 __global__ void __launch_bounds__(TcThreads<MODE>::value, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmWh, const ConvArgs a,
-               const TcRt rt) {
+               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmWh,
+               const __grid_constant__ CUtensorMap tmS, const ConvArgs a, const TcRt rt) {
   using T = typename Op::T;
   constexpr int KB = TC_ROW_BYTES / (int)sizeof(T);  // channels per k-block
   constexpr int TC_EPI_WARPS = EpiWarps<MODE>::value;
@@ -359,7 +363,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   uint8_t* smW = smX + (size_t)rt.n_slab_stages * rt.slab_stage_bytes;   // weight tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(smW + (size_t)rt.n_w_stages * rt.w_stage_bytes);
   const int iXF = 0, iXE = iXF + rt.n_slab_stages, iWF = iXE + rt.n_slab_stages, iWE = iWF + rt.n_w_stages;
-  const int iCF = iWE + rt.n_w_stages, iCE = iCF + 2, nBars = iCE + 2;
+  constexpr bool kStagedRes = (MODE == EPI_RES || MODE == EPI_RS) && RH != 0;  // 2-byte residual input: may be staged by TMA
+  const int iCF = iWE + rt.n_w_stages, iCE = iCF + 2, iRF = iCE + 2, nBars = iRF + (kStagedRes ? 2 * TC_EPI_WARPS : 0);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + nBars);
   float* xchg = reinterpret_cast<float*>(smem + rt.xchg_off);  // EPI_GATE: sigmoid -> tanh warp exchange, 4 pairs x 2 x 4 KB
 
@@ -376,6 +381,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     for (int i = 0; i < rt.n_w_stages; ++i) { mbar_init(BAR(iWF + i), 1); mbar_init(BAR(iWE + i), (CL == 1) ? 2 : 1); }
     // CTA pairs (CL == 2): the even CTA issues the MMAs of both, so ITS accumulator-free barrier collects the epilogue warps of both
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(iCF + i), 1); mbar_init(BAR(iCE + i), (CL == 2) ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
+    if constexpr (kStagedRes) {
+      for (int i = 0; i < 2 * TC_EPI_WARPS; ++i) mbar_init(BAR(iRF + i), 1);
+      tma_prefetch_desc(&tmR);
+      tma_prefetch_desc(&tmS);
+    }
     fence_barrier_init();
   }
   if (warp == TC_WARP_MMA) {
@@ -586,7 +596,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     int sc = 0;
     uint32_t pc = 0;
 
-    struct TileInfo { int b, n, phase, t0, t_lim, n_cols; bool valid, row_ok; };
+    struct TileInfo { int b, n, nb, phase, t0, t_lim, n_cols; bool valid, row_ok, wv; };
     auto decode = [&](int tile) {
       TileInfo ti;
       const Work wk = decode_work(tile);
@@ -597,6 +607,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       ti.t0 = wk.tt * rt.n_time + wk.t_off;
       ti.n_cols = wk.n_cols;
       ti.n = ct * TC_M + q * 32 + lane;  // weight row = output channel of this thread
+      ti.nb = ct * TC_M + q * 32;        // first channel of this warp: its 32 channels are 64 contiguous bytes of a residual row
+      ti.wv = ti.nb < a.epi.ld && ti.nb < n_valid;
       // which logical channel does this row write, and is it inside the destination buffer?
       if (MODE == EPI_RS && a.epi.n_split > 0) ti.valid = (ti.n < a.epi.n_split ? ti.n : ti.n - a.epi.n_split) < n_valid;
       else if (MODE == EPI_GATE) ti.valid = (64 * ct + ((q * 32 + lane) & 63)) < n_valid;  // logical channel of this row
@@ -626,11 +638,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
     // (Measured and dropped: keeping the fp16 residual packed two-per-register and loading it one chunk AHEAD -- same
     //  register count on paper -- spilled ~100 bytes and made every ResBlock conv 5-10 % slower, 8.9 -> 9.3 ms per step.)
+    // Staged residual (kStagedRes): every epilogue warp owns one 2 KB shared-memory buffer + mbarrier per
+    // staged stream (the residual input xin and, for the ResBlock-sum epilogues, the running sum xs).  A chunk's values are
+    // copied to registers at its very start, and the ONE TMA box per stream (32 channels x 32 rows of the 2-byte tensor,
+    // rows past the utterance zero-filled) for the warp's NEXT chunk -- of this tile or the first one of its next tile --
+    // is requested right away, so it is in flight while this chunk is processed: the loads cost no registers, no LSU
+    // queue slots behind the warp's own stores, and their DRAM latency is off the chunk's critical path (per-chunk
+    // stamps of the register path: 1-2 K of a chunk's 3 K cycles went into issuing and awaiting 32 two-byte loads,
+    // profiles/r02_res_epilogue_timeline.txt; the synchronous xs loads made the summing c2 convs 25 % slower still).
+    constexpr bool staged = kStagedRes;  // (the planner refuses these epilogues without the staging buffers)
+    const bool staged_xs = staged && MODE == EPI_RES && (a.epi.sum_mode == 2 || a.epi.sum_mode == 3);
+    const uint32_t res_buf = smem_u32(smem + rt.res_off) + (uint32_t)warp * 2048u;
+    const uint32_t xs_buf = res_buf + (uint32_t)TC_EPI_WARPS * 2048u;
+    const uint32_t bar_r = BAR(iRF + 2 * warp), bar_s = BAR(iRF + 2 * warp + 1);
+    auto has_load = [&](const TileInfo& t, int c) { return t.wv && c < t.n_cols && t.t0 + c < t.t_lim; };
+    auto res_issue = [&](const TileInfo& t, int c) {
+      if (elect_one()) {
+        mbar_expect_tx(bar_r, 2048u);
+        tma_load_3d(res_buf, &tmR, bar_r, t.nb, t.t0 + c, t.b);
+        if (staged_xs) {
+          mbar_expect_tx(bar_s, 2048u);
+          tma_load_3d(xs_buf, &tmS, bar_s, t.nb, t.t0 + c, t.b);
+        }
+      }
+      __syncwarp();
+    };
+    uint32_t rph = 0;       // phase of the warp's staging barriers
+    bool rpending = false;  // the boxes of the next chunk this warp consumes have been requested
+
     float xcur[32];
     int gate_chunk = 0;
     int tile = blockIdx.x;
     TileInfo ti = decode(tile);
-    if (kPrefetch && tile < rt.virt_tiles)
+    if (kPrefetch && !staged && tile < rt.virt_tiles)
       for (int j = 0; j < nch; ++j) l2_prefetch(ti, c_first + CSTEP * j);
 
     while (tile < rt.virt_tiles) {
@@ -638,9 +678,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       TileInfo tn = ti;
       if (have_next) {
         tn = decode(tile + gridDim.x);
-        if (tn.row_ok) for (int j = 0; j < nch; ++j) l2_prefetch(tn, c_first + CSTEP * j);
+        if (tn.row_ok && !staged) for (int j = 0; j < nch; ++j) l2_prefetch(tn, c_first + CSTEP * j);
       }
       if (!ti.row_ok) { ti = tn; tile += gridDim.x; continue; }  // cluster mode: this CTA only relayed weights for this tile
+      if constexpr (kStagedRes) {
+        if (!rpending && has_load(ti, c_first)) { res_issue(ti, c_first); rpending = true; }  // cold start
+      }
       mbar_wait(BAR(iCF + sc), pc);
       tc_fence_after();
       if (rt.dbg && warp == 0 && lane == 0) rt.dbg[((size_t)blockIdx.x * 7 + 2) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
@@ -658,7 +701,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           cdbg = rt.dbg + ((size_t)blockIdx.x * 7 + 3) * 64 + ((tile / gridDim.x) * 3 + (c - c_first) / CSTEP) * 4;
         if (cdbg) cdbg[0] = clock64();
         tmem_ld32(taddr + (uint32_t)c, acc);
-        if constexpr (kPrefetch) prefetch(ti, c, xcur);  // residual of THIS chunk, in flight with the TMEM load
+        if constexpr (kStagedRes) {
+          if (has_load(ti, c)) {
+            if (!rpending) res_issue(ti, c);
+            mbar_wait(bar_r, rph);
+            const uint32_t src = res_buf + (uint32_t)lane * 2u;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              unsigned short hv;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(src + (uint32_t)i * 64u));
+              xcur[i] = __half2float(__ushort_as_half(hv));
+            }
+            if constexpr (MODE == EPI_RES && RH == 2) {  // single stream: xin holds lrelu(x); inverse leaky-relu (inv_slope >= 1)
+              const float inv = a.epi.inv_slope;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) xcur[i] = fminf(xcur[i], xcur[i] * inv);
+            }
+            if constexpr (MODE == EPI_RES) {
+              if (staged_xs) {  // running ResBlock sum: folded into the residual here, epi_res then skips its own xs loads
+                mbar_wait(bar_s, rph);
+                const uint32_t ssrc = xs_buf + (uint32_t)lane * 2u;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  unsigned short hv;
+                  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(ssrc + (uint32_t)i * 64u));
+                  xcur[i] += __half2float(__ushort_as_half(hv));
+                }
+              }
+            }
+            rph ^= 1u;
+            __syncwarp();  // every lane has copied its values out before the next boxes may land in the buffers
+            // request the next chunk of this warp: the next one of this tile, else the first one of its next tile
+            const int nc = c + CSTEP;
+            rpending = false;
+            if (nc < ti.n_cols) { if (has_load(ti, nc)) { res_issue(ti, nc); rpending = true; } }
+            else if (have_next && tn.row_ok && has_load(tn, c_first)) { res_issue(tn, c_first); rpending = true; }
+          }
+        }
+        if constexpr (kPrefetch && !kStagedRes) prefetch(ti, c, xcur);  // residual of THIS chunk, in flight with the TMEM load
         tmem_ld_wait();
         if (cdbg) {
           cdbg[1] = clock64();
@@ -705,7 +785,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             }
           }
         } else if (ti.valid && t_first < ti.t_lim) {
-          tc_epilogue32<Op, MODE, LD, RH>(a.epi, ti.b, ti.n, ti.phase, t_first, min(ti.t_lim - t_first, 32), acc, nullptr, xcur);
+          tc_epilogue32<Op, MODE, LD, RH, kStagedRes>(a.epi, ti.b, ti.n, ti.phase, t_first, min(ti.t_lim - t_first, 32), acc, xcur);
         }
         if (cdbg) cdbg[3] = clock64();
       }
@@ -1006,7 +1086,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const bool live = t_first < t_lim;
         if (live) epi_prefetch<EPI_RES, LD, RH>(a.epi, b, n, t_first, min(t_lim - t_first, 32), xcur);
         tmem_ld_wait();
-        if (live) tc_epilogue32<Op, EPI_RES, LD, RH>(a.epi, b, n, 0, t_first, min(t_lim - t_first, 32), acc, nullptr, xcur);
+        if (live) tc_epilogue32<Op, EPI_RES, LD, RH>(a.epi, b, n, 0, t_first, min(t_lim - t_first, 32), acc, xcur);
       }
       tc_fence_before();
       __syncwarp();
@@ -1073,9 +1153,23 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
   plan->slab_stage_bytes = ((plan->n_boxes * plan->box_rows * TC_ROW_BYTES + 1023) / 1024) * 1024;
   plan->w_stage_bytes = TC_M * TC_ROW_BYTES;
   const int xchg = a.gate ? 32 * 1024 : 0;
+  // Staged residual input (see the epilogue warps): two 2 KB TMA stages + two mbarriers per epilogue warp, for the
+  // epilogues that read a 2-byte residual tensor (those kernels have no register-load path; measured against it at
+  // this commit's parent, profiles/round2_res_stage_ab.txt: every residual-add launch 2-6 % faster, the step 1.7-2 %).
+  const bool staged_mode = (a.epi.mode == EPI_RES || a.epi.mode == EPI_RS) && a.epi.res_half != 0 && prec >= 2;
+  const bool want_staged = staged_mode;
+  if (staged_mode && (a.epi.xin == nullptr || a.epi.row_mul != 1 || (a.epi.mode == EPI_RS && a.epi.n_split < a.N_total)))
+    return "tcgen05 conv: a 2-byte residual epilogue needs xin, unit row mapping and residual rows only";
+  const int kStagedWarps = EpiWarps<EPI_RES>::value;
+  static_assert(EpiWarps<EPI_RES>::value == EpiWarps<EPI_RS>::value, "staged residual rings are sized for both modes");
+  const bool staged_xs = want_staged && a.epi.mode == EPI_RES && (a.epi.sum_mode == 2 || a.epi.sum_mode == 3) && a.epi.xs != nullptr;
+  if (want_staged && a.epi.mode == EPI_RES && (a.epi.sum_mode == 2 || a.epi.sum_mode == 3) && !staged_xs)
+    return "tcgen05 conv: summing residual epilogue without a running-sum buffer";
+  const int res_bytes = want_staged ? kStagedWarps * 2048 * (staged_xs ? 2 : 1) : 0;
+  const int extra_bars = staged_mode ? 2 * kStagedWarps : 0;
   // Bytes in flight are what hide the ~1.3 us L2->SMEM TMA round trip (measured: with 5 x 16 KB weight stages the MMA
   // warp found its weights missing on 45 % of its waits): give the weight ring everything two slab stages leave over.
-  const int budget = 222 * 1024 - xchg;
+  const int budget = 222 * 1024 - xchg - res_bytes;
   // A slab lasts taps x 512 tensor-core cycles: few taps need more slabs in flight, many taps more weight stages.
   plan->n_slab_stages = a.taps == 1 ? 4 : (a.taps <= 4 ? 3 : 2);
   while (plan->n_slab_stages > 2 &&
@@ -1084,10 +1178,11 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
   plan->n_w_stages = (budget - plan->n_slab_stages * plan->slab_stage_bytes) / plan->w_stage_bytes;
   if (plan->n_w_stages > 10) plan->n_w_stages = 10;
   if (plan->n_w_stages < 2) return "tcgen05 conv: not enough shared memory for two weight stages";
-  const int nbars = 2 * plan->n_slab_stages + 2 * plan->n_w_stages + 4;
+  const int nbars = 2 * plan->n_slab_stages + 2 * plan->n_w_stages + 4 + extra_bars;
   plan->xchg_off = (plan->n_slab_stages * plan->slab_stage_bytes + plan->n_w_stages * plan->w_stage_bytes + nbars * 8 + 16 +
                     127) / 128 * 128;
-  plan->smem_bytes = 1024 + plan->xchg_off + xchg;
+  plan->res_off = want_staged ? plan->xchg_off + xchg : 0;
+  plan->smem_bytes = 1024 + plan->xchg_off + xchg + res_bytes;
   if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;  // one CTA per SM: each CTA owns all 512 TMEM columns
   plan->grid = plan->total_tiles < num_sms ? plan->total_tiles : num_sms;
   if (plan->grid < 1) plan->grid = 1;
@@ -1117,9 +1212,10 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
     plan->n_slab_stages = a.taps <= 4 ? 4 : 3;
     plan->n_w_stages = (budget - plan->n_slab_stages * plan->slab_stage_bytes) / plan->w_stage_bytes;
     if (plan->n_w_stages > 10) plan->n_w_stages = 10;
-    const int nb2 = 2 * plan->n_slab_stages + 2 * plan->n_w_stages + 4;
+    const int nb2 = 2 * plan->n_slab_stages + 2 * plan->n_w_stages + 4 + extra_bars;
     plan->xchg_off = (plan->n_slab_stages * plan->slab_stage_bytes + plan->n_w_stages * plan->w_stage_bytes + nb2 * 8 + 16 + 127) / 128 * 128;
-    plan->smem_bytes = 1024 + plan->xchg_off + xchg;
+    plan->res_off = want_staged ? plan->xchg_off + xchg : 0;
+    plan->smem_bytes = 1024 + plan->xchg_off + xchg + res_bytes;
     if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;
     plan->grid = (plan->total_tiles < num_sms ? plan->total_tiles : num_sms) & ~1;  // whole pairs (total_tiles is even)
   }
@@ -1174,18 +1270,32 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
     if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed for the half-tile weight map";
   }
   plan->prefetch_res = 0;
-  if (a.epi.mode == EPI_RES && a.epi.xin != nullptr && a.epi.row_mul == 1) {
+  if ((a.epi.mode == EPI_RES || want_staged) && a.epi.xin != nullptr && a.epi.row_mul == 1) {
     const int rs = a.epi.res_half ? 2 : 4;
     cuuint64_t dims[3] = {(cuuint64_t)a.epi.ld, (cuuint64_t)a.epi.rows_res, (cuuint64_t)a.B};
     cuuint64_t strides[2] = {(cuuint64_t)a.epi.ld * rs, (cuuint64_t)a.epi.rows_res * a.epi.ld * rs};
     cuuint32_t box[3] = {(cuuint32_t)(a.epi.ld < TC_M ? a.epi.ld : TC_M), (cuuint32_t)n_time, 1};
+    if (want_staged) { box[0] = 32; box[1] = 32; }  // one epilogue warp's chunk: 32 channels (64 B) x 32 rows
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&plan->tmR, a.epi.res_half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                      const_cast<void*>(a.epi.xin), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r == CUDA_SUCCESS) plan->prefetch_res = 1;  // a failed encode only loses the prefetch
   }
-  if (!plan->prefetch_res) plan->tmR = plan->tmA;  // placeholder, never dereferenced
+  if (!plan->prefetch_res) {
+    if (want_staged) return "cuTensorMapEncodeTiled failed for the residual map";
+    plan->tmR = plan->tmA;  // placeholder, never dereferenced
+  }
+  plan->tmS = plan->tmR;
+  if (plan->res_off > 0 && staged_xs) {  // the running ResBlock sum: same geometry as the residual tensor
+    cuuint64_t dims[3] = {(cuuint64_t)a.epi.ld, (cuuint64_t)a.epi.rows_res, (cuuint64_t)a.B};
+    cuuint64_t strides[2] = {(cuuint64_t)a.epi.ld * 2, (cuuint64_t)a.epi.rows_res * a.epi.ld * 2};
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&plan->tmS, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, a.epi.xs, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return "cuTensorMapEncodeTiled failed for the running-sum map";
+  }
   return nullptr;
 }
 
@@ -1217,7 +1327,7 @@ static cudaError_t launch_one_cl(const ConvArgs& a, const TcPlan& p, const TcRt&
     attr[1].val.clusterDim.z = 1;
     cfg.numAttrs = 2;
   }
-  return cudaLaunchKernelEx(&cfg, k, p.tmA, p.tmB, p.tmR, p.tmBh, a, rt);
+  return cudaLaunchKernelEx(&cfg, k, p.tmA, p.tmB, p.tmR, p.tmBh, p.tmS, a, rt);
 }
 
 template <typename Op, int MODE, int LD, int RH>
@@ -1353,6 +1463,7 @@ cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStr
   rt.t_tiles = p.t_tiles; rt.c_tiles = p.c_tiles; rt.total_tiles = p.total_tiles;
   rt.prefetch_res = p.prefetch_res;
   rt.xchg_off = p.xchg_off;
+  rt.res_off = p.res_off;
   rt.w_resident = p.w_resident;
   rt.rotate = (p.c_tiles == 2 && (p.grid & 1) == 0 && p.total_tiles > p.grid) ? 1 : 0;
   rt.cluster = p.cluster; rt.rows = p.rows; rt.groups = p.groups;

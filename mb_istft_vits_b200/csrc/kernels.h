@@ -13,7 +13,8 @@ cudaError_t launch_conv_simt(int prec, const ConvArgs& a, cudaStream_t st);
 struct TcPlan {
   CUtensorMap tmA;      // activations: 3-D (Cp_in, L_in, B), box (KB, box_rows, 1), 128B swizzle
   CUtensorMap tmB;      // weights: 2-D (Cp_in, phases*taps*N_total), box (KB, 128), 128B swizzle
-  CUtensorMap tmR;      // residual input (EPI_RES xin): 3-D (C, rows, B), box (128, n_time, 1), used for L2 prefetch only
+  CUtensorMap tmR;      // residual input (EPI_RES xin): 3-D (C, rows, B), box (32, 32, 1): the staged residual chunks of the epilogue warps
+  CUtensorMap tmS;      // running ResBlock sum xs of the summing residual epilogues, same box as tmR
   CUtensorMap tmBh;     // weights with a 64-row box: the half tile a CTA of a cluster pair fetches and multicasts
   int pair_phase;       // cluster == 2: pairs are polyphase branches instead of channel tiles
   int cluster, rows, groups;  // cluster mode (pairs of CTAs share every weight tile): see conv_tc.cu
@@ -23,6 +24,7 @@ struct TcPlan {
   int slab_stage_bytes, w_stage_bytes, n_slab_stages, n_w_stages;
   int t_tiles, c_tiles, total_tiles;
   int xchg_off;         // byte offset of the gate exchange buffer
+  int res_off;          // > 0: byte offset of the per-warp staged-residual rings (tmR then has a 32 x 32 box)
   int w_resident;       // weights of the single channel tile stay resident in the ring
   int smem_bytes;
   int grid;

@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--out", default=None)
     ap.add_argument("--flags", type=int, default=0, help="extra mbv_config flags (16 = fused pairs, 32 = cluster pairs)")
+    ap.add_argument("--ab-flags", type=int, default=None,
+                    help="A/B: a second engine with these flags, run alternately with the first in the same process; prints both columns")
     a = ap.parse_args()
     cfg = get_config(a.config)
     sd = synth.make_state_dict(cfg, seed=1234)
@@ -36,18 +38,44 @@ def main():
     g = None
     if cfg.get("gin_channels", 0):
         g = torch.randn((a.batch, cfg["gin_channels"], 1), generator=torch.Generator().manual_seed(7)).cuda()
+    engb = Engine(cfg, sd, precision=a.precision, flags=a.ab_flags) if a.ab_flags is not None else None
     for _ in range(3):
         eng.flow_decode(z_p, mask, g, want_z=False)
+        if engb is not None:
+            engb.flow_decode(z_p, mask, g, want_z=False)
     torch.cuda.synchronize()
-    eng.set_profiling(True)
-    eng.profile_read()
-    runs = []
+    runs, runs_b = [], []
+    for e, r in ((eng, runs), (engb, runs_b)):
+        if e is not None:
+            e.set_profiling(True)
+            e.profile_read()
     for _ in range(a.reps):
-        eng.flow_decode(z_p, mask, g, want_z=False)
-        torch.cuda.synchronize()
-        runs.append(eng.profile_read_launches())
+        for e, r in ((eng, runs), (engb, runs_b)):
+            if e is None:
+                continue
+            e.flow_decode(z_p, mask, g, want_z=False)
+            torch.cuda.synchronize()
+            r.append(e.profile_read_launches())
     eng.set_profiling(False)
     n = len(runs[0])
+    if engb is not None:  # interleaved A/B: same box, same clock state
+        nb = len(runs_b[0])
+        med = lambda rr, i: sorted(x[i][1] for x in rr)[len(rr) // 2] * 1e3
+        lines = ["A: flags %d   B: flags %d   (median of %d alternating repetitions, us)" % (a.flags, a.ab_flags, a.reps)]
+        ta = tb = 0.0
+        for i in range(max(n, nb)):
+            ua = med(runs, i) if i < n else float("nan")
+            ub = med(runs_b, i) if i < nb else float("nan")
+            ta += ua if i < n else 0.0
+            tb += ub if i < nb else 0.0
+            d = runs[0][i][0] if i < n else runs_b[0][i][0]
+            lines.append("%3d  %-52s A %8.1f  B %8.1f  B-A %+7.1f" % (i, d, ua, ub, ub - ua))
+        lines.append("sum of launches: A %.3f ms (%d launches)   B %.3f ms (%d launches)" % (ta / 1e3, n, tb / 1e3, nb))
+        txt = "\n".join(lines)
+        print(txt)
+        if a.out:
+            open(a.out, "w").write(txt + "\n")
+        return
     lines = []
     total = 0.0
     B = a.batch
