@@ -615,7 +615,7 @@ def run_native(args):
     traffic = {}
     tp = os.path.join(ROOT, "profiles", "traffic.json")   # written by tools/make_traffic.py from the latest ncu launch list
     if not os.path.exists(tp):
-        tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "round2_traffic.json")
     if os.path.exists(tp) and args.precision == "bf16" and B == B_PER_GPU and T == T_FRAMES:
         traffic = json.load(open(tp))  # dram__bytes_read+write per launch from the committed ncu capture of this workload
     conv_ev_ms, conv_n = prof["conv"]
