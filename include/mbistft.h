@@ -98,6 +98,9 @@ typedef struct {
                                      * (conv_pre, first upsampler, 256-channel ResBlocks) as cta_group::2 MMAs over CTA pairs
                                      * (one MMA spans two channel tiles, M = 256; each CTA stages half of the activation rows --
                                      * DESIGN.md section 4.1c).  Results are bit-identical either way. */
+#define MBV_FLAG_NO_PW 512          /* A/B and cross-check tests: run the 1x1 convs of the WN stacks (coupling-layer pre, WN residual convs)
+                                     * on the generic conv kernel (output channel on the accumulator lane) instead of pw_tc_kernel
+                                     * (time on the lane, 256-bit epilogue accesses) */
 #define MBV_FLAG_SPLIT_TAIL 128     /* keep conv_post as its own conv launch writing fp32 logits for the stand-alone tail kernel instead
                                      * of the fused conv_post + tail kernel (the default on the 16-bit paths; A/B and cross-check tests) */
 #define MBV_FLAG_BRANCHES 64         /* experimental: run the parallel ResBlocks of a stage on the library's two extra streams (own

@@ -1128,6 +1128,8 @@ static EncodeTiledFn get_encode_fn() {
 const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, TcPlan* plan) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return "cuTensorMapEncodeTiled entry point unavailable";
+  plan->pw = 0;
+  if (pw_eligible(prec, a, flags)) return pw_make_plan(prec, a, num_sms, plan);  // 1x1 convs of the WN stacks: pw_tc.cu
   const int esize = prec >= 2 ? 2 : 4;
   const int KB = TC_ROW_BYTES / esize;
   if (a.Cp_in % 64 != 0) return "tcgen05 conv: padded input channels must be a multiple of 64";
@@ -1420,7 +1422,7 @@ cudaError_t tc_set_attributes() {
         if (e != cudaSuccess) return e;
       }
     }
-  return cudaSuccess;
+  return pw_set_attributes();
 }
 
 // MBV_TIMELINE=<mode>: after every launch whose epilogue mode matches, print CTA 0's per-tile clock stamps (debug)
@@ -1447,6 +1449,7 @@ static void timeline_dump(const ConvArgs& a, const TcPlan& p, long long* dbg, cu
 }
 
 cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStream_t st, int pdl) {
+  if (p.pw) return launch_pw(prec, a, p, st, pdl);
   static long long* dbg = nullptr;
   static int dbg_mode = -2;
   if (dbg_mode == -2) {

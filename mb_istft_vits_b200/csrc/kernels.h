@@ -28,7 +28,15 @@ struct TcPlan {
   int w_resident;       // weights of the single channel tile stay resident in the ring
   int smem_bytes;
   int grid;
+  // pointwise (1x1) convs on pw_tc_kernel (time on the accumulator lane, pw_tc.cu): tmA = flattened [C, B*L] activation map,
+  // tmB = weight map with an N-row box
+  int pw, pw_N, pw_kblocks, pw_R, pw_tiles, pw_w_bytes, pw_a_stage_bytes, pw_a_stages, pw_a_off, pw_bias_off, pw_bar_off;
 };
+// ---- pw_tc.cu
+bool pw_eligible(int prec, const ConvArgs& a, int flags);
+const char* pw_make_plan(int prec, const ConvArgs& a, int num_sms, TcPlan* plan);
+cudaError_t launch_pw(int prec, const ConvArgs& a, const TcPlan& plan, cudaStream_t st, int pdl);
+cudaError_t pw_set_attributes();
 // Fills plan (tensor maps, staging, grid) for args; returns a message on failure, nullptr on success.
 const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, TcPlan* plan);
 cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& plan, cudaStream_t st, int pdl = 1);

@@ -1,0 +1,404 @@
+// pw_tc.cu -- pointwise (1x1) convs of the WaveNet stacks with TIME on the accumulator lane (sm_100a).
+//
+//   D[128 rows, N channels] = X[128 rows, K] . W[N, K]^T          rows = the flattened (utterance, time) axis, R = B * L
+//
+// The 1x1 convs of the flow / posterior encoder (ResidualCouplingLayer.pre, modules.py:328,341; the residual half of
+// WN.res_skip_layers, modules.py:135-146,169-175) are a few GFLOP each: they are bound by their epilogue, not by MMAs.
+// In conv_tc_kernel (output CHANNEL on the lane) an epilogue thread owns one channel of 32 time steps, so every load /
+// store is a 2-byte access per thread (64 bytes per warp instruction), the 192 output channels fill one and a half
+// 128-row channel tiles, and the per-row mask costs 32 loads per chunk.  Here the roles of the operands are swapped:
+//   * A = the activation tile (128 consecutive rows x 64 channels per k-block, TMA, 128B swizzle), B = ALL weight rows of
+//     the layer (N <= 256, resident in shared memory for the life of the persistent CTA), tcgen05.mma M 128, N = C_out.
+//   * an epilogue thread owns one ROW: its 32 channels of a chunk are 64 contiguous bytes of the channels-last tensors, so
+//     the residual input arrives as two 256-bit loads and every output leaves as two 256-bit stores (full 32-byte
+//     sectors, 16 x fewer memory instructions), the mask is ONE value per thread and tile, the bias a broadcast read.
+//   * a 1x1 conv has no halo: tiles are 128 rows of the flattened [B * L] axis and may straddle utterances (the mask and
+//     every address are per row), so 55 168 rows make 431 full tiles instead of 64 x 7 ragged ones.
+//   * warp roles as in conv_tc.cu: 8 epilogue warps (lane quarter x column half), TMA producer, MMA issuer; two
+//     accumulator stages in TMEM, 2-4 activation stages.
+// Epilogues (same arithmetic and operation order as conv_tc.cu): ACT  y = (acc + bias) [* mask] -> fp16 stream copy +
+// leaky-relu'd operand copy;  RS  x = (xin + acc + bias) * mask -> fp16 stream + operand copy (or, single stream, the
+// fp16 operand tensor only).  Anything else (per-utterance bias, fp32 streams, K > 256, tf32) stays on conv_tc_kernel.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "../../include/mbistft.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_ptx.cuh"
+
+namespace mbv {
+
+constexpr int PW_ROWS = 128;                       // rows per tile (UMMA M)
+constexpr int PW_EPI_WARPS = 8;
+constexpr int PW_WARP_TMA = PW_EPI_WARPS, PW_WARP_MMA = PW_EPI_WARPS + 1;
+constexpr int PW_THREADS = 32 * (PW_EPI_WARPS + 2);
+constexpr int PW_ACC_STRIDE = 256;                 // TMEM columns per accumulator stage
+constexpr int PW_KB_BYTES = PW_ROWS * TC_ROW_BYTES;  // one k-block of an activation tile (16 KB)
+constexpr int PW_MAX_CHUNKS = 4;                   // 32-channel chunks per epilogue warp (N <= 256)
+
+struct PwRt {
+  int R;          // rows in total
+  int kblocks;    // Cp_in / 64
+  int N;          // output channels = UMMA N (multiple of 32, <= 256)
+  int n_tiles;
+  int n_a_stages, a_stage_bytes, w_bytes;
+  int a_off, bias_off, bar_off;
+};
+
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
+  const __half2 h = __halves2half2(to_half_sat(a), to_half_sat(b));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <typename Op> __device__ __forceinline__ uint32_t pack_op2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack_op2<OpBF16>(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack_op2<OpF16>(float a, float b) { return pack_half2_sat(a, b); }
+
+// MODE: EPI_ACT or EPI_RS.  RH: 1 = fp16 stream (xin / xout) next to the operand copy, 2 = single stream (fp16 operands: xin is
+// the operand tensor, no xout), 0 = ACT without a stream copy.
+template <typename Op, int MODE, int RH>
+__global__ void __launch_bounds__(PW_THREADS, 1)
+pw_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmR,
+             const EpiParams p, const PwRt rt) {
+  using T = typename Op::T;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smW = smem;                  // kblocks tiles of N rows x 128 B
+  uint8_t* smA = smem + rt.a_off;       // n_a_stages x kblocks x 16 KB
+  float* s_bias = reinterpret_cast<float*>(smem + rt.bias_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + rt.bar_off);
+  const int iWF = 0, iAF = 1, iAE = iAF + rt.n_a_stages, iCF = iAE + rt.n_a_stages, iCE = iCF + 2, nBars = iCE + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + nBars);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    if constexpr (MODE == EPI_RS) tma_prefetch_desc(&tmR);
+    mbar_init(BAR(iWF), 1);
+    for (int i = 0; i < rt.n_a_stages; ++i) { mbar_init(BAR(iAF + i), 1); mbar_init(BAR(iAE + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(iCF + i), 1); mbar_init(BAR(iCE + i), PW_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == PW_WARP_MMA) tmem_alloc(smem_u32(tmem_ptr_smem), 512u);
+  // weights and bias are constants of the model (never written by a kernel of the step): fetched before the
+  // programmatic-dependency wait, so they overlap the tail of the previous kernel
+  for (int i = threadIdx.x; i < rt.N; i += PW_THREADS) s_bias[i] = p.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  if (warp == PW_WARP_TMA) {
+    if (elect_one()) {
+      mbar_expect_tx(BAR(iWF), (uint32_t)rt.w_bytes);
+      for (int kb = 0; kb < rt.kblocks; ++kb)
+        tma_load_2d(smem_u32(smW) + (uint32_t)(kb * rt.N * TC_ROW_BYTES), &tmW, BAR(iWF), kb * 64, 0);
+    }
+    __syncwarp();
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp == PW_WARP_TMA) {
+    // ===================== TMA producer: one activation tile (all k-blocks) per stage =====================
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < rt.n_tiles; tile += gridDim.x) {
+      mbar_wait(BAR(iAE + s), ph ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(BAR(iAF + s), (uint32_t)(rt.kblocks * PW_KB_BYTES));
+        const uint32_t dst = smem_u32(smA) + (uint32_t)(s * rt.a_stage_bytes);
+        for (int kb = 0; kb < rt.kblocks; ++kb)
+          tma_load_2d(dst + (uint32_t)(kb * PW_KB_BYTES), &tmX, BAR(iAF + s), kb * 64, tile * PW_ROWS);
+        if constexpr (MODE == EPI_RS) {
+          // the residual rows of this tile: asked into L2 now (the producer runs n_a_stages tiles ahead of the epilogue), so the
+          // epilogue's 256-bit loads find them there instead of paying a DRAM round trip per tile
+          for (int c = 0; c < rt.N; c += 64) tma_prefetch_l2_2d(&tmR, c, tile * PW_ROWS);
+        }
+      }
+      __syncwarp();
+      if (++s == rt.n_a_stages) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == PW_WARP_MMA) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t fmt = (Op::kPrec == 3) ? 0u : 1u;  // F16 / BF16
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(rt.N >> 3) << 17) | ((uint32_t)(PW_ROWS >> 4) << 24);
+    int s = 0, sc = 0;
+    uint32_t ph = 0, pc = 0;
+    mbar_wait(BAR(iWF), 0);
+    tc_fence_after();
+    for (int tile = blockIdx.x; tile < rt.n_tiles; tile += gridDim.x) {
+      mbar_wait(BAR(iCE + sc), pc ^ 1);
+      mbar_wait(BAR(iAF + s), ph);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(sc * PW_ACC_STRIDE);
+      for (int kb = 0; kb < rt.kblocks; ++kb) {
+        const uint32_t a_lo = desc_lo(smem_u32(smA) + (uint32_t)(s * rt.a_stage_bytes + kb * PW_KB_BYTES));
+        const uint32_t w_lo = desc_lo(smem_u32(smW) + (uint32_t)(kb * rt.N * TC_ROW_BYTES));
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma<2>(tmem_d, desc64(a_lo + 2 * k), desc64(w_lo + 2 * k), idesc, (kb | k) ? 1u : 0u);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) { tc_commit(BAR(iAE + s)); tc_commit(BAR(iCF + sc)); }
+      __syncwarp();
+      if (++s == rt.n_a_stages) { s = 0; ph ^= 1; }
+      if (++sc == 2) { sc = 0; pc ^= 1; }
+    }
+  } else {
+    // ===================== epilogue warps: one row per thread =====================
+    const int q = warp & 3;       // TMEM lane quarter = rows q*32 .. q*32+31 of the tile
+    const int half = warp >> 2;   // this warp takes the chunks at columns half*32 + 64*j
+    const size_t ld = (size_t)p.ld;
+    const uint32_t bias_s = smem_u32(s_bias);
+    int sc = 0;
+    uint32_t pc = 0;
+    for (int tile = blockIdx.x; tile < rt.n_tiles; tile += gridDim.x) {
+      const int row = tile * PW_ROWS + q * 32 + lane;
+      const bool valid = row < rt.R;
+      float m = 1.f;
+      if (p.mask != nullptr) m = valid ? p.mask[row] : 0.f;
+      // the residual input does not depend on the accumulator: all of this thread's chunks are requested before the wait
+      uint32_t res[PW_MAX_CHUNKS][16];
+      if constexpr (MODE == EPI_RS) {
+        const char* xin = reinterpret_cast<const char*>(p.xin) + ((size_t)row * ld + (size_t)(half * 32)) * 2;
+#pragma unroll
+        for (int j = 0; j < PW_MAX_CHUNKS; ++j) {
+          if (valid && half * 32 + 64 * j < rt.N) {
+            ldg256(xin + (size_t)j * 128, res[j]);
+            ldg256(xin + (size_t)j * 128 + 32, res[j] + 8);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) res[j][i] = 0u;
+          }
+        }
+      }
+      mbar_wait(BAR(iCF + sc), pc);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc * PW_ACC_STRIDE);
+#pragma unroll
+      for (int j = 0; j < PW_MAX_CHUNKS; ++j) {
+        const int c = half * 32 + 64 * j;
+        if (c < rt.N) {  // warp-uniform
+          float acc[32];
+          tmem_ld32(taddr + (uint32_t)c, acc);
+          tmem_ld_wait();
+          float x[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 b4;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(bias_s + (uint32_t)(c + i) * 4u));
+            if constexpr (MODE == EPI_RS) {
+              const __half2 h0 = *reinterpret_cast<const __half2*>(&res[j][i / 2]);
+              const __half2 h1 = *reinterpret_cast<const __half2*>(&res[j][i / 2 + 1]);
+              const float2 r0 = __half22float2(h0), r1 = __half22float2(h1);
+              x[i] = (r0.x + acc[i] + b4.x) * m;
+              x[i + 1] = (r0.y + acc[i + 1] + b4.y) * m;
+              x[i + 2] = (r1.x + acc[i + 2] + b4.z) * m;
+              x[i + 3] = (r1.y + acc[i + 3] + b4.w) * m;
+            } else {
+              x[i] = acc[i] + b4.x; x[i + 1] = acc[i + 1] + b4.y; x[i + 2] = acc[i + 2] + b4.z; x[i + 3] = acc[i + 3] + b4.w;
+              if (p.mask != nullptr) { x[i] *= m; x[i + 1] *= m; x[i + 2] *= m; x[i + 3] *= m; }
+            }
+          }
+          if (valid) {
+            const size_t off = ((size_t)row * ld + (size_t)c) * 2;
+            if constexpr (RH == 1) {  // fp16 stream copy
+              uint32_t u[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) u[i] = pack_half2_sat(x[2 * i], x[2 * i + 1]);
+              char* xo = reinterpret_cast<char*>(p.xout) + off;
+              stg256(xo, u);
+              stg256(xo + 32, u + 8);
+            }
+            if (MODE == EPI_RS || p.n_act > 0) {  // operand copy (leaky-relu'd for ACT; the WN stream is stored as is)
+              uint32_t u[16];
+              if constexpr (MODE == EPI_ACT) {
+                const float slope = p.slope;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  u[i] = pack_op2<Op>(fmaxf(x[2 * i], x[2 * i] * slope), fmaxf(x[2 * i + 1], x[2 * i + 1] * slope));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) u[i] = pack_op2<Op>(x[2 * i], x[2 * i + 1]);
+              }
+              char* ao = reinterpret_cast<char*>(p.act[0]) + off;
+              stg256(ao, u);
+              stg256(ao + 32, u + 8);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(iCE + sc));
+      if (++sc == 2) { sc = 0; pc ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == PW_WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+bool pw_eligible(int prec, const ConvArgs& a, int flags) {
+  const EpiParams& e = a.epi;
+  if (flags & MBV_FLAG_NO_PW) return false;
+  if (prec < 2 || a.taps != 1 || a.n_phases != 1 || a.shift0[0] != 0 || a.gate) return false;
+  if (a.L_in != a.L_out || a.Cp_in % 64 != 0 || a.Cp_in > 256) return false;
+  if (e.bias == nullptr || e.bias_bs != 0) return false;
+  if (e.n_valid % 32 != 0 || e.n_valid < 32 || e.n_valid > 256 || e.n_valid > a.N_total || e.ld < e.n_valid || e.ld % 16 != 0) return false;
+  if (e.row_mul != 1 || e.row_add != 0 || e.rows_out != a.L_out || e.rows_res != a.L_out || e.dup_src >= 0) return false;
+  if (e.mode == EPI_RS) {
+    if (e.res_half != 1 && e.res_half != 2) return false;
+    if (e.res_half == 2 && prec != 3) return false;
+    if (e.n_split < a.N_total || e.xin == nullptr || e.act[0] == nullptr || e.n_act != 1) return false;
+    if (e.res_half == 1 && e.xout == nullptr) return false;
+    if (e.res_half == 2 && e.inv_slope != 1.f) return false;
+    return true;
+  }
+  if (e.mode == EPI_ACT) {
+    if (e.n_act > 1 || (e.n_act == 1 && (e.act[0] == nullptr || e.act_add[0] != nullptr))) return false;
+    if (e.xout != nullptr && e.res_half != 1) return false;
+    if (e.xout == nullptr && e.n_act == 0) return false;
+    return true;
+  }
+  return false;
+}
+
+const char* pw_make_plan(int prec, const ConvArgs& a, int num_sms, TcPlan* plan) {
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(tc_tensormap_encoder());
+  if (!enc) return "cuTensorMapEncodeTiled entry point unavailable";
+  const int kblocks = a.Cp_in / 64, N = a.epi.n_valid;
+  const long long R = (long long)a.B * a.L_out;
+  if (R > 0x7fffffff - PW_ROWS) return "pointwise conv: too many rows";
+  plan->pw = 1;
+  plan->pw_N = N; plan->pw_kblocks = kblocks; plan->pw_R = (int)R;
+  plan->pw_tiles = (int)((R + PW_ROWS - 1) / PW_ROWS);
+  plan->pw_w_bytes = kblocks * N * TC_ROW_BYTES;
+  plan->pw_a_stage_bytes = kblocks * PW_KB_BYTES;
+  const int fixed = 2048;  // bias + barriers
+  int stages = (224 * 1024 - plan->pw_w_bytes - fixed) / plan->pw_a_stage_bytes;
+  if (stages > 4) stages = 4;
+  if (stages < 2) return "pointwise conv: not enough shared memory";
+  plan->pw_a_stages = stages;
+  plan->pw_a_off = plan->pw_w_bytes;
+  plan->pw_bias_off = plan->pw_a_off + stages * plan->pw_a_stage_bytes;
+  plan->pw_bar_off = plan->pw_bias_off + 1024;
+  plan->smem_bytes = 1024 + plan->pw_bar_off + (2 * stages + 5) * 8 + 16;
+  if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;  // one CTA per SM: each CTA owns all 512 TMEM columns
+  plan->grid = plan->pw_tiles < num_sms ? plan->pw_tiles : num_sms;
+  if (plan->grid < 1) plan->grid = 1;
+  plan->n_time = PW_ROWS;
+  plan->cluster = 0;
+  const CUtensorMapDataType dt = prec == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)a.Cp_in, (cuuint64_t)R};
+    cuuint64_t strides[1] = {(cuuint64_t)a.x_ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)PW_ROWS};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&plan->tmA, dt, 2, const_cast<void*>(a.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return "cuTensorMapEncodeTiled failed for the pointwise activation map";
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)a.Cp_in, (cuuint64_t)a.N_total};
+    cuuint64_t strides[1] = {(cuuint64_t)a.Cp_in * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)N};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&plan->tmB, dt, 2, const_cast<void*>(a.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return "cuTensorMapEncodeTiled failed for the pointwise weight map";
+  }
+  plan->tmR = plan->tmA; plan->tmS = plan->tmA; plan->tmBh = plan->tmB;  // unused
+  if (a.epi.mode == EPI_RS) {  // residual rows: L2 prefetch boxes of 64 channels x 128 rows
+    cuuint64_t dims[2] = {(cuuint64_t)a.epi.ld, (cuuint64_t)R};
+    cuuint64_t strides[1] = {(cuuint64_t)a.epi.ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)PW_ROWS};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&plan->tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a.epi.xin), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return "cuTensorMapEncodeTiled failed for the pointwise residual map";
+  }
+  return nullptr;
+}
+
+template <typename Op, int MODE, int RH>
+static cudaError_t pw_launch_one(const ConvArgs& a, const TcPlan& p, const PwRt& rt, cudaStream_t st, int pdl, bool set_attr) {
+  auto k = pw_tc_kernel<Op, MODE, RH>;
+  if (set_attr) return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.grid);
+  cfg.blockDim = dim3(PW_THREADS);
+  cfg.dynamicSmemBytes = p.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k, p.tmA, p.tmB, p.tmR, a.epi, rt);
+}
+
+static cudaError_t pw_dispatch(int prec, const ConvArgs& a, const TcPlan& p, const PwRt& rt, cudaStream_t st, int pdl, bool set_attr,
+                               int mode, int rh) {
+  if (prec == 2) {
+    if (mode == EPI_RS && rh == 1) return pw_launch_one<OpBF16, EPI_RS, 1>(a, p, rt, st, pdl, set_attr);
+    if (mode == EPI_ACT && rh == 1) return pw_launch_one<OpBF16, EPI_ACT, 1>(a, p, rt, st, pdl, set_attr);
+    if (mode == EPI_ACT && rh == 0) return pw_launch_one<OpBF16, EPI_ACT, 0>(a, p, rt, st, pdl, set_attr);
+  } else if (prec == 3) {
+    if (mode == EPI_RS && rh == 1) return pw_launch_one<OpF16, EPI_RS, 1>(a, p, rt, st, pdl, set_attr);
+    if (mode == EPI_RS && rh == 2) return pw_launch_one<OpF16, EPI_RS, 2>(a, p, rt, st, pdl, set_attr);
+    if (mode == EPI_ACT && rh == 1) return pw_launch_one<OpF16, EPI_ACT, 1>(a, p, rt, st, pdl, set_attr);
+    if (mode == EPI_ACT && rh == 0) return pw_launch_one<OpF16, EPI_ACT, 0>(a, p, rt, st, pdl, set_attr);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t pw_set_attributes() {
+  ConvArgs a{};
+  TcPlan p{};
+  PwRt rt{};
+  const int combos[7][3] = {{2, EPI_RS, 1}, {2, EPI_ACT, 1}, {2, EPI_ACT, 0}, {3, EPI_RS, 1}, {3, EPI_RS, 2}, {3, EPI_ACT, 1}, {3, EPI_ACT, 0}};
+  for (auto& c : combos) {
+    cudaError_t e = pw_dispatch(c[0], a, p, rt, nullptr, 0, true, c[1], c[2]);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+cudaError_t launch_pw(int prec, const ConvArgs& a, const TcPlan& p, cudaStream_t st, int pdl) {
+  PwRt rt;
+  rt.R = p.pw_R; rt.kblocks = p.pw_kblocks; rt.N = p.pw_N; rt.n_tiles = p.pw_tiles;
+  rt.n_a_stages = p.pw_a_stages; rt.a_stage_bytes = p.pw_a_stage_bytes; rt.w_bytes = p.pw_w_bytes;
+  rt.a_off = p.pw_a_off; rt.bias_off = p.pw_bias_off; rt.bar_off = p.pw_bar_off;
+  const int rh = (a.epi.mode == EPI_RS) ? a.epi.res_half : (a.epi.xout != nullptr ? 1 : 0);
+  return pw_dispatch(prec, a, p, rt, st, pdl, false, a.epi.mode, rh);
+}
+
+}  // namespace mbv
