@@ -261,6 +261,253 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------------------------------------
+// WN gate conv (in_layers[l], k taps, 2H rows -> tanh(.) * sigmoid(.), commons.py:100-107) with TIME on the accumulator lane
+// and cta_group::2 MMAs over CTA pairs  (gate_tm_kernel).
+//
+// On conv_tc_kernel the gate conv has three 128-row channel tiles (odd: no CTA pairs), single-CTA MMAs at ~175 cycles per
+// N = 224 step (tensor pipe 49 %) and an epilogue in which the tanh and the sigmoid row of a channel live in different
+// warps (shared-memory exchange).  Here
+//   * A = the activation slab of ONE row tile per CTA (128 time steps of one utterance + the taps' halo, all k-blocks
+//     resident while the tile's units run; a tap is a row offset of the A descriptor), B = the packed weight rows, split
+//     between the two CTAs of a cluster: one tcgen05.mma.cta_group::2 (M = 256) multiplies BOTH CTAs' row tiles -- any two
+//     row tiles, they need not be neighbours -- with the same weights, so every weight tile is fetched once per pair and
+//     each CTA reads 4 KB of A + at most 4 KB of B per MMA.
+//   * the packed row order [64 tanh | 64 sigmoid] per 64 channels (mbistft.cu pack_wn) puts both pre-activations of a
+//     channel in the SAME thread (columns c and c + 64 of its row): no exchange.  Units of N = 256 (two packed tiles) while
+//     two remain, then N = 128; consecutive units alternate between two 256-column TMEM slots, so the epilogue of one unit
+//     overlaps the MMAs of the next.
+//   * an epilogue thread owns one row: 32 gated channels = 64 contiguous bytes = two 256-bit stores.
+// ------------------------------------------------------------------------------------------------
+struct GtRt {
+  int B, T, t_tiles, total_tiles, n_pair_tiles;
+  int kblocks, taps, dil, shift0, N_total, n_ct;
+  int slab_kb_bytes, slab_stage_bytes, n_w_stages;
+  int w_off, gb_off, bar_off;
+};
+constexpr int GT_SLAB_STAGES = 2;
+constexpr int GT_W_STAGE_BYTES = 128 * TC_ROW_BYTES;  // one CTA's half of an N = 256 weight tile
+
+__device__ __forceinline__ float gt_tanh(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+template <typename Op>
+__global__ void __launch_bounds__(PW_THREADS, 1)
+gate_tm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWh,
+               const EpiParams p, const GtRt rt) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;                  // GT_SLAB_STAGES x kblocks x slab_kb_bytes
+  uint8_t* smW = smem + rt.w_off;       // n_w_stages x 16 KB
+  float* s_gb = reinterpret_cast<float*>(smem + rt.gb_off);  // 2 x N_total: bias + cond_layer(g) of the row tile's utterance
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + rt.bar_off);
+  const int iAF = 0, iAE = iAF + GT_SLAB_STAGES, iWF = iAE + GT_SLAB_STAGES, iWE = iWF + rt.n_w_stages, iCF = iWE + rt.n_w_stages,
+            iCE = iCF + 2, nBars = iCE + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + nBars);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const uint32_t crank = blockIdx.x & 1u;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  // Schedule: the work is the sequence of (pair tile, packed 128-row weight tile) entries; every pair takes an equal
+  // CONTIGUOUS share of it (55 168 rows = 224 pair tiles x 3 packed tiles = 672 entries = 9 or 10 per pair, where whole
+  // pair tiles would be 3 or 4 per pair: 4 rounds for 3.03 rounds of work).  Consecutive entries of one pair tile run as one
+  // N = 256 unit when two are left in the share, else as an N = 128 unit; a slab is loaded when the pair tile changes.
+  const long long total_e = (long long)rt.n_pair_tiles * rt.n_ct;
+  const int e_begin = (int)((long long)pair * total_e / n_pairs), e_end = (int)((long long)(pair + 1) * total_e / n_pairs);
+  struct Unit { int pt, j, e_next; bool wide, first, last; };
+  auto unit_at = [&](int e) {
+    Unit u;
+    u.pt = e / rt.n_ct;
+    u.j = e - u.pt * rt.n_ct;
+    u.wide = (u.j + 1 < rt.n_ct) && (e + 1 < e_end);
+    u.e_next = e + (u.wide ? 2 : 1);
+    u.first = (e == e_begin) || (u.j == 0);
+    u.last = (u.e_next == e_end) || (u.e_next % rt.n_ct == 0);
+    return u;
+  };
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmWh);
+    for (int i = 0; i < GT_SLAB_STAGES; ++i) { mbar_init(BAR(iAF + i), 1); mbar_init(BAR(iAE + i), 1); }
+    for (int i = 0; i < rt.n_w_stages; ++i) { mbar_init(BAR(iWF + i), 1); mbar_init(BAR(iWE + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(iCF + i), 1); mbar_init(BAR(iCE + i), 2 * PW_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == PW_WARP_MMA) tmem_alloc2(smem_u32(tmem_ptr_smem), 512u);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp == PW_WARP_TMA) {
+    // ===================== TMA producer (both CTAs): own slab, own half of every weight tile =====================
+    int ss = 0, sw = 0;
+    uint32_t ps = 0, pw = 0;
+    for (int e = e_begin; e < e_end;) {
+      const Unit u = unit_at(e);
+      if (u.first) {
+        const int ri = 2 * u.pt + (int)crank;
+        const int b = ri < rt.total_tiles ? ri / rt.t_tiles : rt.B;  // no tile for this CTA: rows of utterance B do not exist -> zeros
+        const int t0 = (ri % rt.t_tiles) * PW_ROWS + rt.shift0;
+        mbar_wait(BAR(iAE + ss), ps ^ 1);
+        if (elect_one()) {
+          if (crank == 0) mbar_expect_tx(BAR(iAF + ss), (uint32_t)(2 * rt.slab_stage_bytes));
+          const uint32_t af = mapa_shared(BAR(iAF + ss), 0);
+          const uint32_t dst = smem_u32(smA) + (uint32_t)(ss * rt.slab_stage_bytes);
+          for (int kb = 0; kb < rt.kblocks; ++kb) tma_load_3d_2sm(dst + (uint32_t)(kb * rt.slab_kb_bytes), &tmX, af, kb * 64, t0, b);
+        }
+        __syncwarp();
+        if (++ss == GT_SLAB_STAGES) { ss = 0; ps ^= 1; }
+      }
+      const int half_rows = u.wide ? 128 : 64;   // N = 256: packed tiles j (even CTA) and j+1 (odd CTA); N = 128: halves of tile j
+      const int row0 = 128 * u.j + (int)crank * half_rows;
+      for (int kb = 0; kb < rt.kblocks; ++kb)
+        for (int tap = 0; tap < rt.taps; ++tap) {
+          mbar_wait(BAR(iWE + sw), pw ^ 1);
+          if (elect_one()) {
+            if (crank == 0) mbar_expect_tx(BAR(iWF + sw), (uint32_t)(2 * half_rows * TC_ROW_BYTES));
+            const uint32_t wf = mapa_shared(BAR(iWF + sw), 0);
+            const uint32_t wdst = smem_u32(smW) + (uint32_t)(sw * GT_W_STAGE_BYTES);
+            tma_load_2d_2sm(wdst, u.wide ? &tmW : &tmWh, wf, kb * 64, tap * rt.N_total + row0);
+          }
+          __syncwarp();
+          if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
+        }
+      e = u.e_next;
+    }
+  } else if (warp == PW_WARP_MMA) {
+    // ===================== MMA issuer (even CTA of the pair) =====================
+    if (crank == 0) {
+      constexpr uint32_t fmt = (Op::kPrec == 3) ? 0u : 1u;
+      const uint32_t idesc0 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)((2 * PW_ROWS) >> 4) << 24);
+      const uint32_t tap_step = (uint32_t)(rt.dil * TC_ROW_BYTES) >> 4;
+      int ss = 0, sw = 0;
+      uint32_t ps = 0, pw = 0, useq = 0;
+      for (int e = e_begin; e < e_end;) {
+        const Unit u = unit_at(e);
+        if (u.first) {
+          mbar_wait(BAR(iAF + ss), ps);
+          tc_fence_after();
+        }
+        const uint32_t idesc = idesc0 | ((uint32_t)((u.wide ? 256 : 128) >> 3) << 17);
+        const uint32_t slot = useq & 1u;
+        mbar_wait(BAR(iCE + slot), ((useq >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + slot * (uint32_t)PW_ACC_STRIDE;
+        uint32_t accum = 0;
+        for (int kb = 0; kb < rt.kblocks; ++kb) {
+          uint32_t a_lo = desc_lo(smem_u32(smA) + (uint32_t)(ss * rt.slab_stage_bytes + kb * rt.slab_kb_bytes));
+          for (int tap = 0; tap < rt.taps; ++tap) {
+            mbar_wait(BAR(iWF + sw), pw);
+            tc_fence_after();
+            const uint32_t w_lo = desc_lo(smem_u32(smW) + (uint32_t)(sw * GT_W_STAGE_BYTES));
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) tc_mma2<2>(tmem_d, desc64(a_lo + 2 * k), desc64(w_lo + 2 * k), idesc, (k == 0) ? accum : 1u);
+              tc_commit2_mc(BAR(iWE + sw), (uint16_t)3);
+            }
+            __syncwarp();
+            accum = 1;
+            a_lo += tap_step;
+            if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
+          }
+        }
+        if (elect_one()) {
+          tc_commit2_mc(BAR(iCF + slot), (uint16_t)3);
+          if (u.last) tc_commit2_mc(BAR(iAE + ss), (uint16_t)3);  // both CTAs' slabs are free once the tile's last unit is done
+        }
+        __syncwarp();
+        ++useq;
+        if (u.last && ++ss == GT_SLAB_STAGES) { ss = 0; ps ^= 1; }
+        e = u.e_next;
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs): one row per thread, tanh and sigmoid columns of a channel side by side
+    using T = typename Op::T;
+    const int q = warp & 3, half = warp >> 2;
+    const int tid_epi = threadIdx.x;  // epilogue warps are warps 0..7
+    uint32_t useq = 0;
+    int it = 0;
+    bool valid = false;
+    uint32_t gb_s = 0;
+    char* out_row = nullptr;
+    for (int e = e_begin; e < e_end;) {
+      const Unit u = unit_at(e);
+      if (u.first) {  // a new pair tile: this thread's row, bias + cond_layer(g) of its utterance
+        const int ri = 2 * u.pt + (int)crank;
+        const bool tile_ok = ri < rt.total_tiles;
+        const int b = tile_ok ? ri / rt.t_tiles : 0;
+        const int t = (ri % rt.t_tiles) * PW_ROWS + q * 32 + lane;
+        valid = tile_ok && t < rt.T;
+        float* gb = s_gb + (it & 1) * rt.N_total;
+        ++it;
+        for (int i = tid_epi; i < rt.N_total; i += 32 * PW_EPI_WARPS) {
+          float v = p.bias[(size_t)b * p.bias_bs + i];
+          if (p.add2 != nullptr) v += p.add2[(size_t)b * p.add2_bs + i];
+          gb[i] = v;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * PW_EPI_WARPS) : "memory");
+        gb_s = smem_u32(gb);
+        out_row = reinterpret_cast<char*>(p.act[0]) + (((size_t)b * p.rows_out + (size_t)t) * p.ld + (size_t)p.ch_off) * sizeof(T);
+      }
+      const uint32_t slot = useq & 1u;
+      mbar_wait(BAR(iCF + slot), (useq >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * (uint32_t)PW_ACC_STRIDE;
+      const int ptile = u.wide ? u.j + half : u.j;  // packed 128-row tile this warp drains
+      const int col0 = u.wide ? 128 * half : 0;
+      const int nsub = u.wide ? 2 : 1;
+      for (int sub = 0; sub < nsub; ++sub) {
+        const int cb = u.wide ? 32 * sub : 32 * half;   // first of the 32 channels (within the packed tile's 64)
+        float ta[32], sg[32];
+        tmem_ld32(taddr + (uint32_t)(col0 + cb), ta);
+        tmem_ld32(taddr + (uint32_t)(col0 + 64 + cb), sg);
+        tmem_ld_wait();
+        const uint32_t gsrc = gb_s + (uint32_t)(128 * ptile + cb) * 4u;
+        uint32_t o[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 bt, bs;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bt.x), "=f"(bt.y), "=f"(bt.z), "=f"(bt.w) : "r"(gsrc + (uint32_t)i * 4u));
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bs.x), "=f"(bs.y), "=f"(bs.z), "=f"(bs.w) : "r"(gsrc + (uint32_t)(64 + i) * 4u));
+          const float g0 = gt_tanh(ta[i] + bt.x) * fmaf(gt_tanh(0.5f * (sg[i] + bs.x)), 0.5f, 0.5f);
+          const float g1 = gt_tanh(ta[i + 1] + bt.y) * fmaf(gt_tanh(0.5f * (sg[i + 1] + bs.y)), 0.5f, 0.5f);
+          const float g2 = gt_tanh(ta[i + 2] + bt.z) * fmaf(gt_tanh(0.5f * (sg[i + 2] + bs.z)), 0.5f, 0.5f);
+          const float g3 = gt_tanh(ta[i + 3] + bt.w) * fmaf(gt_tanh(0.5f * (sg[i + 3] + bs.w)), 0.5f, 0.5f);
+          o[i / 2] = pack_op2<Op>(g0, g1);
+          o[i / 2 + 1] = pack_op2<Op>(g2, g3);
+        }
+        if (valid) {
+          char* dst = out_row + (size_t)(64 * ptile + cb) * sizeof(T);
+          stg256(dst, o);
+          stg256(dst + 32, o + 8);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (crank != 0) mbar_arrive_remote(BAR(iCE + slot), 0u);  // the accumulator-free barriers live in the even CTA
+        else mbar_arrive(BAR(iCE + slot));
+      }
+      ++useq;
+      e = u.e_next;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == PW_WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 bool pw_eligible(int prec, const ConvArgs& a, int flags) {
@@ -348,6 +595,105 @@ const char* pw_make_plan(int prec, const ConvArgs& a, int num_sms, TcPlan* plan)
   return nullptr;
 }
 
+
+// ---- gate_tm_kernel: eligibility, plan, launch
+bool gt_eligible(int prec, const ConvArgs& a, int flags, int num_sms) {
+  const EpiParams& e = a.epi;
+  if (flags & MBV_FLAG_NO_PW) return false;
+  if (prec < 2 || e.mode != EPI_GATE || !a.gate || a.n_phases != 1 || num_sms < 2) return false;
+  if (a.N_total % 128 != 0 || a.N_total > 1024 || a.Cp_in % 64 != 0 || a.L_in != a.L_out || a.x_ld < a.Cp_in) return false;
+  if (e.bias == nullptr || e.act[0] == nullptr || e.n_act != 1 || e.row_mul != 1 || e.row_add != 0) return false;
+  if (e.ld % 16 != 0 || e.ch_off % 16 != 0 || e.n_valid != a.N_total / 2) return false;
+  const int halo = (a.taps - 1) * a.dil;
+  if (PW_ROWS + halo > 256) return false;
+  const int box_rows = (PW_ROWS + halo + 7) / 8 * 8;
+  const int slab = GT_SLAB_STAGES * (a.Cp_in / 64) * box_rows * TC_ROW_BYTES;
+  return slab + 4 * GT_W_STAGE_BYTES + 2 * a.N_total * 4 + 1024 <= 222 * 1024;
+}
+
+const char* gt_make_plan(int prec, const ConvArgs& a, int num_sms, TcPlan* plan) {
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(tc_tensormap_encoder());
+  if (!enc) return "cuTensorMapEncodeTiled entry point unavailable";
+  const int kblocks = a.Cp_in / 64, halo = (a.taps - 1) * a.dil;
+  const int box_rows = (PW_ROWS + halo + 7) / 8 * 8;
+  plan->pw = 2;
+  plan->pw_kblocks = kblocks;
+  plan->pw_tiles = (a.L_out + PW_ROWS - 1) / PW_ROWS;                 // row tiles per utterance
+  plan->pw_R = a.B * plan->pw_tiles;                                   // row tiles in total
+  plan->pw_a_stage_bytes = kblocks * box_rows * TC_ROW_BYTES;
+  plan->pw_w_bytes = box_rows * TC_ROW_BYTES;                          // one k-block of a slab
+  plan->pw_a_off = GT_SLAB_STAGES * plan->pw_a_stage_bytes;            // weight ring starts here
+  int stages = (222 * 1024 - plan->pw_a_off - 2 * a.N_total * 4 - 1024) / GT_W_STAGE_BYTES;
+  if (stages > 8) stages = 8;
+  if (stages < 3) return "gate conv: not enough shared memory for the weight ring";
+  plan->pw_a_stages = stages;
+  plan->pw_bias_off = plan->pw_a_off + stages * GT_W_STAGE_BYTES;
+  plan->pw_bar_off = plan->pw_bias_off + (2 * a.N_total * 4 + 127) / 128 * 128;
+  plan->smem_bytes = 1024 + plan->pw_bar_off + (2 * GT_SLAB_STAGES + 2 * stages + 4) * 8 + 16;
+  if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;
+  const int n_pair_tiles = (plan->pw_R + 1) / 2;
+  const long long entries = (long long)n_pair_tiles * (a.N_total / 128);
+  const int pairs = entries < num_sms / 2 ? (int)entries : num_sms / 2;
+  plan->grid = 2 * (pairs < 1 ? 1 : pairs);
+  plan->n_time = PW_ROWS;
+  plan->cluster = 2;
+  const CUtensorMapDataType dt = prec == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)a.Cp_in, (cuuint64_t)a.L_in, (cuuint64_t)a.B};
+    cuuint64_t strides[2] = {(cuuint64_t)a.x_ld * 2, (cuuint64_t)a.L_in * a.x_ld * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&plan->tmA, dt, 3, const_cast<void*>(a.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return "cuTensorMapEncodeTiled failed for the gate activation map";
+  }
+  for (int which = 0; which < 2; ++which) {
+    cuuint64_t dims[2] = {(cuuint64_t)a.Cp_in, (cuuint64_t)a.taps * a.N_total};
+    cuuint64_t strides[1] = {(cuuint64_t)a.Cp_in * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)(which ? 64 : 128)};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(which ? &plan->tmBh : &plan->tmB, dt, 2, const_cast<void*>(a.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return "cuTensorMapEncodeTiled failed for a gate weight map";
+  }
+  plan->tmR = plan->tmA; plan->tmS = plan->tmA;  // unused
+  return nullptr;
+}
+
+template <typename Op>
+static cudaError_t gt_launch_one(const ConvArgs& a, const TcPlan& p, const GtRt& rt, cudaStream_t st, int pdl, bool set_attr) {
+  auto k = gate_tm_kernel<Op>;
+  if (set_attr) return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.grid);
+  cfg.blockDim = dim3(PW_THREADS);
+  cfg.dynamicSmemBytes = p.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  return cudaLaunchKernelEx(&cfg, k, p.tmA, p.tmB, p.tmBh, a.epi, rt);
+}
+
+static cudaError_t launch_gt(int prec, const ConvArgs& a, const TcPlan& p, cudaStream_t st, int pdl) {
+  GtRt rt;
+  rt.B = a.B; rt.T = a.L_out; rt.t_tiles = p.pw_tiles; rt.total_tiles = p.pw_R; rt.n_pair_tiles = (p.pw_R + 1) / 2;
+  rt.kblocks = p.pw_kblocks; rt.taps = a.taps; rt.dil = a.dil; rt.shift0 = a.shift0[0]; rt.N_total = a.N_total; rt.n_ct = a.N_total / 128;
+  rt.slab_kb_bytes = p.pw_w_bytes; rt.slab_stage_bytes = p.pw_a_stage_bytes; rt.n_w_stages = p.pw_a_stages;
+  rt.w_off = p.pw_a_off; rt.gb_off = p.pw_bias_off; rt.bar_off = p.pw_bar_off;
+  if (prec == 3) return gt_launch_one<OpF16>(a, p, rt, st, pdl, false);
+  return gt_launch_one<OpBF16>(a, p, rt, st, pdl, false);
+}
+
 template <typename Op, int MODE, int RH>
 static cudaError_t pw_launch_one(const ConvArgs& a, const TcPlan& p, const PwRt& rt, cudaStream_t st, int pdl, bool set_attr) {
   auto k = pw_tc_kernel<Op, MODE, RH>;
@@ -389,10 +735,14 @@ cudaError_t pw_set_attributes() {
     cudaError_t e = pw_dispatch(c[0], a, p, rt, nullptr, 0, true, c[1], c[2]);
     if (e != cudaSuccess) return e;
   }
-  return cudaSuccess;
+  GtRt g{};
+  cudaError_t e = gt_launch_one<OpBF16>(a, p, g, nullptr, 0, true);
+  if (e == cudaSuccess) e = gt_launch_one<OpF16>(a, p, g, nullptr, 0, true);
+  return e;
 }
 
 cudaError_t launch_pw(int prec, const ConvArgs& a, const TcPlan& p, cudaStream_t st, int pdl) {
+  if (p.pw == 2) return launch_gt(prec, a, p, st, pdl);
   PwRt rt;
   rt.R = p.pw_R; rt.kblocks = p.pw_kblocks; rt.N = p.pw_N; rt.n_tiles = p.pw_tiles;
   rt.n_a_stages = p.pw_a_stages; rt.a_stage_bytes = p.pw_a_stage_bytes; rt.w_bytes = p.pw_w_bytes;
