@@ -22,6 +22,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/mbistft.h"
 #include "common.cuh"
@@ -283,6 +284,7 @@ struct GtRt {
   int kblocks, taps, dil, shift0, N_total, n_ct;
   int slab_kb_bytes, slab_stage_bytes, n_w_stages;
   int w_off, gb_off, bar_off;
+  int narrow_steps;   // (k-block, tap) steps of an N = 128 unit per weight-ring stage (1 or 2)
 };
 constexpr int GT_SLAB_STAGES = 2;
 constexpr int GT_W_STAGE_BYTES = 128 * TC_ROW_BYTES;  // one CTA's half of an N = 256 weight tile
@@ -365,18 +367,24 @@ gate_tm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       const int half_rows = u.wide ? 128 : 64;   // N = 256: packed tiles j (even CTA) and j+1 (odd CTA); N = 128: halves of tile j
       const int row0 = 128 * u.j + (int)crank * half_rows;
-      for (int kb = 0; kb < rt.kblocks; ++kb)
-        for (int tap = 0; tap < rt.taps; ++tap) {
-          mbar_wait(BAR(iWE + sw), pw ^ 1);
-          if (elect_one()) {
-            if (crank == 0) mbar_expect_tx(BAR(iWF + sw), (uint32_t)(2 * half_rows * TC_ROW_BYTES));
-            const uint32_t wf = mapa_shared(BAR(iWF + sw), 0);
-            const uint32_t wdst = smem_u32(smW) + (uint32_t)(sw * GT_W_STAGE_BYTES);
-            tma_load_2d_2sm(wdst, u.wide ? &tmW : &tmWh, wf, kb * 64, tap * rt.N_total + row0);
+      // one ring stage = one (k-block, tap) step of an N = 256 unit (16 KB per CTA) or TWO steps of an N = 128 unit (2 x 8 KB):
+      // either way a stage lasts ~512 tensor-core cycles, so the ring covers the same TMA round trip
+      const int n_steps = rt.kblocks * rt.taps, per_stage = u.wide ? 1 : rt.narrow_steps;
+      for (int i = 0; i < n_steps; i += per_stage) {
+        const int n_here = min(per_stage, n_steps - i);
+        mbar_wait(BAR(iWE + sw), pw ^ 1);
+        if (elect_one()) {
+          if (crank == 0) mbar_expect_tx(BAR(iWF + sw), (uint32_t)(2 * n_here * half_rows * TC_ROW_BYTES));
+          const uint32_t wf = mapa_shared(BAR(iWF + sw), 0);
+          const uint32_t wdst = smem_u32(smW) + (uint32_t)(sw * GT_W_STAGE_BYTES);
+          for (int d = 0; d < n_here; ++d) {
+            const int kb = (i + d) / rt.taps, tap = (i + d) - kb * rt.taps;
+            tma_load_2d_2sm(wdst + (uint32_t)(d * half_rows * TC_ROW_BYTES), u.wide ? &tmW : &tmWh, wf, kb * 64, tap * rt.N_total + row0);
           }
-          __syncwarp();
-          if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
         }
+        __syncwarp();
+        if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
+      }
       e = u.e_next;
     }
   } else if (warp == PW_WARP_MMA) {
@@ -399,22 +407,26 @@ gate_tm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + slot * (uint32_t)PW_ACC_STRIDE;
         uint32_t accum = 0;
-        for (int kb = 0; kb < rt.kblocks; ++kb) {
-          uint32_t a_lo = desc_lo(smem_u32(smA) + (uint32_t)(ss * rt.slab_stage_bytes + kb * rt.slab_kb_bytes));
-          for (int tap = 0; tap < rt.taps; ++tap) {
-            mbar_wait(BAR(iWF + sw), pw);
-            tc_fence_after();
-            const uint32_t w_lo = desc_lo(smem_u32(smW) + (uint32_t)(sw * GT_W_STAGE_BYTES));
+        const int n_steps = rt.kblocks * rt.taps, per_stage = u.wide ? 1 : rt.narrow_steps;
+        const uint32_t half_bytes = (uint32_t)((u.wide ? 128 : 64) * TC_ROW_BYTES);
+        for (int i = 0; i < n_steps; i += per_stage) {
+          const int n_here = min(per_stage, n_steps - i);
+          mbar_wait(BAR(iWF + sw), pw);
+          tc_fence_after();
+          const uint32_t w_stage = smem_u32(smW) + (uint32_t)(sw * GT_W_STAGE_BYTES);
+          for (int d = 0; d < n_here; ++d) {
+            const int kb = (i + d) / rt.taps, tap = (i + d) - kb * rt.taps;
+            const uint32_t a_lo = desc_lo(smem_u32(smA) + (uint32_t)(ss * rt.slab_stage_bytes + kb * rt.slab_kb_bytes)) + (uint32_t)tap * tap_step;
+            const uint32_t w_lo = desc_lo(w_stage + (uint32_t)d * half_bytes);
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) tc_mma2<2>(tmem_d, desc64(a_lo + 2 * k), desc64(w_lo + 2 * k), idesc, (k == 0) ? accum : 1u);
-              tc_commit2_mc(BAR(iWE + sw), (uint16_t)3);
+              if (d == n_here - 1) tc_commit2_mc(BAR(iWE + sw), (uint16_t)3);
             }
             __syncwarp();
             accum = 1;
-            a_lo += tap_step;
-            if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
           }
+          if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
         }
         if (elect_one()) {
           tc_commit2_mc(BAR(iCF + slot), (uint16_t)3);
@@ -690,6 +702,8 @@ static cudaError_t launch_gt(int prec, const ConvArgs& a, const TcPlan& p, cudaS
   rt.kblocks = p.pw_kblocks; rt.taps = a.taps; rt.dil = a.dil; rt.shift0 = a.shift0[0]; rt.N_total = a.N_total; rt.n_ct = a.N_total / 128;
   rt.slab_kb_bytes = p.pw_w_bytes; rt.slab_stage_bytes = p.pw_a_stage_bytes; rt.n_w_stages = p.pw_a_stages;
   rt.w_off = p.pw_a_off; rt.gb_off = p.pw_bias_off; rt.bar_off = p.pw_bar_off;
+  static const int narrow_env = getenv("MBV_GT_NARROW") ? atoi(getenv("MBV_GT_NARROW")) : 2;  // A/B measurements only
+  rt.narrow_steps = narrow_env == 1 ? 1 : 2;
   if (prec == 3) return gt_launch_one<OpF16>(a, p, rt, st, pdl, false);
   return gt_launch_one<OpBF16>(a, p, rt, st, pdl, false);
 }

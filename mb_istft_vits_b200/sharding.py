@@ -44,7 +44,7 @@ def shard_batch(z: torch.Tensor, lengths: torch.Tensor, rank: int, world_size: i
 
 
 def gather_waveforms(wav: torch.Tensor, n_samples: torch.Tensor, indices: Sequence[int], total: int, dst: int = 0,
-                     group: Optional[dist.ProcessGroup] = None) -> Optional[List[torch.Tensor]]:
+                     group: Optional[dist.ProcessGroup] = None, mode: str = "p2p") -> Optional[List[torch.Tensor]]:
     """Collect every rank's waveforms on rank ``dst`` in the original utterance order.
 
     wav: [b_local, 1, S_local] (padded), n_samples: [b_local] valid sample counts, indices: global utterance ids.
@@ -56,6 +56,10 @@ def gather_waveforms(wav: torch.Tensor, n_samples: torch.Tensor, indices: Sequen
          ``dst``; ``dst`` posts one receive per peer.  The operations go out as one ``batch_isend_irecv`` group
          (NCCL: ncclGroupStart/End, all peers in flight at once over NVSwitch; only ``dst`` receives -- the round-1
          version all-gathered the padded samples to EVERY rank, world x the traffic).
+    ``mode="allgather"`` replaces step 2 by ONE ``all_gather_into_tensor`` of the blocks, each padded to the largest block:
+    world x the bytes, every rank receives everything -- but on an NVSwitch box every GPU has full bandwidth to every peer
+    and the collective runs at several times the rate NCCL's grouped send / recv reaches into a single receiver
+    (tools/gather_bench.py, profiles/round2_gather_modes.txt), so it is the faster way to get the audio to ``dst`` there.
     Returns the list of trimmed 1-D waveforms (views of the received blocks) on ``dst``, None elsewhere.
     """
     world = dist.get_world_size(group)
@@ -75,6 +79,19 @@ def gather_waveforms(wav: torch.Tensor, n_samples: torch.Tensor, indices: Sequen
     host = tables.cpu().view(world, total + 1, 2)  # the only device->host read of the gather
     shapes = [(int(host[r, total, 0]), int(host[r, total, 1])) for r in range(world)]
     block = wav.reshape(b_local, s_local).contiguous() if b_local else None
+    if mode == "allgather":
+        numel = max(r * c for r, c in shapes)
+        flat = torch.zeros(numel, dtype=torch.float32, device=dev) if (block is None or block.numel() < numel) else block.reshape(-1)
+        if block is not None and block.numel() < numel:
+            flat[: block.numel()] = block.reshape(-1)
+        everything = torch.empty(world * numel, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(everything, flat, group=group)
+        if rank != dst:
+            return None
+        bufs = [everything[r * numel: r * numel + shapes[r][0] * shapes[r][1]].view(shapes[r]) if shapes[r][0] else None for r in range(world)]
+        return _assemble(host, bufs, world, total)
+    if mode != "p2p":
+        raise ValueError("mode must be 'p2p' or 'allgather'")
     ops, bufs = [], [None] * world
     if rank == dst:
         for r in range(world):
@@ -90,6 +107,11 @@ def gather_waveforms(wav: torch.Tensor, n_samples: torch.Tensor, indices: Sequen
             req.wait()
     if rank != dst:
         return None
+    return _assemble(host, bufs, world, total)
+
+
+def _assemble(host, bufs, world, total):
+    """Placement table -> the trimmed per-utterance views of the received blocks, in the original utterance order."""
     out: List[Optional[torch.Tensor]] = [None] * total
     ns_all, row_all = host[:, :total, 0].tolist(), host[:, :total, 1].tolist()
     for r in range(world):

@@ -47,9 +47,10 @@ def _worker(rank, world, port, tmp):
     z_loc, len_loc, idx = shard_batch(z, lengths, rank, world)
     wav = orc.decode(sd, cfg, z_loc)[0] if len(idx) else torch.zeros((0, 1, 0))
     out = gather_waveforms(wav, len_loc * 256, idx, total=5, dst=0)
+    out_ag = gather_waveforms(wav, len_loc * 256, idx, total=5, dst=0, mode="allgather")
     if rank == 0:
         full = orc.decode(sd, cfg, z)[0]
-        ok = True
+        ok = all(torch.equal(a, b) for a, b in zip(out, out_ag))  # the two transports deliver the same samples
         for i in range(5):
             n = int(lengths[i]) * 256
             # an utterance decoded inside a shorter padded batch equals the full-batch result away from the padded tail
