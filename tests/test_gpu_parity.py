@@ -826,3 +826,23 @@ def test_pointwise_kernel_matches_generic_conv_kernel(prec):
     torch.cuda.synchronize()
     assert orc.snr_db(b[0].cpu(), a[0].cpu()) > 80.0 and orc.snr_db(b[1].cpu(), a[1].cpu()) > 70.0
     assert float((b[0].cpu() * (1 - mask)).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (1, 127), (3, 128), (2, 129), (5, 300), (1, 1000)])
+def test_time_on_lane_kernels_at_tile_edges(B, T):
+    """pw_tc_kernel / gate_tm_kernel at the edges of their 128-row tiles: one frame, one row short of / exactly / one row past a
+    tile, an odd number of row tiles (one CTA of the last pair has no tile), tiles of the flattened row axis that straddle
+    utterances -- flow reverse against the generic kernels (MBV_FLAG_NO_PW) and, on the mini model, against the CPU oracle."""
+    from mb_istft_vits_b200 import lib as L
+    for cname in ("ljs_mb_istft_vits", "ljs_mini_mb_istft_vits"):
+        cfg = get_config(cname)
+        sd = synth.make_state_dict(cfg, seed=3)
+        lengths = [max(1, T - 37 * i) for i in range(B)]
+        z_p, mask, _ = synth.make_latents(cfg, B, T, seed=B * 1000 + T, lengths=lengths)
+        ref = _engine(cfg, sd, "bf16", L.FLAG_NO_PW).flow_reverse(z_p.cuda(), mask.cuda()).cpu()
+        got = _engine(cfg, sd, "bf16", 0).flow_reverse(z_p.cuda(), mask.cuda()).cpu()
+        assert got.shape == ref.shape and float((got * (1 - mask)).abs().max()) == 0.0
+        assert orc.snr_db(got, ref) > 80.0, (cname, B, T, orc.snr_db(got, ref))
+        if cname == "ljs_mini_mb_istft_vits" and T <= 300:
+            z_cpu = orc.flow_reverse(sd, cfg, z_p, mask)
+            assert orc.snr_db(got, z_cpu) > 40.0

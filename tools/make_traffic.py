@@ -35,11 +35,11 @@ def main(src, dst):
             best = run
     step = best
     step_tail = step[-1]
-    conv = [d[i] for i in step if "conv_tc" in d[i]["name"]]
+    conv = [d[i] for i in step if any(k in d[i]["name"] for k in ("conv_tc", "conv_pair", "pw_tc", "gate_tm"))]
     tail = d[step_tail]
     by = lambda x: x.get("dram__bytes_read.sum", 0.0) + x.get("dram__bytes_write.sum", 0.0)
     out = {
-        "source": f"{src} (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum; one step of bench.py)",
+        "source": f"{src} (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum; one step of tools/profile_step.py = the step bench.py times)",
         "launches_in_step": len(step),
         "conv_launches": len(conv),
         "conv_dram_bytes_per_step": sum(by(c) for c in conv),
