@@ -42,7 +42,9 @@ typedef enum {
  * :387 Multistream_iSTFT_Generator (selected by the three booleans at models.py:634-644) */
 typedef enum { MBV_VARIANT_ISTFT = 0, MBV_VARIANT_MB = 1, MBV_VARIANT_MS = 2 } mbv_variant;
 
-/* arithmetic of the dense contractions (residual stream, head, iSTFT, PQMF are always fp32) */
+/* arithmetic of the dense contractions (accumulators, head, iSTFT, PQMF are always fp32; the residual streams are fp32 on the
+ * FP32 / TF32 paths and on BF16 without MBV_FLAG_RESIDUAL_FP16, saturating fp16 on BF16 with it, and folded into the fp16
+ * operand tensors on FP16 -- DESIGN.md section 3) */
 typedef enum {
   MBV_PREC_FP32 = 0, /* CUDA-core fp32 FMA: exact-order-independent reference path, slow */
   MBV_PREC_TF32 = 1, /* tcgen05 kind::tf32, operands rounded to tf32 (RNE), fp32 accumulate */
@@ -90,7 +92,7 @@ typedef struct {
 
 /* debug / tuning flags */
 #define MBV_FLAG_FORCE_SIMT 4       /* run the CUDA-core conv on the tensor-core operand layout (cross-check) */
-#define MBV_FLAG_RESIDUAL_FP16 8    /* bf16 path: keep the decoder's ResBlock residual stream in (saturating) fp16 */
+#define MBV_FLAG_RESIDUAL_FP16 8    /* bf16 path: keep the ResBlock residual stream and the WN hidden stream in (saturating) fp16 */
 #define MBV_FLAG_CLUSTER_PAIRS 32    /* experimental: run the multi-tap convs as clusters of two CTAs that work on two time tiles of the
                                      * same weight group; each CTA fetches half of every weight tile and TMA-multicasts it to both.
                                      * Parity-tested; < 1 % faster per step on B200, hence opt-in. */
@@ -101,6 +103,7 @@ typedef struct {
 #define MBV_FLAG_NO_PW 512          /* A/B and cross-check tests: run the 1x1 convs of the WN stacks (coupling-layer pre, WN residual convs)
                                      * on the generic conv kernel (output channel on the accumulator lane) instead of pw_tc_kernel
                                      * (time on the lane, 256-bit epilogue accesses) */
+#define MBV_FLAG_NO_PAIR_SPLIT 1024 /* A/B only: do not cut the leftover pair tiles of a CTA-pair launch's last round into column pieces */
 #define MBV_FLAG_SPLIT_TAIL 128     /* keep conv_post as its own conv launch writing fp32 logits for the stand-alone tail kernel instead
                                      * of the fused conv_post + tail kernel (the default on the 16-bit paths; A/B and cross-check tests) */
 #define MBV_FLAG_BRANCHES 64         /* experimental: run the parallel ResBlocks of a stage on the library's two extra streams (own

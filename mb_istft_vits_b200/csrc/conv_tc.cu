@@ -414,7 +414,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   auto decode_work = [&](int tile) {
     Work wk;
     wk.t_off = 0; wk.n_cols = rt.n_time;
-    if (tile >= rt.split_from && rt.split_k > 1) {  // a piece of a tile of the last round
+    if constexpr (CL == 2) {
+      // CTA pairs: the unit of the split is the pair (both CTAs work on the same columns of one time tile); split_from counts pairs
+      int w = tile >> 1;
+      if (w >= rt.split_from && rt.split_k > 1) {
+        const int s = w - rt.split_from;
+        w = rt.split_from + s / rt.split_k;
+        wk.t_off = (s % rt.split_k) * rt.split_n;
+        wk.n_cols = min(rt.split_n, rt.n_time - wk.t_off);
+        tile = 2 * w + (tile & 1);
+      }
+    } else if (tile >= rt.split_from && rt.split_k > 1) {  // a piece of a tile of the last round
       const int s = tile - rt.split_from;
       tile = rt.split_from + s / rt.split_k;
       wk.t_off = (s % rt.split_k) * rt.split_n;
@@ -463,7 +473,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const int t0 = wk.tt * rt.n_time + wk.t_off;
       const int wrow0 = phase * a.taps * a.N_total + ct * TC_M;
       // CTA pairs: this CTA stages its HALF of the tile's time rows (the B operand of a cta_group::2 MMA is split by rows)
-      const int xrow0 = t0 + a.shift0[phase] + ((CL == 2) ? (int)crank * (rt.n_time >> 1) : 0);
+      const int xrow0 = t0 + a.shift0[phase] + ((CL == 2) ? (int)crank * (wk.n_cols >> 1) : 0);
       if (rt.dbg && lane == 0) rt.dbg[((size_t)blockIdx.x * 7 + 0) * 64 + 2 * ((tile / gridDim.x) & 31)] = clock64();
       // (A whole-tile TMA L2 prefetch of the residual box issued here was measured to be too early: a tile-time later
       //  a third of it had been evicted again and DRAM reads grew 40 %.  The epilogue warps prefetch two chunks ahead.)
@@ -1129,6 +1139,7 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return "cuTensorMapEncodeTiled entry point unavailable";
   plan->pw = 0;
+  plan->no_pair_split = (flags & MBV_FLAG_NO_PAIR_SPLIT) ? 1 : 0;
   if (pw_eligible(prec, a, flags)) return pw_make_plan(prec, a, num_sms, plan);  // 1x1 convs of the WN stacks: pw_tc.cu
   static const int gt_env = getenv("MBV_GATE_TM") ? atoi(getenv("MBV_GATE_TM")) : 1;  // A/B measurements only
   if (gt_env && gt_eligible(prec, a, flags, num_sms)) return gt_make_plan(prec, a, num_sms, plan);  // WN gate convs: pw_tc.cu
@@ -1199,7 +1210,8 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
   // Measured (profiles/round2_cta_pairs_ab.txt): stage-0 k=11 convs 245 -> 210 us (1295 -> 1520 TFLOP/s), k=7 156 -> 145,
   // first upsampler 207 -> 180, conv_pre 74 -> 66; the HBM-bound k=3 residual convs get slightly slower (113 -> 125 us:
   // two CTAs in lock step share one tile's epilogue traffic pattern), so RES epilogues pair up from 5 taps on.
-  const bool pair_mode = (a.epi.mode == EPI_ACT && a.taps > 1) || (a.epi.mode == EPI_RES && a.taps >= 5);
+  static const int res_pair_taps = getenv("MBV_RES_PAIR_TAPS") ? atoi(getenv("MBV_RES_PAIR_TAPS")) : 5;  // A/B measurements only
+  const bool pair_mode = (a.epi.mode == EPI_ACT && a.taps > 1) || (a.epi.mode == EPI_RES && a.taps >= res_pair_taps);
   // A pair is two channel tiles of one time tile or -- polyphase upsamplers with an odd number of channel tiles -- two
   // branches that read the same input rows (k16 / stride 4: branches (0,1) and (2,3) have the same first input row).
   bool phase_pairs = (plan->c_tiles % 2 != 0) && (a.n_phases % 2 == 0);
@@ -1476,6 +1488,25 @@ cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStr
   if (p.cluster) rt.rotate = 0;
   rt.split_from = p.total_tiles; rt.split_k = 1; rt.split_n = p.n_time; rt.virt_tiles = p.total_tiles;
   static const int no_split = getenv("MBV_NO_SPLIT") ? atoi(getenv("MBV_NO_SPLIT")) : 0;  // A/B measurements only
+  static const int no_pair_split = getenv("MBV_NO_PAIR_SPLIT") ? atoi(getenv("MBV_NO_PAIR_SPLIT")) : 0;  // A/B measurements only
+  if (!no_split && !no_pair_split && !p.no_pair_split && p.cluster == 2 && (p.total_tiles & 1) == 0 && (p.grid & 1) == 0) {
+    // CTA pairs: the same split in units of pairs (stage 0: 896 pair tiles on 74 pairs = 12.1 rounds of work in 13 rounds;
+    // the 8 leftover pair tiles become 32 pieces of 64 columns: 12.25 rounds)
+    const int pairs = p.total_tiles / 2, gp = p.grid / 2, remp = pairs % gp;
+    if (pairs > gp && remp > 0 && 2 * remp <= gp) {
+      int k = gp / remp;
+      const int kmax = p.n_time / 64;
+      if (k > kmax) k = kmax;
+      if (k >= 2) {
+        const int n_sub = ((p.n_time + k - 1) / k + 31) / 32 * 32;   // each CTA stages half of a piece's rows
+        const int ksub = (p.n_time + n_sub - 1) / n_sub;
+        if (ksub >= 2 && remp * ksub <= gp && p.n_time % 32 == 0) {
+          rt.split_from = pairs - remp; rt.split_k = ksub; rt.split_n = n_sub;   // (pair units)
+          rt.virt_tiles = 2 * (rt.split_from + remp * ksub);
+        }
+      }
+    }
+  }
   const int rem = p.total_tiles % p.grid;
   if (!no_split && !p.cluster && p.total_tiles > p.grid && rem > 0 && 2 * rem <= p.grid) {
     int k = p.grid / rem;                          // pieces per tile so that the last round still fits the grid

@@ -28,6 +28,7 @@ struct TcPlan {
   int w_resident;       // weights of the single channel tile stay resident in the ring
   int smem_bytes;
   int grid;
+  int no_pair_split;    // MBV_FLAG_NO_PAIR_SPLIT: A/B only
   // pointwise (1x1) convs on pw_tc_kernel (time on the accumulator lane, pw_tc.cu): tmA = flattened [C, B*L] activation map,
   // tmB = weight map with an N-row box
   int pw, pw_N, pw_kblocks, pw_R, pw_tiles, pw_w_bytes, pw_a_stage_bytes, pw_a_stages, pw_a_off, pw_bias_off, pw_bar_off;
