@@ -49,7 +49,12 @@ struct TcPairPlan {
   CUtensorMap tmA, tmB, tmB2;   // activations, c1 weights, c2 weights
   int box_rows, n_boxes, slab_stage_bytes, n_slab_stages, n_w_stages;
   int t_tiles, total_tiles, h_off, w_off, bar_off, smem_bytes, grid;
+  // pair_tm_kernel (time on the accumulator lane, CTA pairs, resident weights; pw_tc.cu): tm = 1
+  int tm, tm_out_rows, tm_slab_kb_bytes, tm_slab_stage_bytes, tm_h_kb_bytes, tm_slab_off, tm_bias_off;
 };
+bool ptm_eligible(int prec, const ConvArgs& a, int flags, int num_sms);
+const char* ptm_make_plan(int prec, const ConvArgs& a, int num_sms, TcPairPlan* plan);
+cudaError_t launch_ptm(int prec, const ConvArgs& a, const TcPairPlan& plan, cudaStream_t st, int pdl);
 const char* tc_make_pair_plan(int prec, const ConvArgs& a, int num_sms, TcPairPlan* plan);
 cudaError_t launch_conv_pair(int prec, const ConvArgs& a, const TcPairPlan& plan, cudaStream_t st, int pdl = 1);
 cudaError_t tc_pair_set_attributes();

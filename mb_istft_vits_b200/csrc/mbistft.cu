@@ -924,6 +924,14 @@ bool pair_ok(const mbv_handle* h, const ConvLayer& c1, const ConvLayer& c2) {
          c1.taps <= h->pair_max_taps && c1.n_phases == 1 && c2.n_phases == 1;
 }
 
+// k = 3 conv pairs of a 128-channel stage whose residual add is plain (sum_mode 0) or starts the running ResBlock sum (1):
+// pair_tm_kernel (default on the bf16 path)
+bool pairtm_ok(const mbv_handle* h, const ConvLayer& c1, const ConvLayer& c2, int sum_mode) {
+  return (sum_mode == 0 || sum_mode == 1) && h->prec == MBV_PREC_BF16 && h->res_half && !h->single && h->num_sms >= 2 &&
+         !(h->cfg.flags & (MBV_FLAG_FORCE_SIMT | MBV_FLAG_NO_PW | MBV_FLAG_NO_PAIR_TM)) && c1.Cp_in == 128 && c1.N_total == 128 &&
+         c2.Cp_in == 128 && c2.N_total == 128 && c1.taps == 3 && c2.taps == 3 && c2.dil == 1 && c1.n_phases == 1 && c2.n_phases == 1;
+}
+
 int run_pair(Ctx& cx, const ConvLayer& c1, const ConvLayer& c2, const void* x, int B, int L, const EpiParams& epi, float slope_h) {
   mbv_handle* h = cx.h;
   ConvArgs a;
@@ -938,15 +946,19 @@ int run_pair(Ctx& cx, const ConvLayer& c1, const ConvLayer& c2, const void* x, i
   if (cx.plans_valid && cx.pair_idx < cx.pair_plans->size()) {
     plan = (*cx.pair_plans)[cx.pair_idx];
   } else {
-    const char* msg = tc_make_pair_plan(h->prec, a, h->num_sms, &plan);
+    memset(&plan, 0, sizeof(plan));
+    // k = 3 pairs: pair_tm_kernel (time on the accumulator lane, CTA pairs, resident weights); else the experimental conv_pair_kernel
+    const bool tm = ptm_eligible(h->prec, a, h->cfg.flags, h->num_sms);
+    const char* msg = tm ? ptm_make_plan(h->prec, a, h->num_sms, &plan) : tc_make_pair_plan(h->prec, a, h->num_sms, &plan);
     if (msg) return fail(h, MBV_ERR_CUDA, "%s", msg);
     cx.pair_plans->push_back(plan);
   }
   cx.pair_idx++;
   char desc[56];
-  snprintf(desc, sizeof(desc), "pair m1 Ci%d N%d k%d d%d ph1 L%d nt160", c1.Cp_in, c1.N_total, c1.taps, c1.dil, L);
+  snprintf(desc, sizeof(desc), "pair m1 Ci%d N%d k%d d%d ph1 L%d nt%d", c1.Cp_in, c1.N_total, c1.taps, c1.dil, L, plan.tm ? plan.tm_out_rows : 160);
   ProfScope prof(cx, 0, h->profiling ? desc : "");
-  CUDA_TRY(h, launch_conv_pair(h->prec, a, plan, cx.st, cx.pdl ? 1 : 0));
+  if (plan.tm) CUDA_TRY(h, launch_ptm(h->prec, a, plan, cx.st, cx.pdl ? 1 : 0));
+  else CUDA_TRY(h, launch_conv_pair(h->prec, a, plan, cx.st, cx.pdl ? 1 : 0));
   cx.launches++;
   return MBV_OK;
 }
@@ -1309,7 +1321,8 @@ int run_decode(Ctx& cx, const DecBufs& d, const float* z, const float* z_mask, c
         } else {
           e.xout = h->single ? nullptr : xr;
         }
-        if (c.resblock_type == 1 && pair_ok(h, h->rb_c1[i][j][p], h->rb_c2[i][j][p])) {
+        if (c.resblock_type == 1 && (pair_ok(h, h->rb_c1[i][j][p], h->rb_c2[i][j][p]) ||
+                                     pairtm_ok(h, h->rb_c1[i][j][p], h->rb_c2[i][j][p], e.sum_mode))) {
           // one launch for the conv pair; the operand copies ping-pong (c1 of a neighbouring tile still reads a_in's halo
           // rows while this tile's epilogue writes its output)
           if (final_conv && phase == 0) break;
@@ -1318,15 +1331,18 @@ int run_decode(Ctx& cx, const DecBufs& d, const float* z, const float* z_mask, c
           if ((rc2 = run_pair(cx, h->rb_c1[i][j][p], h->rb_c2[i][j][p], a_in, B, L, e, 0.1f))) return rc2;
           a_in = a_out;
         } else if (c.resblock_type == 1) {
+          // (after fused pairs the operand copy may live in `hop`: the intermediate and the next operand copy take the other buffers)
+          void* hbuf = (a_in == hop) ? ar : hop;
+          void* aout = (hbuf == ar) ? hop : ar;
           if (!(final_conv && phase == 1)) {  // c1 of the last pair still belongs to the branch
             EpiParams e1 = epi_base(EPI_ACT, C, L);
-            e1.slope = 0.1f; e1.act[0] = hop; e1.n_act = 1;
+            e1.slope = 0.1f; e1.act[0] = hbuf; e1.n_act = 1;
             if ((rc2 = run_conv(cx, h->rb_c1[i][j][p], a_in, B, L, L, e1))) return rc2;
           }
           if (final_conv && phase == 0) break;
-          if (!final_conv) { e.act[0] = ar; e.n_act = 1; }
-          if ((rc2 = run_conv(cx, h->rb_c2[i][j][p], hop, B, L, L, e))) return rc2;
-          a_in = ar;
+          if (!final_conv) { e.act[0] = aout; e.n_act = 1; }
+          if ((rc2 = run_conv(cx, h->rb_c2[i][j][p], hbuf, B, L, L, e))) return rc2;
+          a_in = aout;
         } else {
           // ResBlock2: x = x + c_p(lrelu(x)); operand copies ping-pong between ar and hop
           if (final_conv && phase == 0) break;

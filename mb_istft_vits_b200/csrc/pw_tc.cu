@@ -520,6 +520,360 @@ gate_tm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused ResBlock1 conv pair with TIME on the accumulator lane  (pair_tm_kernel):  x' = x + c2(lrelu(c1(a) + b1)) + b2
+// for the k = 3 pairs of a 128-channel stage (modules.py:217-224), the HBM-bound third of that stage: two launches move
+// 1356 MB per pair (the intermediate h = lrelu(c1(a)) goes out and comes back), one kernel 904 MB.
+//
+// Two earlier designs with the output CHANNEL on the lane (conv_pair_kernel) were slower than two launches: a
+// thread owned one channel, so the h tile had to be written to shared memory with 2-byte scattered stores (5 K cycles per
+// tile) and conv 1 -> h-tile epilogue -> conv 2 ran serially inside a CTA.  With time on the lane
+//   * a thread owns one ROW of D1: its 128 channels are the two 128-byte rows (k-blocks) of the K-major, 128B-swizzled
+//     operand tile conv 2 reads -- sixteen 16-byte shared-memory stores per row, conflict-free;
+//   * the epilogue of conv 2 is the row-per-thread residual add of pw_tc_kernel: 256-bit loads of x (requested before the
+//     accumulator wait) and 256-bit stores of x' (fp16 stream) and lrelu(x') (operand copy);
+//   * cta_group::2: each CTA of a pair owns its own row tile (slab, h tile, accumulators) and HALF of every weight tile;
+//     all 12 weight tiles of the two k = 3 convs stay resident (96 KB per CTA) for the life of the persistent pair;
+//   * two D1 and two D2 accumulator slots (4 x 128 TMEM columns): the issuer runs conv 1 of tile i+1 while the epilogue-1
+//     warps turn tile i into its h tile, then conv 2 of tile i; epilogue 2 of tile i-1 streams to HBM meanwhile.
+// A row tile yields 128 - (taps - 1) = 126 output rows: D1 covers rows [t0 - 1, t0 + 127), conv 2's outer taps need one row
+// on either side, and the two rows that would need h rows past D1 are simply not stored (1.6 % of the MMA work).
+// ------------------------------------------------------------------------------------------------
+struct PtRt {
+  int B, L, t_tiles, total_tiles, n_pair_tiles, out_rows;
+  int taps, dil1, shift0;
+  int slab_kb_bytes, slab_stage_bytes, h_kb_bytes;
+  int slab_off, h_off, bias_off, bar_off;
+  float slope_h;
+  const float* bias_h;
+  long long* dbg;   // MBV_TIMELINE=10: clock stamps of pair 0 (both CTAs) [cta][tile < 16][16] (debug only)
+};
+constexpr int PT_KB = 2;                                  // 128 channels = two 64-channel k-blocks
+constexpr int PT_W_TILE = 64 * TC_ROW_BYTES;              // one CTA's half (64 rows) of a weight tile
+constexpr int PT_WARP_TMA = 16, PT_WARP_MMA = 17;         // warps 0-7 epilogue 1, 8-15 epilogue 2
+constexpr int PT_THREADS = 32 * 18;
+
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  // acquire at cluster scope: the arrivals come from both CTAs of the pair and order their shared-memory writes
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    if ((unsigned long long)(clock64() - t0) > TC_TIMEOUT_CYCLES) {
+      printf("mbistft pair_tm: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
+template <typename Op>
+__global__ void __launch_bounds__(PT_THREADS, 1)
+pair_tm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+               const EpiParams p, const PtRt rt) {
+  using T = typename Op::T;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smW = smem;                     // [conv][k-block][tap] half tiles of 8 KB
+  uint8_t* smA = smem + rt.slab_off;       // 2 stages x 2 k-blocks
+  uint8_t* smH = smem + rt.h_off;          // 2 k-blocks x 136 rows x 128 B
+  float* s_b1 = reinterpret_cast<float*>(smem + rt.bias_off);   // [128] c1 bias
+  float* s_b2 = s_b1 + 128;                                     // [2][128] c2 bias (+ per-utterance cond) of the tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + rt.bar_off);
+  const int iWF = 0, iAF = 1, iAE = 3, iD1F = 5, iD1E = 7, iHF = 9, iHE = 10, iD2F = 11, iD2E = 13, nBars = 15;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + nBars);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const uint32_t crank = blockIdx.x & 1u;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int pt_begin = (int)((long long)pair * rt.n_pair_tiles / n_pairs), pt_end = (int)((long long)(pair + 1) * rt.n_pair_tiles / n_pairs);
+  const int n_my = pt_end - pt_begin;
+  const int n_w = 2 * PT_KB * rt.taps;     // resident weight half tiles per CTA
+  auto STAMP = [&](int i, int slot) {
+    if (rt.dbg != nullptr && pair == 0 && lane == 0 && i < 16) rt.dbg[((size_t)crank * 16 + i) * 16 + slot] = clock64();
+  };
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    mbar_init(BAR(iWF), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(BAR(iAF + i), 1); mbar_init(BAR(iAE + i), 1);
+      mbar_init(BAR(iD1F + i), 1); mbar_init(BAR(iD1E + i), 16);
+      mbar_init(BAR(iD2F + i), 1); mbar_init(BAR(iD2E + i), 16);
+    }
+    mbar_init(BAR(iHF), 16);
+    mbar_init(BAR(iHE), 1);
+    fence_barrier_init();
+  }
+  if (warp == PT_WARP_MMA) tmem_alloc2(smem_u32(tmem_ptr_smem), 512u);
+  for (int i = threadIdx.x; i < 128; i += PT_THREADS) s_b1[i] = rt.bias_h[i];
+  const bool shared_bias = p.bias_bs == 0;   // (per-utterance only for the first pair of a ResBlock with speaker conditioning)
+  if (shared_bias) for (int i = threadIdx.x; i < 128; i += PT_THREADS) s_b2[i] = p.bias[i];
+  // rows 128..135 of the h tile are never written (D1 has 128 rows); they only feed the two output rows nobody stores, but
+  // they must not hold NaN patterns
+  for (int i = threadIdx.x; i < PT_KB * 8 * 8; i += PT_THREADS) {
+    const int kb = i / 64, r = 128 + (i % 64) / 8, ch = i % 8;
+    *reinterpret_cast<uint4*>(smH + (size_t)kb * rt.h_kb_bytes + (size_t)r * TC_ROW_BYTES + ch * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  if (warp == PT_WARP_TMA) {  // resident weights: constants of the model, fetched before the dependency wait
+    if (elect_one()) {
+      if (crank == 0) mbar_expect_tx(BAR(iWF), (uint32_t)(2 * n_w * PT_W_TILE));
+      const uint32_t wf = mapa_shared(BAR(iWF), 0);
+      for (int c = 0; c < 2; ++c)
+        for (int kb = 0; kb < PT_KB; ++kb)
+          for (int tap = 0; tap < rt.taps; ++tap)
+            tma_load_2d_2sm(smem_u32(smW) + (uint32_t)(((c * PT_KB + kb) * rt.taps + tap) * PT_W_TILE), c ? &tmW2 : &tmW1, wf, kb * 64,
+                            tap * 128 + (int)crank * 64);
+    }
+    __syncwarp();
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp == PT_WARP_TMA) {
+    // ===================== TMA producer (both CTAs): the slab of its own row tile =====================
+    for (int i = 0; i < n_my; ++i) {
+      const int ri = 2 * (pt_begin + i) + (int)crank;
+      const int b = ri < rt.total_tiles ? ri / rt.t_tiles : rt.B;
+      const int t0 = (ri % rt.t_tiles) * rt.out_rows;
+      const int ss = i & 1;
+      mbar_wait(BAR(iAE + ss), (((uint32_t)i >> 1) & 1u) ^ 1u);
+      if (elect_one()) {
+        if (crank == 0) mbar_expect_tx(BAR(iAF + ss), (uint32_t)(2 * rt.slab_stage_bytes));
+        const uint32_t af = mapa_shared(BAR(iAF + ss), 0);
+        const uint32_t dst = smem_u32(smA) + (uint32_t)(ss * rt.slab_stage_bytes);
+        for (int kb = 0; kb < PT_KB; ++kb) tma_load_3d_2sm(dst + (uint32_t)(kb * rt.slab_kb_bytes), &tmX, af, kb * 64, t0 - 1 + rt.shift0, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == PT_WARP_MMA) {
+    // ===================== MMA issuer (even CTA): conv 1 of tile i+1, then conv 2 of tile i =====================
+    if (crank == 0) {
+      constexpr uint32_t fmt = (Op::kPrec == 3) ? 0u : 1u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)((2 * PW_ROWS) >> 4) << 24);
+      const uint32_t tap_step1 = (uint32_t)(rt.dil1 * TC_ROW_BYTES) >> 4, tap_step2 = (uint32_t)TC_ROW_BYTES >> 4;
+      mbar_wait(BAR(iWF), 0);
+      tc_fence_after();
+      auto conv = [&](int c, uint32_t a_base, uint32_t a_kb_bytes, uint32_t tap_step, uint32_t tmem_d) {
+        uint32_t accum = 0;
+        for (int kb = 0; kb < PT_KB; ++kb) {
+          uint32_t a_lo = desc_lo(a_base + (uint32_t)kb * a_kb_bytes);
+          for (int tap = 0; tap < rt.taps; ++tap) {
+            const uint32_t w_lo = desc_lo(smem_u32(smW) + (uint32_t)(((c * PT_KB + kb) * rt.taps + tap) * PT_W_TILE));
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) tc_mma2<2>(tmem_d, desc64(a_lo + 2 * k), desc64(w_lo + 2 * k), idesc, (k == 0) ? accum : 1u);
+            }
+            __syncwarp();
+            accum = 1;
+            a_lo += tap_step;
+          }
+        }
+      };
+      auto conv1 = [&](int i) {
+        const int s = i & 1;
+        const uint32_t par = ((uint32_t)i >> 1) & 1u;
+        STAMP(i, 0);
+        mbar_wait(BAR(iAF + s), par);
+        STAMP(i, 1);
+        mbar_wait(BAR(iD1E + s), par ^ 1u);
+        tc_fence_after();
+        STAMP(i, 2);
+        conv(0, smem_u32(smA) + (uint32_t)(s * rt.slab_stage_bytes), (uint32_t)rt.slab_kb_bytes, tap_step1, tmem_base + (uint32_t)(s * 128));
+        if (elect_one()) { tc_commit2_mc(BAR(iAE + s), (uint16_t)3); tc_commit2_mc(BAR(iD1F + s), (uint16_t)3); }
+        __syncwarp();
+      };
+      auto conv2 = [&](int i) {
+        const int s = i & 1;
+        const uint32_t par = ((uint32_t)i >> 1) & 1u;
+        STAMP(i, 3);
+        mbar_wait_cluster(BAR(iHF), (uint32_t)i & 1u);   // both CTAs' h tiles are written
+        STAMP(i, 4);
+        mbar_wait(BAR(iD2E + s), par ^ 1u);
+        tc_fence_after();
+        STAMP(i, 5);
+        conv(1, smem_u32(smH), (uint32_t)rt.h_kb_bytes, tap_step2, tmem_base + 256u + (uint32_t)(s * 128));
+        if (elect_one()) { tc_commit2_mc(BAR(iHE), (uint16_t)3); tc_commit2_mc(BAR(iD2F + s), (uint16_t)3); }
+        __syncwarp();
+      };
+      if (n_my > 0) conv1(0);
+      for (int i = 0; i < n_my; ++i) {
+        if (i + 1 < n_my) conv1(i + 1);
+        conv2(i);
+      }
+    }
+  } else if (warp < 8) {
+    // ===================== epilogue-1 warps (8): D1 -> h tile, one row per thread, one k-block (two 32-channel chunks) per warp
+    const int q = warp & 3, r = q * 32 + lane, kbw = warp >> 2;
+    const float slope_h = rt.slope_h;
+    const uint32_t b1_s = smem_u32(s_b1);
+    const uint32_t h_row = smem_u32(smH) + (uint32_t)r * TC_ROW_BYTES;
+    for (int i = 0; i < n_my; ++i) {
+      const int ri = 2 * (pt_begin + i) + (int)crank;
+      const int t_row = (ri % rt.t_tiles) * rt.out_rows - 1 + r;
+      const bool inside = ri < rt.total_tiles && t_row >= 0 && t_row < rt.L;   // outside the utterance h is conv 2's zero padding
+      const int s = i & 1;
+      mbar_wait(BAR(iD1F + s), ((uint32_t)i >> 1) & 1u);
+      tc_fence_after();
+      if (warp == 0) STAMP(i, 6);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 128);
+      // Two halves of two 32-channel chunks (= one k-block of the h tile each), so that only 32 packed registers are live: the first
+      // half is converted while conv 2 of the previous tile still reads the h tile and stored as soon as that conv is done; the
+      // second half follows.  (Holding all four chunks spilled and put local-memory loads in front of every shared-memory store.)
+      auto convert2 = [&](int c0, uint32_t (*hp)[16]) {
+        float acc0[32], acc1[32];
+        tmem_ld32(taddr + (uint32_t)(32 * c0), acc0);
+        tmem_ld32(taddr + (uint32_t)(32 * c0 + 32), acc1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float* acc = h ? acc1 : acc0;
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            float4 b4;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(b1_s + (uint32_t)(32 * (c0 + h) + k) * 4u));
+            float v0 = acc[k] + b4.x, v1 = acc[k + 1] + b4.y, v2 = acc[k + 2] + b4.z, v3 = acc[k + 3] + b4.w;
+            v0 = fmaxf(v0, v0 * slope_h); v1 = fmaxf(v1, v1 * slope_h); v2 = fmaxf(v2, v2 * slope_h); v3 = fmaxf(v3, v3 * slope_h);
+            hp[h][k / 2] = pack_op2<Op>(v0, v1);
+            hp[h][k / 2 + 1] = pack_op2<Op>(v2, v3);
+          }
+        }
+        if (!inside) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) hp[h][k] = 0u;
+        }
+      };
+      auto store2 = [&](int kb, uint32_t (*hp)[16]) {   // chunks 2*kb, 2*kb+1 = the 128-byte row of k-block kb
+        const uint32_t base = h_row + (uint32_t)kb * (uint32_t)rt.h_kb_bytes;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t ci = (uint32_t)(h * 4 + j);
+            const uint32_t addr = base + ((ci ^ (uint32_t)(r & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(hp[h][4 * j]), "r"(hp[h][4 * j + 1]), "r"(hp[h][4 * j + 2]),
+                         "r"(hp[h][4 * j + 3]) : "memory");
+          }
+      };
+      uint32_t hp[2][16];
+      convert2(2 * kbw, hp);          // converted while conv 2 of the previous tile still reads the h tile
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {  // this warp's half of the D1 slot is drained
+        if (crank != 0) mbar_arrive_remote(BAR(iD1E + s), 0u);
+        else mbar_arrive(BAR(iD1E + s));
+      }
+      if (warp == 0) STAMP(i, 7);
+      mbar_wait(BAR(iHE), ((uint32_t)i & 1u) ^ 1u);   // conv 2 of the previous tile has finished reading the h tile
+      if (warp == 0) STAMP(i, 8);
+      store2(kbw, hp);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) {
+        if (crank != 0) mbar_arrive_remote(BAR(iHF), 0u);   // (relaxed: the st.shared + fence.proxy.async above have completed in this SM before the arrive issues)
+        else mbar_arrive(BAR(iHF));
+      }
+      if (warp == 0) STAMP(i, 9);
+    }
+  } else {
+    // ===================== epilogue-2 warps (8): the residual add on D2, one row per thread, two 32-channel chunks per warp
+    const int q = warp & 3, r = q * 32 + lane, half = (warp - 8) >> 2;
+    const int tid2 = threadIdx.x - 256;
+    const float slope = p.slope;
+    for (int i = 0; i < n_my; ++i) {
+      const int ri = 2 * (pt_begin + i) + (int)crank;
+      const bool tile_ok = ri < rt.total_tiles;
+      const int b = tile_ok ? ri / rt.t_tiles : 0;
+      const int t = (ri % rt.t_tiles) * rt.out_rows + r;
+      const bool valid = tile_ok && r < rt.out_rows && t < rt.L;
+      const size_t row_off = ((size_t)b * rt.L + (size_t)t) * (size_t)p.ld * 2 + (size_t)half * 128;
+      uint32_t res[32];
+      if (valid) {
+        const char* xin = reinterpret_cast<const char*>(p.xin) + row_off;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ldg256(xin + j * 32, res + 8 * j);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) res[j] = 0u;
+      }
+      const float* b2 = s_b2;
+      if (!shared_bias) {
+        float* b2w = s_b2 + (i & 1) * 128;
+        if (tid2 < 128) b2w[tid2] = p.bias[(size_t)b * p.bias_bs + tid2];
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        b2 = b2w;
+      }
+      const uint32_t b2_s = smem_u32(b2) + (uint32_t)half * 256u;
+      const int s = i & 1;
+      if (warp == 8) STAMP(i, 10);
+      mbar_wait(BAR(iD2F + s), ((uint32_t)i >> 1) & 1u);
+      tc_fence_after();
+      if (warp == 8) STAMP(i, 11);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)(s * 128) + (uint32_t)half * 64u;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float acc[32];
+        tmem_ld32(taddr + (uint32_t)(32 * c), acc);
+        tmem_ld_wait();
+        if (c == 1) {  // this warp's half of the D2 slot is drained
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (crank != 0) mbar_arrive_remote(BAR(iD2E + s), 0u);
+            else mbar_arrive(BAR(iD2E + s));
+          }
+        }
+        uint32_t xo[16], ao[16];
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {
+          float4 b4;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(b2_s + (uint32_t)(32 * c + k) * 4u));
+          const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&res[16 * c + k / 2]));
+          const float2 r1 = __half22float2(*reinterpret_cast<const __half2*>(&res[16 * c + k / 2 + 1]));
+          const float x0 = r0.x + acc[k] + b4.x, x1 = r0.y + acc[k + 1] + b4.y, x2 = r1.x + acc[k + 2] + b4.z, x3 = r1.y + acc[k + 3] + b4.w;
+          xo[k / 2] = pack_half2_sat(x0, x1);
+          xo[k / 2 + 1] = pack_half2_sat(x2, x3);
+          ao[k / 2] = pack_op2<Op>(fmaxf(x0, x0 * slope), fmaxf(x1, x1 * slope));
+          ao[k / 2 + 1] = pack_op2<Op>(fmaxf(x2, x2 * slope), fmaxf(x3, x3 * slope));
+        }
+        if (valid) {
+          char* xout = reinterpret_cast<char*>(p.sum_mode == 1 ? p.xs : p.xout) + row_off + c * 64;
+          stg256(xout, xo);
+          stg256(xout + 32, xo + 8);
+          if (p.n_act > 0) {
+            char* aout = reinterpret_cast<char*>(p.act[0]) + row_off + c * 64;
+            stg256(aout, ao);
+            stg256(aout + 32, ao + 8);
+          }
+        }
+      }
+      if (warp == 8) STAMP(i, 12);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == PT_WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 bool pw_eligible(int prec, const ConvArgs& a, int flags) {
@@ -607,6 +961,125 @@ const char* pw_make_plan(int prec, const ConvArgs& a, int num_sms, TcPlan* plan)
   return nullptr;
 }
 
+
+// ---- pair_tm_kernel: eligibility, plan, launch
+bool ptm_eligible(int prec, const ConvArgs& a, int flags, int num_sms) {
+  const EpiParams& e = a.epi;
+  if (flags & (MBV_FLAG_NO_PW | MBV_FLAG_NO_PAIR_TM)) return false;
+  if (prec != 2 || num_sms < 2) return false;                       // bf16 operands + fp16 residual stream
+  if (a.Cp_in != 128 || a.N_total != 128 || a.x_ld != 128 || a.n_phases != 1 || a.taps != 3 || a.L_in != a.L_out) return false;
+  if (a.w2 == nullptr || a.bias_h == nullptr) return false;
+  if (e.mode != EPI_RES || e.res_half != 1 || e.xin == nullptr || e.bias == nullptr) return false;
+  // sum_mode 0: x' -> fp16 stream + operand copy;  1 (last pair of the first ResBlock): x' starts the running ResBlock sum, nothing else
+  if (e.sum_mode == 0) { if (e.xout == nullptr || e.n_act != 1 || e.act[0] == nullptr || e.act_add[0] != nullptr) return false; }
+  else if (e.sum_mode == 1) { if (e.xs == nullptr || e.n_act != 0 || e.xout != nullptr) return false; }
+  else return false;
+  if (e.ld != 128 || e.n_valid != 128 || e.row_mul != 1 || e.row_add != 0 || e.rows_out != a.L_out || e.rows_res != a.L_out || e.dup_src >= 0) return false;
+  return PW_ROWS + 2 * a.dil <= 256;
+}
+
+const char* ptm_make_plan(int prec, const ConvArgs& a, int num_sms, TcPairPlan* plan) {
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(tc_tensormap_encoder());
+  if (!enc) return "cuTensorMapEncodeTiled entry point unavailable";
+  const int halo1 = (a.taps - 1) * a.dil;
+  const int box_rows = (PW_ROWS + halo1 + 7) / 8 * 8;
+  plan->tm = 1;
+  plan->tm_out_rows = PW_ROWS - (a.taps - 1);
+  plan->t_tiles = (a.L_out + plan->tm_out_rows - 1) / plan->tm_out_rows;
+  plan->total_tiles = a.B * plan->t_tiles;
+  plan->box_rows = box_rows;
+  plan->tm_slab_kb_bytes = box_rows * TC_ROW_BYTES;
+  plan->tm_slab_stage_bytes = PT_KB * plan->tm_slab_kb_bytes;
+  plan->tm_h_kb_bytes = (PW_ROWS + 8) * TC_ROW_BYTES;
+  plan->tm_slab_off = 2 * PT_KB * a.taps * PT_W_TILE;
+  plan->h_off = plan->tm_slab_off + 2 * plan->tm_slab_stage_bytes;
+  plan->tm_bias_off = plan->h_off + PT_KB * plan->tm_h_kb_bytes;
+  plan->bar_off = plan->tm_bias_off + 3 * 128 * 4;
+  plan->smem_bytes = 1024 + plan->bar_off + 15 * 8 + 16;
+  if (plan->smem_bytes > 227 * 1024) return "conv pair (time on lane): shared memory budget exceeded";
+  const int n_pair_tiles = (plan->total_tiles + 1) / 2;
+  const int pairs = n_pair_tiles < num_sms / 2 ? n_pair_tiles : num_sms / 2;
+  plan->grid = 2 * (pairs < 1 ? 1 : pairs);
+  const CUtensorMapDataType dt = prec == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)a.Cp_in, (cuuint64_t)a.L_in, (cuuint64_t)a.B};
+    cuuint64_t strides[2] = {(cuuint64_t)a.x_ld * 2, (cuuint64_t)a.L_in * a.x_ld * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&plan->tmA, dt, 3, const_cast<void*>(a.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return "cuTensorMapEncodeTiled failed for the pair activation map";
+  }
+  for (int which = 0; which < 2; ++which) {
+    cuuint64_t dims[2] = {(cuuint64_t)a.Cp_in, (cuuint64_t)a.taps * a.N_total};
+    cuuint64_t strides[1] = {(cuuint64_t)a.Cp_in * 2};
+    cuuint32_t box[2] = {64, 64};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(which ? &plan->tmB2 : &plan->tmB, dt, 2, const_cast<void*>(which ? a.w2 : a.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return "cuTensorMapEncodeTiled failed for a pair weight map";
+  }
+  return nullptr;
+}
+
+template <typename Op>
+static cudaError_t ptm_launch_one(const ConvArgs& a, const TcPairPlan& p, const PtRt& rt, cudaStream_t st, int pdl, bool set_attr) {
+  auto k = pair_tm_kernel<Op>;
+  if (set_attr) return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.grid);
+  cfg.blockDim = dim3(PT_THREADS);
+  cfg.dynamicSmemBytes = p.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  return cudaLaunchKernelEx(&cfg, k, p.tmA, p.tmB, p.tmB2, a.epi, rt);
+}
+
+cudaError_t launch_ptm(int prec, const ConvArgs& a, const TcPairPlan& p, cudaStream_t st, int pdl) {
+  PtRt rt;
+  rt.B = a.B; rt.L = a.L_out; rt.t_tiles = p.t_tiles; rt.total_tiles = p.total_tiles; rt.n_pair_tiles = (p.total_tiles + 1) / 2;
+  rt.out_rows = p.tm_out_rows; rt.taps = a.taps; rt.dil1 = a.dil; rt.shift0 = a.shift0[0];
+  rt.slab_kb_bytes = p.tm_slab_kb_bytes; rt.slab_stage_bytes = p.tm_slab_stage_bytes; rt.h_kb_bytes = p.tm_h_kb_bytes;
+  rt.slab_off = p.tm_slab_off; rt.h_off = p.h_off; rt.bias_off = p.tm_bias_off; rt.bar_off = p.bar_off;
+  rt.slope_h = a.slope_h; rt.bias_h = a.bias_h;
+  if (prec != 2) return cudaErrorInvalidValue;
+  static long long* dbg = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) {
+    const char* e = getenv("MBV_TIMELINE");
+    dbg_on = (e && atoi(e) == 10) ? 1 : 0;
+    if (dbg_on) { cudaMalloc(&dbg, 2 * 16 * 16 * sizeof(long long)); cudaMemset(dbg, 0, 2 * 16 * 16 * sizeof(long long)); }
+  }
+  rt.dbg = dbg_on ? dbg : nullptr;
+  cudaError_t e = ptm_launch_one<OpBF16>(a, p, rt, st, pdl, false);
+  if (dbg_on && e == cudaSuccess) {
+    cudaStreamSynchronize(st);
+    long long hb[2 * 16 * 16];
+    cudaMemcpy(hb, dbg, sizeof(hb), cudaMemcpyDeviceToHost);
+    const long long t0 = hb[0];
+    fprintf(stderr, "[pair_tm timeline] d%d  columns: conv1 issue | slab ok | D1 free | conv2 issue | h ok | D2 free || epi1: D1 full | loaded | h free | h written || epi2: top | D2 full | stored\n", a.dil);
+    for (int c = 0; c < 2; ++c)
+      for (int i = 0; i < 12; ++i) {
+        const long long* r = &hb[(c * 16 + i) * 16];
+        fprintf(stderr, "  cta %d tile %2d  %7lld %7lld %7lld | %7lld %7lld %7lld || %7lld %7lld %7lld %7lld || %7lld %7lld %7lld\n", c, i,
+                r[0] ? r[0] - t0 : 0, r[1] ? r[1] - t0 : 0, r[2] ? r[2] - t0 : 0, r[3] ? r[3] - t0 : 0, r[4] ? r[4] - t0 : 0, r[5] ? r[5] - t0 : 0,
+                r[6] - t0, r[7] - t0, r[8] - t0, r[9] - t0, r[10] - t0, r[11] - t0, r[12] - t0);
+      }
+    cudaMemset(dbg, 0, sizeof(hb));
+  }
+  return e;
+}
 
 // ---- gate_tm_kernel: eligibility, plan, launch
 bool gt_eligible(int prec, const ConvArgs& a, int flags, int num_sms) {
@@ -752,6 +1225,7 @@ cudaError_t pw_set_attributes() {
   GtRt g{};
   cudaError_t e = gt_launch_one<OpBF16>(a, p, g, nullptr, 0, true);
   if (e == cudaSuccess) e = gt_launch_one<OpF16>(a, p, g, nullptr, 0, true);
+  if (e == cudaSuccess) { TcPairPlan pp{}; PtRt pr{}; e = ptm_launch_one<OpBF16>(a, pp, pr, nullptr, 0, true); }
   return e;
 }
 

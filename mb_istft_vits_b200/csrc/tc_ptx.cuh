@@ -98,7 +98,16 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"(mask) : "memory");
 }
+// Arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster.  The signals sent this way ("this CTA's
+// epilogue warps have drained a TMEM accumulator", "its h tile is written") order tcgen05 / shared-memory accesses that the
+// tcgen05 fences and fence.proxy.async already cover; a RELEASE at cluster scope would additionally wait until every global
+// store the thread issued before (the epilogue's output!) is performed -- measured as MEMBAR / ERRBAR stalls that made the
+// odd CTA of a pair, and with it the pair, wait a DRAM write latency per tile.  Hence relaxed.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+               "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t bar, uint32_t cta) {
   asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
                "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta) : "memory");
 }

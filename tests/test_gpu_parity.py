@@ -846,3 +846,26 @@ def test_time_on_lane_kernels_at_tile_edges(B, T):
         if cname == "ljs_mini_mb_istft_vits" and T <= 300:
             z_cpu = orc.flow_reverse(sd, cfg, z_p, mask)
             assert orc.snr_db(got, z_cpu) > 40.0
+
+
+def test_fused_k3_conv_pair_time_on_lane_matches_two_launches():
+    """pair_tm_kernel (the k = 3 ResBlock1 conv pairs of a 128-channel stage in ONE kernel: conv 1 -> bf16 h tile in shared
+    memory -> conv 2 -> residual add, time on the accumulator lane, CTA pairs) against the two-launch path
+    (MBV_FLAG_NO_PAIR_TM): the same bf16 intermediate and the same operation order, so the waveforms agree to accumulation-order
+    rounding (held: >= 70 dB); ragged lengths, an odd number of row tiles, utterances shorter than one tile."""
+    from mb_istft_vits_b200 import lib as L
+    for case in ("mb", "ms_spk", "mb_long", "mb_gscale"):
+        cfg, sd, t, meta = load_case(case)
+        ref = _run(_engine(cfg, sd, "bf16", L.FLAG_NO_PAIR_TM), t)
+        got = _run(_engine(cfg, sd, "bf16", 0), t)
+        assert orc.snr_db(got[1], ref[1]) > 70.0, (case, orc.snr_db(got[1], ref[1]))
+        assert orc.snr_db(got[1], t["o"]) > 40.0
+    cfg = get_config("ljs_mb_istft_vits")
+    sd = synth.make_state_dict(cfg, seed=1234)
+    lengths = [300, 299, 17, 300, 1, 256, 123]
+    z_p, mask, _ = synth.make_latents(cfg, len(lengths), 300, seed=5, lengths=lengths)
+    a = _engine(cfg, sd, "bf16", L.FLAG_NO_PAIR_TM).flow_decode(z_p.cuda(), mask.cuda())
+    b = _engine(cfg, sd, "bf16", 0).flow_decode(z_p.cuda(), mask.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(a[0], b[0])   # the flow does not go through the pair kernel
+    assert orc.snr_db(b[1].cpu(), a[1].cpu()) > 70.0
