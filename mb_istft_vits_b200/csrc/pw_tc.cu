@@ -44,8 +44,9 @@ struct PwRt {
   int kblocks;    // Cp_in / 64
   int N;          // output channels = UMMA N (multiple of 32, <= 256)
   int n_tiles;
-  int n_a_stages, a_stage_bytes, w_bytes;
+  int n_a_stages, w_bytes;     // ring of 16 KB k-block stages; bytes of the resident weights
   int a_off, bias_off, bar_off;
+  int res_c0, res_cols, res_box;   // L2 prefetch of the residual rows: first channel, channels, box width (elements)
 };
 
 __device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
@@ -91,7 +92,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
-    if constexpr (MODE == EPI_RS) tma_prefetch_desc(&tmR);
+    if constexpr (MODE != EPI_ACT) tma_prefetch_desc(&tmR);
     mbar_init(BAR(iWF), 1);
     for (int i = 0; i < rt.n_a_stages; ++i) { mbar_init(BAR(iAF + i), 1); mbar_init(BAR(iAE + i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(iCF + i), 1); mbar_init(BAR(iCE + i), PW_EPI_WARPS); }
@@ -117,24 +118,24 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == PW_WARP_TMA) {
-    // ===================== TMA producer: one activation tile (all k-blocks) per stage =====================
+    // ===================== TMA producer: one k-block (128 rows x 64 channels, 16 KB) of an activation tile per ring stage
     int s = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < rt.n_tiles; tile += gridDim.x) {
-      mbar_wait(BAR(iAE + s), ph ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(BAR(iAF + s), (uint32_t)(rt.kblocks * PW_KB_BYTES));
-        const uint32_t dst = smem_u32(smA) + (uint32_t)(s * rt.a_stage_bytes);
-        for (int kb = 0; kb < rt.kblocks; ++kb)
-          tma_load_2d(dst + (uint32_t)(kb * PW_KB_BYTES), &tmX, BAR(iAF + s), kb * 64, tile * PW_ROWS);
-        if constexpr (MODE == EPI_RS) {
-          // the residual rows of this tile: asked into L2 now (the producer runs n_a_stages tiles ahead of the epilogue), so the
-          // epilogue's 256-bit loads find them there instead of paying a DRAM round trip per tile
-          for (int c = 0; c < rt.N; c += 64) tma_prefetch_l2_2d(&tmR, c, tile * PW_ROWS);
+      for (int kb = 0; kb < rt.kblocks; ++kb) {
+        mbar_wait(BAR(iAE + s), ph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(BAR(iAF + s), (uint32_t)PW_KB_BYTES);
+          tma_load_2d(smem_u32(smA) + (uint32_t)(s * PW_KB_BYTES), &tmX, BAR(iAF + s), kb * 64, tile * PW_ROWS);
+          if (MODE != EPI_ACT && kb == 0) {
+            // the residual rows of this tile: asked into L2 now (the producer runs ahead of the epilogue), so the epilogue's
+            // 256-bit loads find them there instead of paying a DRAM round trip per tile
+            for (int c = 0; c < rt.res_cols; c += rt.res_box) tma_prefetch_l2_2d(&tmR, rt.res_c0 + c, tile * PW_ROWS);
+          }
         }
+        __syncwarp();
+        if (++s == rt.n_a_stages) { s = 0; ph ^= 1; }
       }
-      __syncwarp();
-      if (++s == rt.n_a_stages) { s = 0; ph ^= 1; }
     }
   } else if (warp == PW_WARP_MMA) {
     // ===================== MMA issuer =====================
@@ -146,21 +147,23 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     tc_fence_after();
     for (int tile = blockIdx.x; tile < rt.n_tiles; tile += gridDim.x) {
       mbar_wait(BAR(iCE + sc), pc ^ 1);
-      mbar_wait(BAR(iAF + s), ph);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(sc * PW_ACC_STRIDE);
       for (int kb = 0; kb < rt.kblocks; ++kb) {
-        const uint32_t a_lo = desc_lo(smem_u32(smA) + (uint32_t)(s * rt.a_stage_bytes + kb * PW_KB_BYTES));
+        mbar_wait(BAR(iAF + s), ph);
+        tc_fence_after();
+        const uint32_t a_lo = desc_lo(smem_u32(smA) + (uint32_t)(s * PW_KB_BYTES));
         const uint32_t w_lo = desc_lo(smem_u32(smW) + (uint32_t)(kb * rt.N * TC_ROW_BYTES));
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) tc_mma<2>(tmem_d, desc64(a_lo + 2 * k), desc64(w_lo + 2 * k), idesc, (kb | k) ? 1u : 0u);
+          tc_commit(BAR(iAE + s));
         }
         __syncwarp();
+        if (++s == rt.n_a_stages) { s = 0; ph ^= 1; }
       }
-      if (elect_one()) { tc_commit(BAR(iAE + s)); tc_commit(BAR(iCF + sc)); }
+      if (elect_one()) tc_commit(BAR(iCF + sc));
       __syncwarp();
-      if (++s == rt.n_a_stages) { s = 0; ph ^= 1; }
       if (++sc == 2) { sc = 0; pc ^= 1; }
     }
   } else {
@@ -176,6 +179,62 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       const bool valid = row < rt.R;
       float m = 1.f;
       if (p.mask != nullptr) m = valid ? p.mask[row] : 0.f;
+      if constexpr (MODE == EPI_POST) {
+        // coupling update (modules.py:338-352): z[:, ch_off + n] = (z - sign * ((acc + bias) * mask)) * mask on the fp32 latent, plus
+        // its operand copy.  N <= 128: at most two 32-channel chunks per warp, 128 bytes of fp32 z each.
+        const size_t zoff = (size_t)row * ld + (size_t)p.ch_off + (size_t)(half * 32);
+        uint32_t zr[2][32];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (valid && half * 32 + 64 * j < rt.N) {
+            const char* zin = reinterpret_cast<const char*>(p.xin) + (zoff + (size_t)(64 * j)) * 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ldg256(zin + k * 32, zr[j] + 8 * k);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) zr[j][i] = 0u;
+          }
+        }
+        mbar_wait(BAR(iCF + sc), pc);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc * PW_ACC_STRIDE);
+        const float sign = p.post_sign;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c = half * 32 + 64 * j;
+          if (c < rt.N) {
+            float acc[32];
+            tmem_ld32(taddr + (uint32_t)c, acc);
+            tmem_ld_wait();
+            uint32_t zo[32], u[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float4 b4;
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(bias_s + (uint32_t)(c + i) * 4u));
+              const float z0 = (__uint_as_float(zr[j][i]) - sign * ((acc[i] + b4.x) * m)) * m;
+              const float z1 = (__uint_as_float(zr[j][i + 1]) - sign * ((acc[i + 1] + b4.y) * m)) * m;
+              const float z2 = (__uint_as_float(zr[j][i + 2]) - sign * ((acc[i + 2] + b4.z) * m)) * m;
+              const float z3 = (__uint_as_float(zr[j][i + 3]) - sign * ((acc[i + 3] + b4.w) * m)) * m;
+              zo[i] = __float_as_uint(z0); zo[i + 1] = __float_as_uint(z1); zo[i + 2] = __float_as_uint(z2); zo[i + 3] = __float_as_uint(z3);
+              u[i / 2] = pack_op2<Op>(z0, z1);
+              u[i / 2 + 1] = pack_op2<Op>(z2, z3);
+            }
+            if (valid) {
+              char* zout = reinterpret_cast<char*>(p.xout) + (zoff + (size_t)(64 * j)) * 4;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) stg256(zout + k * 32, zo + 8 * k);
+              char* ao = reinterpret_cast<char*>(p.act[0]) + (zoff + (size_t)(64 * j)) * 2;
+              stg256(ao, u);
+              stg256(ao + 32, u + 8);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(iCE + sc));
+        if (++sc == 2) { sc = 0; pc ^= 1; }
+        continue;
+      }
       // the residual input does not depend on the accumulator: all of this thread's chunks are requested before the wait
       uint32_t res[PW_MAX_CHUNKS][16];
       if constexpr (MODE == EPI_RS) {
@@ -880,10 +939,12 @@ bool pw_eligible(int prec, const ConvArgs& a, int flags) {
   const EpiParams& e = a.epi;
   if (flags & MBV_FLAG_NO_PW) return false;
   if (prec < 2 || a.taps != 1 || a.n_phases != 1 || a.shift0[0] != 0 || a.gate) return false;
-  if (a.L_in != a.L_out || a.Cp_in % 64 != 0 || a.Cp_in > 256) return false;
+  if (a.L_in != a.L_out || a.Cp_in % 64 != 0) return false;
   if (e.bias == nullptr || e.bias_bs != 0) return false;
   if (e.n_valid % 32 != 0 || e.n_valid < 32 || e.n_valid > 256 || e.n_valid > a.N_total || e.ld < e.n_valid || e.ld % 16 != 0) return false;
   if (e.row_mul != 1 || e.row_add != 0 || e.rows_out != a.L_out || e.rows_res != a.L_out || e.dup_src >= 0) return false;
+  // resident weights + at least three 16 KB k-block stages
+  if ((a.Cp_in / 64) * e.n_valid * TC_ROW_BYTES + 3 * PW_KB_BYTES + 4096 > 224 * 1024) return false;
   if (e.mode == EPI_RS) {
     if (e.res_half != 1 && e.res_half != 2) return false;
     if (e.res_half == 2 && prec != 3) return false;
@@ -896,6 +957,11 @@ bool pw_eligible(int prec, const ConvArgs& a, int flags) {
     if (e.n_act > 1 || (e.n_act == 1 && (e.act[0] == nullptr || e.act_add[0] != nullptr))) return false;
     if (e.xout != nullptr && e.res_half != 1) return false;
     if (e.xout == nullptr && e.n_act == 0) return false;
+    return true;
+  }
+  if (e.mode == EPI_POST) {  // coupling update on the fp32 latent (K = n_layers * hidden: the weights still fit, N = half the latent)
+    if (e.n_valid > 128 || e.xin == nullptr || e.xout == nullptr || e.act[0] == nullptr || e.n_act != 1 || e.mask == nullptr) return false;
+    if (e.ch_off % 16 != 0 || e.ld % 16 != 0 || e.ch_off + e.n_valid > e.ld) return false;
     return true;
   }
   return false;
@@ -914,11 +980,11 @@ const char* pw_make_plan(int prec, const ConvArgs& a, int num_sms, TcPlan* plan)
   plan->pw_N = N; plan->pw_kblocks = kblocks; plan->pw_R = (int)R;
   plan->pw_tiles = (int)((R + PW_ROWS - 1) / PW_ROWS);
   plan->pw_w_bytes = kblocks * N * TC_ROW_BYTES;
-  plan->pw_a_stage_bytes = kblocks * PW_KB_BYTES;
+  plan->pw_a_stage_bytes = PW_KB_BYTES;    // ring of k-block stages
   const int fixed = 2048;  // bias + barriers
-  int stages = (224 * 1024 - plan->pw_w_bytes - fixed) / plan->pw_a_stage_bytes;
-  if (stages > 4) stages = 4;
-  if (stages < 2) return "pointwise conv: not enough shared memory";
+  int stages = (224 * 1024 - plan->pw_w_bytes - fixed) / PW_KB_BYTES;
+  if (stages > 12) stages = 12;
+  if (stages < 3) return "pointwise conv: not enough shared memory";
   plan->pw_a_stages = stages;
   plan->pw_a_off = plan->pw_w_bytes;
   plan->pw_bias_off = plan->pw_a_off + stages * plan->pw_a_stage_bytes;
@@ -949,12 +1015,13 @@ const char* pw_make_plan(int prec, const ConvArgs& a, int num_sms, TcPlan* plan)
       return "cuTensorMapEncodeTiled failed for the pointwise weight map";
   }
   plan->tmR = plan->tmA; plan->tmS = plan->tmA; plan->tmBh = plan->tmB;  // unused
-  if (a.epi.mode == EPI_RS) {  // residual rows: L2 prefetch boxes of 64 channels x 128 rows
+  if (a.epi.mode == EPI_RS || a.epi.mode == EPI_POST) {  // residual rows: L2 prefetch boxes of 128 bytes x 128 rows
+    const bool f32 = a.epi.mode == EPI_POST;
     cuuint64_t dims[2] = {(cuuint64_t)a.epi.ld, (cuuint64_t)R};
-    cuuint64_t strides[1] = {(cuuint64_t)a.epi.ld * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)PW_ROWS};
+    cuuint64_t strides[1] = {(cuuint64_t)a.epi.ld * (f32 ? 4 : 2)};
+    cuuint32_t box[2] = {(cuuint32_t)(f32 ? 32 : 64), (cuuint32_t)PW_ROWS};
     cuuint32_t estr[2] = {1, 1};
-    if (enc(&plan->tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a.epi.xin), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    if (enc(&plan->tmR, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a.epi.xin), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return "cuTensorMapEncodeTiled failed for the pointwise residual map";
   }
@@ -1204,7 +1271,9 @@ static cudaError_t pw_dispatch(int prec, const ConvArgs& a, const TcPlan& p, con
     if (mode == EPI_RS && rh == 1) return pw_launch_one<OpBF16, EPI_RS, 1>(a, p, rt, st, pdl, set_attr);
     if (mode == EPI_ACT && rh == 1) return pw_launch_one<OpBF16, EPI_ACT, 1>(a, p, rt, st, pdl, set_attr);
     if (mode == EPI_ACT && rh == 0) return pw_launch_one<OpBF16, EPI_ACT, 0>(a, p, rt, st, pdl, set_attr);
+    if (mode == EPI_POST) return pw_launch_one<OpBF16, EPI_POST, 0>(a, p, rt, st, pdl, set_attr);
   } else if (prec == 3) {
+    if (mode == EPI_POST) return pw_launch_one<OpF16, EPI_POST, 0>(a, p, rt, st, pdl, set_attr);
     if (mode == EPI_RS && rh == 1) return pw_launch_one<OpF16, EPI_RS, 1>(a, p, rt, st, pdl, set_attr);
     if (mode == EPI_RS && rh == 2) return pw_launch_one<OpF16, EPI_RS, 2>(a, p, rt, st, pdl, set_attr);
     if (mode == EPI_ACT && rh == 1) return pw_launch_one<OpF16, EPI_ACT, 1>(a, p, rt, st, pdl, set_attr);
@@ -1217,7 +1286,8 @@ cudaError_t pw_set_attributes() {
   ConvArgs a{};
   TcPlan p{};
   PwRt rt{};
-  const int combos[7][3] = {{2, EPI_RS, 1}, {2, EPI_ACT, 1}, {2, EPI_ACT, 0}, {3, EPI_RS, 1}, {3, EPI_RS, 2}, {3, EPI_ACT, 1}, {3, EPI_ACT, 0}};
+  const int combos[9][3] = {{2, EPI_RS, 1}, {2, EPI_ACT, 1}, {2, EPI_ACT, 0}, {3, EPI_RS, 1}, {3, EPI_RS, 2}, {3, EPI_ACT, 1}, {3, EPI_ACT, 0},
+                            {2, EPI_POST, 0}, {3, EPI_POST, 0}};
   for (auto& c : combos) {
     cudaError_t e = pw_dispatch(c[0], a, p, rt, nullptr, 0, true, c[1], c[2]);
     if (e != cudaSuccess) return e;
@@ -1233,9 +1303,10 @@ cudaError_t launch_pw(int prec, const ConvArgs& a, const TcPlan& p, cudaStream_t
   if (p.pw == 2) return launch_gt(prec, a, p, st, pdl);
   PwRt rt;
   rt.R = p.pw_R; rt.kblocks = p.pw_kblocks; rt.N = p.pw_N; rt.n_tiles = p.pw_tiles;
-  rt.n_a_stages = p.pw_a_stages; rt.a_stage_bytes = p.pw_a_stage_bytes; rt.w_bytes = p.pw_w_bytes;
+  rt.n_a_stages = p.pw_a_stages; rt.w_bytes = p.pw_w_bytes;
   rt.a_off = p.pw_a_off; rt.bias_off = p.pw_bias_off; rt.bar_off = p.pw_bar_off;
-  const int rh = (a.epi.mode == EPI_RS) ? a.epi.res_half : (a.epi.xout != nullptr ? 1 : 0);
+  rt.res_c0 = a.epi.mode == EPI_POST ? a.epi.ch_off : 0; rt.res_cols = p.pw_N; rt.res_box = a.epi.mode == EPI_POST ? 32 : 64;
+  const int rh = (a.epi.mode == EPI_RS) ? a.epi.res_half : (a.epi.mode == EPI_POST ? 0 : (a.epi.xout != nullptr ? 1 : 0));
   return pw_dispatch(prec, a, p, rt, st, pdl, false, a.epi.mode, rh);
 }
 
