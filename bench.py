@@ -631,7 +631,7 @@ def run_native(args):
     pk_s = peaks["tflops_sustained"] * (0.5 if tf32 else 1.0)
     pk_b = peaks["tflops_burst"] * (0.5 if tf32 else 1.0)
     roofline = {
-        "kernel": "conv kernels (tcgen05 implicit-GEMM convs: conv_tc_kernel, pw_tc_kernel, gate_tm_kernel; all %d launches per step)" % n_conv_step,
+        "kernel": "conv kernels (tcgen05 implicit-GEMM convs: conv_tc_kernel, pw_tc_kernel, gate_tm_kernel, pair_tm_kernel; all %d launches per step)" % n_conv_step,
         "bound": "tensor", "achieved": conv_tflops, "peak": pk_s, "unit": "TFLOP/s", "frac": conv_tflops / pk_s,
         "frac_vs_burst_peak": conv_tflops / pk_b, "peak_burst": pk_b,
         "traffic": traffic.get("conv_dram_bytes_per_launch"), "traffic_source": traffic.get("source"),
