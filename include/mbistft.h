@@ -106,6 +106,9 @@ typedef struct {
 #define MBV_FLAG_NO_PAIR_SPLIT 1024 /* A/B only: do not cut the leftover pair tiles of a CTA-pair launch's last round into column pieces */
 #define MBV_FLAG_NO_PAIR_TM 2048   /* A/B and cross-check tests: run the k = 3 ResBlock1 conv pairs of a 128-channel stage as two launches instead of
                                      * pair_tm_kernel (one kernel, intermediate activation kept in shared memory) */
+#define MBV_FLAG_NO_CONV_TM 4096    /* A/B and cross-check tests: run the k = 7 / k = 11 convs of a 128-channel ResBlock stage on the generic conv
+                                     * kernel (single-CTA MMAs, channel on the lane) instead of conv_tm_kernel (time on the lane, cta_group::2
+                                     * MMAs over CTA pairs that share every weight tile) */
 #define MBV_FLAG_SPLIT_TAIL 128     /* keep conv_post as its own conv launch writing fp32 logits for the stand-alone tail kernel instead
                                      * of the fused conv_post + tail kernel (the default on the 16-bit paths; A/B and cross-check tests) */
 #define MBV_FLAG_BRANCHES 64         /* experimental: run the parallel ResBlocks of a stage on the library's two extra streams (own

@@ -1145,6 +1145,7 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
   if (pw_eligible(prec, a, flags)) return pw_make_plan(prec, a, num_sms, plan);  // 1x1 convs of the WN stacks: pw_tc.cu
   static const int gt_env = getenv("MBV_GATE_TM") ? atoi(getenv("MBV_GATE_TM")) : 1;  // A/B measurements only
   if (gt_env && gt_eligible(prec, a, flags, num_sms)) return gt_make_plan(prec, a, num_sms, plan);  // WN gate convs: pw_tc.cu
+  if (ct_eligible(prec, a, flags, num_sms)) return ct_make_plan(prec, a, num_sms, plan);  // k >= 5 convs of a 128-channel ResBlock stage: pw_tc.cu
   const int esize = prec >= 2 ? 2 : 4;
   const int KB = TC_ROW_BYTES / esize;
   if (a.Cp_in % 64 != 0) return "tcgen05 conv: padded input channels must be a multiple of 64";

@@ -38,6 +38,8 @@ bool pw_eligible(int prec, const ConvArgs& a, int flags);
 const char* pw_make_plan(int prec, const ConvArgs& a, int num_sms, TcPlan* plan);
 bool gt_eligible(int prec, const ConvArgs& a, int flags, int num_sms);   // WN gate conv on gate_tm_kernel (plan->pw = 2)
 const char* gt_make_plan(int prec, const ConvArgs& a, int num_sms, TcPlan* plan);
+bool ct_eligible(int prec, const ConvArgs& a, int flags, int num_sms);   // k >= 5 convs of a 128-channel ResBlock stage on conv_tm_kernel (plan->pw = 3)
+const char* ct_make_plan(int prec, const ConvArgs& a, int num_sms, TcPlan* plan);
 cudaError_t launch_pw(int prec, const ConvArgs& a, const TcPlan& plan, cudaStream_t st, int pdl);
 cudaError_t pw_set_attributes();
 // Fills plan (tensor maps, staging, grid) for args; returns a message on failure, nullptr on success.

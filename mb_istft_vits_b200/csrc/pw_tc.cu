@@ -933,6 +933,291 @@ pair_tm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Multi-tap convs of a 128-channel ResBlock stage with TIME on the accumulator lane  (conv_tm_kernel): the k = 7 / k = 11
+// convs of ResBlock1 (c1: bias -> lrelu -> operand copy; c2: the residual add in its four running-sum flavours,
+// modules.py:213-228, models.py:355-361).
+//
+// On conv_tc_kernel these convs have ONE 128-row channel tile, so they run as single-CTA MMAs (M 128, N 256: 12 KB of shared
+// memory operands per MMA, ~250 cycles against 128 nominal) -- the largest block of the step.  With time on the lane the
+// operand roles swap (A = activation rows, B = the 128 weight rows of a tap) and a CTA PAIR shares B: one
+// tcgen05.mma.cta_group::2 (M = 256, N = 128) multiplies one 128-row sub-tile of EACH CTA with the same weight tile, half of
+// whose rows each CTA holds: 4 KB of A + 2 KB of B per CTA and MMA, measured ~88 cycles per MMA in pair_tm_kernel (N = 128,
+// i.e. ~176 per N = 256 equivalent).
+//   * a CTA tile is 256 consecutive time steps of one utterance = two 128-row sub-tiles, so every weight stage (two
+//     (k-block, tap) steps = 16 KB per CTA) feeds 16 MMAs and the L2 -> shared-memory weight traffic per output row is that of
+//     the 256-column tiles of conv_tc_kernel; the slab (256 + halo rows, both k-blocks, two TMA boxes per k-block) is loaded
+//     once per tile, a tap is a row offset of the A descriptor; the next tile's slab is requested in the middle of the current
+//     tile's weight stages;
+//   * accumulators: 2 slots x 2 sub-tiles x 128 TMEM columns; 16 epilogue warps (8 per sub-tile: lane quarter x 64-channel half);
+//   * an epilogue thread owns one ROW: 64 channels = 128 contiguous bytes of the channels-last tensors per stream: 256-bit
+//     loads of the residual row (requested before the accumulator wait) and 256-bit stores, as in pair_tm_kernel.
+// ------------------------------------------------------------------------------------------------
+struct CtRt {
+  int B, L, t_tiles, total_tiles, n_pair_tiles;
+  int taps, dil, shift0, box_rows;
+  int slab_kb_bytes, slab_stage_bytes, n_w_stages;
+  int w_off, bias_off, bar_off;
+};
+constexpr int CT_ROWS = 256;                               // rows per CTA tile: two 128-row accumulators
+constexpr int CT_KB = 2;                                   // 128 input channels = two 64-channel k-blocks
+constexpr int CT_W_STEP = 64 * TC_ROW_BYTES;               // one CTA's half (64 rows) of a (k-block, tap) weight tile
+constexpr int CT_W_STAGE_BYTES = 2 * CT_W_STEP;            // two steps per ring stage
+constexpr int CT_SLAB_STAGES = 2;
+constexpr int CT_EPI_WARPS = 16;
+constexpr int CT_WARP_TMA = 16, CT_WARP_MMA = 17;
+constexpr int CT_THREADS = 32 * 18;
+
+// SM = the residual add's running-sum flavour (EpiParams::sum_mode 0..3), compile-time so that each variant holds only its own streams in registers
+template <typename Op, int MODE, int SM>
+__global__ void __launch_bounds__(CT_THREADS, 1)
+conv_tm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const EpiParams p, const CtRt rt) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;                  // CT_SLAB_STAGES x 2 k-blocks x 2 boxes
+  uint8_t* smW = smem + rt.w_off;       // n_w_stages x 16 KB
+  float* s_bias = reinterpret_cast<float*>(smem + rt.bias_off);   // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + rt.bar_off);
+  const int iAF = 0, iAE = iAF + CT_SLAB_STAGES, iWF = iAE + CT_SLAB_STAGES, iWE = iWF + rt.n_w_stages, iCF = iWE + rt.n_w_stages,
+            iCE = iCF + 2, nBars = iCE + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + nBars);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const uint32_t crank = blockIdx.x & 1u;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int pt_begin = (int)((long long)pair * rt.n_pair_tiles / n_pairs), pt_end = (int)((long long)(pair + 1) * rt.n_pair_tiles / n_pairs);
+  const int n_my = pt_end - pt_begin;
+  const int n_stages_tile = rt.taps;    // CT_KB * taps steps, two per stage
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    for (int i = 0; i < CT_SLAB_STAGES; ++i) { mbar_init(BAR(iAF + i), 1); mbar_init(BAR(iAE + i), 1); }
+    for (int i = 0; i < rt.n_w_stages; ++i) { mbar_init(BAR(iWF + i), 1); mbar_init(BAR(iWE + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(iCF + i), 1); mbar_init(BAR(iCE + i), 2 * CT_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == CT_WARP_MMA) tmem_alloc2(smem_u32(tmem_ptr_smem), 512u);
+  const bool shared_bias = p.bias_bs == 0;
+  if (shared_bias) for (int i = threadIdx.x; i < 128; i += CT_THREADS) s_bias[i] = p.bias[i];   // weights: not produced by the previous kernel
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp == CT_WARP_TMA) {
+    // ===================== TMA producer (both CTAs): own slab, own half of every weight tile =====================
+    auto load_slab = [&](int i) {
+      const int ri = 2 * (pt_begin + i) + (int)crank;
+      const int b = ri < rt.total_tiles ? ri / rt.t_tiles : rt.B;   // no tile for this CTA: rows of utterance B do not exist -> zeros
+      const int t0 = (ri % rt.t_tiles) * CT_ROWS + rt.shift0;
+      const int ss = i & 1;
+      mbar_wait(BAR(iAE + ss), (((uint32_t)i >> 1) & 1u) ^ 1u);
+      if (elect_one()) {
+        if (crank == 0) mbar_expect_tx(BAR(iAF + ss), (uint32_t)(2 * rt.slab_stage_bytes));
+        const uint32_t af = mapa_shared(BAR(iAF + ss), 0);
+        const uint32_t dst = smem_u32(smA) + (uint32_t)(ss * rt.slab_stage_bytes);
+        for (int kb = 0; kb < CT_KB; ++kb)
+          for (int bx = 0; bx < 2; ++bx)
+            tma_load_3d_2sm(dst + (uint32_t)(kb * rt.slab_kb_bytes + bx * rt.box_rows * TC_ROW_BYTES), &tmX, af, kb * 64, t0 + bx * rt.box_rows, b);
+      }
+      __syncwarp();
+    };
+    // the next tile's slab is requested once the ring has turned over inside the current tile (its stage is free by then)
+    const int pre = rt.n_w_stages < n_stages_tile - 1 ? rt.n_w_stages : n_stages_tile - 1;
+    int sw = 0;
+    uint32_t pw = 0;
+    if (n_my > 0) load_slab(0);
+    for (int i = 0; i < n_my; ++i) {
+      for (int st = 0; st < n_stages_tile; ++st) {
+        if (st == pre && i + 1 < n_my) load_slab(i + 1);
+        mbar_wait(BAR(iWE + sw), pw ^ 1);
+        if (elect_one()) {
+          if (crank == 0) mbar_expect_tx(BAR(iWF + sw), (uint32_t)(2 * CT_W_STAGE_BYTES));
+          const uint32_t wf = mapa_shared(BAR(iWF + sw), 0);
+          const uint32_t wdst = smem_u32(smW) + (uint32_t)(sw * CT_W_STAGE_BYTES);
+          for (int d = 0; d < 2; ++d) {
+            const int step = 2 * st + d, kb = step / rt.taps, tap = step - kb * rt.taps;
+            tma_load_2d_2sm(wdst + (uint32_t)(d * CT_W_STEP), &tmW, wf, kb * 64, tap * 128 + (int)crank * 64);
+          }
+        }
+        __syncwarp();
+        if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
+      }
+    }
+  } else if (warp == CT_WARP_MMA) {
+    // ===================== MMA issuer (even CTA of the pair) =====================
+    if (crank == 0) {
+      constexpr uint32_t fmt = (Op::kPrec == 3) ? 0u : 1u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)((2 * PW_ROWS) >> 4) << 24);
+      const uint32_t tap_step = (uint32_t)(rt.dil * TC_ROW_BYTES) >> 4;
+      constexpr uint32_t sub_step = (uint32_t)(PW_ROWS * TC_ROW_BYTES) >> 4;   // second sub-tile: 128 rows further down the slab
+      int sw = 0;
+      uint32_t pw = 0;
+      for (int i = 0; i < n_my; ++i) {
+        const int ss = i & 1;
+        const uint32_t par = ((uint32_t)i >> 1) & 1u;
+        mbar_wait(BAR(iAF + ss), par);
+        mbar_wait(BAR(iCE + ss), par ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(ss * 256);
+        const uint32_t a_stage = smem_u32(smA) + (uint32_t)(ss * rt.slab_stage_bytes);
+        uint32_t accum = 0;
+        for (int st = 0; st < n_stages_tile; ++st) {
+          mbar_wait(BAR(iWF + sw), pw);
+          tc_fence_after();
+          const uint32_t w_stage = smem_u32(smW) + (uint32_t)(sw * CT_W_STAGE_BYTES);
+          for (int d = 0; d < 2; ++d) {
+            const int step = 2 * st + d, kb = step / rt.taps, tap = step - kb * rt.taps;
+            const uint32_t a_lo = desc_lo(a_stage + (uint32_t)(kb * rt.slab_kb_bytes)) + (uint32_t)tap * tap_step;
+            const uint32_t w_lo = desc_lo(w_stage + (uint32_t)(d * CT_W_STEP));
+            if (elect_one()) {
+#pragma unroll
+              for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  tc_mma2<2>(tmem_d + (uint32_t)(sub * 128), desc64(a_lo + (uint32_t)sub * sub_step + 2 * k), desc64(w_lo + 2 * k), idesc, (k == 0) ? accum : 1u);
+              if (d == 1) tc_commit2_mc(BAR(iWE + sw), (uint16_t)3);
+            }
+            __syncwarp();
+            accum = 1;
+          }
+          if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
+        }
+        if (elect_one()) {
+          tc_commit2_mc(BAR(iCF + ss), (uint16_t)3);
+          tc_commit2_mc(BAR(iAE + ss), (uint16_t)3);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs): one row per thread, 64 channels (two 32-channel chunks) per warp
+    const int sub = warp >> 3, q = warp & 3, half = (warp >> 2) & 1;
+    const int r = sub * PW_ROWS + q * 32 + lane;
+    const float slope = p.slope, scale = p.scale;
+    constexpr int sum_mode = SM;
+    for (int i = 0; i < n_my; ++i) {
+      const int ri = 2 * (pt_begin + i) + (int)crank;
+      const bool tile_ok = ri < rt.total_tiles;
+      const int b = tile_ok ? ri / rt.t_tiles : 0;
+      const int t = (ri % rt.t_tiles) * CT_ROWS + r;
+      const bool valid = tile_ok && t < rt.L;
+      const size_t res_off = ((size_t)b * p.rows_res + (size_t)t) * (size_t)p.ld * 2 + (size_t)half * 128;
+      const int mrow = t + p.row_add;
+      const size_t map_off = ((size_t)b * p.rows_out + (size_t)mrow) * (size_t)p.ld * 2 + (size_t)half * 128;
+      uint32_t res[32];
+      if constexpr (MODE == EPI_RES) {
+        if (valid) {
+          const char* xin = reinterpret_cast<const char*>(p.xin) + res_off;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ldg256(xin + j * 32, res + 8 * j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) res[j] = 0u;
+        }
+      }
+      if constexpr (MODE == EPI_RES && SM >= 2) {
+        // the running ResBlock sum of this row: no registers to hold it across the accumulator wait (res[] already takes 32), so ask
+        // it into L2 now -- the loads after the wait then see an L2 hit instead of a DRAM access on a saturated memory system
+        if (valid) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.xs) + res_off));
+      }
+      const float* bias = s_bias;
+      if (!shared_bias) {
+        float* bw = s_bias + (i & 1) * 128;
+        if (threadIdx.x < 128) bw[threadIdx.x] = p.bias[(size_t)b * p.bias_bs + threadIdx.x];
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * CT_EPI_WARPS) : "memory");
+        bias = bw;
+      }
+      const uint32_t b_s = smem_u32(bias) + (uint32_t)half * 256u;
+      const int ss = i & 1;
+      mbar_wait(BAR(iCF + ss), ((uint32_t)i >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ss * 256 + sub * 128 + half * 64);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t xsr[16];
+        if constexpr (MODE == EPI_RES) {
+          if (sum_mode >= 2) {
+            if (valid) {
+              const char* xs = reinterpret_cast<const char*>(p.xs) + res_off + c * 64;
+              ldg256(xs, xsr);
+              ldg256(xs + 32, xsr + 8);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) xsr[j] = 0u;
+            }
+          }
+        }
+        float acc[32];
+        tmem_ld32(taddr + (uint32_t)(32 * c), acc);
+        tmem_ld_wait();
+        if (c == 1) {  // this warp's part of the accumulator slot is drained
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (crank != 0) mbar_arrive_remote(BAR(iCE + ss), 0u);   // the accumulator-free barriers live in the even CTA
+            else mbar_arrive(BAR(iCE + ss));
+          }
+        }
+        // 16 channels (one 256-bit store per stream) at a time: o1 = 2-byte stream output (x' / xs'), o2 = operand copy
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint32_t o1[8], o2[8];
+#pragma unroll
+          for (int kk = 0; kk < 16; kk += 4) {
+            const int k = 16 * g + kk;
+            float4 b4;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(b_s + (uint32_t)(32 * c + k) * 4u));
+            float x0, x1, x2, x3;   // operation order of conv_tc.cu's epi_act / epi_res: results are bit-identical to the generic kernel
+            if constexpr (MODE == EPI_RES) {
+              const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&res[16 * c + k / 2]));
+              const float2 r1 = __half22float2(*reinterpret_cast<const __half2*>(&res[16 * c + k / 2 + 1]));
+              x0 = r0.x; x1 = r0.y; x2 = r1.x; x3 = r1.y;
+              if (sum_mode >= 2) {
+                const float2 s0 = __half22float2(*reinterpret_cast<const __half2*>(&xsr[k / 2]));
+                const float2 s1 = __half22float2(*reinterpret_cast<const __half2*>(&xsr[k / 2 + 1]));
+                x0 += s0.x; x1 += s0.y; x2 += s1.x; x3 += s1.y;
+              }
+              x0 = x0 + acc[k] + b4.x; x1 = x1 + acc[k + 1] + b4.y; x2 = x2 + acc[k + 2] + b4.z; x3 = x3 + acc[k + 3] + b4.w;
+              o1[kk / 2] = pack_half2_sat(x0, x1);
+              o1[kk / 2 + 1] = pack_half2_sat(x2, x3);
+              if (sum_mode == 3) { x0 *= scale; x1 *= scale; x2 *= scale; x3 *= scale; }   // mean over the parallel ResBlocks (models.py:361)
+            } else {
+              x0 = acc[k] + b4.x; x1 = acc[k + 1] + b4.y; x2 = acc[k + 2] + b4.z; x3 = acc[k + 3] + b4.w;
+            }
+            o2[kk / 2] = pack_op2<Op>(fmaxf(x0, x0 * slope), fmaxf(x1, x1 * slope));
+            o2[kk / 2 + 1] = pack_op2<Op>(fmaxf(x2, x2 * slope), fmaxf(x3, x3 * slope));
+          }
+          if (valid) {
+            const size_t co = (size_t)(c * 64 + g * 32);
+            if constexpr (MODE == EPI_RES) {
+              if (sum_mode <= 2)   // 0: x' -> residual stream;  1: x' starts the running ResBlock sum;  2: xs + x' -> xs
+                stg256(reinterpret_cast<char*>(sum_mode == 0 ? p.xout : p.xs) + res_off + co, o1);
+            }
+            if (MODE == EPI_ACT || sum_mode == 0 || sum_mode == 3) {
+              stg256(reinterpret_cast<char*>(p.act[0]) + map_off + co, o2);
+              if (mrow == p.dup_src)   // ReflectionPad1d((1, 0)) in front of conv_post
+                stg256(reinterpret_cast<char*>(p.act[0]) + ((size_t)b * p.rows_out + (size_t)p.dup_dst) * (size_t)p.ld * 2 + (size_t)half * 128 + co, o2);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == CT_WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 bool pw_eligible(int prec, const ConvArgs& a, int flags) {
@@ -1248,6 +1533,123 @@ static cudaError_t launch_gt(int prec, const ConvArgs& a, const TcPlan& p, cudaS
   return gt_launch_one<OpBF16>(a, p, rt, st, pdl, false);
 }
 
+// ---- conv_tm_kernel: eligibility, plan, launch (plan->pw = 3)
+bool ct_eligible(int prec, const ConvArgs& a, int flags, int num_sms) {
+  const EpiParams& e = a.epi;
+  if (flags & (MBV_FLAG_NO_PW | MBV_FLAG_NO_CONV_TM)) return false;
+  if (prec != 2 || num_sms < 2 || a.gate) return false;
+  if (a.Cp_in != 128 || a.N_total != 128 || a.x_ld != 128 || a.n_phases != 1 || a.taps < 5 || a.L_in != a.L_out) return false;
+  if (e.bias == nullptr || e.mask != nullptr || e.ld != 128 || e.n_valid != 128 || e.row_mul != 1 || e.rows_res != a.L_out) return false;
+  const bool plain_rows = e.rows_out == a.L_out && e.row_add == 0 && e.dup_src < 0;
+  const bool one_act = e.n_act == 1 && e.act[0] != nullptr && e.act_add[0] == nullptr;
+  if (e.mode == EPI_ACT) {
+    if (!one_act || e.xout != nullptr || !plain_rows) return false;
+  } else if (e.mode == EPI_RES) {
+    if (e.res_half != 1 || e.xin == nullptr) return false;
+    if (e.sum_mode == 0) { if (e.xout == nullptr || !one_act || !plain_rows) return false; }
+    else if (e.sum_mode == 1 || e.sum_mode == 2) { if (e.xs == nullptr || e.n_act != 0 || e.xout != nullptr) return false; }
+    else if (e.sum_mode == 3) {
+      if (e.xs == nullptr || !one_act || e.xout != nullptr || e.row_add < 0 || e.rows_out < a.L_out + e.row_add) return false;
+      if (e.dup_src >= 0 && (e.dup_dst < 0 || e.dup_dst >= e.rows_out)) return false;
+    } else return false;
+  } else return false;
+  const int halo = (a.taps - 1) * a.dil;
+  const int box_rows = ((CT_ROWS + halo + 1) / 2 + 7) / 8 * 8;
+  if (box_rows > 256) return false;
+  const int slab = CT_SLAB_STAGES * CT_KB * 2 * box_rows * TC_ROW_BYTES;
+  return slab + 3 * CT_W_STAGE_BYTES + 2048 <= 224 * 1024;
+}
+
+const char* ct_make_plan(int prec, const ConvArgs& a, int num_sms, TcPlan* plan) {
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(tc_tensormap_encoder());
+  if (!enc) return "cuTensorMapEncodeTiled entry point unavailable";
+  const int halo = (a.taps - 1) * a.dil;
+  const int box_rows = ((CT_ROWS + halo + 1) / 2 + 7) / 8 * 8;
+  plan->pw = 3;
+  plan->pw_kblocks = CT_KB;
+  plan->box_rows = box_rows;
+  plan->pw_tiles = (a.L_out + CT_ROWS - 1) / CT_ROWS;                  // 256-row tiles per utterance
+  plan->pw_R = a.B * plan->pw_tiles;                                    // tiles in total
+  plan->pw_w_bytes = 2 * box_rows * TC_ROW_BYTES;                       // one k-block of a slab (two boxes)
+  plan->pw_a_stage_bytes = CT_KB * plan->pw_w_bytes;
+  plan->pw_a_off = CT_SLAB_STAGES * plan->pw_a_stage_bytes;             // weight ring starts here
+  int stages = (224 * 1024 - plan->pw_a_off - 2048) / CT_W_STAGE_BYTES;
+  if (stages > 6) stages = 6;
+  if (stages < 3) return "conv (time on lane): not enough shared memory for the weight ring";
+  plan->pw_a_stages = stages;
+  plan->pw_bias_off = plan->pw_a_off + stages * CT_W_STAGE_BYTES;
+  plan->pw_bar_off = plan->pw_bias_off + 2 * 128 * 4;
+  plan->smem_bytes = 1024 + plan->pw_bar_off + (2 * CT_SLAB_STAGES + 2 * stages + 4) * 8 + 16;
+  if (plan->smem_bytes < 120 * 1024) plan->smem_bytes = 120 * 1024;    // one CTA per SM: each CTA owns all 512 TMEM columns
+  const int n_pair_tiles = (plan->pw_R + 1) / 2;
+  const int pairs = n_pair_tiles < num_sms / 2 ? n_pair_tiles : num_sms / 2;
+  plan->grid = 2 * (pairs < 1 ? 1 : pairs);
+  plan->n_time = CT_ROWS;
+  plan->cluster = 2;
+  const CUtensorMapDataType dt = prec == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)a.Cp_in, (cuuint64_t)a.L_in, (cuuint64_t)a.B};
+    cuuint64_t strides[2] = {(cuuint64_t)a.x_ld * 2, (cuuint64_t)a.L_in * a.x_ld * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&plan->tmA, dt, 3, const_cast<void*>(a.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return "cuTensorMapEncodeTiled failed for the time-on-lane conv activation map";
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)a.Cp_in, (cuuint64_t)a.taps * a.N_total};
+    cuuint64_t strides[1] = {(cuuint64_t)a.Cp_in * 2};
+    cuuint32_t box[2] = {64, 64};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&plan->tmB, dt, 2, const_cast<void*>(a.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return "cuTensorMapEncodeTiled failed for the time-on-lane conv weight map";
+  }
+  plan->tmR = plan->tmA; plan->tmS = plan->tmA; plan->tmBh = plan->tmB;  // unused
+  return nullptr;
+}
+
+template <typename Op, int MODE, int SM>
+static cudaError_t ct_launch_one(const ConvArgs& a, const TcPlan& p, const CtRt& rt, cudaStream_t st, int pdl, bool set_attr) {
+  auto k = conv_tm_kernel<Op, MODE, SM>;
+  if (set_attr) return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.grid);
+  cfg.blockDim = dim3(CT_THREADS);
+  cfg.dynamicSmemBytes = p.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  return cudaLaunchKernelEx(&cfg, k, p.tmA, p.tmB, a.epi, rt);
+}
+
+static cudaError_t launch_ct(int prec, const ConvArgs& a, const TcPlan& p, cudaStream_t st, int pdl) {
+  CtRt rt;
+  rt.B = a.B; rt.L = a.L_out; rt.t_tiles = p.pw_tiles; rt.total_tiles = p.pw_R; rt.n_pair_tiles = (p.pw_R + 1) / 2;
+  rt.taps = a.taps; rt.dil = a.dil; rt.shift0 = a.shift0[0]; rt.box_rows = p.box_rows;
+  rt.slab_kb_bytes = p.pw_w_bytes; rt.slab_stage_bytes = p.pw_a_stage_bytes; rt.n_w_stages = p.pw_a_stages;
+  rt.w_off = p.pw_a_off; rt.bias_off = p.pw_bias_off; rt.bar_off = p.pw_bar_off;
+  if (prec != 2) return cudaErrorInvalidValue;
+  if (a.epi.mode == EPI_ACT) return ct_launch_one<OpBF16, EPI_ACT, 0>(a, p, rt, st, pdl, false);
+  switch (a.epi.sum_mode) {
+    case 0: return ct_launch_one<OpBF16, EPI_RES, 0>(a, p, rt, st, pdl, false);
+    case 1: return ct_launch_one<OpBF16, EPI_RES, 1>(a, p, rt, st, pdl, false);
+    case 2: return ct_launch_one<OpBF16, EPI_RES, 2>(a, p, rt, st, pdl, false);
+    case 3: return ct_launch_one<OpBF16, EPI_RES, 3>(a, p, rt, st, pdl, false);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 template <typename Op, int MODE, int RH>
 static cudaError_t pw_launch_one(const ConvArgs& a, const TcPlan& p, const PwRt& rt, cudaStream_t st, int pdl, bool set_attr) {
   auto k = pw_tc_kernel<Op, MODE, RH>;
@@ -1296,11 +1698,18 @@ cudaError_t pw_set_attributes() {
   cudaError_t e = gt_launch_one<OpBF16>(a, p, g, nullptr, 0, true);
   if (e == cudaSuccess) e = gt_launch_one<OpF16>(a, p, g, nullptr, 0, true);
   if (e == cudaSuccess) { TcPairPlan pp{}; PtRt pr{}; e = ptm_launch_one<OpBF16>(a, pp, pr, nullptr, 0, true); }
+  CtRt cr{};
+  if (e == cudaSuccess) e = ct_launch_one<OpBF16, EPI_ACT, 0>(a, p, cr, nullptr, 0, true);
+  if (e == cudaSuccess) e = ct_launch_one<OpBF16, EPI_RES, 0>(a, p, cr, nullptr, 0, true);
+  if (e == cudaSuccess) e = ct_launch_one<OpBF16, EPI_RES, 1>(a, p, cr, nullptr, 0, true);
+  if (e == cudaSuccess) e = ct_launch_one<OpBF16, EPI_RES, 2>(a, p, cr, nullptr, 0, true);
+  if (e == cudaSuccess) e = ct_launch_one<OpBF16, EPI_RES, 3>(a, p, cr, nullptr, 0, true);
   return e;
 }
 
 cudaError_t launch_pw(int prec, const ConvArgs& a, const TcPlan& p, cudaStream_t st, int pdl) {
   if (p.pw == 2) return launch_gt(prec, a, p, st, pdl);
+  if (p.pw == 3) return launch_ct(prec, a, p, st, pdl);
   PwRt rt;
   rt.R = p.pw_R; rt.kblocks = p.pw_kblocks; rt.N = p.pw_N; rt.n_tiles = p.pw_tiles;
   rt.n_a_stages = p.pw_a_stages; rt.w_bytes = p.pw_w_bytes;

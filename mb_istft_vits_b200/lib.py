@@ -28,6 +28,7 @@ FLAG_NO_CTA_PAIRS = 256
 FLAG_NO_PW = 512
 FLAG_NO_PAIR_SPLIT = 1024
 FLAG_NO_PAIR_TM = 2048
+FLAG_NO_CONV_TM = 4096
 
 ERRORS = {0: "MBV_OK", -1: "MBV_ERR_INVALID", -2: "MBV_ERR_UNSUPPORTED", -3: "MBV_ERR_WEIGHTS",
           -4: "MBV_ERR_WORKSPACE", -5: "MBV_ERR_CUDA"}
