@@ -401,13 +401,46 @@ gate_tm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (warp != PW_WARP_TMA) {   // (the producer requests the first weight stages first, see below)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
 
   if (warp == PW_WARP_TMA) {
     // ===================== TMA producer (both CTAs): own slab, own half of every weight tile =====================
     int ss = 0, sw = 0;
     uint32_t ps = 0, pw = 0;
+    // one ring stage = one (k-block, tap) step of an N = 256 unit (16 KB per CTA) or TWO steps of an N = 128 unit (2 x 8 KB):
+    // either way a stage lasts ~512 tensor-core cycles, so the ring covers the same TMA round trip
+    const int n_steps = rt.kblocks * rt.taps;
+    auto load_w = [&](const Unit& u, int i) {
+      const int half_rows = u.wide ? 128 : 64;   // N = 256: packed tiles j (even CTA) and j+1 (odd CTA); N = 128: halves of tile j
+      const int row0 = 128 * u.j + (int)crank * half_rows;
+      const int per_stage = u.wide ? 1 : rt.narrow_steps;
+      const int n_here = min(per_stage, n_steps - i);
+      mbar_wait(BAR(iWE + sw), pw ^ 1);
+      if (elect_one()) {
+        if (crank == 0) mbar_expect_tx(BAR(iWF + sw), (uint32_t)(2 * n_here * half_rows * TC_ROW_BYTES));
+        const uint32_t wf = mapa_shared(BAR(iWF + sw), 0);
+        const uint32_t wdst = smem_u32(smW) + (uint32_t)(sw * GT_W_STAGE_BYTES);
+        for (int d = 0; d < n_here; ++d) {
+          const int kb = (i + d) / rt.taps, tap = (i + d) - kb * rt.taps;
+          tma_load_2d_2sm(wdst + (uint32_t)(d * half_rows * TC_ROW_BYTES), u.wide ? &tmW : &tmWh, wf, kb * 64, tap * rt.N_total + row0);
+        }
+      }
+      __syncwarp();
+      if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
+    };
+    // weights are constants of the model: the first turn of the ring is requested BEFORE the programmatic-dependency wait
+    int w_skip = 0;
+    for (int e = e_begin; e < e_end && w_skip < rt.n_w_stages;) {
+      const Unit u = unit_at(e);
+      const int per_stage = u.wide ? 1 : rt.narrow_steps;
+      for (int i = 0; i < n_steps && w_skip < rt.n_w_stages; i += per_stage) { load_w(u, i); ++w_skip; }
+      e = u.e_next;
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (int e = e_begin; e < e_end;) {
       const Unit u = unit_at(e);
       if (u.first) {
@@ -424,25 +457,10 @@ gate_tm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         __syncwarp();
         if (++ss == GT_SLAB_STAGES) { ss = 0; ps ^= 1; }
       }
-      const int half_rows = u.wide ? 128 : 64;   // N = 256: packed tiles j (even CTA) and j+1 (odd CTA); N = 128: halves of tile j
-      const int row0 = 128 * u.j + (int)crank * half_rows;
-      // one ring stage = one (k-block, tap) step of an N = 256 unit (16 KB per CTA) or TWO steps of an N = 128 unit (2 x 8 KB):
-      // either way a stage lasts ~512 tensor-core cycles, so the ring covers the same TMA round trip
-      const int n_steps = rt.kblocks * rt.taps, per_stage = u.wide ? 1 : rt.narrow_steps;
+      const int per_stage = u.wide ? 1 : rt.narrow_steps;
       for (int i = 0; i < n_steps; i += per_stage) {
-        const int n_here = min(per_stage, n_steps - i);
-        mbar_wait(BAR(iWE + sw), pw ^ 1);
-        if (elect_one()) {
-          if (crank == 0) mbar_expect_tx(BAR(iWF + sw), (uint32_t)(2 * n_here * half_rows * TC_ROW_BYTES));
-          const uint32_t wf = mapa_shared(BAR(iWF + sw), 0);
-          const uint32_t wdst = smem_u32(smW) + (uint32_t)(sw * GT_W_STAGE_BYTES);
-          for (int d = 0; d < n_here; ++d) {
-            const int kb = (i + d) / rt.taps, tap = (i + d) - kb * rt.taps;
-            tma_load_2d_2sm(wdst + (uint32_t)(d * half_rows * TC_ROW_BYTES), u.wide ? &tmW : &tmWh, wf, kb * 64, tap * rt.N_total + row0);
-          }
-        }
-        __syncwarp();
-        if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
+        if (w_skip > 0) { --w_skip; continue; }   // requested before the wait
+        load_w(u, i);
       }
       e = u.e_next;
     }
@@ -1005,8 +1023,10 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (warp != CT_WARP_TMA) {   // (the producer requests the first weight stages first, see below)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
 
   if (warp == CT_WARP_TMA) {
     // ===================== TMA producer (both CTAs): own slab, own half of every weight tile =====================
@@ -1026,28 +1046,39 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       __syncwarp();
     };
-    // the next tile's slab is requested once the ring has turned over inside the current tile (its stage is free by then)
-    const int pre = rt.n_w_stages < n_stages_tile - 1 ? rt.n_w_stages : n_stages_tile - 1;
     int sw = 0;
     uint32_t pw = 0;
-    if (n_my > 0) load_slab(0);
-    for (int i = 0; i < n_my; ++i) {
-      for (int st = 0; st < n_stages_tile; ++st) {
-        if (st == pre && i + 1 < n_my) load_slab(i + 1);
-        mbar_wait(BAR(iWE + sw), pw ^ 1);
-        if (elect_one()) {
-          if (crank == 0) mbar_expect_tx(BAR(iWF + sw), (uint32_t)(2 * CT_W_STAGE_BYTES));
-          const uint32_t wf = mapa_shared(BAR(iWF + sw), 0);
-          const uint32_t wdst = smem_u32(smW) + (uint32_t)(sw * CT_W_STAGE_BYTES);
-          for (int d = 0; d < 2; ++d) {
-            const int step = 2 * st + d, kb = step / rt.taps, tap = step - kb * rt.taps;
-            tma_load_2d_2sm(wdst + (uint32_t)(d * CT_W_STEP), &tmW, wf, kb * 64, tap * 128 + (int)crank * 64);
-          }
+    auto load_w = [&](int g) {   // weight stage g of this CTA's flat (tile, stage) sequence
+      const int st = g % n_stages_tile;
+      mbar_wait(BAR(iWE + sw), pw ^ 1);
+      if (elect_one()) {
+        if (crank == 0) mbar_expect_tx(BAR(iWF + sw), (uint32_t)(2 * CT_W_STAGE_BYTES));
+        const uint32_t wf = mapa_shared(BAR(iWF + sw), 0);
+        const uint32_t wdst = smem_u32(smW) + (uint32_t)(sw * CT_W_STAGE_BYTES);
+        for (int d = 0; d < 2; ++d) {
+          const int step = 2 * st + d, kb = step / rt.taps, tap = step - kb * rt.taps;
+          tma_load_2d_2sm(wdst + (uint32_t)(d * CT_W_STEP), &tmW, wf, kb * 64, tap * 128 + (int)crank * 64);
         }
-        __syncwarp();
-        if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
       }
+      __syncwarp();
+      if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
+    };
+    // weights are constants of the model: the first turn of the ring is requested BEFORE the programmatic-dependency wait
+    const int total_g = n_my * n_stages_tile;
+    const int pf = rt.n_w_stages < total_g ? rt.n_w_stages : total_g;
+    int g = 0;
+    for (; g < pf; ++g) load_w(g);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // the next tile's slab is requested once the ring has turned over inside the current tile (its stage is free by then)
+    const int pre = rt.n_w_stages < n_stages_tile - 1 ? rt.n_w_stages : n_stages_tile - 1;
+    int next_slab = 0;
+    if (n_my > 0) load_slab(next_slab++);
+    for (; g < total_g; ++g) {
+      while (next_slab < n_my && g >= (next_slab - 1) * n_stages_tile + pre) load_slab(next_slab++);
+      load_w(g);
     }
+    while (next_slab < n_my) load_slab(next_slab++);
   } else if (warp == CT_WARP_MMA) {
     // ===================== MMA issuer (even CTA of the pair) =====================
     if (crank == 0) {
@@ -1576,7 +1607,7 @@ const char* ct_make_plan(int prec, const ConvArgs& a, int num_sms, TcPlan* plan)
   plan->pw_w_bytes = 2 * box_rows * TC_ROW_BYTES;                       // one k-block of a slab (two boxes)
   plan->pw_a_stage_bytes = CT_KB * plan->pw_w_bytes;
   plan->pw_a_off = CT_SLAB_STAGES * plan->pw_a_stage_bytes;             // weight ring starts here
-  int stages = (224 * 1024 - plan->pw_a_off - 2048) / CT_W_STAGE_BYTES;
+  int stages = (227 * 1024 - 1024 - plan->pw_a_off - 2 * 128 * 4 - 256) / CT_W_STAGE_BYTES;   // all of the 227 KB: the k = 11, dilation 5 slabs leave room for 4
   if (stages > 6) stages = 6;
   if (stages < 3) return "conv (time on lane): not enough shared memory for the weight ring";
   plan->pw_a_stages = stages;
