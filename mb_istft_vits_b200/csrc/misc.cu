@@ -11,38 +11,45 @@ template <typename Op>
 __global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict__ src, const float* __restrict__ mask,
                                                          typename Op::T* __restrict__ dst_op, float* __restrict__ dst_f32,
                                                          int C, int T, int Cp) {
-  __shared__ float tile[32][33];
+  // 64 channels x 32 time steps per block: reads are 128-byte rows along T, writes are 64 consecutive channels of a time step
+  // (two per thread: 128 bytes of 16-bit operands / 256 bytes of fp32 per warp instruction)
+  __shared__ __align__(8) float tile[32][66];
   const int b = blockIdx.z;
-  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  for (int i = ty; i < 32; i += 8) {
-    const int c = c0 + i, t = t0 + tx;
+  const int t_in = t0 + tx;
+  const float m = (mask && t_in < T) ? mask[(size_t)b * T + t_in] : 1.f;
+#pragma unroll
+  for (int i = ty; i < 64; i += 8) {
+    const int c = c0 + i;
     float v = 0.f;
-    if (c < C && t < T) {
-      v = src[((size_t)b * C + c) * T + t];
-      if (mask) v *= mask[(size_t)b * T + t];
+    if (c < C && t_in < T) {
+      v = src[((size_t)b * C + c) * T + t_in];
+      if (mask) v *= m;
     }
-    tile[i][tx] = v;
+    tile[tx][i] = v;
   }
   __syncthreads();
+  const int c = c0 + 2 * tx;   // Cp is a multiple of 64
+#pragma unroll
   for (int i = ty; i < 32; i += 8) {
-    const int t = t0 + i, c = c0 + tx;
+    const int t = t0 + i;
     if (t < T && c < Cp) {
-      const float v = tile[tx][i];
+      const float2 v = *reinterpret_cast<const float2*>(&tile[i][2 * tx]);
       const size_t o = ((size_t)b * T + t) * Cp + c;
       if (dst_op) {
-        if constexpr (Op::kPrec == 3) dst_op[o] = to_half_sat(v);
-        else if constexpr (Op::kPrec == 2) dst_op[o] = __float2bfloat16_rn(v);
-        else dst_op[o] = op_round<Op>(v);
+        if constexpr (Op::kPrec == 3) *reinterpret_cast<__half2*>(dst_op + o) = __halves2half2(to_half_sat(v.x), to_half_sat(v.y));
+        else if constexpr (Op::kPrec == 2) *reinterpret_cast<__nv_bfloat162*>(dst_op + o) = __floats2bfloat162_rn(v.x, v.y);
+        else *reinterpret_cast<float2*>(dst_op + o) = make_float2(op_round<Op>(v.x), op_round<Op>(v.y));
       }
-      if (dst_f32) dst_f32[o] = v;
+      if (dst_f32) *reinterpret_cast<float2*>(dst_f32 + o) = v;
     }
   }
 }
 
 cudaError_t launch_pack_input(int prec, const float* src, const float* mask, void* dst_op, float* dst_f32, int B, int C,
                               int T, int Cp, cudaStream_t st) {
-  dim3 grid((T + 31) / 32, (Cp + 31) / 32, B);
+  dim3 grid((T + 31) / 32, (Cp + 63) / 64, B);
   if (prec == 3)
     pack_input_kernel<OpF16><<<grid, 256, 0, st>>>(src, mask, (__half*)dst_op, dst_f32, C, T, Cp);
   else if (prec == 2)

@@ -623,6 +623,7 @@ struct PtRt {
   float slope_h;
   const float* bias_h;
   long long* dbg;   // MBV_TIMELINE=10: clock stamps of pair 0 (both CTAs) [cta][tile < 16][16] (debug only)
+  int res_pf;       // 1: L2 prefetch of the next tile's residual rows (MBV_NO_RES_PF=1 clears it: A/B only)
 };
 constexpr int PT_KB = 2;                                  // 128 channels = two 64-channel k-blocks
 constexpr int PT_W_TILE = 64 * TC_ROW_BYTES;              // one CTA's half (64 rows) of a weight tile
@@ -887,6 +888,15 @@ pair_tm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) res[j] = 0u;
       }
+      {  // the next tile's residual row: asked into L2 a tile ahead (more bytes in flight: 191 -> 179 us per pair)
+        const int rn = ri + 2;
+        if (rt.res_pf && i + 1 < n_my && rn < rt.total_tiles && r < rt.out_rows) {
+          const int tn = (rn % rt.t_tiles) * rt.out_rows + r;
+          if (tn < rt.L)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.xin) +
+                                                          ((size_t)(rn / rt.t_tiles) * rt.L + (size_t)tn) * (size_t)p.ld * 2 + (size_t)half * 128));
+        }
+      }
       const float* b2 = s_b2;
       if (!shared_bias) {
         float* b2w = s_b2 + (i & 1) * 128;
@@ -975,6 +985,7 @@ struct CtRt {
   int taps, dil, shift0, box_rows;
   int slab_kb_bytes, slab_stage_bytes, n_w_stages;
   int w_off, bias_off, bar_off;
+  int res_pf;     // 1: L2 prefetch of the next tile's residual rows (MBV_NO_RES_PF=1 clears it: A/B only)
 };
 constexpr int CT_ROWS = 256;                               // rows per CTA tile: two 128-row accumulators
 constexpr int CT_KB = 2;                                   // 128 input channels = two 64-channel k-blocks
@@ -1152,9 +1163,20 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
       }
       if constexpr (MODE == EPI_RES && SM >= 2) {
-        // the running ResBlock sum of this row: no registers to hold it across the accumulator wait (res[] already takes 32), so ask
-        // it into L2 now -- the loads after the wait then see an L2 hit instead of a DRAM access on a saturated memory system
-        if (valid) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.xs) + res_off));
+        // The running ResBlock sum has no registers to wait in (res[] already takes 32): it is loaded after the accumulator wait,
+        // chunk by chunk -- from L2, into which it is asked here so that those loads do not see a DRAM access on a saturated memory
+        // system.  SM 2 (the k = 7 ResBlock's last conv, epilogue-bound): a tile AHEAD, together with the residual row (236 -> 193 us);
+        // SM 3 (k = 11, MMA-bound) and the plain residual adds measured no gain from the tile-ahead requests.
+        if ((SM == 3 || i == 0 || !rt.res_pf) && valid) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.xs) + res_off));
+        const int rn = ri + 2;
+        if (SM == 2 && rt.res_pf && i + 1 < n_my && rn < rt.total_tiles) {
+          const int tn = (rn % rt.t_tiles) * CT_ROWS + r;
+          if (tn < rt.L) {
+            const size_t off_n = ((size_t)(rn / rt.t_tiles) * p.rows_res + (size_t)tn) * (size_t)p.ld * 2 + (size_t)half * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.xin) + off_n));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.xs) + off_n));
+          }
+        }
       }
       const float* bias = s_bias;
       if (!shared_bias) {
@@ -1436,6 +1458,8 @@ cudaError_t launch_ptm(int prec, const ConvArgs& a, const TcPairPlan& p, cudaStr
   rt.slab_kb_bytes = p.tm_slab_kb_bytes; rt.slab_stage_bytes = p.tm_slab_stage_bytes; rt.h_kb_bytes = p.tm_h_kb_bytes;
   rt.slab_off = p.tm_slab_off; rt.h_off = p.h_off; rt.bias_off = p.tm_bias_off; rt.bar_off = p.bar_off;
   rt.slope_h = a.slope_h; rt.bias_h = a.bias_h;
+  static const int no_res_pf = getenv("MBV_NO_RES_PF") ? atoi(getenv("MBV_NO_RES_PF")) : 0;  // A/B measurements only
+  rt.res_pf = no_res_pf ? 0 : 1;
   if (prec != 2) return cudaErrorInvalidValue;
   static long long* dbg = nullptr;
   static int dbg_on = -1;
@@ -1670,6 +1694,8 @@ static cudaError_t launch_ct(int prec, const ConvArgs& a, const TcPlan& p, cudaS
   rt.taps = a.taps; rt.dil = a.dil; rt.shift0 = a.shift0[0]; rt.box_rows = p.box_rows;
   rt.slab_kb_bytes = p.pw_w_bytes; rt.slab_stage_bytes = p.pw_a_stage_bytes; rt.n_w_stages = p.pw_a_stages;
   rt.w_off = p.pw_a_off; rt.bias_off = p.pw_bias_off; rt.bar_off = p.pw_bar_off;
+  static const int no_res_pf = getenv("MBV_NO_RES_PF") ? atoi(getenv("MBV_NO_RES_PF")) : 0;  // A/B measurements only
+  rt.res_pf = no_res_pf ? 0 : 1;
   if (prec != 2) return cudaErrorInvalidValue;
   if (a.epi.mode == EPI_ACT) return ct_launch_one<OpBF16, EPI_ACT, 0>(a, p, rt, st, pdl, false);
   switch (a.epi.sum_mode) {
