@@ -1108,13 +1108,13 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         const uint32_t tmem_d = tmem_base + (uint32_t)(ss * 256);
         const uint32_t a_stage = smem_u32(smA) + (uint32_t)(ss * rt.slab_stage_bytes);
         uint32_t accum = 0;
+        uint32_t a_kb = desc_lo(a_stage), a_lo = a_kb;   // (k-block, tap) walked incrementally: no division on the issue path
+        int tap = 0;
         for (int st = 0; st < n_stages_tile; ++st) {
           mbar_wait(BAR(iWF + sw), pw);
           tc_fence_after();
           const uint32_t w_stage = smem_u32(smW) + (uint32_t)(sw * CT_W_STAGE_BYTES);
           for (int d = 0; d < 2; ++d) {
-            const int step = 2 * st + d, kb = step / rt.taps, tap = step - kb * rt.taps;
-            const uint32_t a_lo = desc_lo(a_stage + (uint32_t)(kb * rt.slab_kb_bytes)) + (uint32_t)tap * tap_step;
             const uint32_t w_lo = desc_lo(w_stage + (uint32_t)(d * CT_W_STEP));
             if (elect_one()) {
 #pragma unroll
@@ -1126,6 +1126,8 @@ conv_tm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             }
             __syncwarp();
             accum = 1;
+            a_lo += tap_step;
+            if (++tap == rt.taps) { tap = 0; a_kb += (uint32_t)rt.slab_kb_bytes >> 4; a_lo = a_kb; }
           }
           if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
         }

@@ -35,7 +35,7 @@ def main(src, dst):
             best = run
     step = best
     step_tail = step[-1]
-    conv = [d[i] for i in step if any(k in d[i]["name"] for k in ("conv_tc", "conv_pair", "pw_tc", "gate_tm", "pair_tm"))]
+    conv = [d[i] for i in step if any(k in d[i]["name"] for k in ("conv_tc", "conv_pair", "pw_tc", "gate_tm", "pair_tm", "conv_tm"))]
     tail = d[step_tail]
     by = lambda x: x.get("dram__bytes_read.sum", 0.0) + x.get("dram__bytes_write.sum", 0.0)
     out = {
