@@ -346,12 +346,14 @@ struct GtRt {
   int narrow_steps;   // (k-block, tap) steps of an N = 128 unit per weight-ring stage (1 or 2)
 };
 constexpr int GT_SLAB_STAGES = 2;
+constexpr int GT_WARP_SLAB = PW_EPI_WARPS + 2;   // slab producer (warps 8 / 9: weight producer / MMA issuer)
+constexpr int GT_THREADS = PW_THREADS + 32;
 constexpr int GT_W_STAGE_BYTES = 128 * TC_ROW_BYTES;  // one CTA's half of an N = 256 weight tile
 
 __device__ __forceinline__ float gt_tanh(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 template <typename Op>
-__global__ void __launch_bounds__(PW_THREADS, 1)
+__global__ void __launch_bounds__(GT_THREADS, 1)
 gate_tm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWh,
                const EpiParams p, const GtRt rt) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -401,46 +403,16 @@ gate_tm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  if (warp != PW_WARP_TMA) {   // (the producer requests the first weight stages first, see below)
+  if (warp != PW_WARP_TMA) {   // (the weight producer does not wait: weights are constants of the model)
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   }
 
-  if (warp == PW_WARP_TMA) {
-    // ===================== TMA producer (both CTAs): own slab, own half of every weight tile =====================
-    int ss = 0, sw = 0;
-    uint32_t ps = 0, pw = 0;
-    // one ring stage = one (k-block, tap) step of an N = 256 unit (16 KB per CTA) or TWO steps of an N = 128 unit (2 x 8 KB):
-    // either way a stage lasts ~512 tensor-core cycles, so the ring covers the same TMA round trip
-    const int n_steps = rt.kblocks * rt.taps;
-    auto load_w = [&](const Unit& u, int i) {
-      const int half_rows = u.wide ? 128 : 64;   // N = 256: packed tiles j (even CTA) and j+1 (odd CTA); N = 128: halves of tile j
-      const int row0 = 128 * u.j + (int)crank * half_rows;
-      const int per_stage = u.wide ? 1 : rt.narrow_steps;
-      const int n_here = min(per_stage, n_steps - i);
-      mbar_wait(BAR(iWE + sw), pw ^ 1);
-      if (elect_one()) {
-        if (crank == 0) mbar_expect_tx(BAR(iWF + sw), (uint32_t)(2 * n_here * half_rows * TC_ROW_BYTES));
-        const uint32_t wf = mapa_shared(BAR(iWF + sw), 0);
-        const uint32_t wdst = smem_u32(smW) + (uint32_t)(sw * GT_W_STAGE_BYTES);
-        for (int d = 0; d < n_here; ++d) {
-          const int kb = (i + d) / rt.taps, tap = (i + d) - kb * rt.taps;
-          tma_load_2d_2sm(wdst + (uint32_t)(d * half_rows * TC_ROW_BYTES), u.wide ? &tmW : &tmWh, wf, kb * 64, tap * rt.N_total + row0);
-        }
-      }
-      __syncwarp();
-      if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
-    };
-    // weights are constants of the model: the first turn of the ring is requested BEFORE the programmatic-dependency wait
-    int w_skip = 0;
-    for (int e = e_begin; e < e_end && w_skip < rt.n_w_stages;) {
-      const Unit u = unit_at(e);
-      const int per_stage = u.wide ? 1 : rt.narrow_steps;
-      for (int i = 0; i < n_steps && w_skip < rt.n_w_stages; i += per_stage) { load_w(u, i); ++w_skip; }
-      e = u.e_next;
-    }
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (warp == GT_WARP_SLAB) {
+    // ===================== slab producer (both CTAs): the slab of the next pair tile is requested as soon as its stage is free,
+    // a whole tile ahead of the weight producer's position
+    int ss = 0;
+    uint32_t ps = 0;
     for (int e = e_begin; e < e_end;) {
       const Unit u = unit_at(e);
       if (u.first) {
@@ -457,10 +429,34 @@ gate_tm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         __syncwarp();
         if (++ss == GT_SLAB_STAGES) { ss = 0; ps ^= 1; }
       }
+      e = u.e_next;
+    }
+  } else if (warp == PW_WARP_TMA) {
+    // ===================== weight producer (both CTAs): own half of every weight tile =====================
+    int sw = 0;
+    uint32_t pw = 0;
+    // one ring stage = one (k-block, tap) step of an N = 256 unit (16 KB per CTA) or TWO steps of an N = 128 unit (2 x 8 KB):
+    // either way a stage lasts ~512 tensor-core cycles, so the ring covers the same TMA round trip
+    const int n_steps = rt.kblocks * rt.taps;
+    for (int e = e_begin; e < e_end;) {
+      const Unit u = unit_at(e);
+      const int half_rows = u.wide ? 128 : 64;   // N = 256: packed tiles j (even CTA) and j+1 (odd CTA); N = 128: halves of tile j
+      const int row0 = 128 * u.j + (int)crank * half_rows;
       const int per_stage = u.wide ? 1 : rt.narrow_steps;
       for (int i = 0; i < n_steps; i += per_stage) {
-        if (w_skip > 0) { --w_skip; continue; }   // requested before the wait
-        load_w(u, i);
+        const int n_here = min(per_stage, n_steps - i);
+        mbar_wait(BAR(iWE + sw), pw ^ 1);
+        if (elect_one()) {
+          if (crank == 0) mbar_expect_tx(BAR(iWF + sw), (uint32_t)(2 * n_here * half_rows * TC_ROW_BYTES));
+          const uint32_t wf = mapa_shared(BAR(iWF + sw), 0);
+          const uint32_t wdst = smem_u32(smW) + (uint32_t)(sw * GT_W_STAGE_BYTES);
+          for (int d = 0; d < n_here; ++d) {
+            const int kb = (i + d) / rt.taps, tap = (i + d) - kb * rt.taps;
+            tma_load_2d_2sm(wdst + (uint32_t)(d * half_rows * TC_ROW_BYTES), u.wide ? &tmW : &tmWh, wf, kb * 64, tap * rt.N_total + row0);
+          }
+        }
+        __syncwarp();
+        if (++sw == rt.n_w_stages) { sw = 0; pw ^= 1; }
       }
       e = u.e_next;
     }
@@ -1563,7 +1559,7 @@ static cudaError_t gt_launch_one(const ConvArgs& a, const TcPlan& p, const GtRt&
   if (set_attr) return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p.grid);
-  cfg.blockDim = dim3(PW_THREADS);
+  cfg.blockDim = dim3(GT_THREADS);
   cfg.dynamicSmemBytes = p.smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
