@@ -305,6 +305,40 @@ def run_sharded_config(torch, dist, dev, rank, world, which, steps=3):
         dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
         out["padded_work_balance"] = float(work.item() / world / wmax.item())
+    if which == 5:
+        # the same utterances, dealt in snake order over the ranks and decoded per rank as <= 4 padded batches of similar
+        # length (sharding.decode_in_buckets) written into one flat buffer, which the gather sends as it lies
+        from mb_istft_vits_b200.sharding import deal_utterances, decode_in_buckets
+        idx_b = deal_utterances(lengths, world)[rank]
+        lens_b = [lengths[i] for i in idx_b]
+        zb, _, _ = synth.make_latents(cfg, len(idx_b), max(lens_b), seed=4000 + rank, lengths=torch.tensor(lens_b))
+        zb = zb.to(dev)
+        gb = None
+        if cfg["gin_channels"]:
+            sid = torch.tensor([i % cfg["n_speakers"] for i in idx_b])
+            gb = sd["emb_g.weight"][sid].unsqueeze(-1).to(dev).contiguous()
+        flat, offs, plan = decode_in_buckets(eng, zb, lens_b, g=gb)
+        ns_b = (torch.tensor(lens_b) * 256).to(dev)
+
+        def compute_b():
+            decode_in_buckets(eng, zb, lens_b, g=gb, out=flat, plan=plan)
+
+        def compute_gather_b():
+            compute_b()
+            state["out_b"] = gather_waveforms(flat, ns_b, idx_b, total, dst=0, offsets=offs)
+
+        ms_cb = _timed(torch, dist, dev, compute_b, steps)
+        bk = {"how": "sharding.deal_utterances + sharding.decode_in_buckets (<= 4 length buckets per rank, one flat output buffer)",
+              "this_rank": {"utterances": len(idx_b), "buckets": [[bb, TT] for _, TT, _, _, bb in plan[0]],
+                            "padded_frames": sum(bb * TT for _, TT, _, _, bb in plan[0]), "valid_frames": sum(lens_b)},
+              "ms_per_step_compute": ms_cb, "samples_per_s_compute": valid / (ms_cb * 1e-3)}
+        if dist is not None:
+            ms_gb = _timed(torch, dist, dev, compute_gather_b, steps)
+            bk.update({"ms_per_step_with_gather": ms_gb, "samples_per_s_with_gather": valid / (ms_gb * 1e-3), "gather_ms": ms_gb - ms_cb})
+            if rank == 0:
+                res = state["out_b"]
+                bk["gather_check"] = bool(len(res) == total and all(int(res[i].numel()) == lengths[i] * 256 for i in range(total)))
+        out["length_buckets"] = bk
     eng.close()
     del eng
     torch.cuda.empty_cache()

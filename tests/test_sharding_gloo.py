@@ -9,7 +9,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from mb_istft_vits_b200.sharding import balance_utterances, gather_waveforms, shard_batch
+from mb_istft_vits_b200.sharding import (balance_utterances, bucket_by_length, deal_utterances, decode_in_buckets,
+                                         gather_waveforms, shard_batch)
 
 
 def test_balance_is_a_partition_and_balances_padded_work():
@@ -20,6 +21,48 @@ def test_balance_is_a_partition_and_balances_padded_work():
         cost = [len(b) * max((lengths[i] for i in b), default=0) for b in bins]
         assert max(cost) <= 1.6 * (sum(cost) / w) + max(lengths)
     assert balance_utterances([5, 5, 5, 5], 2) == [[0, 2], [1, 3]]
+
+
+def test_deal_is_a_partition_with_equal_counts_and_similar_sums():
+    gen = torch.Generator().manual_seed(1234)
+    lengths = [int(v) for v in torch.randint(60, 3750, (64,), generator=gen)]
+    for w in (1, 2, 4, 8):
+        bins = deal_utterances(lengths, w)
+        assert sorted(i for b in bins for i in b) == list(range(64))
+        assert {len(b) for b in bins} == {64 // w}
+        sums = [sum(lengths[i] for i in b) for b in bins]
+        assert max(sums) - min(sums) <= max(lengths)
+        for b in bins:
+            assert [lengths[i] for i in b] == sorted((lengths[i] for i in b), reverse=True)
+    assert deal_utterances([9, 8, 7, 6, 5], 2) == [[0, 3, 4], [1, 2]]
+
+
+def test_length_buckets_partition_and_cut_the_padded_work():
+    gen = torch.Generator().manual_seed(7)
+    lengths = [int(v) for v in torch.randint(60, 3750, (64,), generator=gen)]
+
+    def cost(bk, overhead):
+        return sum(len(b) * max(lengths[i] for i in b) + overhead for b in bk)
+
+    one = cost([list(range(64))], 4000)
+    prev = one
+    for k in (1, 2, 3, 4, 6):
+        bk = bucket_by_length(lengths, k, 4000)
+        assert 1 <= len(bk) <= k
+        assert sorted(i for b in bk for i in b) == list(range(64))
+        flat = [lengths[i] for b in bk for i in b]
+        assert flat == sorted(flat, reverse=True)          # buckets are runs of the length-sorted list
+        assert cost(bk, 4000) <= prev                       # more buckets allowed never costs more
+        prev = cost(bk, 4000)
+    assert prev < 0.75 * one                                # uniform lengths: a third of the padded work goes away
+    assert bucket_by_length([], 4) == []
+    assert bucket_by_length([5], 4) == [[0]]
+    assert bucket_by_length([10, 10, 10, 10], 4) == [[0, 1, 2, 3]]      # equal lengths: one batch
+    assert len(bucket_by_length(lengths, 4, 10 ** 9)) == 1              # a prohibitive call overhead: one batch
+    # brute force over every split into two runs
+    srt = sorted(lengths, reverse=True)
+    best2 = min(min(i * srt[0] + (64 - i) * srt[i] + 8000 for i in range(1, 64)), 64 * srt[0] + 4000)
+    assert cost(bucket_by_length(lengths, 2, 4000), 4000) == best2
 
 
 def _free_port():
@@ -48,9 +91,29 @@ def _worker(rank, world, port, tmp):
     wav = orc.decode(sd, cfg, z_loc)[0] if len(idx) else torch.zeros((0, 1, 0))
     out = gather_waveforms(wav, len_loc * 256, idx, total=5, dst=0)
     out_ag = gather_waveforms(wav, len_loc * 256, idx, total=5, dst=0, mode="allgather")
+    # the same utterances dealt in snake order and decoded in length buckets into one flat buffer per rank
+    class _OracleEngine:   # stands in for Engine: what is under test is the bucketing / placement / gather plumbing
+        spf = 256
+
+        def reserve_workspace(self, b, T):
+            return 0
+
+        def flow_decode(self, zb, mask, g, want_z=False, out_wav=None):
+            out_wav.copy_(orc.decode(sd, cfg, zb)[0])
+
+    idx_b = deal_utterances([int(v) for v in lengths], world)[rank]
+    flat, offs, plan = decode_in_buckets(_OracleEngine(), z[idx_b], [int(lengths[i]) for i in idx_b], max_buckets=2, overhead=1)
+    flat2, _, _ = decode_in_buckets(_OracleEngine(), z[idx_b], [int(lengths[i]) for i in idx_b], out=torch.empty_like(flat), plan=plan)
+    assert torch.equal(flat, flat2) and len(plan[0]) == 2
+    out_bk = [gather_waveforms(flat, lengths[idx_b] * 256, idx_b, total=5, dst=0, offsets=offs, mode=m) for m in ("p2p", "allgather")]
     if rank == 0:
         full = orc.decode(sd, cfg, z)[0]
         ok = all(torch.equal(a, b) for a, b in zip(out, out_ag))  # the two transports deliver the same samples
+        for res in out_bk:
+            for i in range(5):
+                n = int(lengths[i]) * 256
+                m = max(0, n - 24 * 256)
+                ok &= res[i].shape[0] == n and bool(torch.allclose(res[i][:m], full[i, 0, :m], atol=1e-5))
         for i in range(5):
             n = int(lengths[i]) * 256
             # an utterance decoded inside a shorter padded batch equals the full-batch result away from the padded tail
@@ -110,3 +173,30 @@ def test_shard_decode_gather_two_gpus_nccl(tmp_path):
     port = _free_port()
     mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert torch.load(os.path.join(str(tmp_path), "ok_nccl.pt")) is True
+
+
+@pytest.mark.gpu
+def test_decode_in_length_buckets_matches_one_padded_batch():
+    """decode_in_buckets (several padded batches of similar length, written into one flat buffer) against ONE flow_decode of
+    the whole batch padded to its longest utterance -- the reference's way (models.py:717-737).  The flow masks every layer,
+    so z is identical; the decoder sees `z * mask`, so samples further than its receptive field (24 latent frames) from an
+    utterance's end are identical too."""
+    from mb_istft_vits_b200 import Engine, get_config, synth
+    cfg = get_config("ljs_mini_mb_istft_vits")
+    sd = synth.make_state_dict(cfg, seed=1)
+    lengths = [200, 61, 137, 190, 88, 33, 140, 75, 199]
+    lens = torch.tensor(lengths)
+    z_p, mask, _ = synth.make_latents(cfg, len(lengths), 200, seed=5, lengths=lens)
+    eng = Engine(cfg, sd, precision="fp32", device=0)
+    z_p, mask = z_p.cuda(), mask.cuda()
+    full = eng.flow_decode(z_p, mask, want_z=False)[1]
+    flat, offs, plan = decode_in_buckets(eng, z_p, lengths, max_buckets=3, overhead=50)
+    assert len(plan[0]) == 3 and flat.numel() == sum(b * 256 * T for _, T, _, _, b in plan[0]) < full.numel()
+    offs = offs.tolist()
+    for i, n in enumerate(lengths):
+        m = (n - 24) * 256
+        got = flat[offs[i]: offs[i] + n * 256]
+        assert torch.allclose(got[:m], full[i, 0, :m], atol=1e-5), i
+    flat2, _, _ = decode_in_buckets(eng, z_p, lengths, plan=plan, out=torch.zeros_like(flat))
+    assert torch.equal(flat, flat2)
+    eng.close()
