@@ -218,8 +218,9 @@ def _emit(line, fd):
 # ------------------------------------------------------------------------------------------------
 # BASELINE configs 3 and 5 (extras): sharded batches + the final NCCL waveform gather
 # ------------------------------------------------------------------------------------------------
-def _timed(torch, dist, dev, fn, steps, warmup=1):
-    """CUDA-event time of `steps` calls of fn, barrier + synchronize on both sides, max over ranks -> ms per call."""
+def _timed(torch, dist, dev, fn, steps, warmup=1, per_step=None):
+    """CUDA-event time of `steps` calls of fn, barrier + synchronize on both sides, max over ranks -> ms per call.
+    per_step: a list that receives this rank's event time of every timed call (diagnostic)."""
     def barrier():
         if dist is not None:
             dist.barrier()
@@ -227,19 +228,21 @@ def _timed(torch, dist, dev, fn, steps, warmup=1):
     for _ in range(warmup):
         fn()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
         fn()
-    e1.record()
+        ev[i + 1].record()
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if per_step is not None:
+        per_step.extend(round(ev[i].elapsed_time(ev[i + 1]), 3) for i in range(steps))
+    t = torch.tensor([ev[0].elapsed_time(ev[steps])], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item()) / steps
 
 
-def run_sharded_config(torch, dist, dev, rank, world, which, steps=3):
+def run_sharded_config(torch, dist, dev, rank, world, which, steps=5):
     """config 3: ljs_ms_istft_vits, B = 256 utterances x T = 862 in total, strong-scaled (256 / N per GPU).
     config 5: uudb_ms_istft_vits_ms (g-conditioned MS decoder, 16 kHz), 64 utterances per GPU in total with lengths uniform
     in [1, 60] s (seed 1234), length-balanced over the ranks (sharding.balance_utterances), every rank decoding its bin
@@ -290,7 +293,11 @@ def run_sharded_config(torch, dist, dev, rank, world, which, steps=3):
     out.update({"utterances": total, "valid_samples": valid, "this_rank": {"utterances": b, "T_padded": T},
                 "ms_per_step_compute": ms_c, "samples_per_s_compute": valid / (ms_c * 1e-3)})
     if dist is not None:
-        ms_g = _timed(torch, dist, dev, compute_gather, steps)
+        # 3 warm-up calls: rank 0 allocates a receive buffer per call while the previous result is still referenced, so the
+        # caching allocator reaches its steady state (two alternating blocks, no cudaMalloc) only after two calls
+        ps = []
+        ms_g = _timed(torch, dist, dev, compute_gather, steps, warmup=3, per_step=ps)
+        out["per_step_ms_with_gather_this_rank"] = ps
         out.update({"ms_per_step_with_gather": ms_g, "samples_per_s_with_gather": valid / (ms_g * 1e-3),
                     "gather_ms": ms_g - ms_c, "gather_bytes": valid * 4,
                     "gather": "sharding.gather_waveforms: 1 all_gather of the placement table + grouped NCCL send/recv to rank 0"})
@@ -333,7 +340,9 @@ def run_sharded_config(torch, dist, dev, rank, world, which, steps=3):
                             "padded_frames": sum(bb * TT for _, TT, _, _, bb in plan[0]), "valid_frames": sum(lens_b)},
               "ms_per_step_compute": ms_cb, "samples_per_s_compute": valid / (ms_cb * 1e-3)}
         if dist is not None:
-            ms_gb = _timed(torch, dist, dev, compute_gather_b, steps)
+            psb = []
+            ms_gb = _timed(torch, dist, dev, compute_gather_b, steps, warmup=3, per_step=psb)
+            bk["per_step_ms_with_gather_this_rank"] = psb
             bk.update({"ms_per_step_with_gather": ms_gb, "samples_per_s_with_gather": valid / (ms_gb * 1e-3), "gather_ms": ms_gb - ms_cb})
             if rank == 0:
                 res = state["out_b"]
