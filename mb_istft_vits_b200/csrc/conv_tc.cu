@@ -104,6 +104,7 @@ struct TcRt {  // runtime scalars the kernel needs beyond ConvArgs
   int pair_phase;    // CTA pairs (CL == 2): the pair is two polyphase branches with equal input shift instead of two channel tiles
   int res_off;       // > 0: byte offset of the per-warp residual staging rings (two 2 KB stages per epilogue warp): the 2-byte
                      // residual input of chunk i+1 is fetched by TMA while chunk i is processed (EPI_RES / EPI_RS, RH != 0)
+  int pack2;         // EPI_ACT, 2-byte streams: lane pairs trade halves and store 4-byte channel pairs (MBV_NO_PACK2=1 clears it: A/B only)
   int pdl;           // launch with programmatic stream serialization
   int rotate;        // two channel tiles, even grid: swap which one a CTA takes every round.  With a static round-robin
                      // an even CTA would otherwise ALWAYS get channel tile 0; when the second tile is half padding
@@ -152,6 +153,95 @@ __device__ __forceinline__ void epi_act(const EpiParams& p, int b, int n, int ph
       const float v = y[i] + add;
       MBV_EL(i) op_store1<Op>(dst + i * step, fmaxf(v, v * slope));  // leaky-relu, slope in (0,1]
     }
+  }
+}
+
+// ---- packed 2-byte stores (round 2).  With the channel on the lane a thread stores its channel for 32 time steps, one
+// 2-byte element per instruction: 1024 warp-level stores per 128 x 256 tile and output stream.  Per-tile stamps with the
+// epilogue's stores switched off (profiles/round2_timeline_k3_stage0.txt) show what they cost the MMAs, which fetch their
+// operands through the same L1 / shared-memory data path: a stage-0 k = 3 c1 tile takes 9.87 K cycles with the scalar
+// stores and 7.8 K without any (k = 11: 23.7 K against 22.5 K = exactly 128 cycles per MMA); the TMEM loads cost nothing.
+// Two adjacent channels (lanes 2j, 2j+1) therefore trade halves of their time steps: the even lane keeps steps 0..15 of
+// BOTH channels, the odd lane 16..31, and each stores 16 four-byte words (channel pair): half the store instructions,
+// the same bytes and the same values (the conversions are the scalar path's, element by element): 9.87 K -> 9.44 K cycles
+// per k = 3 tile.  EPI_ACT only: the same exchange in the residual-add epilogue (12 warps, 128 registers) spilled ~80 bytes.
+template <int KIND> __device__ __forceinline__ uint32_t pack2_16(float lo, float hi) {
+  uint32_t d;
+  if constexpr (KIND == 0) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// row0_even: address of (first row of the chunk, channel n & ~1) in a tensor of 2-byte elements; step: row pitch in elements
+template <int KIND, int STEP, bool FULL>
+__device__ __forceinline__ void store_pairs16(void* row0_even, size_t rstep, int nt, int odd, const float* v) {
+  const size_t step = STEP > 0 ? (size_t)STEP : rstep;
+  uint32_t own[8], oth[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t w_lo = pack2_16<KIND>(v[2 * k], v[2 * k + 1]);            // time steps 2k, 2k+1
+    const uint32_t w_hi = pack2_16<KIND>(v[16 + 2 * k], v[16 + 2 * k + 1]);  // time steps 16+2k, 16+2k+1
+    own[k] = odd ? w_hi : w_lo;
+    oth[k] = __shfl_xor_sync(0xffffffffu, odd ? w_lo : w_hi, 1);             // the partner channel's words for MY time steps
+  }
+  const int r0 = odd ? 16 : 0;
+  char* base = reinterpret_cast<char*>(row0_even) + (size_t)r0 * step * 2;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t ev = odd ? oth[k] : own[k], od = odd ? own[k] : oth[k];   // even channel -> low half, odd channel -> high half
+    if (FULL || r0 + 2 * k < nt) *reinterpret_cast<uint32_t*>(base + (size_t)(2 * k) * step * 2) = __byte_perm(ev, od, 0x5410);
+    if (FULL || r0 + 2 * k + 1 < nt) *reinterpret_cast<uint32_t*>(base + (size_t)(2 * k + 1) * step * 2) = __byte_perm(ev, od, 0x7632);
+  }
+}
+
+// epi_act with packed stores: the whole warp is inside the destination's channels (warp-uniform, checked by the caller)
+template <typename Op, int STEP, bool FULL, int RH>
+__device__ __forceinline__ void epi_act_packed(const EpiParams& p, int b, int n, int phase, int t_first, int nt,
+                                               size_t rstep, const float* acc) {
+  static_assert(sizeof(typename Op::T) == 2, "packed stores: 2-byte operand types");
+  constexpr int KIND = (Op::kPrec == 2) ? 0 : 1;
+  const int odd = n & 1;
+  const float bias = p.bias[(size_t)b * p.bias_bs + n];
+  const size_t off_even = ((size_t)b * p.rows_out + (size_t)t_first * p.row_mul + p.row_add + phase) * p.ld + (n - odd);
+  float y[32];
+  if (p.mask) {
+    const float* mp = p.mask + (size_t)b * p.rows_res + t_first;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { y[i] = acc[i] + bias; MBV_EL(i) y[i] *= mp[i]; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) y[i] = acc[i] + bias;
+  }
+  if (p.xout) {
+    if constexpr (RH != 0) {
+      store_pairs16<1, STEP, FULL>(reinterpret_cast<__half*>(p.xout) + off_even, rstep, nt, odd, y);
+    } else {
+      const size_t step = STEP > 0 ? (size_t)STEP : rstep;
+      float* xo = reinterpret_cast<float*>(p.xout) + off_even + odd;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) MBV_EL(i) xo[i * step] = y[i];
+    }
+  }
+  const float slope = p.slope;
+  for (int j = 0; j < p.n_act; ++j) {
+    const float* addp = j == 0 ? p.act_add[0] : (j == 1 ? p.act_add[1] : p.act_add[2]);
+    void* actp = j == 0 ? p.act[0] : (j == 1 ? p.act[1] : p.act[2]);
+    const float add = addp ? addp[(size_t)b * p.act_add_bs + n] : 0.f;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { const float t = y[i] + add; v[i] = fmaxf(t, t * slope); }
+    store_pairs16<KIND, STEP, FULL>(reinterpret_cast<typename Op::T*>(actp) + off_even, rstep, nt, odd, v);
+  }
+}
+
+template <typename Op, int LD, int RH>
+__device__ __forceinline__ void tc_epilogue_act_packed(const EpiParams& p, int b, int n, int phase, int t_first, int nt, const float* acc) {
+  const size_t rstep = (size_t)p.row_mul * p.ld;
+  if (LD > 0 && p.row_mul == 1) {
+    if (nt == 32) epi_act_packed<Op, LD, true, RH>(p, b, n, phase, t_first, nt, rstep, acc);
+    else epi_act_packed<Op, LD, false, RH>(p, b, n, phase, t_first, nt, rstep, acc);
+  } else {
+    if (nt == 32) epi_act_packed<Op, 0, true, RH>(p, b, n, phase, t_first, nt, rstep, acc);
+    else epi_act_packed<Op, 0, false, RH>(p, b, n, phase, t_first, nt, rstep, acc);
   }
 }
 
@@ -796,6 +886,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
               if (i < nt) op_store1<Op>(dst + i * step, acc[i] * sg);
             }
           }
+        } else if (MODE == EPI_ACT && sizeof(T) == 2 && rt.pack2 && t_first < ti.t_lim && ti.nb + 32 <= n_valid) {
+          // (warp-uniform condition: all 32 channels of this warp are stored -> lane pairs may trade halves)
+          if constexpr (MODE == EPI_ACT && sizeof(T) == 2)
+            tc_epilogue_act_packed<Op, LD, RH>(a.epi, ti.b, ti.n, ti.phase, t_first, min(ti.t_lim - t_first, 32), acc);
         } else if (ti.valid && t_first < ti.t_lim) {
           tc_epilogue32<Op, MODE, LD, RH, kStagedRes>(a.epi, ti.b, ti.n, ti.phase, t_first, min(ti.t_lim - t_first, 32), acc, xcur);
         }
@@ -1476,6 +1570,8 @@ cudaError_t launch_conv_tc(int prec, const ConvArgs& a, const TcPlan& p, cudaStr
   }
   TcRt rt;
   rt.pdl = pdl;
+  static const int no_pack2 = getenv("MBV_NO_PACK2") ? atoi(getenv("MBV_NO_PACK2")) : 0;  // A/B measurements only
+  rt.pack2 = no_pack2 ? 0 : 1;
   rt.dbg = (dbg_mode >= 0 && a.epi.mode == dbg_mode) ? dbg : nullptr;
   rt.n_time = p.n_time; rt.slab_rows = p.slab_rows; rt.box_rows = p.box_rows; rt.n_boxes = p.n_boxes;
   rt.slab_stage_bytes = p.slab_stage_bytes; rt.w_stage_bytes = p.w_stage_bytes;
