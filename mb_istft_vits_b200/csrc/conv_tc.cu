@@ -1305,9 +1305,11 @@ const char* tc_make_plan(int prec, const ConvArgs& a, int flags, int num_sms, Tc
   // operand bytes read per MMA and CTA fall from 12 KB to 8 KB -- the single-CTA MMAs are bound by the shared-memory port
   // (operand reads + TMA writes ~ 107 B/clk of 128), see DESIGN.md.  Needs an even number of channel tiles.
   // Measured (profiles/round2_cta_pairs_ab.txt): stage-0 k=11 convs 245 -> 210 us (1295 -> 1520 TFLOP/s), k=7 156 -> 145,
-  // first upsampler 207 -> 180, conv_pre 74 -> 66; the HBM-bound k=3 residual convs get slightly slower (113 -> 125 us:
-  // two CTAs in lock step share one tile's epilogue traffic pattern), so RES epilogues pair up from 5 taps on.
-  static const int res_pair_taps = getenv("MBV_RES_PAIR_TAPS") ? atoi(getenv("MBV_RES_PAIR_TAPS")) : 5;  // A/B measurements only
+  // first upsampler 207 -> 180, conv_pre 74 -> 66.  The k=3 residual convs were slightly slower in pairs when their residual
+  // came by register loads (113 -> 125 us) and stayed single-CTA; with the TMA-staged residual they gain too (re-measured at
+  // the end of round 2, profiles/round2_res_pair_taps_ab.txt: c2 / c1 time ratio 1.21 -> 1.16, the summing conv 1.12 -> 1.02),
+  // so every multi-tap RES epilogue pairs up now (MBV_RES_PAIR_TAPS=5 restores the old split).
+  static const int res_pair_taps = getenv("MBV_RES_PAIR_TAPS") ? atoi(getenv("MBV_RES_PAIR_TAPS")) : 2;  // A/B measurements only
   const bool pair_mode = (a.epi.mode == EPI_ACT && a.taps > 1) || (a.epi.mode == EPI_RES && a.taps >= res_pair_taps);
   // A pair is two channel tiles of one time tile or -- polyphase upsamplers with an odd number of channel tiles -- two
   // branches that read the same input rows (k16 / stride 4: branches (0,1) and (2,3) have the same first input row).
