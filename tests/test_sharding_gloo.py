@@ -133,6 +133,43 @@ def test_shard_decode_gather_world_size_2(tmp_path):
     assert torch.load(os.path.join(str(tmp_path), "ok.pt")) is True
 
 
+def _worker_empty_rank(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # three utterances on two ranks with dst = 1: rank 1 (the consumer) owns one, rank 0 two; then ONE utterance: rank 1 owns nothing
+    ok = True
+    for lengths in ([5, 9, 2], [7]):
+        total = len(lengths)
+        idx = deal_utterances(lengths, world)[rank]
+        offs, off = [], 0
+        for i in idx:
+            offs.append(off)
+            off += lengths[i] + 3          # utterances lie in the flat buffer with gaps, as bucket padding leaves them
+        flat = torch.full((max(off, 1),), -1.0)
+        for i, o in zip(idx, offs):
+            flat[o: o + lengths[i]] = torch.arange(lengths[i], dtype=torch.float32) + 100 * i
+        for mode in ("p2p", "allgather"):
+            out = gather_waveforms(flat, torch.tensor([lengths[i] for i in idx], dtype=torch.int64), idx, total, dst=1, mode=mode,
+                                   offsets=torch.tensor(offs, dtype=torch.int64))
+            if rank == 1:
+                ok &= len(out) == total
+                for i in range(total):
+                    ok &= bool(torch.equal(out[i], torch.arange(lengths[i], dtype=torch.float32) + 100 * i))
+            else:
+                ok &= out is None
+    if rank == 1:
+        torch.save(bool(ok), os.path.join(tmp, "ok_empty.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_with_offsets_an_idle_rank_and_a_non_zero_consumer(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker_empty_rank, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert torch.load(os.path.join(str(tmp_path), "ok_empty.pt")) is True
+
+
 # ---- the same plumbing on hardware: two ranks, two GPUs, NCCL, the CUDA decoder (needs `gpurun --gpus 2`)
 def _nccl_worker(rank, world, port, tmp):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
