@@ -237,3 +237,40 @@ def test_decode_in_length_buckets_matches_one_padded_batch():
     flat2, _, _ = decode_in_buckets(eng, z_p, lengths, plan=plan, out=torch.zeros_like(flat))
     assert torch.equal(flat, flat2)
     eng.close()
+
+
+def test_decode_in_buckets_plan_offsets_and_reuse_without_a_gpu():
+    """Host logic of decode_in_buckets against a recording stand-in engine: every utterance gets a slot of its BUCKET's padded
+    length, slots tile the flat buffer without gaps, masks follow the lengths, the plan is reusable and the largest bucket is
+    reserved first."""
+    calls, reserved = [], []
+
+    class _Rec:
+        spf = 4
+
+        def reserve_workspace(self, b, T):
+            reserved.append((b, T))
+            return 0
+
+        def flow_decode(self, zb, mask, g, want_z=False, out_wav=None):
+            calls.append((tuple(zb.shape), mask.sum(dim=(1, 2)).tolist(), None if g is None else tuple(g.shape)))
+            out_wav.copy_(zb[:, :1, :].repeat_interleave(4, dim=2))   # "waveform" = channel 0 of the masked latent, 4 samples per frame
+
+    lengths = [9, 2, 7, 3, 8, 1]
+    z = torch.arange(6 * 2 * 9, dtype=torch.float32).view(6, 2, 9) + 1.0
+    g = torch.ones(6, 5, 1)
+    flat, offs, plan = decode_in_buckets(_Rec(), z, lengths, g=g, max_buckets=2, overhead=1)
+    steps, numel, _ = plan
+    assert [(b, T) for _, T, _, _, b in steps] == [(3, 9), (3, 3)] and numel == 4 * (3 * 9 + 3 * 3) == flat.numel()
+    assert reserved == [(3, 9), (3, 3)] and [c[0] for c in calls] == [(3, 2, 9), (3, 2, 3)] and calls[0][2] == (3, 5, 1)
+    assert calls[0][1] == [9.0, 8.0, 7.0] and calls[1][1] == [3.0, 2.0, 1.0]
+    offs = offs.tolist()
+    assert sorted(offs) == [0, 36, 72, 108, 120, 132]
+    for i, n in enumerate(lengths):
+        want = z[i, 0, :n].repeat_interleave(4)
+        assert torch.equal(flat[offs[i]: offs[i] + 4 * n], want), i
+    n_calls = len(calls)
+    flat2, offs2, _ = decode_in_buckets(_Rec(), z, lengths, g=g, out=torch.zeros_like(flat), plan=plan)
+    assert torch.equal(flat2, flat) and torch.equal(offs2, torch.tensor(offs)) and len(calls) == n_calls + 2 and len(reserved) == 2
+    with pytest.raises(AssertionError):
+        decode_in_buckets(_Rec(), z, lengths, g=g, out=torch.zeros(8), plan=plan)
